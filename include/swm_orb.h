@@ -1,0 +1,227 @@
+/*
+ * swm_orb.h -- C ABI of the B200-native ORB front-end for SwarmMap (libswm_orb.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch/OpenCV types.  The C++
+ * wrapper classes with the reference's names (swarmmap_b200/host/ORBextractor.h, ORBmatcher.h)
+ * and the Python mirror (swarmmap_b200/orb.py) sit on top of exactly these entry points.
+ * Every function returns 0 (SWM_OK) or a negative SWM_E_* code; nothing calls exit() or throws
+ * across the boundary (the reference exits on CUDA errors, code/src/cuda/Fast_gpu.cu:346-352).
+ * There is no CPU fallback: every compute entry point needs a CUDA device (sm_100a).
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/code/):
+ *   swm_orb_create/destroy      ORBextractor::ORBextractor           src/ORBextractor.cc:340-405
+ *   swm_orb_extract[_batch]     ORBextractor::operator()             src/ORBextractor.cc:746-819
+ *                               (ComputePyramid :821-855, ComputeKeyPointsOctTree :691-744,
+ *                                GpuFast Fast_gpu.cu:284-389, IC_Angle :403-509, GpuOrb Orb_gpu.cu:67-136)
+ *   swm_orb_level_ptr           public mvImagePyramid / mvImagePyramidBorder  include/ORBextractor.h:91-92
+ *   swm_orb_scale_tables        GetScaleFactors() & friends          include/ORBextractor.h:64-86
+ *   swm_hamming_*               ORBmatcher::DescriptorDistance       src/ORBmatcher.cc:1511-1525
+ *   swm_match_init              ORBmatcher::SearchForInitialization  src/ORBmatcher.cc:375-479
+ *   swm_match_window            ORBmatcher::SearchByProjection x4    src/ORBmatcher.cc:44-121,264-373,1223-1354,1356-1473
+ *   swm_match_bow               ORBmatcher::SearchByBoW x2           src/ORBmatcher.cc:150-262,481-597
+ *   swm_grid_build              Frame::AssignFeaturesToGrid/GetFeaturesInArea  src/Frame.cc:277-292,377-442
+ *   swm_db_*                    role of KeyFrameDatabase::DetectLoopCandidates + SearchByBoW(KF,KF) in
+ *                               AgentMediator::CheckOverlapCandidates (src/AgentMediator.cc:140-202), recast as
+ *                               brute-force Hamming top-k over a sharded descriptor database (BASELINE config 5)
+ */
+#ifndef SWM_ORB_H
+#define SWM_ORB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWM_OK 0
+#define SWM_E_INVALID (-1)   /* bad argument */
+#define SWM_E_CUDA (-2)      /* CUDA runtime error; see swm_last_error */
+#define SWM_E_NODEVICE (-3)  /* no CUDA device / wrong architecture: there is no CPU fallback */
+#define SWM_E_CAPACITY (-4)  /* caller buffer or configured batch too small */
+#define SWM_E_STATE (-5)     /* call order violation (e.g. level_ptr before the first extract) */
+
+#define SWM_EDGE_THRESHOLD 19 /* ORBextractor.cc:78 */
+#define SWM_MAX_LEVELS 16
+
+/* Same size (28 B) and field order as cv::KeyPoint, which the reference already memcpy's raw
+ * to and from the device (Fast_gpu.cu:490,507; Orb_gpu.cu:123). */
+typedef struct swm_keypoint {
+  float x, y;      /* pt, in level-0 pixel units (level coords * scale factor, ORBextractor.cc:808-814) */
+  float size;      /* int(31 * scale[level]) (Fast_gpu.cu:462,470) */
+  float angle;     /* degrees in [0,360) (Fast_gpu.cu:451-456) */
+  float response;  /* FAST score */
+  int32_t octave;  /* pyramid level */
+  int32_t class_id; /* -1 */
+} swm_keypoint;
+
+typedef struct swm_orb_cfg {
+  int32_t nfeatures;     /* ORBextractor.nFeatures */
+  float scale_factor;    /* ORBextractor.scaleFactor (1.2) */
+  int32_t nlevels;       /* ORBextractor.nLevels (8) */
+  int32_t ini_th_fast;   /* ORBextractor.iniThFAST (20) */
+  int32_t min_th_fast;   /* ORBextractor.minThFAST (7) */
+  int32_t max_batch;     /* frames per launch the handle is sized for (>=1) */
+  int32_t max_fast_per_level; /* FAST candidate cap per level; 0 -> 10000 (Fast.hpp:30) */
+} swm_orb_cfg;
+
+typedef struct swm_orb swm_orb; /* opaque extractor handle: owns device buffers, streams, tables */
+
+/* ------------------------------------------------------------------ extractor */
+int swm_orb_create(const swm_orb_cfg* cfg, int device, swm_orb** out);
+void swm_orb_destroy(swm_orb* h);
+/* Last error text of this handle (or of the failed create when h == NULL). */
+const char* swm_last_error(const swm_orb* h);
+
+/* One frame, host buffers in and out (the reference's operator() contract).  img: 8-bit gray,
+ * `stride` bytes per row.  kps/desc: caller-owned, room for `cap` keypoints / cap*32 bytes.
+ * *n receives the count.  An empty image (w or h == 0, or img == NULL) returns SWM_OK with *n = 0
+ * (ORBextractor.cc:750-751). */
+int swm_orb_extract(swm_orb* h, const uint8_t* img, int w, int h_px, int stride, swm_keypoint* kps, uint8_t* desc,
+                    int cap, int* n);
+
+/* `batch` frames of identical size, frame f at imgs + f*frame_stride; outputs for frame f at
+ * kps + f*cap, desc + f*cap*32, n[f].  Host buffers (pinned memory recommended). */
+int swm_orb_extract_batch(swm_orb* h, const uint8_t* imgs, int batch, int w, int h_px, int stride,
+                          size_t frame_stride, swm_keypoint* kps, uint8_t* desc, int cap, int32_t* n);
+
+/* Same, all pointers are DEVICE pointers and the work is enqueued on `stream` (a cudaStream_t
+ * passed as void*; NULL = the handle's own stream).  Does not synchronise. */
+int swm_orb_extract_batch_device(swm_orb* h, const uint8_t* d_imgs, int batch, int w, int h_px, int stride,
+                                 size_t frame_stride, swm_keypoint* d_kps, uint8_t* d_desc, int cap, int32_t* d_n,
+                                 void* stream);
+
+/* Device pointer to pyramid level `level` of frame `frame` of the last batch.
+ * which: 0 = un-blurred ROI inside the bordered plane (pointer to pixel (0,0); the 19-px
+ * reflect-101 border lies at negative offsets), 1 = blurred ROI (what mvImagePyramid holds after
+ * the reference's operator()). */
+int swm_orb_level_ptr(swm_orb* h, int frame, int level, int which, const uint8_t** dev, int* w, int* h_px,
+                      int* pitch);
+int swm_orb_scale_tables(const swm_orb* h, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2);
+int swm_orb_level_quotas(const swm_orb* h, int32_t* quotas);
+/* Capacity a caller must provide per frame so no keypoint is ever dropped. */
+int swm_orb_max_keypoints(const swm_orb* h);
+/* Number of kernel launches issued by the last extract call (bench.py's gpu_launches). */
+int swm_orb_last_launches(const swm_orb* h);
+/* Device time of stages of the last *_device/_batch call is measured by the caller with events;
+ * this hook runs only the pyramid+FAST kernels on the last uploaded batch (roofline timing). */
+int swm_orb_run_stage(swm_orb* h, int stage_mask, int batch, void* stream);
+#define SWM_STAGE_PYRAMID 1 /* pyramid + border + FAST score + blur (fused level kernels) */
+#define SWM_STAGE_NMS 2     /* tile retry + non-max suppression */
+#define SWM_STAGE_OCTREE 4
+#define SWM_STAGE_DESCRIBE 8 /* orientation + rBRIEF + output assembly */
+
+/* Parity introspection (host copies of intermediates of frame `frame` of the last batch).
+ * which: 0 = bordered un-blurred plane ((w+38)x(h+38)), 1 = blurred ROI, 2 = FAST score map (w x h). */
+int swm_orb_debug_plane(swm_orb* h, int frame, int level, int which, uint8_t* out, int out_stride);
+/* FAST candidates after tile-retry+NMS (which = 0; ROI coords; order unspecified) or quadtree
+ * selection (which = 1; final list order).  xys: (x, y, score) int32 triples. Returns count or <0. */
+int swm_orb_debug_points(swm_orb* h, int frame, int level, int which, int32_t* xys, int cap);
+
+/* ------------------------------------------------------------------ Hamming primitives */
+/* Single pair on the host side of the ABI is pointless on a GPU; DescriptorDistance is served by
+ * the batched forms.  a: na x 32 bytes, b: nb x 32 bytes (device pointers), out: na x nb uint16. */
+int swm_hamming_matrix_device(const uint8_t* d_a, int na, const uint8_t* d_b, int nb, uint16_t* d_out, void* stream);
+/* Host-buffer convenience (copies in/out). */
+int swm_hamming_matrix(const uint8_t* a, int na, const uint8_t* b, int nb, uint16_t* out, int device);
+/* Element-wise pairs: out[i] = dist(a[i], b[i]). */
+int swm_hamming_pairs(const uint8_t* a, const uint8_t* b, int n, int32_t* out, int device);
+
+/* ------------------------------------------------------------------ matchers (flat POD views) */
+/* One frame's features as the matchers see them (host pointers). */
+typedef struct swm_frame_view {
+  int32_t n;
+  const float* x;         /* mvKeysUn[i].pt.x */
+  const float* y;
+  const int32_t* octave;
+  const float* angle;
+  const uint8_t* desc;    /* n x 32, row-major (mDescriptors) */
+  float min_x, min_y, max_x, max_y; /* Frame::mnMinX.. (Frame.cc:59-60) */
+} swm_frame_view;
+
+#define SWM_GRID_COLS 64 /* FRAME_GRID_COLS, Frame.h:38 */
+#define SWM_GRID_ROWS 48 /* FRAME_GRID_ROWS, Frame.h:37 */
+
+typedef struct swm_matcher swm_matcher; /* opaque: device scratch + stream for matcher calls */
+int swm_matcher_create(int device, swm_matcher** out);
+void swm_matcher_destroy(swm_matcher* m);
+const char* swm_matcher_last_error(const swm_matcher* m);
+
+/* Frame::AssignFeaturesToGrid as CSR: starts has 64*48+1 entries, cell = ix*48+iy; items (n entries
+ * at most) hold keypoint indices in ascending order per cell. */
+int swm_grid_build(swm_matcher* m, const swm_frame_view* f, int32_t* starts, int32_t* items);
+
+/* M1 SearchForInitialization: prev_xy (n1 x 2 floats) is vbPrevMatched, read and updated;
+ * matches12 (n1) receives F2 indices or -1; *nmatches the return value. */
+int swm_match_init(swm_matcher* m, const swm_frame_view* f1, const swm_frame_view* f2, float* prev_xy,
+                   int32_t* matches12, int window, float nnratio, int check_ori, int* nmatches);
+
+/* Generic windowed projection matcher behind the four SearchByProjection overloads.  The C++
+ * wrapper projects each source (MapPoint) and fills one row per source:
+ *   valid[s]      0 = skipped (bad / not in view / outside image ...)
+ *   u,v,radius    window centre and half-size passed to GetFeaturesInArea
+ *   min_level,max_level   its level arguments (-1,-1 disables; Frame.cc:398)
+ *   desc          the source descriptor (MapPoint::GetDescriptor)
+ *   angle         source keypoint angle for the rotation histogram (ignored if !check_ori)
+ *   blocks[s]     1 if, once assigned, the target slot is unavailable to later sources
+ *                 (pMP->Observations()>0 for :67-69/:1291-1293; always 1 for :306,:1413)
+ * tgt_blocked (n2, may be NULL): slots unavailable from the start.
+ * ratio_mode 0: accept best <= th_dist.  ratio_mode 1: additionally reject when best and second
+ * best share a level and best > nnratio*second (:110-113).
+ * assignment (n2, in/out): source index written at accepted slots (later sources overwrite).
+ * With check_ori the rotation histogram prunes assignments made by this call (:1320-1351). */
+typedef struct swm_window_query {
+  int32_t m;
+  const uint8_t* desc;
+  const float* u;
+  const float* v;
+  const float* radius;
+  const int32_t* min_level;
+  const int32_t* max_level;
+  const uint8_t* valid;
+  const float* angle;
+  const uint8_t* blocks;
+} swm_window_query;
+
+int swm_match_window(swm_matcher* m, const swm_frame_view* tgt, const swm_window_query* q,
+                     const uint8_t* tgt_blocked, int th_dist, int ratio_mode, float nnratio, int check_ori,
+                     int32_t* assignment, int* nmatches);
+
+/* DBoW2::FeatureVector as CSR (ascending node ids; ascending feature indices per node). */
+typedef struct swm_featvec {
+  int32_t n_nodes;
+  const uint32_t* node_ids;
+  const int32_t* offsets; /* n_nodes + 1 */
+  const uint32_t* feats;
+} swm_featvec;
+
+/* M4 SearchByBoW.  mode 0: KeyFrame->Frame (:150-262): valid1 = KF feature has a good MapPoint;
+ * matches (n2) = KF feature index per Frame feature or -1.  mode 1: KeyFrame<->KeyFrame
+ * (:481-597): valid1/valid2 per side; matches (n1) = KF2 feature index or -1. */
+int swm_match_bow(swm_matcher* m, const swm_frame_view* f1, const swm_featvec* fv1, const uint8_t* valid1,
+                  const swm_frame_view* f2, const swm_featvec* fv2, const uint8_t* valid2, int mode, float nnratio,
+                  int check_ori, int32_t* matches, int* nmatches);
+
+/* ------------------------------------------------------------------ place-recognition shard (config 5) */
+typedef struct swm_db swm_db; /* one GPU's shard of the keyframe-descriptor database */
+/* desc: ndesc x 32 bytes (host), kf_of_desc optional (NULL -> desc i belongs to kf i / desc_per_kf). */
+int swm_db_create(int device, const uint8_t* desc, int64_t ndesc, int32_t desc_per_kf, int64_t first_kf_id,
+                  swm_db** out);
+int swm_db_create_device(int device, const uint8_t* d_desc, int64_t ndesc, int32_t desc_per_kf,
+                         int64_t first_kf_id, swm_db** out);
+void swm_db_destroy(swm_db* db);
+/* For each of nq query descriptors (device): the k (<=2) nearest database descriptors of this
+ * shard as packed 64-bit keys (dist << 48 | global_desc_index), ascending; ties -> lower index.
+ * d_votes (optional, n_kf of this shard, int32): += 1 for the keyframe owning each query's best
+ * match when best <= th_votes (TH_LOW). */
+int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t* d_topk, int32_t* d_votes,
+                        int th_votes, void* stream);
+int64_t swm_db_size(const swm_db* db);
+
+/* Build id string ("swm_orb <version> sm_100a <date>"). */
+const char* swm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWM_ORB_H */

@@ -1,0 +1,89 @@
+"""Seeded synthetic frames for the BASELINE.json configs.
+
+No dataset is reachable from the build or GPU boxes, so every test and bench input is generated
+here: "EuRoC-shaped" 752x480 and "KITTI-shaped" 1241x376 8-bit frames with enough corner texture
+that level 0 yields a few thousand FAST candidates (below the reference's 10 000 cap, Fast.hpp:30).
+"""
+import numpy as np
+
+try:
+    import cv2
+except ImportError as e:  # pragma: no cover - cv2 ships in the image
+    raise ImportError("swarmmap_b200.synth needs cv2 (present in the build and GPU images)") from e
+
+EUROC = (752, 480)
+KITTI = (1241, 376)
+
+
+def _box_noise(rng, h, w, amp, box):
+    n = rng.uniform(-amp, amp, (h // box + 2, w // box + 2)).astype(np.float32)
+    n = cv2.resize(n, ((w // box + 2) * box, (h // box + 2) * box), interpolation=cv2.INTER_LINEAR)
+    return n[:h, :w]
+
+
+def make_canvas(w, h, seed, n_rect=600, n_tri=300):
+    """Texture canvas: mid-gray + random rectangles/triangles + 3 octaves of noise, lightly blurred."""
+    rng = np.random.default_rng(seed)
+    scale = (w * h) / float(EUROC[0] * EUROC[1])
+    img = np.full((h, w), 110, np.float32)
+    for _ in range(int(n_rect * scale)):
+        x0, y0 = rng.integers(0, w), rng.integers(0, h)
+        sw, sh = rng.integers(6, 91, 2)
+        img[y0:y0 + sh, x0:x0 + sw] = rng.uniform(20, 235)
+    tri = img.copy()
+    for _ in range(int(n_tri * scale)):
+        c = np.array([rng.integers(0, w), rng.integers(0, h)])
+        pts = (c + rng.integers(-45, 46, (3, 2))).astype(np.int32)
+        cv2.fillConvexPoly(tri, pts, float(rng.uniform(20, 235)))
+    img = tri
+    for amp, box in ((24, 16), (12, 8), (6, 4)):
+        img += _box_noise(rng, h, w, amp, box)
+    img = cv2.GaussianBlur(img, (0, 0), 0.8)
+    return img
+
+
+def make_frame(w=EUROC[0], h=EUROC[1], seed=20220404):
+    """One 8-bit frame (config 1: 752x480 seed 20220404)."""
+    rng = np.random.default_rng(seed + 7919)
+    img = make_canvas(w, h, seed)
+    img = img + rng.normal(0, 2.0, img.shape).astype(np.float32)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def make_sequence(n, w=EUROC[0], h=EUROC[1], seed=20220405, return_h=False):
+    """n frames: a larger canvas seen through a slowly moving homography + fresh sensor noise
+    (config 2: 1241x376 seed 20220405; configs 3/4: 752x480 seeds 20220406..)."""
+    rng = np.random.default_rng(seed + 104729)
+    cw, ch = int(w * 1.3) + 32, int(h * 1.4) + 32
+    canvas = make_canvas(cw, ch, seed)
+    frames = np.empty((n, h, w), np.uint8)
+    hs = []
+    tx, ty, ang, sc = (cw - w) / 2.0, (ch - h) / 2.0, 0.0, 1.0
+    for i in range(n):
+        c, s = np.cos(ang) * sc, np.sin(ang) * sc
+        cx, cy = w / 2.0, h / 2.0
+        # frame pixel -> canvas pixel
+        m = np.array([[c, -s, tx + cx - c * cx + s * cy], [s, c, ty + cy - s * cx - c * cy]], np.float64)
+        warped = cv2.warpAffine(canvas, m, (w, h), flags=cv2.INTER_LINEAR | cv2.WARP_INVERSE_MAP,
+                                borderMode=cv2.BORDER_REFLECT_101)
+        warped = warped + rng.normal(0, 2.0, warped.shape).astype(np.float32)
+        frames[i] = np.clip(np.rint(warped), 0, 255).astype(np.uint8)
+        hs.append(m.copy())
+        tx = float(np.clip(tx + rng.uniform(-6, 6), 8, cw - w - 8))
+        ty = float(np.clip(ty + rng.uniform(-6, 6), 8, ch - h - 8))
+        ang += float(np.deg2rad(rng.uniform(-0.3, 0.3)))
+        sc *= float(1 + rng.uniform(-0.002, 0.002))
+    return (frames, hs) if return_h else frames
+
+
+def make_batch(n, w=EUROC[0], h=EUROC[1], seed=20220410):
+    """n independent frames (cheap variant for throughput runs: one canvas, n shifted crops + noise)."""
+    rng = np.random.default_rng(seed + 15485863)
+    cw, ch = w + 256, h + 256
+    canvas = make_canvas(cw, ch, seed)
+    out = np.empty((n, h, w), np.uint8)
+    for i in range(n):
+        ox, oy = rng.integers(0, 257, 2)
+        f = canvas[oy:oy + h, ox:ox + w] + rng.normal(0, 2.0, (h, w)).astype(np.float32)
+        out[i] = np.clip(np.rint(f), 0, 255).astype(np.uint8)
+    return out

@@ -1,0 +1,14 @@
+// host_harness.cpp -- TEST INFRASTRUCTURE.  Compiles the product's host/device-neutral logic
+// (quadtree core) as a serial CPU emulation so its control flow can be checked against the oracle
+// on a box without a GPU.  Nothing here ships in libswm_orb.so.
+#define SWM_OCTREE_HOST 1
+#include "../swarmmap_b200/csrc/octree_core.cuh"
+
+#include <vector>
+
+extern "C" int hh_octree(const uint32_t* pts, int n, int W, int H, int N, uint32_t* out, int out_cap) {
+  static swm::OtState S;
+  std::vector<uint16_t> pnode(n + 1);
+  std::vector<uint8_t> pchild(n + 1);
+  return swm::ot_distribute(S, pts, pnode.data(), pchild.data(), n, W, H, N, out, out_cap);
+}

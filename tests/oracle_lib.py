@@ -1,0 +1,268 @@
+"""ctypes binding of the CPU oracle (oracle/liborb_oracle.so).
+
+TEST INFRASTRUCTURE: imported only by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+legs.  The product package (swarmmap_b200/) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_DIR = os.path.join(os.path.dirname(_HERE), "oracle")
+
+
+class Keypoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32), ("class_id", C.c_int32)]
+
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+FASTPT_DTYPE = np.dtype([("x", "<i2"), ("y", "<i2"), ("score", "<i4")])
+
+
+class Frame(C.Structure):
+    _fields_ = [("n", C.c_int), ("x", C.c_void_p), ("y", C.c_void_p), ("octave", C.c_void_p),
+                ("angle", C.c_void_p), ("desc", C.c_void_p), ("min_x", C.c_float), ("min_y", C.c_float),
+                ("max_x", C.c_float), ("max_y", C.c_float)]
+
+
+class WindowQuery(C.Structure):
+    _fields_ = [("m", C.c_int), ("desc", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
+                ("radius", C.c_void_p), ("min_level", C.c_void_p), ("max_level", C.c_void_p),
+                ("valid", C.c_void_p), ("angle", C.c_void_p), ("blocks", C.c_void_p),
+                ("pred_level", C.c_void_p)]
+
+
+class FeatVec(C.Structure):
+    _fields_ = [("n_nodes", C.c_int), ("node_ids", C.c_void_p), ("offsets", C.c_void_p), ("feats", C.c_void_p)]
+
+
+_lib = None
+
+
+def build(force=False):
+    so = os.path.join(ORACLE_DIR, "liborb_oracle.so")
+    srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".cpp", ".h", ".inc"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["make", "-C", ORACLE_DIR, "liborb_oracle.so"], check=True, capture_output=True)
+    return so
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        vp, ci, cf = C.c_void_p, C.c_int, C.c_float
+        L.orc_scale_tables.argtypes = [cf, ci, vp, vp, vp, vp]
+        L.orc_level_quotas.argtypes = [ci, cf, ci, vp]
+        L.orc_umax.argtypes = [vp]
+        L.orc_level_sizes.argtypes = [ci, ci, cf, ci, vp, vp]
+        L.orc_resize_linear_u8.argtypes = [vp, ci, ci, ci, vp, ci, ci, ci]
+        L.orc_border_reflect101.argtypes = [vp, ci, ci, ci, vp, ci, ci]
+        L.orc_gauss7_u8.argtypes = [vp, ci, ci, ci, vp, ci]
+        L.orc_fast_score_map.argtypes = [vp, ci, ci, ci, ci, vp, ci]
+        L.orc_fast_tile_select.argtypes = [vp, ci, ci, ci, ci, vp, ci, vp]
+        L.orc_fast_tile_select.restype = ci
+        L.orc_octree.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, ci]
+        L.orc_octree.restype = ci
+        L.orc_ic_angle.argtypes = [vp, ci, ci, ci]
+        L.orc_ic_angle.restype = cf
+        L.orc_ic_moments.argtypes = [vp, ci, ci, ci, vp, vp]
+        L.orc_rbrief.argtypes = [vp, ci, ci, ci, cf, vp]
+        L.orc_hamming256.argtypes = [vp, vp]
+        L.orc_hamming256.restype = ci
+        L.orc_extractor_create.argtypes = [ci, cf, ci, ci, ci]
+        L.orc_extractor_create.restype = vp
+        L.orc_extractor_destroy.argtypes = [vp]
+        L.orc_extract.argtypes = [vp, vp, ci, ci, ci, vp, vp, ci]
+        L.orc_extract.restype = ci
+        L.orc_extractor_level.argtypes = [vp, ci, ci, vp, vp, vp, vp]
+        L.orc_extractor_level.restype = ci
+        L.orc_extractor_level_fast.argtypes = [vp, ci, vp]
+        L.orc_extractor_level_fast.restype = ci
+        L.orc_extractor_level_selected.argtypes = [vp, ci, vp]
+        L.orc_extractor_level_selected.restype = ci
+        L.orc_time_extract.argtypes = [vp, vp, ci, ci, ci, ci]
+        L.orc_time_extract.restype = C.c_double
+        L.orc_grid_build.argtypes = [vp]
+        L.orc_grid_build.restype = vp
+        L.orc_grid_destroy.argtypes = [vp]
+        L.orc_grid_csr.argtypes = [vp, vp, vp]
+        L.orc_grid_query.argtypes = [vp, vp, cf, cf, cf, ci, ci, vp, ci]
+        L.orc_grid_query.restype = ci
+        L.orc_search_for_initialization.argtypes = [vp, vp, vp, vp, ci, cf, ci]
+        L.orc_search_for_initialization.restype = ci
+        L.orc_match_window.argtypes = [vp, vp, vp, ci, ci, cf, ci, vp]
+        L.orc_match_window.restype = ci
+        L.orc_search_by_bow.argtypes = [vp, vp, vp, vp, vp, vp, ci, cf, ci, vp]
+        L.orc_search_by_bow.restype = ci
+        L.orc_bruteforce_top2.argtypes = [vp, ci, vp, C.c_int64, vp]
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ---- numpy-friendly wrappers ---------------------------------------------------------------------
+
+def scale_tables(scale_factor=1.2, nlevels=8):
+    out = [np.zeros(nlevels, np.float32) for _ in range(4)]
+    lib().orc_scale_tables(scale_factor, nlevels, *[_p(o) for o in out])
+    return out
+
+
+def level_quotas(nfeatures, scale_factor=1.2, nlevels=8):
+    q = np.zeros(nlevels, np.int32)
+    lib().orc_level_quotas(nfeatures, scale_factor, nlevels, _p(q))
+    return q
+
+
+def umax():
+    u = np.zeros(16, np.int32)
+    lib().orc_umax(_p(u))
+    return u
+
+
+def level_sizes(w, h, scale_factor=1.2, nlevels=8):
+    ws, hs = np.zeros(nlevels, np.int32), np.zeros(nlevels, np.int32)
+    lib().orc_level_sizes(w, h, scale_factor, nlevels, _p(ws), _p(hs))
+    return ws, hs
+
+
+def resize_linear(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), dw, dh, dw)
+    return dst
+
+
+def border_reflect101(src, border=19):
+    src = np.ascontiguousarray(src, np.uint8)
+    h, w = src.shape
+    dst = np.empty((h + 2 * border, w + 2 * border), np.uint8)
+    lib().orc_border_reflect101(_p(src), w, h, w, _p(dst), w + 2 * border, border)
+    return dst
+
+
+def gauss7(src):
+    src = np.ascontiguousarray(src, np.uint8)
+    dst = np.empty_like(src)
+    lib().orc_gauss7_u8(_p(src), src.shape[1], src.shape[0], src.shape[1], _p(dst), src.shape[1])
+    return dst
+
+
+def fast_score_map(img, min_th=7):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros_like(img)
+    lib().orc_fast_score_map(_p(img), img.shape[1], img.shape[0], img.shape[1], min_th, _p(out), img.shape[1])
+    return out
+
+
+def fast_tile_select(score, ini_th=20, cap=10000, want_retry=False):
+    score = np.ascontiguousarray(score, np.uint8)
+    h, w = score.shape
+    out = np.zeros(cap, FASTPT_DTYPE)
+    retry = np.zeros(((h + 31) // 32, (w + 31) // 32), np.uint8)
+    n = lib().orc_fast_tile_select(_p(score), w, h, w, ini_th, _p(out), cap, _p(retry))
+    return (out[:n], retry) if want_retry else out[:n]
+
+
+def octree(pts, min_x, max_x, min_y, max_y, target):
+    pts = np.ascontiguousarray(pts, FASTPT_DTYPE)
+    out = np.zeros(len(pts) + 16, FASTPT_DTYPE)
+    n = lib().orc_octree(_p(pts), len(pts), min_x, max_x, min_y, max_y, target, _p(out), len(out))
+    return out[:n]
+
+
+def ic_angle(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    return float(lib().orc_ic_angle(_p(img), img.shape[1], int(x), int(y)))
+
+
+def ic_moments(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    a, b = C.c_int(), C.c_int()
+    lib().orc_ic_moments(_p(img), img.shape[1], int(x), int(y), C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def rbrief(img, x, y, angle_deg):
+    img = np.ascontiguousarray(img, np.uint8)
+    d = np.zeros(32, np.uint8)
+    lib().orc_rbrief(_p(img), img.shape[1], int(x), int(y), float(angle_deg), _p(d))
+    return d
+
+
+def hamming256(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return int(lib().orc_hamming256(_p(a), _p(b)))
+
+
+class Extractor:
+    """CPU oracle of ORBextractor (reference ORBextractor.cc:340-855)."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self.h = lib().orc_extractor_create(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        if not self.h:
+            raise ValueError("bad extractor parameters")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_extractor_destroy(self.h)
+            self.h = None
+
+    def __call__(self, img):
+        img = np.ascontiguousarray(img, np.uint8)
+        cap = 4 * self.nfeatures + 64
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = lib().orc_extract(self.h, _p(img), img.shape[1], img.shape[0], img.shape[1], _p(kps), _p(desc), cap)
+        if n < 0:
+            raise ValueError("orc_extract failed")
+        return kps[:n].copy(), desc[:n].copy()
+
+    def level(self, level, which):
+        data, w, h, s = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+        rc = lib().orc_extractor_level(self.h, level, which, C.byref(data), C.byref(w), C.byref(h), C.byref(s))
+        assert rc == 0
+        buf = (C.c_uint8 * (s.value * h.value)).from_address(data.value)
+        return np.frombuffer(buf, np.uint8).reshape(h.value, s.value)[:, :w.value].copy()
+
+    def _pts(self, fn, level):
+        p = C.c_void_p()
+        n = fn(self.h, level, C.byref(p))
+        assert n >= 0
+        if n == 0:
+            return np.zeros(0, FASTPT_DTYPE)
+        buf = (C.c_uint8 * (n * FASTPT_DTYPE.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, FASTPT_DTYPE).copy()
+
+    def level_fast(self, level):
+        return self._pts(lib().orc_extractor_level_fast, level)
+
+    def level_selected(self, level):
+        return self._pts(lib().orc_extractor_level_selected, level)
+
+    def time(self, imgs, iters):
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        n, h, w = imgs.shape
+        return lib().orc_time_extract(self.h, _p(imgs), n, w, h, iters)
+
+
+def make_frame(x, y, octave, angle, desc, bounds):
+    """Returns (Frame struct, keepalive tuple)."""
+    x = np.ascontiguousarray(x, np.float32)
+    y = np.ascontiguousarray(y, np.float32)
+    octave = np.ascontiguousarray(octave, np.int32)
+    angle = np.ascontiguousarray(angle, np.float32)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    f = Frame(len(x), _p(x).value, _p(y).value, _p(octave).value, _p(angle).value, _p(desc).value,
+              *[float(b) for b in bounds])
+    return f, (x, y, octave, angle, desc)
