@@ -1,0 +1,332 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200-native ORB front-end (BASELINE.json metric).
+
+A "step" is one pass of extract+describe (ORBextractor::operator(), 8 levels, scale 1.2, FAST 20/7,
+1000 features) over one batch of synthetic 752x480 EuRoC-shaped frames on every rank's own GPU
+(one agent stream set per GPU, no data-path collective: the path shards by agent -> "weak" scaling).
+
+  value      frames/s, whole job, inputs and outputs resident in HBM (CUDA events on the launching stream)
+  e2e        frames/s through the public host-buffer API (pinned host frames in, keypoints +
+             descriptors out, H2D/D2H inside the timed region, two handles double-buffering)
+  roofline   pyramid+FAST kernels (fused level kernels + NMS), algorithmic bytes / live event time
+  cpu_baseline  the CPU oracle (port of the reference path) on this box's host cores, bounded sample
+
+`--impl reference` times the reference path's CPU restatement (oracle/, the reference itself cannot
+be built: SURVEY.md F3) with all host threads on the same workload and prints the same JSON line.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H, NFEAT = 752, 480, 1000
+PYR_FAST_BYTES = 3912047   # pyramid R+W + FAST R per 752x480 frame
+BLUR_BYTES = 2234734       # blur R+W per frame (fused into the same kernels)
+METRIC = "orb_extract_frames_per_sec"
+UNIT = "frames/s"
+WORKLOAD = "EuRoC-shaped 752x480 8-bit frames, ORBextractor(1000, 1.2, 8, 20, 7), extract+describe"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_rate(frames, seconds_budget, threads):
+    """frames/s of the CPU oracle on `threads` host threads over a bounded sample."""
+    import oracle_lib
+    from concurrent.futures import ThreadPoolExecutor
+    ex = [oracle_lib.Extractor(NFEAT, 1.2, 8, 20, 7) for _ in range(threads)]
+    t0 = time.perf_counter()
+    ex[0].time(frames[:1], 1)
+    per = max(time.perf_counter() - t0, 1e-3)
+    iters = max(2, min(200, int(seconds_budget / per)))
+
+    def run(i):
+        return ex[i].time(frames[i % len(frames):i % len(frames) + 1], iters)
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as pool:
+        list(pool.map(run, range(threads)))
+    dt = time.perf_counter() - t0
+    return threads * iters / dt, threads * iters
+
+
+def run_reference(args):
+    from swarmmap_b200 import synth
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    frames = synth.make_batch(max(8, threads), W, H, 20220410)
+    for _ in range(max(args.warmup, 1) - 1):
+        cpu_oracle_rate(frames, 0.5, threads)
+    rates, n_total = [], 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, n = cpu_oracle_rate(frames, 4.0, threads)
+        rates.append(r)
+        n_total += n
+    dt = time.perf_counter() - t0
+    value = statistics.median(rates)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frame": [W, H], "nfeatures": NFEAT},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{n_total} frames over {args.steps} steps, oracle -O2, one extractor per thread"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="frames per step per GPU")
+    ap.add_argument("--impl", default="swm", choices=["swm", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "swm" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    from swarmmap_b200 import build, synth
+    build.build()
+    from swarmmap_b200.orb import ORBextractor, KP_DTYPE
+    from swarmmap_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the ORB front-end has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    B = args.batch
+
+    # ---- synthetic input: B distinct frames per rank (one agent stream per GPU)
+    frames = synth.make_batch(B, W, H, 20220410 + rank)
+    ex = ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local_rank, max_batch=B)
+    cap = ex.max_keypoints()
+
+    # ---- device-resident arm
+    d_img = torch.from_numpy(frames).to(dev)
+    d_kps = torch.empty((B, cap, 7), dtype=torch.float32, device=dev)
+    d_desc = torch.empty((B, cap, 32), dtype=torch.uint8, device=dev)
+    d_n = torch.zeros(B, dtype=torch.int32, device=dev)
+    # a dedicated (non-default) torch stream: the kernels are enqueued on it through the C ABI and the
+    # torch.cuda.Events below are recorded on the same stream.
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    sptr = C.c_void_p(stream.cuda_stream)
+    assert sptr.value, "need a non-default stream handle"
+
+    def step_device():
+        ex.extract_batch_device(d_img.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), cap,
+                                d_n.data_ptr(), sptr)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    launches_per_step = ex.last_launches() + 1  # + the counter memset
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    n_kp = int(d_n.sum().item())
+
+    # ---- per-stage device times (events around each stage on the same stream)
+    stage_ms = {}
+    for name, mask in (("pyramid_fast_blur", _lib.STAGE_PYRAMID), ("nms", _lib.STAGE_NMS),
+                       ("octree", _lib.STAGE_OCTREE), ("describe", _lib.STAGE_DESCRIBE)):
+        reps = max(3, min(args.steps, 10))
+        ex.run_stage(mask, B, sptr)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            ex.run_stage(mask, B, sptr)
+        b.record()
+        torch.cuda.synchronize()
+        stage_ms[name] = a.elapsed_time(b) / reps
+
+    # ---- end-to-end arm: pinned host frames in, host keypoints/descriptors out, two handles
+    nslot = 2
+    eb = min(B, 64)
+    exs = [ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local_rank, max_batch=eb) for _ in range(nslot)]
+    h_img = torch.from_numpy(frames).pin_memory()
+    h_np = h_img.numpy()
+    outs = []
+    for _ in range(nslot):
+        k = torch.empty((eb, cap, 7), dtype=torch.float32).pin_memory()
+        d = torch.empty((eb, cap, 32), dtype=torch.uint8).pin_memory()
+        n = torch.zeros(eb, dtype=torch.int32).pin_memory()
+        outs.append((k.numpy().view(KP_DTYPE).reshape(eb, cap), d.numpy(), n.numpy(), (k, d, n)))
+    chunks = [(i, min(eb, B - i)) for i in range(0, B, eb)]
+
+    def step_e2e():
+        total = 0
+        pending = [None] * nslot
+        for ci, (f0, nb) in enumerate(chunks):
+            s = ci % nslot
+            if pending[s] is not None:
+                exs[s].sync()
+                total += int(outs[s][2][:pending[s]].sum())
+            exs[s].extract_batch_async(h_np[f0:f0 + nb], (outs[s][0], outs[s][1], outs[s][2]))
+            pending[s] = nb
+        for s in range(nslot):
+            if pending[s] is not None:
+                exs[s].sync()
+                total += int(outs[s][2][:pending[s]].sum())
+        return total
+
+    for _ in range(args.warmup):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    kp_e2e = 0
+    for _ in range(args.steps):
+        kp_e2e += step_e2e()
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # ---- reduce over ranks (max time), rank 0 prints
+    t = torch.tensor([ms_total, t_e2e * 1e3, stage_ms["pyramid_fast_blur"] + stage_ms["nms"]], dtype=torch.float64,
+                     device=dev)
+    cnt = torch.tensor([float(n_kp)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_total, ms_e2e, ms_pf = [float(x) for x in t.tolist()]
+    frames_total = world * B * args.steps
+    value = frames_total / (ms_total * 1e-3)
+    e2e_value = frames_total / (ms_e2e * 1e-3)
+    peak, peak_src = _peaks()
+    achieved = PYR_FAST_BYTES * B / (ms_pf * 1e-3) / 1e9
+    h2d = B * W * H
+    d2h = B * (cap * (28 + 32) + 4)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        v, n = cpu_oracle_rate(frames[:8], 12.0, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{n} frames of the same workload, single thread, oracle -O2 (reference extractor is single-threaded per agent)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frame": [W, H], "nfeatures": NFEAT, "batch_per_gpu": B,
+                       "agents": world, "cache": "working set per step (frames + 3 plane sets) "
+                       f"{(B * (W * H + 3 * 1.45e6)) / 1e6:.0f} MB > 126 MB L2, no reuse across steps"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": f"pinned host buffers, {nslot} handles x {eb}-frame chunks double-buffered"},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "level_kernel x8 (pyramid+border+FAST score+blur fused) + nms_kernel x2",
+                         "bytes_per_frame": PYR_FAST_BYTES, "ms_per_launch_set": ms_pf,
+                         "frac_counting_fused_blur_bytes": (PYR_FAST_BYTES + BLUR_BYTES) * B / (ms_pf * 1e-3) / 1e9 / peak},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+            "stages_ms_per_step": stage_ms,
+            "keypoints_per_frame": float(cnt.item()) / (world * B),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -85,6 +85,14 @@ int swm_orb_extract(swm_orb* h, const uint8_t* img, int w, int h_px, int stride,
 int swm_orb_extract_batch(swm_orb* h, const uint8_t* imgs, int batch, int w, int h_px, int stride,
                           size_t frame_stride, swm_keypoint* kps, uint8_t* desc, int cap, int32_t* n);
 
+/* Asynchronous form of swm_orb_extract_batch: enqueues the H2D copies, the kernels and the D2H
+ * copies on the handle's stream and returns.  batch <= cfg.max_batch.  Host buffers (pinned, or
+ * the copies serialise) must stay valid until swm_orb_sync(h) returns; results are defined then.
+ * Two handles used alternately overlap one batch's transfers with the other's kernels. */
+int swm_orb_extract_batch_async(swm_orb* h, const uint8_t* imgs, int batch, int w, int h_px, int stride,
+                                size_t frame_stride, swm_keypoint* kps, uint8_t* desc, int cap, int32_t* n);
+int swm_orb_sync(swm_orb* h);
+
 /* Same, all pointers are DEVICE pointers and the work is enqueued on `stream` (a cudaStream_t
  * passed as void*; NULL = the handle's own stream).  Does not synchronise. */
 int swm_orb_extract_batch_device(swm_orb* h, const uint8_t* d_imgs, int batch, int w, int h_px, int stride,

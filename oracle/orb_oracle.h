@@ -119,7 +119,6 @@ typedef struct orc_window_query {
   const uint8_t* valid;
   const float* angle;        /* may be NULL when check_ori == 0 */
   const uint8_t* blocks;     /* 1: once assigned, the target slot is unavailable to later sources */
-  const int32_t* pred_level; /* only used by ratio_mode 1 bookkeeping (unused otherwise, may be NULL) */
 } orc_window_query;
 
 int orc_match_window(const orc_frame* tgt, const orc_window_query* q, const uint8_t* tgt_blocked_init, int th_dist,

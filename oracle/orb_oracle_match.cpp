@@ -1,2 +1,333 @@
-// placeholder, filled in below
+// orb_oracle_match.cpp -- CPU ORACLE for the ORBmatcher path on flat POD inputs.
+// TEST INFRASTRUCTURE ONLY (see orb_oracle.h).  Loop order, greedy state and the threshold /
+// ratio asymmetries of the reference are kept literally; every function cites the reference
+// file:line it restates (paths relative to /root/reference/code/).
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
 #include "orb_oracle.h"
+
+namespace {
+
+constexpr int TH_HIGH = 100;     // ORBmatcher.cc:37
+constexpr int TH_LOW = 50;       // ORBmatcher.cc:38
+constexpr int HISTO_LENGTH = 30; // ORBmatcher.cc:39
+constexpr int GRID_COLS = 64;    // Frame.h:38
+constexpr int GRID_ROWS = 48;    // Frame.h:37
+
+inline int dist256(const uint8_t* a, const uint8_t* b) { return orc_hamming256(a, b); }
+
+// ORBmatcher.cc:1475-1506 (histogram passed by value; strict > so the first bin wins ties)
+void three_maxima(const std::vector<std::vector<int>>& histo, int L, int& ind1, int& ind2, int& ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  for (int i = 0; i < L; i++) {
+    const int s = (int)histo[i].size();
+    if (s > max1) {
+      max3 = max2; max2 = max1; max1 = s;
+      ind3 = ind2; ind2 = ind1; ind1 = i;
+    } else if (s > max2) {
+      max3 = max2; max2 = s;
+      ind3 = ind2; ind2 = i;
+    } else if (s > max3) {
+      max3 = s;
+      ind3 = i;
+    }
+  }
+  if (max2 < 0.1f * (float)max1) {
+    ind2 = -1;
+    ind3 = -1;
+  } else if (max3 < 0.1f * (float)max1) {
+    ind3 = -1;
+  }
+}
+
+// The rotation-histogram bin, inlined six times in the reference (e.g. ORBmatcher.cc:218-227):
+// factor = 1.0f/HISTO_LENGTH, so only bins 0..12 are ever hit (upstream quirk, kept).
+inline int rot_bin(float a1, float a2) {
+  const float factor = 1.0f / HISTO_LENGTH;
+  float rot = a1 - a2;
+  if (rot < 0.0) rot += 360.0f;
+  int bin = (int)std::round(rot * factor);
+  if (bin == HISTO_LENGTH) bin = 0;
+  return bin;
+}
+
+}  // namespace
+
+struct orc_grid {
+  std::vector<int32_t> cell[GRID_COLS][GRID_ROWS];
+  float inv_w, inv_h;
+};
+
+extern "C" {
+
+// Frame::AssignFeaturesToGrid (Frame.cc:277-292) + PosInGrid (:432-442, uses round)
+orc_grid* orc_grid_build(const orc_frame* f) {
+  orc_grid* g = new orc_grid;
+  g->inv_w = (float)GRID_COLS / (float)(f->max_x - f->min_x);  // Frame.cc:259-260
+  g->inv_h = (float)GRID_ROWS / (float)(f->max_y - f->min_y);
+  for (int i = 0; i < f->n; i++) {
+    const int px = (int)std::round((f->x[i] - f->min_x) * g->inv_w);
+    const int py = (int)std::round((f->y[i] - f->min_y) * g->inv_h);
+    if (px < 0 || px >= GRID_COLS || py < 0 || py >= GRID_ROWS) continue;
+    g->cell[px][py].push_back(i);
+  }
+  return g;
+}
+
+void orc_grid_destroy(orc_grid* g) { delete g; }
+
+void orc_grid_csr(const orc_grid* g, int32_t* starts, int32_t* items) {
+  int k = 0;
+  for (int ix = 0; ix < GRID_COLS; ix++)
+    for (int iy = 0; iy < GRID_ROWS; iy++) {
+      starts[ix * GRID_ROWS + iy] = k;
+      for (int32_t v : g->cell[ix][iy]) items[k++] = v;
+    }
+  starts[GRID_COLS * GRID_ROWS] = k;
+}
+
+// Frame::GetFeaturesInArea (Frame.cc:377-430); result order = for ix, for iy, for j in cell.
+static void features_in_area(const orc_grid* g, const orc_frame* f, float x, float y, float r, int min_level,
+                             int max_level, std::vector<int32_t>& out) {
+  out.clear();
+  const int min_cx = std::max(0, (int)std::floor((x - f->min_x - r) * g->inv_w));
+  if (min_cx >= GRID_COLS) return;
+  const int max_cx = std::min(GRID_COLS - 1, (int)std::ceil((x - f->min_x + r) * g->inv_w));
+  if (max_cx < 0) return;
+  const int min_cy = std::max(0, (int)std::floor((y - f->min_y - r) * g->inv_h));
+  if (min_cy >= GRID_ROWS) return;
+  const int max_cy = std::min(GRID_ROWS - 1, (int)std::ceil((y - f->min_y + r) * g->inv_h));
+  if (max_cy < 0) return;
+  const bool check_levels = (min_level > 0) || (max_level >= 0);
+  for (int ix = min_cx; ix <= max_cx; ix++)
+    for (int iy = min_cy; iy <= max_cy; iy++)
+      for (int32_t j : g->cell[ix][iy]) {
+        if (check_levels) {
+          if (f->octave[j] < min_level) continue;
+          if (max_level >= 0 && f->octave[j] > max_level) continue;
+        }
+        const float dx = f->x[j] - x, dy = f->y[j] - y;
+        if (std::fabs(dx) < r && std::fabs(dy) < r) out.push_back(j);
+      }
+}
+
+int orc_grid_query(const orc_grid* g, const orc_frame* f, float x, float y, float r, int min_level, int max_level,
+                   int32_t* out, int cap) {
+  std::vector<int32_t> v;
+  features_in_area(g, f, x, y, r, min_level, max_level, v);
+  const int n = std::min((int)v.size(), cap);
+  std::memcpy(out, v.data(), (size_t)n * sizeof(int32_t));
+  return (int)v.size();
+}
+
+// ORBmatcher::SearchForInitialization, ORBmatcher.cc:375-479
+int orc_search_for_initialization(const orc_frame* f1, const orc_frame* f2, float* prev_xy, int32_t* matches12,
+                                  int window, float nnratio, int check_ori) {
+  int nmatches = 0;
+  for (int i = 0; i < f1->n; i++) matches12[i] = -1;
+  std::vector<std::vector<int>> rot_hist(HISTO_LENGTH);
+  std::vector<int> matched_dist(f2->n, INT_MAX), matches21(f2->n, -1);
+  orc_grid* g2 = orc_grid_build(f2);
+  std::vector<int32_t> cand;
+  for (int i1 = 0; i1 < f1->n; i1++) {
+    const int level1 = f1->octave[i1];
+    if (level1 > 0) continue;
+    features_in_area(g2, f2, prev_xy[2 * i1], prev_xy[2 * i1 + 1], (float)window, level1, level1, cand);
+    if (cand.empty()) continue;
+    const uint8_t* d1 = f1->desc + (size_t)i1 * 32;
+    int best = INT_MAX, best2 = INT_MAX, best_idx2 = -1;
+    for (int32_t i2 : cand) {
+      const int dist = dist256(d1, f2->desc + (size_t)i2 * 32);
+      if (matched_dist[i2] <= dist) continue;
+      if (dist < best) {
+        best2 = best;
+        best = dist;
+        best_idx2 = i2;
+      } else if (dist < best2) {
+        best2 = dist;
+      }
+    }
+    if (best <= TH_LOW) {
+      if (best < (float)best2 * nnratio) {
+        if (matches21[best_idx2] >= 0) {
+          matches12[matches21[best_idx2]] = -1;
+          nmatches--;
+        }
+        matches12[i1] = best_idx2;
+        matches21[best_idx2] = i1;
+        matched_dist[best_idx2] = best;
+        nmatches++;
+        if (check_ori) rot_hist[rot_bin(f1->angle[i1], f2->angle[best_idx2])].push_back(i1);
+      }
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rot_hist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rot_hist[i])
+        if (matches12[idx1] >= 0) {
+          matches12[idx1] = -1;
+          nmatches--;
+        }
+    }
+  }
+  for (int i1 = 0; i1 < f1->n; i1++)
+    if (matches12[i1] >= 0) {
+      prev_xy[2 * i1] = f2->x[matches12[i1]];
+      prev_xy[2 * i1 + 1] = f2->y[matches12[i1]];
+    }
+  orc_grid_destroy(g2);
+  return nmatches;
+}
+
+// Generic windowed projection matcher.  One loop body covers
+//   SearchByProjection(Frame&, vector<MapPoint*>&, th)            ORBmatcher.cc:44-121   (ratio_mode 1, TH_HIGH)
+//   SearchByProjection(KeyFrame*, Scw, points, matched, th)       ORBmatcher.cc:264-373  (ratio_mode 0, TH_LOW)
+//   SearchByProjection(Frame& cur, const Frame& last, th, mono)   ORBmatcher.cc:1223-1354 (ratio_mode 0, TH_HIGH, ori)
+//   SearchByProjection(Frame&, KeyFrame*, found, th, ORBdist)     ORBmatcher.cc:1356-1473 (ratio_mode 0, ORBdist, ori)
+// after the caller has projected every source point (see include/swm_orb.h swm_match_window).
+int orc_match_window(const orc_frame* tgt, const orc_window_query* q, const uint8_t* tgt_blocked_init, int th_dist,
+                     int ratio_mode, float nnratio, int check_ori, int32_t* assignment) {
+  int nmatches = 0;
+  std::vector<uint8_t> blocked(tgt->n, 0);
+  if (tgt_blocked_init) std::memcpy(blocked.data(), tgt_blocked_init, tgt->n);
+  std::vector<std::vector<int>> rot_hist(HISTO_LENGTH);
+  orc_grid* g = orc_grid_build(tgt);
+  std::vector<int32_t> cand;
+  for (int s = 0; s < q->m; s++) {
+    if (!q->valid[s]) continue;
+    features_in_area(g, tgt, q->u[s], q->v[s], q->radius[s], q->min_level[s], q->max_level[s], cand);
+    if (cand.empty()) continue;
+    const uint8_t* d = q->desc + (size_t)s * 32;
+    int best = 256, best2 = 256, best_level = -1, best_level2 = -1, best_idx = -1;
+    for (int32_t i2 : cand) {
+      if (blocked[i2]) continue;  // :67-69 / :306 / :1291-1293 / :1413
+      const int dist = dist256(d, tgt->desc + (size_t)i2 * 32);
+      if (dist < best) {
+        best2 = best;
+        best = dist;
+        best_level2 = best_level;
+        best_level = tgt->octave[i2];
+        best_idx = i2;
+      } else if (dist < best2) {
+        best_level2 = tgt->octave[i2];
+        best2 = dist;
+      }
+    }
+    if (best <= th_dist) {
+      if (ratio_mode == 1 && best_level == best_level2 && best > nnratio * best2) continue;  // :110-113
+      assignment[best_idx] = s;
+      if (q->blocks[s]) blocked[best_idx] = 1;
+      nmatches++;
+      if (check_ori) rot_hist[rot_bin(q->angle[s], tgt->angle[best_idx])].push_back(best_idx);
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rot_hist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i != ind1 && i != ind2 && i != ind3) {
+        for (int idx : rot_hist[i]) {
+          assignment[idx] = -1;
+          nmatches--;
+        }
+      }
+    }
+  }
+  orc_grid_destroy(g);
+  return nmatches;
+}
+
+// ORBmatcher::SearchByBoW: mode 0 KeyFrame->Frame (:150-262), mode 1 KeyFrame<->KeyFrame (:481-597)
+int orc_search_by_bow(const orc_frame* f1, const orc_featvec* fv1, const uint8_t* valid1, const orc_frame* f2,
+                      const orc_featvec* fv2, const uint8_t* valid2, int mode, float nnratio, int check_ori,
+                      int32_t* matches) {
+  int nmatches = 0;
+  const int n_out = mode == 0 ? f2->n : f1->n;
+  for (int i = 0; i < n_out; i++) matches[i] = -1;
+  std::vector<uint8_t> taken2(f2->n, 0);  // mode 0: vpMapPointMatches[idxF] != NULL ; mode 1: vbMatched2
+  std::vector<std::vector<int>> rot_hist(HISTO_LENGTH);
+  int a = 0, b = 0;
+  while (a < fv1->n_nodes && b < fv2->n_nodes) {
+    if (fv1->node_ids[a] == fv2->node_ids[b]) {
+      for (int i1 = fv1->offsets[a]; i1 < fv1->offsets[a + 1]; i1++) {
+        const uint32_t idx1 = fv1->feats[i1];
+        if (!valid1[idx1]) continue;  // !pMP || pMP->isBad()
+        const uint8_t* d1 = f1->desc + (size_t)idx1 * 32;
+        int best1 = 256, best_idx2 = -1, best2 = 256;
+        for (int i2 = fv2->offsets[b]; i2 < fv2->offsets[b + 1]; i2++) {
+          const uint32_t idx2 = fv2->feats[i2];
+          if (taken2[idx2]) continue;
+          if (mode == 1 && !valid2[idx2]) continue;
+          const int dist = dist256(d1, f2->desc + (size_t)idx2 * 32);
+          if (dist < best1) {
+            best2 = best1;
+            best1 = dist;
+            best_idx2 = (int)idx2;
+          } else if (dist < best2) {
+            best2 = dist;
+          }
+        }
+        const bool pass = mode == 0 ? (best1 <= TH_LOW) : (best1 < TH_LOW);  // :212 vs :550
+        if (pass && (float)best1 < nnratio * (float)best2) {
+          taken2[best_idx2] = 1;
+          if (mode == 0) {
+            matches[best_idx2] = (int32_t)idx1;
+            if (check_ori) rot_hist[rot_bin(f1->angle[idx1], f2->angle[best_idx2])].push_back(best_idx2);
+          } else {
+            matches[idx1] = best_idx2;
+            if (check_ori) rot_hist[rot_bin(f1->angle[idx1], f2->angle[best_idx2])].push_back((int)idx1);
+          }
+          nmatches++;
+        }
+      }
+      a++;
+      b++;
+    } else if (fv1->node_ids[a] < fv2->node_ids[b]) {
+      a = (int)(std::lower_bound(fv1->node_ids, fv1->node_ids + fv1->n_nodes, fv2->node_ids[b]) - fv1->node_ids);
+    } else {
+      b = (int)(std::lower_bound(fv2->node_ids, fv2->node_ids + fv2->n_nodes, fv1->node_ids[a]) - fv2->node_ids);
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rot_hist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx : rot_hist[i]) {
+        matches[idx] = -1;
+        nmatches--;
+      }
+    }
+  }
+  return nmatches;
+}
+
+// Brute-force top-2 (config 5): ties broken by the lower database index.
+void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int32_t* out4) {
+  for (int i = 0; i < nq; i++) {
+    int d0 = 257, d1 = 257;
+    int64_t i0 = -1, i1 = -1;
+    for (int64_t j = 0; j < ndb; j++) {
+      const int d = dist256(q + (size_t)i * 32, db + (size_t)j * 32);
+      if (d < d0) {
+        d1 = d0; i1 = i0;
+        d0 = d; i0 = j;
+      } else if (d < d1) {
+        d1 = d; i1 = j;
+      }
+    }
+    out4[4 * i] = d0;
+    out4[4 * i + 1] = (int32_t)i0;
+    out4[4 * i + 2] = d1;
+    out4[4 * i + 3] = (int32_t)i1;
+  }
+}
+
+}  // extern "C"

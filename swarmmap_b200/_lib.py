@@ -1,0 +1,114 @@
+"""ctypes binding of libswm_orb.so (the C ABI declared in include/swm_orb.h).
+
+There is deliberately no fallback: if the shared library is missing, or no sm_100 device is
+present, the calls raise.  Nothing in this package imports the CPU oracle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libswm_orb.so")
+
+SWM_OK = 0
+ERRORS = {-1: "SWM_E_INVALID", -2: "SWM_E_CUDA", -3: "SWM_E_NODEVICE", -4: "SWM_E_CAPACITY", -5: "SWM_E_STATE"}
+
+STAGE_PYRAMID, STAGE_NMS, STAGE_OCTREE, STAGE_DESCRIBE = 1, 2, 4, 8
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+assert KP_DTYPE.itemsize == 28
+
+
+class SwmError(RuntimeError):
+    pass
+
+
+class OrbCfg(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("max_batch", C.c_int32),
+                ("max_fast_per_level", C.c_int32)]
+
+
+class FrameView(C.Structure):
+    _fields_ = [("n", C.c_int32), ("x", C.c_void_p), ("y", C.c_void_p), ("octave", C.c_void_p),
+                ("angle", C.c_void_p), ("desc", C.c_void_p), ("min_x", C.c_float), ("min_y", C.c_float),
+                ("max_x", C.c_float), ("max_y", C.c_float)]
+
+
+class WindowQuery(C.Structure):
+    _fields_ = [("m", C.c_int32), ("desc", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
+                ("radius", C.c_void_p), ("min_level", C.c_void_p), ("max_level", C.c_void_p),
+                ("valid", C.c_void_p), ("angle", C.c_void_p), ("blocks", C.c_void_p)]
+
+
+class FeatVec(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("node_ids", C.c_void_p), ("offsets", C.c_void_p), ("feats", C.c_void_p)]
+
+
+# every symbol include/swm_orb.h declares: (name, restype, argtypes)
+_vp, _i, _f, _sz, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
+SYMBOLS = [
+    ("swm_version", C.c_char_p, []),
+    ("swm_orb_create", _i, [_vp, _i, _vp]),
+    ("swm_orb_destroy", None, [_vp]),
+    ("swm_last_error", C.c_char_p, [_vp]),
+    ("swm_orb_extract", _i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    ("swm_orb_extract_batch", _i, [_vp, _vp, _i, _i, _i, _i, _sz, _vp, _vp, _i, _vp]),
+    ("swm_orb_extract_batch_async", _i, [_vp, _vp, _i, _i, _i, _i, _sz, _vp, _vp, _i, _vp]),
+    ("swm_orb_sync", _i, [_vp]),
+    ("swm_orb_extract_batch_device", _i, [_vp, _vp, _i, _i, _i, _i, _sz, _vp, _vp, _i, _vp, _vp]),
+    ("swm_orb_level_ptr", _i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    ("swm_orb_scale_tables", _i, [_vp, _vp, _vp, _vp, _vp]),
+    ("swm_orb_level_quotas", _i, [_vp, _vp]),
+    ("swm_orb_max_keypoints", _i, [_vp]),
+    ("swm_orb_last_launches", _i, [_vp]),
+    ("swm_orb_run_stage", _i, [_vp, _i, _i, _vp]),
+    ("swm_orb_debug_plane", _i, [_vp, _i, _i, _i, _vp, _i]),
+    ("swm_orb_debug_points", _i, [_vp, _i, _i, _i, _vp, _i]),
+    ("swm_hamming_matrix_device", _i, [_vp, _i, _vp, _i, _vp, _vp]),
+    ("swm_hamming_matrix", _i, [_vp, _i, _vp, _i, _vp, _i]),
+    ("swm_hamming_pairs", _i, [_vp, _vp, _i, _vp, _i]),
+    ("swm_matcher_create", _i, [_i, _vp]),
+    ("swm_matcher_destroy", None, [_vp]),
+    ("swm_matcher_last_error", C.c_char_p, [_vp]),
+    ("swm_grid_build", _i, [_vp, _vp, _vp, _vp]),
+    ("swm_match_init", _i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp]),
+    ("swm_match_window", _i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp]),
+    ("swm_match_bow", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp]),
+    ("swm_db_create", _i, [_i, _vp, _i64, C.c_int32, _i64, _vp]),
+    ("swm_db_create_device", _i, [_i, _vp, _i64, C.c_int32, _i64, _vp]),
+    ("swm_db_destroy", None, [_vp]),
+    ("swm_db_query_device", _i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    ("swm_db_size", _i64, [_vp]),
+]
+
+_lib = None
+
+
+def load():
+    """Loads libswm_orb.so; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SwmError(f"{LIB_PATH} is missing: build it with `python -m swarmmap_b200.build` "
+                           "(there is no CPU or PyTorch fallback for the ORB front-end)")
+        lib = C.CDLL(LIB_PATH)
+        for name, res, args in SYMBOLS:
+            fn = getattr(lib, name)  # AttributeError if the ABI is incomplete
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def check(rc, handle=None, what=""):
+    if rc != SWM_OK:
+        lib = load()
+        msg = lib.swm_last_error(handle)
+        raise SwmError(f"{what}: {ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")

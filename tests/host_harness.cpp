@@ -12,3 +12,13 @@ extern "C" int hh_octree(const uint32_t* pts, int n, int W, int H, int N, uint32
   std::vector<uint8_t> pchild(n + 1);
   return swm::ot_distribute(S, pts, pnode.data(), pchild.data(), n, W, H, N, out, out_cap);
 }
+
+#include "../swarmmap_b200/csrc/swm_core.cuh"
+
+// Per-pixel helpers of the level kernel, run serially over an image (same arithmetic as the device).
+extern "C" void hh_fast_score_map(const uint8_t* img, int w, int h, int stride, int th, uint8_t* out) {
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++)
+      out[(size_t)y * w + x] =
+          (x >= 3 && y >= 3 && x < w - 3 && y < h - 3) ? (uint8_t)swm::fast_score(img + (size_t)y * stride + x, stride, th) : 0;
+}

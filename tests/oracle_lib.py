@@ -32,8 +32,7 @@ class Frame(C.Structure):
 class WindowQuery(C.Structure):
     _fields_ = [("m", C.c_int), ("desc", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
                 ("radius", C.c_void_p), ("min_level", C.c_void_p), ("max_level", C.c_void_p),
-                ("valid", C.c_void_p), ("angle", C.c_void_p), ("blocks", C.c_void_p),
-                ("pred_level", C.c_void_p)]
+                ("valid", C.c_void_p), ("angle", C.c_void_p), ("blocks", C.c_void_p)]
 
 
 class FeatVec(C.Structure):

@@ -1,0 +1,136 @@
+"""GPU parity of the extractor against the CPU oracle, stage by stage (run with -m gpu on a B200).
+
+Bar (BASELINE.json north_star): pyramid, FAST keypoint set, quadtree selection bit-exact;
+orientation within 1e-4 rad; >= 99.9 % of descriptor bits identical.
+"""
+import numpy as np
+import pytest
+
+from swarmmap_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_TOL_RAD = 1e-4
+DESC_BIT_FRACTION = 0.999
+
+
+def _extractors(oracle, nfeatures, max_batch=1, **kw):
+    from swarmmap_b200.orb import ORBextractor
+    gpu = ORBextractor(nfeatures, 1.2, 8, 20, 7, max_batch=max_batch, **kw)
+    cpu = oracle.Extractor(nfeatures, 1.2, 8, 20, 7)
+    return gpu, cpu
+
+
+def _check_frame(gpu, cpu, img, frame=0, kd=None):
+    """Compares every intermediate of `frame` of the last GPU batch with the oracle run on img."""
+    okps, odesc = cpu(img)
+    for l in range(8):
+        np.testing.assert_array_equal(gpu.debug_plane(frame, l, 0), cpu.level(l, 0), err_msg=f"bordered plane L{l}")
+        np.testing.assert_array_equal(gpu.debug_plane(frame, l, 2), cpu.level(l, 2), err_msg=f"FAST score map L{l}")
+        np.testing.assert_array_equal(gpu.debug_plane(frame, l, 1), cpu.level(l, 1), err_msg=f"blurred plane L{l}")
+        g = gpu.debug_points(frame, l, 0)
+        o = cpu.level_fast(l)
+        # raster order (y, then x); the reference keeps at most 10 000 per level (Fast.hpp:30)
+        gset = sorted(map(tuple, g.tolist()), key=lambda t: (t[1], t[0]))[:10000]
+        oset = sorted(zip(o["x"].tolist(), o["y"].tolist(), o["score"].tolist()), key=lambda t: (t[1], t[0]))
+        assert gset == oset, f"FAST keypoint set differs at level {l}: {len(gset)} vs {len(oset)}"
+        g = gpu.debug_points(frame, l, 1)
+        o = cpu.level_selected(l)
+        assert g.tolist() == [list(t) for t in zip(o["x"].tolist(), o["y"].tolist(), o["score"].tolist())], \
+            f"quadtree selection (ordered) differs at level {l}"
+    if kd is not None:
+        kps, desc = kd
+        assert len(kps) == len(okps)
+        for fld in ("x", "y", "size", "response", "octave", "class_id"):
+            np.testing.assert_array_equal(kps[fld], okps[fld], err_msg=fld)
+        dang = np.abs(kps["angle"] - okps["angle"])
+        dang = np.minimum(dang, 360.0 - dang)
+        assert np.deg2rad(dang.max()) <= ANGLE_TOL_RAD, f"max angle error {dang.max()} deg"
+        bits = np.unpackbits(desc ^ odesc).sum()
+        frac = 1.0 - bits / float(desc.size * 8)
+        assert frac >= DESC_BIT_FRACTION, f"descriptor bit agreement {frac}"
+    return okps, odesc
+
+
+def test_single_frame_config1(oracle, swm):
+    gpu, cpu = _extractors(oracle, 1000)
+    img = synth.make_frame(752, 480, 20220404)
+    kps, desc = gpu(img)
+    assert 900 <= len(kps) <= gpu.max_keypoints()
+    _check_frame(gpu, cpu, img, 0, (kps, desc))
+    # determinism: same frame again -> identical bytes
+    kps2, desc2 = gpu(img)
+    assert kps.tobytes() == kps2.tobytes() and desc.tobytes() == desc2.tobytes()
+
+
+def test_single_frame_config2_kitti(oracle, swm):
+    for nf in (2000, 4000):
+        gpu, cpu = _extractors(oracle, nf)
+        img = synth.make_frame(1241, 376, 20220405)
+        kps, desc = gpu(img)
+        _check_frame(gpu, cpu, img, 0, (kps, desc))
+
+
+def test_batch_matches_single(oracle, swm):
+    gpu, cpu = _extractors(oracle, 1000, max_batch=4)
+    imgs = synth.make_batch(6, 752, 480, 20220410)  # 6 frames through a batch-4 handle: two chunks
+    kps, desc, n = gpu.extract_batch(imgs)
+    for f in range(6):
+        okps, odesc = cpu(imgs[f])
+        assert n[f] == len(okps)
+        for fld in ("x", "y", "size", "response", "octave"):
+            np.testing.assert_array_equal(kps[f, :n[f]][fld], okps[fld])
+        bits = np.unpackbits(desc[f, :n[f]] ^ odesc).sum()
+        assert 1.0 - bits / float(odesc.size * 8) >= DESC_BIT_FRACTION
+    # intermediates of the last chunk (frames 4,5 sit in slots 0,1)
+    _check_frame(gpu, cpu, imgs[5], 1)
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (333, 257), (200, 150), (1001, 301)])
+def test_odd_sizes(oracle, swm, w, h):
+    gpu, cpu = _extractors(oracle, 500)
+    img = synth.make_frame(w, h, 1234 + w)
+    kps, desc = gpu(img)
+    _check_frame(gpu, cpu, img, 0, (kps, desc))
+
+
+def test_textureless_and_noise(oracle, swm):
+    gpu, cpu = _extractors(oracle, 1000)
+    flat = np.full((480, 752), 128, np.uint8)
+    kps, desc = gpu(flat)
+    assert len(kps) == 0 and desc.shape == (0, 32)
+    # low-contrast frame: exercises the minThFAST tile retry everywhere
+    rng = np.random.default_rng(3)
+    low = (120 + 6 * rng.standard_normal((480, 752))).clip(0, 255).astype(np.uint8)
+    low[100:300, 200:500] = synth.make_frame(752, 480, 5)[100:300, 200:500]
+    kps, desc = gpu(low)
+    _check_frame(gpu, cpu, low, 0, (kps, desc))
+    # white noise: more FAST survivors than the reference's 10 000-entry buffer on level 0
+    noise = rng.integers(0, 256, (480, 752), dtype=np.uint8)
+    kps, desc = gpu(noise)
+    _check_frame(gpu, cpu, noise, 0, (kps, desc))
+
+
+def test_strided_input_and_empty(oracle, swm):
+    gpu, cpu = _extractors(oracle, 1000)
+    big = synth.make_frame(800, 500, 99)
+    view = big[10:490, 20:772]  # non-contiguous rows (stride 800)
+    kps, desc = gpu(view)
+    okps, odesc = cpu(np.ascontiguousarray(view))
+    np.testing.assert_array_equal(kps["x"], okps["x"])
+    np.testing.assert_array_equal(kps["y"], okps["y"])
+    k0, d0 = gpu(np.zeros((0, 0), np.uint8))
+    assert len(k0) == 0
+    with pytest.raises(TypeError):
+        gpu(np.zeros((480, 752), np.float32))
+
+
+def test_scale_tables_and_quotas(oracle, swm):
+    gpu, cpu = _extractors(oracle, 1000)
+    sf, inv, s2, inv2 = oracle.scale_tables(1.2, 8)
+    np.testing.assert_array_equal(gpu.GetScaleFactors(), sf)
+    np.testing.assert_array_equal(gpu.GetInverseScaleFactors(), inv)
+    np.testing.assert_array_equal(gpu.GetScaleSigmaSquares(), s2)
+    np.testing.assert_array_equal(gpu.GetInverseScaleSigmaSquares(), inv2)
+    np.testing.assert_array_equal(gpu.mnFeaturesPerLevel, oracle.level_quotas(1000))
+    assert gpu.GetLevels() == 8 and abs(gpu.GetScaleFactor() - 1.2) < 1e-6
