@@ -1,19 +1,1123 @@
-// match.cu -- TEMPORARY stubs (replaced by the Hamming matchers); every entry point fails loudly.
+// match.cu -- B200 (sm_100a) Hamming matchers behind the ORBmatcher API (include/swm_orb.h).
+//
+// Reference behaviour restated (paths relative to /root/reference/code/):
+//   ORBmatcher::DescriptorDistance        src/ORBmatcher.cc:1511-1525
+//   ORBmatcher::SearchForInitialization   src/ORBmatcher.cc:375-479
+//   ORBmatcher::SearchByProjection x4     src/ORBmatcher.cc:44-121, 264-373, 1223-1354, 1356-1473
+//   ORBmatcher::SearchByBoW x2            src/ORBmatcher.cc:150-262, 481-597
+//   ComputeThreeMaxima                    src/ORBmatcher.cc:1475-1506
+//   Frame grid                            src/Frame.cc:277-292 (AssignFeaturesToGrid), :377-442
+//
+// Structure: every Search* is "for each source in order: enumerate candidates in a fixed order,
+// take best / second best Hamming distance among candidates that are still free, accept under a
+// threshold + ratio rule, mutate the free-state".  The enumeration and all distances are
+// embarrassingly parallel (one warp per source row, LOP3+POPC on the CUDA cores); only the greedy
+// accept/steal state is order dependent, and that is replayed by a single warp over the
+// pre-computed candidate rows (resolve_kernel), which keeps match indices bit-exact.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
 #include "swm_internal.cuh"
-extern "C" {
-int swm_hamming_matrix_device(const uint8_t*, int, const uint8_t*, int, uint16_t*, void*) { return SWM_E_STATE; }
-int swm_hamming_matrix(const uint8_t*, int, const uint8_t*, int, uint16_t*, int) { return SWM_E_STATE; }
-int swm_hamming_pairs(const uint8_t*, const uint8_t*, int, int32_t*, int) { return SWM_E_STATE; }
-int swm_matcher_create(int, swm_matcher**) { return SWM_E_STATE; }
-void swm_matcher_destroy(swm_matcher*) {}
-const char* swm_matcher_last_error(const swm_matcher*) { return "matchers not built yet"; }
-int swm_grid_build(swm_matcher*, const swm_frame_view*, int32_t*, int32_t*) { return SWM_E_STATE; }
-int swm_match_init(swm_matcher*, const swm_frame_view*, const swm_frame_view*, float*, int32_t*, int, float, int, int*) { return SWM_E_STATE; }
-int swm_match_window(swm_matcher*, const swm_frame_view*, const swm_window_query*, const uint8_t*, int, int, float, int, int32_t*, int*) { return SWM_E_STATE; }
-int swm_match_bow(swm_matcher*, const swm_frame_view*, const swm_featvec*, const uint8_t*, const swm_frame_view*, const swm_featvec*, const uint8_t*, int, float, int, int32_t*, int*) { return SWM_E_STATE; }
-int swm_db_create(int, const uint8_t*, int64_t, int32_t, int64_t, swm_db**) { return SWM_E_STATE; }
-int swm_db_create_device(int, const uint8_t*, int64_t, int32_t, int64_t, swm_db**) { return SWM_E_STATE; }
-void swm_db_destroy(swm_db*) {}
-int swm_db_query_device(swm_db*, const uint8_t*, int, int, uint64_t*, int32_t*, int, void*) { return SWM_E_STATE; }
-int64_t swm_db_size(const swm_db*) { return 0; }
+
+namespace swm {
+
+constexpr int kThHigh = 100;    // ORBmatcher.cc:37
+constexpr int kThLow = 50;      // ORBmatcher.cc:38
+constexpr int kHistoLen = 30;   // ORBmatcher.cc:39
+constexpr int kGridCols = SWM_GRID_COLS, kGridRows = SWM_GRID_ROWS, kCells = kGridCols * kGridRows;
+
+__device__ __forceinline__ int ham256(const uint4 a0, const uint4 a1, const uint4* __restrict__ b) {
+  const uint4 b0 = __ldg(b), b1 = __ldg(b + 1);
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
+
+// ---------------------------------------------------------------------------------------------
+// DescriptorDistance in bulk
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hamming_matrix_kernel(const uint4* __restrict__ a, int na,
+                                                             const uint4* __restrict__ b, int nb,
+                                                             uint16_t* __restrict__ out) {
+  const int j = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int i0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * 4;
+  if (j >= nb) return;
+  const uint4 b0 = __ldg(b + 2 * j), b1 = __ldg(b + 2 * j + 1);
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int i = i0 + k;
+    if (i < na) out[(size_t)i * nb + j] = (uint16_t)ham256(b0, b1, a + 2 * i);
+  }
+}
+
+__global__ void hamming_pairs_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, int n,
+                                     int32_t* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = ham256(__ldg(a + 2 * i), __ldg(a + 2 * i + 1), b + 2 * i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Frame grid (Frame.cc:277-292, PosInGrid :432-442 uses round()).  One CTA; cell lists keep
+// ascending keypoint index, cell index = ix*48+iy so a column's cells are contiguous in `items`
+// (GetFeaturesInArea's "for ix, for iy, for j" order = a few contiguous spans).
+// ---------------------------------------------------------------------------------------------
+struct FrameDev {
+  int n;
+  const float* x;
+  const float* y;
+  const int32_t* octave;
+  const float* angle;
+  const uint4* desc;
+  float min_x, min_y, max_x, max_y, inv_w, inv_h;
+  const int32_t* starts;  // kCells + 1
+  const int32_t* items;
+};
+
+__global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int32_t* __restrict__ starts,
+                                                          int32_t* __restrict__ items, int32_t* __restrict__ cell_of) {
+  __shared__ int s_cnt[kCells + 1];
+  __shared__ int s_part[1024];
+  const int tid = threadIdx.x;
+  for (int c = tid; c <= kCells; c += 1024) s_cnt[c] = 0;
+  __syncthreads();
+  for (int i = tid; i < f.n; i += 1024) {
+    const int px = (int)roundf((f.x[i] - f.min_x) * f.inv_w);
+    const int py = (int)roundf((f.y[i] - f.min_y) * f.inv_h);
+    int cell = -1;
+    if (px >= 0 && px < kGridCols && py >= 0 && py < kGridRows) {
+      cell = px * kGridRows + py;
+      atomicAdd(&s_cnt[cell], 1);
+    }
+    cell_of[i] = cell;
+  }
+  __syncthreads();
+  // exclusive scan over 3072 cells: 3 per thread
+  const int c0 = tid * 3;
+  int local = 0;
+  for (int k = 0; k < 3; k++) local += s_cnt[c0 + k];
+  s_part[tid] = local;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = tid >= o ? s_part[tid - o] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int run = s_part[tid] - local;
+  for (int k = 0; k < 3; k++) {
+    const int v = s_cnt[c0 + k];
+    starts[c0 + k] = run;
+    s_cnt[c0 + k] = run;  // becomes the scatter cursor
+    run += v;
+  }
+  if (tid == 1023) starts[kCells] = run;
+  __syncthreads();
+  for (int i = tid; i < f.n; i += 1024) {
+    const int cell = cell_of[i];
+    if (cell >= 0) items[atomicAdd(&s_cnt[cell], 1)] = i;
+  }
+  __syncthreads();
+  // restore ascending index order inside each cell (insertion sort; cells hold a handful of items)
+  for (int c = tid; c < kCells; c += 1024) {
+    const int b = starts[c], e = s_cnt[c];
+    for (int i = b + 1; i < e; i++) {
+      const int v = items[i];
+      int j = i - 1;
+      while (j >= b && items[j] > v) {
+        items[j + 1] = items[j];
+        j--;
+      }
+      items[j + 1] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Candidate rows by window query (Frame::GetFeaturesInArea, Frame.cc:377-430), one warp per
+// source.  pass 0 counts, pass 1 writes (index, level<<16 | distance) in the reference's order.
+// ---------------------------------------------------------------------------------------------
+struct WindowDev {
+  int m;
+  const uint4* desc;
+  const float* u;
+  const float* v;
+  const float* radius;
+  const int32_t* min_level;
+  const int32_t* max_level;
+  const uint8_t* valid;
+};
+
+__global__ void __launch_bounds__(256) window_rows_kernel(FrameDev f, WindowDev q, int pass,
+                                                          int32_t* __restrict__ row_count,
+                                                          const int32_t* __restrict__ row_start,
+                                                          int32_t* __restrict__ cand_idx, uint32_t* __restrict__ cand_val) {
+  const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (s >= q.m) return;
+  int total = 0;
+  if (q.valid[s]) {
+    const float x = q.u[s], y = q.v[s], r = q.radius[s];
+    const int min_level = q.min_level[s], max_level = q.max_level[s];
+    // Frame.cc:382-396
+    const int min_cx = max(0, (int)floorf((x - f.min_x - r) * f.inv_w));
+    const int max_cx = min(kGridCols - 1, (int)ceilf((x - f.min_x + r) * f.inv_w));
+    const int min_cy = max(0, (int)floorf((y - f.min_y - r) * f.inv_h));
+    const int max_cy = min(kGridRows - 1, (int)ceilf((y - f.min_y + r) * f.inv_h));
+    if (min_cx < kGridCols && max_cx >= 0 && min_cy < kGridRows && max_cy >= 0) {
+      const bool check_levels = (min_level > 0) || (max_level >= 0);
+      uint4 d0 = make_uint4(0, 0, 0, 0), d1 = d0;
+      int base = 0;
+      if (pass) {
+        d0 = __ldg(q.desc + 2 * s);
+        d1 = __ldg(q.desc + 2 * s + 1);
+        base = row_start[s];
+      }
+      for (int ix = min_cx; ix <= max_cx; ix++) {
+        const int b = f.starts[ix * kGridRows + min_cy], e = f.starts[ix * kGridRows + max_cy + 1];
+        for (int c0 = b; c0 < e; c0 += 32) {
+          const int c = c0 + lane;
+          bool ok = false;
+          int j = 0, oct = 0;
+          if (c < e) {
+            j = f.items[c];
+            oct = f.octave[j];
+            ok = true;
+            if (check_levels) {
+              if (oct < min_level) ok = false;
+              if (max_level >= 0 && oct > max_level) ok = false;
+            }
+            const float dx = f.x[j] - x, dy = f.y[j] - y;
+            ok = ok && fabsf(dx) < r && fabsf(dy) < r;
+          }
+          const unsigned mask = __ballot_sync(0xffffffffu, ok);
+          if (pass && ok) {
+            const int pos = base + total + __popc(mask & ((1u << lane) - 1));
+            cand_idx[pos] = j;
+            cand_val[pos] = ((uint32_t)oct << 16) | (uint32_t)ham256(d0, d1, f.desc + 2 * j);
+          }
+          total += __popc(mask);
+        }
+      }
+    }
+  }
+  if (!pass && lane == 0) row_count[s] = total;
+}
+
+// BoW rows: candidate indices come from the shared vocabulary nodes (host-built spans); fill distances.
+__global__ void __launch_bounds__(256) list_rows_kernel(const uint4* __restrict__ desc1, const uint4* __restrict__ desc2,
+                                                        const int32_t* __restrict__ octave2, int rows,
+                                                        const int32_t* __restrict__ row_src,
+                                                        const int32_t* __restrict__ row_start,
+                                                        const int32_t* __restrict__ cand_idx,
+                                                        uint32_t* __restrict__ cand_val) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int s = row_src[r];
+  const uint4 d0 = __ldg(desc1 + 2 * s), d1 = __ldg(desc1 + 2 * s + 1);
+  for (int c = row_start[r] + lane; c < row_start[r + 1]; c += 32) {
+    const int j = cand_idx[c];
+    cand_val[c] = ((uint32_t)octave2[j] << 16) | (uint32_t)ham256(d0, d1, desc2 + 2 * j);
+  }
+}
+
+// single-CTA exclusive scan of row counts -> row_start[0..m]
+__global__ void __launch_bounds__(1024) scan_rows_kernel(const int32_t* __restrict__ count, int m,
+                                                         int32_t* __restrict__ start) {
+  __shared__ int s_part[1024];
+  const int tid = threadIdx.x;
+  const int per = (m + 1023) / 1024;
+  const int b = tid * per, e = min(b + per, m);
+  int local = 0;
+  for (int i = b; i < e; i++) local += count[i];
+  s_part[tid] = local;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = tid >= o ? s_part[tid - o] : 0;
+    __syncthreads();
+    s_part[tid] += v;
+    __syncthreads();
+  }
+  int run = s_part[tid] - local;
+  for (int i = b; i < e; i++) {
+    start[i] = run;
+    run += count[i];
+  }
+  if (tid == 1023) start[m] = s_part[1023];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sequential resolve by one warp.
+// ---------------------------------------------------------------------------------------------
+enum ResolveMode { kModeInit = 0, kModeWindow = 1, kModeBowFrame = 2, kModeBowKf = 3 };
+
+struct ResolveArgs {
+  int mode;
+  int rows;                 // rows to replay, in order
+  const int32_t* row_src;   // row -> source index (NULL: identity)
+  const uint8_t* row_valid; // per source (NULL: all valid)
+  const int32_t* row_start;
+  const int32_t* cand_idx;
+  const uint32_t* cand_val;
+  int n1, n2;
+  const float* angle1;      // per source
+  const float* angle2;      // per target
+  const uint8_t* blocks;    // window mode: per source
+  const uint8_t* valid2;    // BowKf: per target validity
+  int th_dist;
+  int ratio_mode;
+  float nnratio;
+  int check_ori;
+  // state / outputs (global memory, single warp)
+  uint8_t* blocked;         // n2 (pre-initialised by the host for window mode)
+  int32_t* matched_dist;    // n2 (init mode)
+  int32_t* matches21;       // n2 (init mode)
+  int32_t* out;             // init: matches12[n1]; window: assignment[n2]; bowFrame: n2; bowKf: n1
+  int32_t* ev_bin;          // per source: histogram bin of its accepted match (-1 none)
+  int32_t* ev_tgt;          // per source: index stored in rotHist (what gets pruned)
+  float* prev_xy;           // init mode: vbPrevMatched
+  const float* x2;
+  const float* y2;
+  int32_t* nmatches;
+};
+
+// rot = a1 - a2; if (rot < 0) rot += 360; bin = round(rot * (1/30)); if (bin == 30) bin = 0
+__device__ __forceinline__ int rot_bin(float a1, float a2) {
+  const float factor = 1.0f / kHistoLen;
+  float rot = __fsub_rn(a1, a2);
+  if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+  int bin = (int)roundf(__fmul_rn(rot, factor));
+  if (bin == kHistoLen) bin = 0;
+  return bin;
+}
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = w < v ? w : v;
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(32) resolve_kernel(ResolveArgs a) {
+  const int lane = threadIdx.x;
+  const unsigned long long kNone = ~0ull;
+  int nmatches = 0;
+  for (int r = 0; r < a.rows; r++) {
+    const int s = a.row_src ? a.row_src[r] : r;
+    if (a.row_valid && !a.row_valid[s]) continue;
+    const int b = a.row_start[r], e = a.row_start[r + 1];
+    if (b == e) continue;
+    // key = dist << 32 | position: min key = smallest distance, first in enumeration order
+    unsigned long long best = kNone;
+    for (int c = b + lane; c < e; c += 32) {
+      const int j = a.cand_idx[c];
+      const unsigned dist = a.cand_val[c] & 0xFFFFu;
+      bool skip;
+      if (a.mode == kModeInit) skip = a.matched_dist[j] <= (int)dist;            // :414-415
+      else if (a.mode == kModeBowKf) skip = a.blocked[j] || !a.valid2[j];          // :531-535
+      else skip = a.blocked[j] != 0;                                               // :67-69,:196-197,:306,:1291,:1413
+      if (!skip) {
+        const unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(c - b);
+        best = key < best ? key : best;
+      }
+    }
+    best = warp_min_u64(best);
+    if (best == kNone) continue;
+    const int best_pos = (int)(best & 0xFFFFFFFFu);
+    const int best_dist = (int)(best >> 32);
+    // second best: P = first minimum before the winner, Q = first minimum after it; the running
+    // "bestDist2" of the reference ends as P if P <= Q else Q (matcher section).
+    unsigned long long p = kNone, q = kNone;
+    for (int c = b + lane; c < e; c += 32) {
+      if (c - b == best_pos) continue;
+      const int j = a.cand_idx[c];
+      const unsigned dist = a.cand_val[c] & 0xFFFFu;
+      bool skip;
+      if (a.mode == kModeInit) skip = a.matched_dist[j] <= (int)dist;
+      else if (a.mode == kModeBowKf) skip = a.blocked[j] || !a.valid2[j];
+      else skip = a.blocked[j] != 0;
+      if (!skip) {
+        const unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(c - b);
+        if (c - b < best_pos) p = key < p ? key : p;
+        else q = key < q ? key : q;
+      }
+    }
+    p = warp_min_u64(p);
+    q = warp_min_u64(q);
+    const unsigned long long sec = (p >> 32) <= (q >> 32) ? p : q;
+    const bool has_second = sec != kNone;
+    const int best_idx = a.cand_idx[b + best_pos];
+    const int best_level = (int)(a.cand_val[b + best_pos] >> 16);
+    int second_dist, second_level = -1;
+    if (has_second) {
+      second_dist = (int)(sec >> 32);
+      second_level = (int)(a.cand_val[b + (int)(sec & 0xFFFFFFFFu)] >> 16);
+    } else {
+      second_dist = a.mode == kModeInit ? 0x7FFFFFFF : 256;  // INT_MAX (:404) vs 256 (:57,:190)
+    }
+    bool accept;
+    if (a.mode == kModeInit) {
+      accept = best_dist <= kThLow && (float)best_dist < __fmul_rn((float)second_dist, a.nnratio);  // :426-427
+    } else if (a.mode == kModeWindow) {
+      accept = best_dist <= a.th_dist;                                                             // :111,:365,:1316,:1428
+      if (accept && a.ratio_mode == 1 && best_level == second_level &&
+          (float)best_dist > __fmul_rn(a.nnratio, (float)second_dist))                             // :112
+        accept = false;
+    } else if (a.mode == kModeBowFrame) {
+      accept = best_dist <= kThLow && (float)best_dist < __fmul_rn(a.nnratio, (float)second_dist);  // :212-213
+    } else {
+      accept = best_dist < kThLow && (float)best_dist < __fmul_rn(a.nnratio, (float)second_dist);   // :550-551
+    }
+    if (!accept) continue;
+    if (lane == 0) {
+      int ev_tgt = best_idx;
+      if (a.mode == kModeInit) {
+        const int prev_owner = a.matches21[best_idx];
+        if (prev_owner >= 0) {  // steal (:428-431)
+          a.out[prev_owner] = -1;
+          nmatches--;
+        }
+        a.out[s] = best_idx;
+        a.matches21[best_idx] = s;
+        a.matched_dist[best_idx] = best_dist;
+        ev_tgt = s;
+      } else if (a.mode == kModeWindow) {
+        a.out[best_idx] = s;
+        if (a.blocks[s]) a.blocked[best_idx] = 1;
+      } else if (a.mode == kModeBowFrame) {
+        a.out[best_idx] = s;
+        a.blocked[best_idx] = 1;
+      } else {
+        a.out[s] = best_idx;
+        a.blocked[best_idx] = 1;
+        ev_tgt = s;
+      }
+      nmatches++;
+      if (a.check_ori) {
+        a.ev_bin[s] = rot_bin(a.angle1[s], a.angle2[best_idx]);
+        a.ev_tgt[s] = ev_tgt;
+      }
+    }
+    __syncwarp();
+    __threadfence_block();
+  }
+  __syncwarp();
+  __threadfence_block();
+  // rotation-consistency pruning (e.g. :229-246): histogram of accepted events, keep the top three bins
+  if (a.check_ori) {
+    __shared__ int s_hist[kHistoLen];
+    __shared__ int s_keep[3];
+    if (lane < kHistoLen) s_hist[lane] = 0;
+    __syncwarp();
+    for (int s = lane; s < a.n1; s += 32)
+      if (a.ev_bin[s] >= 0) atomicAdd(&s_hist[a.ev_bin[s]], 1);
+    __syncwarp();
+    if (lane == 0) {  // ComputeThreeMaxima, :1475-1506
+      int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+      for (int i = 0; i < kHistoLen; i++) {
+        const int c = s_hist[i];
+        if (c > max1) {
+          max3 = max2; max2 = max1; max1 = c;
+          ind3 = ind2; ind2 = ind1; ind1 = i;
+        } else if (c > max2) {
+          max3 = max2; max2 = c;
+          ind3 = ind2; ind2 = i;
+        } else if (c > max3) {
+          max3 = c;
+          ind3 = i;
+        }
+      }
+      if ((float)max2 < 0.1f * (float)max1) {
+        ind2 = -1;
+        ind3 = -1;
+      } else if ((float)max3 < 0.1f * (float)max1) {
+        ind3 = -1;
+      }
+      s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+    }
+    __syncwarp();
+    int dropped = 0;
+    for (int s = lane; s < a.n1; s += 32) {
+      const int bin = a.ev_bin[s];
+      if (bin < 0 || bin == s_keep[0] || bin == s_keep[1] || bin == s_keep[2]) continue;
+      const int t = a.ev_tgt[s];
+      if (a.mode == kModeInit) {
+        if (a.out[t] >= 0) {  // :462-465 (only live matches are counted down)
+          a.out[t] = -1;
+          dropped++;
+        }
+      } else {
+        a.out[t] = -1;  // idempotent store; every event counts down (:240-243,:1345-1348)
+        dropped++;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dropped += __shfl_xor_sync(0xffffffffu, dropped, o);
+    nmatches -= dropped;  // lane 0's running count minus everybody's drops
+  }
+  __syncwarp();
+  __threadfence_block();
+  if (a.mode == kModeInit) {  // :474-476
+    for (int s = lane; s < a.n1; s += 32) {
+      const int j = a.out[s];
+      if (j >= 0) {
+        a.prev_xy[2 * s] = a.x2[j];
+        a.prev_xy[2 * s + 1] = a.y2[j];
+      }
+    }
+  }
+  if (lane == 0) *a.nmatches = nmatches;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Place-recognition shard (BASELINE config 5): brute-force top-2 of each query over the shard.
+// Each thread owns one query (descriptor in registers); the CTA streams database tiles through
+// shared memory (broadcast reads), keeping a running top-2 of packed keys dist<<48 | global index.
+// Per-CTA partials are merged by a second kernel (deterministic: ties -> lower index).
+// ---------------------------------------------------------------------------------------------
+constexpr int kDbTile = 256;     // database descriptors per smem tile
+constexpr int kDbQPerCta = 128;  // queries per CTA (one per thread)
+
+__global__ void __launch_bounds__(kDbQPerCta) db_top2_kernel(const uint4* __restrict__ db, long long ndb,
+                                                             long long first_index, const uint4* __restrict__ q, int nq,
+                                                             int tiles_per_cta, unsigned long long* __restrict__ partial) {
+  __shared__ uint4 s_db[kDbTile * 2];
+  const int qi = blockIdx.y * kDbQPerCta + threadIdx.x;
+  uint4 q0 = make_uint4(0, 0, 0, 0), q1 = q0;
+  if (qi < nq) {
+    q0 = __ldg(q + 2 * qi);
+    q1 = __ldg(q + 2 * qi + 1);
+  }
+  unsigned long long k0 = ~0ull, k1 = ~0ull;
+  const long long tile0 = (long long)blockIdx.x * tiles_per_cta;
+  for (int t = 0; t < tiles_per_cta; t++) {
+    const long long base = (tile0 + t) * kDbTile;
+    if (base >= ndb) break;
+    const int cnt = (int)min((long long)kDbTile, ndb - base);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * 2; i += kDbQPerCta) s_db[i] = __ldg(db + 2 * base + i);
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < cnt; j++) {
+      const uint4 b0 = s_db[2 * j], b1 = s_db[2 * j + 1];
+      const unsigned d = __popc(q0.x ^ b0.x) + __popc(q0.y ^ b0.y) + __popc(q0.z ^ b0.z) + __popc(q0.w ^ b0.w) +
+                         __popc(q1.x ^ b1.x) + __popc(q1.y ^ b1.y) + __popc(q1.z ^ b1.z) + __popc(q1.w ^ b1.w);
+      const unsigned long long key = ((unsigned long long)d << 48) | (unsigned long long)(first_index + base + j);
+      if (key < k1) {
+        if (key < k0) {
+          k1 = k0;
+          k0 = key;
+        } else {
+          k1 = key;
+        }
+      }
+    }
+  }
+  if (qi < nq) {
+    partial[((size_t)blockIdx.x * nq + qi) * 2] = k0;
+    partial[((size_t)blockIdx.x * nq + qi) * 2 + 1] = k1;
+  }
+}
+
+__global__ void db_merge_kernel(const unsigned long long* __restrict__ partial, int nparts, int nq, int k,
+                                unsigned long long* __restrict__ topk, int32_t* __restrict__ votes, int th_votes,
+                                long long first_kf, int desc_per_kf, long long first_index, long long n_kf) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= nq) return;
+  unsigned long long k0 = ~0ull, k1 = ~0ull;
+  for (int p = 0; p < nparts; p++) {
+    for (int e = 0; e < 2; e++) {
+      const unsigned long long key = partial[((size_t)p * nq + qi) * 2 + e];
+      if (key < k1) {
+        if (key < k0) {
+          k1 = k0;
+          k0 = key;
+        } else {
+          k1 = key;
+        }
+      }
+    }
+  }
+  topk[(size_t)qi * k] = k0;
+  if (k > 1) topk[(size_t)qi * k + 1] = k1;
+  if (votes && k0 != ~0ull && (int)(k0 >> 48) <= th_votes) {
+    const long long idx = (long long)(k0 & 0xFFFFFFFFFFFFull) - first_index;
+    const long long kf = idx / desc_per_kf;
+    if (kf >= 0 && kf < n_kf) atomicAdd(votes + kf, 1);
+  }
+  (void)first_kf;
+}
+
+}  // namespace swm
+
+// =================================================================================================
+// Host side
+// =================================================================================================
+using namespace swm;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 2 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct swm_matcher {
+  int device = 0;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  // frame uploads (two frames), query uploads, rows, state
+  DevBuf f[2][6];  // x, y, octave, angle, desc, (grid starts+items+cell_of)
+  DevBuf q[10];
+  DevBuf rows[5];  // row_count, row_start, cand_idx, cand_val, row_src
+  DevBuf state[7]; // blocked, matched_dist, matches21, out, ev_bin, ev_tgt, nmatches/prev
+  void free_all() {
+    for (auto& a : f) for (auto& b : a) b.release();
+    for (auto& b : q) b.release();
+    for (auto& b : rows) b.release();
+    for (auto& b : state) b.release();
+  }
+};
+
+namespace {
+
+thread_local std::string g_match_create_error;
+
+#define MCK(m, call)                                   \
+  do {                                                 \
+    cudaError_t e_ = (call);                           \
+    if (e_ != cudaSuccess) {                           \
+      (m)->err = cuda_err(#call, e_);                  \
+      return SWM_E_CUDA;                               \
+    }                                                  \
+  } while (0)
+
+int upload(swm_matcher* m, DevBuf& b, const void* src, size_t bytes) {
+  MCK(m, b.ensure(bytes ? bytes : 4));
+  if (bytes) MCK(m, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, m->stream));
+  return SWM_OK;
+}
+
+bool frame_ok(const swm_frame_view* f) {
+  return f && f->n >= 0 && (f->n == 0 || (f->x && f->y && f->octave && f->angle && f->desc)) && f->max_x > f->min_x &&
+         f->max_y > f->min_y;
+}
+
+// Uploads a frame and builds its grid on the device.
+int upload_frame(swm_matcher* m, int slot, const swm_frame_view* f, FrameDev* out, bool want_grid) {
+  const size_t n = (size_t)f->n;
+  int rc;
+  if ((rc = upload(m, m->f[slot][0], f->x, n * 4))) return rc;
+  if ((rc = upload(m, m->f[slot][1], f->y, n * 4))) return rc;
+  if ((rc = upload(m, m->f[slot][2], f->octave, n * 4))) return rc;
+  if ((rc = upload(m, m->f[slot][3], f->angle, n * 4))) return rc;
+  if ((rc = upload(m, m->f[slot][4], f->desc, n * 32))) return rc;
+  FrameDev d;
+  d.n = f->n;
+  d.x = m->f[slot][0].as<float>();
+  d.y = m->f[slot][1].as<float>();
+  d.octave = m->f[slot][2].as<int32_t>();
+  d.angle = m->f[slot][3].as<float>();
+  d.desc = m->f[slot][4].as<uint4>();
+  d.min_x = f->min_x; d.min_y = f->min_y; d.max_x = f->max_x; d.max_y = f->max_y;
+  d.inv_w = (float)kGridCols / (float)(f->max_x - f->min_x);  // Frame.cc:259-260
+  d.inv_h = (float)kGridRows / (float)(f->max_y - f->min_y);
+  d.starts = nullptr;
+  d.items = nullptr;
+  if (want_grid) {
+    MCK(m, m->f[slot][5].ensure(((size_t)kCells + 1 + 2 * n + 8) * 4));
+    int32_t* starts = m->f[slot][5].as<int32_t>();
+    int32_t* items = starts + kCells + 1;
+    int32_t* cell_of = items + n + 4;
+    grid_build_kernel<<<1, 1024, 0, m->stream>>>(d, starts, items, cell_of);
+    MCK(m, cudaGetLastError());
+    d.starts = starts;
+    d.items = items;
+  }
+  *out = d;
+  return SWM_OK;
+}
+
+// window rows: count -> scan -> fill.  Returns total candidates through *total.
+int build_window_rows(swm_matcher* m, const FrameDev& tgt, const WindowDev& q, int* total) {
+  const int M = q.m;
+  MCK(m, m->rows[0].ensure((size_t)(M + 1) * 4));
+  MCK(m, m->rows[1].ensure((size_t)(M + 2) * 4));
+  int32_t* row_count = m->rows[0].as<int32_t>();
+  int32_t* row_start = m->rows[1].as<int32_t>();
+  const int grid = (M + 7) / 8;
+  window_rows_kernel<<<grid, 256, 0, m->stream>>>(tgt, q, 0, row_count, nullptr, nullptr, nullptr);
+  scan_rows_kernel<<<1, 1024, 0, m->stream>>>(row_count, M, row_start);
+  int tot = 0;
+  MCK(m, cudaMemcpyAsync(&tot, row_start + M, 4, cudaMemcpyDeviceToHost, m->stream));
+  MCK(m, cudaStreamSynchronize(m->stream));
+  MCK(m, m->rows[2].ensure((size_t)(tot + 1) * 4));
+  MCK(m, m->rows[3].ensure((size_t)(tot + 1) * 4));
+  window_rows_kernel<<<grid, 256, 0, m->stream>>>(tgt, q, 1, row_count, row_start, m->rows[2].as<int32_t>(),
+                                                  m->rows[3].as<uint32_t>());
+  MCK(m, cudaGetLastError());
+  *total = tot;
+  return SWM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int swm_matcher_create(int device, swm_matcher** out) {
+  if (!out) return SWM_E_INVALID;
+  *out = nullptr;
+  int rc = check_device(device, &g_match_create_error);
+  if (rc != SWM_OK) return rc;
+  swm_matcher* m = new swm_matcher;
+  m->device = device;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    g_match_create_error = cuda_err("swm_matcher_create", e);
+    delete m;
+    return SWM_E_CUDA;
+  }
+  *out = m;
+  return SWM_OK;
+}
+
+void swm_matcher_destroy(swm_matcher* m) {
+  if (!m) return;
+  cudaSetDevice(m->device);
+  m->free_all();
+  if (m->stream) cudaStreamDestroy(m->stream);
+  delete m;
+}
+
+const char* swm_matcher_last_error(const swm_matcher* m) { return m ? m->err.c_str() : g_match_create_error.c_str(); }
+
+int swm_hamming_matrix_device(const uint8_t* d_a, int na, const uint8_t* d_b, int nb, uint16_t* d_out, void* stream) {
+  if (!d_a || !d_b || !d_out || na < 0 || nb < 0) return SWM_E_INVALID;
+  if (na == 0 || nb == 0) return SWM_OK;
+  dim3 grid((nb + 31) / 32, (na + 31) / 32);
+  hamming_matrix_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)d_a, na, (const uint4*)d_b, nb, d_out);
+  return cudaGetLastError() == cudaSuccess ? SWM_OK : SWM_E_CUDA;
+}
+
+int swm_hamming_matrix(const uint8_t* a, int na, const uint8_t* b, int nb, uint16_t* out, int device) {
+  if (!a || !b || !out || na < 0 || nb < 0) return SWM_E_INVALID;
+  std::string err;
+  int rc = check_device(device, &err);
+  if (rc != SWM_OK) return rc;
+  if (na == 0 || nb == 0) return SWM_OK;
+  if (cudaSetDevice(device) != cudaSuccess) return SWM_E_CUDA;
+  uint8_t *da = nullptr, *db = nullptr;
+  uint16_t* dout = nullptr;
+  cudaError_t e = cudaMalloc(&da, (size_t)na * 32);
+  if (e == cudaSuccess) e = cudaMalloc(&db, (size_t)nb * 32);
+  if (e == cudaSuccess) e = cudaMalloc(&dout, (size_t)na * nb * 2);
+  if (e == cudaSuccess) e = cudaMemcpy(da, a, (size_t)na * 32, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(db, b, (size_t)nb * 32, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) rc = swm_hamming_matrix_device(da, na, db, nb, dout, nullptr);
+  if (e == cudaSuccess && rc == SWM_OK) e = cudaMemcpy(out, dout, (size_t)na * nb * 2, cudaMemcpyDeviceToHost);
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return e == cudaSuccess ? rc : SWM_E_CUDA;
+}
+
+int swm_hamming_pairs(const uint8_t* a, const uint8_t* b, int n, int32_t* out, int device) {
+  if (!a || !b || !out || n < 0) return SWM_E_INVALID;
+  std::string err;
+  int rc = check_device(device, &err);
+  if (rc != SWM_OK) return rc;
+  if (n == 0) return SWM_OK;
+  if (cudaSetDevice(device) != cudaSuccess) return SWM_E_CUDA;
+  uint8_t *da = nullptr, *db = nullptr;
+  int32_t* dout = nullptr;
+  cudaError_t e = cudaMalloc(&da, (size_t)n * 32);
+  if (e == cudaSuccess) e = cudaMalloc(&db, (size_t)n * 32);
+  if (e == cudaSuccess) e = cudaMalloc(&dout, (size_t)n * 4);
+  if (e == cudaSuccess) e = cudaMemcpy(da, a, (size_t)n * 32, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(db, b, (size_t)n * 32, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    hamming_pairs_kernel<<<(n + 255) / 256, 256>>>((const uint4*)da, (const uint4*)db, n, dout);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost);
+  cudaFree(da); cudaFree(db); cudaFree(dout);
+  return e == cudaSuccess ? SWM_OK : SWM_E_CUDA;
+}
+
+int swm_grid_build(swm_matcher* m, const swm_frame_view* f, int32_t* starts, int32_t* items) {
+  if (!m) return SWM_E_INVALID;
+  if (!frame_ok(f) || !starts || !items) { m->err = "bad argument"; return SWM_E_INVALID; }
+  MCK(m, cudaSetDevice(m->device));
+  FrameDev d;
+  int rc = upload_frame(m, 0, f, &d, true);
+  if (rc) return rc;
+  MCK(m, cudaMemcpyAsync(starts, d.starts, ((size_t)kCells + 1) * 4, cudaMemcpyDeviceToHost, m->stream));
+  MCK(m, cudaStreamSynchronize(m->stream));
+  const int total = starts[kCells];
+  if (total) MCK(m, cudaMemcpy(items, d.items, (size_t)total * 4, cudaMemcpyDeviceToHost));
+  return SWM_OK;
+}
+
+int swm_match_init(swm_matcher* m, const swm_frame_view* f1, const swm_frame_view* f2, float* prev_xy,
+                   int32_t* matches12, int window, float nnratio, int check_ori, int* nmatches) {
+  if (!m) return SWM_E_INVALID;
+  if (!frame_ok(f1) || !frame_ok(f2) || !prev_xy || !matches12 || !nmatches) { m->err = "bad argument"; return SWM_E_INVALID; }
+  *nmatches = 0;
+  const int n1 = f1->n, n2 = f2->n;
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  if (n1 == 0 || n2 == 0) return SWM_OK;
+  MCK(m, cudaSetDevice(m->device));
+  FrameDev d1, d2;
+  int rc;
+  if ((rc = upload_frame(m, 0, f1, &d1, false))) return rc;
+  if ((rc = upload_frame(m, 1, f2, &d2, true))) return rc;
+  // sources = F1 keypoints at octave 0 (:390-392), window centre = vbPrevMatched, levels (0,0) (:394-396)
+  std::vector<float> u(n1), v(n1), rad(n1, (float)window);
+  std::vector<int32_t> lv(n1, 0);
+  std::vector<uint8_t> valid(n1);
+  for (int i = 0; i < n1; i++) {
+    u[i] = prev_xy[2 * i];
+    v[i] = prev_xy[2 * i + 1];
+    valid[i] = f1->octave[i] > 0 ? 0 : 1;
+    lv[i] = f1->octave[i];
+  }
+  if ((rc = upload(m, m->q[0], u.data(), (size_t)n1 * 4))) return rc;
+  if ((rc = upload(m, m->q[1], v.data(), (size_t)n1 * 4))) return rc;
+  if ((rc = upload(m, m->q[2], rad.data(), (size_t)n1 * 4))) return rc;
+  if ((rc = upload(m, m->q[3], lv.data(), (size_t)n1 * 4))) return rc;
+  if ((rc = upload(m, m->q[4], valid.data(), (size_t)n1))) return rc;
+  if ((rc = upload(m, m->q[5], prev_xy, (size_t)n1 * 8))) return rc;
+  WindowDev q;
+  q.m = n1;
+  q.desc = d1.desc;
+  q.u = m->q[0].as<float>();
+  q.v = m->q[1].as<float>();
+  q.radius = m->q[2].as<float>();
+  q.min_level = m->q[3].as<int32_t>();
+  q.max_level = m->q[3].as<int32_t>();
+  q.valid = m->q[4].as<uint8_t>();
+  int total = 0;
+  if ((rc = build_window_rows(m, d2, q, &total))) return rc;
+  // state
+  MCK(m, m->state[1].ensure((size_t)n2 * 4));
+  MCK(m, m->state[2].ensure((size_t)n2 * 4));
+  MCK(m, m->state[3].ensure((size_t)n1 * 4));
+  MCK(m, m->state[4].ensure((size_t)n1 * 4));
+  MCK(m, m->state[5].ensure((size_t)n1 * 4));
+  MCK(m, m->state[6].ensure(16));
+  std::vector<int32_t> big(n2, 0x7FFFFFFF);
+  MCK(m, cudaMemcpyAsync(m->state[1].p, big.data(), (size_t)n2 * 4, cudaMemcpyHostToDevice, m->stream));
+  MCK(m, cudaMemsetAsync(m->state[2].p, 0xFF, (size_t)n2 * 4, m->stream));
+  MCK(m, cudaMemsetAsync(m->state[3].p, 0xFF, (size_t)n1 * 4, m->stream));
+  MCK(m, cudaMemsetAsync(m->state[4].p, 0xFF, (size_t)n1 * 4, m->stream));
+  ResolveArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = kModeInit;
+  a.rows = n1;
+  a.row_valid = q.valid;
+  a.row_start = m->rows[1].as<int32_t>();
+  a.cand_idx = m->rows[2].as<int32_t>();
+  a.cand_val = m->rows[3].as<uint32_t>();
+  a.n1 = n1; a.n2 = n2;
+  a.angle1 = d1.angle; a.angle2 = d2.angle;
+  a.nnratio = nnratio;
+  a.check_ori = check_ori;
+  a.matched_dist = m->state[1].as<int32_t>();
+  a.matches21 = m->state[2].as<int32_t>();
+  a.out = m->state[3].as<int32_t>();
+  a.ev_bin = m->state[4].as<int32_t>();
+  a.ev_tgt = m->state[5].as<int32_t>();
+  a.prev_xy = m->q[5].as<float>();
+  a.x2 = d2.x; a.y2 = d2.y;
+  a.nmatches = m->state[6].as<int32_t>();
+  resolve_kernel<<<1, 32, 0, m->stream>>>(a);
+  MCK(m, cudaGetLastError());
+  MCK(m, cudaMemcpyAsync(matches12, a.out, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
+  MCK(m, cudaMemcpyAsync(prev_xy, a.prev_xy, (size_t)n1 * 8, cudaMemcpyDeviceToHost, m->stream));
+  MCK(m, cudaMemcpyAsync(nmatches, a.nmatches, 4, cudaMemcpyDeviceToHost, m->stream));
+  MCK(m, cudaStreamSynchronize(m->stream));
+  return SWM_OK;
+}
+
+int swm_match_window(swm_matcher* m, const swm_frame_view* tgt, const swm_window_query* wq,
+                     const uint8_t* tgt_blocked, int th_dist, int ratio_mode, float nnratio, int check_ori,
+                     int32_t* assignment, int* nmatches) {
+  if (!m) return SWM_E_INVALID;
+  if (!frame_ok(tgt) || !wq || wq->m < 0 || !assignment || !nmatches ||
+      (wq->m > 0 && (!wq->desc || !wq->u || !wq->v || !wq->radius || !wq->min_level || !wq->max_level || !wq->valid ||
+                     !wq->blocks || (check_ori && !wq->angle)))) {
+    m->err = "bad argument";
+    return SWM_E_INVALID;
+  }
+  *nmatches = 0;
+  const int M = wq->m, n2 = tgt->n;
+  if (M == 0 || n2 == 0) return SWM_OK;
+  MCK(m, cudaSetDevice(m->device));
+  FrameDev d2;
+  int rc;
+  if ((rc = upload_frame(m, 1, tgt, &d2, true))) return rc;
+  if ((rc = upload(m, m->q[0], wq->u, (size_t)M * 4))) return rc;
+  if ((rc = upload(m, m->q[1], wq->v, (size_t)M * 4))) return rc;
+  if ((rc = upload(m, m->q[2], wq->radius, (size_t)M * 4))) return rc;
+  if ((rc = upload(m, m->q[3], wq->min_level, (size_t)M * 4))) return rc;
+  if ((rc = upload(m, m->q[6], wq->max_level, (size_t)M * 4))) return rc;
+  if ((rc = upload(m, m->q[4], wq->valid, (size_t)M))) return rc;
+  if ((rc = upload(m, m->q[7], wq->desc, (size_t)M * 32))) return rc;
+  if ((rc = upload(m, m->q[8], wq->blocks, (size_t)M))) return rc;
+  if (check_ori && (rc = upload(m, m->q[9], wq->angle, (size_t)M * 4))) return rc;
+  WindowDev q;
+  q.m = M;
+  q.desc = m->q[7].as<uint4>();
+  q.u = m->q[0].as<float>();
+  q.v = m->q[1].as<float>();
+  q.radius = m->q[2].as<float>();
+  q.min_level = m->q[3].as<int32_t>();
+  q.max_level = m->q[6].as<int32_t>();
+  q.valid = m->q[4].as<uint8_t>();
+  int total = 0;
+  if ((rc = build_window_rows(m, d2, q, &total))) return rc;
+  MCK(m, m->state[0].ensure((size_t)n2));
+  MCK(m, m->state[3].ensure((size_t)n2 * 4));
+  MCK(m, m->state[4].ensure((size_t)M * 4));
+  MCK(m, m->state[5].ensure((size_t)M * 4));
+  MCK(m, m->state[6].ensure(16));
+  if (tgt_blocked) MCK(m, cudaMemcpyAsync(m->state[0].p, tgt_blocked, (size_t)n2, cudaMemcpyHostToDevice, m->stream));
+  else MCK(m, cudaMemsetAsync(m->state[0].p, 0, (size_t)n2, m->stream));
+  MCK(m, cudaMemcpyAsync(m->state[3].p, assignment, (size_t)n2 * 4, cudaMemcpyHostToDevice, m->stream));
+  MCK(m, cudaMemsetAsync(m->state[4].p, 0xFF, (size_t)M * 4, m->stream));
+  ResolveArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = kModeWindow;
+  a.rows = M;
+  a.row_valid = q.valid;
+  a.row_start = m->rows[1].as<int32_t>();
+  a.cand_idx = m->rows[2].as<int32_t>();
+  a.cand_val = m->rows[3].as<uint32_t>();
+  a.n1 = M; a.n2 = n2;
+  a.angle1 = m->q[9].as<float>();
+  a.angle2 = d2.angle;
+  a.blocks = m->q[8].as<uint8_t>();
+  a.th_dist = th_dist;
+  a.ratio_mode = ratio_mode;
+  a.nnratio = nnratio;
+  a.check_ori = check_ori;
+  a.blocked = m->state[0].as<uint8_t>();
+  a.out = m->state[3].as<int32_t>();
+  a.ev_bin = m->state[4].as<int32_t>();
+  a.ev_tgt = m->state[5].as<int32_t>();
+  a.nmatches = m->state[6].as<int32_t>();
+  resolve_kernel<<<1, 32, 0, m->stream>>>(a);
+  MCK(m, cudaGetLastError());
+  MCK(m, cudaMemcpyAsync(assignment, a.out, (size_t)n2 * 4, cudaMemcpyDeviceToHost, m->stream));
+  MCK(m, cudaMemcpyAsync(nmatches, a.nmatches, 4, cudaMemcpyDeviceToHost, m->stream));
+  MCK(m, cudaStreamSynchronize(m->stream));
+  return SWM_OK;
+}
+
+int swm_match_bow(swm_matcher* m, const swm_frame_view* f1, const swm_featvec* fv1, const uint8_t* valid1,
+                  const swm_frame_view* f2, const swm_featvec* fv2, const uint8_t* valid2, int mode, float nnratio,
+                  int check_ori, int32_t* matches, int* nmatches) {
+  if (!m) return SWM_E_INVALID;
+  if (!frame_ok(f1) || !frame_ok(f2) || !fv1 || !fv2 || !valid1 || (mode == 1 && !valid2) || !matches || !nmatches ||
+      (mode != 0 && mode != 1)) {
+    m->err = "bad argument";
+    return SWM_E_INVALID;
+  }
+  *nmatches = 0;
+  const int n1 = f1->n, n2 = f2->n;
+  const int n_out = mode == 0 ? n2 : n1;
+  for (int i = 0; i < n_out; i++) matches[i] = -1;
+  if (n1 == 0 || n2 == 0) return SWM_OK;
+  // merge-walk the two sorted FeatureVectors (:166-241 / :507-581); rows = valid side-1 features of
+  // shared nodes in visiting order, candidates = side-2 features of the node.
+  std::vector<int32_t> row_src, row_start(1, 0), cand;
+  int a = 0, b = 0;
+  while (a < fv1->n_nodes && b < fv2->n_nodes) {
+    const uint32_t ia = fv1->node_ids[a], ib = fv2->node_ids[b];
+    if (ia == ib) {
+      for (int i1 = fv1->offsets[a]; i1 < fv1->offsets[a + 1]; i1++) {
+        const uint32_t idx1 = fv1->feats[i1];
+        if ((int)idx1 >= n1) { m->err = "feature index out of range"; return SWM_E_INVALID; }
+        if (!valid1[idx1]) continue;
+        row_src.push_back((int32_t)idx1);
+        for (int i2 = fv2->offsets[b]; i2 < fv2->offsets[b + 1]; i2++) {
+          if ((int)fv2->feats[i2] >= n2) { m->err = "feature index out of range"; return SWM_E_INVALID; }
+          cand.push_back((int32_t)fv2->feats[i2]);
+        }
+        row_start.push_back((int32_t)cand.size());
+      }
+      a++;
+      b++;
+    } else if (ia < ib) {
+      a = (int)(std::lower_bound(fv1->node_ids, fv1->node_ids + fv1->n_nodes, ib) - fv1->node_ids);
+    } else {
+      b = (int)(std::lower_bound(fv2->node_ids, fv2->node_ids + fv2->n_nodes, ia) - fv2->node_ids);
+    }
+  }
+  const int R = (int)row_src.size();
+  if (R == 0) return SWM_OK;
+  MCK(m, cudaSetDevice(m->device));
+  FrameDev d1, d2;
+  int rc;
+  if ((rc = upload_frame(m, 0, f1, &d1, false))) return rc;
+  if ((rc = upload_frame(m, 1, f2, &d2, false))) return rc;
+  if ((rc = upload(m, m->rows[4], row_src.data(), (size_t)R * 4))) return rc;
+  if ((rc = upload(m, m->rows[1], row_start.data(), (size_t)(R + 1) * 4))) return rc;
+  if ((rc = upload(m, m->rows[2], cand.data(), cand.size() * 4))) return rc;
+  MCK(m, m->rows[3].ensure((cand.size() + 1) * 4));
+  if (mode == 1 && (rc = upload(m, m->q[4], valid2, (size_t)n2))) return rc;
+  list_rows_kernel<<<(R + 7) / 8, 256, 0, m->stream>>>(d1.desc, d2.desc, d2.octave, R, m->rows[4].as<int32_t>(),
+                                                      m->rows[1].as<int32_t>(), m->rows[2].as<int32_t>(),
+                                                      m->rows[3].as<uint32_t>());
+  MCK(m, cudaGetLastError());
+  MCK(m, m->state[0].ensure((size_t)n2));
+  MCK(m, m->state[3].ensure((size_t)n_out * 4));
+  MCK(m, m->state[4].ensure((size_t)n1 * 4));
+  MCK(m, m->state[5].ensure((size_t)n1 * 4));
+  MCK(m, m->state[6].ensure(16));
+  MCK(m, cudaMemsetAsync(m->state[0].p, 0, (size_t)n2, m->stream));
+  MCK(m, cudaMemsetAsync(m->state[3].p, 0xFF, (size_t)n_out * 4, m->stream));
+  MCK(m, cudaMemsetAsync(m->state[4].p, 0xFF, (size_t)n1 * 4, m->stream));
+  ResolveArgs ra;
+  memset(&ra, 0, sizeof(ra));
+  ra.mode = mode == 0 ? kModeBowFrame : kModeBowKf;
+  ra.rows = R;
+  ra.row_src = m->rows[4].as<int32_t>();
+  ra.row_start = m->rows[1].as<int32_t>();
+  ra.cand_idx = m->rows[2].as<int32_t>();
+  ra.cand_val = m->rows[3].as<uint32_t>();
+  ra.n1 = n1; ra.n2 = n2;
+  ra.angle1 = d1.angle; ra.angle2 = d2.angle;
+  ra.valid2 = m->q[4].as<uint8_t>();
+  ra.nnratio = nnratio;
+  ra.check_ori = check_ori;
+  ra.blocked = m->state[0].as<uint8_t>();
+  ra.out = m->state[3].as<int32_t>();
+  ra.ev_bin = m->state[4].as<int32_t>();
+  ra.ev_tgt = m->state[5].as<int32_t>();
+  ra.nmatches = m->state[6].as<int32_t>();
+  resolve_kernel<<<1, 32, 0, m->stream>>>(ra);
+  MCK(m, cudaGetLastError());
+  MCK(m, cudaMemcpyAsync(matches, ra.out, (size_t)n_out * 4, cudaMemcpyDeviceToHost, m->stream));
+  MCK(m, cudaMemcpyAsync(nmatches, ra.nmatches, 4, cudaMemcpyDeviceToHost, m->stream));
+  MCK(m, cudaStreamSynchronize(m->stream));
+  return SWM_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// Place-recognition shard
+// ---------------------------------------------------------------------------------------------
+struct swm_db {
+  int device = 0;
+  uint8_t* d_desc = nullptr;
+  bool owns = false;
+  long long ndesc = 0;
+  int desc_per_kf = 1;
+  long long first_kf = 0;
+  unsigned long long* d_partial = nullptr;
+  size_t partial_cap = 0;
+  int n_sm = 148;
+};
+
+extern "C" {
+
+int swm_db_create_device(int device, const uint8_t* d_desc, int64_t ndesc, int32_t desc_per_kf, int64_t first_kf_id,
+                         swm_db** out) {
+  if (!out || !d_desc || ndesc <= 0 || desc_per_kf <= 0) return SWM_E_INVALID;
+  std::string err;
+  int rc = check_device(device, &err);
+  if (rc != SWM_OK) return rc;
+  swm_db* db = new swm_db;
+  db->device = device;
+  db->d_desc = const_cast<uint8_t*>(d_desc);
+  db->ndesc = ndesc;
+  db->desc_per_kf = desc_per_kf;
+  db->first_kf = first_kf_id;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) db->n_sm = prop.multiProcessorCount;
+  *out = db;
+  return SWM_OK;
+}
+
+int swm_db_create(int device, const uint8_t* desc, int64_t ndesc, int32_t desc_per_kf, int64_t first_kf_id,
+                  swm_db** out) {
+  if (!out || !desc || ndesc <= 0 || desc_per_kf <= 0) return SWM_E_INVALID;
+  std::string err;
+  int rc = check_device(device, &err);
+  if (rc != SWM_OK) return rc;
+  if (cudaSetDevice(device) != cudaSuccess) return SWM_E_CUDA;
+  uint8_t* d = nullptr;
+  if (cudaMalloc(&d, (size_t)ndesc * 32) != cudaSuccess) return SWM_E_CUDA;
+  if (cudaMemcpy(d, desc, (size_t)ndesc * 32, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(d);
+    return SWM_E_CUDA;
+  }
+  rc = swm_db_create_device(device, d, ndesc, desc_per_kf, first_kf_id, out);
+  if (rc != SWM_OK) {
+    cudaFree(d);
+    return rc;
+  }
+  (*out)->owns = true;
+  return SWM_OK;
+}
+
+void swm_db_destroy(swm_db* db) {
+  if (!db) return;
+  cudaSetDevice(db->device);
+  if (db->owns) cudaFree(db->d_desc);
+  cudaFree(db->d_partial);
+  delete db;
+}
+
+int64_t swm_db_size(const swm_db* db) { return db ? db->ndesc : 0; }
+
+int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t* d_topk, int32_t* d_votes,
+                        int th_votes, void* stream) {
+  if (!db || !d_q || nq <= 0 || k < 1 || k > 2 || !d_topk) return SWM_E_INVALID;
+  if (cudaSetDevice(db->device) != cudaSuccess) return SWM_E_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long tiles = (db->ndesc + kDbTile - 1) / kDbTile;
+  const int qblocks = (nq + kDbQPerCta - 1) / kDbQPerCta;
+  // enough database slices that slices x query blocks fills the machine a few times over
+  long long parts = std::max<long long>(1, (long long)db->n_sm * 8 / qblocks);
+  parts = std::min<long long>(parts, tiles);
+  const int tiles_per_cta = (int)((tiles + parts - 1) / parts);
+  parts = (tiles + tiles_per_cta - 1) / tiles_per_cta;
+  const size_t need = (size_t)parts * nq * 2 * sizeof(unsigned long long);
+  if (need > db->partial_cap) {
+    cudaFree(db->d_partial);
+    db->d_partial = nullptr;
+    db->partial_cap = 0;
+    if (cudaMalloc(&db->d_partial, need) != cudaSuccess) return SWM_E_CUDA;
+    db->partial_cap = need;
+  }
+  const long long first_index = db->first_kf * db->desc_per_kf;
+  dim3 grid((unsigned)parts, qblocks);
+  db_top2_kernel<<<grid, kDbQPerCta, 0, st>>>((const uint4*)db->d_desc, db->ndesc, first_index, (const uint4*)d_q, nq,
+                                              tiles_per_cta, db->d_partial);
+  const long long n_kf = (db->ndesc + db->desc_per_kf - 1) / db->desc_per_kf;
+  db_merge_kernel<<<(nq + 127) / 128, 128, 0, st>>>(db->d_partial, (int)parts, nq, k, (unsigned long long*)d_topk,
+                                                    d_votes, th_votes, db->first_kf, db->desc_per_kf, first_index, n_kf);
+  return cudaGetLastError() == cudaSuccess ? SWM_OK : SWM_E_CUDA;
+}
+
+}  // extern "C"

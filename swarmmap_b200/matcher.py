@@ -1,0 +1,210 @@
+"""Host-side mirror of ORB_SLAM2::ORBmatcher (reference code/include/ORBmatcher.h:37-102) on top of
+the C ABI.  The matchers take flat views of the Frame/KeyFrame fields they touch; pointers to
+MapPoints never cross the boundary (the C++ wrapper in swarmmap_b200/host/ORBmatcher.h gathers the
+same arrays from Frame/KeyFrame/MapPoint objects and scatters the results back).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import FeatVec, FrameView, SwmError, WindowQuery, check, ptr
+
+__all__ = ["ORBmatcher", "Frame", "FeatureVector"]
+
+GRID_COLS, GRID_ROWS = 64, 48
+
+
+class Frame:
+    """The slice of ORB_SLAM2::Frame / KeyFrame the matchers read: undistorted keypoints (x, y, octave,
+    angle), descriptors (N x 32) and the image bounds mnMinX.. (Frame.cc:486-513)."""
+
+    def __init__(self, x, y, octave, angle, desc, bounds, scale_factors=None):
+        self.x = np.ascontiguousarray(x, np.float32)
+        self.y = np.ascontiguousarray(y, np.float32)
+        self.octave = np.ascontiguousarray(octave, np.int32)
+        self.angle = np.ascontiguousarray(angle, np.float32)
+        self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.N = len(self.x)
+        assert len(self.y) == self.N and len(self.octave) == self.N and len(self.desc) == self.N
+        self.bounds = tuple(float(b) for b in bounds)  # (mnMinX, mnMinY, mnMaxX, mnMaxY)
+        self.mvScaleFactors = scale_factors
+
+    @classmethod
+    def from_keypoints(cls, kps, desc, width, height, scale_factors=None):
+        return cls(kps["x"], kps["y"], kps["octave"], kps["angle"], desc, (0.0, 0.0, float(width), float(height)),
+                   scale_factors)
+
+    def view(self):
+        b = self.bounds
+        return FrameView(self.N, ptr(self.x).value, ptr(self.y).value, ptr(self.octave).value, ptr(self.angle).value,
+                         ptr(self.desc).value, b[0], b[1], b[2], b[3])
+
+
+class FeatureVector:
+    """DBoW2::FeatureVector as CSR: ascending node ids, ascending feature indices per node
+    (Thirdparty/DBoW2/DBoW2/FeatureVector.cpp:31-45)."""
+
+    def __init__(self, node_of_feature):
+        node_of_feature = np.asarray(node_of_feature, np.int64)
+        keep = np.nonzero(node_of_feature >= 0)[0]
+        order = keep[np.argsort(node_of_feature[keep], kind="stable")]
+        nodes = node_of_feature[order]
+        self.node_ids, first = np.unique(nodes, return_index=True)
+        self.node_ids = self.node_ids.astype(np.uint32)
+        self.offsets = np.append(first, len(nodes)).astype(np.int32)
+        self.feats = order.astype(np.uint32)
+
+    def view(self):
+        return FeatVec(len(self.node_ids), ptr(self.node_ids).value, ptr(self.offsets).value, ptr(self.feats).value)
+
+
+class ORBmatcher:
+    """ORBmatcher(nnratio=0.6, checkOri=true), ORBmatcher.cc:41."""
+
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30  # ORBmatcher.cc:37-39
+
+    def __init__(self, nnratio=0.6, checkOri=True, device=0):
+        self._lib = _lib.load()
+        self.mfNNratio = float(nnratio)
+        self.mbCheckOrientation = bool(checkOri)
+        self.device = int(device)
+        h = C.c_void_p()
+        rc = self._lib.swm_matcher_create(self.device, C.byref(h))
+        if rc != 0:
+            raise SwmError(f"swm_matcher_create: {_lib.ERRORS.get(rc, rc)}: "
+                           f"{self._lib.swm_matcher_last_error(None).decode()}")
+        self._h = h
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.swm_matcher_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise SwmError(f"{what}: {_lib.ERRORS.get(rc, rc)}: {self._lib.swm_matcher_last_error(self._h).decode()}")
+
+    # ---- DescriptorDistance (ORBmatcher.cc:1511-1525), batched
+    def DescriptorDistance(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        assert len(a) == len(b)
+        out = np.zeros(len(a), np.int32)
+        rc = self._lib.swm_hamming_pairs(ptr(a), ptr(b), len(a), ptr(out), self.device)
+        self._check(rc, "swm_hamming_pairs")
+        return int(out[0]) if len(out) == 1 else out
+
+    def distance_matrix(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32)
+        b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        out = np.zeros((len(a), len(b)), np.uint16)
+        self._check(self._lib.swm_hamming_matrix(ptr(a), len(a), ptr(b), len(b), ptr(out), self.device),
+                    "swm_hamming_matrix")
+        return out
+
+    # ---- Frame grid (Frame.cc:277-292)
+    def grid(self, frame):
+        starts = np.zeros(GRID_COLS * GRID_ROWS + 1, np.int32)
+        items = np.zeros(max(frame.N, 1), np.int32)
+        v = frame.view()
+        self._check(self._lib.swm_grid_build(self._h, C.byref(v), ptr(starts), ptr(items)), "swm_grid_build")
+        return starts, items[:starts[-1]]
+
+    # ---- SearchForInitialization (ORBmatcher.cc:375-479)
+    def SearchForInitialization(self, F1, F2, vbPrevMatched, windowSize=10):
+        """vbPrevMatched: (N1, 2) float32, updated in place.  Returns (nmatches, vnMatches12)."""
+        assert vbPrevMatched.dtype == np.float32 and vbPrevMatched.shape == (F1.N, 2) and vbPrevMatched.flags.c_contiguous
+        matches = np.full(F1.N, -1, np.int32)
+        n = C.c_int(0)
+        v1, v2 = F1.view(), F2.view()
+        rc = self._lib.swm_match_init(self._h, C.byref(v1), C.byref(v2), ptr(vbPrevMatched), ptr(matches),
+                                      int(windowSize), self.mfNNratio, int(self.mbCheckOrientation), C.byref(n))
+        self._check(rc, "swm_match_init")
+        return n.value, matches
+
+    # ---- generic windowed projection matcher behind the SearchByProjection overloads
+    def match_window(self, tgt, desc, u, v, radius, min_level, max_level, valid, blocks, th_dist, ratio_mode=0,
+                     angle=None, tgt_blocked=None, assignment=None, check_ori=None):
+        m = len(u)
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        arrs = dict(u=np.ascontiguousarray(u, np.float32), v=np.ascontiguousarray(v, np.float32),
+                    radius=np.ascontiguousarray(radius, np.float32),
+                    min_level=np.ascontiguousarray(min_level, np.int32),
+                    max_level=np.ascontiguousarray(max_level, np.int32),
+                    valid=np.ascontiguousarray(valid, np.uint8), blocks=np.ascontiguousarray(blocks, np.uint8))
+        check_ori = self.mbCheckOrientation if check_ori is None else bool(check_ori)
+        ang = np.ascontiguousarray(angle, np.float32) if angle is not None else None
+        if check_ori and ang is None:
+            raise ValueError("angle is required when the orientation check is on")
+        q = WindowQuery(m, ptr(desc).value, ptr(arrs["u"]).value, ptr(arrs["v"]).value, ptr(arrs["radius"]).value,
+                        ptr(arrs["min_level"]).value, ptr(arrs["max_level"]).value, ptr(arrs["valid"]).value,
+                        ptr(ang).value if ang is not None else None, ptr(arrs["blocks"]).value)
+        if assignment is None:
+            assignment = np.full(tgt.N, -1, np.int32)
+        tb = np.ascontiguousarray(tgt_blocked, np.uint8) if tgt_blocked is not None else None
+        n = C.c_int(0)
+        tv = tgt.view()
+        rc = self._lib.swm_match_window(self._h, C.byref(tv), C.byref(q), ptr(tb) if tb is not None else None,
+                                        int(th_dist), int(ratio_mode), self.mfNNratio, int(check_ori),
+                                        ptr(assignment), C.byref(n))
+        self._check(rc, "swm_match_window")
+        return n.value, assignment
+
+    def SearchByProjectionLastFrame(self, cur, last, proj_u, proj_v, valid, th, last_obs_positive=None,
+                                    cur_blocked=None):
+        """SearchByProjection(Frame &cur, const Frame &last, th, bMono=true), ORBmatcher.cc:1223-1354.
+        proj_u/v: last-frame MapPoints projected with cur.mTcw (done by the caller); valid[i] = the point
+        exists, is an inlier, has positive depth and projects inside the image."""
+        sf = np.asarray(cur.mvScaleFactors, np.float32)
+        radius = np.float32(th) * sf[last.octave]
+        blocks = np.ones(last.N, np.uint8) if last_obs_positive is None else last_obs_positive
+        return self.match_window(cur, last.desc, proj_u, proj_v, radius, last.octave - 1, last.octave + 1, valid,
+                                 blocks, self.TH_HIGH, 0, last.angle, cur_blocked)
+
+    def SearchByProjectionMapPoints(self, F, desc, proj_u, proj_v, pred_level, view_cos, valid, th=1.0,
+                                    obs_positive=None, blocked=None):
+        """SearchByProjection(Frame &F, const vector<MapPoint*>&, th), ORBmatcher.cc:44-121."""
+        sf = np.asarray(F.mvScaleFactors, np.float32)
+        pred_level = np.asarray(pred_level, np.int32)
+        r = np.where(np.asarray(view_cos, np.float32) > np.float32(0.998), np.float32(2.5), np.float32(4.0))  # :123-128
+        if th != 1.0:
+            r = (r * np.float32(th)).astype(np.float32)
+        radius = (r.astype(np.float32) * sf[pred_level]).astype(np.float32)
+        blocks = np.ones(len(proj_u), np.uint8) if obs_positive is None else obs_positive
+        return self.match_window(F, desc, proj_u, proj_v, radius, pred_level - 1, pred_level, valid, blocks,
+                                 self.TH_HIGH, 1, None, blocked, check_ori=False)
+
+    # ---- SearchByBoW (ORBmatcher.cc:150-262 KeyFrame->Frame, :481-597 KeyFrame<->KeyFrame)
+    def SearchByBoW(self, KF, fvKF, validKF, F, fvF, validF=None):
+        mode = 0 if validF is None else 1
+        validKF = np.ascontiguousarray(validKF, np.uint8)
+        v2 = np.ascontiguousarray(validF, np.uint8) if validF is not None else None
+        out = np.full(F.N if mode == 0 else KF.N, -1, np.int32)
+        n = C.c_int(0)
+        a, b = KF.view(), F.view()
+        fa, fb = fvKF.view(), fvF.view()
+        rc = self._lib.swm_match_bow(self._h, C.byref(a), C.byref(fa), ptr(validKF), C.byref(b), C.byref(fb),
+                                     ptr(v2) if v2 is not None else None, mode, self.mfNNratio,
+                                     int(self.mbCheckOrientation), ptr(out), C.byref(n))
+        self._check(rc, "swm_match_bow")
+        return n.value, out
+
+
+def smoke(kps, desc):
+    """Tiny matcher call for __graft_entry__.smoke(): match a frame against itself."""
+    f = Frame.from_keypoints(kps, desc, 752, 480)
+    m = ORBmatcher(0.9, True)
+    prev = np.stack([f.x, f.y], 1).astype(np.float32).copy()
+    n, m12 = m.SearchForInitialization(f, f, prev, 100)
+    lvl0 = int((f.octave == 0).sum())
+    assert n > 0.5 * lvl0, (n, lvl0)
+    ok = m12[m12 >= 0] == np.nonzero(m12 >= 0)[0]
+    assert ok.mean() > 0.95
+    print(f"matcher smoke ok: {n} self-matches of {lvl0} level-0 keypoints")

@@ -265,3 +265,67 @@ def make_frame(x, y, octave, angle, desc, bounds):
     f = Frame(len(x), _p(x).value, _p(y).value, _p(octave).value, _p(angle).value, _p(desc).value,
               *[float(b) for b in bounds])
     return f, (x, y, octave, angle, desc)
+
+
+# ---- matcher wrappers (frames are swarmmap_b200.matcher.Frame-like objects: x,y,octave,angle,desc,bounds) ----
+
+def _frame(f):
+    return make_frame(f.x, f.y, f.octave, f.angle, f.desc, f.bounds)
+
+
+def grid_csr(f):
+    fr, keep = _frame(f)
+    g = lib().orc_grid_build(C.byref(fr))
+    starts = np.zeros(64 * 48 + 1, np.int32)
+    items = np.zeros(max(f.N, 1), np.int32)
+    lib().orc_grid_csr(g, _p(starts), _p(items))
+    lib().orc_grid_destroy(g)
+    return starts, items[:starts[-1]]
+
+
+def search_for_initialization(f1, f2, prev_xy, window, nnratio, check_ori):
+    a, k1 = _frame(f1)
+    b, k2 = _frame(f2)
+    prev = np.ascontiguousarray(prev_xy, np.float32).copy()
+    m12 = np.full(f1.N, -1, np.int32)
+    n = lib().orc_search_for_initialization(C.byref(a), C.byref(b), _p(prev), _p(m12), int(window), float(nnratio),
+                                            int(check_ori))
+    return n, m12, prev
+
+
+def match_window(tgt, desc, u, v, radius, min_level, max_level, valid, blocks, th_dist, ratio_mode, nnratio,
+                 check_ori, angle=None, tgt_blocked=None, assignment=None):
+    t, keep = _frame(tgt)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    arr = [np.ascontiguousarray(u, np.float32), np.ascontiguousarray(v, np.float32),
+           np.ascontiguousarray(radius, np.float32), np.ascontiguousarray(min_level, np.int32),
+           np.ascontiguousarray(max_level, np.int32), np.ascontiguousarray(valid, np.uint8)]
+    ang = np.ascontiguousarray(angle, np.float32) if angle is not None else np.zeros(len(u), np.float32)
+    blk = np.ascontiguousarray(blocks, np.uint8)
+    q = WindowQuery(len(u), _p(desc).value, *[_p(a).value for a in arr], _p(ang).value, _p(blk).value)
+    asg = np.full(tgt.N, -1, np.int32) if assignment is None else assignment.copy()
+    tb = np.ascontiguousarray(tgt_blocked, np.uint8) if tgt_blocked is not None else None
+    n = lib().orc_match_window(C.byref(t), C.byref(q), _p(tb) if tb is not None else None, int(th_dist),
+                               int(ratio_mode), float(nnratio), int(check_ori), _p(asg))
+    return n, asg
+
+
+def search_by_bow(f1, fv1, valid1, f2, fv2, valid2, mode, nnratio, check_ori):
+    a, k1 = _frame(f1)
+    b, k2 = _frame(f2)
+    v1 = np.ascontiguousarray(valid1, np.uint8)
+    v2 = np.ascontiguousarray(valid2, np.uint8) if valid2 is not None else np.ones(f2.N, np.uint8)
+    fa = FeatVec(len(fv1.node_ids), _p(fv1.node_ids).value, _p(fv1.offsets).value, _p(fv1.feats).value)
+    fb = FeatVec(len(fv2.node_ids), _p(fv2.node_ids).value, _p(fv2.offsets).value, _p(fv2.feats).value)
+    out = np.full(f2.N if mode == 0 else f1.N, -1, np.int32)
+    n = lib().orc_search_by_bow(C.byref(a), C.byref(fa), _p(v1), C.byref(b), C.byref(fb), _p(v2), int(mode),
+                                float(nnratio), int(check_ori), _p(out))
+    return n, out
+
+
+def bruteforce_top2(q, db):
+    q = np.ascontiguousarray(q, np.uint8)
+    db = np.ascontiguousarray(db, np.uint8)
+    out = np.zeros((len(q), 4), np.int32)
+    lib().orc_bruteforce_top2(_p(q), len(q), _p(db), len(db), _p(out))
+    return out

@@ -1,0 +1,213 @@
+"""GPU parity of the Hamming matchers against the CPU oracle (bit-exact distances and match indices)."""
+import numpy as np
+import pytest
+
+from swarmmap_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def frames(oracle):
+    """Keypoints/descriptors of a short KITTI-shaped and a EuRoC-shaped synthetic sequence (CPU oracle)."""
+    from swarmmap_b200.matcher import Frame
+    out = {}
+    for name, (w, h, nf, seed) in {"kitti": (1241, 376, 4000, 20220405), "euroc": (752, 480, 1000, 20220406)}.items():
+        seq = synth.make_sequence(4, w, h, seed)
+        ex = oracle.Extractor(nf, 1.2, 8, 20, 7)
+        sf = oracle.scale_tables(1.2, 8)[0]
+        fs = []
+        for img in seq:
+            k, d = ex(img)
+            fs.append(Frame.from_keypoints(k, d, w, h, sf))
+        out[name] = fs
+    return out
+
+
+def test_descriptor_distance(oracle, swm):
+    from swarmmap_b200.matcher import ORBmatcher
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    b = rng.integers(0, 256, (517, 32), dtype=np.uint8)
+    b[:50] = a[:50]
+    b[50:100] = a[50:100] ^ np.uint8(1)
+    m = ORBmatcher()
+    ref = np.unpackbits(a[:, None, :] ^ b[None, :, :], axis=2).sum(2)
+    np.testing.assert_array_equal(m.distance_matrix(a, b), ref)
+    pair = m.DescriptorDistance(a, b[:300])
+    np.testing.assert_array_equal(pair, np.diag(ref[:, :300]))
+    assert m.DescriptorDistance(a[0], a[0]) == 0
+    assert m.DescriptorDistance(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
+    for i in range(20):
+        assert oracle.hamming256(a[i], b[i]) == ref[i, i]
+
+
+def test_grid_matches_oracle(oracle, swm, frames):
+    from swarmmap_b200.matcher import ORBmatcher
+    m = ORBmatcher()
+    for f in frames["kitti"][:2] + frames["euroc"][:1]:
+        s, it = m.grid(f)
+        os_, oit = oracle.grid_csr(f)
+        np.testing.assert_array_equal(s, os_)
+        np.testing.assert_array_equal(it, oit)
+
+
+@pytest.mark.parametrize("name,window", [("kitti", 100), ("euroc", 100), ("euroc", 30)])
+def test_search_for_initialization(oracle, swm, frames, name, window):
+    from swarmmap_b200.matcher import ORBmatcher
+    fs = frames[name]
+    m = ORBmatcher(0.9, True)
+    f1 = fs[0]
+    prev_g = np.stack([f1.x, f1.y], 1).astype(np.float32).copy()
+    prev_o = prev_g.copy()
+    for k in (1, 2, 3):  # as Tracking::MonocularInitialization does: same F1, successive F2, prev carried over
+        n, m12 = m.SearchForInitialization(f1, fs[k], prev_g, window)
+        on, om12, prev_o = oracle.search_for_initialization(f1, fs[k], prev_o, window, 0.9, True)
+        assert n == on
+        np.testing.assert_array_equal(m12, om12)
+        np.testing.assert_array_equal(prev_g, prev_o)
+        assert n > 50
+    m2 = ORBmatcher(0.9, False)
+    prev = np.stack([f1.x, f1.y], 1).astype(np.float32).copy()
+    n, m12 = m2.SearchForInitialization(f1, fs[1], prev, window)
+    on, om12, _ = oracle.search_for_initialization(f1, fs[1], np.stack([f1.x, f1.y], 1), window, 0.9, False)
+    assert n == on and (m12 == om12).all()
+
+
+def _window_case(rng, src, tgt, th, band, jitter):
+    sf = tgt.mvScaleFactors
+    u = src.x + rng.normal(0, jitter, src.N).astype(np.float32)
+    v = src.y + rng.normal(0, jitter, src.N).astype(np.float32)
+    radius = (np.float32(th) * sf[src.octave]).astype(np.float32)
+    lo, hi = src.octave + band[0], src.octave + band[1]
+    valid = (rng.random(src.N) < 0.8).astype(np.uint8)
+    blocks = (rng.random(src.N) < 0.7).astype(np.uint8)
+    return u, v, radius, lo, hi, valid, blocks
+
+
+@pytest.mark.parametrize("ratio_mode,ori,th_dist", [(0, True, 100), (1, False, 100), (0, False, 50), (0, True, 64)])
+def test_match_window(oracle, swm, frames, ratio_mode, ori, th_dist):
+    from swarmmap_b200.matcher import ORBmatcher
+    rng = np.random.default_rng(ratio_mode * 7 + th_dist)
+    m = ORBmatcher(0.8, ori)
+    for name in ("euroc", "kitti"):
+        src, tgt = frames[name][0], frames[name][1]
+        band = (-1, 0) if ratio_mode else (-1, 1)
+        u, v, radius, lo, hi, valid, blocks = _window_case(rng, src, tgt, 15 if ratio_mode == 0 else 4, band, 3.0)
+        tgt_blocked = (rng.random(tgt.N) < 0.1).astype(np.uint8)
+        asg0 = np.full(tgt.N, -1, np.int32)
+        asg0[rng.random(tgt.N) < 0.05] = 7  # pre-existing assignments must survive unless overwritten
+        n, asg = m.match_window(tgt, src.desc, u, v, radius, lo, hi, valid, blocks, th_dist, ratio_mode, src.angle,
+                                tgt_blocked, asg0.copy(), check_ori=ori)
+        on, oasg = oracle.match_window(tgt, src.desc, u, v, radius, lo, hi, valid, blocks, th_dist, ratio_mode, 0.8,
+                                       ori, src.angle, tgt_blocked, asg0)
+        assert n == on
+        np.testing.assert_array_equal(asg, oasg)
+        assert n > 20
+    # level filter disabled (-1,-1) and a window that leaves the image
+    src, tgt = frames["euroc"][0], frames["euroc"][2]
+    u = src.x.copy(); v = src.y.copy()
+    u[:50] = -500; v[50:100] = 5000; u[100:150] = 751.5
+    neg = np.full(src.N, -1, np.int32)
+    ones = np.ones(src.N, np.uint8)
+    rad = np.full(src.N, 20, np.float32)
+    n, asg = m.match_window(tgt, src.desc, u, v, rad, neg, neg, ones, ones, th_dist, ratio_mode, src.angle,
+                            check_ori=ori)
+    on, oasg = oracle.match_window(tgt, src.desc, u, v, rad, neg, neg, ones, ones, th_dist, ratio_mode, 0.8, ori,
+                                   src.angle)
+    assert n == on and (asg == oasg).all()
+
+
+def test_search_by_projection_wrappers(oracle, swm, frames):
+    from swarmmap_b200.matcher import ORBmatcher
+    last, cur = frames["euroc"][0], frames["euroc"][1]
+    rng = np.random.default_rng(5)
+    u = last.x + rng.normal(0, 2, last.N).astype(np.float32)
+    v = last.y + rng.normal(0, 2, last.N).astype(np.float32)
+    valid = np.ones(last.N, np.uint8)
+    m = ORBmatcher(0.9, True)
+    n, asg = m.SearchByProjectionLastFrame(cur, last, u, v, valid, 15)
+    sf = cur.mvScaleFactors
+    on, oasg = oracle.match_window(cur, last.desc, u, v, (np.float32(15) * sf[last.octave]).astype(np.float32),
+                                   last.octave - 1, last.octave + 1, valid, valid, 100, 0, 0.9, True, last.angle)
+    assert n == on and (asg == oasg).all() and n > 200
+    m3 = ORBmatcher(0.8, True)
+    cosv = rng.uniform(0.99, 1.0, last.N).astype(np.float32)
+    n, asg = m3.SearchByProjectionMapPoints(cur, last.desc, u, v, last.octave, cosv, valid, th=1.0)
+    r = np.where(cosv > np.float32(0.998), np.float32(2.5), np.float32(4.0)).astype(np.float32) * sf[last.octave]
+    on, oasg = oracle.match_window(cur, last.desc, u, v, r.astype(np.float32), last.octave - 1, last.octave, valid,
+                                   valid, 100, 1, 0.8, False)
+    assert n == on and (asg == oasg).all() and n > 100
+
+
+def _buckets(desc, seed=7, n_nodes=1000):
+    """Synthetic vocabulary buckets (ORBvoc.bin is a missing blob): node = hash of 10 descriptor bits."""
+    rng = np.random.default_rng(seed)
+    bits = np.unpackbits(desc, axis=1)
+    pick = rng.choice(256, 10, replace=False)
+    node = (bits[:, pick].astype(np.int64) * (1 << np.arange(10))).sum(1) % n_nodes
+    return node
+
+
+@pytest.mark.parametrize("mode,ratio", [(0, 0.7), (0, 0.75), (1, 0.75)])
+def test_search_by_bow(oracle, swm, frames, mode, ratio):
+    from swarmmap_b200.matcher import ORBmatcher, FeatureVector
+    rng = np.random.default_rng(11 + mode)
+    m = ORBmatcher(ratio, True)
+    for name in ("euroc", "kitti"):
+        kf, f = frames[name][0], frames[name][1]
+        # coarse buckets (few bits) so that nodes hold several features on both sides
+        fv1 = FeatureVector(_buckets(kf.desc, 7, 64))
+        fv2 = FeatureVector(_buckets(f.desc, 7, 64))
+        v1 = (rng.random(kf.N) < 0.85).astype(np.uint8)
+        v2 = (rng.random(f.N) < 0.85).astype(np.uint8) if mode == 1 else None
+        n, out = m.SearchByBoW(kf, fv1, v1, f, fv2, v2)
+        on, oout = oracle.search_by_bow(kf, fv1, v1, f, fv2, v2, mode, ratio, True)
+        assert n == on
+        np.testing.assert_array_equal(out, oout)
+        assert n > 10
+    # disjoint vocabularies -> no shared node, zero matches
+    kf, f = frames["euroc"][0], frames["euroc"][1]
+    fa = FeatureVector(_buckets(kf.desc, 7, 64))
+    fb = FeatureVector(_buckets(f.desc, 7, 64) + 1000)
+    n, out = m.SearchByBoW(kf, fa, np.ones(kf.N, np.uint8), f, fb, None if mode == 0 else np.ones(f.N, np.uint8))
+    assert n == 0 and (out == -1).all()
+
+
+def test_db_top2_shard(oracle, swm):
+    import ctypes as C
+    import torch
+    from swarmmap_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(99)
+    q = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    db = rng.integers(0, 256, (20000, 32), dtype=np.uint8)
+    for i in range(0, 300, 3):  # planted noisy copies + exact duplicates (tie-break on index)
+        j = int(rng.integers(0, 20000))
+        noisy = q[i].copy()
+        flip = rng.choice(256, 20, replace=False)
+        bits = np.unpackbits(noisy); bits[flip] ^= 1
+        db[j] = np.packbits(bits)
+    db[777] = db[123]
+    q[5] = db[123]
+    ref = oracle.bruteforce_top2(q, db)
+    h = C.c_void_p()
+    first_kf = 1000
+    assert lib.swm_db_create(0, _lib.ptr(db), len(db), 8, first_kf, C.byref(h)) == 0
+    dq = torch.from_numpy(q).cuda()
+    topk = torch.zeros((300, 2), dtype=torch.int64, device="cuda")
+    votes = torch.zeros(len(db) // 8, dtype=torch.int32, device="cuda")
+    rc = lib.swm_db_query_device(h, dq.data_ptr(), 300, 2, topk.data_ptr(), votes.data_ptr(), 50, None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    t = topk.cpu().numpy().astype(np.uint64)
+    dist = (t >> np.uint64(48)).astype(np.int64)
+    idx = (t & np.uint64((1 << 48) - 1)).astype(np.int64) - first_kf * 8
+    np.testing.assert_array_equal(dist[:, 0], ref[:, 0])
+    np.testing.assert_array_equal(idx[:, 0], ref[:, 1])
+    np.testing.assert_array_equal(dist[:, 1], ref[:, 2])
+    np.testing.assert_array_equal(idx[:, 1], ref[:, 3])
+    exp_votes = np.bincount(ref[ref[:, 0] <= 50, 1] // 8, minlength=len(db) // 8)
+    np.testing.assert_array_equal(votes.cpu().numpy(), exp_votes)
+    assert lib.swm_db_size(h) == len(db)
+    lib.swm_db_destroy(h)
