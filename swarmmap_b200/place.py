@@ -1,0 +1,141 @@
+"""Server-side cross-agent place recognition, sharded over GPUs (BASELINE.json config 5).
+
+Role in the reference: AgentMediator::CheckOverlapCandidates walks every other agent's
+KeyFrameDatabase on the CPU (code/src/AgentMediator.cc:140-202, KeyFrameDatabase::DetectLoopCandidates
+code/src/KeyFrameDatabase.cc:74-185) and then matches candidates with SearchByBoW(KF,KF).  Here the
+keyframe-descriptor database is partitioned by keyframe id range, one shard per rank/GPU; a query
+keyframe's descriptors are brute-force matched against the local shard by the CUDA top-2 kernel
+(swm_db_query_device), and the only exchange step is one all-gather of the fixed-size per-shard
+candidate blocks (nq x k packed 64-bit keys + per-keyframe vote counts stay local), followed by a
+deterministic merge (ascending key = distance, then global descriptor index) on every rank.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+__all__ = ["partition", "merge_topk", "PlaceShard", "unpack_keys"]
+
+KEY_IDX_BITS = 48
+
+
+def partition(n_keyframes, world_size):
+    """Contiguous keyframe-id ranges per rank: [(first_kf, n_kf), ...] (remainder spread over the low ranks)."""
+    base, rem = divmod(int(n_keyframes), int(world_size))
+    out, first = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < rem else 0)
+        out.append((first, n))
+        first += n
+    return out
+
+
+def unpack_keys(keys):
+    """packed keys (dist << 48 | global descriptor index) -> (dist, index) int64 arrays; ~0 -> (-1, -1)."""
+    k = keys.to(torch.int64) if isinstance(keys, torch.Tensor) else torch.from_numpy(np.asarray(keys).astype(np.int64))
+    none = k == -1
+    d = (k >> KEY_IDX_BITS) & 0xFFFF
+    i = k & ((1 << KEY_IDX_BITS) - 1)
+    d = torch.where(none, torch.full_like(d, -1), d)
+    i = torch.where(none, torch.full_like(i, -1), i)
+    return d, i
+
+
+def merge_topk(gathered, k):
+    """gathered: (world, nq, k) packed keys -> (nq, k) smallest keys per query (unsigned order)."""
+    w, nq, kk = gathered.shape
+    flat = gathered.permute(1, 0, 2).reshape(nq, w * kk)
+    # keys are < 2^63 except the all-ones "none" marker (-1 as int64): map it to int64 max for sorting
+    big = torch.iinfo(torch.int64).max
+    flat = torch.where(flat < 0, torch.full_like(flat, big), flat)
+    out = torch.sort(flat, dim=1).values[:, :k]
+    return torch.where(out == big, torch.full_like(out, -1), out)
+
+
+class PlaceShard:
+    """One rank's shard of the keyframe-descriptor database."""
+
+    def __init__(self, desc, desc_per_kf, first_kf, device=0, group=None, local_topk=None):
+        """desc: (n_desc, 32) uint8 (numpy or CUDA tensor) of this rank's keyframes, desc_per_kf each.
+        local_topk: test hook replacing the CUDA kernel (CPU-only gloo tests of the exchange logic)."""
+        self.group = group
+        self.desc_per_kf = int(desc_per_kf)
+        self.first_kf = int(first_kf)
+        self._local_topk = local_topk
+        self._h = None
+        if local_topk is not None:
+            self.desc = np.ascontiguousarray(desc, np.uint8)
+            self.n_desc = len(self.desc)
+            self.device = torch.device("cpu")
+            return
+        self._lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        if isinstance(desc, torch.Tensor):
+            self.d_desc = desc.to(self.device).contiguous()
+        else:
+            self.d_desc = torch.from_numpy(np.ascontiguousarray(desc, np.uint8)).to(self.device)
+        self.n_desc = int(self.d_desc.shape[0])
+        h = C.c_void_p()
+        rc = self._lib.swm_db_create_device(device, self.d_desc.data_ptr(), self.n_desc, self.desc_per_kf,
+                                            self.first_kf, C.byref(h))
+        if rc != 0:
+            raise _lib.SwmError(f"swm_db_create_device: {_lib.ERRORS.get(rc, rc)}")
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self._lib.swm_db_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def n_kf(self):
+        return (self.n_desc + self.desc_per_kf - 1) // self.desc_per_kf
+
+    def query_local(self, q, k=2, th_votes=50):
+        """q: (nq, 32) uint8.  Returns (keys (nq,k) int64 packed, votes (n_kf,) int32) for this shard."""
+        if self._local_topk is not None:
+            return self._local_topk(self, q, k, th_votes)
+        dq = q.to(self.device).contiguous() if isinstance(q, torch.Tensor) else \
+            torch.from_numpy(np.ascontiguousarray(q, np.uint8)).to(self.device)
+        nq = int(dq.shape[0])
+        keys = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        votes = torch.zeros(self.n_kf, dtype=torch.int32, device=self.device)
+        st = torch.cuda.current_stream(self.device)
+        rc = self._lib.swm_db_query_device(self._h, dq.data_ptr(), nq, k, keys.data_ptr(), votes.data_ptr(),
+                                           int(th_votes), C.c_void_p(st.cuda_stream))
+        if rc != 0:
+            raise _lib.SwmError(f"swm_db_query_device: {_lib.ERRORS.get(rc, rc)}")
+        return keys, votes
+
+    def query(self, q, k=2, th_votes=50):
+        """Global top-k over all shards: local kernel -> all-gather of (nq,k) key blocks -> merge.
+        Returns (keys (nq,k), local votes).  With no process group this is the 1-shard case."""
+        keys, votes = self.query_local(q, k, th_votes)
+        if not (dist.is_available() and dist.is_initialized()):
+            return keys, votes
+        world = dist.get_world_size(self.group)
+        if world == 1:
+            return keys, votes
+        bucket = [torch.empty_like(keys) for _ in range(world)]
+        dist.all_gather(bucket, keys, group=self.group)
+        merged = merge_topk(torch.stack(bucket, 0), k)
+        return merged, self.votes_from_global(merged, th_votes)
+
+    def votes_from_global(self, merged, th_votes):
+        """Per-keyframe votes of THIS shard from the merged result: a query votes for the keyframe owning
+        its global best match when that distance is <= th_votes (TH_LOW); summed over ranks this equals
+        the single-shard vote histogram."""
+        d, i = unpack_keys(merged[:, 0])
+        first = self.first_kf * self.desc_per_kf
+        mask = (d >= 0) & (d <= th_votes) & (i >= first) & (i < first + self.n_desc)
+        kf = torch.div(i[mask] - first, self.desc_per_kf, rounding_mode="floor")
+        return torch.bincount(kf, minlength=self.n_kf).to(torch.int32)
