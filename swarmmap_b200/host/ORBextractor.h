@@ -1,0 +1,132 @@
+// ORBextractor.h -- drop-in ORB_SLAM2::ORBextractor on top of libswm_orb.so (include/swm_orb.h).
+//
+// Same class name, constructor, operator() signature, getters and public flags as the reference
+// (/root/reference/code/include/ORBextractor.h:48-125), so Frame / KeyFrame / Tracking compile
+// unchanged: replace the reference's src/ORBextractor.cc + src/cuda/*.cu with this header and link
+// libswm_orb.so.  Build with -DSWM_HAVE_OPENCV against the real OpenCV, or without it against
+// cv_shim.h (tests).  Error behaviour mirrors the reference: CUDA / setup failures are fatal
+// (checkCudaErrors -> exit, Fast_gpu.cu:346-352) -- here a std::runtime_error carrying
+// swm_last_error(); an empty image returns silently (ORBextractor.cc:750-751).
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#ifdef SWM_HAVE_OPENCV
+#include <opencv2/core.hpp>
+#else
+#include "cv_shim.h"
+#endif
+#include "../../include/swm_orb.h"
+
+namespace ORB_SLAM2 {
+
+// What the public mvImagePyramid / mvImagePyramidBorder vectors expose (device memory, as in the
+// reference where they are cv::cuda::GpuMat over cudaMallocManaged buffers).
+struct PyramidLevelView {
+  const unsigned char* data = nullptr;  // device pointer to ROI pixel (0,0)
+  int cols = 0, rows = 0;
+  size_t step = 0;
+};
+
+class ORBextractor {
+ public:
+  enum { HARRIS_SCORE = 0, FAST_SCORE = 1 };
+
+  ORBextractor(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST, int device = 0)
+      : mvImagePyramidAllocatedFlag(false), nlevels_(nlevels), scaleFactor_(scaleFactor) {
+    swm_orb_cfg cfg;
+    cfg.nfeatures = nfeatures;
+    cfg.scale_factor = scaleFactor;
+    cfg.nlevels = nlevels;
+    cfg.ini_th_fast = iniThFAST;
+    cfg.min_th_fast = minThFAST;
+    cfg.max_batch = 1;
+    cfg.max_fast_per_level = 0;
+    if (swm_orb_create(&cfg, device, &h_) != SWM_OK)
+      throw std::runtime_error(std::string("ORBextractor: ") + swm_last_error(nullptr));
+    mvScaleFactor.resize(nlevels);
+    mvInvScaleFactor.resize(nlevels);
+    mvLevelSigma2.resize(nlevels);
+    mvInvLevelSigma2.resize(nlevels);
+    swm_orb_scale_tables(h_, mvScaleFactor.data(), mvInvScaleFactor.data(), mvLevelSigma2.data(),
+                         mvInvLevelSigma2.data());
+  }
+  ~ORBextractor() { swm_orb_destroy(h_); }
+  ORBextractor(const ORBextractor&) = delete;
+  ORBextractor& operator=(const ORBextractor&) = delete;
+
+  // Compute the ORB features and descriptors on an image.  Mask is ignored, as in the reference.
+  void operator()(cv::InputArray _image, cv::InputArray /*_mask*/, std::vector<cv::KeyPoint>& _keypoints,
+                  cv::OutputArray _descriptors) {
+#ifdef SWM_HAVE_OPENCV
+    if (_image.empty()) return;
+    cv::Mat image = _image.getMat();
+    CV_Assert(image.type() == CV_8UC1);
+#else
+    const cv::Mat& image = _image;
+    if (image.empty()) return;
+#endif
+    const int cap = swm_orb_max_keypoints(h_);
+    kp_buf_.resize(cap);
+    desc_buf_.resize((size_t)cap * 32);
+    int n = 0;
+    const int rc = swm_orb_extract(h_, image.data, image.cols, image.rows, (int)image.step,
+                                   reinterpret_cast<swm_keypoint*>(kp_buf_.data()), desc_buf_.data(), cap, &n);
+    if (rc != SWM_OK) throw std::runtime_error(std::string("ORBextractor: ") + swm_last_error(h_));
+    _keypoints.assign(kp_buf_.begin(), kp_buf_.begin() + n);
+    if (n == 0) {
+      _descriptors.release();
+    } else {
+      _descriptors.create(n, 32, CV_8U);
+#ifdef SWM_HAVE_OPENCV
+      cv::Mat d = _descriptors.getMat();
+#else
+      cv::Mat& d = _descriptors;
+#endif
+      for (int i = 0; i < n; i++) std::memcpy(d.ptr(i), desc_buf_.data() + (size_t)i * 32, 32);
+    }
+    refresh_pyramid_views();
+  }
+
+  int inline GetLevels() { return nlevels_; }
+  float inline GetScaleFactor() { return scaleFactor_; }
+  std::vector<float> inline GetScaleFactors() { return mvScaleFactor; }
+  std::vector<float> inline GetInverseScaleFactors() { return mvInvScaleFactor; }
+  std::vector<float> inline GetScaleSigmaSquares() { return mvLevelSigma2; }
+  std::vector<float> inline GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
+
+  // Public pyramid members of the reference (ORBextractor.h:90-92).  mvImagePyramid[l] is the level
+  // ROI after the call (blurred, like the reference's in-place filter); mvImagePyramidBorder[l] the
+  // un-blurred plane whose 19-px reflect-101 border lies at negative offsets of `data`.
+  bool mvImagePyramidAllocatedFlag;
+  std::vector<PyramidLevelView> mvImagePyramid;
+  std::vector<PyramidLevelView> mvImagePyramidBorder;
+
+  swm_orb* handle() { return h_; }
+
+ protected:
+  void refresh_pyramid_views() {
+    mvImagePyramid.resize(nlevels_);
+    mvImagePyramidBorder.resize(nlevels_);
+    for (int l = 0; l < nlevels_; l++) {
+      for (int which = 0; which < 2; which++) {
+        const unsigned char* dev = nullptr;
+        int w = 0, h = 0, pitch = 0;
+        if (swm_orb_level_ptr(h_, 0, l, which, &dev, &w, &h, &pitch) != SWM_OK) return;
+        PyramidLevelView& v = which ? mvImagePyramid[l] : mvImagePyramidBorder[l];
+        v.data = dev; v.cols = w; v.rows = h; v.step = (size_t)pitch;
+      }
+    }
+    mvImagePyramidAllocatedFlag = true;
+  }
+
+  swm_orb* h_ = nullptr;
+  int nlevels_;
+  float scaleFactor_;
+  std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+  std::vector<cv::KeyPoint> kp_buf_;
+  std::vector<unsigned char> desc_buf_;
+};
+
+}  // namespace ORB_SLAM2

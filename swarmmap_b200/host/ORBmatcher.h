@@ -1,0 +1,290 @@
+// ORBmatcher.h -- drop-in ORB_SLAM2::ORBmatcher on top of libswm_orb.so (include/swm_orb.h).
+//
+// Same constructor, constants and member signatures as the reference
+// (/root/reference/code/include/ORBmatcher.h:37-102) for the entry points on the hot path:
+//   DescriptorDistance, SearchForInitialization, SearchByProjection(Frame&, const Frame&, th, bMono),
+//   SearchByProjection(Frame&, const vector<MapPoint*>&, th), SearchByBoW(KeyFrame*, Frame&, ...),
+//   SearchByBoW(KeyFrame*, KeyFrame*, ...).
+// The member functions are templates over the Frame / KeyFrame / MapPoint types so this header
+// compiles both against the reference's own headers (instantiate with ORB_SLAM2::Frame etc.) and
+// against small test doubles; they only touch the members the reference's implementation touches
+// (file:line cited at each gather).  MapPoint pointers never cross the C ABI: the wrapper gathers
+// flat arrays, calls swm_match_*, and scatters the indices back into mvpMapPoints / vpMatches.
+#pragma once
+#include <cmath>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#ifdef SWM_HAVE_OPENCV
+#include <opencv2/core.hpp>
+#else
+#include "cv_shim.h"
+#endif
+#include "../../include/swm_orb.h"
+
+namespace ORB_SLAM2 {
+
+class ORBmatcher {
+ public:
+  static const int TH_LOW = 50;        // ORBmatcher.cc:38
+  static const int TH_HIGH = 100;      // ORBmatcher.cc:37
+  static const int HISTO_LENGTH = 30;  // ORBmatcher.cc:39
+
+  ORBmatcher(float nnratio = 0.6, bool checkOri = true, int device = 0)
+      : mfNNratio(nnratio), mbCheckOrientation(checkOri), device_(device) {
+    if (swm_matcher_create(device, &m_) != SWM_OK)
+      throw std::runtime_error(std::string("ORBmatcher: ") + swm_matcher_last_error(nullptr));
+  }
+  ~ORBmatcher() { swm_matcher_destroy(m_); }
+  ORBmatcher(const ORBmatcher&) = delete;
+  ORBmatcher& operator=(const ORBmatcher&) = delete;
+
+  // Hamming distance between two ORB descriptors (ORBmatcher.cc:1511-1525).  One pair per call goes
+  // through swm_hamming_pairs; bulk callers (MapPoint::ComputeDistinctiveDescriptors' N x N loop,
+  // MapPoint.cc:361-391) should call DescriptorDistanceMatrix instead.
+  static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b, int device = 0) {
+    int32_t d = -1;
+    if (swm_hamming_pairs(a.ptr(0), b.ptr(0), 1, &d, device) != SWM_OK)
+      throw std::runtime_error("ORBmatcher::DescriptorDistance: no CUDA device (there is no CPU fallback)");
+    return d;
+  }
+  static void DescriptorDistanceMatrix(const unsigned char* a, int na, const unsigned char* b, int nb,
+                                       std::vector<uint16_t>& out, int device = 0) {
+    out.resize((size_t)na * nb);
+    if (swm_hamming_matrix(a, na, b, nb, out.data(), device) != SWM_OK)
+      throw std::runtime_error("ORBmatcher::DescriptorDistanceMatrix failed");
+  }
+
+  // ---- Matching for the Map Initialization (ORBmatcher.cc:375-479)
+  template <class FrameT, class Point2fT>
+  int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<Point2fT>& vbPrevMatched,
+                              std::vector<int>& vnMatches12, int windowSize = 10) {
+    FlatFrame a, b;
+    gather(F1, a);
+    gather(F2, b);
+    std::vector<float> prev(2 * a.n);
+    for (int i = 0; i < a.n; i++) { prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
+    vnMatches12.assign(a.n, -1);
+    int n = 0;
+    swm_frame_view va = a.view(), vb = b.view();
+    check(swm_match_init(m_, &va, &vb, prev.data(), vnMatches12.data(), windowSize, mfNNratio, mbCheckOrientation, &n));
+    for (int i = 0; i < a.n; i++) { vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
+    return n;
+  }
+
+  // ---- Project MapPoints tracked in last frame into the current frame (ORBmatcher.cc:1223-1354), monocular.
+  // The stereo-only forward/backward branches (:1243-1244,:1274-1277) need bMono == false and are not served.
+  template <class FrameT>
+  int SearchByProjection(FrameT& CurrentFrame, const FrameT& LastFrame, const float th, const bool bMono) {
+    if (!bMono) throw std::runtime_error("ORBmatcher::SearchByProjection: stereo/RGB-D branch not supported (monocular SwarmMap)");
+    FlatFrame cur;
+    gather(CurrentFrame, cur);
+    const int M = LastFrame.N;
+    Query q(M);
+    float R[9], t[3];
+    pose(CurrentFrame.mTcw, R, t);
+    for (int i = 0; i < M; i++) {
+      auto* pMP = LastFrame.mvpMapPoints[i];
+      if (!pMP || LastFrame.mvbOutlier[i]) continue;                       // :1247-1250
+      float xw[3];
+      world_pos(pMP->GetWorldPos(), xw);
+      float xc[3];
+      transform(R, t, xw, xc);                                              // :1252-1253
+      const float invzc = 1.0 / xc[2];                                      // :1257
+      if (invzc < 0) continue;
+      const float u = CurrentFrame.fx * xc[0] * invzc + CurrentFrame.cx;    // :1262-1263
+      const float v = CurrentFrame.fy * xc[1] * invzc + CurrentFrame.cy;
+      if (u < CurrentFrame.mnMinX || u > CurrentFrame.mnMaxX) continue;
+      if (v < CurrentFrame.mnMinY || v > CurrentFrame.mnMaxY) continue;
+      const int oct = LastFrame.mvKeys[i].octave;                           // :1270
+      q.valid[i] = 1;
+      q.u[i] = u; q.v[i] = v;
+      q.radius[i] = th * CurrentFrame.mvScaleFactors[oct];                  // :1273
+      q.min_level[i] = oct - 1; q.max_level[i] = oct + 1;                   // :1282
+      q.angle[i] = LastFrame.mvKeysUn[i].angle;
+      q.blocks[i] = pMP->Observations() > 0;                                // :1291-1293
+      std::memcpy(&q.desc[(size_t)i * 32], descriptor_of(pMP).ptr(0), 32);  // :1287
+    }
+    std::vector<uint8_t> blocked(cur.n, 0);
+    for (int j = 0; j < cur.n; j++)
+      blocked[j] = CurrentFrame.mvpMapPoints[j] && CurrentFrame.mvpMapPoints[j]->Observations() > 0;
+    // assignment is in/out: untouched slots keep the sentinel, accepted slots get the source index,
+    // slots assigned and then pruned by the rotation histogram come back as -1 (NULL, :1345-1348)
+    const int32_t kUntouched = -3;
+    std::vector<int32_t> asg(cur.n, kUntouched);
+    int n = 0;
+    swm_frame_view vc = cur.view();
+    swm_window_query wq = q.view();
+    check(swm_match_window(m_, &vc, &wq, blocked.data(), TH_HIGH, 0, mfNNratio, mbCheckOrientation, asg.data(), &n));
+    for (int j = 0; j < cur.n; j++) {
+      if (asg[j] >= 0) CurrentFrame.mvpMapPoints[j] = LastFrame.mvpMapPoints[asg[j]];  // :1317
+      else if (asg[j] == -1) CurrentFrame.mvpMapPoints[j] = nullptr;
+    }
+    return n;
+  }
+
+  // ---- Search matches between Frame keypoints and projected MapPoints (ORBmatcher.cc:44-121).
+  template <class FrameT, class MapPointT>
+  int SearchByProjection(FrameT& F, const std::vector<MapPointT*>& vpMapPoints, const float th = 3) {
+    FlatFrame f;
+    gather(F, f);
+    const int M = (int)vpMapPoints.size();
+    Query q(M);
+    const bool bFactor = th != 1.0;
+    for (int i = 0; i < M; i++) {
+      MapPointT* pMP = vpMapPoints[i];
+      if (!pMP->mbTrackInView || pMP->isBad()) continue;                    // :51-55
+      const int lvl = pMP->mnTrackScaleLevel;
+      float r = pMP->mTrackViewCos > 0.998 ? 2.5f : 4.0f;                   // RadiusByViewingCos :123-128
+      if (bFactor) r *= th;
+      q.valid[i] = 1;
+      q.u[i] = pMP->mTrackProjX; q.v[i] = pMP->mTrackProjY;
+      q.radius[i] = r * F.mvScaleFactors[lvl];                              // :66
+      q.min_level[i] = lvl - 1; q.max_level[i] = lvl;
+      q.blocks[i] = pMP->Observations() > 0;
+      std::memcpy(&q.desc[(size_t)i * 32], descriptor_of(pMP).ptr(0), 32);
+    }
+    std::vector<uint8_t> blocked(f.n, 0);
+    for (int j = 0; j < f.n; j++) blocked[j] = F.mvpMapPoints[j] && F.mvpMapPoints[j]->Observations() > 0;  // :78-80
+    std::vector<int32_t> asg(f.n, -1);
+    int n = 0;
+    swm_frame_view vf = f.view();
+    swm_window_query wq = q.view();
+    check(swm_match_window(m_, &vf, &wq, blocked.data(), TH_HIGH, 1, mfNNratio, 0, asg.data(), &n));
+    for (int j = 0; j < f.n; j++)
+      if (asg[j] >= 0) F.mvpMapPoints[j] = vpMapPoints[asg[j]];             // :115
+    return n;
+  }
+
+  // ---- Search matches between MapPoints in a KeyFrame and ORB in a Frame (ORBmatcher.cc:150-262).
+  template <class KeyFrameT, class FrameT, class MapPointT>
+  int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches) {
+    const std::vector<MapPointT*> vpMapPointsKF = pKF->GetMapPointMatches();
+    FlatFrame a, b;
+    gather(*pKF, a);
+    gather(F, b);
+    std::vector<uint8_t> valid(a.n, 0);
+    for (int i = 0; i < a.n; i++) valid[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();  // :182-188
+    FlatFeatVec fa(pKF->mFeatVec), fb(F.mFeatVec);
+    std::vector<int32_t> out(b.n, -1);
+    int n = 0;
+    swm_frame_view va = a.view(), vb = b.view();
+    swm_featvec ga = fa.view(), gb = fb.view();
+    check(swm_match_bow(m_, &va, &ga, valid.data(), &vb, &gb, nullptr, 0, mfNNratio, mbCheckOrientation, out.data(), &n));
+    vpMapPointMatches.assign(b.n, static_cast<MapPointT*>(nullptr));
+    for (int j = 0; j < b.n; j++)
+      if (out[j] >= 0) vpMapPointMatches[j] = vpMapPointsKF[out[j]];
+    return n;
+  }
+
+  // ---- KeyFrame <-> KeyFrame (loop / merge candidates), ORBmatcher.cc:481-597.
+  template <class KeyFrameT, class MapPointT>
+  int SearchByBoW(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12) {
+    const std::vector<MapPointT*> mp1 = pKF1->GetMapPointMatches(), mp2 = pKF2->GetMapPointMatches();
+    FlatFrame a, b;
+    gather(*pKF1, a);
+    gather(*pKF2, b);
+    std::vector<uint8_t> v1(a.n, 0), v2(b.n, 0);
+    for (int i = 0; i < a.n; i++) v1[i] = mp1[i] && !mp1[i]->isBad();
+    for (int i = 0; i < b.n; i++) v2[i] = mp2[i] && !mp2[i]->isBad();
+    FlatFeatVec fa(pKF1->mFeatVec), fb(pKF2->mFeatVec);
+    std::vector<int32_t> out(a.n, -1);
+    int n = 0;
+    swm_frame_view va = a.view(), vb = b.view();
+    swm_featvec ga = fa.view(), gb = fb.view();
+    check(swm_match_bow(m_, &va, &ga, v1.data(), &vb, &gb, v2.data(), 1, mfNNratio, mbCheckOrientation, out.data(), &n));
+    vpMatches12.assign(a.n, static_cast<MapPointT*>(nullptr));
+    for (int i = 0; i < a.n; i++)
+      if (out[i] >= 0) vpMatches12[i] = mp2[out[i]];
+    return n;
+  }
+
+ protected:
+  struct FlatFrame {
+    int n = 0;
+    std::vector<float> x, y, angle;
+    std::vector<int32_t> octave;
+    std::vector<uint8_t> desc;
+    float min_x = 0, min_y = 0, max_x = 1, max_y = 1;
+    swm_frame_view view() const {
+      swm_frame_view v;
+      v.n = n; v.x = x.data(); v.y = y.data(); v.octave = octave.data(); v.angle = angle.data(); v.desc = desc.data();
+      v.min_x = min_x; v.min_y = min_y; v.max_x = max_x; v.max_y = max_y;
+      return v;
+    }
+  };
+  struct Query {
+    std::vector<uint8_t> desc, valid, blocks;
+    std::vector<float> u, v, radius, angle;
+    std::vector<int32_t> min_level, max_level;
+    explicit Query(int m) : desc((size_t)m * 32), valid(m, 0), blocks(m, 1), u(m), v(m), radius(m), angle(m),
+                            min_level(m, -1), max_level(m, -1) {}
+    swm_window_query view() const {
+      swm_window_query q;
+      q.m = (int)valid.size(); q.desc = desc.data(); q.u = u.data(); q.v = v.data(); q.radius = radius.data();
+      q.min_level = min_level.data(); q.max_level = max_level.data(); q.valid = valid.data();
+      q.angle = angle.data(); q.blocks = blocks.data();
+      return q;
+    }
+  };
+  // DBoW2::FeatureVector (std::map<NodeId, std::vector<unsigned>>) -> CSR in map order
+  struct FlatFeatVec {
+    std::vector<uint32_t> node_ids, feats;
+    std::vector<int32_t> offsets;
+    template <class FeatVecT>
+    explicit FlatFeatVec(const FeatVecT& fv) {
+      offsets.push_back(0);
+      for (auto it = fv.begin(); it != fv.end(); ++it) {
+        node_ids.push_back((uint32_t)it->first);
+        for (unsigned idx : it->second) feats.push_back(idx);
+        offsets.push_back((int32_t)feats.size());
+      }
+    }
+    swm_featvec view() const {
+      swm_featvec v;
+      v.n_nodes = (int)node_ids.size(); v.node_ids = node_ids.data(); v.offsets = offsets.data(); v.feats = feats.data();
+      return v;
+    }
+  };
+
+  // Frame / KeyFrame members read by every matcher: N, mvKeysUn, mDescriptors, image bounds.
+  template <class FrameT>
+  static void gather(const FrameT& F, FlatFrame& o) {
+    o.n = F.N;
+    o.x.resize(o.n); o.y.resize(o.n); o.angle.resize(o.n); o.octave.resize(o.n); o.desc.resize((size_t)o.n * 32);
+    for (int i = 0; i < o.n; i++) {
+      o.x[i] = F.mvKeysUn[i].pt.x; o.y[i] = F.mvKeysUn[i].pt.y;
+      o.angle[i] = F.mvKeysUn[i].angle; o.octave[i] = F.mvKeysUn[i].octave;
+      std::memcpy(&o.desc[(size_t)i * 32], F.mDescriptors.ptr(i), 32);
+    }
+    o.min_x = F.mnMinX; o.min_y = F.mnMinY; o.max_x = F.mnMaxX; o.max_y = F.mnMaxY;
+  }
+  template <class MapPointT>
+  static cv::Mat descriptor_of(MapPointT* p) { return p->GetDescriptor(); }
+  // mTcw is a 4x4 CV_32F; cv::Mat products of CV_32F accumulate in double (OpenCV gemm), mirrored here.
+  template <class MatT>
+  static void pose(const MatT& Tcw, float R[9], float t[3]) {
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) R[3 * r + c] = Tcw.template at<float>(r, c);
+      t[r] = Tcw.template at<float>(r, 3);
+    }
+  }
+  template <class MatT>
+  static void world_pos(const MatT& p, float x[3]) { for (int i = 0; i < 3; i++) x[i] = p.template at<float>(i); }
+  static void transform(const float R[9], const float t[3], const float x[3], float out[3]) {
+    for (int r = 0; r < 3; r++)
+      out[r] = (float)((double)R[3 * r] * x[0] + (double)R[3 * r + 1] * x[1] + (double)R[3 * r + 2] * x[2] + (double)t[r]);
+  }
+  void check(int rc) {
+    if (rc != SWM_OK) throw std::runtime_error(std::string("ORBmatcher: ") + swm_matcher_last_error(m_));
+  }
+
+  float mfNNratio;
+  bool mbCheckOrientation;
+  int device_;
+  swm_matcher* m_ = nullptr;
+};
+
+}  // namespace ORB_SLAM2

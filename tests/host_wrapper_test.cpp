@@ -1,0 +1,112 @@
+// host_wrapper_test.cpp -- compiles the drop-in C++ wrapper classes (swarmmap_b200/host/) against the
+// cv shim with small test doubles of Frame / KeyFrame / MapPoint that carry exactly the members the
+// reference's ORBmatcher touches.  Linked against libswm_orb.so; run on the GPU box by tests/test_gpu_host.py.
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <vector>
+
+#include "../swarmmap_b200/host/ORBextractor.h"
+#include "../swarmmap_b200/host/ORBmatcher.h"
+
+struct Mat4 {  // stand-in for the CV_32F cv::Mat pose / position
+  float v[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  int n = 16;
+  template <typename T> T at(int r, int c) const { return v[r * 4 + c]; }
+  template <typename T> T at(int i) const { return v[i]; }
+};
+
+struct MapPoint {
+  Mat4 pos;
+  cv::Mat desc;
+  int nobs = 1;
+  bool bad = false;
+  bool mbTrackInView = true;
+  float mTrackProjX = 0, mTrackProjY = 0, mTrackViewCos = 1.0f;
+  int mnTrackScaleLevel = 0;
+  Mat4 GetWorldPos() { return pos; }
+  cv::Mat GetDescriptor() { return desc; }
+  int Observations() { return nobs; }
+  bool isBad() { return bad; }
+};
+
+struct Frame {
+  int N = 0;
+  std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
+  cv::Mat mDescriptors;
+  float mnMinX = 0, mnMinY = 0, mnMaxX = 752, mnMaxY = 480;
+  std::vector<MapPoint*> mvpMapPoints;
+  std::vector<bool> mvbOutlier;
+  Mat4 mTcw;
+  float fx = 458.654f, fy = 457.296f, cx = 367.215f, cy = 248.375f;
+  std::vector<float> mvScaleFactors;
+  std::map<unsigned, std::vector<unsigned>> mFeatVec;
+  std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+};
+
+static void fill(Frame& f, ORB_SLAM2::ORBextractor& ex, const cv::Mat& img) {
+  ex(img, cv::Mat(), f.mvKeys, f.mDescriptors);
+  f.mvKeysUn = f.mvKeys;
+  f.N = (int)f.mvKeys.size();
+  f.mvpMapPoints.assign(f.N, nullptr);
+  f.mvbOutlier.assign(f.N, false);
+  f.mvScaleFactors = ex.GetScaleFactors();
+  for (int i = 0; i < f.N; i++) f.mFeatVec[f.mDescriptors.ptr(i)[0] & 31].push_back(i);
+}
+
+int main(int argc, char** argv) {
+  const int w = 752, h = 480;
+  cv::Mat img(h, w, CV_8U);
+  unsigned s = 1;
+  for (int y = 0; y < h; y++)
+    for (int x = 0; x < w; x++) {  // blocky texture with corners
+      s = s * 1664525u + 1013904223u;
+      img.ptr(y)[x] = (unsigned char)(((x / 23 + y / 17) % 2 ? 60 : 180) + ((x / 7 * 31 + y / 5 * 17) % 40) + (s >> 29));
+    }
+  ORB_SLAM2::ORBextractor ex(1000, 1.2f, 8, 20, 7);
+  Frame f1, f2;
+  fill(f1, ex, img);
+  fill(f2, ex, img);
+  std::printf("keypoints %d levels %d pyramid0 %dx%d allocated %d\n", f1.N, ex.GetLevels(), ex.mvImagePyramid[0].cols,
+              ex.mvImagePyramid[0].rows, (int)ex.mvImagePyramidAllocatedFlag);
+  if (f1.N < 300) return 1;
+  ORB_SLAM2::ORBmatcher m(0.9f, true);
+  std::vector<cv::Point2f> prev(f1.N);
+  for (int i = 0; i < f1.N; i++) prev[i] = f1.mvKeysUn[i].pt;
+  std::vector<int> m12;
+  const int n_init = m.SearchForInitialization(f1, f2, prev, m12, 100);
+  // give frame 1 map points in front of an identity camera that project onto their own keypoints
+  std::vector<MapPoint> pts(f1.N);
+  for (int i = 0; i < f1.N; i++) {
+    const float z = 2.0f;
+    pts[i].pos.v[0] = (f1.mvKeysUn[i].pt.x - f1.cx) / f1.fx * z;
+    pts[i].pos.v[1] = (f1.mvKeysUn[i].pt.y - f1.cy) / f1.fy * z;
+    pts[i].pos.v[2] = z;
+    pts[i].desc = f1.mDescriptors.row(i);
+    pts[i].mTrackProjX = f1.mvKeysUn[i].pt.x;
+    pts[i].mTrackProjY = f1.mvKeysUn[i].pt.y;
+    pts[i].mnTrackScaleLevel = f1.mvKeysUn[i].octave;
+    f1.mvpMapPoints[i] = &pts[i];
+  }
+  const int n_proj = m.SearchByProjection(f2, f1, 15.0f, true);
+  int self = 0;
+  for (int j = 0; j < f2.N; j++) self += f2.mvpMapPoints[j] == &pts[j];
+  Frame f3;
+  fill(f3, ex, img);
+  std::vector<MapPoint*> local;
+  for (auto& p : pts) local.push_back(&p);
+  ORB_SLAM2::ORBmatcher m3(0.8f, true);
+  const int n_mp = m3.SearchByProjection(f3, local, 1.0f);
+  std::vector<MapPoint*> bow;
+  ORB_SLAM2::ORBmatcher mb(0.7f, true);
+  const int n_bow = mb.SearchByBoW(&f1, f3, bow);
+  std::vector<MapPoint*> bow2;
+  const int n_bow2 = mb.SearchByBoW(&f1, &f2, bow2);
+  const int d0 = ORB_SLAM2::ORBmatcher::DescriptorDistance(f1.mDescriptors.row(0), f1.mDescriptors.row(0));
+  const int d1 = ORB_SLAM2::ORBmatcher::DescriptorDistance(f1.mDescriptors.row(0), f1.mDescriptors.row(1));
+  std::printf("init %d proj %d self %d mappoints %d bow %d bowkf %d d0 %d d1 %d\n", n_init, n_proj, self, n_mp, n_bow,
+              n_bow2, d0, d1);
+  const bool ok = n_init > 50 && n_proj > f1.N / 2 && self > f1.N / 2 && n_mp > f1.N / 2 && n_bow > 20 && d0 == 0 && d1 > 0;
+  std::printf("%s\n", ok ? "HOST_WRAPPER_OK" : "HOST_WRAPPER_FAIL");
+  return ok ? 0 : 1;
+}
