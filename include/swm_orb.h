@@ -121,6 +121,8 @@ int swm_orb_run_stage(swm_orb* h, int stage_mask, int batch, void* stream);
 
 /* Parity introspection (host copies of intermediates of frame `frame` of the last batch).
  * which: 0 = bordered un-blurred plane ((w+38)x(h+38)), 1 = blurred ROI, 2 = FAST score map (w x h). */
+/* which = 2 needs swm_orb_set_debug(h, 1) before the first extract (the product keeps no score map). */
+int swm_orb_set_debug(swm_orb* h, int keep_score_map);
 int swm_orb_debug_plane(swm_orb* h, int frame, int level, int which, uint8_t* out, int out_stride);
 /* FAST candidates after tile-retry+NMS (which = 0; ROI coords; order unspecified) or quadtree
  * selection (which = 1; final list order).  xys: (x, y, score) int32 triples. Returns count or <0. */

@@ -29,25 +29,30 @@ __constant__ signed char c_pattern[1024];
 __constant__ int c_umax[16];
 
 // ------------------------------------------------------------------------------------------------
-// Level kernel: one CTA produces a 64x32 tile of level l (plus the mirrored border pixels that
-// reflect into it), its FAST score map and its blurred tile, from a shared-memory staging tile
-// with a 3-pixel halo.  Level 0 copies the input frame, levels >= 1 resize the un-blurred level l-1.
+// Pyramid kernel: one CTA produces a 64x32 tile of level l -- the un-blurred plane (plus the
+// mirrored border pixels that reflect into the tile) and the Gaussian-blurred plane.  Everything
+// is done on packed 32-bit words (4 pixels): level 0 copies the input frame; levels >= 1 stage the
+// needed window of level l-1 in shared memory and run cv::resize's separable fixed-point bilinear
+// (row pass once per SOURCE row, then the column pass).  The blur is column pass first on two
+// 16-bit lanes per register, then the row pass with IDP.2A dot products (exact: no intermediate
+// rounding in cv::GaussianBlur's 8-bit path, so pass order does not matter).
 // ------------------------------------------------------------------------------------------------
-constexpr int TW = 64, TH = 32, HALO = 3;
-constexpr int SW = TW + 2 * HALO, SH = TH + 2 * HALO, SP = 72;
+constexpr int TW = 64, TH = 32;
+constexpr int PS_WORDS = 18;            // staged words per row: x0-4 .. x0+67
+constexpr int PS_COLS = PS_WORDS * 4;   // 72
+constexpr int PS_ROWS = TH + 6;         // y0-3 .. y0+34
+constexpr int SRC_ROWS = 62, SRC_WORDS = 30;  // level l-1 window of one tile, scale factor <= 1.5 (checked on the host)
 
-struct LevelArgs {
+struct PyrArgs {
   LevelGeom dst, src;
   const uint8_t* img;
   int img_stride;
   long long img_frame_stride;
   uint8_t* plain;
   uint8_t* blur;
-  uint8_t* score;
   long long slab_bytes;
   const ResizeTap* xtab;
   const ResizeTap* ytab;
-  int min_th;
 };
 
 __device__ __forceinline__ void store4(uint8_t* row, int gx, int w, uint32_t word) {
@@ -60,62 +65,107 @@ __device__ __forceinline__ void store4(uint8_t* row, int gx, int w, uint32_t wor
 }
 
 template <bool kFirst>
-__global__ void __launch_bounds__(256) level_kernel(const LevelArgs a) {
-  __shared__ __align__(16) uint8_t s_px[SH * SP];
-  __shared__ __align__(16) uint16_t s_h[SH * TW];
+__global__ void __launch_bounds__(256) pyr_kernel(const PyrArgs a) {
+  __shared__ __align__(16) uint32_t s_px[PS_ROWS * PS_WORDS];
+  __shared__ __align__(16) uint32_t s_src[kFirst ? 1 : SRC_ROWS * SRC_WORDS];
+  __shared__ __align__(16) uint16_t s_h[kFirst ? 4 : SRC_ROWS * PS_COLS];
+  __shared__ __align__(16) uint2 s_v[TH * PS_WORDS];
+  __shared__ ResizeTap s_xt[kFirst ? 1 : PS_COLS];
+  __shared__ ResizeTap s_yt[kFirst ? 1 : PS_ROWS];
   const int tid = threadIdx.x;
   const int f = blockIdx.z;
   const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
   const int w = a.dst.w, h = a.dst.h;
   const long long fo = (long long)f * a.slab_bytes;
-
-  const uint8_t* src;
-  int spitch;
   if (kFirst) {
-    src = a.img + (long long)f * a.img_frame_stride;
-    spitch = a.img_stride;
+    // ---- level 0: copy the frame tile (+halo, reflect-101 at the image edge)
+    const uint8_t* src = a.img + (long long)f * a.img_frame_stride;
+    const bool aligned = ((reinterpret_cast<unsigned long long>(src) | (unsigned long long)a.img_stride) & 3ull) == 0;
+    for (int i = tid; i < PS_ROWS * PS_WORDS; i += 256) {
+      const int r = i / PS_WORDS, j = i - r * PS_WORDS;
+      const int gy = reflect101(min(y0 - 3 + r, h + 2), h);
+      const int gx = x0 - 4 + 4 * j;
+      const uint8_t* row = src + (long long)gy * a.img_stride;
+      uint32_t v;
+      if (aligned && gx >= 0 && gx + 3 < w) {
+        v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
+      } else {
+        v = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(row + reflect101(min(gx + k, w + 2), w)) << (8 * k);
+      }
+      s_px[i] = v;
+    }
   } else {
-    src = a.plain + fo + a.src.plane_off + (long long)kEdge * a.src.pitch + kPadX;
-    spitch = a.src.pitch;
-  }
-  const ResizeTap* __restrict__ xt = a.xtab + a.dst.xtab_off;
-  const ResizeTap* __restrict__ yt = a.ytab + a.dst.ytab_off;
-
-  // ---- stage the un-blurred tile (+halo, reflect-101 at the image edge) in shared memory
-  for (int i = tid; i < SH * SW; i += 256) {
-    const int ly = i / SW, lx = i - ly * SW;
-    const int gx = reflect101(x0 - HALO + lx, w), gy = reflect101(y0 - HALO + ly, h);
-    int v;
-    if (kFirst) v = __ldg(src + (long long)gy * spitch + gx);
-    else v = resize_fetch(src, spitch, a.src.w, a.src.h, xt[gx], yt[gy]);
-    s_px[ly * SP + lx] = (uint8_t)v;
+    // ---- levels >= 1: bilinear resize of the un-blurred level l-1 (cv::resize INTER_LINEAR 8U)
+    const uint8_t* src = a.plain + fo + a.src.plane_off + (long long)kEdge * a.src.pitch + kPadX;
+    const int spitch = a.src.pitch, sh = a.src.h;
+    const ResizeTap* __restrict__ xt = a.xtab + a.dst.xtab_off;
+    const ResizeTap* __restrict__ yt = a.ytab + a.dst.ytab_off;
+    // taps of the staged columns/rows (reflected destination coordinates), window of level l-1
+    const int dlo = max(0, x0 - 4), dhi = min(w - 1, x0 + PS_COLS - 5);
+    const int rlo = max(0, y0 - 3), rhi = min(h - 1, y0 + PS_ROWS - 4);
+    const int sx_base = xt[dlo].ofs & ~3;
+    const int sy_base = yt[rlo].ofs;
+    const int nwords = ((xt[dhi].ofs + 1 - sx_base) >> 2) + 1;
+    const int nrows = min(yt[rhi].ofs + 1, sh - 1) - sy_base + 1;
+    if (tid < PS_COLS) {
+      ResizeTap t = xt[reflect101(min(x0 - 4 + tid, w + 2), w)];
+      t.ofs = (int16_t)(t.ofs - sx_base);
+      s_xt[tid] = t;
+    } else if (tid >= 128 && tid < 128 + PS_ROWS) {
+      ResizeTap t = yt[reflect101(min(y0 - 3 + (tid - 128), h + 2), h)];
+      const int o0 = t.ofs - sy_base;
+      t.ofs = (int16_t)o0;
+      t.pad = (int16_t)min(o0 + 1, sh - 1 - sy_base);  // second source row, clamped like cv::resize
+      s_yt[tid - 128] = t;
+    }
+    for (int i = tid; i < nrows * nwords; i += 256) {
+      const int r = i / nwords, j = i - r * nwords;
+      s_src[r * SRC_WORDS + j] =
+          __ldg(reinterpret_cast<const uint32_t*>(src + (long long)(sy_base + r) * spitch + sx_base + 4 * j));
+    }
+    __syncthreads();
+    // row pass: one value per (source row, destination column), kept as (sum >> 4) in 16 bits
+    if (tid < 3 * PS_COLS) {
+      const int c = tid % PS_COLS, g = tid / PS_COLS;
+      const ResizeTap t = s_xt[c];
+      const uint8_t* sb = reinterpret_cast<const uint8_t*>(s_src) + t.ofs;
+      for (int r = g; r < nrows; r += 3) {
+        const uint8_t* p = sb + r * (SRC_WORDS * 4);
+        s_h[r * PS_COLS + c] = (uint16_t)((p[0] * t.a0 + p[1] * t.a1) >> 4);
+      }
+    }
+    __syncthreads();
+    // column pass, 4 pixels per item
+    for (int i = tid; i < PS_ROWS * PS_WORDS; i += 256) {
+      const int r = i / PS_WORDS, j = i - r * PS_WORDS;
+      const ResizeTap t = s_yt[r];
+      const uint2 h0 = *reinterpret_cast<const uint2*>(s_h + t.ofs * PS_COLS + 4 * j);
+      const uint2 h1 = *reinterpret_cast<const uint2*>(s_h + t.pad * PS_COLS + 4 * j);
+      const int b0 = t.a0, b1 = t.a1;
+      const uint32_t p0 = (((b0 * (int)(h0.x & 0xFFFF)) >> 16) + ((b1 * (int)(h1.x & 0xFFFF)) >> 16) + 2) >> 2;
+      const uint32_t p1 = (((b0 * (int)(h0.x >> 16)) >> 16) + ((b1 * (int)(h1.x >> 16)) >> 16) + 2) >> 2;
+      const uint32_t p2 = (((b0 * (int)(h0.y & 0xFFFF)) >> 16) + ((b1 * (int)(h1.y & 0xFFFF)) >> 16) + 2) >> 2;
+      const uint32_t p3 = (((b0 * (int)(h0.y >> 16)) >> 16) + ((b1 * (int)(h1.y >> 16)) >> 16) + 2) >> 2;
+      s_px[i] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
+    }
   }
   __syncthreads();
 
   const long long roi0 = fo + a.dst.plane_off + (long long)kEdge * a.dst.pitch + kPadX;
   uint8_t* dplain = a.plain + roi0;
-  uint8_t* dscore = a.score + roi0;
   uint8_t* dblur = a.blur + roi0;
   const int pitch = a.dst.pitch;
   const bool edge_tile = (x0 <= kEdge) || (x0 + TW >= w - 1 - kEdge) || (y0 <= kEdge) || (y0 + TH >= h - 1 - kEdge);
 
-  // ---- horizontal blur pass for all staged rows (row pass of cv::GaussianBlur, 8.8 fixed point)
-  for (int i = tid; i < SH * TW; i += 256) {
-    const int r = i / TW, c = i - r * TW;
-    const uint8_t* p = s_px + r * SP + c;
-    const int acc = 18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3];
-    s_h[i] = (uint16_t)acc;
-  }
-
-  // ---- un-blurred tile, border mirrors, FAST score
-  const int c4 = (tid & 15) * 4;
+  // ---- un-blurred tile and the border pixels that mirror into it
 #pragma unroll
   for (int pass = 0; pass < 2; pass++) {
-    const int r = (tid >> 4) + 16 * pass;
-    const int gy = y0 + r, gx = x0 + c4;
+    const int r = (tid >> 4) + 16 * pass, j = tid & 15;
+    const int gy = y0 + r, gx = x0 + 4 * j;
     if (gy < h && gx < w) {
-      const uint8_t* p = s_px + (r + HALO) * SP + c4 + HALO;
-      const uint32_t word = p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24);
+      const uint32_t word = s_px[(r + 3) * PS_WORDS + j + 1];
       store4(dplain + (long long)gy * pitch, gx, w, word);
       if (edge_tile) {
         // copyMakeBorder(BORDER_REFLECT_101, 19): every in-image pixel also lands at the border
@@ -133,118 +183,274 @@ __global__ void __launch_bounds__(256) level_kernel(const LevelArgs a) {
           if (x >= w - 1 - kEdge && x <= w - 2) xs[nx++] = 2 * (w - 1) - x;
           for (int iy = 0; iy < ny; iy++)
             for (int ix = 0; ix < nx; ix++)
-              if (ix | iy) dplain[(long long)ys[iy] * pitch + xs[ix]] = p[k];
+              if (ix | iy) dplain[(long long)ys[iy] * pitch + xs[ix]] = (uint8_t)(word >> (8 * k));
         }
       }
-      // FAST score at minThFAST on the band [19, w-19) x [19, h-19) (ORBextractor.cc:695-713 + 3 px ring)
-      uint32_t sword = 0;
-      if (gy >= kEdge && gy < h - kEdge) {
+    }
+  }
+
+  // ---- blur, column pass: thread = (word column, group of 4 output rows); two pixels per register
+  if (tid < PS_WORDS * 8) {
+    const int j = tid % PS_WORDS, g = tid / PS_WORDS;
+    uint32_t e[10], o[10];
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          const int x = gx + k;
-          if (x >= kEdge && x < w - kEdge) sword |= (uint32_t)fast_score(p + k, SP, a.min_th) << (8 * k);
-        }
-      }
-      store4(dscore + (long long)gy * pitch, gx, w, sword);
+    for (int k = 0; k < 10; k++) {
+      const uint32_t wv = s_px[(4 * g + k) * PS_WORDS + j];
+      e[k] = wv & 0x00FF00FFu;
+      o[k] = (wv >> 8) & 0x00FF00FFu;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint32_t ve = 18u * (e[i] + e[i + 6]) + 34u * (e[i + 1] + e[i + 5]) + 48u * (e[i + 2] + e[i + 4]) + 56u * e[i + 3];
+      const uint32_t vo = 18u * (o[i] + o[i + 6]) + 34u * (o[i + 1] + o[i + 5]) + 48u * (o[i + 2] + o[i + 4]) + 56u * o[i + 3];
+      // lanes: ve = (V0, V2), vo = (V1, V3) -> adjacent pairs (V0,V1), (V2,V3)
+      s_v[(4 * g + i) * PS_WORDS + j] = make_uint2(__byte_perm(ve, vo, 0x5410), __byte_perm(ve, vo, 0x7632));
     }
   }
   __syncthreads();
 
-  // ---- vertical blur pass (16.16 fixed point, round half up)
+  // ---- blur, row pass: 4 outputs per item from the pairs of words j-1, j, j+1
 #pragma unroll
   for (int pass = 0; pass < 2; pass++) {
-    const int r = (tid >> 4) + 16 * pass;
-    const int gy = y0 + r, gx = x0 + c4;
+    const int r = (tid >> 4) + 16 * pass, j = (tid & 15) + 1;
+    const int gy = y0 + r, gx = x0 + 4 * (j - 1);
     if (gy < h && gx < w) {
-      uint32_t word = 0;
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint16_t* q = s_h + r * TW + c4 + k;
-        const uint32_t acc = 18u * (q[0] + q[6 * TW]) + 34u * (q[TW] + q[5 * TW]) + 48u * (q[2 * TW] + q[4 * TW]) +
-                             56u * q[3 * TW];
-        word |= ((acc + 0x8000u) >> 16) << (8 * k);
-      }
+      const uint2 A = s_v[r * PS_WORDS + j - 1], Bm = s_v[r * PS_WORDS + j], Cn = s_v[r * PS_WORDS + j + 1];
+      // V index relative to the first pixel of word j: A = (-4,-3),(-2,-1); Bm = (0,1),(2,3); Cn = (4,5),(6,7)
+      const uint32_t m3m2 = __byte_perm(A.x, A.y, 0x5432);    // (-3,-2)
+      const uint32_t m1p0 = __byte_perm(A.y, Bm.x, 0x5432);   // (-1, 0)
+      const uint32_t p1p2 = __byte_perm(Bm.x, Bm.y, 0x5432);  // ( 1, 2)
+      const uint32_t p3p4 = __byte_perm(Bm.y, Cn.x, 0x5432);  // ( 3, 4)
+      const uint32_t p5p6 = __byte_perm(Cn.x, Cn.y, 0x5432);  // ( 5, 6)
+      const uint32_t k01 = 18u | (34u << 8), k23 = 48u | (56u << 8), k45 = 48u | (34u << 8), k6 = 18u;
+      uint32_t o0 = __dp2a_lo(m3m2, k01, 0x8000u);
+      o0 = __dp2a_lo(m1p0, k23, o0);
+      o0 = __dp2a_lo(p1p2, k45, o0);
+      o0 = __dp2a_lo(p3p4, k6, o0);
+      uint32_t o1 = __dp2a_lo(A.y, k01, 0x8000u);
+      o1 = __dp2a_lo(Bm.x, k23, o1);
+      o1 = __dp2a_lo(Bm.y, k45, o1);
+      o1 = __dp2a_lo(Cn.x, k6, o1);
+      uint32_t o2 = __dp2a_lo(m1p0, k01, 0x8000u);
+      o2 = __dp2a_lo(p1p2, k23, o2);
+      o2 = __dp2a_lo(p3p4, k45, o2);
+      o2 = __dp2a_lo(p5p6, k6, o2);
+      uint32_t o3 = __dp2a_lo(Bm.x, k01, 0x8000u);
+      o3 = __dp2a_lo(Bm.y, k23, o3);
+      o3 = __dp2a_lo(Cn.x, k45, o3);
+      o3 = __dp2a_lo(Cn.y, k6, o3);
+      const uint32_t word = (o0 >> 16) | ((o1 >> 16) << 8) | ((o2 >> 16) << 16) | ((o3 >> 16) << 24);
       store4(dblur + (long long)gy * pitch, gx, w, word);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tile retry + non-max suppression (Fast_gpu.cu:284-341), deterministic lock-step form:
-//   pass 1: keypoint iff S_hi(p) > S_hi(q) for the 8 neighbours; a tile without any pass-1
-//           keypoint is flagged for retry;
-//   pass 2 (retry tiles only): keypoint iff S(p) > S_eff(q), S_eff = S in retried tiles, S_hi elsewhere.
-// Survivors are appended (unordered) to the per-(frame, level) candidate list; everything downstream
-// orders by explicit keys, so the append order does not matter.
+// FAST kernel (Fast_gpu.cu:284-341, deterministic lock-step form).  One CTA = two horizontally
+// adjacent 32x32 FAST tiles of one level, anchored on the reference's tile grid (level pixel
+// (19,19)).  The tile (+4 px halo) is staged as words; a packed-byte test of the four opposite
+// ring pairs rejects most pixels 4 at a time (exact: every 9-arc contains one pixel of each pair);
+// survivors are compacted into a shared list, scored (largest threshold at which the pixel is
+// still a corner) and non-max suppressed against the shared score tile.
+//   pass 1: keypoint iff S_hi(p) > S_hi(q) for the 8 neighbours; a tile with no pass-1 keypoint
+//           is flagged for retry;
+//   pass 2 (blocks with a retry tile): keypoint iff S(p) > S_eff(q), S_eff = S in retried tiles,
+//           S_hi elsewhere.  Scores are recomputed, no score map is kept in HBM (debug builds of
+//           the tests can ask for one).
+// Survivors are appended (unordered) to the per-(frame, level) candidate list; everything
+// downstream orders by explicit keys, so the append order does not matter.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) nms_kernel(const FrameLayout* __restrict__ L, const uint8_t* __restrict__ score,
-                                                  int ini_th, int pass, uint8_t* __restrict__ retry,
-                                                  uint32_t* __restrict__ cand, int* __restrict__ cand_count) {
-  __shared__ uint8_t s[34][36];
-  __shared__ int s_any;
-  __shared__ uint8_t s_flag[9];
-  const int tid = threadIdx.x;
+constexpr int FS_WORDS = 19, FS_COLS = FS_WORDS * 4, FS_ROWS = TH + 8;  // staged 76 x 40 bytes
+constexpr int FS_MAXCAND = 66 * 34;
+
+__device__ __forceinline__ uint32_t oob_mask(uint32_t a, uint32_t v, uint32_t c7) {
+  // bit 7 of each byte set iff |a - v| > th, with c7 = (127 - th) * 0x01010101
+  const uint32_t ad = __vabsdiffu4(a, v);
+  return (((ad & 0x7F7F7F7Fu) + c7) | ad) & 0x80808080u;
+}
+
+__global__ void __launch_bounds__(256) fast_kernel(const FrameLayout* __restrict__ L, const uint8_t* __restrict__ plain,
+                                                   int ini_th, int min_th, int pass, uint8_t* __restrict__ retry,
+                                                   uint32_t* __restrict__ cand, int* __restrict__ cand_count,
+                                                   uint8_t* __restrict__ dbg_score) {
+  __shared__ __align__(16) uint32_t s_px[FS_ROWS * FS_WORDS];
+  __shared__ __align__(16) uint32_t s_sc[FS_ROWS * FS_WORDS];
+  __shared__ uint16_t s_list[FS_MAXCAND + 2];
+  __shared__ int s_warp[8];
+  __shared__ int s_total;
+  __shared__ int s_any[2];
+  __shared__ uint8_t s_flag[12];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int f = blockIdx.y;
-  const int t = blockIdx.x;
   int lvl = 0;
-  while (lvl + 1 < L->nlevels && t >= L->lv[lvl + 1].tile_off) lvl++;
+  while (lvl + 1 < L->nlevels && (int)blockIdx.x >= L->lv[lvl + 1].fblk_off) lvl++;
   const LevelGeom& g = L->lv[lvl];
-  uint8_t* fretry = retry + (long long)f * L->tiles_total;
-  if (pass == 2 && !fretry[t]) return;
-  const int tl = t - g.tile_off;
-  const int by = tl / g.tiles_x, bx = tl - by * g.tiles_x;
-  if (tid == 0) s_any = 0;
-  if (pass == 2 && tid < 9) {
-    const int ny = by + tid / 3 - 1, nx = bx + tid % 3 - 1;
-    s_flag[tid] = (ny >= 0 && ny < g.tiles_y && nx >= 0 && nx < g.tiles_x) ? fretry[g.tile_off + ny * g.tiles_x + nx] : 0;
-  }
-  __syncthreads();
-  const uint8_t* sc = score + (long long)f * L->slab_bytes + g.plane_off + (long long)kEdge * g.pitch + kPadX;
-  const int ox = kEdge + 32 * bx - 1, oy = kEdge + 32 * by - 1;  // level coords of s[0][0]
-  for (int i = tid; i < 34 * 34; i += 256) {
-    const int ly = i / 34, lx = i - ly * 34;
-    const int gx = ox + lx, gy = oy + ly;
-    int v = (gx < g.w && gy < g.h) ? sc[(long long)gy * g.pitch + gx] : 0;
-    bool raw = false;
-    if (pass == 2) {
-      const int fy = ly == 0 ? 0 : (ly == 33 ? 2 : 1), fx = lx == 0 ? 0 : (lx == 33 ? 2 : 1);
-      raw = s_flag[fy * 3 + fx] != 0;
+  const int bl = blockIdx.x - g.fblk_off;
+  const int by = bl / g.fblk_x, bx = bl - by * g.fblk_x;
+  uint8_t* fretry = retry + (long long)f * L->tiles_total + g.tile_off;
+  const int t0 = by * g.tiles_x + 2 * bx;           // first of the two tiles of this block
+  const bool has_t1 = 2 * bx + 1 < g.tiles_x;
+  if (pass == 2) {
+    if (!(fretry[t0] || (has_t1 && fretry[t0 + 1]))) return;
+    if (tid < 12) {
+      const int ny = by + tid / 4 - 1, nx = 2 * bx + (tid & 3) - 1;
+      s_flag[tid] = (ny >= 0 && ny < g.tiles_y && nx >= 0 && nx < g.tiles_x) ? fretry[ny * g.tiles_x + nx] : 0;
     }
-    if (!raw && v < ini_th) v = 0;
-    s[ly][lx] = (uint8_t)v;
+  }
+  if (tid < 2) s_any[tid] = 0;
+  const int w = g.w, h = g.h;
+  const int X0 = kEdge + 64 * bx, Y0 = kEdge + 32 * by;  // first interior pixel (level coords)
+  const int sx0 = X0 - 7, sy0 = Y0 - 4;                  // staged origin; sx0 = 12 + 64 bx is 4-aligned
+  const uint8_t* roi = plain + (long long)f * L->slab_bytes + g.plane_off + (long long)kEdge * g.pitch + kPadX;
+  uint8_t* s_scb = reinterpret_cast<uint8_t*>(s_sc);
+  const uint8_t* s_pxb = reinterpret_cast<const uint8_t*>(s_px);
+
+  for (int i = tid; i < FS_ROWS * FS_WORDS; i += 256) {
+    const int r = i / FS_WORDS, j = i - r * FS_WORDS;
+    const int gy = sy0 + r, gx = sx0 + 4 * j;
+    uint32_t v = 0;
+    if (gy < h + kEdge && gx < w + kEdge - 3) v = __ldg(reinterpret_cast<const uint32_t*>(roi + (long long)gy * g.pitch + gx));
+    s_px[i] = v;
+    s_sc[i] = 0;
   }
   __syncthreads();
-  const int lx = (tid & 31) + 1;
-  const int lane = tid & 31;
-  bool any = false;
+
+  // ---- packed quick reject on the scored region (interior + 1 px): rows ly 3..36, words 1..17
+  const uint32_t c7 = (uint32_t)(127 - min_th) * 0x01010101u;
+  uint32_t masks[3];
+  int n_mine = 0;
 #pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const int ly = (tid >> 5) * 4 + k + 1;
-    const int c = s[ly][lx];
-    bool kp = c > 0;
-    if (kp) {
-      kp = c > s[ly - 1][lx - 1] && c > s[ly - 1][lx] && c > s[ly - 1][lx + 1] && c > s[ly][lx - 1] &&
-           c > s[ly][lx + 1] && c > s[ly + 1][lx - 1] && c > s[ly + 1][lx] && c > s[ly + 1][lx + 1];
+  for (int it = 0; it < 3; it++) {
+    const int i = tid + 256 * it;
+    uint32_t m = 0;
+    if (i < 34 * 17) {
+      const int r = i / 17, ly = r + 3, jw = i - r * 17 + 1;
+      const int gy = sy0 + ly;
+      if (gy >= kEdge && gy < h - kEdge) {
+        const uint32_t* row = s_px + ly * FS_WORDS + jw;
+        const uint32_t v = row[0];
+        m = oob_mask(row[-3 * FS_WORDS], v, c7) | oob_mask(row[3 * FS_WORDS], v, c7);
+        if (m) m &= oob_mask(__funnelshift_r(row[0], row[1], 24), v, c7) | oob_mask(__funnelshift_r(row[-1], row[0], 8), v, c7);
+        if (m) {
+          const uint32_t* rp = row + 2 * FS_WORDS;
+          const uint32_t* rm = row - 2 * FS_WORDS;
+          m &= oob_mask(__funnelshift_r(rp[0], rp[1], 16), v, c7) | oob_mask(__funnelshift_r(rm[-1], rm[0], 16), v, c7);
+          if (m) m &= oob_mask(__funnelshift_r(rm[0], rm[1], 16), v, c7) | oob_mask(__funnelshift_r(rp[-1], rp[0], 16), v, c7);
+        }
+        if (m) {  // keep pixels inside the scored columns and the valid FAST band [19, w-19)
+          const int gx = sx0 + 4 * jw;
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const int x = gx + k, lx = 4 * jw + k;
+            if (lx < 6 || lx > 71 || x < kEdge || x >= w - kEdge) m &= ~(0x80u << (8 * k));
+          }
+        }
+      }
+    }
+    masks[it] = m;
+    n_mine += __popc(m);
+  }
+  // block-wide exclusive scan of the per-thread candidate counts
+  int incl = n_mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int k = 0; k < 8; k++) {
+      const int v = s_warp[k];
+      s_warp[k] = run;
+      run += v;
+    }
+    s_total = run;
+  }
+  __syncthreads();
+  int pos = s_warp[wid] + incl - n_mine;
+#pragma unroll
+  for (int it = 0; it < 3; it++) {
+    const uint32_t m = masks[it];
+    if (m) {
+      const int i = tid + 256 * it;
+      const int r = i / 17, ly = r + 3, jw = i - r * 17 + 1;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (m & (0x80u << (8 * k))) s_list[pos++] = (uint16_t)((ly << 7) | (4 * jw + k));
+    }
+  }
+  __syncthreads();
+  const int n_cand = s_total;
+
+  // ---- score the survivors
+  for (int i = tid; i < n_cand; i += 256) {
+    const int e = s_list[i], ly = e >> 7, lx = e & 127;
+    s_scb[ly * FS_COLS + lx] = (uint8_t)fast_score(s_pxb + ly * FS_COLS + lx, FS_COLS, min_th);
+  }
+  __syncthreads();
+
+  // ---- non-max suppression of interior candidates
+  for (int i0 = 0; i0 < n_cand; i0 += 256) {
+    const int i = i0 + tid;
+    bool kp = false;
+    int lx = 0, ly = 0, c = 0;
+    if (i < n_cand) {
+      const int e = s_list[i];
+      ly = e >> 7;
+      lx = e & 127;
+      c = s_scb[ly * FS_COLS + lx];
+      const bool interior = lx >= 7 && lx <= 70 && ly >= 4 && ly <= 35;
+      const int tile = lx >= 39 ? 1 : 0;
+      if (pass == 1) kp = interior && c >= ini_th;
+      else kp = interior && c > 0 && s_flag[4 + 1 + tile] != 0;
+      if (kp) {
+#pragma unroll
+        for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+          for (int dx = -1; dx <= 1; dx++) {
+            if (dx == 0 && dy == 0) continue;
+            const int qx = lx + dx, qy = ly + dy;
+            int q = s_scb[qy * FS_COLS + qx];
+            bool raw = false;
+            if (pass == 2) {
+              const int fy = qy < 4 ? 0 : (qy > 35 ? 2 : 1);
+              const int fx = qx < 7 ? 0 : (qx < 39 ? 1 : (qx < 71 ? 2 : 3));
+              raw = s_flag[fy * 4 + fx] != 0;
+            }
+            if (!raw && q < ini_th) q = 0;
+            kp = kp && c > q;
+          }
+      }
+      if (kp && pass == 1) s_any[tile] = 1;
     }
     const unsigned m = __ballot_sync(0xffffffffu, kp);
     if (m) {
-      any = true;
       int base = 0;
       if (lane == 0) base = atomicAdd(cand_count + f * L->nlevels + lvl, __popc(m));
       base = __shfl_sync(0xffffffffu, base, 0);
       if (kp) {
         const int idx = base + __popc(m & ((1u << lane) - 1));
-        if (idx < g.cand_cap) {
-          const int gx = ox + lx, gy = oy + ly;
-          cand[(long long)f * L->cand_total + g.cand_off + idx] = pack_pt(gx - kBand, gy - kBand, c);
-        }
+        if (idx < g.cand_cap)
+          cand[(long long)f * L->cand_total + g.cand_off + idx] = pack_pt(sx0 + lx - kBand, sy0 + ly - kBand, c);
       }
     }
   }
   if (pass == 1) {
-    if (any && lane == 0) s_any = 1;
     __syncthreads();
-    if (tid == 0) fretry[t] = s_any ? 0 : 1;
+    if (tid == 0) {
+      fretry[t0] = s_any[0] ? 0 : 1;
+      if (has_t1) fretry[t0 + 1] = s_any[1] ? 0 : 1;
+    }
+    if (dbg_score) {  // parity introspection only: the score map S at minThFAST for the block interior
+      uint8_t* sc = dbg_score + (long long)f * L->slab_bytes + g.plane_off + (long long)kEdge * g.pitch + kPadX;
+      for (int i = tid; i < 64 * 32; i += 256) {
+        const int ly = (i >> 6) + 4, lx = (i & 63) + 7;
+        const int gx = sx0 + lx, gy = sy0 + ly;
+        if (gx < w - kEdge && gy < h - kEdge) sc[(long long)gy * g.pitch + gx] = s_scb[ly * FS_COLS + lx];
+      }
+    }
   }
 }
 
@@ -469,6 +675,7 @@ struct swm_orb {
   int32_t* d_n = nullptr;
   int last_batch = 0;
   int last_launches = 0;
+  bool debug_score = false;  // keep a FAST score map in HBM for parity tests (swm_orb_set_debug)
   // last input (for swm_orb_run_stage)
   const uint8_t* last_img = nullptr;
   int last_stride = 0;
@@ -530,7 +737,7 @@ int setup_geometry(swm_orb* h, int w, int hh) {
   L.h = hh;
   std::vector<ResizeTap> xt, yt;
   long long off = 0;
-  int tile_off = 0, cand_off = 0, sel_off = 0;
+  int tile_off = 0, cand_off = 0, sel_off = 0, fblk_off = 0;
   for (int l = 0; l < nl; l++) {
     LevelGeom& g = L.lv[l];
     g.w = cv_round_f((float)w * h->inv_sf[l]);
@@ -554,10 +761,25 @@ int setup_geometry(swm_orb* h, int w, int hh) {
       build_taps(L.lv[l - 1].w, g.w, xt, true);
       build_taps(L.lv[l - 1].h, g.h, yt, false);
     }
+    if (l > 0) {  // the source window of every 64x32 tile must fit the kernel's shared-memory staging
+      const ResizeTap* xt0 = xt.data() + g.xtab_off;
+      const ResizeTap* yt0 = yt.data() + g.ytab_off;
+      for (int x0 = 0; x0 < g.w; x0 += TW) {
+        const int dlo = std::max(0, x0 - 4), dhi = std::min(g.w - 1, x0 + PS_COLS - 5);
+        if (((xt0[dhi].ofs + 1 - (xt0[dlo].ofs & ~3)) >> 2) + 1 > SRC_WORDS) { h->err = "scale factor too large for the pyramid tile"; return SWM_E_INVALID; }
+      }
+      for (int y0 = 0; y0 < g.h; y0 += TH) {
+        const int rlo = std::max(0, y0 - 3), rhi = std::min(g.h - 1, y0 + PS_ROWS - 4);
+        if (yt0[rhi].ofs + 2 - yt0[rlo].ofs > SRC_ROWS) { h->err = "scale factor too large for the pyramid tile"; return SWM_E_INVALID; }
+      }
+    }
     g.tiles_x = (g.w - 2 * kEdge + 31) / 32;
     g.tiles_y = (g.h - 2 * kEdge + 31) / 32;
     g.tile_off = tile_off;
     tile_off += g.tiles_x * g.tiles_y;
+    g.fblk_x = (g.tiles_x + 1) / 2;
+    g.fblk_off = fblk_off;
+    fblk_off += g.fblk_x * g.tiles_y;
     // strict 8-neighbour maxima cannot be adjacent: at most one per 2x2 block
     g.cand_cap = ((g.w - 2 * kEdge + 1) / 2 + 1) * ((g.h - 2 * kEdge + 1) / 2 + 1);
     g.cand_off = cand_off;
@@ -572,6 +794,7 @@ int setup_geometry(swm_orb* h, int w, int hh) {
   if (xt.empty()) { xt.push_back(ResizeTap{0, 2048, 0, 0}); yt.push_back(ResizeTap{0, 2048, 0, 0}); }
   L.slab_bytes = off;
   L.tiles_total = tile_off;
+  L.fblk_total = fblk_off;
   L.cand_total = cand_off;
   L.sel_total = sel_off;
   int maxkp = 0;
@@ -585,7 +808,7 @@ int setup_geometry(swm_orb* h, int w, int hh) {
   SWM_CK(h, cudaMalloc(&h->d_ytab, yt.size() * sizeof(ResizeTap)));
   SWM_CK(h, cudaMalloc(&h->d_plain, (size_t)L.slab_bytes * B));
   SWM_CK(h, cudaMalloc(&h->d_blur, (size_t)L.slab_bytes * B));
-  SWM_CK(h, cudaMalloc(&h->d_score, (size_t)L.slab_bytes * B));
+  if (h->debug_score) SWM_CK(h, cudaMalloc(&h->d_score, (size_t)L.slab_bytes * B));
   SWM_CK(h, cudaMalloc(&h->d_retry, (size_t)L.tiles_total * B));
   SWM_CK(h, cudaMalloc(&h->d_cand, (size_t)L.cand_total * B * sizeof(uint32_t)));
   SWM_CK(h, cudaMalloc(&h->d_sel, (size_t)L.sel_total * B * sizeof(uint32_t)));
@@ -601,7 +824,7 @@ int setup_geometry(swm_orb* h, int w, int hh) {
   // planes start zeroed so padding bytes are deterministic
   SWM_CK(h, cudaMemset(h->d_plain, 0, (size_t)L.slab_bytes * B));
   SWM_CK(h, cudaMemset(h->d_blur, 0, (size_t)L.slab_bytes * B));
-  SWM_CK(h, cudaMemset(h->d_score, 0, (size_t)L.slab_bytes * B));
+  if (h->debug_score) SWM_CK(h, cudaMemset(h->d_score, 0, (size_t)L.slab_bytes * B));
   h->allocated = true;
   return SWM_OK;
 }
@@ -618,7 +841,7 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
   int* d_sel_count = h->d_counts + (size_t)h->cfg.max_batch * nl;
   if (mask & SWM_STAGE_PYRAMID) {
     for (int l = 0; l < nl; l++) {
-      LevelArgs a;
+      PyrArgs a;
       a.dst = L.lv[l];
       a.src = L.lv[l ? l - 1 : 0];
       a.img = d_imgs;
@@ -626,22 +849,23 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
       a.img_frame_stride = frame_stride;
       a.plain = h->d_plain;
       a.blur = h->d_blur;
-      a.score = h->d_score;
       a.slab_bytes = L.slab_bytes;
       a.xtab = h->d_xtab;
       a.ytab = h->d_ytab;
-      a.min_th = h->cfg.min_th_fast;
       dim3 grid((a.dst.w + TW - 1) / TW, (a.dst.h + TH - 1) / TH, batch);
-      if (l == 0) level_kernel<true><<<grid, 256, 0, st>>>(a);
-      else level_kernel<false><<<grid, 256, 0, st>>>(a);
+      if (l == 0) pyr_kernel<true><<<grid, 256, 0, st>>>(a);
+      else pyr_kernel<false><<<grid, 256, 0, st>>>(a);
       launches++;
     }
   }
   if (mask & SWM_STAGE_NMS) {
     SWM_CK(h, cudaMemsetAsync(h->d_counts, 0, (size_t)2 * h->cfg.max_batch * nl * sizeof(int), st));
-    dim3 grid(L.tiles_total, batch);
-    nms_kernel<<<grid, 256, 0, st>>>(h->d_lay, h->d_score, h->cfg.ini_th_fast, 1, h->d_retry, h->d_cand, d_cand_count);
-    nms_kernel<<<grid, 256, 0, st>>>(h->d_lay, h->d_score, h->cfg.ini_th_fast, 2, h->d_retry, h->d_cand, d_cand_count);
+    dim3 grid(L.fblk_total, batch);
+    uint8_t* dbg = h->debug_score ? h->d_score : nullptr;
+    fast_kernel<<<grid, 256, 0, st>>>(h->d_lay, h->d_plain, h->cfg.ini_th_fast, h->cfg.min_th_fast, 1, h->d_retry,
+                                      h->d_cand, d_cand_count, dbg);
+    fast_kernel<<<grid, 256, 0, st>>>(h->d_lay, h->d_plain, h->cfg.ini_th_fast, h->cfg.min_th_fast, 2, h->d_retry,
+                                      h->d_cand, d_cand_count, nullptr);
     launches += 2;
   }
   if (mask & SWM_STAGE_OCTREE) {
@@ -672,7 +896,8 @@ int swm_orb_create(const swm_orb_cfg* cfg, int device, swm_orb** out) {
   if (!cfg || !out) return SWM_E_INVALID;
   *out = nullptr;
   if (cfg->nfeatures <= 0 || cfg->nlevels < 1 || cfg->nlevels > SWM_MAX_LEVELS || !(cfg->scale_factor > 1.0f) ||
-      cfg->min_th_fast < 1 || cfg->ini_th_fast < cfg->min_th_fast || cfg->ini_th_fast > 254 || cfg->max_batch < 1) {
+      cfg->scale_factor > 1.5f || cfg->min_th_fast < 1 || cfg->min_th_fast > 126 ||
+      cfg->ini_th_fast < cfg->min_th_fast || cfg->ini_th_fast > 254 || cfg->max_batch < 1) {
     g_create_error = "invalid swm_orb_cfg";
     return SWM_E_INVALID;
   }
@@ -916,6 +1141,13 @@ int swm_orb_max_keypoints(const swm_orb* h) {
 
 int swm_orb_last_launches(const swm_orb* h) { return h ? h->last_launches : SWM_E_INVALID; }
 
+int swm_orb_set_debug(swm_orb* h, int keep_score_map) {
+  if (!h) return SWM_E_INVALID;
+  if (h->allocated) { h->err = "set_debug must precede the first extract"; return SWM_E_STATE; }
+  h->debug_score = keep_score_map != 0;
+  return SWM_OK;
+}
+
 int swm_orb_debug_plane(swm_orb* h, int frame, int level, int which, uint8_t* out, int out_stride) {
   if (!h || !out) return SWM_E_INVALID;
   if (!h->allocated) { h->err = "debug_plane before extract"; return SWM_E_STATE; }
@@ -928,6 +1160,7 @@ int swm_orb_debug_plane(swm_orb* h, int frame, int level, int which, uint8_t* ou
     SWM_CK(h, cudaMemcpy2D(out, out_stride, h->d_plain + fo + (kPadX - kEdge), g.pitch, g.w + 2 * kEdge, g.rows,
                            cudaMemcpyDeviceToHost));
   } else if (which == 1 || which == 2) {
+    if (which == 2 && !h->d_score) { h->err = "score map not kept: call swm_orb_set_debug(h, 1) before the first extract"; return SWM_E_STATE; }
     const uint8_t* base = which == 1 ? h->d_blur : h->d_score;
     SWM_CK(h, cudaMemcpy2D(out, out_stride, base + fo + (size_t)kEdge * g.pitch + kPadX, g.pitch, g.w, g.h,
                            cudaMemcpyDeviceToHost));

@@ -21,6 +21,7 @@ struct LevelGeom {
   int xtab_off, ytab_off;  // offsets into the resize tap tables (levels >= 1)
   int tiles_x, tiles_y;    // 32x32 FAST tiles (Fast_gpu.cu:374-375)
   int tile_off;            // offset of this level's tiles in the per-frame retry-flag array
+  int fblk_x, fblk_off;    // FAST kernel blocks (two tiles wide) per row / offset of this level in the grid
   int cand_off, cand_cap;  // per-frame candidate array slice (FAST survivors, pre-quadtree)
   int sel_off, sel_cap;    // per-frame selection slice (post-quadtree)
   int quota;               // mnFeaturesPerLevel[level]
@@ -33,6 +34,7 @@ struct FrameLayout {
   int w, h;
   long long slab_bytes;  // bytes per frame of one plane set
   int tiles_total;       // FAST tiles per frame (all levels)
+  int fblk_total;        // FAST kernel blocks per frame (all levels)
   int cand_total;        // candidate slots per frame
   int sel_total;         // selection slots per frame
   LevelGeom lv[SWM_MAX_LEVELS];

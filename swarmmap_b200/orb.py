@@ -22,7 +22,7 @@ class ORBextractor:
     HARRIS_SCORE, FAST_SCORE = 0, 1  # ORBextractor.h:52
 
     def __init__(self, nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST, device=0, max_batch=1,
-                 max_fast_per_level=0):
+                 max_fast_per_level=0, debug_score=False):
         self._lib = _lib.load()
         self.nfeatures, self.scaleFactor, self.nlevels = int(nfeatures), float(scaleFactor), int(nlevels)
         self.iniThFAST, self.minThFAST = int(iniThFAST), int(minThFAST)
@@ -33,6 +33,8 @@ class ORBextractor:
         rc = self._lib.swm_orb_create(C.byref(cfg), self.device, C.byref(h))
         check(rc, None, "swm_orb_create")
         self._h = h
+        if debug_score:
+            check(self._lib.swm_orb_set_debug(h, 1), h, "swm_orb_set_debug")
         n = self.nlevels
         self.mvScaleFactor = np.zeros(n, np.float32)
         self.mvInvScaleFactor = np.zeros(n, np.float32)

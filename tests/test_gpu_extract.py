@@ -16,7 +16,7 @@ DESC_BIT_FRACTION = 0.999
 
 def _extractors(oracle, nfeatures, max_batch=1, **kw):
     from swarmmap_b200.orb import ORBextractor
-    gpu = ORBextractor(nfeatures, 1.2, 8, 20, 7, max_batch=max_batch, **kw)
+    gpu = ORBextractor(nfeatures, 1.2, 8, 20, 7, max_batch=max_batch, debug_score=True, **kw)
     cpu = oracle.Extractor(nfeatures, 1.2, 8, 20, 7)
     return gpu, cpu
 

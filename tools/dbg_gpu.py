@@ -4,7 +4,7 @@ import numpy as np
 import oracle_lib as o
 from swarmmap_b200 import synth
 from swarmmap_b200.orb import ORBextractor
-g = ORBextractor(1000, 1.2, 8, 20, 7)
+g = ORBextractor(1000, 1.2, 8, 20, 7, debug_score=True)
 c = o.Extractor(1000)
 img = synth.make_frame()
 k, d = g(img)
