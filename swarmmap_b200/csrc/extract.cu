@@ -269,152 +269,225 @@ __device__ __forceinline__ uint32_t oob_mask(uint32_t a, uint32_t v, uint32_t c7
   return (((ad & 0x7F7F7F7Fu) + c7) | ad) & 0x80808080u;
 }
 
-__global__ void __launch_bounds__(256) fast_kernel(const FrameLayout* __restrict__ L, const uint8_t* __restrict__ plain,
-                                                   int ini_th, int min_th, int pass, uint8_t* __restrict__ retry,
-                                                   uint32_t* __restrict__ cand, int* __restrict__ cand_count,
-                                                   uint8_t* __restrict__ dbg_score) {
+// FAST score on two 16-bit lanes per register: lane 0 = bright ring max(r - v, 0), lane 1 = dark ring
+// max(v - r, 0); sliding 9-minimum by doubling with VIMNMX(3).U16x2, maximum over the 16 arcs.
+// Same value as swm::fast_score (swm_core.cuh) without its early-outs; checked bit-exact on the device
+// by the parity tests (the ptxas negated-max hazard does not apply: nothing is negated after a min/max).
+__device__ __forceinline__ int fast_score_x2(const uint8_t* c, int pitch, int th) {
+  const int v = c[0];
+  const uint32_t nv = ((uint32_t)(-v) & 0xFFFFu) | ((uint32_t)v << 16);  // (-v, +v)
+  uint32_t d[16];
+#define SWM_RING(k, off) d[k] = __viaddmax_s16x2((uint32_t)c[off] * 0xFFFF0001u, nv, 0u)  // (r,-r)+(-v,v), clamp 0
+  SWM_RING(0, 3 * pitch);      SWM_RING(1, 3 * pitch + 1);   SWM_RING(2, 2 * pitch + 2);   SWM_RING(3, pitch + 3);
+  SWM_RING(4, 3);              SWM_RING(5, -pitch + 3);      SWM_RING(6, -2 * pitch + 2);  SWM_RING(7, -3 * pitch + 1);
+  SWM_RING(8, -3 * pitch);     SWM_RING(9, -3 * pitch - 1);  SWM_RING(10, -2 * pitch - 2); SWM_RING(11, -pitch - 3);
+  SWM_RING(12, -3);            SWM_RING(13, pitch - 3);      SWM_RING(14, 2 * pitch - 2);  SWM_RING(15, 3 * pitch - 1);
+#undef SWM_RING
+  uint32_t p2[16], p4[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) p2[k] = __vminu2(d[k], d[(k + 1) & 15]);
+#pragma unroll
+  for (int k = 0; k < 16; k++) p4[k] = __vminu2(p2[k], p2[(k + 2) & 15]);
+  uint32_t best = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    const uint32_t m0 = __vimin3_u16x2(p4[k], p4[(k + 4) & 15], d[(k + 8) & 15]);
+    const uint32_t m1 = __vimin3_u16x2(p4[k + 1], p4[(k + 5) & 15], d[(k + 9) & 15]);
+    best = __vimax3_u16x2(best, m0, m1);
+  }
+  const int b = max((int)(best & 0xFFFFu), (int)(best >> 16));
+  return b > th ? b - 1 : 0;
+}
+
+__global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restrict__ L, const uint8_t* __restrict__ plain,
+                                                      int ini_th, int min_th, int pass, uint8_t* __restrict__ retry,
+                                                      int* __restrict__ retry_list, uint32_t* __restrict__ cand,
+                                                      int* __restrict__ cand_count, uint8_t* __restrict__ dbg_score) {
   __shared__ __align__(16) uint32_t s_px[FS_ROWS * FS_WORDS];
   __shared__ __align__(16) uint32_t s_sc[FS_ROWS * FS_WORDS];
   __shared__ uint16_t s_list[FS_MAXCAND + 2];
+  __shared__ uint16_t s_list2[TW * TH + 2];
+  __shared__ uint32_t s_colmask[FS_WORDS];
   __shared__ int s_warp[8];
-  __shared__ int s_total;
+  __shared__ int s_total, s_n2, s_blk;
   __shared__ int s_any[2];
   __shared__ uint8_t s_flag[12];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int f = blockIdx.y;
-  int lvl = 0;
-  while (lvl + 1 < L->nlevels && (int)blockIdx.x >= L->lv[lvl + 1].fblk_off) lvl++;
-  const LevelGeom& g = L->lv[lvl];
-  const int bl = blockIdx.x - g.fblk_off;
-  const int by = bl / g.fblk_x, bx = bl - by * g.fblk_x;
-  uint8_t* fretry = retry + (long long)f * L->tiles_total + g.tile_off;
-  const int t0 = by * g.tiles_x + 2 * bx;           // first of the two tiles of this block
-  const bool has_t1 = 2 * bx + 1 < g.tiles_x;
-  if (pass == 2) {
-    if (!(fretry[t0] || (has_t1 && fretry[t0 + 1]))) return;
-    if (tid < 12) {
+  const int nblk = L->fblk_total;
+  // pass 1: one block per (frame, tile pair).  pass 2: a persistent grid walks the list of blocks that
+  // hold a retry tile (appended by pass 1), so the common "nothing to retry" case costs almost nothing.
+  for (int work = blockIdx.x;; work += gridDim.x) {
+    int fb;
+    if (pass == 1) {
+      if (work != (int)blockIdx.x) break;
+      fb = blockIdx.y * nblk + blockIdx.x;
+    } else {
+      __syncthreads();
+      if (tid == 0) s_blk = work < retry_list[0] ? retry_list[1 + work] : -1;
+      __syncthreads();
+      fb = s_blk;
+      if (fb < 0) break;
+    }
+    const int f = fb / nblk, blk = fb - f * nblk;
+    int lvl = 0;
+    while (lvl + 1 < L->nlevels && blk >= L->lv[lvl + 1].fblk_off) lvl++;
+    const LevelGeom& g = L->lv[lvl];
+    const int bl = blk - g.fblk_off;
+    const int by = bl / g.fblk_x, bx = bl - by * g.fblk_x;
+    uint8_t* fretry = retry + (long long)f * L->tiles_total + g.tile_off;
+    const int t0 = by * g.tiles_x + 2 * bx;  // first of the two tiles of this block
+    const bool has_t1 = 2 * bx + 1 < g.tiles_x;
+    const int w = g.w, h = g.h;
+    const int X0 = kEdge + 64 * bx, Y0 = kEdge + 32 * by;  // first interior pixel (level coords)
+    const int sx0 = X0 - 7, sy0 = Y0 - 4;                  // staged origin; sx0 = 12 + 64 bx is 4-aligned
+    if (pass == 2 && tid < 12) {
       const int ny = by + tid / 4 - 1, nx = 2 * bx + (tid & 3) - 1;
       s_flag[tid] = (ny >= 0 && ny < g.tiles_y && nx >= 0 && nx < g.tiles_x) ? fretry[ny * g.tiles_x + nx] : 0;
     }
-  }
-  if (tid < 2) s_any[tid] = 0;
-  const int w = g.w, h = g.h;
-  const int X0 = kEdge + 64 * bx, Y0 = kEdge + 32 * by;  // first interior pixel (level coords)
-  const int sx0 = X0 - 7, sy0 = Y0 - 4;                  // staged origin; sx0 = 12 + 64 bx is 4-aligned
-  const uint8_t* roi = plain + (long long)f * L->slab_bytes + g.plane_off + (long long)kEdge * g.pitch + kPadX;
-  uint8_t* s_scb = reinterpret_cast<uint8_t*>(s_sc);
-  const uint8_t* s_pxb = reinterpret_cast<const uint8_t*>(s_px);
+    if (tid < 2) s_any[tid] = 0;
+    if (tid == 2) s_n2 = 0;
+    if (tid >= 32 && tid < 32 + FS_WORDS) {
+      // per-word byte mask of the columns that are scored: local x in [6, 71] and level x in [19, w-19)
+      const int jw = tid - 32;
+      const int lo = max(6, kEdge - sx0), hi = min(71, w - kEdge - 1 - sx0);
+      uint32_t m = 0;
+      for (int k = 0; k < 4; k++)
+        if (4 * jw + k >= lo && 4 * jw + k <= hi) m |= 0x80u << (8 * k);
+      s_colmask[jw] = m;
+    }
+    const uint8_t* roi = plain + (long long)f * L->slab_bytes + g.plane_off + (long long)kEdge * g.pitch + kPadX;
+    uint8_t* s_scb = reinterpret_cast<uint8_t*>(s_sc);
+    const uint8_t* s_pxb = reinterpret_cast<const uint8_t*>(s_px);
 
-  for (int i = tid; i < FS_ROWS * FS_WORDS; i += 256) {
-    const int r = i / FS_WORDS, j = i - r * FS_WORDS;
-    const int gy = sy0 + r, gx = sx0 + 4 * j;
-    uint32_t v = 0;
-    if (gy < h + kEdge && gx < w + kEdge - 3) v = __ldg(reinterpret_cast<const uint32_t*>(roi + (long long)gy * g.pitch + gx));
-    s_px[i] = v;
-    s_sc[i] = 0;
-  }
-  __syncthreads();
-
-  // ---- packed quick reject on the scored region (interior + 1 px): rows ly 3..36, words 1..17
-  const uint32_t c7 = (uint32_t)(127 - min_th) * 0x01010101u;
-  uint32_t masks[3];
-  int n_mine = 0;
+    {  // stage 76 x 40 bytes: all loads first, then the stores
+      uint32_t v[3];
 #pragma unroll
-  for (int it = 0; it < 3; it++) {
-    const int i = tid + 256 * it;
-    uint32_t m = 0;
-    if (i < 34 * 17) {
-      const int r = i / 17, ly = r + 3, jw = i - r * 17 + 1;
-      const int gy = sy0 + ly;
-      if (gy >= kEdge && gy < h - kEdge) {
-        const uint32_t* row = s_px + ly * FS_WORDS + jw;
-        const uint32_t v = row[0];
-        m = oob_mask(row[-3 * FS_WORDS], v, c7) | oob_mask(row[3 * FS_WORDS], v, c7);
-        if (m) m &= oob_mask(__funnelshift_r(row[0], row[1], 24), v, c7) | oob_mask(__funnelshift_r(row[-1], row[0], 8), v, c7);
-        if (m) {
-          const uint32_t* rp = row + 2 * FS_WORDS;
-          const uint32_t* rm = row - 2 * FS_WORDS;
-          m &= oob_mask(__funnelshift_r(rp[0], rp[1], 16), v, c7) | oob_mask(__funnelshift_r(rm[-1], rm[0], 16), v, c7);
-          if (m) m &= oob_mask(__funnelshift_r(rm[0], rm[1], 16), v, c7) | oob_mask(__funnelshift_r(rp[-1], rp[0], 16), v, c7);
-        }
-        if (m) {  // keep pixels inside the scored columns and the valid FAST band [19, w-19)
-          const int gx = sx0 + 4 * jw;
+      for (int it = 0; it < 3; it++) {
+        const int i = tid + 256 * it;
+        const int r = i / FS_WORDS, j = i - r * FS_WORDS;
+        const int gy = sy0 + r, gx = sx0 + 4 * j;
+        v[it] = 0;
+        if (i < FS_ROWS * FS_WORDS && gy < h + kEdge && gx < w + kEdge - 3)
+          v[it] = __ldg(reinterpret_cast<const uint32_t*>(roi + (long long)gy * g.pitch + gx));
+      }
 #pragma unroll
-          for (int k = 0; k < 4; k++) {
-            const int x = gx + k, lx = 4 * jw + k;
-            if (lx < 6 || lx > 71 || x < kEdge || x >= w - kEdge) m &= ~(0x80u << (8 * k));
-          }
+      for (int it = 0; it < 3; it++) {
+        const int i = tid + 256 * it;
+        if (i < FS_ROWS * FS_WORDS) {
+          s_px[i] = v[it];
+          s_sc[i] = 0;
         }
       }
     }
-    masks[it] = m;
-    n_mine += __popc(m);
-  }
-  // block-wide exclusive scan of the per-thread candidate counts
-  int incl = n_mine;
+    __syncthreads();
+
+    // ---- packed quick reject on the scored region (interior + 1 px): rows ly 3..36, words 1..17
+    const uint32_t c7 = (uint32_t)(127 - min_th) * 0x01010101u;
+    uint32_t masks[3];
+    int n_mine = 0;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
-  }
-  if (lane == 31) s_warp[wid] = incl;
-  __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int k = 0; k < 8; k++) {
-      const int v = s_warp[k];
-      s_warp[k] = run;
-      run += v;
-    }
-    s_total = run;
-  }
-  __syncthreads();
-  int pos = s_warp[wid] + incl - n_mine;
-#pragma unroll
-  for (int it = 0; it < 3; it++) {
-    const uint32_t m = masks[it];
-    if (m) {
+    for (int it = 0; it < 3; it++) {
       const int i = tid + 256 * it;
-      const int r = i / 17, ly = r + 3, jw = i - r * 17 + 1;
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-        if (m & (0x80u << (8 * k))) s_list[pos++] = (uint16_t)((ly << 7) | (4 * jw + k));
+      uint32_t m = 0;
+      if (i < 34 * 17) {
+        const int r = i / 17, ly = r + 3, jw = i - r * 17 + 1;
+        const int gy = sy0 + ly;
+        if (gy >= kEdge && gy < h - kEdge) {
+          const uint32_t* row = s_px + ly * FS_WORDS + jw;
+          const uint32_t v = row[0];
+          m = (oob_mask(row[-3 * FS_WORDS], v, c7) | oob_mask(row[3 * FS_WORDS], v, c7)) & s_colmask[jw];
+          if (m) m &= oob_mask(__funnelshift_r(row[0], row[1], 24), v, c7) | oob_mask(__funnelshift_r(row[-1], row[0], 8), v, c7);
+          if (m) {
+            const uint32_t* rp = row + 2 * FS_WORDS;
+            const uint32_t* rm = row - 2 * FS_WORDS;
+            m &= oob_mask(__funnelshift_r(rp[0], rp[1], 16), v, c7) | oob_mask(__funnelshift_r(rm[-1], rm[0], 16), v, c7);
+            if (m) m &= oob_mask(__funnelshift_r(rm[0], rm[1], 16), v, c7) | oob_mask(__funnelshift_r(rp[-1], rp[0], 16), v, c7);
+          }
+        }
+      }
+      masks[it] = m;
+      n_mine += __popc(m);
     }
-  }
-  __syncthreads();
-  const int n_cand = s_total;
+    // block-wide exclusive scan of the per-thread candidate counts
+    int incl = n_mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int k = 0; k < 8; k++) {
+        const int v = s_warp[k];
+        s_warp[k] = run;
+        run += v;
+      }
+      s_total = run;
+    }
+    __syncthreads();
+    int pos = s_warp[wid] + incl - n_mine;
+#pragma unroll
+    for (int it = 0; it < 3; it++) {
+      const uint32_t m = masks[it];
+      if (m) {
+        const int i = tid + 256 * it;
+        const int r = i / 17, ly = r + 3, jw = i - r * 17 + 1;
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+          if (m & (0x80u << (8 * k))) s_list[pos++] = (uint16_t)((ly << 7) | (4 * jw + k));
+      }
+    }
+    __syncthreads();
+    const int n_cand = s_total;
 
-  // ---- score the survivors
-  for (int i = tid; i < n_cand; i += 256) {
-    const int e = s_list[i], ly = e >> 7, lx = e & 127;
-    s_scb[ly * FS_COLS + lx] = (uint8_t)fast_score(s_pxb + ly * FS_COLS + lx, FS_COLS, min_th);
-  }
-  __syncthreads();
+    // ---- score the survivors; those that can be keypoints go on a second, much shorter list
+    for (int i0 = 0; i0 < n_cand; i0 += 256) {
+      const int i = i0 + tid;
+      bool second = false;
+      int e = 0;
+      if (i < n_cand) {
+        e = s_list[i];
+        const int ly = e >> 7, lx = e & 127;
+        const int sc = fast_score_x2(s_pxb + ly * FS_COLS + lx, FS_COLS, min_th);
+        s_scb[ly * FS_COLS + lx] = (uint8_t)sc;
+        const bool interior = lx >= 7 && lx <= 70 && ly >= 4 && ly <= 35;
+        if (pass == 1) second = interior && sc >= ini_th;
+        else second = interior && sc > 0 && s_flag[4 + 1 + (lx >= 39 ? 1 : 0)] != 0;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, second);
+      if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_n2, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (second) s_list2[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)e;
+      }
+    }
+    __syncthreads();
+    const int n2 = s_n2;
 
-  // ---- non-max suppression of interior candidates
-  for (int i0 = 0; i0 < n_cand; i0 += 256) {
-    const int i = i0 + tid;
-    bool kp = false;
-    int lx = 0, ly = 0, c = 0;
-    if (i < n_cand) {
-      const int e = s_list[i];
-      ly = e >> 7;
-      lx = e & 127;
-      c = s_scb[ly * FS_COLS + lx];
-      const bool interior = lx >= 7 && lx <= 70 && ly >= 4 && ly <= 35;
-      const int tile = lx >= 39 ? 1 : 0;
-      if (pass == 1) kp = interior && c >= ini_th;
-      else kp = interior && c > 0 && s_flag[4 + 1 + tile] != 0;
-      if (kp) {
+    // ---- non-max suppression (strict, 8 neighbours) of the short list
+    for (int i0 = 0; i0 < n2; i0 += 256) {
+      const int i = i0 + tid;
+      bool kp = false;
+      int lx = 0, ly = 0, c = 0;
+      if (i < n2) {
+        const int e = s_list2[i];
+        ly = e >> 7;
+        lx = e & 127;
+        const uint8_t* sp = s_scb + ly * FS_COLS + lx;
+        c = sp[0];
+        kp = true;
 #pragma unroll
         for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
           for (int dx = -1; dx <= 1; dx++) {
             if (dx == 0 && dy == 0) continue;
-            const int qx = lx + dx, qy = ly + dy;
-            int q = s_scb[qy * FS_COLS + qx];
+            int q = sp[dy * FS_COLS + dx];
             bool raw = false;
             if (pass == 2) {
+              const int qx = lx + dx, qy = ly + dy;
               const int fy = qy < 4 ? 0 : (qy > 35 ? 2 : 1);
               const int fx = qx < 7 ? 0 : (qx < 39 ? 1 : (qx < 71 ? 2 : 3));
               raw = s_flag[fy * 4 + fx] != 0;
@@ -422,33 +495,35 @@ __global__ void __launch_bounds__(256) fast_kernel(const FrameLayout* __restrict
             if (!raw && q < ini_th) q = 0;
             kp = kp && c > q;
           }
+        if (kp && pass == 1) s_any[lx >= 39 ? 1 : 0] = 1;
       }
-      if (kp && pass == 1) s_any[tile] = 1;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, kp);
-    if (m) {
-      int base = 0;
-      if (lane == 0) base = atomicAdd(cand_count + f * L->nlevels + lvl, __popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (kp) {
-        const int idx = base + __popc(m & ((1u << lane) - 1));
-        if (idx < g.cand_cap)
-          cand[(long long)f * L->cand_total + g.cand_off + idx] = pack_pt(sx0 + lx - kBand, sy0 + ly - kBand, c);
+      const unsigned m = __ballot_sync(0xffffffffu, kp);
+      if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(cand_count + f * L->nlevels + lvl, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (kp) {
+          const int idx = base + __popc(m & ((1u << lane) - 1));
+          if (idx < g.cand_cap)
+            cand[(long long)f * L->cand_total + g.cand_off + idx] = pack_pt(sx0 + lx - kBand, sy0 + ly - kBand, c);
+        }
       }
     }
-  }
-  if (pass == 1) {
-    __syncthreads();
-    if (tid == 0) {
-      fretry[t0] = s_any[0] ? 0 : 1;
-      if (has_t1) fretry[t0 + 1] = s_any[1] ? 0 : 1;
-    }
-    if (dbg_score) {  // parity introspection only: the score map S at minThFAST for the block interior
-      uint8_t* sc = dbg_score + (long long)f * L->slab_bytes + g.plane_off + (long long)kEdge * g.pitch + kPadX;
-      for (int i = tid; i < 64 * 32; i += 256) {
-        const int ly = (i >> 6) + 4, lx = (i & 63) + 7;
-        const int gx = sx0 + lx, gy = sy0 + ly;
-        if (gx < w - kEdge && gy < h - kEdge) sc[(long long)gy * g.pitch + gx] = s_scb[ly * FS_COLS + lx];
+    if (pass == 1) {
+      __syncthreads();
+      if (tid == 0) {
+        const int r0 = s_any[0] ? 0 : 1, r1 = (has_t1 && !s_any[1]) ? 1 : 0;
+        fretry[t0] = (uint8_t)r0;
+        if (has_t1) fretry[t0 + 1] = (uint8_t)r1;
+        if (r0 | r1) retry_list[1 + atomicAdd(retry_list, 1)] = fb;  // pass 2 re-runs only these blocks
+      }
+      if (dbg_score) {  // parity introspection only: the score map S at minThFAST for the block interior
+        uint8_t* sc = dbg_score + (long long)f * L->slab_bytes + g.plane_off + (long long)kEdge * g.pitch + kPadX;
+        for (int i = tid; i < 64 * 32; i += 256) {
+          const int ly = (i >> 6) + 4, lx = (i & 63) + 7;
+          const int gx = sx0 + lx, gy = sy0 + ly;
+          if (gx < w - kEdge && gy < h - kEdge) sc[(long long)gy * g.pitch + gx] = s_scb[ly * FS_COLS + lx];
+        }
       }
     }
   }
@@ -516,6 +591,7 @@ __global__ void __launch_bounds__(256) describe_kernel(const FrameLayout* __rest
                                                        const uint8_t* __restrict__ blur, const uint32_t* __restrict__ sel,
                                                        const int* __restrict__ sel_count, swm_keypoint* __restrict__ kps,
                                                        uint8_t* __restrict__ desc, int cap, int32_t* __restrict__ n_out) {
+  __shared__ __align__(16) uint32_t s_patch[8 * 37 * 11];
   const int f = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int gidx = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -541,6 +617,7 @@ __global__ void __launch_bounds__(256) describe_kernel(const FrameLayout* __rest
   const uint8_t* c = plain + off;
   int m10 = 0, m01 = 0;
   if (lane <= 2 * kHalfPatch) m10 = (lane - kHalfPatch) * (int)c[lane - kHalfPatch];
+#pragma unroll
   for (int v = 1; v <= kHalfPatch; ++v) {
     const int d = c_umax[v];
     if (lane <= 2 * d) {
@@ -560,19 +637,40 @@ __global__ void __launch_bounds__(256) describe_kernel(const FrameLayout* __rest
   if (ang < 0) ang = __fadd_rn(ang, 2.0f * kPiF);
   ang = __fmul_rn(ang, 180.0f / kPiF);
 
-  // calcOrb_kernel (Orb_gpu.cu:67-100): lane t -> descriptor byte t
+  // calcOrb_kernel (Orb_gpu.cu:67-100): lane t -> descriptor byte t.  The 37x37 neighbourhood of the
+  // blurred plane is staged per warp with aligned word loads (2-3 sectors per row instead of one sector
+  // per sample), then the 512 rotated samples are read from shared memory.
   const float factor_pi = (float)(3.1415926535897932384626433832795 / 180.f);
   const float rad = __fmul_rn(ang, factor_pi);
   const float ca = cosf(rad), sb = sinf(rad);
-  const uint8_t* b = blur + off;
+  constexpr int kPR = 18, kPW = 11;  // patch radius (max rotated pattern offset is 18), words per patch row
+  uint32_t* patch = s_patch + (threadIdx.x >> 5) * ((2 * kPR + 1) * kPW);
+  const int ox = (x - kPR) & ~3;
+  {
+    const uint8_t* b0 = blur + (long long)f * L->slab_bytes + g.plane_off + (long long)(y - kPR + kEdge) * g.pitch + kPadX + ox;
+    uint32_t v[13];
+#pragma unroll
+    for (int it = 0; it < 13; it++) {
+      const int idx = lane + 32 * it;
+      const int r = idx / kPW, wd = idx - r * kPW;
+      v[it] = idx < (2 * kPR + 1) * kPW ? __ldg(reinterpret_cast<const uint32_t*>(b0 + (long long)r * pitch) + wd) : 0u;
+    }
+#pragma unroll
+    for (int it = 0; it < 13; it++) {
+      const int idx = lane + 32 * it;
+      if (idx < (2 * kPR + 1) * kPW) patch[idx] = v[it];
+    }
+  }
+  __syncwarp();
+  const uint8_t* b = reinterpret_cast<const uint8_t*>(patch) + kPR * (kPW * 4) + (x - ox);
   const signed char* pat = c_pattern + 32 * lane;
   int val = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const float x0 = pat[4 * k], y0 = pat[4 * k + 1], x1 = pat[4 * k + 2], y1 = pat[4 * k + 3];
-    const int t0 = b[__float2int_rn(__fadd_rn(__fmul_rn(x0, sb), __fmul_rn(y0, ca))) * pitch +
+    const int t0 = b[__float2int_rn(__fadd_rn(__fmul_rn(x0, sb), __fmul_rn(y0, ca))) * (kPW * 4) +
                      __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sb)))];
-    const int t1 = b[__float2int_rn(__fadd_rn(__fmul_rn(x1, sb), __fmul_rn(y1, ca))) * pitch +
+    const int t1 = b[__float2int_rn(__fadd_rn(__fmul_rn(x1, sb), __fmul_rn(y1, ca))) * (kPW * 4) +
                      __float2int_rn(__fsub_rn(__fmul_rn(x1, ca), __fmul_rn(y1, sb)))];
     val |= (t0 < t1) << k;
   }
@@ -665,6 +763,8 @@ struct swm_orb {
   ResizeTap *d_xtab = nullptr, *d_ytab = nullptr;
   uint8_t *d_plain = nullptr, *d_blur = nullptr, *d_score = nullptr;
   uint8_t* d_retry = nullptr;
+  int* d_retry_list = nullptr;  // [0] = count, then (frame * blocks + block) ids holding a retry tile
+  int n_sm = 148;
   uint32_t *d_cand = nullptr, *d_sel = nullptr;
   int *d_counts = nullptr;  // [2][B][nlevels]: candidate counts, selection counts
   // staging for the host-buffer entry points
@@ -695,11 +795,11 @@ namespace {
 void free_frame_buffers(swm_orb* h) {
   cudaFree(h->d_lay); cudaFree(h->d_xtab); cudaFree(h->d_ytab);
   cudaFree(h->d_plain); cudaFree(h->d_blur); cudaFree(h->d_score);
-  cudaFree(h->d_retry); cudaFree(h->d_cand); cudaFree(h->d_sel); cudaFree(h->d_counts);
+  cudaFree(h->d_retry); cudaFree(h->d_retry_list); cudaFree(h->d_cand); cudaFree(h->d_sel); cudaFree(h->d_counts);
   cudaFree(h->d_img); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_n);
   h->d_lay = nullptr; h->d_xtab = h->d_ytab = nullptr;
   h->d_plain = h->d_blur = h->d_score = nullptr;
-  h->d_retry = nullptr; h->d_cand = h->d_sel = nullptr; h->d_counts = nullptr;
+  h->d_retry = nullptr; h->d_retry_list = nullptr; h->d_cand = h->d_sel = nullptr; h->d_counts = nullptr;
   h->d_img = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->d_n = nullptr;
   h->allocated = false;
 }
@@ -810,6 +910,7 @@ int setup_geometry(swm_orb* h, int w, int hh) {
   SWM_CK(h, cudaMalloc(&h->d_blur, (size_t)L.slab_bytes * B));
   if (h->debug_score) SWM_CK(h, cudaMalloc(&h->d_score, (size_t)L.slab_bytes * B));
   SWM_CK(h, cudaMalloc(&h->d_retry, (size_t)L.tiles_total * B));
+  SWM_CK(h, cudaMalloc(&h->d_retry_list, ((size_t)L.fblk_total * B + 1) * sizeof(int)));
   SWM_CK(h, cudaMalloc(&h->d_cand, (size_t)L.cand_total * B * sizeof(uint32_t)));
   SWM_CK(h, cudaMalloc(&h->d_sel, (size_t)L.sel_total * B * sizeof(uint32_t)));
   SWM_CK(h, cudaMalloc(&h->d_counts, (size_t)2 * B * nl * sizeof(int)));
@@ -860,12 +961,13 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
   }
   if (mask & SWM_STAGE_NMS) {
     SWM_CK(h, cudaMemsetAsync(h->d_counts, 0, (size_t)2 * h->cfg.max_batch * nl * sizeof(int), st));
+    SWM_CK(h, cudaMemsetAsync(h->d_retry_list, 0, sizeof(int), st));
     dim3 grid(L.fblk_total, batch);
     uint8_t* dbg = h->debug_score ? h->d_score : nullptr;
     fast_kernel<<<grid, 256, 0, st>>>(h->d_lay, h->d_plain, h->cfg.ini_th_fast, h->cfg.min_th_fast, 1, h->d_retry,
-                                      h->d_cand, d_cand_count, dbg);
-    fast_kernel<<<grid, 256, 0, st>>>(h->d_lay, h->d_plain, h->cfg.ini_th_fast, h->cfg.min_th_fast, 2, h->d_retry,
-                                      h->d_cand, d_cand_count, nullptr);
+                                      h->d_retry_list, h->d_cand, d_cand_count, dbg);
+    fast_kernel<<<h->n_sm * 3, 256, 0, st>>>(h->d_lay, h->d_plain, h->cfg.ini_th_fast, h->cfg.min_th_fast, 2,
+                                             h->d_retry, h->d_retry_list, h->d_cand, d_cand_count, nullptr);
     launches += 2;
   }
   if (mask & SWM_STAGE_OCTREE) {
@@ -939,6 +1041,7 @@ int swm_orb_create(const swm_orb_cfg* cfg, int device, swm_orb** out) {
       }
   }
   cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->n_sm, cudaDevAttrMultiProcessorCount, device);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) {
     // constant tables are per device; identical for every handle (ORBextractor.cc:380-404)
