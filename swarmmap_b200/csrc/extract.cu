@@ -25,7 +25,10 @@
 
 namespace swm {
 
-__constant__ signed char c_pattern[1024];
+// rBRIEF test points as floats, transposed so that lane t reads entry [k*32 + t] = (P0.x, P0.y, P1.x, P1.y)
+// of its k-th comparison with one coalesced 16-byte load (constant memory would serialise: every lane
+// indexes a different address).
+__device__ float4 g_pattern[8 * 32];
 __constant__ int c_umax[16];
 
 // ------------------------------------------------------------------------------------------------
@@ -663,11 +666,11 @@ __global__ void __launch_bounds__(256) describe_kernel(const FrameLayout* __rest
   }
   __syncwarp();
   const uint8_t* b = reinterpret_cast<const uint8_t*>(patch) + kPR * (kPW * 4) + (x - ox);
-  const signed char* pat = c_pattern + 32 * lane;
   int val = 0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
-    const float x0 = pat[4 * k], y0 = pat[4 * k + 1], x1 = pat[4 * k + 2], y1 = pat[4 * k + 3];
+    const float4 pp = __ldg(&g_pattern[k * 32 + lane]);
+    const float x0 = pp.x, y0 = pp.y, x1 = pp.z, y1 = pp.w;
     const int t0 = b[__float2int_rn(__fadd_rn(__fmul_rn(x0, sb), __fmul_rn(y0, ca))) * (kPW * 4) +
                      __float2int_rn(__fsub_rn(__fmul_rn(x0, ca), __fmul_rn(y0, sb)))];
     const int t1 = b[__float2int_rn(__fadd_rn(__fmul_rn(x1, sb), __fmul_rn(y1, ca))) * (kPW * 4) +
@@ -914,7 +917,7 @@ int setup_geometry(swm_orb* h, int w, int hh) {
   SWM_CK(h, cudaMalloc(&h->d_cand, (size_t)L.cand_total * B * sizeof(uint32_t)));
   SWM_CK(h, cudaMalloc(&h->d_sel, (size_t)L.sel_total * B * sizeof(uint32_t)));
   SWM_CK(h, cudaMalloc(&h->d_counts, (size_t)2 * B * nl * sizeof(int)));
-  h->img_pitch = (int)align_up(w, 128);
+  h->img_pitch = (int)align_up(w, 4);  // rows stay word-aligned; equals the usual host stride so uploads are 1-D
   SWM_CK(h, cudaMalloc(&h->d_img, (size_t)h->img_pitch * hh * B));
   SWM_CK(h, cudaMalloc(&h->d_kps, (size_t)h->max_kp * B * sizeof(swm_keypoint)));
   SWM_CK(h, cudaMalloc(&h->d_desc, (size_t)h->max_kp * B * 32));
@@ -1058,7 +1061,13 @@ int swm_orb_create(const swm_orb_cfg* cfg, int device, swm_orb** out) {
         ++v0;
       }
       cudaError_t e2 = cudaMemcpyToSymbol(c_umax, umax, sizeof(umax));
-      if (e2 == cudaSuccess) e2 = cudaMemcpyToSymbol(c_pattern, kSwmOrbPattern, 1024);
+      if (e2 == cudaSuccess) {
+        std::vector<float> pat(8 * 32 * 4);
+        for (int t = 0; t < 32; t++)
+          for (int k = 0; k < 8; k++)
+            for (int c = 0; c < 4; c++) pat[(k * 32 + t) * 4 + c] = (float)kSwmOrbPattern[32 * t + 4 * k + c];
+        e2 = cudaMemcpyToSymbol(g_pattern, pat.data(), pat.size() * sizeof(float));
+      }
       if (e2 != cudaSuccess) e = e2;
     });
   }
@@ -1106,7 +1115,9 @@ static int enqueue_host_chunk(swm_orb* h, const uint8_t* src, int nb, int w, int
                               size_t frame_stride, swm_keypoint* kps, uint8_t* desc, int cap, int32_t* n) {
   const int kcap = h->max_kp;
   const int ccap = cap < kcap ? cap : kcap;
-  if (frame_stride == (size_t)stride * h_px) {
+  if (frame_stride == (size_t)stride * h_px && stride == h->img_pitch) {
+    SWM_CK(h, cudaMemcpyAsync(h->d_img, src, (size_t)stride * h_px * nb, cudaMemcpyHostToDevice, h->stream));
+  } else if (frame_stride == (size_t)stride * h_px) {
     SWM_CK(h, cudaMemcpy2DAsync(h->d_img, h->img_pitch, src, stride, w, (size_t)h_px * nb, cudaMemcpyHostToDevice,
                                 h->stream));
   } else {
@@ -1118,10 +1129,15 @@ static int enqueue_host_chunk(swm_orb* h, const uint8_t* src, int nb, int w, int
                                         h->d_desc, kcap, h->d_n, h->stream);
   if (rc != SWM_OK) return rc;
   SWM_CK(h, cudaMemcpyAsync(n, h->d_n, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-  SWM_CK(h, cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(swm_keypoint), h->d_kps, (size_t)kcap * sizeof(swm_keypoint),
-                              (size_t)ccap * sizeof(swm_keypoint), nb, cudaMemcpyDeviceToHost, h->stream));
-  SWM_CK(h, cudaMemcpy2DAsync(desc, (size_t)cap * 32, h->d_desc, (size_t)kcap * 32, (size_t)ccap * 32, nb,
-                              cudaMemcpyDeviceToHost, h->stream));
+  if (cap == kcap) {
+    SWM_CK(h, cudaMemcpyAsync(kps, h->d_kps, (size_t)kcap * nb * sizeof(swm_keypoint), cudaMemcpyDeviceToHost, h->stream));
+    SWM_CK(h, cudaMemcpyAsync(desc, h->d_desc, (size_t)kcap * nb * 32, cudaMemcpyDeviceToHost, h->stream));
+  } else {
+    SWM_CK(h, cudaMemcpy2DAsync(kps, (size_t)cap * sizeof(swm_keypoint), h->d_kps, (size_t)kcap * sizeof(swm_keypoint),
+                                (size_t)ccap * sizeof(swm_keypoint), nb, cudaMemcpyDeviceToHost, h->stream));
+    SWM_CK(h, cudaMemcpy2DAsync(desc, (size_t)cap * 32, h->d_desc, (size_t)kcap * 32, (size_t)ccap * 32, nb,
+                                cudaMemcpyDeviceToHost, h->stream));
+  }
   h->pending_n = n;
   h->pending_batch = nb;
   h->pending_cap = cap;
