@@ -123,10 +123,13 @@ __global__ void __launch_bounds__(256) pyr_kernel(const PyrArgs a) {
       t.pad = (int16_t)min(o0 + 1, sh - 1 - sy_base);  // second source row, clamped like cv::resize
       s_yt[tid - 128] = t;
     }
-    for (int i = tid; i < nrows * nwords; i += 256) {
-      const int r = i / nwords, j = i - r * nwords;
-      s_src[r * SRC_WORDS + j] =
-          __ldg(reinterpret_cast<const uint32_t*>(src + (long long)(sy_base + r) * spitch + sx_base + 4 * j));
+    {
+      const int lane = tid & 31;
+      if (lane < nwords) {
+        const uint8_t* col = src + sx_base + 4 * lane;
+        for (int r = tid >> 5; r < nrows; r += 8)
+          s_src[r * SRC_WORDS + lane] = __ldg(reinterpret_cast<const uint32_t*>(col + (long long)(sy_base + r) * spitch));
+      }
     }
     __syncthreads();
     // row pass: one value per (source row, destination column), kept as (sum >> 4) in 16 bits
@@ -303,8 +306,9 @@ __device__ __forceinline__ int fast_score_x2(const uint8_t* c, int pitch, int th
 }
 
 __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restrict__ L, const uint8_t* __restrict__ plain,
-                                                      int ini_th, int min_th, int pass, uint8_t* __restrict__ retry,
-                                                      int* __restrict__ retry_list, uint32_t* __restrict__ cand,
+                                                      const int4* __restrict__ fblk_desc, int ini_th, int min_th, int pass,
+                                                      uint8_t* __restrict__ retry, int* __restrict__ retry_list,
+                                                      uint32_t* __restrict__ cand,
                                                       int* __restrict__ cand_count, uint8_t* __restrict__ dbg_score) {
   __shared__ __align__(16) uint32_t s_px[FS_ROWS * FS_WORDS];
   __shared__ __align__(16) uint32_t s_sc[FS_ROWS * FS_WORDS];
@@ -331,12 +335,11 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
       fb = s_blk;
       if (fb < 0) break;
     }
-    const int f = fb / nblk, blk = fb - f * nblk;
-    int lvl = 0;
-    while (lvl + 1 < L->nlevels && blk >= L->lv[lvl + 1].fblk_off) lvl++;
+    const int f = pass == 1 ? (int)blockIdx.y : fb / nblk;
+    const int blk = fb - f * nblk;
+    const int4 bd = __ldg(&fblk_desc[blk]);  // (level, bx, by, -) of this block, built on the host
+    const int lvl = bd.x, bx = bd.y, by = bd.z;
     const LevelGeom& g = L->lv[lvl];
-    const int bl = blk - g.fblk_off;
-    const int by = bl / g.fblk_x, bx = bl - by * g.fblk_x;
     uint8_t* fretry = retry + (long long)f * L->tiles_total + g.tile_off;
     const int t0 = by * g.tiles_x + 2 * bx;  // first of the two tiles of this block
     const bool has_t1 = 2 * bx + 1 < g.tiles_x;
@@ -446,26 +449,14 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
     const int n_cand = s_total;
 
     // ---- score the survivors; those that can be keypoints go on a second, much shorter list
-    for (int i0 = 0; i0 < n_cand; i0 += 256) {
-      const int i = i0 + tid;
-      bool second = false;
-      int e = 0;
-      if (i < n_cand) {
-        e = s_list[i];
-        const int ly = e >> 7, lx = e & 127;
-        const int sc = fast_score_x2(s_pxb + ly * FS_COLS + lx, FS_COLS, min_th);
-        s_scb[ly * FS_COLS + lx] = (uint8_t)sc;
-        const bool interior = lx >= 7 && lx <= 70 && ly >= 4 && ly <= 35;
-        if (pass == 1) second = interior && sc >= ini_th;
-        else second = interior && sc > 0 && s_flag[4 + 1 + (lx >= 39 ? 1 : 0)] != 0;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, second);
-      if (m) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&s_n2, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (second) s_list2[base + __popc(m & ((1u << lane) - 1))] = (uint16_t)e;
-      }
+    for (int i = tid; i < n_cand; i += 256) {
+      const int e = s_list[i];
+      const int ly = e >> 7, lx = e & 127;
+      const int sc = fast_score_x2(s_pxb + ly * FS_COLS + lx, FS_COLS, min_th);
+      s_scb[ly * FS_COLS + lx] = (uint8_t)sc;
+      if (sc >= (pass == 1 ? ini_th : 1) && lx >= 7 && lx <= 70 && ly >= 4 && ly <= 35 &&
+          (pass == 1 || s_flag[4 + 1 + (lx >= 39 ? 1 : 0)] != 0))
+        s_list2[atomicAdd(&s_n2, 1)] = (uint16_t)e;
     }
     __syncthreads();
     const int n2 = s_n2;
@@ -766,6 +757,7 @@ struct swm_orb {
   ResizeTap *d_xtab = nullptr, *d_ytab = nullptr;
   uint8_t *d_plain = nullptr, *d_blur = nullptr, *d_score = nullptr;
   uint8_t* d_retry = nullptr;
+  int4* d_fblk = nullptr;       // per FAST block: (level, bx, by, 0)
   int* d_retry_list = nullptr;  // [0] = count, then (frame * blocks + block) ids holding a retry tile
   int n_sm = 148;
   uint32_t *d_cand = nullptr, *d_sel = nullptr;
@@ -798,11 +790,11 @@ namespace {
 void free_frame_buffers(swm_orb* h) {
   cudaFree(h->d_lay); cudaFree(h->d_xtab); cudaFree(h->d_ytab);
   cudaFree(h->d_plain); cudaFree(h->d_blur); cudaFree(h->d_score);
-  cudaFree(h->d_retry); cudaFree(h->d_retry_list); cudaFree(h->d_cand); cudaFree(h->d_sel); cudaFree(h->d_counts);
+  cudaFree(h->d_retry); cudaFree(h->d_retry_list); cudaFree(h->d_fblk); cudaFree(h->d_cand); cudaFree(h->d_sel); cudaFree(h->d_counts);
   cudaFree(h->d_img); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_n);
   h->d_lay = nullptr; h->d_xtab = h->d_ytab = nullptr;
   h->d_plain = h->d_blur = h->d_score = nullptr;
-  h->d_retry = nullptr; h->d_retry_list = nullptr; h->d_cand = h->d_sel = nullptr; h->d_counts = nullptr;
+  h->d_retry = nullptr; h->d_retry_list = nullptr; h->d_fblk = nullptr; h->d_cand = h->d_sel = nullptr; h->d_counts = nullptr;
   h->d_img = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->d_n = nullptr;
   h->allocated = false;
 }
@@ -922,6 +914,14 @@ int setup_geometry(swm_orb* h, int w, int hh) {
   SWM_CK(h, cudaMalloc(&h->d_kps, (size_t)h->max_kp * B * sizeof(swm_keypoint)));
   SWM_CK(h, cudaMalloc(&h->d_desc, (size_t)h->max_kp * B * 32));
   SWM_CK(h, cudaMalloc(&h->d_n, (size_t)B * sizeof(int32_t)));
+  {
+    std::vector<int4> desc(L.fblk_total);
+    for (int l = 0; l < nl; l++)
+      for (int by = 0; by < L.lv[l].tiles_y; by++)
+        for (int bx = 0; bx < L.lv[l].fblk_x; bx++) desc[L.lv[l].fblk_off + by * L.lv[l].fblk_x + bx] = make_int4(l, bx, by, 0);
+    SWM_CK(h, cudaMalloc(&h->d_fblk, desc.size() * sizeof(int4)));
+    SWM_CK(h, cudaMemcpy(h->d_fblk, desc.data(), desc.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  }
   SWM_CK(h, cudaMemcpy(h->d_lay, &L, sizeof(L), cudaMemcpyHostToDevice));
   SWM_CK(h, cudaMemcpy(h->d_xtab, xt.data(), xt.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
   SWM_CK(h, cudaMemcpy(h->d_ytab, yt.data(), yt.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
@@ -967,9 +967,9 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
     SWM_CK(h, cudaMemsetAsync(h->d_retry_list, 0, sizeof(int), st));
     dim3 grid(L.fblk_total, batch);
     uint8_t* dbg = h->debug_score ? h->d_score : nullptr;
-    fast_kernel<<<grid, 256, 0, st>>>(h->d_lay, h->d_plain, h->cfg.ini_th_fast, h->cfg.min_th_fast, 1, h->d_retry,
-                                      h->d_retry_list, h->d_cand, d_cand_count, dbg);
-    fast_kernel<<<h->n_sm * 3, 256, 0, st>>>(h->d_lay, h->d_plain, h->cfg.ini_th_fast, h->cfg.min_th_fast, 2,
+    fast_kernel<<<grid, 256, 0, st>>>(h->d_lay, h->d_plain, h->d_fblk, h->cfg.ini_th_fast, h->cfg.min_th_fast, 1,
+                                      h->d_retry, h->d_retry_list, h->d_cand, d_cand_count, dbg);
+    fast_kernel<<<h->n_sm * 3, 256, 0, st>>>(h->d_lay, h->d_plain, h->d_fblk, h->cfg.ini_th_fast, h->cfg.min_th_fast, 2,
                                              h->d_retry, h->d_retry_list, h->d_cand, d_cand_count, nullptr);
     launches += 2;
   }
