@@ -280,14 +280,36 @@ def main():
     t_e2e = time.perf_counter() - t0
     clocks = sampler.stop()
 
+    # ---- Hamming matches/s: server-side place recognition shard (BASELINE config 5, scaled to one step):
+    # 2000 query descriptors against this rank's shard of the keyframe-descriptor database, top-2 per
+    # query, then the all-gather + merge of the per-shard candidates when world > 1.
+    from swarmmap_b200 import place
+    NQ, DPK, KF_PER_RANK = 2000, 256, 8192          # 2.1 M descriptors (67 MB) per GPU
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99 + rank)
+    db = torch.randint(0, 256, (KF_PER_RANK * DPK, 32), dtype=torch.uint8, device=dev, generator=gen)
+    qd = torch.randint(0, 256, (NQ, 32), dtype=torch.uint8, device=dev, generator=gen)
+    shard = place.PlaceShard(db, DPK, rank * KF_PER_RANK, device=local_rank)
+    for _ in range(2):
+        shard.query(qd, 2, 50)
+    barrier()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    h0.record()
+    for _ in range(reps):
+        keys, votes = shard.query(qd, 2, 50)
+    h1.record()
+    barrier()
+    ms_ham = h0.elapsed_time(h1) / reps
+
     # ---- reduce over ranks (max time), rank 0 prints
-    t = torch.tensor([ms_total, t_e2e * 1e3, stage_ms["pyramid_fast_blur"] + stage_ms["nms"]], dtype=torch.float64,
-                     device=dev)
+    t = torch.tensor([ms_total, t_e2e * 1e3, stage_ms["pyramid_fast_blur"] + stage_ms["nms"], ms_ham],
+                     dtype=torch.float64, device=dev)
     cnt = torch.tensor([float(n_kp)], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_total, ms_e2e, ms_pf = [float(x) for x in t.tolist()]
+    ms_total, ms_e2e, ms_pf, ms_ham = [float(x) for x in t.tolist()]
     frames_total = world * B * args.steps
     value = frames_total / (ms_total * 1e-3)
     e2e_value = frames_total / (ms_e2e * 1e-3)
@@ -322,6 +344,10 @@ def main():
             "clocks": clocks,
             "stages_ms_per_step": stage_ms,
             "keypoints_per_frame": float(cnt.item()) / (world * B),
+            "hamming": {"metric": "hamming_matches_per_sec", "value": world * NQ * KF_PER_RANK * DPK / (ms_ham * 1e-3),
+                        "unit": "256-bit pairs/s", "ms_per_query_batch": ms_ham,
+                        "config": f"{NQ} queries x {KF_PER_RANK * DPK} descriptors per GPU shard ({KF_PER_RANK} keyframes x {DPK}), "
+                                  f"top-2 + votes" + (", all_gather of 32 KB key blocks + merge" if world > 1 else "")},
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
