@@ -387,8 +387,11 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
     }
     __syncthreads();
 
+    // Pass 1 only ever uses S_hi (scores below iniThFAST count as 0), so it detects at iniThFAST: same
+    // keypoints, a fraction of the candidates.  Pass 2 (and the debug score map) need S at minThFAST.
+    const int th_run = (pass == 1 && dbg_score == nullptr) ? ini_th : min_th;
     // ---- packed quick reject on the scored region (interior + 1 px): rows ly 3..36, words 1..17
-    const uint32_t c7 = (uint32_t)(127 - min_th) * 0x01010101u;
+    const uint32_t c7 = (uint32_t)(127 - th_run) * 0x01010101u;
     uint32_t masks[3];
     int n_mine = 0;
 #pragma unroll
@@ -452,7 +455,7 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
     for (int i = tid; i < n_cand; i += 256) {
       const int e = s_list[i];
       const int ly = e >> 7, lx = e & 127;
-      const int sc = fast_score_x2(s_pxb + ly * FS_COLS + lx, FS_COLS, min_th);
+      const int sc = fast_score_x2(s_pxb + ly * FS_COLS + lx, FS_COLS, th_run);
       s_scb[ly * FS_COLS + lx] = (uint8_t)sc;
       if (sc >= (pass == 1 ? ini_th : 1) && lx >= 7 && lx <= 70 && ly >= 4 && ly <= 35 &&
           (pass == 1 || s_flag[4 + 1 + (lx >= 39 ? 1 : 0)] != 0))
@@ -1001,7 +1004,7 @@ int swm_orb_create(const swm_orb_cfg* cfg, int device, swm_orb** out) {
   if (!cfg || !out) return SWM_E_INVALID;
   *out = nullptr;
   if (cfg->nfeatures <= 0 || cfg->nlevels < 1 || cfg->nlevels > SWM_MAX_LEVELS || !(cfg->scale_factor > 1.0f) ||
-      cfg->scale_factor > 1.5f || cfg->min_th_fast < 1 || cfg->min_th_fast > 126 ||
+      cfg->scale_factor > 1.5f || cfg->min_th_fast < 1 || cfg->ini_th_fast > 126 ||
       cfg->ini_th_fast < cfg->min_th_fast || cfg->ini_th_fast > 254 || cfg->max_batch < 1) {
     g_create_error = "invalid swm_orb_cfg";
     return SWM_E_INVALID;

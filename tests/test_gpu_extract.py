@@ -71,6 +71,27 @@ def test_single_frame_config2_kitti(oracle, swm):
         _check_frame(gpu, cpu, img, 0, (kps, desc))
 
 
+def test_product_config_without_debug_map(oracle, swm):
+    """The shipped configuration keeps no score map and detects pass 1 at iniThFAST; same keypoints."""
+    from swarmmap_b200.orb import ORBextractor
+    rng = np.random.default_rng(3)
+    low = (120 + 6 * rng.standard_normal((480, 752))).clip(0, 255).astype(np.uint8)
+    low[100:300, 200:500] = synth.make_frame(752, 480, 5)[100:300, 200:500]
+    for img, nf in ((synth.make_frame(752, 480, 20220404), 1000), (low, 1000), (synth.make_frame(1241, 376, 20220405), 2000)):
+        gpu = ORBextractor(nf, 1.2, 8, 20, 7)
+        cpu = oracle.Extractor(nf, 1.2, 8, 20, 7)
+        kps, desc = gpu(img)
+        okps, odesc = cpu(img)
+        assert len(kps) == len(okps)
+        for fld in ("x", "y", "size", "response", "octave"):
+            np.testing.assert_array_equal(kps[fld], okps[fld])
+        for l in range(8):
+            g = sorted(map(tuple, gpu.debug_points(0, l, 0).tolist()))
+            o = cpu.level_fast(l)
+            assert g == sorted(zip(o["x"].tolist(), o["y"].tolist(), o["score"].tolist()))
+        assert 1.0 - np.unpackbits(desc ^ odesc).sum() / float(desc.size * 8) >= DESC_BIT_FRACTION
+
+
 def test_batch_matches_single(oracle, swm):
     gpu, cpu = _extractors(oracle, 1000, max_batch=4)
     imgs = synth.make_batch(6, 752, 480, 20220410)  # 6 frames through a batch-4 handle: two chunks
