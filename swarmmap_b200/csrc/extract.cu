@@ -175,21 +175,24 @@ __global__ void __launch_bounds__(256) pyr_kernel(const PyrArgs a) {
       store4(dplain + (long long)gy * pitch, gx, w, word);
       if (edge_tile) {
         // copyMakeBorder(BORDER_REFLECT_101, 19): every in-image pixel also lands at the border
-        // positions that reflect onto it (ORBextractor.cc:846-851).
+        // positions that reflect onto it (ORBextractor.cc:846-851).  Row mirrors are whole-word stores;
+        // column mirrors (byte order reversed) only exist in the first / last tile column.
         int ys[3], ny = 0;
         ys[ny++] = gy;
         if (gy >= 1 && gy <= kEdge) ys[ny++] = -gy;
         if (gy >= h - 1 - kEdge && gy <= h - 2) ys[ny++] = 2 * (h - 1) - gy;
-        for (int k = 0; k < 4; k++) {
-          const int x = gx + k;
-          if (x >= w) break;
-          int xs[3], nx = 0;
-          xs[nx++] = x;
-          if (x >= 1 && x <= kEdge) xs[nx++] = -x;
-          if (x >= w - 1 - kEdge && x <= w - 2) xs[nx++] = 2 * (w - 1) - x;
-          for (int iy = 0; iy < ny; iy++)
-            for (int ix = 0; ix < nx; ix++)
-              if (ix | iy) dplain[(long long)ys[iy] * pitch + xs[ix]] = (uint8_t)(word >> (8 * k));
+        for (int iy = 1; iy < ny; iy++) store4(dplain + (long long)ys[iy] * pitch, gx, w, word);
+        if (gx <= kEdge || gx + 3 >= w - 1 - kEdge) {
+          for (int k = 0; k < 4; k++) {
+            const int x = gx + k;
+            if (x >= w) break;
+            const uint8_t v = (uint8_t)(word >> (8 * k));
+            for (int iy = 0; iy < ny; iy++) {
+              uint8_t* drow = dplain + (long long)ys[iy] * pitch;
+              if (x >= 1 && x <= kEdge) drow[-x] = v;
+              if (x >= w - 1 - kEdge && x <= w - 2) drow[2 * (w - 1) - x] = v;
+            }
+          }
         }
       }
     }
@@ -529,27 +532,28 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
 // ------------------------------------------------------------------------------------------------
 // Quadtree: one CTA per (level, frame).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) octree_kernel(const FrameLayout* __restrict__ L, const uint32_t* __restrict__ cand,
+template <int kMaxLive>
+__global__ void __launch_bounds__(256) octree_kernel(const FrameLayout* __restrict__ L, const uint32_t* __restrict__ cand,
                                                      const int* __restrict__ cand_count, int max_pts,
-                                                     uint32_t* __restrict__ sel, int* __restrict__ sel_count) {
+                                                     uint32_t* __restrict__ pts_scratch, uint16_t* __restrict__ pnode_scratch,
+                                                     uint8_t* __restrict__ pchild_scratch, uint32_t* __restrict__ sel,
+                                                     int* __restrict__ sel_count) {
   extern __shared__ __align__(16) uint8_t smem[];
-  OtState& S = *reinterpret_cast<OtState*>(smem);
-  uint32_t* pts = reinterpret_cast<uint32_t*>(smem + sizeof(OtState));
-  uint16_t* pnode = reinterpret_cast<uint16_t*>(pts + max_pts);
-  uint8_t* pchild = reinterpret_cast<uint8_t*>(pnode + max_pts);
+  OtState<kMaxLive>& S = *reinterpret_cast<OtState<kMaxLive>*>(smem);
   const int lvl = blockIdx.x, f = blockIdx.y;
   const LevelGeom& g = L->lv[lvl];
   const int tid = threadIdx.x;
+  const long long slot = ((long long)f * L->nlevels + lvl) * max_pts;
+  uint16_t* pnode = pnode_scratch + slot;
+  uint8_t* pchild = pchild_scratch + slot;
   int n_all = cand_count[f * L->nlevels + lvl];
   if (n_all > g.cand_cap) n_all = g.cand_cap;
   const uint32_t* src = cand + (long long)f * L->cand_total + g.cand_off;
-  int n;
-  if (n_all <= max_pts) {
-    for (int i = tid; i < n_all; i += blockDim.x) pts[i] = src[i];
-    n = n_all;
-  } else {
+  const uint32_t* pts = src;
+  int n = n_all;
+  if (n_all > max_pts) {
     // More survivors than the reference's buffer (Fast.hpp:30): keep the first max_pts in raster
-    // order = the max_pts smallest packed words.  Bisect on the value.
+    // order = the max_pts smallest packed words.  Bisect on the value, then gather them.
     int* cnt = &S.scalars[OT_TMP0];
     uint32_t lo = 0, hi = 0xFFFFFFFFu;
     for (int it = 0; it < 32; it++) {
@@ -566,13 +570,15 @@ __global__ void __launch_bounds__(512) octree_kernel(const FrameLayout* __restri
     }
     if (tid == 0) *cnt = 0;
     __syncthreads();
+    uint32_t* dst = pts_scratch + slot;
     for (int i = tid; i < n_all; i += blockDim.x) {
       const uint32_t v = src[i];
       if (v <= lo) {
         const int k = atomicAdd(cnt, 1);
-        if (k < max_pts) pts[k] = v;
+        if (k < max_pts) dst[k] = v;
       }
     }
+    pts = dst;
     n = max_pts;
   }
   __syncthreads();
@@ -764,6 +770,9 @@ struct swm_orb {
   int* d_retry_list = nullptr;  // [0] = count, then (frame * blocks + block) ids holding a retry tile
   int n_sm = 148;
   uint32_t *d_cand = nullptr, *d_sel = nullptr;
+  uint32_t* d_pts = nullptr;     // quadtree scratch per (frame, level): capped point list, node labels, child ids
+  uint16_t* d_pnode = nullptr;
+  uint8_t* d_pchild = nullptr;
   int *d_counts = nullptr;  // [2][B][nlevels]: candidate counts, selection counts
   // staging for the host-buffer entry points
   uint8_t* d_img = nullptr;
@@ -793,11 +802,11 @@ namespace {
 void free_frame_buffers(swm_orb* h) {
   cudaFree(h->d_lay); cudaFree(h->d_xtab); cudaFree(h->d_ytab);
   cudaFree(h->d_plain); cudaFree(h->d_blur); cudaFree(h->d_score);
-  cudaFree(h->d_retry); cudaFree(h->d_retry_list); cudaFree(h->d_fblk); cudaFree(h->d_cand); cudaFree(h->d_sel); cudaFree(h->d_counts);
+  cudaFree(h->d_retry); cudaFree(h->d_retry_list); cudaFree(h->d_fblk); cudaFree(h->d_pts); cudaFree(h->d_pnode); cudaFree(h->d_pchild); cudaFree(h->d_cand); cudaFree(h->d_sel); cudaFree(h->d_counts);
   cudaFree(h->d_img); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_n);
   h->d_lay = nullptr; h->d_xtab = h->d_ytab = nullptr;
   h->d_plain = h->d_blur = h->d_score = nullptr;
-  h->d_retry = nullptr; h->d_retry_list = nullptr; h->d_fblk = nullptr; h->d_cand = h->d_sel = nullptr; h->d_counts = nullptr;
+  h->d_retry = nullptr; h->d_retry_list = nullptr; h->d_fblk = nullptr; h->d_pts = nullptr; h->d_pnode = nullptr; h->d_pchild = nullptr; h->d_cand = h->d_sel = nullptr; h->d_counts = nullptr;
   h->d_img = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->d_n = nullptr;
   h->allocated = false;
 }
@@ -883,7 +892,7 @@ int setup_geometry(swm_orb* h, int w, int hh) {
     g.cand_off = cand_off;
     cand_off += (g.cand_cap + 31) / 32 * 32;
     g.quota = h->quota[l];
-    g.sel_cap = std::max(g.quota + 3, 4 * n_ini) + 1;
+    g.sel_cap = std::max(g.quota + 3, 4 * n_ini) + 1;  // also the bound on live quadtree nodes (<= quota + 64)
     g.sel_off = sel_off;
     sel_off += (g.sel_cap + 31) / 32 * 32;
     g.scale = h->sf[l];
@@ -911,6 +920,9 @@ int setup_geometry(swm_orb* h, int w, int hh) {
   SWM_CK(h, cudaMalloc(&h->d_retry_list, ((size_t)L.fblk_total * B + 1) * sizeof(int)));
   SWM_CK(h, cudaMalloc(&h->d_cand, (size_t)L.cand_total * B * sizeof(uint32_t)));
   SWM_CK(h, cudaMalloc(&h->d_sel, (size_t)L.sel_total * B * sizeof(uint32_t)));
+  SWM_CK(h, cudaMalloc(&h->d_pts, (size_t)h->max_pts * nl * B * sizeof(uint32_t)));
+  SWM_CK(h, cudaMalloc(&h->d_pnode, (size_t)h->max_pts * nl * B * sizeof(uint16_t)));
+  SWM_CK(h, cudaMalloc(&h->d_pchild, (size_t)h->max_pts * nl * B));
   SWM_CK(h, cudaMalloc(&h->d_counts, (size_t)2 * B * nl * sizeof(int)));
   h->img_pitch = (int)align_up(w, 4);  // rows stay word-aligned; equals the usual host stride so uploads are 1-D
   SWM_CK(h, cudaMalloc(&h->d_img, (size_t)h->img_pitch * hh * B));
@@ -936,7 +948,16 @@ int setup_geometry(swm_orb* h, int w, int hh) {
   return SWM_OK;
 }
 
-size_t octree_smem(const swm_orb* h) { return sizeof(OtState) + (size_t)h->max_pts * 7 + 16; }
+// quadtree instantiations by the largest per-level quota of the handle
+int octree_variant(const swm_orb* h) {
+  int q = 0;
+  for (int l = 0; l < h->cfg.nlevels; l++) q = std::max(q, h->quota[l]);
+  return q <= 512 ? 0 : (q <= 1024 ? 1 : 2);
+}
+size_t octree_smem(const swm_orb* h) {
+  const int v = octree_variant(h);
+  return v == 0 ? sizeof(OtState<ot_max_live(512)>) : (v == 1 ? sizeof(OtState<ot_max_live(1024)>) : sizeof(OtState<ot_max_live(2048)>));
+}
 
 // Enqueue the stages selected by `mask` for `batch` frames on `st`.
 int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, long long frame_stride,
@@ -978,8 +999,16 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
   }
   if (mask & SWM_STAGE_OCTREE) {
     dim3 grid(nl, batch);
-    octree_kernel<<<grid, 512, octree_smem(h), st>>>(h->d_lay, h->d_cand, d_cand_count, h->max_pts, h->d_sel,
-                                                     d_sel_count);
+    const int v = octree_variant(h);
+    if (v == 0)
+      octree_kernel<ot_max_live(512)><<<grid, 256, octree_smem(h), st>>>(h->d_lay, h->d_cand, d_cand_count, h->max_pts, h->d_pts,
+                                                                         h->d_pnode, h->d_pchild, h->d_sel, d_sel_count);
+    else if (v == 1)
+      octree_kernel<ot_max_live(1024)><<<grid, 256, octree_smem(h), st>>>(h->d_lay, h->d_cand, d_cand_count, h->max_pts, h->d_pts,
+                                                                          h->d_pnode, h->d_pchild, h->d_sel, d_sel_count);
+    else
+      octree_kernel<ot_max_live(2048)><<<grid, 256, octree_smem(h), st>>>(h->d_lay, h->d_cand, d_cand_count, h->max_pts, h->d_pts,
+                                                                          h->d_pnode, h->d_pchild, h->d_sel, d_sel_count);
     launches++;
   }
   if (mask & SWM_STAGE_DESCRIBE) {
@@ -1074,8 +1103,12 @@ int swm_orb_create(const swm_orb_cfg* cfg, int device, swm_orb** out) {
       if (e2 != cudaSuccess) e = e2;
     });
   }
-  if (e == cudaSuccess)
-    e = cudaFuncSetAttribute(octree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_smem(h));
+  if (e == cudaSuccess) {
+    const int v = octree_variant(h);
+    const void* fn = v == 0 ? (const void*)octree_kernel<ot_max_live(512)>
+                            : (v == 1 ? (const void*)octree_kernel<ot_max_live(1024)> : (const void*)octree_kernel<ot_max_live(2048)>);
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)octree_smem(h));
+  }
   if (e != cudaSuccess) {
     g_create_error = cuda_err("swm_orb_create", e);
     if (h->stream) cudaStreamDestroy(h->stream);

@@ -53,27 +53,29 @@ OT_DEV int pt_x(uint32_t p) { return (int)((p >> 8) & 0xFFF); }
 OT_DEV int pt_y(uint32_t p) { return (int)(p >> 20); }
 OT_DEV int pt_score(uint32_t p) { return (int)(p & 0xFF); }
 
-constexpr int kOtMaxLive = 2176;  // live quadtree nodes: quota (<= 2048) + 3, or 4 * n_ini, with slack
-constexpr int kOtMaxQuota = 2048;
+constexpr int kOtMaxQuota = 2048;  // largest per-level quota any instantiation serves
 constexpr int kOtMaxIni = 16;
 constexpr int kOtNone = 0xFFFF;
+// Live quadtree nodes never exceed max(quota + 3, 4 * n_ini); the state is a template on
+// that bound so small quotas (the usual 1000/2000-feature extractors) leave room for several CTAs per SM.
+constexpr int ot_max_live(int max_quota) { return max_quota + 64; }
 
 struct OtNode {
   int16_t ulx, uly, brx, bry;
 };
 
-// Shared-memory working set (the kernel carves this out of dynamic smem; pts/pnode sized by the
-// configured candidate cap).
+// Shared-memory working set of one (frame, level) quadtree.  Points and their labels live in global
+// memory (L1/L2 resident, a few thousand entries).
+template <int kMaxLive>
 struct OtState {
-  OtNode nodes[2][kOtMaxLive];
-  uint32_t cnt[2][kOtMaxLive];      // points per node
-  uint32_t ord[kOtMaxLive];         // old position -> processing index this round (kOtNone if not split-able)
-  uint32_t cand[kOtMaxLive];        // processing index -> old position
-  uint32_t ccnt[kOtMaxLive][4];     // per processing index: points per child
-  uint32_t cbase[kOtMaxLive + 1];   // exclusive prefix of non-empty children over processing order
-  uint32_t spos[kOtMaxLive + 1];    // old position -> new position if it survives un-split
+  OtNode nodes[2][kMaxLive];
+  uint32_t cnt[2][kMaxLive];      // points per node
+  uint32_t ord[kMaxLive];         // old position -> processing index this round (kOtNone if not split-able)
+  uint32_t cand[kMaxLive];        // processing index -> old position
+  uint32_t ccnt[kMaxLive][4];     // per processing index: points per child; reused as per-leaf winner key
+  uint32_t cbase[kMaxLive + 1];   // exclusive prefix of non-empty children over processing order
+  uint32_t spos[kMaxLive + 1];    // old position -> new position if it survives un-split
   uint32_t scan_tmp[1024 + 32];
-  uint32_t best[kOtMaxLive];
   int scalars[16];
 };
 
@@ -117,7 +119,8 @@ OT_DEV void ot_exclusive_scan(uint32_t* a, int n, uint32_t* tmp, uint32_t* total
 
 // pts: packed candidates (ROI coords), n <= capacity of pnode.  Writes the selection (list order)
 // to out[0..ret) and returns the count.  W,H = ROI extent (maxX-minX, maxY-minY), N = quota.
-OT_DEV int ot_distribute(OtState& S, const uint32_t* pts, uint16_t* pnode, uint8_t* pchild, int n, int W, int H, int N,
+template <int kMaxLive>
+OT_DEV int ot_distribute(OtState<kMaxLive>& S, const uint32_t* pts, uint16_t* pnode, uint8_t* pchild, int n, int W, int H, int N,
                          uint32_t* out, int out_cap) {
   int* sc = S.scalars;
   if (n == 0) return 0;
@@ -300,17 +303,18 @@ OT_DEV int ot_distribute(OtState& S, const uint32_t* pts, uint16_t* pnode, uint8
   const int cur = sc[OT_CUR];
   const int L = sc[OT_L];
   (void)cur;
-  OT_FOR(i, L) S.best[i] = 0;
+  uint32_t* best = &S.ccnt[0][0];  // the child counters are dead by now
+  OT_FOR(i, L) best[i] = 0;
   OT_SYNC();
   OT_FOR(p, n) {
     const uint32_t v = pts[p];
     const uint32_t key = ((uint32_t)pt_score(v) << 24) | (0xFFFFFFu - (v >> 8));
-    ot_atomic_max(&S.best[pnode[p]], key);
+    ot_atomic_max(&best[pnode[p]], key);
   }
   OT_SYNC();
   OT_FOR(i, L) {
     if (i < out_cap) {
-      const uint32_t key = S.best[i];
+      const uint32_t key = best[i];
       const uint32_t yx = 0xFFFFFFu - (key & 0xFFFFFFu);
       out[i] = (yx << 8) | (key >> 24);
     }

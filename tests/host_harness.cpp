@@ -7,7 +7,7 @@
 #include <vector>
 
 extern "C" int hh_octree(const uint32_t* pts, int n, int W, int H, int N, uint32_t* out, int out_cap) {
-  static swm::OtState S;
+  static swm::OtState<swm::ot_max_live(2048)> S;
   std::vector<uint16_t> pnode(n + 1);
   std::vector<uint8_t> pchild(n + 1);
   return swm::ot_distribute(S, pts, pnode.data(), pchild.data(), n, W, H, N, out, out_cap);
