@@ -302,6 +302,46 @@ def main():
     barrier()
     ms_ham = h0.elapsed_time(h1) / reps
 
+    # ---- single-frame latency of the drop-in operator() path and per-call matcher times (rank 0, informational)
+    extras = {}
+    if rank == 0:
+        from swarmmap_b200.matcher import Frame, ORBmatcher
+        ex1 = ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local_rank, max_batch=1)
+        for _ in range(5):
+            ex1(frames[0])
+        t0 = time.perf_counter()
+        for i in range(50):
+            ex1(frames[i % B])
+        extras["single_frame_operator_ms"] = (time.perf_counter() - t0) / 50 * 1e3
+        seq = synth.make_sequence(3, 1241, 376, 20220405)
+        ex4k = ORBextractor(4000, 1.2, 8, 20, 7, device=local_rank, max_batch=1)
+        fs = [Frame.from_keypoints(*ex4k(img), 1241, 376, ex4k.GetScaleFactors()) for img in seq]
+        m = ORBmatcher(0.9, True, device=local_rank)
+        prev0 = np.stack([fs[0].x, fs[0].y], 1).astype(np.float32)
+        for _ in range(3):
+            m.SearchForInitialization(fs[0], fs[1], prev0.copy(), 100)
+        t0 = time.perf_counter()
+        for i in range(20):
+            nm, _ = m.SearchForInitialization(fs[0], fs[1 + i % 2], prev0.copy(), 100)
+        extras["search_for_initialization_ms"] = (time.perf_counter() - t0) / 20 * 1e3
+        extras["search_for_initialization_cfg"] = f"KITTI-shaped 1241x376, {fs[0].N} x {fs[1].N} keypoints, window 100, host arrays in/out, {nm} matches"
+        sf = ex4k.GetScaleFactors()
+        u, v = fs[0].x.copy(), fs[0].y.copy()
+        valid = np.ones(fs[0].N, np.uint8)
+        fs[1].mvScaleFactors = sf
+        for _ in range(3):
+            m.SearchByProjectionLastFrame(fs[1], fs[0], u, v, valid, 15)
+        t0 = time.perf_counter()
+        for i in range(20):
+            m.SearchByProjectionLastFrame(fs[1], fs[0], u, v, valid, 15)
+        extras["search_by_projection_ms"] = (time.perf_counter() - t0) / 20 * 1e3
+        if not args.no_cpu_baseline:
+            import oracle_lib
+            t0 = time.perf_counter()
+            for i in range(5):
+                oracle_lib.search_for_initialization(fs[0], fs[1 + i % 2], prev0, 100, 0.9, True)
+            extras["search_for_initialization_cpu_oracle_ms"] = (time.perf_counter() - t0) / 5 * 1e3
+
     # ---- reduce over ranks (max time), rank 0 prints
     t = torch.tensor([ms_total, t_e2e * 1e3, stage_ms["pyramid_fast_blur"] + stage_ms["nms"], ms_ham],
                      dtype=torch.float64, device=dev)
@@ -344,6 +384,7 @@ def main():
             "clocks": clocks,
             "stages_ms_per_step": stage_ms,
             "keypoints_per_frame": float(cnt.item()) / (world * B),
+            "latency": extras,
             "hamming": {"metric": "hamming_matches_per_sec", "value": world * NQ * KF_PER_RANK * DPK / (ms_ham * 1e-3),
                         "unit": "256-bit pairs/s", "ms_per_query_batch": ms_ham,
                         "config": f"{NQ} queries x {KF_PER_RANK * DPK} descriptors per GPU shard ({KF_PER_RANK} keyframes x {DPK}), "
