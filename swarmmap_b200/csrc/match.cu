@@ -15,6 +15,9 @@
 // accept/steal state is order dependent, and that is replayed by a single warp over the
 // pre-computed candidate rows (resolve_kernel), which keeps match indices bit-exact.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -301,121 +304,224 @@ __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v)
   return v;
 }
 
-__global__ void __launch_bounds__(32) resolve_kernel(ResolveArgs a) {
-  const int lane = threadIdx.x;
+// The greedy state a row reads: "is candidate j still available" (per mode).
+__device__ __forceinline__ bool cand_skip(const ResolveArgs& a, const int* matched_dist, const uint8_t* blocked, int j,
+                                          unsigned dist) {
+  if (a.mode == kModeInit) return matched_dist[j] <= (int)dist;       // :414-415
+  if (a.mode == kModeBowKf) return blocked[j] || !a.valid2[j];        // :531-535
+  return blocked[j] != 0;                                             // :67-69,:196-197,:306,:1291,:1413
+}
+
+// Replays the reference's greedy loop.  Within a call the state only ever REMOVES candidates
+// (blocked[] gets set, vMatchedDistance[] only decreases), and removing candidate t changes a row's
+// outcome only if t is that row's best or (when a ratio test is used) second-best candidate.  So the
+// block evaluates a batch of consecutive rows speculatively (one warp per row, against the state at
+// batch start), marks the target each accepted row takes, and commits rows in order up to the first
+// row whose best / second-best target is taken by an earlier row of the batch; that row starts the
+// next batch.  Every committed row decided exactly as the serial loop would: indices stay bit-exact.
+constexpr int kResolveWarps = 32;
+
+__global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs a) {
+  extern __shared__ __align__(16) uint8_t dsm[];
+  __shared__ int s_row[kResolveWarps], s_accept[kResolveWarps], s_best_idx[kResolveWarps], s_best_dist[kResolveWarps];
+  __shared__ int s_second_idx[kResolveWarps], s_after[kResolveWarps];
+  __shared__ int s_src[kResolveWarps], s_blk[kResolveWarps], s_bin[kResolveWarps];
+  __shared__ int s_nb, s_cursor, s_nmatches, s_batches;
+  __shared__ int s_hist[kHistoLen];
+  __shared__ int s_keep[3];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned long long kNone = ~0ull;
-  int nmatches = 0;
-  for (int r = 0; r < a.rows; r++) {
-    const int s = a.row_src ? a.row_src[r] : r;
-    if (a.row_valid && !a.row_valid[s]) continue;
-    const int b = a.row_start[r], e = a.row_start[r + 1];
-    if (b == e) continue;
-    // key = dist << 32 | position: min key = smallest distance, first in enumeration order
-    unsigned long long best = kNone;
-    for (int c = b + lane; c < e; c += 32) {
-      const int j = a.cand_idx[c];
-      const unsigned dist = a.cand_val[c] & 0xFFFFu;
-      bool skip;
-      if (a.mode == kModeInit) skip = a.matched_dist[j] <= (int)dist;            // :414-415
-      else if (a.mode == kModeBowKf) skip = a.blocked[j] || !a.valid2[j];          // :531-535
-      else skip = a.blocked[j] != 0;                                               // :67-69,:196-197,:306,:1291,:1413
-      if (!skip) {
-        const unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(c - b);
-        best = key < best ? key : best;
-      }
-    }
-    best = warp_min_u64(best);
-    if (best == kNone) continue;
-    const int best_pos = (int)(best & 0xFFFFFFFFu);
-    const int best_dist = (int)(best >> 32);
-    // second best: P = first minimum before the winner, Q = first minimum after it; the running
-    // "bestDist2" of the reference ends as P if P <= Q else Q (matcher section).
-    unsigned long long p = kNone, q = kNone;
-    for (int c = b + lane; c < e; c += 32) {
-      if (c - b == best_pos) continue;
-      const int j = a.cand_idx[c];
-      const unsigned dist = a.cand_val[c] & 0xFFFFu;
-      bool skip;
-      if (a.mode == kModeInit) skip = a.matched_dist[j] <= (int)dist;
-      else if (a.mode == kModeBowKf) skip = a.blocked[j] || !a.valid2[j];
-      else skip = a.blocked[j] != 0;
-      if (!skip) {
-        const unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(c - b);
-        if (c - b < best_pos) p = key < p ? key : p;
-        else q = key < q ? key : q;
-      }
-    }
-    p = warp_min_u64(p);
-    q = warp_min_u64(q);
-    const unsigned long long sec = (p >> 32) <= (q >> 32) ? p : q;
-    const bool has_second = sec != kNone;
-    const int best_idx = a.cand_idx[b + best_pos];
-    const int best_level = (int)(a.cand_val[b + best_pos] >> 16);
-    int second_dist, second_level = -1;
-    if (has_second) {
-      second_dist = (int)(sec >> 32);
-      second_level = (int)(a.cand_val[b + (int)(sec & 0xFFFFFFFFu)] >> 16);
-    } else {
-      second_dist = a.mode == kModeInit ? 0x7FFFFFFF : 256;  // INT_MAX (:404) vs 256 (:57,:190)
-    }
-    bool accept;
+  const int n2 = a.n2;
+  // greedy state lives in shared memory
+  int* matched_dist = reinterpret_cast<int*>(dsm);
+  int* matches21 = matched_dist + (a.mode == kModeInit ? n2 : 0);
+  uint8_t* blocked = reinterpret_cast<uint8_t*>(matches21 + (a.mode == kModeInit ? n2 : 0));
+  int* mark = reinterpret_cast<int*>(blocked + ((n2 + 3) & ~3));
+  for (int j = tid; j < n2; j += blockDim.x) {
     if (a.mode == kModeInit) {
-      accept = best_dist <= kThLow && (float)best_dist < __fmul_rn((float)second_dist, a.nnratio);  // :426-427
-    } else if (a.mode == kModeWindow) {
-      accept = best_dist <= a.th_dist;                                                             // :111,:365,:1316,:1428
-      if (accept && a.ratio_mode == 1 && best_level == second_level &&
-          (float)best_dist > __fmul_rn(a.nnratio, (float)second_dist))                             // :112
-        accept = false;
-    } else if (a.mode == kModeBowFrame) {
-      accept = best_dist <= kThLow && (float)best_dist < __fmul_rn(a.nnratio, (float)second_dist);  // :212-213
-    } else {
-      accept = best_dist < kThLow && (float)best_dist < __fmul_rn(a.nnratio, (float)second_dist);   // :550-551
+      matched_dist[j] = 0x7FFFFFFF;
+      matches21[j] = -1;
     }
-    if (!accept) continue;
-    if (lane == 0) {
-      int ev_tgt = best_idx;
-      if (a.mode == kModeInit) {
-        const int prev_owner = a.matches21[best_idx];
-        if (prev_owner >= 0) {  // steal (:428-431)
-          a.out[prev_owner] = -1;
-          nmatches--;
-        }
-        a.out[s] = best_idx;
-        a.matches21[best_idx] = s;
-        a.matched_dist[best_idx] = best_dist;
-        ev_tgt = s;
-      } else if (a.mode == kModeWindow) {
-        a.out[best_idx] = s;
-        if (a.blocks[s]) a.blocked[best_idx] = 1;
-      } else if (a.mode == kModeBowFrame) {
-        a.out[best_idx] = s;
-        a.blocked[best_idx] = 1;
-      } else {
-        a.out[s] = best_idx;
-        a.blocked[best_idx] = 1;
-        ev_tgt = s;
-      }
-      nmatches++;
-      if (a.check_ori) {
-        a.ev_bin[s] = rot_bin(a.angle1[s], a.angle2[best_idx]);
-        a.ev_tgt[s] = ev_tgt;
-      }
-    }
-    __syncwarp();
-    __threadfence_block();
+    blocked[j] = a.mode == kModeInit ? 0 : a.blocked[j];
+    mark[j] = 0x7FFFFFFF;
   }
-  __syncwarp();
-  __threadfence_block();
-  // rotation-consistency pruning (e.g. :229-246): histogram of accepted events, keep the top three bins
+  if (tid == 0) {
+    s_cursor = 0;
+    s_nmatches = 0;
+    s_batches = 0;
+  }
+  __syncthreads();
+
+  while (true) {
+    // ---- 1. next batch: up to kResolveWarps valid, non-empty rows in order
+    if (wid == 0) {
+      int nb = 0, cur = s_cursor;
+      while (nb < kResolveWarps && cur < a.rows) {
+        const int r = cur + lane;
+        bool ok = false;
+        if (r < a.rows) {
+          const int s = a.row_src ? a.row_src[r] : r;
+          ok = (!a.row_valid || a.row_valid[s]) && a.row_start[r] != a.row_start[r + 1];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        const int k = nb + __popc(m & ((1u << lane) - 1));
+        if (ok && k < kResolveWarps) {
+          s_row[k] = r;
+          s_after[k] = r + 1;
+        }
+        nb = min(kResolveWarps, nb + __popc(m));
+        cur += 32;
+      }
+      if (lane == 0) s_nb = nb;
+    }
+    __syncthreads();
+    const int nb = s_nb;
+    if (nb == 0) break;
+
+    // ---- 2. speculative evaluation, one warp per row
+    if (wid < nb) {
+      int b, e, best_pos = -1;
+      const int r = s_row[wid];
+      b = a.row_start[r];
+      e = a.row_start[r + 1];
+      unsigned long long best = kNone;  // key = dist << 32 | position: smallest distance, first in enumeration order
+      for (int c = b + lane; c < e; c += 32) {
+        const int j = a.cand_idx[c];
+        const unsigned dist = a.cand_val[c] & 0xFFFFu;
+        if (!cand_skip(a, matched_dist, blocked, j, dist)) {
+          const unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(c - b);
+          best = key < best ? key : best;
+        }
+      }
+      best = warp_min_u64(best);
+      bool accept = false;
+      int best_idx = -1, best_dist = 0, second_idx = -1;
+      if (best != kNone) {
+        best_pos = (int)(best & 0xFFFFFFFFu);
+        best_dist = (int)(best >> 32);
+        best_idx = a.cand_idx[b + best_pos];
+        const bool need_second = !(a.mode == kModeWindow && a.ratio_mode == 0);
+        int second_dist = a.mode == kModeInit ? 0x7FFFFFFF : 256, second_level = -1;  // INT_MAX (:404) vs 256 (:57,:190)
+        if (need_second) {
+          // second best: P = first minimum before the winner, Q = first minimum after it; the running
+          // "bestDist2" of the reference ends as P if P <= Q else Q (matcher section).
+          unsigned long long p = kNone, q = kNone;
+          for (int c = b + lane; c < e; c += 32) {
+            if (c - b == best_pos) continue;
+            const int j = a.cand_idx[c];
+            const unsigned dist = a.cand_val[c] & 0xFFFFu;
+            if (!cand_skip(a, matched_dist, blocked, j, dist)) {
+              const unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(c - b);
+              if (c - b < best_pos) p = key < p ? key : p;
+              else q = key < q ? key : q;
+            }
+          }
+          p = warp_min_u64(p);
+          q = warp_min_u64(q);
+          const unsigned long long sec = (p >> 32) <= (q >> 32) ? p : q;
+          if (sec != kNone) {
+            second_dist = (int)(sec >> 32);
+            second_level = (int)(a.cand_val[b + (int)(sec & 0xFFFFFFFFu)] >> 16);
+            second_idx = a.cand_idx[b + (int)(sec & 0xFFFFFFFFu)];
+          }
+        }
+        const int best_level = (int)(a.cand_val[b + best_pos] >> 16);
+        if (a.mode == kModeInit) {
+          accept = best_dist <= kThLow && (float)best_dist < __fmul_rn((float)second_dist, a.nnratio);  // :426-427
+        } else if (a.mode == kModeWindow) {
+          accept = best_dist <= a.th_dist;                                                             // :111,:365,:1316,:1428
+          if (accept && a.ratio_mode == 1 && best_level == second_level &&
+              (float)best_dist > __fmul_rn(a.nnratio, (float)second_dist))                             // :112
+            accept = false;
+        } else if (a.mode == kModeBowFrame) {
+          accept = best_dist <= kThLow && (float)best_dist < __fmul_rn(a.nnratio, (float)second_dist);  // :212-213
+        } else {
+          accept = best_dist < kThLow && (float)best_dist < __fmul_rn(a.nnratio, (float)second_dist);   // :550-551
+        }
+      }
+      if (lane == 0) {
+        s_accept[wid] = accept;
+        s_best_idx[wid] = best_idx;
+        s_best_dist[wid] = best_dist;
+        s_second_idx[wid] = second_idx;
+        // everything the in-order commit needs from global memory is fetched here, in parallel
+        const int s = a.row_src ? a.row_src[r] : r;
+        s_src[wid] = s;
+        s_blk[wid] = (a.mode == kModeWindow && accept) ? a.blocks[s] : 1;
+        s_bin[wid] = (accept && a.check_ori) ? rot_bin(a.angle1[s], a.angle2[best_idx]) : -1;
+        if (accept) atomicMin(mark + best_idx, wid);
+      }
+    }
+    __syncthreads();
+
+    // ---- 3. commit, by the lanes of warp 0 (lane k = row k of the batch).  A row conflicts if an earlier
+    // row of this batch removes its best (or, when a ratio test is in play, second-best) candidate; rows
+    // before the first conflict touch pairwise different targets, so their commits are independent.
+    if (wid == 0) {
+      const bool uses_second = !(a.mode == kModeWindow && a.ratio_mode == 0);
+      const int k = lane;
+      bool conflict = false, acc = false;
+      int bi = -1;
+      if (k < nb) {
+        bi = s_best_idx[k];
+        const int si = s_second_idx[k];
+        acc = s_accept[k] != 0;
+        conflict = bi >= 0 && (uses_second || acc) && (mark[bi] < k || (si >= 0 && mark[si] < k));
+      }
+      const unsigned cm = __ballot_sync(0xffffffffu, conflict);
+      const int first = cm ? __ffs(cm) - 1 : nb;
+      int delta = 0;
+      if (k < first && acc) {
+        const int s = s_src[k];
+        int ev_tgt = bi;
+        if (a.mode == kModeInit) {
+          const int prev_owner = matches21[bi];
+          if (prev_owner >= 0) {  // steal (:428-431)
+            a.out[prev_owner] = -1;
+            delta--;
+          }
+          a.out[s] = bi;
+          matches21[bi] = s;
+          matched_dist[bi] = s_best_dist[k];
+          ev_tgt = s;
+        } else if (a.mode == kModeWindow) {
+          a.out[bi] = s;
+          if (s_blk[k]) blocked[bi] = 1;
+        } else if (a.mode == kModeBowFrame) {
+          a.out[bi] = s;
+          blocked[bi] = 1;
+        } else {
+          a.out[s] = bi;
+          blocked[bi] = 1;
+          ev_tgt = s;
+        }
+        delta++;
+        if (a.check_ori) {
+          a.ev_bin[s] = s_bin[k];
+          a.ev_tgt[s] = ev_tgt;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
+      __syncwarp();
+      if (k < nb && acc) mark[bi] = 0x7FFFFFFF;
+      if (lane == 0) {
+        s_nmatches += delta;
+        s_batches++;
+        s_cursor = first < nb ? s_row[first] : s_after[nb - 1];
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- rotation-consistency pruning (e.g. :229-246): histogram of accepted events, keep the top three bins
   if (a.check_ori) {
-    __shared__ int s_hist[kHistoLen];
-    __shared__ int s_keep[3];
-    if (lane < kHistoLen) s_hist[lane] = 0;
-    __syncwarp();
-    for (int s = lane; s < a.n1; s += 32)
+    if (tid < kHistoLen) s_hist[tid] = 0;
+    __syncthreads();
+    for (int s = tid; s < a.n1; s += blockDim.x)
       if (a.ev_bin[s] >= 0) atomicAdd(&s_hist[a.ev_bin[s]], 1);
-    __syncwarp();
-    if (lane == 0) {  // ComputeThreeMaxima, :1475-1506
+    __syncthreads();
+    if (tid == 0) {  // ComputeThreeMaxima, :1475-1506
       int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
       for (int i = 0; i < kHistoLen; i++) {
         const int c = s_hist[i];
@@ -438,9 +544,9 @@ __global__ void __launch_bounds__(32) resolve_kernel(ResolveArgs a) {
       }
       s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
     }
-    __syncwarp();
+    __syncthreads();
     int dropped = 0;
-    for (int s = lane; s < a.n1; s += 32) {
+    for (int s = tid; s < a.n1; s += blockDim.x) {
       const int bin = a.ev_bin[s];
       if (bin < 0 || bin == s_keep[0] || bin == s_keep[1] || bin == s_keep[2]) continue;
       const int t = a.ev_tgt[s];
@@ -454,14 +560,11 @@ __global__ void __launch_bounds__(32) resolve_kernel(ResolveArgs a) {
         dropped++;
       }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) dropped += __shfl_xor_sync(0xffffffffu, dropped, o);
-    nmatches -= dropped;  // lane 0's running count minus everybody's drops
+    if (dropped) atomicSub(&s_nmatches, dropped);
   }
-  __syncwarp();
-  __threadfence_block();
+  __syncthreads();
   if (a.mode == kModeInit) {  // :474-476
-    for (int s = lane; s < a.n1; s += 32) {
+    for (int s = tid; s < a.n1; s += blockDim.x) {
       const int j = a.out[s];
       if (j >= 0) {
         a.prev_xy[2 * s] = a.x2[j];
@@ -469,7 +572,10 @@ __global__ void __launch_bounds__(32) resolve_kernel(ResolveArgs a) {
       }
     }
   }
-  if (lane == 0) *a.nmatches = nmatches;
+  if (tid == 0) {
+    a.nmatches[0] = s_nmatches;
+    a.nmatches[1] = s_batches;  // diagnostics: speculative batches executed
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -561,9 +667,17 @@ using namespace swm;
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
+  bool owned = true;
+  void view(void* ptr) {  // point into the upload arena (non-owning)
+    if (owned && p) cudaFree(p);
+    p = ptr;
+    cap = 0;
+    owned = false;
+  }
   cudaError_t ensure(size_t bytes) {
-    if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (owned && bytes <= cap) return cudaSuccess;
+    if (owned && p) cudaFree(p);
+    owned = true;
     p = nullptr;
     cap = 0;
     size_t want = bytes + bytes / 2 + 256;
@@ -572,9 +686,10 @@ struct DevBuf {
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (owned && p) cudaFree(p);
     p = nullptr;
     cap = 0;
+    owned = true;
   }
   template <typename T>
   T* as() const { return reinterpret_cast<T*>(p); }
@@ -589,7 +704,15 @@ struct swm_matcher {
   DevBuf q[10];
   DevBuf rows[5];  // row_count, row_start, cand_idx, cand_val, row_src
   DevBuf state[7]; // blocked, matched_dist, matches21, out, ev_bin, ev_tgt, nmatches/prev
+  // upload arena: every host array of a call is packed into one pinned buffer and sent with ONE copy
+  uint8_t* h_arena = nullptr;
+  uint8_t* d_arena = nullptr;
+  size_t arena_cap = 0, arena_used = 0;
   void free_all() {
+    if (h_arena) cudaFreeHost(h_arena);
+    if (d_arena) cudaFree(d_arena);
+    h_arena = d_arena = nullptr;
+    arena_cap = arena_used = 0;
     for (auto& a : f) for (auto& b : a) b.release();
     for (auto& b : q) b.release();
     for (auto& b : rows) b.release();
@@ -601,6 +724,21 @@ namespace {
 
 thread_local std::string g_match_create_error;
 
+// SWM_MATCH_PROFILE=1: print host-side phase times of each matcher call to stderr (debug aid).
+struct PhaseTimer {
+  bool on;
+  cudaStream_t st;
+  std::chrono::steady_clock::time_point t0;
+  explicit PhaseTimer(cudaStream_t s) : on(getenv("SWM_MATCH_PROFILE") != nullptr), st(s) { t0 = std::chrono::steady_clock::now(); }
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[swm match] %-18s %8.1f us\n", what, std::chrono::duration<double, std::micro>(t1 - t0).count());
+    t0 = t1;
+  }
+};
+
 #define MCK(m, call)                                   \
   do {                                                 \
     cudaError_t e_ = (call);                           \
@@ -610,19 +748,49 @@ thread_local std::string g_match_create_error;
     }                                                  \
   } while (0)
 
-int upload(swm_matcher* m, DevBuf& b, const void* src, size_t bytes) {
-  MCK(m, b.ensure(bytes ? bytes : 4));
-  if (bytes) MCK(m, cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, m->stream));
+// Reserve the upload arena for one call (upper bound on the packed bytes); previous views die here.
+int arena_begin(swm_matcher* m, size_t bytes) {
+  bytes += 4096;
+  if (bytes > m->arena_cap) {
+    MCK(m, cudaStreamSynchronize(m->stream));
+    if (m->h_arena) cudaFreeHost(m->h_arena);
+    if (m->d_arena) cudaFree(m->d_arena);
+    m->h_arena = m->d_arena = nullptr;
+    m->arena_cap = 0;
+    const size_t want = bytes + bytes / 2;
+    MCK(m, cudaMallocHost(&m->h_arena, want));
+    MCK(m, cudaMalloc(&m->d_arena, want));
+    m->arena_cap = want;
+  }
+  m->arena_used = 0;
   return SWM_OK;
 }
+
+// Packs a host array into the arena; `b` becomes a view of its device copy (valid after arena_flush).
+int upload(swm_matcher* m, DevBuf& b, const void* src, size_t bytes) {
+  const size_t off = (m->arena_used + 255) & ~(size_t)255;
+  if (off + bytes > m->arena_cap) { m->err = "internal: upload arena overflow"; return SWM_E_CAPACITY; }
+  if (bytes) memcpy(m->h_arena + off, src, bytes);
+  b.view(m->d_arena + off);
+  m->arena_used = off + bytes;
+  return SWM_OK;
+}
+
+int arena_flush(swm_matcher* m) {
+  if (m->arena_used)
+    MCK(m, cudaMemcpyAsync(m->d_arena, m->h_arena, m->arena_used, cudaMemcpyHostToDevice, m->stream));
+  return SWM_OK;
+}
+
+size_t frame_bytes(const swm_frame_view* f) { return (size_t)f->n * 48 + 5 * 256; }
 
 bool frame_ok(const swm_frame_view* f) {
   return f && f->n >= 0 && (f->n == 0 || (f->x && f->y && f->octave && f->angle && f->desc)) && f->max_x > f->min_x &&
          f->max_y > f->min_y;
 }
 
-// Uploads a frame and builds its grid on the device.
-int upload_frame(swm_matcher* m, int slot, const swm_frame_view* f, FrameDev* out, bool want_grid) {
+// Packs a frame's arrays into the upload arena (device views valid after arena_flush).
+int upload_frame(swm_matcher* m, int slot, const swm_frame_view* f, FrameDev* out) {
   const size_t n = (size_t)f->n;
   int rc;
   if ((rc = upload(m, m->f[slot][0], f->x, n * 4))) return rc;
@@ -642,17 +810,38 @@ int upload_frame(swm_matcher* m, int slot, const swm_frame_view* f, FrameDev* ou
   d.inv_h = (float)kGridRows / (float)(f->max_y - f->min_y);
   d.starts = nullptr;
   d.items = nullptr;
-  if (want_grid) {
-    MCK(m, m->f[slot][5].ensure(((size_t)kCells + 1 + 2 * n + 8) * 4));
-    int32_t* starts = m->f[slot][5].as<int32_t>();
-    int32_t* items = starts + kCells + 1;
-    int32_t* cell_of = items + n + 4;
-    grid_build_kernel<<<1, 1024, 0, m->stream>>>(d, starts, items, cell_of);
-    MCK(m, cudaGetLastError());
-    d.starts = starts;
-    d.items = items;
-  }
   *out = d;
+  return SWM_OK;
+}
+
+// Builds the frame grid on the device (after arena_flush).
+int build_grid(swm_matcher* m, int slot, FrameDev* d) {
+  const size_t n = (size_t)d->n;
+  MCK(m, m->f[slot][5].ensure(((size_t)kCells + 1 + 2 * n + 8) * 4));
+  int32_t* starts = m->f[slot][5].as<int32_t>();
+  int32_t* items = starts + kCells + 1;
+  int32_t* cell_of = items + n + 4;
+  grid_build_kernel<<<1, 1024, 0, m->stream>>>(*d, starts, items, cell_of);
+  MCK(m, cudaGetLastError());
+  d->starts = starts;
+  d->items = items;
+  return SWM_OK;
+}
+
+int launch_resolve(swm_matcher* m, const ResolveArgs& a) {
+  const size_t n2 = (size_t)a.n2;
+  const size_t bytes = (a.mode == kModeInit ? 8 * n2 : 0) + ((n2 + 3) & ~(size_t)3) + 4 * n2 + 16;
+  if (bytes > 200 * 1024) {
+    m->err = "target frame too large for the matcher's shared-memory state (n2 limit ~15000 keypoints)";
+    return SWM_E_CAPACITY;
+  }
+  static bool attr_set[64] = {};
+  if (!attr_set[m->device & 63]) {
+    MCK(m, cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set[m->device & 63] = true;
+  }
+  resolve_kernel<<<1, kResolveWarps * 32, bytes, m->stream>>>(a);
+  MCK(m, cudaGetLastError());
   return SWM_OK;
 }
 
@@ -766,8 +955,11 @@ int swm_grid_build(swm_matcher* m, const swm_frame_view* f, int32_t* starts, int
   if (!frame_ok(f) || !starts || !items) { m->err = "bad argument"; return SWM_E_INVALID; }
   MCK(m, cudaSetDevice(m->device));
   FrameDev d;
-  int rc = upload_frame(m, 0, f, &d, true);
-  if (rc) return rc;
+  int rc;
+  if ((rc = arena_begin(m, frame_bytes(f)))) return rc;
+  if ((rc = upload_frame(m, 0, f, &d))) return rc;
+  if ((rc = arena_flush(m))) return rc;
+  if ((rc = build_grid(m, 0, &d))) return rc;
   MCK(m, cudaMemcpyAsync(starts, d.starts, ((size_t)kCells + 1) * 4, cudaMemcpyDeviceToHost, m->stream));
   MCK(m, cudaStreamSynchronize(m->stream));
   const int total = starts[kCells];
@@ -786,8 +978,9 @@ int swm_match_init(swm_matcher* m, const swm_frame_view* f1, const swm_frame_vie
   MCK(m, cudaSetDevice(m->device));
   FrameDev d1, d2;
   int rc;
-  if ((rc = upload_frame(m, 0, f1, &d1, false))) return rc;
-  if ((rc = upload_frame(m, 1, f2, &d2, true))) return rc;
+  if ((rc = arena_begin(m, frame_bytes(f1) + frame_bytes(f2) + (size_t)n1 * 32 + 8 * 256))) return rc;
+  if ((rc = upload_frame(m, 0, f1, &d1))) return rc;
+  if ((rc = upload_frame(m, 1, f2, &d2))) return rc;
   // sources = F1 keypoints at octave 0 (:390-392), window centre = vbPrevMatched, levels (0,0) (:394-396)
   std::vector<float> u(n1), v(n1), rad(n1, (float)window);
   std::vector<int32_t> lv(n1, 0);
@@ -804,6 +997,8 @@ int swm_match_init(swm_matcher* m, const swm_frame_view* f1, const swm_frame_vie
   if ((rc = upload(m, m->q[3], lv.data(), (size_t)n1 * 4))) return rc;
   if ((rc = upload(m, m->q[4], valid.data(), (size_t)n1))) return rc;
   if ((rc = upload(m, m->q[5], prev_xy, (size_t)n1 * 8))) return rc;
+  if ((rc = arena_flush(m))) return rc;
+  if ((rc = build_grid(m, 1, &d2))) return rc;
   WindowDev q;
   q.m = n1;
   q.desc = d1.desc;
@@ -847,7 +1042,7 @@ int swm_match_init(swm_matcher* m, const swm_frame_view* f1, const swm_frame_vie
   a.prev_xy = m->q[5].as<float>();
   a.x2 = d2.x; a.y2 = d2.y;
   a.nmatches = m->state[6].as<int32_t>();
-  resolve_kernel<<<1, 32, 0, m->stream>>>(a);
+  if ((rc = launch_resolve(m, a))) return rc;
   MCK(m, cudaGetLastError());
   MCK(m, cudaMemcpyAsync(matches12, a.out, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
   MCK(m, cudaMemcpyAsync(prev_xy, a.prev_xy, (size_t)n1 * 8, cudaMemcpyDeviceToHost, m->stream));
@@ -870,9 +1065,11 @@ int swm_match_window(swm_matcher* m, const swm_frame_view* tgt, const swm_window
   const int M = wq->m, n2 = tgt->n;
   if (M == 0 || n2 == 0) return SWM_OK;
   MCK(m, cudaSetDevice(m->device));
+  PhaseTimer pt(m->stream);
   FrameDev d2;
   int rc;
-  if ((rc = upload_frame(m, 1, tgt, &d2, true))) return rc;
+  if ((rc = arena_begin(m, frame_bytes(tgt) + (size_t)M * 64 + (size_t)n2 * 8 + 16 * 256))) return rc;
+  if ((rc = upload_frame(m, 1, tgt, &d2))) return rc;
   if ((rc = upload(m, m->q[0], wq->u, (size_t)M * 4))) return rc;
   if ((rc = upload(m, m->q[1], wq->v, (size_t)M * 4))) return rc;
   if ((rc = upload(m, m->q[2], wq->radius, (size_t)M * 4))) return rc;
@@ -882,6 +1079,14 @@ int swm_match_window(swm_matcher* m, const swm_frame_view* tgt, const swm_window
   if ((rc = upload(m, m->q[7], wq->desc, (size_t)M * 32))) return rc;
   if ((rc = upload(m, m->q[8], wq->blocks, (size_t)M))) return rc;
   if (check_ori && (rc = upload(m, m->q[9], wq->angle, (size_t)M * 4))) return rc;
+  // initial greedy state travels in the same packed upload
+  std::vector<uint8_t> zero_blocked;
+  if (!tgt_blocked) zero_blocked.assign((size_t)n2, 0);
+  if ((rc = upload(m, m->state[0], tgt_blocked ? tgt_blocked : zero_blocked.data(), (size_t)n2))) return rc;
+  if ((rc = upload(m, m->state[3], assignment, (size_t)n2 * 4))) return rc;
+  if ((rc = arena_flush(m))) return rc;
+  pt.mark("upload (1 copy)");
+  if ((rc = build_grid(m, 1, &d2))) return rc;
   WindowDev q;
   q.m = M;
   q.desc = m->q[7].as<uint4>();
@@ -893,14 +1098,10 @@ int swm_match_window(swm_matcher* m, const swm_frame_view* tgt, const swm_window
   q.valid = m->q[4].as<uint8_t>();
   int total = 0;
   if ((rc = build_window_rows(m, d2, q, &total))) return rc;
-  MCK(m, m->state[0].ensure((size_t)n2));
-  MCK(m, m->state[3].ensure((size_t)n2 * 4));
+  pt.mark("grid + window rows");
   MCK(m, m->state[4].ensure((size_t)M * 4));
   MCK(m, m->state[5].ensure((size_t)M * 4));
   MCK(m, m->state[6].ensure(16));
-  if (tgt_blocked) MCK(m, cudaMemcpyAsync(m->state[0].p, tgt_blocked, (size_t)n2, cudaMemcpyHostToDevice, m->stream));
-  else MCK(m, cudaMemsetAsync(m->state[0].p, 0, (size_t)n2, m->stream));
-  MCK(m, cudaMemcpyAsync(m->state[3].p, assignment, (size_t)n2 * 4, cudaMemcpyHostToDevice, m->stream));
   MCK(m, cudaMemsetAsync(m->state[4].p, 0xFF, (size_t)M * 4, m->stream));
   ResolveArgs a;
   memset(&a, 0, sizeof(a));
@@ -923,11 +1124,18 @@ int swm_match_window(swm_matcher* m, const swm_frame_view* tgt, const swm_window
   a.ev_bin = m->state[4].as<int32_t>();
   a.ev_tgt = m->state[5].as<int32_t>();
   a.nmatches = m->state[6].as<int32_t>();
-  resolve_kernel<<<1, 32, 0, m->stream>>>(a);
-  MCK(m, cudaGetLastError());
+  pt.mark("state init");
+  if ((rc = launch_resolve(m, a))) return rc;
+  pt.mark("resolve");
+  if (pt.on) {
+    int dbg[2] = {0, 0};
+    cudaMemcpy(dbg, a.nmatches, 8, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[swm match] rows %d batches %d matches %d\n", M, dbg[1], dbg[0]);
+  }
   MCK(m, cudaMemcpyAsync(assignment, a.out, (size_t)n2 * 4, cudaMemcpyDeviceToHost, m->stream));
   MCK(m, cudaMemcpyAsync(nmatches, a.nmatches, 4, cudaMemcpyDeviceToHost, m->stream));
   MCK(m, cudaStreamSynchronize(m->stream));
+  pt.mark("download");
   return SWM_OK;
 }
 
@@ -976,13 +1184,15 @@ int swm_match_bow(swm_matcher* m, const swm_frame_view* f1, const swm_featvec* f
   MCK(m, cudaSetDevice(m->device));
   FrameDev d1, d2;
   int rc;
-  if ((rc = upload_frame(m, 0, f1, &d1, false))) return rc;
-  if ((rc = upload_frame(m, 1, f2, &d2, false))) return rc;
+  if ((rc = arena_begin(m, frame_bytes(f1) + frame_bytes(f2) + (size_t)R * 8 + cand.size() * 4 + (size_t)n2 + 8 * 256))) return rc;
+  if ((rc = upload_frame(m, 0, f1, &d1))) return rc;
+  if ((rc = upload_frame(m, 1, f2, &d2))) return rc;
   if ((rc = upload(m, m->rows[4], row_src.data(), (size_t)R * 4))) return rc;
   if ((rc = upload(m, m->rows[1], row_start.data(), (size_t)(R + 1) * 4))) return rc;
   if ((rc = upload(m, m->rows[2], cand.data(), cand.size() * 4))) return rc;
-  MCK(m, m->rows[3].ensure((cand.size() + 1) * 4));
   if (mode == 1 && (rc = upload(m, m->q[4], valid2, (size_t)n2))) return rc;
+  if ((rc = arena_flush(m))) return rc;
+  MCK(m, m->rows[3].ensure((cand.size() + 1) * 4));
   list_rows_kernel<<<(R + 7) / 8, 256, 0, m->stream>>>(d1.desc, d2.desc, d2.octave, R, m->rows[4].as<int32_t>(),
                                                       m->rows[1].as<int32_t>(), m->rows[2].as<int32_t>(),
                                                       m->rows[3].as<uint32_t>());
@@ -1013,7 +1223,7 @@ int swm_match_bow(swm_matcher* m, const swm_frame_view* f1, const swm_featvec* f
   ra.ev_bin = m->state[4].as<int32_t>();
   ra.ev_tgt = m->state[5].as<int32_t>();
   ra.nmatches = m->state[6].as<int32_t>();
-  resolve_kernel<<<1, 32, 0, m->stream>>>(ra);
+  if ((rc = launch_resolve(m, ra))) return rc;
   MCK(m, cudaGetLastError());
   MCK(m, cudaMemcpyAsync(matches, ra.out, (size_t)n_out * 4, cudaMemcpyDeviceToHost, m->stream));
   MCK(m, cudaMemcpyAsync(nmatches, ra.nmatches, 4, cudaMemcpyDeviceToHost, m->stream));
