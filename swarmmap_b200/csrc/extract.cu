@@ -163,9 +163,8 @@ __global__ void __launch_bounds__(256) pyr_kernel(const PyrArgs a) {
   uint8_t* dplain = a.plain + roi0;
   uint8_t* dblur = a.blur + roi0;
   const int pitch = a.dst.pitch;
-  const bool edge_tile = (x0 <= kEdge) || (x0 + TW >= w - 1 - kEdge) || (y0 <= kEdge) || (y0 + TH >= h - 1 - kEdge);
 
-  // ---- un-blurred tile and the border pixels that mirror into it
+  // ---- un-blurred tile and the border rows that mirror into it
 #pragma unroll
   for (int pass = 0; pass < 2; pass++) {
     const int r = (tid >> 4) + 16 * pass, j = tid & 15;
@@ -173,27 +172,31 @@ __global__ void __launch_bounds__(256) pyr_kernel(const PyrArgs a) {
     if (gy < h && gx < w) {
       const uint32_t word = s_px[(r + 3) * PS_WORDS + j + 1];
       store4(dplain + (long long)gy * pitch, gx, w, word);
-      if (edge_tile) {
-        // copyMakeBorder(BORDER_REFLECT_101, 19): every in-image pixel also lands at the border
-        // positions that reflect onto it (ORBextractor.cc:846-851).  Row mirrors are whole-word stores;
-        // column mirrors (byte order reversed) only exist in the first / last tile column.
-        int ys[3], ny = 0;
-        ys[ny++] = gy;
-        if (gy >= 1 && gy <= kEdge) ys[ny++] = -gy;
-        if (gy >= h - 1 - kEdge && gy <= h - 2) ys[ny++] = 2 * (h - 1) - gy;
-        for (int iy = 1; iy < ny; iy++) store4(dplain + (long long)ys[iy] * pitch, gx, w, word);
-        if (gx <= kEdge || gx + 3 >= w - 1 - kEdge) {
-          for (int k = 0; k < 4; k++) {
-            const int x = gx + k;
-            if (x >= w) break;
-            const uint8_t v = (uint8_t)(word >> (8 * k));
-            for (int iy = 0; iy < ny; iy++) {
-              uint8_t* drow = dplain + (long long)ys[iy] * pitch;
-              if (x >= 1 && x <= kEdge) drow[-x] = v;
-              if (x >= w - 1 - kEdge && x <= w - 2) drow[2 * (w - 1) - x] = v;
-            }
-          }
-        }
+      // copyMakeBorder(BORDER_REFLECT_101, 19), rows: an in-image row within 19 px of the top / bottom edge
+      // is also the border row that reflects onto it (ORBextractor.cc:846-851) -> same word, mirrored row.
+      if (gy >= 1 && gy <= kEdge) store4(dplain + (long long)(-gy) * pitch, gx, w, word);
+      if (gy >= h - 1 - kEdge && gy <= h - 2) store4(dplain + (long long)(2 * (h - 1) - gy) * pitch, gx, w, word);
+    }
+  }
+  // copyMakeBorder, columns: only tiles that hold x in [1,19] or [w-20,w-2] take part; each such pixel is
+  // written to its mirrored column, in its own row and in that row's mirrored rows (the corners).
+  {
+    const int lo0 = max(x0, 1), hi0 = min(x0 + TW - 1, kEdge);                  // left strip sources
+    const int lo1 = max(x0, w - 1 - kEdge), hi1 = min(x0 + TW - 1, w - 2);      // right strip sources
+    const int n0 = max(hi0 - lo0 + 1, 0), n1 = max(hi1 - lo1 + 1, 0);
+    const int ncols = n0 + n1;
+    if (ncols > 0) {
+      const uint8_t* s_pxb = reinterpret_cast<const uint8_t*>(s_px);
+      for (int i = tid; i < TH * ncols; i += 256) {
+        const int r = i / ncols, ci = i - r * ncols;
+        const int gy = y0 + r;
+        if (gy >= h) break;
+        const int x = ci < n0 ? lo0 + ci : lo1 + (ci - n0);
+        const int dx = ci < n0 ? -x : 2 * (w - 1) - x;
+        const uint8_t v = s_pxb[(r + 3) * PS_COLS + (x - x0) + 4];
+        dplain[(long long)gy * pitch + dx] = v;
+        if (gy >= 1 && gy <= kEdge) dplain[(long long)(-gy) * pitch + dx] = v;
+        if (gy >= h - 1 - kEdge && gy <= h - 2) dplain[(long long)(2 * (h - 1) - gy) * pitch + dx] = v;
       }
     }
   }
