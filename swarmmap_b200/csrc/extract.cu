@@ -272,8 +272,39 @@ __global__ void __launch_bounds__(256) pyr_kernel(const PyrArgs a) {
 // Survivors are appended (unordered) to the per-(frame, level) candidate list; everything
 // downstream orders by explicit keys, so the append order does not matter.
 // ------------------------------------------------------------------------------------------------
-constexpr int FS_WORDS = 19, FS_COLS = FS_WORDS * 4, FS_ROWS = TH + 8;  // staged 76 x 40 bytes
+// Staged tile: 96 x 40 bytes whose first column is level x = 64*bx, i.e. 16-byte aligned in the plane, so
+// every row is one TMA bulk copy (cp.async.bulk, 96 B) completing on an mbarrier.  Local column of the
+// first interior pixel (level x = 19 + 64 bx) is kFx = 19; local row of the first interior row is 4.
+constexpr int FS_WORDS = 24, FS_COLS = FS_WORDS * 4, FS_ROWS = TH + 8;
+constexpr int kFx = 19;
 constexpr int FS_MAXCAND = 66 * 34;
+
+// ---- mbarrier / TMA bulk-copy helpers (PTX ISA: mbarrier, cp.async.bulk)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t done;
+  int spins = 0;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    if (!done && ++spins > (1 << 22)) __trap();  // a lost transaction must abort, not hang the GPU
+  } while (!done);
+}
 
 __device__ __forceinline__ uint32_t oob_mask(uint32_t a, uint32_t v, uint32_t c7) {
   // bit 7 of each byte set iff |a - v| > th, with c7 = (127 - th) * 0x01010101
@@ -325,8 +356,12 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
   __shared__ int s_total, s_n2, s_blk;
   __shared__ int s_any[2];
   __shared__ uint8_t s_flag[12];
+  __shared__ __align__(8) uint64_t s_bar;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nblk = L->fblk_total;
+  uint32_t bar_phase = 0;
+  if (tid == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
   // pass 1: one block per (frame, tile pair).  pass 2: a persistent grid walks the list of blocks that
   // hold a retry tile (appended by pass 1), so the common "nothing to retry" case costs almost nothing.
   for (int work = blockIdx.x;; work += gridDim.x) {
@@ -351,7 +386,7 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
     const bool has_t1 = 2 * bx + 1 < g.tiles_x;
     const int w = g.w, h = g.h;
     const int X0 = kEdge + 64 * bx, Y0 = kEdge + 32 * by;  // first interior pixel (level coords)
-    const int sx0 = X0 - 7, sy0 = Y0 - 4;                  // staged origin; sx0 = 12 + 64 bx is 4-aligned
+    const int sx0 = X0 - kFx, sy0 = Y0 - 4;                // staged origin; sx0 = 64 bx is 16-byte aligned
     if (pass == 2 && tid < 12) {
       const int ny = by + tid / 4 - 1, nx = 2 * bx + (tid & 3) - 1;
       s_flag[tid] = (ny >= 0 && ny < g.tiles_y && nx >= 0 && nx < g.tiles_x) ? fretry[ny * g.tiles_x + nx] : 0;
@@ -359,9 +394,9 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
     if (tid < 2) s_any[tid] = 0;
     if (tid == 2) s_n2 = 0;
     if (tid >= 32 && tid < 32 + FS_WORDS) {
-      // per-word byte mask of the columns that are scored: local x in [6, 71] and level x in [19, w-19)
+      // per-word byte mask of the columns that are scored: interior +- 1 px and level x in [19, w-19)
       const int jw = tid - 32;
-      const int lo = max(6, kEdge - sx0), hi = min(71, w - kEdge - 1 - sx0);
+      const int lo = max(kFx - 1, kEdge - sx0), hi = min(kFx + 64, w - kEdge - 1 - sx0);
       uint32_t m = 0;
       for (int k = 0; k < 4; k++)
         if (4 * jw + k >= lo && 4 * jw + k <= hi) m |= 0x80u << (8 * k);
@@ -371,32 +406,27 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
     uint8_t* s_scb = reinterpret_cast<uint8_t*>(s_sc);
     const uint8_t* s_pxb = reinterpret_cast<const uint8_t*>(s_px);
 
-    {  // stage 76 x 40 bytes: all loads first, then the stores
-      uint32_t v[3];
-#pragma unroll
-      for (int it = 0; it < 3; it++) {
-        const int i = tid + 256 * it;
-        const int r = i / FS_WORDS, j = i - r * FS_WORDS;
-        const int gy = sy0 + r, gx = sx0 + 4 * j;
-        v[it] = 0;
-        if (i < FS_ROWS * FS_WORDS && gy < h + kEdge && gx < w + kEdge - 3)
-          v[it] = __ldg(reinterpret_cast<const uint32_t*>(roi + (long long)gy * g.pitch + gx));
+    // ---- stage 96 x 40 bytes: warp 0 issues one TMA bulk copy per row (rows past the plane are skipped: only
+    // pixels outside the FAST band could read them, and those are masked), the others clear the score tile.
+    if (wid == 0) {
+      const int nrows = min(FS_ROWS, h + kEdge - sy0);
+      if (lane == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&s_bar, (uint32_t)nrows * FS_COLS);
       }
-#pragma unroll
-      for (int it = 0; it < 3; it++) {
-        const int i = tid + 256 * it;
-        if (i < FS_ROWS * FS_WORDS) {
-          s_px[i] = v[it];
-          s_sc[i] = 0;
-        }
-      }
+      __syncwarp();
+      for (int r = lane; r < nrows; r += 32)
+        bulk_g2s(s_px + r * FS_WORDS, roi + (long long)(sy0 + r) * g.pitch + sx0, FS_COLS, &s_bar);
     }
+    for (int i = tid; i < FS_ROWS * FS_WORDS; i += 256) s_sc[i] = 0;
+    mbar_wait(&s_bar, bar_phase);
+    bar_phase ^= 1;
     __syncthreads();
 
     // Pass 1 only ever uses S_hi (scores below iniThFAST count as 0), so it detects at iniThFAST: same
     // keypoints, a fraction of the candidates.  Pass 2 (and the debug score map) need S at minThFAST.
     const int th_run = (pass == 1 && dbg_score == nullptr) ? ini_th : min_th;
-    // ---- packed quick reject on the scored region (interior + 1 px): rows ly 3..36, words 1..17
+    // ---- packed quick reject on the scored region (interior + 1 px): rows ly 3..36, words 4..20
     const uint32_t c7 = (uint32_t)(127 - th_run) * 0x01010101u;
     uint32_t masks[3];
     int n_mine = 0;
@@ -405,7 +435,7 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
       const int i = tid + 256 * it;
       uint32_t m = 0;
       if (i < 34 * 17) {
-        const int r = i / 17, ly = r + 3, jw = i - r * 17 + 1;
+        const int r = i / 17, ly = r + 3, jw = i - r * 17 + 4;
         const int gy = sy0 + ly;
         if (gy >= kEdge && gy < h - kEdge) {
           const uint32_t* row = s_px + ly * FS_WORDS + jw;
@@ -448,7 +478,7 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
       const uint32_t m = masks[it];
       if (m) {
         const int i = tid + 256 * it;
-        const int r = i / 17, ly = r + 3, jw = i - r * 17 + 1;
+        const int r = i / 17, ly = r + 3, jw = i - r * 17 + 4;
 #pragma unroll
         for (int k = 0; k < 4; k++)
           if (m & (0x80u << (8 * k))) s_list[pos++] = (uint16_t)((ly << 7) | (4 * jw + k));
@@ -463,8 +493,8 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
       const int ly = e >> 7, lx = e & 127;
       const int sc = fast_score_x2(s_pxb + ly * FS_COLS + lx, FS_COLS, th_run);
       s_scb[ly * FS_COLS + lx] = (uint8_t)sc;
-      if (sc >= (pass == 1 ? ini_th : 1) && lx >= 7 && lx <= 70 && ly >= 4 && ly <= 35 &&
-          (pass == 1 || s_flag[4 + 1 + (lx >= 39 ? 1 : 0)] != 0))
+      if (sc >= (pass == 1 ? ini_th : 1) && lx >= kFx && lx <= kFx + 63 && ly >= 4 && ly <= 35 &&
+          (pass == 1 || s_flag[4 + 1 + (lx >= kFx + 32 ? 1 : 0)] != 0))
         s_list2[atomicAdd(&s_n2, 1)] = (uint16_t)e;
     }
     __syncthreads();
@@ -492,13 +522,13 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
             if (pass == 2) {
               const int qx = lx + dx, qy = ly + dy;
               const int fy = qy < 4 ? 0 : (qy > 35 ? 2 : 1);
-              const int fx = qx < 7 ? 0 : (qx < 39 ? 1 : (qx < 71 ? 2 : 3));
+              const int fx = qx < kFx ? 0 : (qx < kFx + 32 ? 1 : (qx < kFx + 64 ? 2 : 3));
               raw = s_flag[fy * 4 + fx] != 0;
             }
             if (!raw && q < ini_th) q = 0;
             kp = kp && c > q;
           }
-        if (kp && pass == 1) s_any[lx >= 39 ? 1 : 0] = 1;
+        if (kp && pass == 1) s_any[lx >= kFx + 32 ? 1 : 0] = 1;
       }
       const unsigned m = __ballot_sync(0xffffffffu, kp);
       if (m) {
@@ -523,7 +553,7 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
       if (dbg_score) {  // parity introspection only: the score map S at minThFAST for the block interior
         uint8_t* sc = dbg_score + (long long)f * L->slab_bytes + g.plane_off + (long long)kEdge * g.pitch + kPadX;
         for (int i = tid; i < 64 * 32; i += 256) {
-          const int ly = (i >> 6) + 4, lx = (i & 63) + 7;
+          const int ly = (i >> 6) + 4, lx = (i & 63) + kFx;
           const int gx = sx0 + lx, gy = sy0 + ly;
           if (gx < w - kEdge && gy < h - kEdge) sc[(long long)gy * g.pitch + gx] = s_scb[ly * FS_COLS + lx];
         }
@@ -916,7 +946,7 @@ int setup_geometry(swm_orb* h, int w, int hh) {
   SWM_CK(h, cudaMalloc(&h->d_lay, sizeof(FrameLayout)));
   SWM_CK(h, cudaMalloc(&h->d_xtab, xt.size() * sizeof(ResizeTap)));
   SWM_CK(h, cudaMalloc(&h->d_ytab, yt.size() * sizeof(ResizeTap)));
-  SWM_CK(h, cudaMalloc(&h->d_plain, (size_t)L.slab_bytes * B));
+  SWM_CK(h, cudaMalloc(&h->d_plain, (size_t)L.slab_bytes * B + 1024));  // + slack: bulk-copied rows may overhang the last plane
   SWM_CK(h, cudaMalloc(&h->d_blur, (size_t)L.slab_bytes * B));
   if (h->debug_score) SWM_CK(h, cudaMalloc(&h->d_score, (size_t)L.slab_bytes * B));
   SWM_CK(h, cudaMalloc(&h->d_retry, (size_t)L.tiles_total * B));
