@@ -158,6 +158,116 @@ class ORBmatcher {
     return n;
   }
 
+  // ---- Project MapPoints seen in a KeyFrame into the Frame (relocalisation), ORBmatcher.cc:1356-1473.
+  template <class FrameT, class KeyFrameT, class MapPointT>
+  int SearchByProjection(FrameT& CurrentFrame, KeyFrameT* pKF, const std::set<MapPointT*>& sAlreadyFound, const float th,
+                         const int ORBdist, const bool bGlobal = false) {
+    FlatFrame cur;
+    gather(CurrentFrame, cur);
+    const std::vector<MapPointT*> vpMPs = pKF->GetMapPointMatches();
+    const int M = (int)vpMPs.size();
+    Query q(M);
+    float R[9], t[3];
+    pose(CurrentFrame.mTcw, R, t);
+    // Ow = -Rcw^T * tcw (:1362)
+    float Ow[3];
+    for (int c = 0; c < 3; c++)
+      Ow[c] = (float)-((double)R[c] * t[0] + (double)R[3 + c] * t[1] + (double)R[6 + c] * t[2]);
+    for (int i = 0; i < M; i++) {
+      MapPointT* pMP = vpMPs[i];
+      if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;     // :1379
+      float xw[3];
+      world_pos(bGlobal ? pMP->GetGlobalPos() : pMP->GetWorldPos(), xw);  // :1382
+      float xc[3];
+      transform(R, t, xw, xc);
+      const float invzc = 1.0 / xc[2];
+      const float u = FrameT::fx * xc[0] * invzc + FrameT::cx;            // :1389-1390
+      const float v = FrameT::fy * xc[1] * invzc + FrameT::cy;
+      if (u < FrameT::mnMinX || u > FrameT::mnMaxX) continue;
+      if (v < FrameT::mnMinY || v > FrameT::mnMaxY) continue;
+      const float dx = xw[0] - Ow[0], dy = xw[1] - Ow[1], dz = xw[2] - Ow[2];
+      const float dist3D = std::sqrt(dx * dx + dy * dy + dz * dz);        // cv::norm(PO), :1399
+      if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+      const int lvl = pMP->PredictScale(dist3D, CurrentFrame.mfLogScaleFactor, CurrentFrame.mnScaleLevels);
+      q.valid[i] = 1;
+      q.u[i] = u; q.v[i] = v;
+      q.radius[i] = th * CurrentFrame.mvScaleFactors[lvl];                // :1413
+      q.min_level[i] = lvl - 1; q.max_level[i] = lvl + 1;
+      q.angle[i] = pKF->mvKeysUn[i].angle;
+      q.blocks[i] = 1;
+      std::memcpy(&q.desc[(size_t)i * 32], descriptor_of(pMP).ptr(0), 32);
+    }
+    std::vector<uint8_t> blocked(cur.n, 0);
+    for (int j = 0; j < cur.n; j++) blocked[j] = CurrentFrame.mvpMapPoints[j] != nullptr;  // :1425
+    const int32_t kUntouched = -3;
+    std::vector<int32_t> asg(cur.n, kUntouched);
+    int n = 0;
+    swm_frame_view vc = cur.view();
+    swm_window_query wq = q.view();
+    check(swm_match_window(m_, &vc, &wq, blocked.data(), ORBdist, 0, mfNNratio, mbCheckOrientation, asg.data(), &n));
+    for (int j = 0; j < cur.n; j++) {
+      if (asg[j] >= 0) CurrentFrame.mvpMapPoints[j] = vpMPs[asg[j]];
+      else if (asg[j] == -1) CurrentFrame.mvpMapPoints[j] = nullptr;
+    }
+    return n;
+  }
+
+  // ---- Project MapPoints with a Sim3 into a KeyFrame (loop closing), ORBmatcher.cc:264-373.
+  template <class KeyFrameT, class MatT, class MapPointT>
+  int SearchByProjection(KeyFrameT* pKF, const MatT& Scw, const std::vector<MapPointT*>& vpPoints,
+                         std::vector<MapPointT*>& vpMatched, int th) {
+    FlatFrame kf;
+    gather(*pKF, kf);
+    // decompose Scw (:273-277)
+    float sR[9], st[3];
+    pose(Scw, sR, st);
+    const float scw = std::sqrt(sR[0] * sR[0] + sR[1] * sR[1] + sR[2] * sR[2]);
+    float R[9], t[3], Ow[3];
+    for (int i = 0; i < 9; i++) R[i] = sR[i] / scw;
+    for (int i = 0; i < 3; i++) t[i] = st[i] / scw;
+    for (int c = 0; c < 3; c++)
+      Ow[c] = (float)-((double)R[c] * t[0] + (double)R[3 + c] * t[1] + (double)R[6 + c] * t[2]);
+    std::set<MapPointT*> found(vpMatched.begin(), vpMatched.end());
+    found.erase(static_cast<MapPointT*>(nullptr));
+    const int M = (int)vpPoints.size();
+    Query q(M);
+    for (int i = 0; i < M; i++) {
+      MapPointT* pMP = vpPoints[i];
+      if (pMP->isBad() || found.count(pMP)) continue;                     // :291
+      float xw[3], xc[3];
+      world_pos(pMP->GetWorldPos(), xw);
+      transform(R, t, xw, xc);
+      if (xc[2] < 0.0) continue;                                          // :301
+      const float invz = 1 / xc[2];
+      const float u = pKF->fx * (xc[0] * invz) + pKF->cx;
+      const float v = pKF->fy * (xc[1] * invz) + pKF->cy;
+      if (!pKF->IsInImage(u, v)) continue;                                // :314
+      const float dx = xw[0] - Ow[0], dy = xw[1] - Ow[1], dz = xw[2] - Ow[2];
+      const float dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+      if (dist < pMP->GetMinDistanceInvariance() || dist > pMP->GetMaxDistanceInvariance()) continue;
+      float pn[3];
+      world_pos(pMP->GetNormal(), pn);
+      if (dx * pn[0] + dy * pn[1] + dz * pn[2] < 0.5 * dist) continue;    // :327
+      const int lvl = pMP->PredictScale(dist, pKF->mfLogScaleFactor, pKF->mnScaleLevels);
+      q.valid[i] = 1;
+      q.u[i] = u; q.v[i] = v;
+      q.radius[i] = th * pKF->mvScaleFactors[lvl];                        // :334
+      q.min_level[i] = lvl - 1; q.max_level[i] = lvl;                     // :351
+      q.blocks[i] = 1;
+      std::memcpy(&q.desc[(size_t)i * 32], descriptor_of(pMP).ptr(0), 32);
+    }
+    std::vector<uint8_t> blocked(kf.n, 0);
+    for (int j = 0; j < kf.n; j++) blocked[j] = vpMatched[j] != nullptr;  // :346
+    std::vector<int32_t> asg(kf.n, -1);
+    int n = 0;
+    swm_frame_view vk = kf.view();
+    swm_window_query wq = q.view();
+    check(swm_match_window(m_, &vk, &wq, blocked.data(), TH_LOW, 0, mfNNratio, 0, asg.data(), &n));
+    for (int j = 0; j < kf.n; j++)
+      if (asg[j] >= 0) vpMatched[j] = vpPoints[asg[j]];                   // :366
+    return n;
+  }
+
   // ---- Search matches between MapPoints in a KeyFrame and ORB in a Frame (ORBmatcher.cc:150-262).
   template <class KeyFrameT, class FrameT, class MapPointT>
   int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches) {

@@ -181,6 +181,31 @@ class ORBmatcher:
         return self.match_window(F, desc, proj_u, proj_v, radius, pred_level - 1, pred_level, valid, blocks,
                                  self.TH_HIGH, 1, None, blocked, check_ori=False)
 
+    def SearchByProjectionKeyFrame(self, cur, kf_desc, kf_angle, proj_u, proj_v, pred_level, valid, th, ORBdist,
+                                   cur_has_mappoint=None):
+        """SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist, bGlobal) (relocalisation),
+        ORBmatcher.cc:1356-1473.  valid[i]: the KeyFrame MapPoint exists, is good, is not in sAlreadyFound,
+        projects inside the image and its distance is inside the scale-invariance range (caller-side checks
+        :1380-1407); pred_level = PredictScale.  Any already-assigned slot of `cur` is unavailable (:1413)."""
+        sf = np.asarray(cur.mvScaleFactors, np.float32)
+        pred_level = np.asarray(pred_level, np.int32)
+        radius = (np.float32(th) * sf[pred_level]).astype(np.float32)
+        ones = np.ones(len(proj_u), np.uint8)
+        return self.match_window(cur, kf_desc, proj_u, proj_v, radius, pred_level - 1, pred_level + 1, valid, ones,
+                                 int(ORBdist), 0, kf_angle, cur_has_mappoint)
+
+    def SearchByProjectionSim3(self, kf, desc, proj_u, proj_v, pred_level, valid, th, already_matched=None):
+        """SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (loop closing), ORBmatcher.cc:264-373.
+        valid[i]: the point is good, not already found, in front of the camera, inside the image, inside its
+        distance range and within 60 degrees of its normal (caller-side checks :289-329).  The level filter
+        [pred-1, pred] of :349-352 is applied inside the window query; no ratio test, no orientation check."""
+        sf = np.asarray(kf.mvScaleFactors, np.float32)
+        pred_level = np.asarray(pred_level, np.int32)
+        radius = (np.float32(th) * sf[pred_level]).astype(np.float32)
+        ones = np.ones(len(proj_u), np.uint8)
+        return self.match_window(kf, desc, proj_u, proj_v, radius, pred_level - 1, pred_level, valid, ones,
+                                 self.TH_LOW, 0, None, already_matched, check_ori=False)
+
     # ---- SearchByBoW (ORBmatcher.cc:150-262 KeyFrame->Frame, :481-597 KeyFrame<->KeyFrame)
     def SearchByBoW(self, KF, fvKF, validKF, F, fvF, validF=None):
         mode = 0 if validF is None else 1

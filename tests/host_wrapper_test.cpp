@@ -25,6 +25,11 @@ struct MapPoint {
   float mTrackProjX = 0, mTrackProjY = 0, mTrackViewCos = 1.0f;
   int mnTrackScaleLevel = 0;
   Mat4 GetWorldPos() { return pos; }
+  Mat4 GetGlobalPos() { return pos; }
+  Mat4 GetNormal() { Mat4 n; n.v[0] = 0; n.v[1] = 0; n.v[2] = 1; return n; }
+  float GetMinDistanceInvariance() { return 0.1f; }
+  float GetMaxDistanceInvariance() { return 100.f; }
+  int PredictScale(float, float, int) { return mnTrackScaleLevel; }
   cv::Mat GetDescriptor() { return desc; }
   int Observations() { return nobs; }
   bool isBad() { return bad; }
@@ -34,11 +39,14 @@ struct Frame {
   int N = 0;
   std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
   cv::Mat mDescriptors;
-  float mnMinX = 0, mnMinY = 0, mnMaxX = 752, mnMaxY = 480;
   std::vector<MapPoint*> mvpMapPoints;
   std::vector<bool> mvbOutlier;
   Mat4 mTcw;
-  float fx = 458.654f, fy = 457.296f, cx = 367.215f, cy = 248.375f;
+  static constexpr float fx = 458.654f, fy = 457.296f, cx = 367.215f, cy = 248.375f;
+  static constexpr float mnMinX = 0, mnMinY = 0, mnMaxX = 752, mnMaxY = 480;
+  float mfLogScaleFactor = 0.1823f;
+  int mnScaleLevels = 8;
+  bool IsInImage(float x, float y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }
   std::vector<float> mvScaleFactors;
   std::map<unsigned, std::vector<unsigned>> mFeatVec;
   std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
@@ -102,6 +110,19 @@ int main(int argc, char** argv) {
   const int n_bow = mb.SearchByBoW(&f1, f3, bow);
   std::vector<MapPoint*> bow2;
   const int n_bow2 = mb.SearchByBoW(&f1, &f2, bow2);
+  Frame f4;
+  fill(f4, ex, img);
+  std::set<MapPoint*> already;
+  ORB_SLAM2::ORBmatcher mr(0.9f, true);
+  const int n_reloc = mr.SearchByProjection(f4, &f1, already, 10.0f, 100);
+  Frame f5;
+  fill(f5, ex, img);
+  Mat4 Scw;
+  std::vector<MapPoint*> matched(f5.N, nullptr);
+  ORB_SLAM2::ORBmatcher ml(0.75f, true);
+  const int n_loop = ml.SearchByProjection(&f5, Scw, local, matched, 10);
+  std::printf("reloc %d loop %d\n", n_reloc, n_loop);
+  if (n_reloc < f1.N / 2 || n_loop < f1.N / 2) { std::printf("HOST_WRAPPER_FAIL\n"); return 1; }
   const int d0 = ORB_SLAM2::ORBmatcher::DescriptorDistance(f1.mDescriptors.row(0), f1.mDescriptors.row(0));
   const int d1 = ORB_SLAM2::ORBmatcher::DescriptorDistance(f1.mDescriptors.row(0), f1.mDescriptors.row(1));
   std::printf("init %d proj %d self %d mappoints %d bow %d bowkf %d d0 %d d1 %d\n", n_init, n_proj, self, n_mp, n_bow,

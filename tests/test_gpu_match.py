@@ -140,6 +140,31 @@ def test_search_by_projection_wrappers(oracle, swm, frames):
     assert n == on and (asg == oasg).all() and n > 100
 
 
+def test_search_by_projection_reloc_and_loop_wrappers(oracle, swm, frames):
+    from swarmmap_b200.matcher import ORBmatcher
+    kf, cur = frames["kitti"][0], frames["kitti"][2]
+    rng = np.random.default_rng(9)
+    u = kf.x + rng.normal(0, 3, kf.N).astype(np.float32)
+    v = kf.y + rng.normal(0, 3, kf.N).astype(np.float32)
+    valid = (rng.random(kf.N) < 0.9).astype(np.uint8)
+    pred = np.clip(kf.octave + rng.integers(-1, 2, kf.N), 0, 7).astype(np.int32)
+    sf = cur.mvScaleFactors
+    has_mp = (rng.random(cur.N) < 0.2).astype(np.uint8)
+    ones = np.ones(kf.N, np.uint8)
+    for th, orbdist in ((10, 100), (3, 64)):  # Tracking.cc:1235 / :1248
+        m = ORBmatcher(0.9, True)
+        n, asg = m.SearchByProjectionKeyFrame(cur, kf.desc, kf.angle, u, v, pred, valid, th, orbdist, has_mp)
+        on, oasg = oracle.match_window(cur, kf.desc, u, v, (np.float32(th) * sf[pred]).astype(np.float32), pred - 1,
+                                       pred + 1, valid, ones, orbdist, 0, 0.9, True, kf.angle, has_mp)
+        assert n == on and (asg == oasg).all() and n > 50
+    m = ORBmatcher(0.75, True)
+    found = (rng.random(cur.N) < 0.3).astype(np.uint8)
+    n, asg = m.SearchByProjectionSim3(cur, kf.desc, u, v, pred, valid, 10, found)
+    on, oasg = oracle.match_window(cur, kf.desc, u, v, (np.float32(10) * sf[pred]).astype(np.float32), pred - 1, pred,
+                                   valid, ones, 50, 0, 0.75, False, None, found)
+    assert n == on and (asg == oasg).all() and n > 50
+
+
 def _buckets(desc, seed=7, n_nodes=1000):
     """Synthetic vocabulary buckets (ORBvoc.bin is a missing blob): node = hash of 10 descriptor bits."""
     rng = np.random.default_rng(seed)
