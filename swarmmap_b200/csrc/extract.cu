@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
         bulk_g2s(s_px + r * FS_WORDS, roi + (long long)(sy0 + r) * g.pitch + sx0, FS_COLS, &s_bar);
     }
     for (int i = tid; i < FS_ROWS * FS_WORDS; i += 256) s_sc[i] = 0;
-    mbar_wait(&s_bar, bar_phase);
+    if (wid == 0) mbar_wait(&s_bar, bar_phase);  // one warp polls the mbarrier, the rest park on the CTA barrier
     bar_phase ^= 1;
     __syncthreads();
 
