@@ -38,6 +38,15 @@ UNIT = "frames/s"
 WORKLOAD = "EuRoC-shaped 752x480 8-bit frames, ORBextractor(1000, 1.2, 8, 20, 7), extract+describe"
 
 
+def _traffic_per_frame():
+    """DRAM bytes per frame of the roofline kernels from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "r1i_traffic.json")
+    try:
+        return float(json.load(open(p))["dram_bytes_per_frame"])
+    except Exception:
+        return None
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -376,7 +385,9 @@ def main():
                     "note": f"pinned host buffers, {nslot} extractor handles x {eb}-frame chunks in flight"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": (_traffic_per_frame() * B if _traffic_per_frame() else None),
+                         "traffic_source": "ncu dram__bytes_read+write, same 10 launches at B=256 (profiles/r1i_traffic.json)",
+                         "peak_source": peak_src,
                          "kernel": "pyr_kernel x8 (pyramid+border, blur fused) + fast_kernel x2 (FAST score+tile retry+NMS)",
                          "bytes_per_frame": PYR_FAST_BYTES, "ms_per_launch_set": ms_pf,
                          "frac_counting_fused_blur_bytes": (PYR_FAST_BYTES + BLUR_BYTES) * B / (ms_pf * 1e-3) / 1e9 / peak},
