@@ -628,6 +628,132 @@ __global__ void __launch_bounds__(kDbQPerCta) db_top2_kernel(const uint4* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Tensor-core variant of the shard scan.  With descriptors expanded to 0/1 bytes,
+//     hamming(q, d) = popc(q) + popc(d) - 2 * dot(q, d),
+// and dot() over 256 dimensions is eight m16n8k32 u8 x u8 -> s32 MMAs per 16 x 8 block of pairs
+// (north_star's "popc(a)+popc(b)-2*popc(a&b)" identity; the b1 AND/XOR-popc MMA it mentions is not native
+// on sm_100a -- it compiles to IMMA plus bit expansion -- so the expansion is done once per CTA tile here).
+// One warp owns 16 queries (A fragments for all 256 dimensions stay in 32 registers); the CTA streams the
+// database in tiles of 128 descriptors, expanded to bytes in shared memory (row stride 272 B -> the 8
+// descriptors of a fragment hit different banks).  Per thread a running top-2 of (dist << 20 | index in
+// this CTA's slice) for its two query rows; quads are merged by shuffles at the end.  Output format and
+// the cross-slice merge are those of the POPC kernel, results are identical (ties -> lower index).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMmaTile = 128;          // database descriptors per smem tile
+constexpr int kMmaRow = 272;           // bytes per expanded descriptor row: 68 words = 4 mod 32 -> the (g,t) fragment loads hit 32 banks
+constexpr int kMmaQPerCta = 128;       // 8 warps x 16 queries
+
+__device__ __forceinline__ uint32_t expand_nibble(uint32_t w, int shift) {
+  return (((w >> shift) & 0xFu) * 0x00204081u) & 0x01010101u;  // 4 bits -> 4 bytes of 0/1
+}
+
+__device__ __forceinline__ void top2_insert(uint32_t key, uint32_t& k0, uint32_t& k1) {
+  if (key < k1) {
+    if (key < k0) {
+      k1 = k0;
+      k0 = key;
+    } else {
+      k1 = key;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) db_top2_mma_kernel(const uint4* __restrict__ db, long long ndb, long long first_index,
+                                                          const uint32_t* __restrict__ q, int nq, int tiles_per_cta,
+                                                          unsigned long long* __restrict__ partial) {
+  __shared__ __align__(16) uint8_t s_exp[kMmaTile * kMmaRow];
+  __shared__ int s_pd[kMmaTile];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  // ---- A fragments: queries (rows g and g+8 of this warp's 16), all 8 k-steps, expanded from bits
+  const int q0 = blockIdx.y * kMmaQPerCta + wid * 16 + g, q1 = q0 + 8;
+  uint32_t a[8][4];
+  int pq0 = 0, pq1 = 0;
+#pragma unroll
+  for (int ks = 0; ks < 8; ks++) {
+    const uint32_t w0 = q0 < nq ? __ldg(q + (size_t)q0 * 8 + ks) : 0u;
+    const uint32_t w1 = q1 < nq ? __ldg(q + (size_t)q1 * 8 + ks) : 0u;
+    pq0 += __popc(w0);
+    pq1 += __popc(w1);
+    a[ks][0] = expand_nibble(w0, 4 * t);
+    a[ks][1] = expand_nibble(w1, 4 * t);
+    a[ks][2] = expand_nibble(w0, 16 + 4 * t);
+    a[ks][3] = expand_nibble(w1, 16 + 4 * t);
+  }
+  uint32_t k00 = ~0u, k01 = ~0u, k10 = ~0u, k11 = ~0u;  // running top-2 keys of row g / row g+8
+  const long long tile0 = (long long)blockIdx.x * tiles_per_cta;
+  for (int tile = 0; tile < tiles_per_cta; tile++) {
+    const long long base = (tile0 + tile) * kMmaTile;
+    if (base >= ndb) break;
+    __syncthreads();
+    {  // expand this tile: thread = (descriptor n, half of its 8 words)
+      const int n = tid >> 1, half = tid & 1;
+      uint4 w = make_uint4(0, 0, 0, 0);
+      const bool live = base + n < ndb;
+      if (live) w = __ldg(db + 2 * (base + n) + half);
+      int pc = __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+      pc += __shfl_xor_sync(0xffffffffu, pc, 1);
+      if (half == 0) s_pd[n] = live ? pc : 1000;  // padding rows can never win (and d << 20 still fits 32 bits)
+      uint32_t* dst = reinterpret_cast<uint32_t*>(s_exp + n * kMmaRow + 128 * half);
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) dst[8 * k + j] = expand_nibble(ww[k], 4 * j);
+    }
+    __syncthreads();
+    const uint32_t idx_base = (uint32_t)(tile * kMmaTile);
+#pragma unroll 2
+    for (int nt = 0; nt < kMmaTile / 8; nt++) {
+      int c[4] = {0, 0, 0, 0};
+      const uint8_t* brow = s_exp + (nt * 8 + g) * kMmaRow + 4 * t;
+#pragma unroll
+      for (int ks = 0; ks < 8; ks++) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + 32 * ks);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(brow + 32 * ks + 16);
+        asm volatile(
+            "mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+            : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+            : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b0), "r"(b1));
+      }
+      // c0:(row g, col 2t) c1:(row g, col 2t+1) c2:(row g+8, col 2t) c3:(row g+8, col 2t+1)
+      const int n0 = nt * 8 + 2 * t;
+      const int pd0 = s_pd[n0], pd1 = s_pd[n0 + 1];
+      const uint32_t i0 = idx_base + n0, i1 = i0 + 1;
+      top2_insert(((uint32_t)(pq0 + pd0 - 2 * c[0]) << 20) | i0, k00, k01);
+      top2_insert(((uint32_t)(pq0 + pd1 - 2 * c[1]) << 20) | i1, k00, k01);
+      top2_insert(((uint32_t)(pq1 + pd0 - 2 * c[2]) << 20) | i0, k10, k11);
+      top2_insert(((uint32_t)(pq1 + pd1 - 2 * c[3]) << 20) | i1, k10, k11);
+    }
+  }
+  // ---- merge the four lanes of a quad (they hold different columns of the same two rows)
+#pragma unroll
+  for (int o = 1; o <= 2; o <<= 1) {
+    const uint32_t o00 = __shfl_xor_sync(0xffffffffu, k00, o), o01 = __shfl_xor_sync(0xffffffffu, k01, o);
+    const uint32_t o10 = __shfl_xor_sync(0xffffffffu, k10, o), o11 = __shfl_xor_sync(0xffffffffu, k11, o);
+    top2_insert(o00, k00, k01);
+    top2_insert(o01, k00, k01);
+    top2_insert(o10, k10, k11);
+    top2_insert(o11, k10, k11);
+  }
+  if (t == 0) {
+    const unsigned long long slice_base = (unsigned long long)(first_index + tile0 * kMmaTile);
+    auto widen = [&](uint32_t key) -> unsigned long long {
+      if (key == ~0u || (key >> 20) > 256) return ~0ull;
+      return ((unsigned long long)(key >> 20) << 48) | (slice_base + (key & 0xFFFFFu));
+    };
+    if (q0 < nq) {
+      partial[((size_t)blockIdx.x * nq + q0) * 2] = widen(k00);
+      partial[((size_t)blockIdx.x * nq + q0) * 2 + 1] = widen(k01);
+    }
+    if (q1 < nq) {
+      partial[((size_t)blockIdx.x * nq + q1) * 2] = widen(k10);
+      partial[((size_t)blockIdx.x * nq + q1) * 2 + 1] = widen(k11);
+    }
+  }
+}
+
 __global__ void db_merge_kernel(const unsigned long long* __restrict__ partial, int nparts, int nq, int k,
                                 unsigned long long* __restrict__ topk, int32_t* __restrict__ votes, int th_votes,
                                 long long first_kf, int desc_per_kf, long long first_index, long long n_kf) {
@@ -1305,12 +1431,18 @@ int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t*
   if (!db || !d_q || nq <= 0 || k < 1 || k > 2 || !d_topk) return SWM_E_INVALID;
   if (cudaSetDevice(db->device) != cudaSuccess) return SWM_E_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
-  const long long tiles = (db->ndesc + kDbTile - 1) / kDbTile;
-  const int qblocks = (nq + kDbQPerCta - 1) / kDbQPerCta;
+  // SWM_DB_POPC=1 selects the CUDA-core LOP3+POPC kernel (kept for the A/B measurement in profiles/);
+  // the default is the tensor-core kernel.  Both produce identical keys.
+  static const bool use_popc = getenv("SWM_DB_POPC") != nullptr;
+  const int tile = use_popc ? kDbTile : kMmaTile;
+  const int qper = use_popc ? kDbQPerCta : kMmaQPerCta;
+  const long long tiles = (db->ndesc + tile - 1) / tile;
+  const int qblocks = (nq + qper - 1) / qper;
   // enough database slices that slices x query blocks fills the machine a few times over
   long long parts = std::max<long long>(1, (long long)db->n_sm * 8 / qblocks);
   parts = std::min<long long>(parts, tiles);
-  const int tiles_per_cta = (int)((tiles + parts - 1) / parts);
+  int tiles_per_cta = (int)((tiles + parts - 1) / parts);
+  if (!use_popc) tiles_per_cta = std::min(tiles_per_cta, (1 << 20) / kMmaTile);  // 20-bit in-slice index
   parts = (tiles + tiles_per_cta - 1) / tiles_per_cta;
   const size_t need = (size_t)parts * nq * 2 * sizeof(unsigned long long);
   if (need > db->partial_cap) {
@@ -1322,8 +1454,12 @@ int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t*
   }
   const long long first_index = db->first_kf * db->desc_per_kf;
   dim3 grid((unsigned)parts, qblocks);
-  db_top2_kernel<<<grid, kDbQPerCta, 0, st>>>((const uint4*)db->d_desc, db->ndesc, first_index, (const uint4*)d_q, nq,
-                                              tiles_per_cta, db->d_partial);
+  if (use_popc)
+    db_top2_kernel<<<grid, kDbQPerCta, 0, st>>>((const uint4*)db->d_desc, db->ndesc, first_index, (const uint4*)d_q, nq,
+                                                tiles_per_cta, db->d_partial);
+  else
+    db_top2_mma_kernel<<<grid, 256, 0, st>>>((const uint4*)db->d_desc, db->ndesc, first_index, (const uint32_t*)d_q, nq,
+                                             tiles_per_cta, db->d_partial);
   const long long n_kf = (db->ndesc + db->desc_per_kf - 1) / db->desc_per_kf;
   db_merge_kernel<<<(nq + 127) / 128, 128, 0, st>>>(db->d_partial, (int)parts, nq, k, (unsigned long long*)d_topk,
                                                     d_votes, th_votes, db->first_kf, db->desc_per_kf, first_index, n_kf);
