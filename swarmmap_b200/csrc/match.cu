@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(kDbQPerCta) db_top2_kernel(const uint4* __rest
 // and dot() over 256 dimensions is eight m16n8k32 u8 x u8 -> s32 MMAs per 16 x 8 block of pairs
 // (north_star's "popc(a)+popc(b)-2*popc(a&b)" identity; the b1 AND/XOR-popc MMA it mentions is not native
 // on sm_100a -- it compiles to IMMA plus bit expansion -- so the expansion is done once per CTA tile here).
-// One warp owns 16 queries (A fragments for all 256 dimensions stay in 32 registers); the CTA streams the
+// One warp owns 32 queries (A fragments for all 256 dimensions stay in 64 registers); the CTA streams the
 // database in tiles of 128 descriptors, expanded to bytes in shared memory (row stride 272 B -> the 8
 // descriptors of a fragment hit different banks).  Per thread a running top-2 of (dist << 20 | index in
 // this CTA's slice) for its two query rows; quads are merged by shuffles at the end.  Output format and
@@ -642,46 +642,54 @@ __global__ void __launch_bounds__(kDbQPerCta) db_top2_kernel(const uint4* __rest
 // ---------------------------------------------------------------------------------------------
 constexpr int kMmaTile = 128;          // database descriptors per smem tile
 constexpr int kMmaRow = 272;           // bytes per expanded descriptor row: 68 words = 4 mod 32 -> the (g,t) fragment loads hit 32 banks
-constexpr int kMmaQPerCta = 128;       // 8 warps x 16 queries
+constexpr int kMmaQPerCta = 256;       // 8 warps x 32 queries
 
 __device__ __forceinline__ uint32_t expand_nibble(uint32_t w, int shift) {
   return (((w >> shift) & 0xFu) * 0x00204081u) & 0x01010101u;  // 4 bits -> 4 bytes of 0/1
 }
 
 __device__ __forceinline__ void top2_insert(uint32_t key, uint32_t& k0, uint32_t& k1) {
-  if (key < k1) {
-    if (key < k0) {
-      k1 = k0;
-      k0 = key;
-    } else {
-      k1 = key;
-    }
-  }
+  k1 = min(k1, max(k0, key));  // branch-free: second smallest of {k0, k1, key}
+  k0 = min(k0, key);
 }
 
-__global__ void __launch_bounds__(256) db_top2_mma_kernel(const uint4* __restrict__ db, long long ndb, long long first_index,
-                                                          const uint32_t* __restrict__ q, int nq, int tiles_per_cta,
-                                                          unsigned long long* __restrict__ partial) {
+__device__ __forceinline__ void mma_u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 2) db_top2_mma_kernel(const uint4* __restrict__ db, long long ndb, long long first_index,
+                                                             const uint32_t* __restrict__ q, int nq, int tiles_per_cta,
+                                                             unsigned long long* __restrict__ partial) {
   __shared__ __align__(16) uint8_t s_exp[kMmaTile * kMmaRow];
   __shared__ int s_pd[kMmaTile];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  // ---- A fragments: queries (rows g and g+8 of this warp's 16), all 8 k-steps, expanded from bits
-  const int q0 = blockIdx.y * kMmaQPerCta + wid * 16 + g, q1 = q0 + 8;
-  uint32_t a[8][4];
-  int pq0 = 0, pq1 = 0;
+  // ---- A fragments: this warp's 32 queries = two 16-row blocks (rows g, g+8 of each), all 8 k-steps,
+  // expanded from bits.  Every B fragment read from shared memory then feeds two MMAs (the kernel is
+  // otherwise bound by shared-memory bandwidth: 256 B of B operand per MMA).
+  int qrow[4];
+  uint32_t a[2][8][4];
+  int pq[4] = {0, 0, 0, 0};
 #pragma unroll
-  for (int ks = 0; ks < 8; ks++) {
-    const uint32_t w0 = q0 < nq ? __ldg(q + (size_t)q0 * 8 + ks) : 0u;
-    const uint32_t w1 = q1 < nq ? __ldg(q + (size_t)q1 * 8 + ks) : 0u;
-    pq0 += __popc(w0);
-    pq1 += __popc(w1);
-    a[ks][0] = expand_nibble(w0, 4 * t);
-    a[ks][1] = expand_nibble(w1, 4 * t);
-    a[ks][2] = expand_nibble(w0, 16 + 4 * t);
-    a[ks][3] = expand_nibble(w1, 16 + 4 * t);
+  for (int mt = 0; mt < 2; mt++) {
+    qrow[2 * mt] = blockIdx.y * kMmaQPerCta + wid * 32 + mt * 16 + g;
+    qrow[2 * mt + 1] = qrow[2 * mt] + 8;
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+      const uint32_t w0 = qrow[2 * mt] < nq ? __ldg(q + (size_t)qrow[2 * mt] * 8 + ks) : 0u;
+      const uint32_t w1 = qrow[2 * mt + 1] < nq ? __ldg(q + (size_t)qrow[2 * mt + 1] * 8 + ks) : 0u;
+      pq[2 * mt] += __popc(w0);
+      pq[2 * mt + 1] += __popc(w1);
+      a[mt][ks][0] = expand_nibble(w0, 4 * t);
+      a[mt][ks][1] = expand_nibble(w1, 4 * t);
+      a[mt][ks][2] = expand_nibble(w0, 16 + 4 * t);
+      a[mt][ks][3] = expand_nibble(w1, 16 + 4 * t);
+    }
   }
-  uint32_t k00 = ~0u, k01 = ~0u, k10 = ~0u, k11 = ~0u;  // running top-2 keys of row g / row g+8
+  uint32_t k0[4] = {~0u, ~0u, ~0u, ~0u}, k1[4] = {~0u, ~0u, ~0u, ~0u};  // running top-2 keys of the 4 rows
   const long long tile0 = (long long)blockIdx.x * tiles_per_cta;
   for (int tile = 0; tile < tiles_per_cta; tile++) {
     const long long base = (tile0 + tile) * kMmaTile;
@@ -704,53 +712,58 @@ __global__ void __launch_bounds__(256) db_top2_mma_kernel(const uint4* __restric
     }
     __syncthreads();
     const uint32_t idx_base = (uint32_t)(tile * kMmaTile);
-#pragma unroll 2
-    for (int nt = 0; nt < kMmaTile / 8; nt++) {
-      int c[4] = {0, 0, 0, 0};
+    for (int nt = 0; nt < kMmaTile / 8; nt += 2) {  // 2 column blocks x 2 row blocks per step: 4 independent MMAs
+      int c[2][2][4] = {};
       const uint8_t* brow = s_exp + (nt * 8 + g) * kMmaRow + 4 * t;
+      const uint8_t* drow = brow + 8 * kMmaRow;
 #pragma unroll
       for (int ks = 0; ks < 8; ks++) {
         const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + 32 * ks);
         const uint32_t b1 = *reinterpret_cast<const uint32_t*>(brow + 32 * ks + 16);
-        asm volatile(
-            "mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-            : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
-            : "r"(a[ks][0]), "r"(a[ks][1]), "r"(a[ks][2]), "r"(a[ks][3]), "r"(b0), "r"(b1));
+        const uint32_t e0 = *reinterpret_cast<const uint32_t*>(drow + 32 * ks);
+        const uint32_t e1 = *reinterpret_cast<const uint32_t*>(drow + 32 * ks + 16);
+        mma_u8(c[0][0], a[0][ks], b0, b1);
+        mma_u8(c[0][1], a[0][ks], e0, e1);
+        mma_u8(c[1][0], a[1][ks], b0, b1);
+        mma_u8(c[1][1], a[1][ks], e0, e1);
       }
-      // c0:(row g, col 2t) c1:(row g, col 2t+1) c2:(row g+8, col 2t) c3:(row g+8, col 2t+1)
+      // c[.][.][0]:(row g, col 2t) [1]:(row g, col 2t+1) [2]:(row g+8, col 2t) [3]:(row g+8, col 2t+1)
       const int n0 = nt * 8 + 2 * t;
-      const int pd0 = s_pd[n0], pd1 = s_pd[n0 + 1];
-      const uint32_t i0 = idx_base + n0, i1 = i0 + 1;
-      top2_insert(((uint32_t)(pq0 + pd0 - 2 * c[0]) << 20) | i0, k00, k01);
-      top2_insert(((uint32_t)(pq0 + pd1 - 2 * c[1]) << 20) | i1, k00, k01);
-      top2_insert(((uint32_t)(pq1 + pd0 - 2 * c[2]) << 20) | i0, k10, k11);
-      top2_insert(((uint32_t)(pq1 + pd1 - 2 * c[3]) << 20) | i1, k10, k11);
+      const int pd[2][2] = {{s_pd[n0], s_pd[n0 + 1]}, {s_pd[n0 + 8], s_pd[n0 + 9]}};
+      const uint32_t i0 = idx_base + n0;
+#pragma unroll
+      for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nb = 0; nb < 2; nb++) {
+          const uint32_t ib = i0 + 8 * nb;
+          top2_insert(((uint32_t)(pq[2 * mt] + pd[nb][0] - 2 * c[mt][nb][0]) << 20) | ib, k0[2 * mt], k1[2 * mt]);
+          top2_insert(((uint32_t)(pq[2 * mt] + pd[nb][1] - 2 * c[mt][nb][1]) << 20) | (ib + 1), k0[2 * mt], k1[2 * mt]);
+          top2_insert(((uint32_t)(pq[2 * mt + 1] + pd[nb][0] - 2 * c[mt][nb][2]) << 20) | ib, k0[2 * mt + 1], k1[2 * mt + 1]);
+          top2_insert(((uint32_t)(pq[2 * mt + 1] + pd[nb][1] - 2 * c[mt][nb][3]) << 20) | (ib + 1), k0[2 * mt + 1], k1[2 * mt + 1]);
+        }
     }
   }
-  // ---- merge the four lanes of a quad (they hold different columns of the same two rows)
+  // ---- merge the four lanes of a quad (they hold different columns of the same rows)
 #pragma unroll
-  for (int o = 1; o <= 2; o <<= 1) {
-    const uint32_t o00 = __shfl_xor_sync(0xffffffffu, k00, o), o01 = __shfl_xor_sync(0xffffffffu, k01, o);
-    const uint32_t o10 = __shfl_xor_sync(0xffffffffu, k10, o), o11 = __shfl_xor_sync(0xffffffffu, k11, o);
-    top2_insert(o00, k00, k01);
-    top2_insert(o01, k00, k01);
-    top2_insert(o10, k10, k11);
-    top2_insert(o11, k10, k11);
-  }
+  for (int o = 1; o <= 2; o <<= 1)
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const uint32_t o0 = __shfl_xor_sync(0xffffffffu, k0[r], o), o1 = __shfl_xor_sync(0xffffffffu, k1[r], o);
+      top2_insert(o0, k0[r], k1[r]);
+      top2_insert(o1, k0[r], k1[r]);
+    }
   if (t == 0) {
     const unsigned long long slice_base = (unsigned long long)(first_index + tile0 * kMmaTile);
     auto widen = [&](uint32_t key) -> unsigned long long {
       if (key == ~0u || (key >> 20) > 256) return ~0ull;
       return ((unsigned long long)(key >> 20) << 48) | (slice_base + (key & 0xFFFFFu));
     };
-    if (q0 < nq) {
-      partial[((size_t)blockIdx.x * nq + q0) * 2] = widen(k00);
-      partial[((size_t)blockIdx.x * nq + q0) * 2 + 1] = widen(k01);
-    }
-    if (q1 < nq) {
-      partial[((size_t)blockIdx.x * nq + q1) * 2] = widen(k10);
-      partial[((size_t)blockIdx.x * nq + q1) * 2 + 1] = widen(k11);
-    }
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      if (qrow[r] < nq) {
+        partial[((size_t)blockIdx.x * nq + qrow[r]) * 2] = widen(k0[r]);
+        partial[((size_t)blockIdx.x * nq + qrow[r]) * 2 + 1] = widen(k1[r]);
+      }
   }
 }
 
