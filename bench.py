@@ -322,6 +322,30 @@ def main():
         for i in range(50):
             ex1(frames[i % B])
         extras["single_frame_operator_ms"] = (time.perf_counter() - t0) / 50 * 1e3
+        # KITTI-shaped extraction throughput (north_star's second frame size), device-resident, B=128
+        kb = 128
+        kf = synth.make_batch(kb, 1241, 376, 20220405)
+        exk = ORBextractor(2000, 1.2, 8, 20, 7, device=local_rank, max_batch=kb)
+        kcap = exk.max_keypoints()
+        dk_img = torch.from_numpy(kf).to(dev)
+        dk_kps = torch.empty((kb, kcap, 7), dtype=torch.float32, device=dev)
+        dk_desc = torch.empty((kb, kcap, 32), dtype=torch.uint8, device=dev)
+        dk_n = torch.zeros(kb, dtype=torch.int32, device=dev)
+        def kstep():
+            exk.extract_batch_device(dk_img.data_ptr(), kb, 1241, 376, 1241, 1241 * 376, dk_kps.data_ptr(),
+                                     dk_desc.data_ptr(), kcap, dk_n.data_ptr(), sptr)
+        for _ in range(3):
+            kstep()
+        torch.cuda.synchronize()
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        k0.record()
+        for _ in range(10):
+            kstep()
+        k1.record()
+        torch.cuda.synchronize()
+        extras["kitti_1241x376_2000feat_frames_per_s"] = 10 * kb / (k0.elapsed_time(k1) * 1e-3)
+        extras["kitti_keypoints_per_frame"] = float(dk_n.float().mean().item())
+        del exk, dk_img, dk_kps, dk_desc
         seq = synth.make_sequence(3, 1241, 376, 20220405)
         ex4k = ORBextractor(4000, 1.2, 8, 20, 7, device=local_rank, max_batch=1)
         fs = [Frame.from_keypoints(*ex4k(img), 1241, 376, ex4k.GetScaleFactors()) for img in seq]

@@ -155,3 +155,24 @@ def test_scale_tables_and_quotas(oracle, swm):
     np.testing.assert_array_equal(gpu.GetInverseScaleSigmaSquares(), inv2)
     np.testing.assert_array_equal(gpu.mnFeaturesPerLevel, oracle.level_quotas(1000))
     assert gpu.GetLevels() == 8 and abs(gpu.GetScaleFactor() - 1.2) < 1e-6
+
+
+@pytest.mark.parametrize("cfg", [(500, 1.3, 5, 15, 5), (1500, 1.1, 10, 30, 10), (300, 1.5, 3, 20, 7), (2000, 1.2, 8, 40, 20)])
+def test_other_extractor_settings(oracle, swm, cfg):
+    """Non-default ORBextractor.* settings (nFeatures, scaleFactor, nLevels, iniThFAST, minThFAST)."""
+    from swarmmap_b200.orb import ORBextractor
+    nf, sf, nl, ini, mn = cfg
+    gpu = ORBextractor(nf, sf, nl, ini, mn, debug_score=True)
+    cpu = oracle.Extractor(nf, sf, nl, ini, mn)
+    img = synth.make_frame(640, 480, 77)
+    kps, desc = gpu(img)
+    okps, odesc = cpu(img)
+    for l in range(nl):
+        np.testing.assert_array_equal(gpu.debug_plane(0, l, 0), cpu.level(l, 0), err_msg=f"plane L{l}")
+        np.testing.assert_array_equal(gpu.debug_plane(0, l, 1), cpu.level(l, 1), err_msg=f"blur L{l}")
+        np.testing.assert_array_equal(gpu.debug_plane(0, l, 2), cpu.level(l, 2), err_msg=f"score L{l}")
+    assert len(kps) == len(okps) and len(kps) > 100
+    for fld in ("x", "y", "size", "response", "octave"):
+        np.testing.assert_array_equal(kps[fld], okps[fld], err_msg=fld)
+    assert 1.0 - np.unpackbits(desc ^ odesc).sum() / float(desc.size * 8) >= DESC_BIT_FRACTION
+    np.testing.assert_array_equal(gpu.mnFeaturesPerLevel, oracle.level_quotas(nf, sf, nl))
