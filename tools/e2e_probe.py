@@ -5,7 +5,7 @@ import numpy as np, torch
 from swarmmap_b200 import synth
 from swarmmap_b200.orb import ORBextractor, KP_DTYPE
 W, H = 752, 480
-B = 256
+B = 512
 frames = synth.make_batch(B, W, H, 20220410)
 h_img = torch.from_numpy(frames).pin_memory()
 d = torch.empty_like(h_img, device="cuda")
@@ -15,7 +15,7 @@ for _ in range(10): d.copy_(h_img, non_blocking=True)
 torch.cuda.synchronize(); dt = time.perf_counter() - t
 print("raw pinned H2D GB/s", 10 * h_img.numel() / dt / 1e9)
 h_np = h_img.numpy()
-for nslot, eb in ((2, 64), (3, 32), (4, 32), (2, 128), (4, 64)):
+for nslot, eb in ((4, 32), (4, 64), (3, 64), (2, 128), (8, 32), (6, 16), (4, 128)):
     exs = [ORBextractor(1000, 1.2, 8, 20, 7, max_batch=eb) for _ in range(nslot)]
     cap = exs[0].max_keypoints()
     outs = []

@@ -1,0 +1,29 @@
+"""Small run of every kernel for compute-sanitizer (memcheck / racecheck)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, ctypes as C
+from swarmmap_b200 import synth, place
+from swarmmap_b200.orb import ORBextractor
+from swarmmap_b200.matcher import Frame, ORBmatcher, FeatureVector
+ex = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=2)
+imgs = synth.make_batch(3, 752, 480, 1)
+k, d, n = ex.extract_batch(imgs)
+rng = np.random.default_rng(0)
+noise = rng.integers(0, 256, (333, 257), dtype=np.uint8)   # odd size, > 10000 candidates on level 0? (cap path on big noise)
+ex2 = ORBextractor(500, 1.2, 8, 20, 7)
+ex2(noise)
+big = rng.integers(0, 256, (480, 752), dtype=np.uint8)
+ex(big)
+fs = [Frame.from_keypoints(k[i, :n[i]], d[i, :n[i]], 752, 480, ex.GetScaleFactors()) for i in range(2)]
+m = ORBmatcher(0.9, True)
+prev = np.stack([fs[0].x, fs[0].y], 1).astype(np.float32).copy()
+print("init", m.SearchForInitialization(fs[0], fs[1], prev, 100)[0])
+print("proj", m.SearchByProjectionLastFrame(fs[1], fs[0], fs[0].x, fs[0].y, np.ones(fs[0].N, np.uint8), 15)[0])
+node = lambda f: (f.desc[:, 0] & 31).astype(np.int64)
+print("bow", m.SearchByBoW(fs[0], FeatureVector(node(fs[0])), np.ones(fs[0].N, np.uint8), fs[1], FeatureVector(node(fs[1])))[0])
+db = torch.randint(0, 256, (5000, 32), dtype=torch.uint8, device="cuda")
+q = torch.randint(0, 256, (300, 32), dtype=torch.uint8, device="cuda")
+s = place.PlaceShard(db, 8, 0)
+keys, votes = s.query(q, 2, 50)
+torch.cuda.synchronize()
+print("ok", int(n.sum()))
