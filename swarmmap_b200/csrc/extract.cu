@@ -272,12 +272,18 @@ __global__ void __launch_bounds__(256) pyr_kernel(const PyrArgs a) {
 // Survivors are appended (unordered) to the per-(frame, level) candidate list; everything
 // downstream orders by explicit keys, so the append order does not matter.
 // ------------------------------------------------------------------------------------------------
-// Staged tile: 96 x 40 bytes whose first column is level x = 64*bx, i.e. 16-byte aligned in the plane, so
-// every row is one TMA bulk copy (cp.async.bulk, 96 B) completing on an mbarrier.  Local column of the
-// first interior pixel (level x = 19 + 64 bx) is kFx = 19; local row of the first interior row is 4.
-constexpr int FS_WORDS = 24, FS_COLS = FS_WORDS * 4, FS_ROWS = TH + 8;
+// One CTA = kFT horizontally adjacent 32x32 FAST tiles (FB_W = 128 pixels).  Staged tile: 160 x 40 bytes whose
+// first column is level x = FB_W*bx, i.e. 16-byte aligned in the plane, so every row is one TMA bulk copy
+// (cp.async.bulk, 160 B) completing on an mbarrier.  Local column of the first interior pixel
+// (level x = 19 + FB_W bx) is kFx = 19; local row of the first interior row is 4.
+constexpr int kFT = 4, FB_W = 32 * kFT;
+constexpr int FS_WORDS = 40, FS_COLS = FS_WORDS * 4, FS_ROWS = TH + 8;
 constexpr int kFx = 19;
-constexpr int FS_MAXCAND = 66 * 34;
+constexpr int FS_SW = FB_W / 4 + 1;                  // words per row that hold scored pixels (local x 18 .. 19+FB_W)
+constexpr int FS_ITEMS = 34 * FS_SW;                // quick-reject word items per CTA
+constexpr int FS_IT = (FS_ITEMS + 255) / 256;
+constexpr int FS_MAXCAND = (FB_W + 2) * 34;
+static_assert(kFx + FB_W + 4 <= FS_COLS && 4 + FS_SW <= FS_WORDS - 1, "staged tile too narrow");
 
 // ---- mbarrier / TMA bulk-copy helpers (PTX ISA: mbarrier, cp.async.bulk)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -350,12 +356,12 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
   __shared__ __align__(16) uint32_t s_px[FS_ROWS * FS_WORDS];
   __shared__ __align__(16) uint32_t s_sc[FS_ROWS * FS_WORDS];
   __shared__ uint16_t s_list[FS_MAXCAND + 2];
-  __shared__ uint16_t s_list2[TW * TH + 2];
+  __shared__ uint16_t s_list2[FB_W * TH + 2];
   __shared__ uint32_t s_colmask[FS_WORDS];
   __shared__ int s_warp[8];
   __shared__ int s_total, s_n2, s_blk;
-  __shared__ int s_any[2];
-  __shared__ uint8_t s_flag[12];
+  __shared__ int s_any[kFT];
+  __shared__ uint8_t s_flag[3 * (kFT + 2)];
   __shared__ __align__(8) uint64_t s_bar;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nblk = L->fblk_total;
@@ -382,21 +388,21 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
     const int lvl = bd.x, bx = bd.y, by = bd.z;
     const LevelGeom& g = L->lv[lvl];
     uint8_t* fretry = retry + (long long)f * L->tiles_total + g.tile_off;
-    const int t0 = by * g.tiles_x + 2 * bx;  // first of the two tiles of this block
-    const bool has_t1 = 2 * bx + 1 < g.tiles_x;
+    const int t0 = by * g.tiles_x + kFT * bx;  // first of this block's tiles
+    const int ntile = min(kFT, g.tiles_x - kFT * bx);
     const int w = g.w, h = g.h;
-    const int X0 = kEdge + 64 * bx, Y0 = kEdge + 32 * by;  // first interior pixel (level coords)
-    const int sx0 = X0 - kFx, sy0 = Y0 - 4;                // staged origin; sx0 = 64 bx is 16-byte aligned
-    if (pass == 2 && tid < 12) {
-      const int ny = by + tid / 4 - 1, nx = 2 * bx + (tid & 3) - 1;
+    const int X0 = kEdge + FB_W * bx, Y0 = kEdge + 32 * by;  // first interior pixel (level coords)
+    const int sx0 = X0 - kFx, sy0 = Y0 - 4;                // staged origin; sx0 = FB_W bx is 16-byte aligned
+    if (pass == 2 && tid < 3 * (kFT + 2)) {
+      const int ny = by + tid / (kFT + 2) - 1, nx = kFT * bx + tid % (kFT + 2) - 1;
       s_flag[tid] = (ny >= 0 && ny < g.tiles_y && nx >= 0 && nx < g.tiles_x) ? fretry[ny * g.tiles_x + nx] : 0;
     }
-    if (tid < 2) s_any[tid] = 0;
-    if (tid == 2) s_n2 = 0;
+    if (tid < kFT) s_any[tid] = 0;
+    if (tid == kFT) s_n2 = 0;
     if (tid >= 32 && tid < 32 + FS_WORDS) {
       // per-word byte mask of the columns that are scored: interior +- 1 px and level x in [19, w-19)
       const int jw = tid - 32;
-      const int lo = max(kFx - 1, kEdge - sx0), hi = min(kFx + 64, w - kEdge - 1 - sx0);
+      const int lo = max(kFx - 1, kEdge - sx0), hi = min(kFx + FB_W, w - kEdge - 1 - sx0);
       uint32_t m = 0;
       for (int k = 0; k < 4; k++)
         if (4 * jw + k >= lo && 4 * jw + k <= hi) m |= 0x80u << (8 * k);
@@ -426,16 +432,16 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
     // Pass 1 only ever uses S_hi (scores below iniThFAST count as 0), so it detects at iniThFAST: same
     // keypoints, a fraction of the candidates.  Pass 2 (and the debug score map) need S at minThFAST.
     const int th_run = (pass == 1 && dbg_score == nullptr) ? ini_th : min_th;
-    // ---- packed quick reject on the scored region (interior + 1 px): rows ly 3..36, words 4..20
+    // ---- packed quick reject on the scored region (interior + 1 px): rows ly 3..36, words 4..4+FS_SW-1
     const uint32_t c7 = (uint32_t)(127 - th_run) * 0x01010101u;
-    uint32_t masks[3];
+    uint32_t masks[FS_IT];
     int n_mine = 0;
 #pragma unroll
-    for (int it = 0; it < 3; it++) {
+    for (int it = 0; it < FS_IT; it++) {
       const int i = tid + 256 * it;
       uint32_t m = 0;
-      if (i < 34 * 17) {
-        const int r = i / 17, ly = r + 3, jw = i - r * 17 + 4;
+      if (i < FS_ITEMS) {
+        const int r = i / FS_SW, ly = r + 3, jw = i - r * FS_SW + 4;
         const int gy = sy0 + ly;
         if (gy >= kEdge && gy < h - kEdge) {
           const uint32_t* row = s_px + ly * FS_WORDS + jw;
@@ -474,14 +480,14 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
     __syncthreads();
     int pos = s_warp[wid] + incl - n_mine;
 #pragma unroll
-    for (int it = 0; it < 3; it++) {
+    for (int it = 0; it < FS_IT; it++) {
       const uint32_t m = masks[it];
       if (m) {
         const int i = tid + 256 * it;
-        const int r = i / 17, ly = r + 3, jw = i - r * 17 + 4;
+        const int r = i / FS_SW, ly = r + 3, jw = i - r * FS_SW + 4;
 #pragma unroll
         for (int k = 0; k < 4; k++)
-          if (m & (0x80u << (8 * k))) s_list[pos++] = (uint16_t)((ly << 7) | (4 * jw + k));
+          if (m & (0x80u << (8 * k))) s_list[pos++] = (uint16_t)((ly << 8) | (4 * jw + k));
       }
     }
     __syncthreads();
@@ -490,11 +496,11 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
     // ---- score the survivors; those that can be keypoints go on a second, much shorter list
     for (int i = tid; i < n_cand; i += 256) {
       const int e = s_list[i];
-      const int ly = e >> 7, lx = e & 127;
+      const int ly = e >> 8, lx = e & 255;
       const int sc = fast_score_x2(s_pxb + ly * FS_COLS + lx, FS_COLS, th_run);
       s_scb[ly * FS_COLS + lx] = (uint8_t)sc;
-      if (sc >= (pass == 1 ? ini_th : 1) && lx >= kFx && lx <= kFx + 63 && ly >= 4 && ly <= 35 &&
-          (pass == 1 || s_flag[4 + 1 + (lx >= kFx + 32 ? 1 : 0)] != 0))
+      if (sc >= (pass == 1 ? ini_th : 1) && lx >= kFx && lx < kFx + FB_W && ly >= 4 && ly <= 35 &&
+          (pass == 1 || s_flag[(kFT + 2) + 1 + ((lx - kFx) >> 5)] != 0))
         s_list2[atomicAdd(&s_n2, 1)] = (uint16_t)e;
     }
     __syncthreads();
@@ -507,8 +513,8 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
       int lx = 0, ly = 0, c = 0;
       if (i < n2) {
         const int e = s_list2[i];
-        ly = e >> 7;
-        lx = e & 127;
+        ly = e >> 8;
+        lx = e & 255;
         const uint8_t* sp = s_scb + ly * FS_COLS + lx;
         c = sp[0];
         kp = true;
@@ -522,13 +528,13 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
             if (pass == 2) {
               const int qx = lx + dx, qy = ly + dy;
               const int fy = qy < 4 ? 0 : (qy > 35 ? 2 : 1);
-              const int fx = qx < kFx ? 0 : (qx < kFx + 32 ? 1 : (qx < kFx + 64 ? 2 : 3));
-              raw = s_flag[fy * 4 + fx] != 0;
+              const int fx = qx < kFx ? 0 : 1 + ((qx - kFx) >> 5);
+              raw = s_flag[fy * (kFT + 2) + fx] != 0;
             }
             if (!raw && q < ini_th) q = 0;
             kp = kp && c > q;
           }
-        if (kp && pass == 1) s_any[lx >= kFx + 32 ? 1 : 0] = 1;
+        if (kp && pass == 1) s_any[(lx - kFx) >> 5] = 1;
       }
       const unsigned m = __ballot_sync(0xffffffffu, kp);
       if (m) {
@@ -545,15 +551,18 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
     if (pass == 1) {
       __syncthreads();
       if (tid == 0) {
-        const int r0 = s_any[0] ? 0 : 1, r1 = (has_t1 && !s_any[1]) ? 1 : 0;
-        fretry[t0] = (uint8_t)r0;
-        if (has_t1) fretry[t0 + 1] = (uint8_t)r1;
-        if (r0 | r1) retry_list[1 + atomicAdd(retry_list, 1)] = fb;  // pass 2 re-runs only these blocks
+        int any_retry = 0;
+        for (int j = 0; j < ntile; j++) {
+          const int rj = s_any[j] ? 0 : 1;
+          fretry[t0 + j] = (uint8_t)rj;
+          any_retry |= rj;
+        }
+        if (any_retry) retry_list[1 + atomicAdd(retry_list, 1)] = fb;  // pass 2 re-runs only these blocks
       }
       if (dbg_score) {  // parity introspection only: the score map S at minThFAST for the block interior
         uint8_t* sc = dbg_score + (long long)f * L->slab_bytes + g.plane_off + (long long)kEdge * g.pitch + kPadX;
-        for (int i = tid; i < 64 * 32; i += 256) {
-          const int ly = (i >> 6) + 4, lx = (i & 63) + kFx;
+        for (int i = tid; i < FB_W * 32; i += 256) {
+          const int ly = (i / FB_W) + 4, lx = (i % FB_W) + kFx;
           const int gx = sx0 + lx, gy = sy0 + ly;
           if (gx < w - kEdge && gy < h - kEdge) sc[(long long)gy * g.pitch + gx] = s_scb[ly * FS_COLS + lx];
         }
@@ -917,7 +926,7 @@ int setup_geometry(swm_orb* h, int w, int hh) {
     g.tiles_y = (g.h - 2 * kEdge + 31) / 32;
     g.tile_off = tile_off;
     tile_off += g.tiles_x * g.tiles_y;
-    g.fblk_x = (g.tiles_x + 1) / 2;
+    g.fblk_x = (g.tiles_x + kFT - 1) / kFT;
     g.fblk_off = fblk_off;
     fblk_off += g.fblk_x * g.tiles_y;
     // strict 8-neighbour maxima cannot be adjacent: at most one per 2x2 block
