@@ -40,7 +40,7 @@ WORKLOAD = "EuRoC-shaped 752x480 8-bit frames, ORBextractor(1000, 1.2, 8, 20, 7)
 
 def _traffic_per_frame():
     """DRAM bytes per frame of the roofline kernels from the committed ncu --set full capture (profiles/)."""
-    p = os.path.join(ROOT, "profiles", "r1i_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r1k_traffic.json")
     try:
         return float(json.load(open(p))["dram_bytes_per_frame"])
     except Exception:
@@ -435,7 +435,7 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (_traffic_per_frame() * B if _traffic_per_frame() else None),
-                         "traffic_source": "ncu dram__bytes_read+write, same 10 launches at B=256 (profiles/r1i_traffic.json)",
+                         "traffic_source": "ncu dram__bytes_read+write, same 10 launches at B=256 (profiles/r1k_traffic.json)",
                          "peak_source": peak_src,
                          "kernel": "pyr_kernel x8 (pyramid+border, blur fused) + fast_kernel x2 (FAST score+tile retry+NMS)",
                          "bytes_per_frame": PYR_FAST_BYTES, "ms_per_launch_set": ms_pf,
