@@ -33,7 +33,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 W, H, NFEAT = 752, 480, 1000
 PYR_FAST_BYTES = 3912047   # pyramid R+W + FAST R per 752x480 frame
 BLUR_BYTES = 2234734       # blur R+W per frame (fused into the same kernels)
-METRIC = "orb_extract_frames_per_sec"
+METRIC = "orb_extract_frames_per_sec"  # BASELINE.json: ORB frames/sec (1000 feat, 752x480), whole job over all GPUs
 UNIT = "frames/s"
 WORKLOAD = "EuRoC-shaped 752x480 8-bit frames, ORBextractor(1000, 1.2, 8, 20, 7), extract+describe"
 
@@ -232,7 +232,7 @@ def main():
 
     for _ in range(args.warmup):
         step_device()
-    launches_per_step = NH * (dex[0].last_launches() + 2)  # + the two small memsets
+    launches_per_step = NH * dex[0].last_launches()  # kernels only (8 pyr + 2 fast + quadtree + describe per handle)
     # one single-handle pass so that `ex` holds the whole batch for the per-stage timings below
     ex.extract_batch_device(d_img.data_ptr(), B, W, H, W, W * H, d_kps.data_ptr(), d_desc.data_ptr(), cap,
                             d_n.data_ptr(), sptr)

@@ -176,3 +176,63 @@ def test_other_extractor_settings(oracle, swm, cfg):
         np.testing.assert_array_equal(kps[fld], okps[fld], err_msg=fld)
     assert 1.0 - np.unpackbits(desc ^ odesc).sum() / float(desc.size * 8) >= DESC_BIT_FRACTION
     np.testing.assert_array_equal(gpu.mnFeaturesPerLevel, oracle.level_quotas(nf, sf, nl))
+
+
+def test_size_change_on_one_handle(oracle, swm):
+    """The reference assumes one frame size per extractor (ORBextractor.h:89); the handle re-plans instead."""
+    from swarmmap_b200.orb import ORBextractor
+    gpu = ORBextractor(800, 1.2, 8, 20, 7)
+    cpu = oracle.Extractor(800, 1.2, 8, 20, 7)
+    for (w, h, seed) in ((752, 480, 1), (640, 360, 2), (752, 480, 3), (401, 299, 4)):
+        img = synth.make_frame(w, h, seed)
+        kps, desc = gpu(img)
+        okps, odesc = cpu(img)
+        assert len(kps) == len(okps)
+        np.testing.assert_array_equal(kps["x"], okps["x"])
+        np.testing.assert_array_equal(kps["response"], okps["response"])
+        assert 1.0 - np.unpackbits(desc ^ odesc).sum() / float(desc.size * 8) >= DESC_BIT_FRACTION
+
+
+def test_concurrent_handles_from_threads(oracle, swm):
+    """One extractor per agent thread (swarm_map.cc:329-337): handles are independent and deterministic."""
+    import threading
+    from swarmmap_b200.orb import ORBextractor
+    imgs = synth.make_batch(4, 752, 480, 123)
+    cpu = oracle.Extractor(1000, 1.2, 8, 20, 7)
+    ref = [cpu(im) for im in imgs]
+    out = [None] * 4
+
+    def agent(i):
+        ex = ORBextractor(1000, 1.2, 8, 20, 7)
+        res = None
+        for _ in range(5):
+            res = ex(imgs[i])
+        out[i] = res
+
+    ts = [threading.Thread(target=agent, args=(i,)) for i in range(4)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    for i in range(4):
+        kps, desc = out[i]
+        okps, odesc = ref[i]
+        assert len(kps) == len(okps)
+        for fld in ("x", "y", "response", "octave"):
+            np.testing.assert_array_equal(kps[fld], okps[fld])
+        assert 1.0 - np.unpackbits(desc ^ odesc).sum() / float(desc.size * 8) >= DESC_BIT_FRACTION
+
+
+def test_small_caller_capacity(oracle, swm):
+    """A caller buffer smaller than the keypoint count gets the first `cap` keypoints and n == cap."""
+    import ctypes as C
+    from swarmmap_b200.orb import ORBextractor
+    from swarmmap_b200._lib import KP_DTYPE, ptr
+    gpu = ORBextractor(1000, 1.2, 8, 20, 7)
+    img = synth.make_frame(752, 480, 20220404)
+    full_k, full_d = gpu(img)
+    cap = 300
+    kps = np.zeros(cap, KP_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    n = C.c_int(0)
+    rc = gpu._lib.swm_orb_extract(gpu._h, ptr(img), 752, 480, 752, ptr(kps), ptr(desc), cap, C.byref(n))
+    assert rc == 0 and n.value == cap
+    assert kps.tobytes() == full_k[:cap].tobytes() and (desc == full_d[:cap]).all()
