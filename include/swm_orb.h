@@ -111,11 +111,11 @@ int swm_orb_level_quotas(const swm_orb* h, int32_t* quotas);
 int swm_orb_max_keypoints(const swm_orb* h);
 /* Number of kernel launches issued by the last extract call (bench.py's gpu_launches). */
 int swm_orb_last_launches(const swm_orb* h);
-/* Device time of stages of the last *_device/_batch call is measured by the caller with events;
- * this hook runs only the pyramid+FAST kernels on the last uploaded batch (roofline timing). */
+/* Re-runs the selected stages on the data of the last *_device/_batch call (the caller brackets it with
+ * CUDA events on `stream`): per-stage timing for bench.py's roofline and stage breakdown. */
 int swm_orb_run_stage(swm_orb* h, int stage_mask, int batch, void* stream);
-#define SWM_STAGE_PYRAMID 1 /* pyramid + border + FAST score + blur (fused level kernels) */
-#define SWM_STAGE_NMS 2     /* tile retry + non-max suppression */
+#define SWM_STAGE_PYRAMID 1 /* pyramid + border + Gaussian blur (pyr_kernel x nlevels) */
+#define SWM_STAGE_NMS 2     /* FAST score + tile retry + non-max suppression (fast_kernel x 2) */
 #define SWM_STAGE_OCTREE 4
 #define SWM_STAGE_DESCRIBE 8 /* orientation + rBRIEF + output assembly */
 

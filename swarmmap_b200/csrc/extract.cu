@@ -1,13 +1,14 @@
-// extract.cu -- B200 (sm_100a) ORB extractor: fused pyramid/border/FAST-score/blur level kernels,
-// tile-retry non-max suppression, block-parallel quadtree, orientation + rBRIEF, and the C ABI of
-// the extractor (include/swm_orb.h).  Batched over frames: every launch covers all frames of a
-// batch, nothing returns to the host between stages.
+// extract.cu -- B200 (sm_100a) ORB extractor: word-packed pyramid + border + Gaussian blur kernel,
+// FAST kernel (TMA-staged tiles, packed quick reject, 16x2-SIMD score, tile retry + non-max
+// suppression), block-parallel quadtree, orientation + rBRIEF, and the C ABI of the extractor
+// (include/swm_orb.h).  Batched over frames: every launch covers all frames of a batch, nothing
+// returns to the host between stages.
 //
 // Reference behaviour restated (paths relative to /root/reference/code/):
 //   ORBextractor::operator()            src/ORBextractor.cc:746-819
 //   ORBextractor::ComputePyramid        src/ORBextractor.cc:821-855   (cv::resize INTER_LINEAR 8U semantics)
 //   ComputeKeyPointsOctTree             src/ORBextractor.cc:691-744
-//   tileCalcKeypoints_kernel            src/cuda/Fast_gpu.cu:284-341  (lock-step deterministic form)
+//   tileCalcKeypoints_kernel            src/cuda/Fast_gpu.cu:284-341  (lock-step deterministic form, fast_kernel)
 //   DistributeOctTree                   src/ORBextractor.cc:465-689   (octree_core.cuh)
 //   IC_Angle_kernel / addBorder_kernel  src/cuda/Fast_gpu.cu:403-471
 //   Gaussian 7x7 sigma 2                src/ORBextractor.cc:835,719,742 (cv::GaussianBlur 8U semantics)

@@ -12,8 +12,9 @@
 // take best / second best Hamming distance among candidates that are still free, accept under a
 // threshold + ratio rule, mutate the free-state".  The enumeration and all distances are
 // embarrassingly parallel (one warp per source row, LOP3+POPC on the CUDA cores); only the greedy
-// accept/steal state is order dependent, and that is replayed by a single warp over the
-// pre-computed candidate rows (resolve_kernel), which keeps match indices bit-exact.
+// accept/steal state is order dependent, and that is replayed over the pre-computed candidate rows
+// by resolve_kernel (speculative batches of 32 rows, in-order commit), which keeps match indices
+// bit-exact.  The place-recognition shard scan uses the u8 tensor-core MMA (db_top2_mma_kernel).
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -26,7 +27,6 @@
 
 namespace swm {
 
-constexpr int kThHigh = 100;    // ORBmatcher.cc:37
 constexpr int kThLow = 50;      // ORBmatcher.cc:38
 constexpr int kHistoLen = 30;   // ORBmatcher.cc:39
 constexpr int kGridCols = SWM_GRID_COLS, kGridRows = SWM_GRID_ROWS, kCells = kGridCols * kGridRows;
