@@ -635,13 +635,13 @@ __global__ void __launch_bounds__(kDbQPerCta) db_top2_kernel(const uint4* __rest
 // (north_star's "popc(a)+popc(b)-2*popc(a&b)" identity; the b1 AND/XOR-popc MMA it mentions is not native
 // on sm_100a -- it compiles to IMMA plus bit expansion -- so the expansion is done once per CTA tile here).
 // One warp owns 32 queries (A fragments for all 256 dimensions stay in 64 registers); the CTA streams the
-// database in tiles of 128 descriptors, expanded to bytes in shared memory (row stride 272 B -> the 8
-// descriptors of a fragment hit different banks).  Per thread a running top-2 of (dist << 20 | index in
+// database in tiles of 128 descriptors, expanded to bytes in shared memory in fragment order (one 64-bit
+// load per B fragment, row stride 288 B -> conflict-free).  Per thread a running top-2 of (dist << 20 | index in
 // this CTA's slice) for its two query rows; quads are merged by shuffles at the end.  Output format and
 // the cross-slice merge are those of the POPC kernel, results are identical (ties -> lower index).
 // ---------------------------------------------------------------------------------------------
 constexpr int kMmaTile = 128;          // database descriptors per smem tile
-constexpr int kMmaRow = 272;           // bytes per expanded descriptor row: 68 words = 4 mod 32 -> the (g,t) fragment loads hit 32 banks
+constexpr int kMmaRow = 288;           // bytes per expanded descriptor row: 36 x 8 B = 4 mod 16 -> 64-bit fragment loads are conflict-free
 constexpr int kMmaQPerCta = 256;       // 8 warps x 32 queries
 
 __device__ __forceinline__ uint32_t expand_nibble(uint32_t w, int shift) {
@@ -664,82 +664,83 @@ __global__ void __launch_bounds__(256, 2) db_top2_mma_kernel(const uint4* __rest
                                                              const uint32_t* __restrict__ q, int nq, int tiles_per_cta,
                                                              unsigned long long* __restrict__ partial) {
   __shared__ __align__(16) uint8_t s_exp[kMmaTile * kMmaRow];
-  __shared__ int s_pd[kMmaTile];
+  __shared__ __align__(8) uint32_t s_cb[kMmaTile];  // per column: (popc + 256) << 20 | index in slice
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   // ---- A fragments: this warp's 32 queries = two 16-row blocks (rows g, g+8 of each), all 8 k-steps,
   // expanded from bits.  Every B fragment read from shared memory then feeds two MMAs (the kernel is
   // otherwise bound by shared-memory bandwidth: 256 B of B operand per MMA).
-  int qrow[4];
+  const int qrow0 = blockIdx.y * kMmaQPerCta + wid * 32 + g;  // rows of this thread: qrow0 + 8 r, r = 0..3
   uint32_t a[2][8][4];
-  int pq[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int mt = 0; mt < 2; mt++) {
-    qrow[2 * mt] = blockIdx.y * kMmaQPerCta + wid * 32 + mt * 16 + g;
-    qrow[2 * mt + 1] = qrow[2 * mt] + 8;
+    const int r0 = qrow0 + 16 * mt, r1 = r0 + 8;
 #pragma unroll
     for (int ks = 0; ks < 8; ks++) {
-      const uint32_t w0 = qrow[2 * mt] < nq ? __ldg(q + (size_t)qrow[2 * mt] * 8 + ks) : 0u;
-      const uint32_t w1 = qrow[2 * mt + 1] < nq ? __ldg(q + (size_t)qrow[2 * mt + 1] * 8 + ks) : 0u;
-      pq[2 * mt] += __popc(w0);
-      pq[2 * mt + 1] += __popc(w1);
+      const uint32_t w0 = r0 < nq ? __ldg(q + (size_t)r0 * 8 + ks) : 0u;
+      const uint32_t w1 = r1 < nq ? __ldg(q + (size_t)r1 * 8 + ks) : 0u;
       a[mt][ks][0] = expand_nibble(w0, 4 * t);
       a[mt][ks][1] = expand_nibble(w1, 4 * t);
       a[mt][ks][2] = expand_nibble(w0, 16 + 4 * t);
       a[mt][ks][3] = expand_nibble(w1, 16 + 4 * t);
     }
   }
-  uint32_t k0[4] = {~0u, ~0u, ~0u, ~0u}, k1[4] = {~0u, ~0u, ~0u, ~0u};  // running top-2 keys of the 4 rows
+  // running top-2 keys of the 4 rows.  Inside the scan a key is (popc(d) + 256 - 2 dot) << 20 | index: the
+  // query's own popcount is the same for every column of a row, so it is added only when the key is widened.
+  uint32_t k0[4] = {~0u, ~0u, ~0u, ~0u}, k1[4] = {~0u, ~0u, ~0u, ~0u};
   const long long tile0 = (long long)blockIdx.x * tiles_per_cta;
+  // thread = (descriptor n of the tile, half of its 8 words); the next tile's bits are fetched into
+  // registers before the MMA loop of the current one, so the DRAM latency is off the critical path
+  const int xn = tid >> 1, xhalf = tid & 1;
+  uint4 w_next = make_uint4(0, 0, 0, 0);
+  if (tile0 * kMmaTile + xn < ndb) w_next = __ldg(db + 2 * (tile0 * kMmaTile + xn) + xhalf);
   for (int tile = 0; tile < tiles_per_cta; tile++) {
     const long long base = (tile0 + tile) * kMmaTile;
     if (base >= ndb) break;
     __syncthreads();
-    {  // expand this tile: thread = (descriptor n, half of its 8 words)
-      const int n = tid >> 1, half = tid & 1;
-      uint4 w = make_uint4(0, 0, 0, 0);
-      const bool live = base + n < ndb;
-      if (live) w = __ldg(db + 2 * (base + n) + half);
+    {  // expand this tile to 0/1 bytes, in fragment order: k-step ks, lane t -> 8 bytes (b0 | b1) at 32 ks + 8 t
+      const uint4 w = w_next;
+      const bool live = base + xn < ndb;
       int pc = __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
       pc += __shfl_xor_sync(0xffffffffu, pc, 1);
-      if (half == 0) s_pd[n] = live ? pc : 1000;  // padding rows can never win (and d << 20 still fits 32 bits)
-      uint32_t* dst = reinterpret_cast<uint32_t*>(s_exp + n * kMmaRow + 128 * half);
+      // padding rows can never win (dot = 0 and the key still fits 32 bits)
+      if (xhalf == 0) s_cb[xn] = ((uint32_t)((live ? pc : 1000) + 256) << 20) | (uint32_t)(tile * kMmaTile + xn);
+      uint4* dst = reinterpret_cast<uint4*>(s_exp + xn * kMmaRow + 128 * xhalf);
       const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int k = 0; k < 4; k++)
-#pragma unroll
-        for (int j = 0; j < 8; j++) dst[8 * k + j] = expand_nibble(ww[k], 4 * j);
+      for (int k = 0; k < 4; k++) {
+        dst[2 * k] = make_uint4(expand_nibble(ww[k], 0), expand_nibble(ww[k], 16), expand_nibble(ww[k], 4), expand_nibble(ww[k], 20));
+        dst[2 * k + 1] = make_uint4(expand_nibble(ww[k], 8), expand_nibble(ww[k], 24), expand_nibble(ww[k], 12), expand_nibble(ww[k], 28));
+      }
+      const long long nb = base + kMmaTile + xn;
+      w_next = (tile + 1 < tiles_per_cta && nb < ndb) ? __ldg(db + 2 * nb + xhalf) : make_uint4(0, 0, 0, 0);
     }
     __syncthreads();
-    const uint32_t idx_base = (uint32_t)(tile * kMmaTile);
     for (int nt = 0; nt < kMmaTile / 8; nt += 2) {  // 2 column blocks x 2 row blocks per step: 4 independent MMAs
       int c[2][2][4] = {};
-      const uint8_t* brow = s_exp + (nt * 8 + g) * kMmaRow + 4 * t;
+      const uint8_t* brow = s_exp + (nt * 8 + g) * kMmaRow + 8 * t;
       const uint8_t* drow = brow + 8 * kMmaRow;
 #pragma unroll
       for (int ks = 0; ks < 8; ks++) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + 32 * ks);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(brow + 32 * ks + 16);
-        const uint32_t e0 = *reinterpret_cast<const uint32_t*>(drow + 32 * ks);
-        const uint32_t e1 = *reinterpret_cast<const uint32_t*>(drow + 32 * ks + 16);
-        mma_u8(c[0][0], a[0][ks], b0, b1);
-        mma_u8(c[0][1], a[0][ks], e0, e1);
-        mma_u8(c[1][0], a[1][ks], b0, b1);
-        mma_u8(c[1][1], a[1][ks], e0, e1);
+        const uint2 b = *reinterpret_cast<const uint2*>(brow + 32 * ks);
+        const uint2 e = *reinterpret_cast<const uint2*>(drow + 32 * ks);
+        mma_u8(c[0][0], a[0][ks], b.x, b.y);
+        mma_u8(c[0][1], a[0][ks], e.x, e.y);
+        mma_u8(c[1][0], a[1][ks], b.x, b.y);
+        mma_u8(c[1][1], a[1][ks], e.x, e.y);
       }
       // c[.][.][0]:(row g, col 2t) [1]:(row g, col 2t+1) [2]:(row g+8, col 2t) [3]:(row g+8, col 2t+1)
       const int n0 = nt * 8 + 2 * t;
-      const int pd[2][2] = {{s_pd[n0], s_pd[n0 + 1]}, {s_pd[n0 + 8], s_pd[n0 + 9]}};
-      const uint32_t i0 = idx_base + n0;
+      const uint2 cb[2] = {*reinterpret_cast<const uint2*>(s_cb + n0), *reinterpret_cast<const uint2*>(s_cb + n0 + 8)};
+      constexpr uint32_t kNeg2 = 0u - (2u << 20);  // key = column base - (2 dot) << 20: one multiply-add per element
 #pragma unroll
       for (int mt = 0; mt < 2; mt++)
 #pragma unroll
         for (int nb = 0; nb < 2; nb++) {
-          const uint32_t ib = i0 + 8 * nb;
-          top2_insert(((uint32_t)(pq[2 * mt] + pd[nb][0] - 2 * c[mt][nb][0]) << 20) | ib, k0[2 * mt], k1[2 * mt]);
-          top2_insert(((uint32_t)(pq[2 * mt] + pd[nb][1] - 2 * c[mt][nb][1]) << 20) | (ib + 1), k0[2 * mt], k1[2 * mt]);
-          top2_insert(((uint32_t)(pq[2 * mt + 1] + pd[nb][0] - 2 * c[mt][nb][2]) << 20) | ib, k0[2 * mt + 1], k1[2 * mt + 1]);
-          top2_insert(((uint32_t)(pq[2 * mt + 1] + pd[nb][1] - 2 * c[mt][nb][3]) << 20) | (ib + 1), k0[2 * mt + 1], k1[2 * mt + 1]);
+          top2_insert((uint32_t)c[mt][nb][0] * kNeg2 + cb[nb].x, k0[2 * mt], k1[2 * mt]);
+          top2_insert((uint32_t)c[mt][nb][1] * kNeg2 + cb[nb].y, k0[2 * mt], k1[2 * mt]);
+          top2_insert((uint32_t)c[mt][nb][2] * kNeg2 + cb[nb].x, k0[2 * mt + 1], k1[2 * mt + 1]);
+          top2_insert((uint32_t)c[mt][nb][3] * kNeg2 + cb[nb].y, k0[2 * mt + 1], k1[2 * mt + 1]);
         }
     }
   }
@@ -754,16 +755,21 @@ __global__ void __launch_bounds__(256, 2) db_top2_mma_kernel(const uint4* __rest
     }
   if (t == 0) {
     const unsigned long long slice_base = (unsigned long long)(first_index + tile0 * kMmaTile);
-    auto widen = [&](uint32_t key) -> unsigned long long {
-      if (key == ~0u || (key >> 20) > 256) return ~0ull;
-      return ((unsigned long long)(key >> 20) << 48) | (slice_base + (key & 0xFFFFFu));
-    };
 #pragma unroll
-    for (int r = 0; r < 4; r++)
-      if (qrow[r] < nq) {
-        partial[((size_t)blockIdx.x * nq + qrow[r]) * 2] = widen(k0[r]);
-        partial[((size_t)blockIdx.x * nq + qrow[r]) * 2 + 1] = widen(k1[r]);
-      }
+    for (int r = 0; r < 4; r++) {
+      const int row = qrow0 + 8 * r;
+      if (row >= nq) continue;
+      int pq = 0;
+#pragma unroll
+      for (int ks = 0; ks < 8; ks++) pq += __popc(__ldg(q + (size_t)row * 8 + ks));
+      auto widen = [&](uint32_t key) -> unsigned long long {
+        const int d = (int)(key >> 20) + pq - 256;
+        if (key == ~0u || d > 256) return ~0ull;
+        return ((unsigned long long)d << 48) | (slice_base + (key & 0xFFFFFu));
+      };
+      partial[((size_t)blockIdx.x * nq + row) * 2] = widen(k0[r]);
+      partial[((size_t)blockIdx.x * nq + row) * 2 + 1] = widen(k1[r]);
+    }
   }
 }
 
