@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "swm_internal.cuh"
+#include "db_umma.cuh"
 
 namespace swm {
 
@@ -1450,18 +1451,24 @@ int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t*
   if (!db || !d_q || nq <= 0 || k < 1 || k > 2 || !d_topk) return SWM_E_INVALID;
   if (cudaSetDevice(db->device) != cudaSuccess) return SWM_E_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
-  // SWM_DB_POPC=1 selects the CUDA-core LOP3+POPC kernel (kept for the A/B measurement in profiles/);
-  // the default is the tensor-core kernel.  Both produce identical keys.
-  static const bool use_popc = getenv("SWM_DB_POPC") != nullptr;
-  const int tile = use_popc ? kDbTile : kMmaTile;
-  const int qper = use_popc ? kDbQPerCta : kMmaQPerCta;
+  // Three kernels produce identical keys.  Default: tcgen05 int8 (db_umma.cuh).  SWM_DB_KERNEL=imma selects the
+  // legacy mma.sync kernel, SWM_DB_KERNEL=popc the CUDA-core LOP3+POPC kernel; both are kept as A/B baselines for
+  // profiles/ and as independent implementations the parity tests cross-check.
+  const int kind = [] {  // read per call so that one process can cross-check the three kernels
+    const char* e = getenv("SWM_DB_KERNEL");
+    if (e && !strcmp(e, "popc")) return 2;
+    if (e && !strcmp(e, "imma")) return 1;
+    return 0;
+  }();
+  const int tile = kind == 2 ? kDbTile : kind == 1 ? kMmaTile : umma::kTileN;
+  const int qper = kind == 2 ? kDbQPerCta : kind == 1 ? kMmaQPerCta : umma::kQPerCta;
   const long long tiles = (db->ndesc + tile - 1) / tile;
   const int qblocks = (nq + qper - 1) / qper;
   // enough database slices that slices x query blocks fills the machine a few times over
-  long long parts = std::max<long long>(1, (long long)db->n_sm * 8 / qblocks);
+  long long parts = std::max<long long>(1, (long long)db->n_sm * (kind == 0 ? 4 : 8) / qblocks);
   parts = std::min<long long>(parts, tiles);
   int tiles_per_cta = (int)((tiles + parts - 1) / parts);
-  if (!use_popc) tiles_per_cta = std::min(tiles_per_cta, (1 << 20) / kMmaTile);  // 20-bit in-slice index
+  if (kind != 2) tiles_per_cta = std::min(tiles_per_cta, (1 << 20) / tile);  // 20-bit in-slice index
   parts = (tiles + tiles_per_cta - 1) / tiles_per_cta;
   const size_t need = (size_t)parts * nq * 2 * sizeof(unsigned long long);
   if (need > db->partial_cap) {
@@ -1473,12 +1480,19 @@ int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t*
   }
   const long long first_index = db->first_kf * db->desc_per_kf;
   dim3 grid((unsigned)parts, qblocks);
-  if (use_popc)
+  if (kind == 2) {
     db_top2_kernel<<<grid, kDbQPerCta, 0, st>>>((const uint4*)db->d_desc, db->ndesc, first_index, (const uint4*)d_q, nq,
                                                 tiles_per_cta, db->d_partial);
-  else
+  } else if (kind == 1) {
     db_top2_mma_kernel<<<grid, 256, 0, st>>>((const uint4*)db->d_desc, db->ndesc, first_index, (const uint32_t*)d_q, nq,
                                              tiles_per_cta, db->d_partial);
+  } else {
+    if (cudaFuncSetAttribute(umma::db_top2_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             umma::kSmemBytes) != cudaSuccess)
+      return SWM_E_CUDA;
+    umma::db_top2_umma_kernel<<<grid, umma::kThreads, umma::kSmemBytes, st>>>(
+        (const uint4*)db->d_desc, db->ndesc, first_index, (const uint4*)d_q, nq, tiles_per_cta, db->d_partial);
+  }
   const long long n_kf = (db->ndesc + db->desc_per_kf - 1) / db->desc_per_kf;
   db_merge_kernel<<<(nq + 127) / 128, 128, 0, st>>>(db->d_partial, (int)parts, nq, k, (unsigned long long*)d_topk,
                                                     d_votes, th_votes, db->first_kf, db->desc_per_kf, first_index, n_kf);

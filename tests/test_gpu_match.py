@@ -199,40 +199,55 @@ def test_search_by_bow(oracle, swm, frames, mode, ratio):
     assert n == 0 and (out == -1).all()
 
 
-def test_db_top2_shard(oracle, swm):
+def _db_case(rng, nq, ndb):
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    db = rng.integers(0, 256, (ndb, 32), dtype=np.uint8)
+    for i in range(0, nq, 3):  # planted noisy copies + exact duplicates (tie-break on index)
+        j = int(rng.integers(0, ndb))
+        bits = np.unpackbits(q[i])
+        bits[rng.choice(256, 20, replace=False)] ^= 1
+        db[j] = np.packbits(bits)
+    if ndb > 800:
+        db[777] = db[123]
+        q[5] = db[123]
+    # extreme popcounts on both sides: distance 0 and 256, all-zero / all-one rows
+    q[1] = 0
+    q[2] = 255
+    db[ndb - 1] = 0
+    db[ndb // 2] = 255
+    return q, db
+
+
+@pytest.mark.parametrize("kernel", ["umma", "imma", "popc"])
+@pytest.mark.parametrize("nq,ndb", [(300, 20000), (256, 128 * 40), (17, 77), (513, 2), (40, 70001)])
+def test_db_top2_shard(oracle, swm, monkeypatch, kernel, nq, ndb):
+    """Shard scan == oracle brute force (distance, index, tie-break, votes) for each of the three kernels:
+    tcgen05 int8 (default), legacy mma.sync, CUDA-core POPC."""
     import ctypes as C
     import torch
     from swarmmap_b200 import _lib
     lib = _lib.load()
-    rng = np.random.default_rng(99)
-    q = rng.integers(0, 256, (300, 32), dtype=np.uint8)
-    db = rng.integers(0, 256, (20000, 32), dtype=np.uint8)
-    for i in range(0, 300, 3):  # planted noisy copies + exact duplicates (tie-break on index)
-        j = int(rng.integers(0, 20000))
-        noisy = q[i].copy()
-        flip = rng.choice(256, 20, replace=False)
-        bits = np.unpackbits(noisy); bits[flip] ^= 1
-        db[j] = np.packbits(bits)
-    db[777] = db[123]
-    q[5] = db[123]
+    monkeypatch.setenv("SWM_DB_KERNEL", kernel)
+    q, db = _db_case(np.random.default_rng(99 + nq), nq, ndb)
     ref = oracle.bruteforce_top2(q, db)
     h = C.c_void_p()
-    first_kf = 1000
-    assert lib.swm_db_create(0, _lib.ptr(db), len(db), 8, first_kf, C.byref(h)) == 0
+    first_kf, per_kf = 1000, 8
+    n_kf = (ndb + per_kf - 1) // per_kf
+    assert lib.swm_db_create(0, _lib.ptr(db), ndb, per_kf, first_kf, C.byref(h)) == 0
     dq = torch.from_numpy(q).cuda()
-    topk = torch.zeros((300, 2), dtype=torch.int64, device="cuda")
-    votes = torch.zeros(len(db) // 8, dtype=torch.int32, device="cuda")
-    rc = lib.swm_db_query_device(h, dq.data_ptr(), 300, 2, topk.data_ptr(), votes.data_ptr(), 50, None)
+    topk = torch.zeros((nq, 2), dtype=torch.int64, device="cuda")
+    votes = torch.zeros(n_kf, dtype=torch.int32, device="cuda")
+    rc = lib.swm_db_query_device(h, dq.data_ptr(), nq, 2, topk.data_ptr(), votes.data_ptr(), 50, None)
     assert rc == 0
     torch.cuda.synchronize()
     t = topk.cpu().numpy().astype(np.uint64)
     dist = (t >> np.uint64(48)).astype(np.int64)
-    idx = (t & np.uint64((1 << 48) - 1)).astype(np.int64) - first_kf * 8
+    idx = (t & np.uint64((1 << 48) - 1)).astype(np.int64) - first_kf * per_kf
     np.testing.assert_array_equal(dist[:, 0], ref[:, 0])
     np.testing.assert_array_equal(idx[:, 0], ref[:, 1])
     np.testing.assert_array_equal(dist[:, 1], ref[:, 2])
     np.testing.assert_array_equal(idx[:, 1], ref[:, 3])
-    exp_votes = np.bincount(ref[ref[:, 0] <= 50, 1] // 8, minlength=len(db) // 8)
+    exp_votes = np.bincount(ref[ref[:, 0] <= 50, 1] // per_kf, minlength=n_kf)
     np.testing.assert_array_equal(votes.cpu().numpy(), exp_votes)
-    assert lib.swm_db_size(h) == len(db)
+    assert lib.swm_db_size(h) == ndb
     lib.swm_db_destroy(h)
