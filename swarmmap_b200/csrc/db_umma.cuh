@@ -12,9 +12,9 @@
 //   A[m][256..260] = bytes summing to 2 popc(q_m), A[m][261] = 1;  B[n][256..260] = 64, B[n][261] = n
 // so the accumulator is D[m][n] = 128 hamming(q_m, x_n) + n  with n < 128 the column inside the tile:
 // a ready-made 16-bit sort key (distance << 7 | column).  The epilogue never computes a distance: it
-// packs the keys of two queries (rows m and m + 128 of the CTA's 256) into one register and keeps a
-// per-tile top-2 with 16x2 SIMD min/max, folding it into a 32-bit (distance << 20 | index) top-2 once
-// per tile.
+// packs the keys of two queries (rows m and m + 128 of the CTA's 256) into one register, finds chunk minima with
+// 16x2 SIMD min, runs the exact 16x2 top-2 insertion only for chunks that can still matter, and folds the tile's
+// top-2 into a 32-bit (distance << 20 | index) top-2 once per tile.
 //
 // CTA = 9 warps: 0-3 epilogue (TMEM lane quarter = warp id), 4 = MMA issuer, 5-8 = producers that
 // expand database bits to bytes in shared memory (K-major, no swizzle: 8-row x 16-byte core matrices).
@@ -64,16 +64,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   const uint32_t lo = ((addr & 0x3FFFFu) >> 4) | ((uint32_t)(kLbo >> 4) << 16);
-  const uint32_t hi = (uint32_t)(kSbo >> 4) | (1u << 14);  // version 1 (sm_100), no swizzle, base offset 0
-  return ((uint64_t)hi << 32) | lo;
+  return ((uint64_t)((uint32_t)(kSbo >> 4) | (1u << 14)) << 32) | lo;
 }
 
-__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(kIdesc), "r"(accumulate)
-      : "memory");
+// Descriptors are passed as their low words; the high word (strides, version) is the same constant for all.
+constexpr uint32_t kDescHi = (uint32_t)(kSbo >> 4) | (1u << 14);  // version 1 (sm_100), no swizzle, base offset 0
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, bool accumulate) {
+  if (accumulate)
+    asm volatile(
+        "{\n.reg .b64 da, db;\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n}" ::"r"(tmem_d),
+        "r"(adesc_lo), "r"(bdesc_lo), "r"(kDescHi), "r"(kIdesc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n.reg .b64 da, db;\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n}" ::"r"(tmem_d),
+        "r"(adesc_lo), "r"(bdesc_lo), "r"(kDescHi), "r"(kIdesc)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xFFFFFFFF;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -104,26 +117,35 @@ __device__ __forceinline__ uint32_t expand_nibble2(uint32_t w, int shift) {
   return (((w >> shift) & 0xFu) * 0x00408102u) & 0x02020202u;
 }
 
-// Top-2 of two independent 16-bit key streams (low / high half) with 16x2 SIMD min/max.
+// One chunk = 16 accumulator columns of both A tiles.  The keys of rows m (low half) and m + 128 (high half) are
+// packed into one register and a 16x2 SIMD min tree finds the chunk minimum; only when some lane of the warp sees
+// a key below its running second-best distance (thr, packed per half) is the exact top-2 insertion run.  Keys that
+// are skipped have distance >= the second-best of an earlier (lower-index) entry, so they can never be reported.
 template <bool kMask>
 __device__ __forceinline__ void consume16(const uint32_t (&a)[16], const uint32_t (&b)[16], int col0, int limit,
-                                          uint32_t& k0, uint32_t& k1) {
+                                          uint32_t thr, uint32_t& k0, uint32_t& k1) {
+  uint32_t p[16];
 #pragma unroll
-  for (int i = 0; i < 16; i += 2) {
-    uint32_t p0 = __byte_perm(a[i], b[i], 0x5410), p1 = __byte_perm(a[i + 1], b[i + 1], 0x5410);
-    if (kMask) {  // last, partial tile only: columns past the end of the database never win
-      if (col0 + i >= limit) p0 = 0xFFFFFFFFu;
-      if (col0 + i + 1 >= limit) p1 = 0xFFFFFFFFu;
+  for (int i = 0; i < 16; i++) {
+    p[i] = b[i] * 65536u + a[i];  // a < 65536: a multiply-add on the FMA pipe instead of a byte permute on the ALU
+    if (kMask && col0 + i >= limit) p[i] = 0xFFFFFFFFu;  // last, partial tile: columns past the end never win
+  }
+  uint32_t m = __vminu2(p[0], p[1]);
+#pragma unroll
+  for (int i = 2; i < 16; i += 2) m = __vminu2(__vminu2(m, p[i]), p[i + 1]);
+  if (__any_sync(0xFFFFFFFFu, __vminu2(m, thr) != thr)) {
+#pragma unroll
+    for (int i = 0; i < 16; i += 2) {
+      const uint32_t lo = __vminu2(p[i], p[i + 1]), hi = __vmaxu2(p[i], p[i + 1]);
+      const uint32_t t = __vmaxu2(k0, lo);
+      k1 = __vminu2(__vminu2(t, k1), hi);
+      k0 = __vminu2(k0, lo);
     }
-    const uint32_t lo = __vminu2(p0, p1), hi = __vmaxu2(p0, p1);
-    const uint32_t t = __vmaxu2(k0, lo);
-    k1 = __vminu2(__vminu2(t, k1), hi);
-    k0 = __vminu2(k0, lo);
   }
 }
 
 template <bool kMask>
-__device__ __forceinline__ void scan_tile(uint32_t taddr0, int limit, uint32_t& k0, uint32_t& k1) {
+__device__ __forceinline__ void scan_tile(uint32_t taddr0, int limit, uint32_t thr, uint32_t& k0, uint32_t& k1) {
   // taddr0: accumulator of A tile 0 (queries m), +128 columns: A tile 1 (queries m + 128)
   uint32_t a0[16], a1[16], b0[16], b1[16];
   tmem_ld16(a0, taddr0);
@@ -133,13 +155,13 @@ __device__ __forceinline__ void scan_tile(uint32_t taddr0, int limit, uint32_t& 
     tmem_wait(a0, a1);
     tmem_ld16(b0, taddr0 + 16 * (c + 1));
     tmem_ld16(b1, taddr0 + 128 + 16 * (c + 1));
-    consume16<kMask>(a0, a1, 16 * c, limit, k0, k1);
+    consume16<kMask>(a0, a1, 16 * c, limit, thr, k0, k1);
     tmem_wait(b0, b1);
     if (c + 2 < kTileN / 16) {
       tmem_ld16(a0, taddr0 + 16 * (c + 2));
       tmem_ld16(a1, taddr0 + 128 + 16 * (c + 2));
     }
-    consume16<kMask>(b0, b1, 16 * (c + 1), limit, k0, k1);
+    consume16<kMask>(b0, b1, 16 * (c + 1), limit, thr, k0, k1);
   }
 }
 
@@ -241,11 +263,13 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
       mbar_wait(bar_tfull + 8 * t, (i >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
+      // packed per-half threshold: the running second-best distance << 7 (a later key must be strictly closer)
+      const uint32_t thr = min((r1[0] >> 20) << 7, 0xFFFFu) | (min((r1[1] >> 20) << 7, 0xFFFFu) << 16);
       const long long remain = ndb - (tile0 + i) * kTileN;
       if (remain >= kTileN)
-        scan_tile<false>(lane_addr + t * 256, kTileN, k0, k1);
+        scan_tile<false>(lane_addr + t * 256, kTileN, thr, k0, k1);
       else
-        scan_tile<true>(lane_addr + t * 256, (int)remain, k0, k1);
+        scan_tile<true>(lane_addr + t * 256, (int)remain, thr, k0, k1);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * t);
@@ -272,27 +296,28 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
       partial[((size_t)blockIdx.x * nq + row) * 2 + 1] = widen(r1[h]);
     }
   } else if (warp == 4) {
-    // ===== MMA issuer: one thread
-    if (lane == 0) {
-      const uint64_t a0 = smem_desc(smem_u32(s_a)), a1 = smem_desc(smem_u32(s_a + kTileBytes));
-      for (int i = 0; i < ntiles; i++) {
-        const int s = i % kStages, t = i & 1;
-        mbar_wait(bar_tempty + 8 * t, ((i >> 1) & 1) ^ 1);
-        mbar_wait(bar_full + 8 * s, (i / kStages) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint64_t b = smem_desc(smem_u32(s_b + s * kTileBytes));
-        const uint32_t d0 = tmem_base + t * 256, d1 = d0 + 128;
+    // ===== MMA issuer.  The whole warp runs the loop so that descriptors and barrier addresses stay warp-uniform
+    // (uniform registers feed UTCIMMA directly); one elected lane issues.
+    const uint32_t a0 = (uint32_t)smem_desc(smem_u32(s_a)), a1 = (uint32_t)smem_desc(smem_u32(s_a + kTileBytes));
+    for (int i = 0; i < ntiles; i++) {
+      const int s = i % kStages, t = i & 1;
+      mbar_wait(bar_tempty + 8 * t, ((i >> 1) & 1) ^ 1);
+      mbar_wait(bar_full + 8 * s, (i / kStages) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t b = (uint32_t)smem_desc(smem_u32(s_b + s * kTileBytes));
+      const uint32_t d0 = tmem_base + t * 256, d1 = d0 + 128;
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < kKSteps; ks++) {  // one k-step = two 16-byte K chunks = 2 kLbo bytes
-          const uint64_t adv = (uint64_t)((2 * kLbo * ks) >> 4);
+          const uint32_t adv = (uint32_t)((2 * kLbo * ks) >> 4);
           mma_i8(d0, a0 + adv, b + adv, ks > 0);
           mma_i8(d1, a1 + adv, b + adv, ks > 0);
         }
         mma_commit(bar_empty + 8 * s);  // B stage free once these MMAs have read it
         mma_commit(bar_tfull + 8 * t);  // accumulators complete
       }
+      __syncwarp();
     }
-    __syncwarp();
   } else {
     // ===== producers: thread = database row n of the tile
     const int n = tid - 5 * 32;

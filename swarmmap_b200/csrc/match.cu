@@ -1465,7 +1465,7 @@ int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t*
   const long long tiles = (db->ndesc + tile - 1) / tile;
   const int qblocks = (nq + qper - 1) / qper;
   // enough database slices that slices x query blocks fills the machine a few times over
-  long long parts = std::max<long long>(1, (long long)db->n_sm * (kind == 0 ? 4 : 8) / qblocks);
+  long long parts = std::max<long long>(1, (long long)db->n_sm * (kind == 0 ? 2 : 8) / qblocks);
   parts = std::min<long long>(parts, tiles);
   int tiles_per_cta = (int)((tiles + parts - 1) / parts);
   if (kind != 2) tiles_per_cta = std::min(tiles_per_cta, (1 << 20) / tile);  // 20-bit in-slice index

@@ -11,7 +11,7 @@ q = torch.randint(0, 256, (nq, 32), dtype=torch.uint8, device="cuda", generator=
 h = C.c_void_p()
 assert lib.swm_db_create_device(0, db.data_ptr(), ndb, 256, 0, C.byref(h)) == 0
 topk = torch.zeros((nq, 2), dtype=torch.int64, device="cuda")
-for _ in range(2):
+for _ in range(3):
     assert lib.swm_db_query_device(h, q.data_ptr(), nq, 2, topk.data_ptr(), None, 50, None) == 0
 torch.cuda.synchronize()
 print("ok", int(topk[0, 0]) >> 48)
