@@ -9,17 +9,28 @@
 //   A[m][k] = +64 if bit k of query m is 0, -64 if it is 1          (s8, k < 256)
 //   B[n][k] = 2 * bit k of database row n                          (u8, k < 256)
 // the int8 product sums to 128 (popc(x) - 2 q.x).  A ninth K block of 32 constants adds the rest:
-//   A[m][256..260] = bytes summing to 2 popc(q_m), A[m][261] = 1;  B[n][256..260] = 64, B[n][261] = n
-// so the accumulator is D[m][n] = 128 hamming(q_m, x_n) + n  with n < 128 the column inside the tile:
-// a ready-made 16-bit sort key (distance << 7 | column).  The epilogue never computes a distance: it
-// packs the keys of two queries (rows m and m + 128 of the CTA's 256) into one register, finds chunk minima with
-// 16x2 SIMD min, runs the exact 16x2 top-2 insertion only for chunks that can still matter, and folds the tile's
-// top-2 into a 32-bit (distance << 20 | index) top-2 once per tile.
+//   A[m][256..260] = bytes summing to 2 popc(q_m), A[m][261] = 1;  B[n][256..260] = 64, B[n][261] = col(n)
+// so the accumulator is D[m][n] = 128 hamming(q_m, x_n) + col(n), col < 128: a ready-made 16-bit sort key
+// (distance << 7 | column).  The epilogue never computes a distance: it packs the keys of two queries (rows m
+// and m + 128 of the CTA's 256) into one register, finds chunk minima with 16x2 SIMD min, runs the exact 16x2
+// top-2 insertion only for chunks that can still matter, and folds the top-2 of every pair of tiles into a
+// 32-bit (distance << 20 | index) top-2.
 //
-// CTA = 9 warps: 0-3 epilogue (TMEM lane quarter = warp id), 4 = MMA issuer, 5-8 = producers that
-// expand database bits to bytes in shared memory (K-major, no swizzle: 8-row x 16-byte core matrices).
-// Pipelines: full/empty mbarriers over kStages B tiles, tmem_full/tmem_empty over two accumulator
-// stages of 256 TMEM columns (two 128 x 128 s32 tiles, one per A tile).  One CTA per SM.
+// Operands.  The two 128-query A tiles are written once into TMEM (tcgen05.st, 72 columns each) and every MMA
+// takes A from there (.ts form): shared-memory bandwidth is then spent on B only.  With A in shared memory the
+// 128x128x32 MMA reads 8 KB per 64 cycles, the full shared-memory rate, and the kernel stalls on it (measured:
+// tensor pipe 75 % with l1tex tc wavefronts at the same 75 %).  B tiles are 64 database rows expanded from bits
+// to bytes by producer warps (K-major, no swizzle: 8-row x 16-byte core matrices), one tile = two
+// 128x64x32 MMAs per K step.
+//
+// CTA = 22 warps: 0-15 epilogue in four groups of four (TMEM lane quarter = warp & 3; group g takes the tiles of
+// parity g & 1 and columns 32 (g >> 1) .. + 31; the four partial top-2 are merged at the end), 16-17 = MMA
+// issuers (even / odd tiles: the tensor pipe's queue is short, so one issuer's barrier waits between tiles would
+// drain it; with two, one is always issuing), 18-21 = producers (warps 18-19 even tiles, 20-21 odd).  Pipelines: full/empty mbarriers over kStages B tiles,
+// tmem_full/tmem_empty over two accumulator stages of 128 TMEM columns (two 128 x 64 s32 tiles, one per A tile).
+// The epilogue copies its columns to registers and releases the accumulator stage before it looks at them:
+// with two stages the MMA of tile i + 2 waits for the hand-back of tile i, so that latency, not the epilogue's
+// arithmetic, is what the tensor pipe sees.  One CTA per SM.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -27,16 +38,21 @@
 namespace umma {
 
 constexpr int kQPerCta = 256;                 // two A tiles of 128 queries
-constexpr int kTileN = 128;                   // database rows per B tile (= MMA N)
+constexpr int kTileN = 64;                    // database rows per B tile (= MMA N)
 constexpr int kKSteps = 9;                    // 8 x 32 descriptor bits + the constant block
 constexpr int kLbo = 128;                     // bytes between the two 16-byte K chunks of one MMA
 constexpr int kSbo = 18 * 128;                // bytes between 8-row groups: 18 K chunks of 128 B
-constexpr int kTileBytes = 16 * kSbo;         // 128 rows
-constexpr int kStages = 3;
-constexpr int kThreads = 9 * 32;
-constexpr int kSmemBytes = (2 + kStages) * kTileBytes + 256;
+constexpr int kTileBytes = (kTileN / 8) * kSbo;
+constexpr int kStages = 6;                    // even: the stage parity is the tile parity (column field, below)
+constexpr int kThreads = 22 * 32;
+constexpr int kMmaWarp = 16, kProdWarp0 = 18;  // warps 16, 17 issue MMAs
+constexpr int kScratchBytes = 3 * 128 * 16;   // epilogue groups 1-3 -> group 0 hand-over
+constexpr int kSmemBytes = kStages * kTileBytes + kScratchBytes + 256;
 constexpr uint32_t kTmemCols = 512;
-// instruction descriptor (kind::i8): D = s32, A = s8, B = u8, both K-major, N = 128, M = 128
+constexpr uint32_t kAccCols = 2 * kTileN;     // accumulator stage: A tile 0 | A tile 1
+constexpr uint32_t kTmemA = 2 * kAccCols;     // A operands behind the two accumulator stages
+constexpr uint32_t kATileCols = kKSteps * 8;  // 128 rows x 288 bytes = 72 columns
+// instruction descriptor (kind::i8): D = s32, A = s8, B = u8, both K-major, N = 64, M = 128
 constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (0u << 10) | ((kTileN >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,21 +83,27 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   return ((uint64_t)((uint32_t)(kSbo >> 4) | (1u << 14)) << 32) | lo;
 }
 
-// Descriptors are passed as their low words; the high word (strides, version) is the same constant for all.
+// A from TMEM, B through a shared-memory descriptor passed as its low word; the high word (strides, version)
+// is the same constant for every B tile.
 constexpr uint32_t kDescHi = (uint32_t)(kSbo >> 4) | (1u << 14);  // version 1 (sm_100), no swizzle, base offset 0
-__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo, bool accumulate) {
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, bool accumulate) {
   if (accumulate)
     asm volatile(
-        "{\n.reg .b64 da, db;\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n}" ::"r"(tmem_d),
-        "r"(adesc_lo), "r"(bdesc_lo), "r"(kDescHi), "r"(kIdesc)
+        "{\n.reg .b64 db;\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\nmov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %4, p;\n}" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(bdesc_lo), "r"(kDescHi), "r"(kIdesc)
         : "memory");
   else
     asm volatile(
-        "{\n.reg .b64 da, db;\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %3};\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %4, p;\n}" ::"r"(tmem_d),
-        "r"(adesc_lo), "r"(bdesc_lo), "r"(kDescHi), "r"(kIdesc)
+        "{\n.reg .b64 db;\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\nmov.b64 db, {%2, %3};\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %4, p;\n}" ::"r"(tmem_d),
+        "r"(tmem_a), "r"(bdesc_lo), "r"(kDescHi), "r"(kIdesc)
         : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -130,9 +152,11 @@ __device__ __forceinline__ void consume16(const uint32_t (&a)[16], const uint32_
     p[i] = b[i] * 65536u + a[i];  // a < 65536: a multiply-add on the FMA pipe instead of a byte permute on the ALU
     if (kMask && col0 + i >= limit) p[i] = 0xFFFFFFFFu;  // last, partial tile: columns past the end never win
   }
-  uint32_t m = __vminu2(p[0], p[1]);
+  uint32_t m3[5];  // min tree of depth 3 (three-input SIMD min)
 #pragma unroll
-  for (int i = 2; i < 16; i += 2) m = __vminu2(__vminu2(m, p[i]), p[i + 1]);
+  for (int i = 0; i < 5; i++) m3[i] = __vminu2(__vminu2(p[3 * i], p[3 * i + 1]), p[3 * i + 2]);
+  const uint32_t ma = __vminu2(__vminu2(m3[0], m3[1]), m3[2]), mb = __vminu2(__vminu2(m3[3], m3[4]), p[15]);
+  const uint32_t m = __vminu2(ma, mb);
   if (__any_sync(0xFFFFFFFFu, __vminu2(m, thr) != thr)) {
 #pragma unroll
     for (int i = 0; i < 16; i += 2) {
@@ -141,27 +165,6 @@ __device__ __forceinline__ void consume16(const uint32_t (&a)[16], const uint32_
       k1 = __vminu2(__vminu2(t, k1), hi);
       k0 = __vminu2(k0, lo);
     }
-  }
-}
-
-template <bool kMask>
-__device__ __forceinline__ void scan_tile(uint32_t taddr0, int limit, uint32_t thr, uint32_t& k0, uint32_t& k1) {
-  // taddr0: accumulator of A tile 0 (queries m), +128 columns: A tile 1 (queries m + 128)
-  uint32_t a0[16], a1[16], b0[16], b1[16];
-  tmem_ld16(a0, taddr0);
-  tmem_ld16(a1, taddr0 + 128);
-#pragma unroll
-  for (int c = 0; c < kTileN / 16; c += 2) {
-    tmem_wait(a0, a1);
-    tmem_ld16(b0, taddr0 + 16 * (c + 1));
-    tmem_ld16(b1, taddr0 + 128 + 16 * (c + 1));
-    consume16<kMask>(a0, a1, 16 * c, limit, thr, k0, k1);
-    tmem_wait(b0, b1);
-    if (c + 2 < kTileN / 16) {
-      tmem_ld16(a0, taddr0 + 16 * (c + 2));
-      tmem_ld16(a1, taddr0 + 128 + 16 * (c + 2));
-    }
-    consume16<kMask>(b0, b1, 16 * (c + 1), limit, thr, k0, k1);
   }
 }
 
@@ -175,10 +178,10 @@ __global__ void __launch_bounds__(kThreads, 1)
 db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first_index, const uint4* __restrict__ q, int nq,
                     int tiles_per_cta, unsigned long long* __restrict__ partial) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_a = smem;                       // 2 A tiles
-  uint8_t* s_b = smem + 2 * kTileBytes;      // kStages B tiles
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + (2 + kStages) * kTileBytes);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 16);
+  uint8_t* s_b = smem;  // kStages B tiles
+  uint4* s_scratch = reinterpret_cast<uint4*>(smem + kStages * kTileBytes);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kStages * kTileBytes + kScratchBytes);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * kStages + 4);
   const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + kStages);
   const uint32_t bar_tfull = smem_u32(s_bar + 2 * kStages), bar_tempty = smem_u32(s_bar + 2 * kStages + 2);
 
@@ -188,63 +191,29 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
   const int ntiles = (int)min((long long)tiles_per_cta, total_tiles - tile0);
   const int qbase = blockIdx.y * kQPerCta;
 
-  // ---- setup: barriers, TMEM, the A tiles and the constant K block of every B stage
+  // ---- setup: barriers, TMEM, the A tiles (TMEM) and the constant K block of every B stage
   if (tid == 0) {
     for (int s = 0; s < kStages; s++) {
-      mbar_init(bar_full + 8 * s, 4);   // one arrive per producer warp
+      mbar_init(bar_full + 8 * s, 2);   // one arrive per producer warp of the tile's pair
       mbar_init(bar_empty + 8 * s, 1);  // tcgen05.commit
     }
     for (int t = 0; t < 2; t++) {
       mbar_init(bar_tfull + 8 * t, 1);   // tcgen05.commit
-      mbar_init(bar_tempty + 8 * t, 4);  // one arrive per epilogue warp
+      mbar_init(bar_tempty + 8 * t, 8);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (tid < kQPerCta) {  // one query row per thread
-    const int row = qbase + tid;
-    const bool live = row < nq;
-    uint8_t* dst = s_a + (tid >> 7) * kTileBytes + ((tid & 127) >> 3) * kSbo + (tid & 7) * 16;
-    int pq = 0;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const uint4 w = live ? __ldg(q + 2 * (size_t)row + h) : make_uint4(0, 0, 0, 0);
-      pq += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
-      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-      for (int k = 0; k < 4; k++)
-#pragma unroll
-        for (int c = 0; c < 2; c++) {  // K chunk 8 h + 2 k + c: bits 16 c .. 16 c + 15 of word k
-          uint4 v;
-          v.x = 0x40404040u ^ (expand_nibble2(ww[k], 16 * c) << 6);
-          v.y = 0x40404040u ^ (expand_nibble2(ww[k], 16 * c + 4) << 6);
-          v.z = 0x40404040u ^ (expand_nibble2(ww[k], 16 * c + 8) << 6);
-          v.w = 0x40404040u ^ (expand_nibble2(ww[k], 16 * c + 12) << 6);
-          if (!live) v = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(dst + (8 * h + 2 * k + c) * kLbo) = v;
-        }
-    }
-    // constant block: bytes 0..4 sum to 2 popc(q) (each <= 127), byte 5 = 1
-    int rem = live ? 2 * pq : 0;
-    uint32_t e[5];
-#pragma unroll
-    for (int i = 0; i < 5; i++) {
-      e[i] = (uint32_t)min(rem, 127);
-      rem -= (int)e[i];
-    }
-    *reinterpret_cast<uint4*>(dst + 16 * kLbo) =
-        make_uint4(e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24), e[4] | (live ? 0x100u : 0u), 0, 0);
-    *reinterpret_cast<uint4*>(dst + 17 * kLbo) = make_uint4(0, 0, 0, 0);
-  }
-  if (warp >= 5) {  // B constant block: bytes 0..4 = 64, byte 5 = column
-    const int n = tid - 5 * 32;
-    for (int s = 0; s < kStages; s++) {
+  if (warp >= kProdWarp0) {  // B constant block: bytes 0..4 = 64, byte 5 = column field = row + 64 (stage parity)
+    const int n = (tid - kProdWarp0 * 32) & (kTileN - 1);
+    for (int s = (tid - kProdWarp0 * 32) / kTileN; s < kStages; s += 2) {
       uint8_t* dst = s_b + s * kTileBytes + (n >> 3) * kSbo + (n & 7) * 16;
-      *reinterpret_cast<uint4*>(dst + 16 * kLbo) = make_uint4(0x40404040u, 0x40u | ((uint32_t)n << 8), 0, 0);
+      *reinterpret_cast<uint4*>(dst + 16 * kLbo) =
+          make_uint4(0x40404040u, 0x40u | ((uint32_t)(n + kTileN * (s & 1)) << 8), 0, 0);
       *reinterpret_cast<uint4*>(dst + 17 * kLbo) = make_uint4(0, 0, 0, 0);
     }
   }
@@ -254,88 +223,133 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp < 4) {
-    // ===== epilogue: thread = TMEM lane m = queries qbase + m (low half) and qbase + 128 + m (high half)
-    uint32_t r0[2] = {~0u, ~0u}, r1[2] = {~0u, ~0u};  // running 32-bit top-2 per half: dist << 20 | index in slice
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
-    for (int i = 0; i < ntiles; i++) {
-      const int t = i & 1;
-      mbar_wait(bar_tfull + 8 * t, (i >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
-      // packed per-half threshold: the running second-best distance << 7 (a later key must be strictly closer)
-      const uint32_t thr = min((r1[0] >> 20) << 7, 0xFFFFu) | (min((r1[1] >> 20) << 7, 0xFFFFu) << 16);
-      const long long remain = ndb - (tile0 + i) * kTileN;
-      if (remain >= kTileN)
-        scan_tile<false>(lane_addr + t * 256, kTileN, thr, k0, k1);
-      else
-        scan_tile<true>(lane_addr + t * 256, (int)remain, thr, k0, k1);
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * t);
-      // fold the tile's 16-bit keys (dist << 7 | column) into the running 32-bit keys
-      const uint32_t tile_bits = (uint32_t)i << 7;
-#pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const uint32_t x0 = h ? (k0 >> 16) : (k0 & 0xFFFFu), x1 = h ? (k1 >> 16) : (k1 & 0xFFFFu);
-        top2_insert32(((x0 & 0xFF80u) << 13) | (x0 & 0x7Fu) | tile_bits, r0[h], r1[h]);
-        top2_insert32(((x1 & 0xFF80u) << 13) | (x1 & 0x7Fu) | tile_bits, r0[h], r1[h]);
-      }
-    }
-    const unsigned long long slice_base = (unsigned long long)(first_index + tile0 * kTileN);
+  uint32_t r0[2] = {~0u, ~0u}, r1[2] = {~0u, ~0u};  // running 32-bit top-2 per half: dist << 20 | index in slice
+  const int m = (warp & 3) * 32 + lane;               // epilogue: TMEM lane = query row inside each A tile
+  const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  if (warp < 8) {
+    // ---- this thread's query row -> TMEM: lane m, 8 columns per K step (4 consecutive k per column)
+    const int atile = warp >> 2;
+    const int row = qbase + 128 * atile + m;
+    const bool live = row < nq;
+    const uint32_t a_addr = lane_base + kTmemA + atile * kATileCols;
+    int pq = 0;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
-      const int row = qbase + 128 * h + tid;
-      if (row >= nq) continue;
-      auto widen = [&](uint32_t key) -> unsigned long long {
-        const uint32_t d = key >> 20;
-        if (d > 256) return ~0ull;
-        return ((unsigned long long)d << 48) | (slice_base + (key & 0xFFFFFu));
-      };
-      partial[((size_t)blockIdx.x * nq + row) * 2] = widen(r0[h]);
-      partial[((size_t)blockIdx.x * nq + row) * 2 + 1] = widen(r1[h]);
+      const uint4 w = live ? __ldg(q + 2 * (size_t)row + h) : make_uint4(0, 0, 0, 0);
+      pq += __popc(w.x) + __popc(w.y) + __popc(w.z) + __popc(w.w);
+      const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint32_t v[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) v[c] = live ? (0x40404040u ^ (expand_nibble2(ww[k], 4 * c) << 6)) : 0u;
+        tmem_st8(a_addr + 8 * (4 * h + k), v);
+      }
     }
-  } else if (warp == 4) {
-    // ===== MMA issuer.  The whole warp runs the loop so that descriptors and barrier addresses stay warp-uniform
-    // (uniform registers feed UTCIMMA directly); one elected lane issues.
-    const uint32_t a0 = (uint32_t)smem_desc(smem_u32(s_a)), a1 = (uint32_t)smem_desc(smem_u32(s_a + kTileBytes));
-    for (int i = 0; i < ntiles; i++) {
-      const int s = i % kStages, t = i & 1;
-      mbar_wait(bar_tempty + 8 * t, ((i >> 1) & 1) ^ 1);
+    {  // constant block: bytes 0..4 sum to 2 popc(q) (each <= 127), byte 5 = 1
+      int rem = live ? 2 * pq : 0;
+      uint32_t e[5];
+#pragma unroll
+      for (int i = 0; i < 5; i++) {
+        e[i] = (uint32_t)min(rem, 127);
+        rem -= (int)e[i];
+      }
+      const uint32_t v[8] = {e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24), e[4] | (live ? 0x100u : 0u), 0, 0, 0, 0, 0, 0};
+      tmem_st8(a_addr + 8 * 8, v);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  if (warp < 16) {
+    // ===== epilogue: thread = TMEM lane m = queries qbase + m (low half) and qbase + 128 + m (high half)
+    const int par = (warp >> 2) & 1, col_base = (warp >> 3) * 32;
+    const uint32_t taddr0 = lane_base + par * kAccCols + col_base;  // tiles of parity par use accumulator stage par
+    uint32_t thr = 0xFFFFFFFFu;
+    for (int i = par; i < ntiles; i += 2) {
+      mbar_wait(bar_tfull + 8 * par, (i >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // accumulator of A tile 0 (queries m) at taddr0; + kTileN columns: A tile 1 (queries m + 128)
+      uint32_t a0[16], a1[16], b0[16], b1[16];
+      tmem_ld16(a0, taddr0);
+      tmem_ld16(a1, taddr0 + kTileN);
+      tmem_ld16(b0, taddr0 + 16);
+      tmem_ld16(b1, taddr0 + kTileN + 16);
+      tmem_wait(a0, a1);  // waits for all four loads; b0/b1 are tied to the second statement only for the compiler
+      tmem_wait(b0, b1);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * par);  // stage released: the keys are in registers
+      uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
+      const long long remain = ndb - (tile0 + i) * kTileN;
+      if (remain >= kTileN) {
+        consume16<false>(a0, a1, col_base, kTileN, thr, k0, k1);
+        consume16<false>(b0, b1, col_base + 16, kTileN, thr, k0, k1);
+      } else {
+        consume16<true>(a0, a1, col_base, (int)remain, thr, k0, k1);
+        consume16<true>(b0, b1, col_base + 16, (int)remain, thr, k0, k1);
+      }
+      if (k0 != 0xFFFFFFFFu) {
+        // fold the tile's 16-bit keys (dist << 7 | column field) into the running 32-bit keys
+        const uint32_t pair_bits = (uint32_t)(i >> 1) << 7;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const uint32_t x0 = h ? (k0 >> 16) : (k0 & 0xFFFFu), x1 = h ? (k1 >> 16) : (k1 & 0xFFFFu);
+          top2_insert32(((x0 & 0xFF80u) << 13) | (x0 & 0x7Fu) | pair_bits, r0[h], r1[h]);
+          top2_insert32(((x1 & 0xFF80u) << 13) | (x1 & 0x7Fu) | pair_bits, r0[h], r1[h]);
+        }
+        // packed per-half threshold: the running second-best distance << 7 (a later key must be strictly closer)
+        thr = min((r1[0] >> 20) << 7, 0xFFFFu) | (min((r1[1] >> 20) << 7, 0xFFFFu) << 16);
+      }
+    }
+    // groups 1-3 hand their result to group 0 through shared memory
+    if (warp >= 4) s_scratch[((warp >> 2) - 1) * 128 + m] = make_uint4(r0[0], r1[0], r0[1], r1[1]);
+  } else if (warp < kProdWarp0) {
+    // ===== MMA issuers: warp kMmaWarp + par takes the tiles of parity par (accumulator stage par).  The whole warp
+    // runs the loop so that descriptors and barrier addresses stay warp-uniform (uniform registers feed UTCIMMA
+    // directly); one elected lane issues.
+    const int par = warp - kMmaWarp;
+    const uint32_t a0 = tmem_base + kTmemA, a1 = a0 + kATileCols;
+    const uint32_t d0 = tmem_base + par * kAccCols, d1 = d0 + kTileN;
+    const uint32_t b_base = (uint32_t)smem_desc(smem_u32(s_b));
+    for (int i = par; i < ntiles; i += 2) {
+      const int s = i % kStages;
+      mbar_wait(bar_tempty + 8 * par, ((i >> 1) & 1) ^ 1);
       mbar_wait(bar_full + 8 * s, (i / kStages) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t b = (uint32_t)smem_desc(smem_u32(s_b + s * kTileBytes));
-      const uint32_t d0 = tmem_base + t * 256, d1 = d0 + 128;
+      const uint32_t b = b_base + (uint32_t)((s * kTileBytes) >> 4);
       if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < kKSteps; ks++) {  // one k-step = two 16-byte K chunks = 2 kLbo bytes
+        for (int ks = 0; ks < kKSteps; ks++) {  // one k-step = two 16-byte K chunks of B, 8 TMEM columns of A
           const uint32_t adv = (uint32_t)((2 * kLbo * ks) >> 4);
-          mma_i8(d0, a0 + adv, b + adv, ks > 0);
-          mma_i8(d1, a1 + adv, b + adv, ks > 0);
+          mma_i8(d0, a0 + 8 * ks, b + adv, ks > 0);
+          mma_i8(d1, a1 + 8 * ks, b + adv, ks > 0);
         }
-        mma_commit(bar_empty + 8 * s);  // B stage free once these MMAs have read it
-        mma_commit(bar_tfull + 8 * t);  // accumulators complete
+        mma_commit(bar_empty + 8 * s);    // B stage free once these MMAs have read it
+        mma_commit(bar_tfull + 8 * par);  // accumulators complete
       }
       __syncwarp();
     }
   } else {
-    // ===== producers: thread = database row n of the tile
-    const int n = tid - 5 * 32;
-    const int pwarp_lane0 = lane == 0;
+    // ===== producers: thread = database row n of the tile; two warps fill even tiles, two odd tiles
+    const int n = (tid - kProdWarp0 * 32) & (kTileN - 1);
+    const int first = (tid - kProdWarp0 * 32) / kTileN;
     uint4 w0 = make_uint4(0, 0, 0, 0), w1 = w0;
     {
-      const long long row = tile0 * kTileN + n;
-      if (ntiles > 0 && row < ndb) {
+      const long long row = (tile0 + first) * kTileN + n;
+      if (first < ntiles && row < ndb) {
         w0 = __ldg(db + 2 * row);
         w1 = __ldg(db + 2 * row + 1);
       }
     }
-    for (int i = 0; i < ntiles; i++) {
+    for (int i = first; i < ntiles; i += 2) {
       const int s = i % kStages;
       const uint4 c0 = w0, c1 = w1;
-      {  // next tile's bits: in flight while this one is expanded
-        const long long row = (tile0 + i + 1) * kTileN + n;
-        const bool live = i + 1 < ntiles && row < ndb;
+      {  // this thread's next tile: in flight while the current one is expanded
+        const long long row = (tile0 + i + 2) * kTileN + n;
+        const bool live = i + 2 < ntiles && row < ndb;
         w0 = live ? __ldg(db + 2 * row) : make_uint4(0, 0, 0, 0);
         w1 = live ? __ldg(db + 2 * row + 1) : make_uint4(0, 0, 0, 0);
       }
@@ -351,15 +365,38 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
                          expand_nibble2(ww[k], 16 * c + 8), expand_nibble2(ww[k], 16 * c + 12));
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (pwarp_lane0) mbar_arrive(bar_full + 8 * s);
+      if (lane == 0) mbar_arrive(bar_full + 8 * s);
     }
   }
   // ---- teardown
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+  if (warp < 4) {
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      const uint4 o = s_scratch[g * 128 + m];
+      top2_insert32(o.x, r0[0], r1[0]);
+      top2_insert32(o.y, r0[0], r1[0]);
+      top2_insert32(o.z, r0[1], r1[1]);
+      top2_insert32(o.w, r0[1], r1[1]);
+    }
+    const unsigned long long slice_base = (unsigned long long)(first_index + tile0 * kTileN);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int row = qbase + 128 * h + m;
+      if (row >= nq) continue;
+      auto widen = [&](uint32_t key) -> unsigned long long {
+        const uint32_t d = key >> 20;
+        if (d > 256) return ~0ull;
+        return ((unsigned long long)d << 48) | (slice_base + (key & 0xFFFFFu));
+      };
+      partial[((size_t)blockIdx.x * nq + row) * 2] = widen(r0[h]);
+      partial[((size_t)blockIdx.x * nq + row) * 2 + 1] = widen(r1[h]);
+    }
   }
 }
 
