@@ -9,28 +9,28 @@
 //   A[m][k] = +64 if bit k of query m is 0, -64 if it is 1          (s8, k < 256)
 //   B[n][k] = 2 * bit k of database row n                          (u8, k < 256)
 // the int8 product sums to 128 (popc(x) - 2 q.x).  A ninth K block of 32 constants adds the rest:
-//   A[m][256..260] = bytes summing to 2 popc(q_m), A[m][261] = 1;  B[n][256..260] = 64, B[n][261] = col(n)
-// so the accumulator is D[m][n] = 128 hamming(q_m, x_n) + col(n), col < 128: a ready-made 16-bit sort key
-// (distance << 7 | column).  The epilogue never computes a distance: it packs the keys of two queries (rows m
-// and m + 128 of the CTA's 256) into one register, finds chunk minima with 16x2 SIMD min, runs the exact 16x2
-// top-2 insertion only for chunks that can still matter, and folds the top-2 of every pair of tiles into a
-// 32-bit (distance << 20 | index) top-2.
+//   A[m][256..260] = bytes summing to 2 popc(q_m), A[m][261] = 1;  B[n][256..260] = 64, B[n][261] = n
+// so the accumulator is D[m][n] = 128 hamming(q_m, x_n) + n with n < 64 the row inside the B tile: a ready-made
+// 16-bit sort key (distance << 7 | column).  The epilogue never computes a distance: it packs the keys of two
+// queries (rows m and m + 128 of the CTA's 256) into one register, finds chunk minima with 16x2 SIMD min, runs
+// the exact 16x2 top-2 insertion only for chunks that can still matter, and folds a tile's top-2 into a 32-bit
+// (distance << 20 | index) top-2.
 //
-// Operands.  The two 128-query A tiles are written once into TMEM (tcgen05.st, 72 columns each) and every MMA
-// takes A from there (.ts form): shared-memory bandwidth is then spent on B only.  With A in shared memory the
-// 128x128x32 MMA reads 8 KB per 64 cycles, the full shared-memory rate, and the kernel stalls on it (measured:
-// tensor pipe 75 % with l1tex tc wavefronts at the same 75 %).  B tiles are 64 database rows expanded from bits
-// to bytes by producer warps (K-major, no swizzle: 8-row x 16-byte core matrices), one tile = two
-// 128x64x32 MMAs per K step.
+// Operands.  The descriptor bits of the two 128-query A tiles are written once into TMEM (tcgen05.st, 64 columns
+// each) and K steps 0-7 take A from there (.ts MMAs): shared-memory bandwidth is spent on B only.  (With A in
+// shared memory a 128x128x32 MMA reads 8 KB per 64 cycles, the full shared-memory rate; measured: tensor pipe
+// 75 % with l1tex tc wavefronts at the same 75 %.)  The constant K block of A stays in shared memory (4 KB per A
+// tile, K step 8 is an .ss MMA) so that TMEM holds 128 columns of A plus THREE accumulator stages of 128 columns
+// (two 128 x 64 s32 tiles, one per A tile) = 512.  B tiles are 64 database rows expanded from bits to bytes by
+// producer warps (K-major, no swizzle: 8-row x 16-byte core matrices); one tile = two 128x64x32 MMAs per K step.
 //
-// CTA = 22 warps: 0-15 epilogue in four groups of four (TMEM lane quarter = warp & 3; group g takes the tiles of
-// parity g & 1 and columns 32 (g >> 1) .. + 31; the four partial top-2 are merged at the end), 16-17 = MMA
-// issuers (even / odd tiles: the tensor pipe's queue is short, so one issuer's barrier waits between tiles would
-// drain it; with two, one is always issuing), 18-21 = producers (warps 18-19 even tiles, 20-21 odd).  Pipelines: full/empty mbarriers over kStages B tiles,
-// tmem_full/tmem_empty over two accumulator stages of 128 TMEM columns (two 128 x 64 s32 tiles, one per A tile).
-// The epilogue copies its columns to registers and releases the accumulator stage before it looks at them:
-// with two stages the MMA of tile i + 2 waits for the hand-back of tile i, so that latency, not the epilogue's
-// arithmetic, is what the tensor pipe sees.  One CTA per SM.
+// CTA = 19 warps.  0-11 epilogue in three groups of four (TMEM lane quarter = warp & 3): group g owns accumulator
+// stage g = tiles i with i % 3 == g; it copies the tile to registers in two halves and releases the stage before
+// doing the arithmetic of the second half.  12-14 MMA issuers, one per accumulator stage (the tensor pipe's queue
+// is short: a single issuer's barrier waits between tiles drain it).  15-18 producers (15-16 even tiles, 17-18
+// odd).  Pipelines: full/empty mbarriers over kStages B tiles, tmem_full/tmem_empty per accumulator stage.  With
+// three stages the hand-back latency of one stage (commit -> epilogue wake-up -> TMEM loads -> arrive -> issuer
+// wake-up) is covered by the MMAs of the other two.  One CTA per SM.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -41,19 +41,26 @@ constexpr int kQPerCta = 256;                 // two A tiles of 128 queries
 constexpr int kTileN = 64;                    // database rows per B tile (= MMA N)
 constexpr int kKSteps = 9;                    // 8 x 32 descriptor bits + the constant block
 constexpr int kLbo = 128;                     // bytes between the two 16-byte K chunks of one MMA
-constexpr int kSbo = 18 * 128;                // bytes between 8-row groups: 18 K chunks of 128 B
+constexpr int kSbo = 18 * 128;                // B: bytes between 8-row groups: 18 K chunks of 128 B
 constexpr int kTileBytes = (kTileN / 8) * kSbo;
-constexpr int kStages = 6;                    // even: the stage parity is the tile parity (column field, below)
-constexpr int kThreads = 22 * 32;
-constexpr int kMmaWarp = 16, kProdWarp0 = 18;  // warps 16, 17 issue MMAs
-constexpr int kScratchBytes = 3 * 128 * 16;   // epilogue groups 1-3 -> group 0 hand-over
-constexpr int kSmemBytes = kStages * kTileBytes + kScratchBytes + 256;
+constexpr int kStages = 6;                    // B stages
+constexpr int kAccStages = 3;
+constexpr int kEpiWarps = 4 * kAccStages, kMmaWarp = kEpiWarps, kProdWarp0 = kMmaWarp + kAccStages;
+constexpr int kThreads = (kProdWarp0 + 4) * 32;
+constexpr int kAConstSbo = 256;               // A constant block: one K step = 2 chunks per 8-row group
+constexpr int kAConstBytes = 16 * kAConstSbo; // per A tile
+constexpr int kScratchBytes = (kAccStages - 1) * 128 * 16;  // epilogue groups 1.. -> group 0 hand-over
+constexpr int kSmemBytes = kStages * kTileBytes + 2 * kAConstBytes + kScratchBytes + 256;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kAccCols = 2 * kTileN;     // accumulator stage: A tile 0 | A tile 1
-constexpr uint32_t kTmemA = 2 * kAccCols;     // A operands behind the two accumulator stages
-constexpr uint32_t kATileCols = kKSteps * 8;  // 128 rows x 288 bytes = 72 columns
+constexpr uint32_t kAccCols = 2 * kTileN;              // accumulator stage: A tile 0 | A tile 1
+constexpr uint32_t kTmemA = kAccStages * kAccCols;     // A operands behind the accumulator stages
+constexpr uint32_t kATileCols = 8 * 8;                 // 128 rows x 256 bytes = 64 columns
+static_assert(kTmemA + 2 * kATileCols <= kTmemCols, "TMEM budget");
 // instruction descriptor (kind::i8): D = s32, A = s8, B = u8, both K-major, N = 64, M = 128
 constexpr uint32_t kIdesc = (2u << 4) | (1u << 7) | (0u << 10) | ((kTileN >> 3) << 17) | ((128u >> 4) << 24);
+// shared-memory matrix descriptors, high word: stride between 8-row groups, version 1 (sm_100), no swizzle
+constexpr uint32_t kDescHiB = (uint32_t)(kSbo >> 4) | (1u << 14);
+constexpr uint32_t kDescHiA = (uint32_t)(kAConstSbo >> 4) | (1u << 14);
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -63,42 +70,54 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Bounded wait: a pipeline bug traps (launch error) instead of hanging the device.
+// Wait with a hardware suspend hint (the warp sleeps inside try_wait instead of spinning through the issue slots
+// that producers and epilogue share).  Bounded: a pipeline bug traps (launch error) instead of hanging the device.
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity), "r"(0x989680)
+      : "memory");
+  return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0;
+  if (mbar_try(bar, parity)) return;
   const long long t0 = clock64();
-  for (int spin = 0;; spin++) {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
-    if ((spin & 1023) == 1023 && clock64() - t0 > 4000000000ll) __trap();
-  }
+  while (!mbar_try(bar, parity))
+    if (clock64() - t0 > 4000000000ll) __trap();
 }
 
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
-  const uint32_t lo = ((addr & 0x3FFFFu) >> 4) | ((uint32_t)(kLbo >> 4) << 16);
-  return ((uint64_t)((uint32_t)(kSbo >> 4) | (1u << 14)) << 32) | lo;
-}
 
-// A from TMEM, B through a shared-memory descriptor passed as its low word; the high word (strides, version)
-// is the same constant for every B tile.
-constexpr uint32_t kDescHi = (uint32_t)(kSbo >> 4) | (1u << 14);  // version 1 (sm_100), no swizzle, base offset 0
-__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, bool accumulate) {
+// low word of a shared-memory matrix descriptor: start address and the K-chunk stride
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t addr) {
+  return ((addr & 0x3FFFFu) >> 4) | ((uint32_t)(kLbo >> 4) << 16);
+}
+// D[tmem] (+)= A[tmem] . B[smem]
+__device__ __forceinline__ void mma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t bdesc_lo, bool accumulate) {
   if (accumulate)
     asm volatile(
         "{\n.reg .b64 db;\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\nmov.b64 db, {%2, %3};\n"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %4, p;\n}" ::"r"(tmem_d),
-        "r"(tmem_a), "r"(bdesc_lo), "r"(kDescHi), "r"(kIdesc)
+        "r"(tmem_a), "r"(bdesc_lo), "r"(kDescHiB), "r"(kIdesc)
         : "memory");
   else
     asm volatile(
         "{\n.reg .b64 db;\n.reg .pred p;\nsetp.eq.u32 p, 1, 0;\nmov.b64 db, {%2, %3};\n"
         "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], db, %4, p;\n}" ::"r"(tmem_d),
-        "r"(tmem_a), "r"(bdesc_lo), "r"(kDescHi), "r"(kIdesc)
+        "r"(tmem_a), "r"(bdesc_lo), "r"(kDescHiB), "r"(kIdesc)
         : "memory");
+}
+// D[tmem] += A[smem] . B[smem]
+__device__ __forceinline__ void mma_i8_ss(uint32_t tmem_d, uint32_t adesc_lo, uint32_t bdesc_lo) {
+  asm volatile(
+      "{\n.reg .b64 da, db;\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %4};\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n}" ::"r"(tmem_d),
+      "r"(adesc_lo), "r"(bdesc_lo), "r"(kDescHiA), "r"(kDescHiB), "r"(kIdesc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
@@ -109,9 +128,6 @@ __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xFFFFFFFF;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
   return pred != 0;
-}
-__device__ __forceinline__ void mma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
 #define SWM_LD16_OUT(v)                                                                                              \
@@ -178,12 +194,13 @@ __global__ void __launch_bounds__(kThreads, 1)
 db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first_index, const uint4* __restrict__ q, int nq,
                     int tiles_per_cta, unsigned long long* __restrict__ partial) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_b = smem;  // kStages B tiles
-  uint4* s_scratch = reinterpret_cast<uint4*>(smem + kStages * kTileBytes);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem + kStages * kTileBytes + kScratchBytes);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * kStages + 4);
+  uint8_t* s_b = smem;                                   // kStages B tiles
+  uint8_t* s_ac = smem + kStages * kTileBytes;           // constant K block of the two A tiles
+  uint4* s_scratch = reinterpret_cast<uint4*>(s_ac + 2 * kAConstBytes);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ac + 2 * kAConstBytes + kScratchBytes);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * kStages + 2 * kAccStages);
   const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + kStages);
-  const uint32_t bar_tfull = smem_u32(s_bar + 2 * kStages), bar_tempty = smem_u32(s_bar + 2 * kStages + 2);
+  const uint32_t bar_tfull = smem_u32(s_bar + 2 * kStages), bar_tempty = smem_u32(s_bar + 2 * kStages + kAccStages);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long total_tiles = (ndb + kTileN - 1) / kTileN;
@@ -191,15 +208,15 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
   const int ntiles = (int)min((long long)tiles_per_cta, total_tiles - tile0);
   const int qbase = blockIdx.y * kQPerCta;
 
-  // ---- setup: barriers, TMEM, the A tiles (TMEM) and the constant K block of every B stage
+  // ---- setup: barriers, TMEM, the A tiles and the constant K block of every B stage
   if (tid == 0) {
     for (int s = 0; s < kStages; s++) {
       mbar_init(bar_full + 8 * s, 2);   // one arrive per producer warp of the tile's pair
       mbar_init(bar_empty + 8 * s, 1);  // tcgen05.commit
     }
-    for (int t = 0; t < 2; t++) {
+    for (int t = 0; t < kAccStages; t++) {
       mbar_init(bar_tfull + 8 * t, 1);   // tcgen05.commit
-      mbar_init(bar_tempty + 8 * t, 8);  // one arrive per epilogue warp
+      mbar_init(bar_tempty + 8 * t, 4);  // one arrive per epilogue warp of the stage's group
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -208,16 +225,14 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp >= kProdWarp0) {  // B constant block: bytes 0..4 = 64, byte 5 = column field = row + 64 (stage parity)
+  if (warp >= kProdWarp0) {  // B constant block: bytes 0..4 = 64, byte 5 = row inside the tile
     const int n = (tid - kProdWarp0 * 32) & (kTileN - 1);
     for (int s = (tid - kProdWarp0 * 32) / kTileN; s < kStages; s += 2) {
       uint8_t* dst = s_b + s * kTileBytes + (n >> 3) * kSbo + (n & 7) * 16;
-      *reinterpret_cast<uint4*>(dst + 16 * kLbo) =
-          make_uint4(0x40404040u, 0x40u | ((uint32_t)(n + kTileN * (s & 1)) << 8), 0, 0);
+      *reinterpret_cast<uint4*>(dst + 16 * kLbo) = make_uint4(0x40404040u, 0x40u | ((uint32_t)n << 8), 0, 0);
       *reinterpret_cast<uint4*>(dst + 17 * kLbo) = make_uint4(0, 0, 0, 0);
     }
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -227,7 +242,8 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
   const int m = (warp & 3) * 32 + lane;               // epilogue: TMEM lane = query row inside each A tile
   const uint32_t lane_base = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
   if (warp < 8) {
-    // ---- this thread's query row -> TMEM: lane m, 8 columns per K step (4 consecutive k per column)
+    // ---- this thread's query row: descriptor bits -> TMEM (lane m, 8 columns per K step, 4 consecutive k per
+    // column), constant block -> shared memory
     const int atile = warp >> 2;
     const int row = qbase + 128 * atile + m;
     const bool live = row < nq;
@@ -246,89 +262,109 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
         tmem_st8(a_addr + 8 * (4 * h + k), v);
       }
     }
-    {  // constant block: bytes 0..4 sum to 2 popc(q) (each <= 127), byte 5 = 1
-      int rem = live ? 2 * pq : 0;
-      uint32_t e[5];
+    // constant block: bytes 0..4 sum to 2 popc(q) (each <= 127), byte 5 = 1
+    int rem = live ? 2 * pq : 0;
+    uint32_t e[5];
 #pragma unroll
-      for (int i = 0; i < 5; i++) {
-        e[i] = (uint32_t)min(rem, 127);
-        rem -= (int)e[i];
-      }
-      const uint32_t v[8] = {e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24), e[4] | (live ? 0x100u : 0u), 0, 0, 0, 0, 0, 0};
-      tmem_st8(a_addr + 8 * 8, v);
+    for (int i = 0; i < 5; i++) {
+      e[i] = (uint32_t)min(rem, 127);
+      rem -= (int)e[i];
     }
+    uint8_t* dst = s_ac + atile * kAConstBytes + (m >> 3) * kAConstSbo + (m & 7) * 16;
+    *reinterpret_cast<uint4*>(dst) =
+        make_uint4(e[0] | (e[1] << 8) | (e[2] << 16) | (e[3] << 24), e[4] | (live ? 0x100u : 0u), 0, 0);
+    *reinterpret_cast<uint4*>(dst + kLbo) = make_uint4(0, 0, 0, 0);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
   }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-  if (warp < 16) {
+  if (warp < kEpiWarps) {
     // ===== epilogue: thread = TMEM lane m = queries qbase + m (low half) and qbase + 128 + m (high half)
-    const int par = (warp >> 2) & 1, col_base = (warp >> 3) * 32;
-    const uint32_t taddr0 = lane_base + par * kAccCols + col_base;  // tiles of parity par use accumulator stage par
+    const int grp = warp >> 2;
+    const uint32_t taddr0 = lane_base + grp * kAccCols;  // A tile 0 (queries m); + kTileN columns: A tile 1
     uint32_t thr = 0xFFFFFFFFu;
-    for (int i = par; i < ntiles; i += 2) {
-      mbar_wait(bar_tfull + 8 * par, (i >> 1) & 1);
+    for (int i = grp; i < ntiles; i += kAccStages) {
+      mbar_wait(bar_tfull + 8 * grp, (i / kAccStages) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // accumulator of A tile 0 (queries m) at taddr0; + kTileN columns: A tile 1 (queries m + 128)
       uint32_t a0[16], a1[16], b0[16], b1[16];
+      uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
+      const long long remain = ndb - (tile0 + i) * kTileN;
+      const bool full_tile = remain >= kTileN;
+      // columns 0-31
       tmem_ld16(a0, taddr0);
       tmem_ld16(a1, taddr0 + kTileN);
       tmem_ld16(b0, taddr0 + 16);
       tmem_ld16(b1, taddr0 + kTileN + 16);
       tmem_wait(a0, a1);  // waits for all four loads; b0/b1 are tied to the second statement only for the compiler
       tmem_wait(b0, b1);
+      if (full_tile) {
+        consume16<false>(a0, a1, 0, kTileN, thr, k0, k1);
+        consume16<false>(b0, b1, 16, kTileN, thr, k0, k1);
+      } else {
+        consume16<true>(a0, a1, 0, (int)remain, thr, k0, k1);
+        consume16<true>(b0, b1, 16, (int)remain, thr, k0, k1);
+      }
+      // columns 32-63, then the stage goes back to its issuer: the keys are in registers
+      tmem_ld16(a0, taddr0 + 32);
+      tmem_ld16(a1, taddr0 + kTileN + 32);
+      tmem_ld16(b0, taddr0 + 48);
+      tmem_ld16(b1, taddr0 + kTileN + 48);
+      tmem_wait(a0, a1);
+      tmem_wait(b0, b1);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * par);  // stage released: the keys are in registers
-      uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
-      const long long remain = ndb - (tile0 + i) * kTileN;
-      if (remain >= kTileN) {
-        consume16<false>(a0, a1, col_base, kTileN, thr, k0, k1);
-        consume16<false>(b0, b1, col_base + 16, kTileN, thr, k0, k1);
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * grp);
+      if (full_tile) {
+        consume16<false>(a0, a1, 32, kTileN, thr, k0, k1);
+        consume16<false>(b0, b1, 48, kTileN, thr, k0, k1);
       } else {
-        consume16<true>(a0, a1, col_base, (int)remain, thr, k0, k1);
-        consume16<true>(b0, b1, col_base + 16, (int)remain, thr, k0, k1);
+        consume16<true>(a0, a1, 32, (int)remain, thr, k0, k1);
+        consume16<true>(b0, b1, 48, (int)remain, thr, k0, k1);
       }
       if (k0 != 0xFFFFFFFFu) {
-        // fold the tile's 16-bit keys (dist << 7 | column field) into the running 32-bit keys
-        const uint32_t pair_bits = (uint32_t)(i >> 1) << 7;
+        // fold the tile's 16-bit keys (dist << 7 | row in tile) into the running 32-bit keys
+        const uint32_t tile_bits = (uint32_t)i << 6;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           const uint32_t x0 = h ? (k0 >> 16) : (k0 & 0xFFFFu), x1 = h ? (k1 >> 16) : (k1 & 0xFFFFu);
-          top2_insert32(((x0 & 0xFF80u) << 13) | (x0 & 0x7Fu) | pair_bits, r0[h], r1[h]);
-          top2_insert32(((x1 & 0xFF80u) << 13) | (x1 & 0x7Fu) | pair_bits, r0[h], r1[h]);
+          top2_insert32(((x0 & 0xFF80u) << 13) | (x0 & 0x7Fu) | tile_bits, r0[h], r1[h]);
+          top2_insert32(((x1 & 0xFF80u) << 13) | (x1 & 0x7Fu) | tile_bits, r0[h], r1[h]);
         }
         // packed per-half threshold: the running second-best distance << 7 (a later key must be strictly closer)
         thr = min((r1[0] >> 20) << 7, 0xFFFFu) | (min((r1[1] >> 20) << 7, 0xFFFFu) << 16);
       }
     }
-    // groups 1-3 hand their result to group 0 through shared memory
-    if (warp >= 4) s_scratch[((warp >> 2) - 1) * 128 + m] = make_uint4(r0[0], r1[0], r0[1], r1[1]);
+    // groups 1.. hand their result to group 0 through shared memory
+    if (grp > 0) s_scratch[(grp - 1) * 128 + m] = make_uint4(r0[0], r1[0], r0[1], r1[1]);
   } else if (warp < kProdWarp0) {
-    // ===== MMA issuers: warp kMmaWarp + par takes the tiles of parity par (accumulator stage par).  The whole warp
+    // ===== MMA issuers: warp kMmaWarp + g takes the tiles with i % 3 == g (accumulator stage g).  The whole warp
     // runs the loop so that descriptors and barrier addresses stay warp-uniform (uniform registers feed UTCIMMA
     // directly); one elected lane issues.
-    const int par = warp - kMmaWarp;
+    const int grp = warp - kMmaWarp;
     const uint32_t a0 = tmem_base + kTmemA, a1 = a0 + kATileCols;
-    const uint32_t d0 = tmem_base + par * kAccCols, d1 = d0 + kTileN;
-    const uint32_t b_base = (uint32_t)smem_desc(smem_u32(s_b));
-    for (int i = par; i < ntiles; i += 2) {
+    const uint32_t d0 = tmem_base + grp * kAccCols, d1 = d0 + kTileN;
+    const uint32_t b_base = smem_desc_lo(smem_u32(s_b));
+    const uint32_t ac0 = smem_desc_lo(smem_u32(s_ac)), ac1 = smem_desc_lo(smem_u32(s_ac + kAConstBytes));
+    for (int i = grp; i < ntiles; i += kAccStages) {
       const int s = i % kStages;
-      mbar_wait(bar_tempty + 8 * par, ((i >> 1) & 1) ^ 1);
+      mbar_wait(bar_tempty + 8 * grp, ((i / kAccStages) & 1) ^ 1);
       mbar_wait(bar_full + 8 * s, (i / kStages) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t b = b_base + (uint32_t)((s * kTileBytes) >> 4);
       if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < kKSteps; ks++) {  // one k-step = two 16-byte K chunks of B, 8 TMEM columns of A
+        for (int ks = 0; ks < 8; ks++) {  // one k-step = two 16-byte K chunks of B, 8 TMEM columns of A
           const uint32_t adv = (uint32_t)((2 * kLbo * ks) >> 4);
-          mma_i8(d0, a0 + 8 * ks, b + adv, ks > 0);
-          mma_i8(d1, a1 + 8 * ks, b + adv, ks > 0);
+          mma_i8_ts(d0, a0 + 8 * ks, b + adv, ks > 0);
+          mma_i8_ts(d1, a1 + 8 * ks, b + adv, ks > 0);
         }
+        mma_i8_ss(d0, ac0, b + (uint32_t)((2 * kLbo * 8) >> 4));  // constant block: + 128 popc(q) + row in tile
+        mma_i8_ss(d1, ac1, b + (uint32_t)((2 * kLbo * 8) >> 4));
         mma_commit(bar_empty + 8 * s);    // B stage free once these MMAs have read it
-        mma_commit(bar_tfull + 8 * par);  // accumulators complete
+        mma_commit(bar_tfull + 8 * grp);  // accumulators complete
       }
       __syncwarp();
     }
@@ -377,7 +413,7 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
   }
   if (warp < 4) {
 #pragma unroll
-    for (int g = 0; g < 3; g++) {
+    for (int g = 0; g < kAccStages - 1; g++) {
       const uint4 o = s_scratch[g * 128 + m];
       top2_insert32(o.x, r0[0], r1[0]);
       top2_insert32(o.y, r0[0], r1[0]);
