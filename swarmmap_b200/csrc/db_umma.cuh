@@ -137,10 +137,12 @@ __device__ __forceinline__ bool elect_one() {
   "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),       \
       "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
 
-// 16 consecutive accumulator columns of this thread's TMEM lane (asynchronous until tmem_wait).
-__device__ __forceinline__ void tmem_ld16(uint32_t (&v)[16], uint32_t taddr) {
+// 32 consecutive accumulator columns of this thread's TMEM lane, the low 16 bits of two adjacent columns packed
+// into each register (asynchronous until tmem_wait).  Which column lands in which half does not matter here: a
+// key carries its own column.
+__device__ __forceinline__ void tmem_ld32p(uint32_t (&v)[16], uint32_t taddr) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : SWM_LD16_OUT(v)
       : "r"(taddr)
       : "memory");
@@ -155,18 +157,20 @@ __device__ __forceinline__ uint32_t expand_nibble2(uint32_t w, int shift) {
   return (((w >> shift) & 0xFu) * 0x00408102u) & 0x02020202u;
 }
 
-// One chunk = 16 accumulator columns of both A tiles.  The keys of rows m (low half) and m + 128 (high half) are
-// packed into one register and a 16x2 SIMD min tree finds the chunk minimum; only when some lane of the warp sees
-// a key below its running second-best distance (thr, packed per half) is the exact top-2 insertion run.  Keys that
-// are skipped have distance >= the second-best of an earlier (lower-index) entry, so they can never be reported.
+// One chunk = 32 accumulator columns of one query, two 16-bit keys per register.  A 16x2 SIMD min tree finds the
+// minimum of each half; only when some lane of the warp sees a key below its running second-best distance (thr, in
+// both halves) is the exact top-2 insertion run (the two halves are independent streams, merged per tile).  Keys
+// that are skipped have distance >= the second-best of an earlier (lower-index) entry: they can never be reported.
 template <bool kMask>
-__device__ __forceinline__ void consume16(const uint32_t (&a)[16], const uint32_t (&b)[16], int col0, int limit,
-                                          uint32_t thr, uint32_t& k0, uint32_t& k1) {
-  uint32_t p[16];
+__device__ __forceinline__ void consume32(uint32_t (&p)[16], int limit, uint32_t thr, uint32_t& k0, uint32_t& k1) {
+  if (kMask) {  // last, partial tile: rows past the end of the database never win
 #pragma unroll
-  for (int i = 0; i < 16; i++) {
-    p[i] = b[i] * 65536u + a[i];  // a < 65536: a multiply-add on the FMA pipe instead of a byte permute on the ALU
-    if (kMask && col0 + i >= limit) p[i] = 0xFFFFFFFFu;  // last, partial tile: columns past the end never win
+    for (int i = 0; i < 16; i++) {
+      uint32_t lo = p[i] & 0xFFFFu, hi = p[i] >> 16;
+      if ((int)(lo & 0x7Fu) >= limit) lo = 0xFFFFu;
+      if ((int)(hi & 0x7Fu) >= limit) hi = 0xFFFFu;
+      p[i] = lo | (hi << 16);
+    }
   }
   uint32_t m3[5];  // min tree of depth 3 (three-input SIMD min)
 #pragma unroll
@@ -198,9 +202,10 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
   uint8_t* s_ac = smem + kStages * kTileBytes;           // constant K block of the two A tiles
   uint4* s_scratch = reinterpret_cast<uint4*>(s_ac + 2 * kAConstBytes);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_ac + 2 * kAConstBytes + kScratchBytes);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * kStages + 2 * kAccStages);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2 * kStages + 3 * kAccStages);
   const uint32_t bar_full = smem_u32(s_bar), bar_empty = smem_u32(s_bar + kStages);
   const uint32_t bar_tfull = smem_u32(s_bar + 2 * kStages), bar_tempty = smem_u32(s_bar + 2 * kStages + kAccStages);
+  const uint32_t bar_token = smem_u32(s_bar + 2 * kStages + 2 * kAccStages);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long total_tiles = (ndb + kTileN - 1) / kTileN;
@@ -217,6 +222,7 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
     for (int t = 0; t < kAccStages; t++) {
       mbar_init(bar_tfull + 8 * t, 1);   // tcgen05.commit
       mbar_init(bar_tempty + 8 * t, 4);  // one arrive per epilogue warp of the stage's group
+      mbar_init(bar_token + 8 * t, 1);   // issue-order token, passed by the previous issuer
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -285,56 +291,43 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
     // ===== epilogue: thread = TMEM lane m = queries qbase + m (low half) and qbase + 128 + m (high half)
     const int grp = warp >> 2;
     const uint32_t taddr0 = lane_base + grp * kAccCols;  // A tile 0 (queries m); + kTileN columns: A tile 1
-    uint32_t thr = 0xFFFFFFFFu;
+    uint32_t thr[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
     for (int i = grp; i < ntiles; i += kAccStages) {
       mbar_wait(bar_tfull + 8 * grp, (i / kAccStages) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint32_t a0[16], a1[16], b0[16], b1[16];
-      uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
-      const long long remain = ndb - (tile0 + i) * kTileN;
-      const bool full_tile = remain >= kTileN;
-      // columns 0-31
-      tmem_ld16(a0, taddr0);
-      tmem_ld16(a1, taddr0 + kTileN);
-      tmem_ld16(b0, taddr0 + 16);
-      tmem_ld16(b1, taddr0 + kTileN + 16);
-      tmem_wait(a0, a1);  // waits for all four loads; b0/b1 are tied to the second statement only for the compiler
-      tmem_wait(b0, b1);
-      if (full_tile) {
-        consume16<false>(a0, a1, 0, kTileN, thr, k0, k1);
-        consume16<false>(b0, b1, 16, kTileN, thr, k0, k1);
-      } else {
-        consume16<true>(a0, a1, 0, (int)remain, thr, k0, k1);
-        consume16<true>(b0, b1, 16, (int)remain, thr, k0, k1);
+      // the whole tile (64 columns x 2 A tiles) goes to 64 registers, then the stage returns to its issuer
+      uint32_t x[2][2][16];
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        tmem_ld32p(x[h][0], taddr0 + h * kTileN);
+        tmem_ld32p(x[h][1], taddr0 + h * kTileN + 32);
       }
-      // columns 32-63, then the stage goes back to its issuer: the keys are in registers
-      tmem_ld16(a0, taddr0 + 32);
-      tmem_ld16(a1, taddr0 + kTileN + 32);
-      tmem_ld16(b0, taddr0 + 48);
-      tmem_ld16(b1, taddr0 + kTileN + 48);
-      tmem_wait(a0, a1);
-      tmem_wait(b0, b1);
+      tmem_wait(x[0][0], x[0][1]);  // waits for all four loads; the second statement ties the rest for the compiler
+      tmem_wait(x[1][0], x[1][1]);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * grp);
-      if (full_tile) {
-        consume16<false>(a0, a1, 32, kTileN, thr, k0, k1);
-        consume16<false>(b0, b1, 48, kTileN, thr, k0, k1);
-      } else {
-        consume16<true>(a0, a1, 32, (int)remain, thr, k0, k1);
-        consume16<true>(b0, b1, 48, (int)remain, thr, k0, k1);
-      }
-      if (k0 != 0xFFFFFFFFu) {
-        // fold the tile's 16-bit keys (dist << 7 | row in tile) into the running 32-bit keys
-        const uint32_t tile_bits = (uint32_t)i << 6;
+      const long long remain = ndb - (tile0 + i) * kTileN;
+      const uint32_t tile_bits = (uint32_t)i << 6;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const uint32_t x0 = h ? (k0 >> 16) : (k0 & 0xFFFFu), x1 = h ? (k1 >> 16) : (k1 & 0xFFFFu);
-          top2_insert32(((x0 & 0xFF80u) << 13) | (x0 & 0x7Fu) | tile_bits, r0[h], r1[h]);
-          top2_insert32(((x1 & 0xFF80u) << 13) | (x1 & 0x7Fu) | tile_bits, r0[h], r1[h]);
+      for (int h = 0; h < 2; h++) {
+        uint32_t k0 = 0xFFFFFFFFu, k1 = 0xFFFFFFFFu;
+        if (remain >= kTileN) {
+          consume32<false>(x[h][0], kTileN, thr[h], k0, k1);
+          consume32<false>(x[h][1], kTileN, thr[h], k0, k1);
+        } else {
+          consume32<true>(x[h][0], (int)remain, thr[h], k0, k1);
+          consume32<true>(x[h][1], (int)remain, thr[h], k0, k1);
         }
-        // packed per-half threshold: the running second-best distance << 7 (a later key must be strictly closer)
-        thr = min((r1[0] >> 20) << 7, 0xFFFFu) | (min((r1[1] >> 20) << 7, 0xFFFFu) << 16);
+        if (k0 != 0xFFFFFFFFu) {
+          // fold the tile's 16-bit keys (dist << 7 | row in tile; two streams x top-2) into the running 32-bit keys
+          const uint32_t c[4] = {k0 & 0xFFFFu, k0 >> 16, k1 & 0xFFFFu, k1 >> 16};
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            top2_insert32(((c[j] & 0xFF80u) << 13) | (c[j] & 0x7Fu) | tile_bits, r0[h], r1[h]);
+          // threshold: the running second-best distance << 7 in both halves (a later key must be strictly closer)
+          thr[h] = min((r1[h] >> 20) << 7, 0xFFFFu) * 0x10001u;
+        }
       }
     }
     // groups 1.. hand their result to group 0 through shared memory
@@ -354,12 +347,17 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
       mbar_wait(bar_full + 8 * s, (i / kStages) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t b = b_base + (uint32_t)((s * kTileBytes) >> 4);
+      // Issue order = tile order: the token arrives from the issuer of tile i - 1 once most of its MMAs are
+      // queued.  (Free-running issuers interleave MMA by MMA, all three stages then complete together and sit in
+      // their hand-back latency together.)  The operand waits above are already done when the token comes.
+      if (i > 0) mbar_wait(bar_token + 8 * grp, ((i - (grp == 0 ? kAccStages : 0)) / kAccStages) & 1);
       if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < 8; ks++) {  // one k-step = two 16-byte K chunks of B, 8 TMEM columns of A
           const uint32_t adv = (uint32_t)((2 * kLbo * ks) >> 4);
           mma_i8_ts(d0, a0 + 8 * ks, b + adv, ks > 0);
           mma_i8_ts(d1, a1 + 8 * ks, b + adv, ks > 0);
+          if (ks == 6) mbar_arrive(bar_token + 8 * ((grp + 1) % kAccStages));
         }
         mma_i8_ss(d0, ac0, b + (uint32_t)((2 * kLbo * 8) >> 4));  // constant block: + 128 popc(q) + row in tile
         mma_i8_ss(d1, ac1, b + (uint32_t)((2 * kLbo * 8) >> 4));
