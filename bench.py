@@ -447,6 +447,14 @@ def main():
             "latency": extras,
             "hamming": {"metric": "hamming_matches_per_sec", "value": world * NQ * KF_PER_RANK * DPK / (ms_ham * 1e-3),
                         "unit": "256-bit pairs/s", "ms_per_query_batch": ms_ham,
+                        "kernel": "db_top2_umma_kernel (tcgen05 kind::i8, A in TMEM, accumulators in TMEM) + db_merge_kernel",
+                        "roofline": {"bound": "tensor", "unit": "TOP/s (int8)",
+                                     "achieved": NQ * KF_PER_RANK * DPK * 512 / (ms_ham * 1e-3) / 1e12,
+                                     "peak": 4500.0,
+                                     "frac": NQ * KF_PER_RANK * DPK * 512 / (ms_ham * 1e-3) / 1e12 / 4500.0,
+                                     "peak_source": "nominal dense int8 per GPU (MEASURED_PEAKS.json has no int8 figure); "
+                                                    "algorithmic ops = 2 x 256 per pair, the kernel issues 2 x 288 "
+                                                    "(constant K block); per GPU, timed with CUDA events incl. merge"},
                         "config": f"{NQ} queries x {KF_PER_RANK * DPK} descriptors per GPU shard ({KF_PER_RANK} keyframes x {DPK}), "
                                   f"top-2 + votes" + (", all_gather of 32 KB key blocks + merge" if world > 1 else "")},
         }
