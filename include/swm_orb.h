@@ -212,6 +212,46 @@ int swm_match_bow(swm_matcher* m, const swm_frame_view* f1, const swm_featvec* f
                   const swm_frame_view* f2, const swm_featvec* fv2, const uint8_t* valid2, int mode, float nnratio,
                   int check_ori, int32_t* matches, int* nmatches);
 
+/* ------------------------------------------------------------------ resident frames
+ * Frame::UndistortKeyPoints (code/src/Frame.cc:454-484), ComputeImageBounds
+ * (:486-514) and AssignFeaturesToGrid (:277-292, PosInGrid :427-442) on the device, so that the
+ * extractor's output feeds the matchers without a host round trip.  The *_resident matchers have
+ * exactly the semantics and results of their swm_frame_view forms. */
+typedef struct swm_camera {
+  float fx, fy, cx, cy;       /* mK */
+  float k1, k2, p1, p2, k3;   /* mDistCoef (k3 = 0 when the settings file has four coefficients) */
+} swm_camera;
+
+/* bounds4 = mnMinX, mnMaxX, mnMinY, mnMaxY (Frame.cc:486-514); the four corners go through the same
+ * device undistortion as the keypoints. */
+int swm_camera_bounds(int device, const swm_camera* cam, int cols, int rows, float* bounds4);
+
+typedef struct swm_frame swm_frame; /* opaque: undistorted keypoints (SoA), descriptors, grid, on one device */
+int swm_frame_create(int device, swm_frame** out);
+void swm_frame_destroy(swm_frame* f);
+const char* swm_frame_last_error(const swm_frame* f);
+int32_t swm_frame_size(const swm_frame* f);
+/* Frame `index` of the extractor's most recent batch -> resident frame, on the extractor's stream:
+ * cv::undistortPoints(K, D, P = K) semantics in double (bit-identical to OpenCV's scalar code), mvKeysUn =
+ * mvKeys when cam is NULL or k1 == 0 (:456-460), descriptor copy, grid.  Only the 4-byte keypoint count is
+ * read back. */
+int swm_frame_from_extractor(swm_frame* f, swm_orb* h, int index, const swm_camera* cam, const float* bounds4);
+/* The same from host arrays (e.g. a keyframe of the map); v's x / y are already undistorted. */
+int swm_frame_upload(swm_frame* f, const swm_frame_view* v);
+/* Reads a resident frame back (tracking needs mvKeysUn for pose optimisation); any pointer may be NULL.
+ * grid_starts: 64*48+1 entries, grid_items: up to n entries (same CSR as swm_grid_build). */
+int swm_frame_download(swm_frame* f, float* x, float* y, int32_t* octave, float* angle, uint8_t* desc,
+                       int32_t* grid_starts, int32_t* grid_items);
+
+int swm_match_init_resident(swm_matcher* m, const swm_frame* f1, const swm_frame* f2, float* prev_xy, int32_t* matches12,
+                            int window, float nnratio, int check_ori, int* nmatches);
+int swm_match_window_resident(swm_matcher* m, const swm_frame* tgt, const swm_window_query* q,
+                              const uint8_t* tgt_blocked, int th_dist, int ratio_mode, float nnratio, int check_ori,
+                              int32_t* assignment, int* nmatches);
+int swm_match_bow_resident(swm_matcher* m, const swm_frame* f1, const swm_featvec* fv1, const uint8_t* valid1,
+                           const swm_frame* f2, const swm_featvec* fv2, const uint8_t* valid2, int mode, float nnratio,
+                           int check_ori, int32_t* matches, int* nmatches);
+
 /* ------------------------------------------------------------------ place-recognition shard (config 5) */
 typedef struct swm_db swm_db; /* one GPU's shard of the keyframe-descriptor database */
 /* desc: ndesc x 32 bytes (host), kf_of_desc optional (NULL -> desc i belongs to kf i / desc_per_kf). */

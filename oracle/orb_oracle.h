@@ -141,6 +141,16 @@ int orc_search_by_bow(const orc_frame* f1, const orc_featvec* fv1, const uint8_t
  * (dist0, idx0, dist1, idx1); ties broken by lower index. */
 void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int32_t* out4);
 
+/* Frame::UndistortKeyPoints (code/src/Frame.cc:454-484): cv::undistortPoints(pts, pts, K, D, Mat(), K) on float32
+ * points.  OpenCV is a third-party dependency absent from /root/reference (the reference links the system OpenCV 3.x);
+ * the algorithm restated here is cvUndistortPointsInternal with the default criteria (5 fixed-point iterations, all
+ * arithmetic in double, float in/out).  k4,k5,k6, thin-prism and tilt terms are zero (ORB-SLAM passes 4 or 5
+ * coefficients).  cam9 = fx, fy, cx, cy, k1, k2, p1, p2, k3.  With k1 == 0 the points are copied (:456-460).  Pinned
+ * against cv2.undistortPoints in tests/test_oracle_cv2.py. */
+void orc_undistort_points(const float* xy, int n, const float* cam9, float* out_xy);
+/* Frame::ComputeImageBounds (Frame.cc:486-514): out4 = mnMinX, mnMaxX, mnMinY, mnMaxY. */
+void orc_image_bounds(int cols, int rows, const float* cam9, float* out4);
+
 /* ---- timing helpers for bench.py's cpu_baseline (run entirely on the CPU) ---- */
 double orc_time_extract(orc_extractor* e, const uint8_t* imgs, int n_imgs, int w, int h, int iters);
 

@@ -330,4 +330,53 @@ void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* db, int64_t nd
   }
 }
 
+// cv::undistortPoints with P = K, R = I (see header).  One statement per OpenCV expression, evaluated left to right in
+// double; compiled with -ffp-contract=off so that no multiply-add is fused.
+static void undistort_one(float px, float py, const float* cam9, float* ox, float* oy) {
+  const double fx = cam9[0], fy = cam9[1], cx = cam9[2], cy = cam9[3];
+  const double k1 = cam9[4], k2 = cam9[5], p1 = cam9[6], p2 = cam9[7], k3 = cam9[8];
+  const double ifx = 1. / fx, ify = 1. / fy;
+  const double u = px, v = py;
+  double x = (u - cx) * ifx, y = (v - cy) * ify;
+  const double x0 = x, y0 = y;
+  for (int j = 0; j < 5; j++) {
+    const double r2 = x * x + y * y;
+    const double icdist = 1. / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);  // numerator 1 + ((k6 r2 + k5) r2 + k4) r2 = 1
+    if (icdist < 0) {
+      x = (u - cx) * ifx;
+      y = (v - cy) * ify;
+      break;
+    }
+    const double dx = 2 * p1 * x * y + p2 * (r2 + 2 * x * x);
+    const double dy = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+    x = (x0 - dx) * icdist;
+    y = (y0 - dy) * icdist;
+  }
+  // new camera matrix = K: xx = fx x + 0 y + cx, ww = 1 / (0 x + 0 y + 1)
+  *ox = (float)(fx * x + cx);
+  *oy = (float)(fy * y + cy);
+}
+
+void orc_undistort_points(const float* xy, int n, const float* cam9, float* out_xy) {
+  if (cam9[4] == 0.0f) {
+    for (int i = 0; i < 2 * n; i++) out_xy[i] = xy[i];
+    return;
+  }
+  for (int i = 0; i < n; i++) undistort_one(xy[2 * i], xy[2 * i + 1], cam9, &out_xy[2 * i], &out_xy[2 * i + 1]);
+}
+
+void orc_image_bounds(int cols, int rows, const float* cam9, float* out4) {
+  if (cam9[4] == 0.0f) {
+    out4[0] = 0.0f; out4[1] = (float)cols; out4[2] = 0.0f; out4[3] = (float)rows;
+    return;
+  }
+  const float c[8] = {0.f, 0.f, (float)cols, 0.f, 0.f, (float)rows, (float)cols, (float)rows};
+  float m[8];
+  orc_undistort_points(c, 4, cam9, m);
+  out4[0] = std::min(m[0], m[4]);  // mnMinX = min(mat(0,0), mat(2,0))
+  out4[1] = std::max(m[2], m[6]);  // mnMaxX = max(mat(1,0), mat(3,0))
+  out4[2] = std::min(m[1], m[3]);  // mnMinY = min(mat(0,1), mat(1,1))
+  out4[3] = std::max(m[5], m[7]);  // mnMaxY = max(mat(2,1), mat(3,1))
+}
+
 }  // extern "C"

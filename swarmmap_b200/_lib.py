@@ -43,6 +43,11 @@ class WindowQuery(C.Structure):
                 ("valid", C.c_void_p), ("angle", C.c_void_p), ("blocks", C.c_void_p)]
 
 
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("k1", C.c_float), ("k2", C.c_float), ("p1", C.c_float), ("p2", C.c_float), ("k3", C.c_float)]
+
+
 class FeatVec(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("node_ids", C.c_void_p), ("offsets", C.c_void_p), ("feats", C.c_void_p)]
 
@@ -78,6 +83,17 @@ SYMBOLS = [
     ("swm_match_init", _i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp]),
     ("swm_match_window", _i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp]),
     ("swm_match_bow", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp]),
+    ("swm_camera_bounds", _i, [_i, _vp, _i, _i, _vp]),
+    ("swm_frame_create", _i, [_i, _vp]),
+    ("swm_frame_destroy", None, [_vp]),
+    ("swm_frame_last_error", C.c_char_p, [_vp]),
+    ("swm_frame_size", C.c_int32, [_vp]),
+    ("swm_frame_from_extractor", _i, [_vp, _vp, _i, _vp, _vp]),
+    ("swm_frame_upload", _i, [_vp, _vp]),
+    ("swm_frame_download", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("swm_match_init_resident", _i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp]),
+    ("swm_match_window_resident", _i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp]),
+    ("swm_match_bow_resident", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp]),
     ("swm_db_create", _i, [_i, _vp, _i64, C.c_int32, _i64, _vp]),
     ("swm_db_create_device", _i, [_i, _vp, _i64, C.c_int32, _i64, _vp]),
     ("swm_db_destroy", None, [_vp]),

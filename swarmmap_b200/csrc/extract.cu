@@ -831,6 +831,7 @@ struct swm_orb {
   int last_stride = 0;
   long long last_frame_stride = 0;
   swm_keypoint* last_kps = nullptr;
+  cudaStream_t last_stream = nullptr;
   uint8_t* last_desc = nullptr;
   int32_t* last_n = nullptr;
   int last_cap = 0;
@@ -1187,6 +1188,7 @@ int swm_orb_extract_batch_device(swm_orb* h, const uint8_t* d_imgs, int batch, i
   h->last_img = d_imgs; h->last_stride = stride; h->last_frame_stride = (long long)frame_stride;
   h->last_kps = d_kps; h->last_desc = d_desc; h->last_n = d_n; h->last_cap = cap;
   h->last_batch = batch;
+  h->last_stream = st;
   return enqueue(h, 15, d_imgs, batch, stride, (long long)frame_stride, d_kps, d_desc, cap, d_n, st);
 }
 
@@ -1396,3 +1398,19 @@ int swm_orb_debug_points(swm_orb* h, int frame, int level, int which, int32_t* x
 }
 
 }  // extern "C"
+
+namespace swm {
+int orb_device_view(swm_orb* h, OrbDeviceView* out) {
+  if (!h || !out) return SWM_E_INVALID;
+  if (!h->last_kps || h->last_batch < 1) { h->err = "no extracted batch is resident"; return SWM_E_STATE; }
+  out->kps = h->last_kps;
+  out->desc = h->last_desc;
+  out->n = h->last_n;
+  out->cap = h->last_cap;
+  out->batch = h->last_batch;
+  out->device = h->device;
+  out->stream = h->last_stream;
+  return SWM_OK;
+}
+}  // namespace swm
+

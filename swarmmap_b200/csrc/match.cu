@@ -141,6 +141,86 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int32_t* _
 // Candidate rows by window query (Frame::GetFeaturesInArea, Frame.cc:377-430), one warp per
 // source.  pass 0 counts, pass 1 writes (index, level<<16 | distance) in the reference's order.
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// Resident frames: Frame::UndistortKeyPoints (Frame.cc:454-484) + SoA split of the
+// extractor's cv::KeyPoint records, so that extract -> grid -> match never leaves the GPU.
+// cv::undistortPoints(pts, pts, K, D, Mat(), K): 5 fixed-point iterations in double (OpenCV's default criteria),
+// float in/out; every operation is an explicit round-to-nearest intrinsic so that nothing is contracted into an
+// FMA and the result is bit-identical to OpenCV's scalar code (and to oracle/orc_undistort_points).
+// ---------------------------------------------------------------------------------------------
+struct CameraDev {
+  float fx, fy, cx, cy, k1, k2, p1, p2, k3;
+  int distorted;  // mDistCoef.at<float>(0) != 0
+};
+
+__device__ __forceinline__ void undistort_point(const CameraDev& c, float px, float py, float* ox, float* oy) {
+  const double fx = c.fx, fy = c.fy, cx = c.cx, cy = c.cy, k1 = c.k1, k2 = c.k2, p1 = c.p1, p2 = c.p2, k3 = c.k3;
+  const double ifx = __ddiv_rn(1.0, fx), ify = __ddiv_rn(1.0, fy);
+  const double u = px, v = py;
+  double x = __dmul_rn(__dsub_rn(u, cx), ifx), y = __dmul_rn(__dsub_rn(v, cy), ify);
+  const double x0 = x, y0 = y;
+  for (int j = 0; j < 5; j++) {
+    const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+    const double poly = __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k3, r2), k2), r2), k1), r2);
+    const double icdist = __ddiv_rn(1.0, __dadd_rn(1.0, poly));
+    if (icdist < 0) {
+      x = __dmul_rn(__dsub_rn(u, cx), ifx);
+      y = __dmul_rn(__dsub_rn(v, cy), ify);
+      break;
+    }
+    // deltaX = 2 p1 x y + p2 (r2 + 2 x x);  deltaY = p1 (r2 + 2 y y) + 2 p2 x y   (left to right)
+    const double dx = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, p1), x), y),
+                                __dmul_rn(p2, __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x))));
+    const double dy = __dadd_rn(__dmul_rn(p1, __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))),
+                                __dmul_rn(__dmul_rn(__dmul_rn(2.0, p2), x), y));
+    x = __dmul_rn(__dsub_rn(x0, dx), icdist);
+    y = __dmul_rn(__dsub_rn(y0, dy), icdist);
+  }
+  *ox = (float)__dadd_rn(__dmul_rn(fx, x), cx);
+  *oy = (float)__dadd_rn(__dmul_rn(fy, y), cy);
+}
+
+__global__ void __launch_bounds__(256) frame_from_kps_kernel(const swm_keypoint* __restrict__ kps,
+                                                             const uint4* __restrict__ desc_in, int n, CameraDev cam,
+                                                             float* __restrict__ x, float* __restrict__ y,
+                                                             int32_t* __restrict__ octave, float* __restrict__ angle,
+                                                             uint4* __restrict__ desc_out) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const swm_keypoint kp = kps[i];
+  float ux = kp.x, uy = kp.y;
+  if (cam.distorted) undistort_point(cam, kp.x, kp.y, &ux, &uy);
+  x[i] = ux;
+  y[i] = uy;
+  octave[i] = kp.octave;
+  angle[i] = kp.angle;
+  desc_out[2 * i] = desc_in[2 * i];
+  desc_out[2 * i + 1] = desc_in[2 * i + 1];
+}
+
+__global__ void undistort_points_kernel(const float* __restrict__ in_xy, int n, CameraDev cam, float* __restrict__ out_xy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float ux = in_xy[2 * i], uy = in_xy[2 * i + 1];
+  if (cam.distorted) undistort_point(cam, ux, uy, &ux, &uy);
+  out_xy[2 * i] = ux;
+  out_xy[2 * i + 1] = uy;
+}
+
+// SearchForInitialization's source rows (ORBmatcher.cc:390-396): F1 keypoints of octave 0, window centre =
+// vbPrevMatched, levels (0, 0).
+__global__ void init_query_kernel(const int32_t* __restrict__ octave1, const float* __restrict__ prev_xy, int n1,
+                                  float window, float* __restrict__ u, float* __restrict__ v, float* __restrict__ rad,
+                                  int32_t* __restrict__ lv, uint8_t* __restrict__ valid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n1) return;
+  u[i] = prev_xy[2 * i];
+  v[i] = prev_xy[2 * i + 1];
+  rad[i] = window;
+  lv[i] = octave1[i];
+  valid[i] = octave1[i] > 0 ? 0 : 1;
+}
+
 struct WindowDev {
   int m;
   const uint4* desc;
@@ -848,6 +928,7 @@ struct swm_matcher {
   // frame uploads (two frames), query uploads, rows, state
   DevBuf f[2][6];  // x, y, octave, angle, desc, (grid starts+items+cell_of)
   DevBuf q[10];
+  DevBuf iq[5];    // SearchForInitialization's source rows, built on the device (owned)
   DevBuf rows[5];  // row_count, row_start, cand_idx, cand_val, row_src
   DevBuf state[7]; // blocked, matched_dist, matches21, out, ev_bin, ev_tgt, nmatches/prev
   // upload arena: every host array of a call is packed into one pinned buffer and sent with ONE copy
@@ -861,14 +942,34 @@ struct swm_matcher {
     arena_cap = arena_used = 0;
     for (auto& a : f) for (auto& b : a) b.release();
     for (auto& b : q) b.release();
+    for (auto& b : iq) b.release();
     for (auto& b : rows) b.release();
     for (auto& b : state) b.release();
   }
 };
 
+// A frame's features resident on the device: undistorted keypoints (SoA), descriptors, grid CSR.
+struct swm_frame {
+  int device = 0;
+  std::string err;
+  int n = 0;
+  DevBuf b[6];  // x, y, octave, angle, desc, grid (starts | items | cell_of)
+  FrameDev dev{};
+  cudaStream_t stream = nullptr;  // uploads; frames built from the extractor use the extractor's stream
+  cudaEvent_t ready = nullptr;    // recorded after the last kernel that writes the frame
+};
+
 namespace {
 
 thread_local std::string g_match_create_error;
+thread_local std::string g_frame_create_error;
+
+// A matcher operand: host arrays (uploaded per call) or a resident frame.
+struct FrameSrc {
+  const swm_frame_view* host;
+  const swm_frame* dev;
+  int n() const { return dev ? dev->n : host->n; }
+};
 
 // SWM_MATCH_PROFILE=1: print host-side phase times of each matcher call to stderr (debug aid).
 struct PhaseTimer {
@@ -971,6 +1072,76 @@ int build_grid(swm_matcher* m, int slot, FrameDev* d) {
   MCK(m, cudaGetLastError());
   d->starts = starts;
   d->items = items;
+  return SWM_OK;
+}
+
+// Operand -> device views.  Host arrays are packed into the arena (valid after arena_flush); a resident frame is
+// used in place once its producer's event has been waited for on the matcher stream.
+int acquire_frame(swm_matcher* m, int slot, const FrameSrc& f, FrameDev* out) {
+  if (!f.dev) return upload_frame(m, slot, f.host, out);
+  if (f.dev->device != m->device) { m->err = "resident frame lives on another device"; return SWM_E_INVALID; }
+  MCK(m, cudaStreamWaitEvent(m->stream, f.dev->ready, 0));
+  *out = f.dev->dev;
+  return SWM_OK;
+}
+int acquire_grid(swm_matcher* m, int slot, const FrameSrc& f, FrameDev* d) {
+  if (f.dev) return SWM_OK;  // built with the frame
+  return build_grid(m, slot, d);
+}
+size_t src_bytes(const FrameSrc& f) { return f.dev ? 0 : frame_bytes(f.host); }
+
+CameraDev camera_dev(const swm_camera* cam) {
+  CameraDev c{};
+  if (cam) {
+    c.fx = cam->fx; c.fy = cam->fy; c.cx = cam->cx; c.cy = cam->cy;
+    c.k1 = cam->k1; c.k2 = cam->k2; c.p1 = cam->p1; c.p2 = cam->p2; c.k3 = cam->k3;
+    c.distorted = cam->k1 != 0.0f;  // Frame.cc:456
+  }
+  return c;
+}
+
+#define FCK(f, call)                                   \
+  do {                                                 \
+    cudaError_t e_ = (call);                           \
+    if (e_ != cudaSuccess) {                           \
+      (f)->err = cuda_err(#call, e_);                  \
+      return SWM_E_CUDA;                               \
+    }                                                  \
+  } while (0)
+
+// Allocates the SoA arrays + grid for n keypoints and points f->dev at them.
+int frame_reserve(swm_frame* f, int n, const float* bounds4) {
+  const size_t nn = (size_t)(n > 0 ? n : 1);
+  FCK(f, f->b[0].ensure(nn * 4));
+  FCK(f, f->b[1].ensure(nn * 4));
+  FCK(f, f->b[2].ensure(nn * 4));
+  FCK(f, f->b[3].ensure(nn * 4));
+  FCK(f, f->b[4].ensure(nn * 32));
+  FCK(f, f->b[5].ensure(((size_t)kCells + 1 + 2 * nn + 8) * 4));
+  FrameDev d{};
+  d.n = n;
+  d.x = f->b[0].as<float>();
+  d.y = f->b[1].as<float>();
+  d.octave = f->b[2].as<int32_t>();
+  d.angle = f->b[3].as<float>();
+  d.desc = f->b[4].as<uint4>();
+  d.min_x = bounds4[0]; d.max_x = bounds4[1]; d.min_y = bounds4[2]; d.max_y = bounds4[3];
+  d.inv_w = (float)kGridCols / (float)(d.max_x - d.min_x);  // Frame.cc:259-260
+  d.inv_h = (float)kGridRows / (float)(d.max_y - d.min_y);
+  d.starts = f->b[5].as<int32_t>();
+  d.items = f->b[5].as<int32_t>() + kCells + 1;
+  f->dev = d;
+  f->n = n;
+  return SWM_OK;
+}
+
+int frame_grid(swm_frame* f, cudaStream_t st) {
+  int32_t* starts = f->b[5].as<int32_t>();
+  int32_t* items = starts + kCells + 1;
+  int32_t* cell_of = items + (f->n > 0 ? f->n : 1) + 4;
+  grid_build_kernel<<<1, 1024, 0, st>>>(f->dev, starts, items, cell_of);
+  FCK(f, cudaGetLastError());
+  FCK(f, cudaEventRecord(f->ready, st));
   return SWM_OK;
 }
 
@@ -1113,47 +1284,42 @@ int swm_grid_build(swm_matcher* m, const swm_frame_view* f, int32_t* starts, int
   return SWM_OK;
 }
 
-int swm_match_init(swm_matcher* m, const swm_frame_view* f1, const swm_frame_view* f2, float* prev_xy,
-                   int32_t* matches12, int window, float nnratio, int check_ori, int* nmatches) {
-  if (!m) return SWM_E_INVALID;
-  if (!frame_ok(f1) || !frame_ok(f2) || !prev_xy || !matches12 || !nmatches) { m->err = "bad argument"; return SWM_E_INVALID; }
+}  // extern "C"
+
+namespace {
+
+int match_init_impl(swm_matcher* m, const FrameSrc& f1, const FrameSrc& f2, float* prev_xy, int32_t* matches12,
+                    int window, float nnratio, int check_ori, int* nmatches) {
   *nmatches = 0;
-  const int n1 = f1->n, n2 = f2->n;
+  const int n1 = f1.n(), n2 = f2.n();
   for (int i = 0; i < n1; i++) matches12[i] = -1;
   if (n1 == 0 || n2 == 0) return SWM_OK;
   MCK(m, cudaSetDevice(m->device));
   FrameDev d1, d2;
   int rc;
-  if ((rc = arena_begin(m, frame_bytes(f1) + frame_bytes(f2) + (size_t)n1 * 32 + 8 * 256))) return rc;
-  if ((rc = upload_frame(m, 0, f1, &d1))) return rc;
-  if ((rc = upload_frame(m, 1, f2, &d2))) return rc;
-  // sources = F1 keypoints at octave 0 (:390-392), window centre = vbPrevMatched, levels (0,0) (:394-396)
-  std::vector<float> u(n1), v(n1), rad(n1, (float)window);
-  std::vector<int32_t> lv(n1, 0);
-  std::vector<uint8_t> valid(n1);
-  for (int i = 0; i < n1; i++) {
-    u[i] = prev_xy[2 * i];
-    v[i] = prev_xy[2 * i + 1];
-    valid[i] = f1->octave[i] > 0 ? 0 : 1;
-    lv[i] = f1->octave[i];
-  }
-  if ((rc = upload(m, m->q[0], u.data(), (size_t)n1 * 4))) return rc;
-  if ((rc = upload(m, m->q[1], v.data(), (size_t)n1 * 4))) return rc;
-  if ((rc = upload(m, m->q[2], rad.data(), (size_t)n1 * 4))) return rc;
-  if ((rc = upload(m, m->q[3], lv.data(), (size_t)n1 * 4))) return rc;
-  if ((rc = upload(m, m->q[4], valid.data(), (size_t)n1))) return rc;
+  if ((rc = arena_begin(m, src_bytes(f1) + src_bytes(f2) + (size_t)n1 * 8 + 8 * 256))) return rc;
+  if ((rc = acquire_frame(m, 0, f1, &d1))) return rc;
+  if ((rc = acquire_frame(m, 1, f2, &d2))) return rc;
   if ((rc = upload(m, m->q[5], prev_xy, (size_t)n1 * 8))) return rc;
   if ((rc = arena_flush(m))) return rc;
-  if ((rc = build_grid(m, 1, &d2))) return rc;
+  if ((rc = acquire_grid(m, 1, f2, &d2))) return rc;
+  // sources = F1 keypoints at octave 0 (:390-392), window centre = vbPrevMatched, levels (0,0) (:394-396)
+  for (int i = 0; i < 4; i++) MCK(m, m->iq[i].ensure((size_t)n1 * 4));
+  MCK(m, m->iq[4].ensure((size_t)n1));
+  init_query_kernel<<<(n1 + 255) / 256, 256, 0, m->stream>>>(d1.octave, m->q[5].as<float>(), n1, (float)window,
+                                                             m->iq[0].as<float>(), m->iq[1].as<float>(),
+                                                             m->iq[2].as<float>(), m->iq[3].as<int32_t>(),
+                                                             m->iq[4].as<uint8_t>());
+  MCK(m, cudaGetLastError());
   WindowDev q;
   q.m = n1;
   q.desc = d1.desc;
-  q.u = m->q[0].as<float>();
-  q.v = m->q[1].as<float>();
-  q.radius = m->q[2].as<float>();
-  q.min_level = m->q[3].as<int32_t>();
-  q.max_level = m->q[3].as<int32_t>();
-  q.valid = m->q[4].as<uint8_t>();
+  q.u = m->iq[0].as<float>();
+  q.v = m->iq[1].as<float>();
+  q.radius = m->iq[2].as<float>();
+  q.min_level = m->iq[3].as<int32_t>();
+  q.max_level = m->iq[3].as<int32_t>();
+  q.valid = m->iq[4].as<uint8_t>();
   int total = 0;
   if ((rc = build_window_rows(m, d2, q, &total))) return rc;
   // state
@@ -1197,25 +1363,23 @@ int swm_match_init(swm_matcher* m, const swm_frame_view* f1, const swm_frame_vie
   return SWM_OK;
 }
 
-int swm_match_window(swm_matcher* m, const swm_frame_view* tgt, const swm_window_query* wq,
-                     const uint8_t* tgt_blocked, int th_dist, int ratio_mode, float nnratio, int check_ori,
-                     int32_t* assignment, int* nmatches) {
-  if (!m) return SWM_E_INVALID;
-  if (!frame_ok(tgt) || !wq || wq->m < 0 || !assignment || !nmatches ||
-      (wq->m > 0 && (!wq->desc || !wq->u || !wq->v || !wq->radius || !wq->min_level || !wq->max_level || !wq->valid ||
-                     !wq->blocks || (check_ori && !wq->angle)))) {
-    m->err = "bad argument";
-    return SWM_E_INVALID;
-  }
+bool window_query_ok(const swm_window_query* wq, int check_ori) {
+  return wq && wq->m >= 0 &&
+         (wq->m == 0 || (wq->desc && wq->u && wq->v && wq->radius && wq->min_level && wq->max_level && wq->valid &&
+                         wq->blocks && (!check_ori || wq->angle)));
+}
+
+int match_window_impl(swm_matcher* m, const FrameSrc& tgt, const swm_window_query* wq, const uint8_t* tgt_blocked,
+                      int th_dist, int ratio_mode, float nnratio, int check_ori, int32_t* assignment, int* nmatches) {
   *nmatches = 0;
-  const int M = wq->m, n2 = tgt->n;
+  const int M = wq->m, n2 = tgt.n();
   if (M == 0 || n2 == 0) return SWM_OK;
   MCK(m, cudaSetDevice(m->device));
   PhaseTimer pt(m->stream);
   FrameDev d2;
   int rc;
-  if ((rc = arena_begin(m, frame_bytes(tgt) + (size_t)M * 64 + (size_t)n2 * 8 + 16 * 256))) return rc;
-  if ((rc = upload_frame(m, 1, tgt, &d2))) return rc;
+  if ((rc = arena_begin(m, src_bytes(tgt) + (size_t)M * 64 + (size_t)n2 * 8 + 16 * 256))) return rc;
+  if ((rc = acquire_frame(m, 1, tgt, &d2))) return rc;
   if ((rc = upload(m, m->q[0], wq->u, (size_t)M * 4))) return rc;
   if ((rc = upload(m, m->q[1], wq->v, (size_t)M * 4))) return rc;
   if ((rc = upload(m, m->q[2], wq->radius, (size_t)M * 4))) return rc;
@@ -1232,7 +1396,7 @@ int swm_match_window(swm_matcher* m, const swm_frame_view* tgt, const swm_window
   if ((rc = upload(m, m->state[3], assignment, (size_t)n2 * 4))) return rc;
   if ((rc = arena_flush(m))) return rc;
   pt.mark("upload (1 copy)");
-  if ((rc = build_grid(m, 1, &d2))) return rc;
+  if ((rc = acquire_grid(m, 1, tgt, &d2))) return rc;
   WindowDev q;
   q.m = M;
   q.desc = m->q[7].as<uint4>();
@@ -1285,17 +1449,11 @@ int swm_match_window(swm_matcher* m, const swm_frame_view* tgt, const swm_window
   return SWM_OK;
 }
 
-int swm_match_bow(swm_matcher* m, const swm_frame_view* f1, const swm_featvec* fv1, const uint8_t* valid1,
-                  const swm_frame_view* f2, const swm_featvec* fv2, const uint8_t* valid2, int mode, float nnratio,
-                  int check_ori, int32_t* matches, int* nmatches) {
-  if (!m) return SWM_E_INVALID;
-  if (!frame_ok(f1) || !frame_ok(f2) || !fv1 || !fv2 || !valid1 || (mode == 1 && !valid2) || !matches || !nmatches ||
-      (mode != 0 && mode != 1)) {
-    m->err = "bad argument";
-    return SWM_E_INVALID;
-  }
+int match_bow_impl(swm_matcher* m, const FrameSrc& f1, const swm_featvec* fv1, const uint8_t* valid1, const FrameSrc& f2,
+                   const swm_featvec* fv2, const uint8_t* valid2, int mode, float nnratio, int check_ori, int32_t* matches,
+                   int* nmatches) {
   *nmatches = 0;
-  const int n1 = f1->n, n2 = f2->n;
+  const int n1 = f1.n(), n2 = f2.n();
   const int n_out = mode == 0 ? n2 : n1;
   for (int i = 0; i < n_out; i++) matches[i] = -1;
   if (n1 == 0 || n2 == 0) return SWM_OK;
@@ -1330,9 +1488,9 @@ int swm_match_bow(swm_matcher* m, const swm_frame_view* f1, const swm_featvec* f
   MCK(m, cudaSetDevice(m->device));
   FrameDev d1, d2;
   int rc;
-  if ((rc = arena_begin(m, frame_bytes(f1) + frame_bytes(f2) + (size_t)R * 8 + cand.size() * 4 + (size_t)n2 + 8 * 256))) return rc;
-  if ((rc = upload_frame(m, 0, f1, &d1))) return rc;
-  if ((rc = upload_frame(m, 1, f2, &d2))) return rc;
+  if ((rc = arena_begin(m, src_bytes(f1) + src_bytes(f2) + (size_t)R * 8 + cand.size() * 4 + (size_t)n2 + 8 * 256))) return rc;
+  if ((rc = acquire_frame(m, 0, f1, &d1))) return rc;
+  if ((rc = acquire_frame(m, 1, f2, &d2))) return rc;
   if ((rc = upload(m, m->rows[4], row_src.data(), (size_t)R * 4))) return rc;
   if ((rc = upload(m, m->rows[1], row_start.data(), (size_t)(R + 1) * 4))) return rc;
   if ((rc = upload(m, m->rows[2], cand.data(), cand.size() * 4))) return rc;
@@ -1374,6 +1532,207 @@ int swm_match_bow(swm_matcher* m, const swm_frame_view* f1, const swm_featvec* f
   MCK(m, cudaMemcpyAsync(matches, ra.out, (size_t)n_out * 4, cudaMemcpyDeviceToHost, m->stream));
   MCK(m, cudaMemcpyAsync(nmatches, ra.nmatches, 4, cudaMemcpyDeviceToHost, m->stream));
   MCK(m, cudaStreamSynchronize(m->stream));
+  return SWM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int swm_match_init(swm_matcher* m, const swm_frame_view* f1, const swm_frame_view* f2, float* prev_xy,
+                   int32_t* matches12, int window, float nnratio, int check_ori, int* nmatches) {
+  if (!m) return SWM_E_INVALID;
+  if (!frame_ok(f1) || !frame_ok(f2) || !prev_xy || !matches12 || !nmatches) { m->err = "bad argument"; return SWM_E_INVALID; }
+  return match_init_impl(m, FrameSrc{f1, nullptr}, FrameSrc{f2, nullptr}, prev_xy, matches12, window, nnratio, check_ori,
+                         nmatches);
+}
+
+int swm_match_init_resident(swm_matcher* m, const swm_frame* f1, const swm_frame* f2, float* prev_xy, int32_t* matches12,
+                            int window, float nnratio, int check_ori, int* nmatches) {
+  if (!m) return SWM_E_INVALID;
+  if (!f1 || !f2 || !prev_xy || !matches12 || !nmatches) { m->err = "bad argument"; return SWM_E_INVALID; }
+  return match_init_impl(m, FrameSrc{nullptr, f1}, FrameSrc{nullptr, f2}, prev_xy, matches12, window, nnratio, check_ori,
+                         nmatches);
+}
+
+int swm_match_window(swm_matcher* m, const swm_frame_view* tgt, const swm_window_query* wq,
+                     const uint8_t* tgt_blocked, int th_dist, int ratio_mode, float nnratio, int check_ori,
+                     int32_t* assignment, int* nmatches) {
+  if (!m) return SWM_E_INVALID;
+  if (!frame_ok(tgt) || !window_query_ok(wq, check_ori) || !assignment || !nmatches) {
+    m->err = "bad argument";
+    return SWM_E_INVALID;
+  }
+  return match_window_impl(m, FrameSrc{tgt, nullptr}, wq, tgt_blocked, th_dist, ratio_mode, nnratio, check_ori, assignment,
+                           nmatches);
+}
+
+int swm_match_window_resident(swm_matcher* m, const swm_frame* tgt, const swm_window_query* wq,
+                              const uint8_t* tgt_blocked, int th_dist, int ratio_mode, float nnratio, int check_ori,
+                              int32_t* assignment, int* nmatches) {
+  if (!m) return SWM_E_INVALID;
+  if (!tgt || !window_query_ok(wq, check_ori) || !assignment || !nmatches) {
+    m->err = "bad argument";
+    return SWM_E_INVALID;
+  }
+  return match_window_impl(m, FrameSrc{nullptr, tgt}, wq, tgt_blocked, th_dist, ratio_mode, nnratio, check_ori, assignment,
+                           nmatches);
+}
+
+int swm_match_bow(swm_matcher* m, const swm_frame_view* f1, const swm_featvec* fv1, const uint8_t* valid1,
+                  const swm_frame_view* f2, const swm_featvec* fv2, const uint8_t* valid2, int mode, float nnratio,
+                  int check_ori, int32_t* matches, int* nmatches) {
+  if (!m) return SWM_E_INVALID;
+  if (!frame_ok(f1) || !frame_ok(f2) || !fv1 || !fv2 || !valid1 || (mode == 1 && !valid2) || !matches || !nmatches ||
+      (mode != 0 && mode != 1)) {
+    m->err = "bad argument";
+    return SWM_E_INVALID;
+  }
+  return match_bow_impl(m, FrameSrc{f1, nullptr}, fv1, valid1, FrameSrc{f2, nullptr}, fv2, valid2, mode, nnratio, check_ori,
+                        matches, nmatches);
+}
+
+int swm_match_bow_resident(swm_matcher* m, const swm_frame* f1, const swm_featvec* fv1, const uint8_t* valid1,
+                           const swm_frame* f2, const swm_featvec* fv2, const uint8_t* valid2, int mode, float nnratio,
+                           int check_ori, int32_t* matches, int* nmatches) {
+  if (!m) return SWM_E_INVALID;
+  if (!f1 || !f2 || !fv1 || !fv2 || !valid1 || (mode == 1 && !valid2) || !matches || !nmatches ||
+      (mode != 0 && mode != 1)) {
+    m->err = "bad argument";
+    return SWM_E_INVALID;
+  }
+  return match_bow_impl(m, FrameSrc{nullptr, f1}, fv1, valid1, FrameSrc{nullptr, f2}, fv2, valid2, mode, nnratio, check_ori,
+                        matches, nmatches);
+}
+
+// ------------------------------------------------------------------------------ resident frames
+int swm_frame_create(int device, swm_frame** out) {
+  if (!out) return SWM_E_INVALID;
+  *out = nullptr;
+  std::string err;
+  int rc = check_device(device, &err);
+  if (rc != SWM_OK) { g_frame_create_error = err; return rc; }
+  swm_frame* f = new swm_frame();
+  f->device = device;
+  if (cudaStreamCreateWithFlags(&f->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&f->ready, cudaEventDisableTiming) != cudaSuccess) {
+    g_frame_create_error = "cudaStreamCreate / cudaEventCreate failed";
+    delete f;
+    return SWM_E_CUDA;
+  }
+  *out = f;
+  return SWM_OK;
+}
+
+void swm_frame_destroy(swm_frame* f) {
+  if (!f) return;
+  cudaSetDevice(f->device);
+  if (f->ready) cudaEventSynchronize(f->ready);
+  for (auto& b : f->b) b.release();
+  if (f->ready) cudaEventDestroy(f->ready);
+  if (f->stream) cudaStreamDestroy(f->stream);
+  delete f;
+}
+
+const char* swm_frame_last_error(const swm_frame* f) { return f ? f->err.c_str() : g_frame_create_error.c_str(); }
+
+int32_t swm_frame_size(const swm_frame* f) { return f ? f->n : 0; }
+
+int swm_camera_bounds(int device, const swm_camera* cam, int cols, int rows, float* bounds4) {
+  if (!cam || !bounds4 || cols <= 0 || rows <= 0) return SWM_E_INVALID;
+  if (cam->k1 == 0.0f) {  // Frame.cc:507-513
+    bounds4[0] = 0.0f; bounds4[1] = (float)cols; bounds4[2] = 0.0f; bounds4[3] = (float)rows;
+    return SWM_OK;
+  }
+  std::string err;
+  int rc = check_device(device, &err);
+  if (rc != SWM_OK) return rc;
+  if (cudaSetDevice(device) != cudaSuccess) return SWM_E_CUDA;
+  const float corners[8] = {0.f, 0.f, (float)cols, 0.f, 0.f, (float)rows, (float)cols, (float)rows};  // Frame.cc:490-494
+  float* d = nullptr;
+  if (cudaMalloc(&d, 64) != cudaSuccess) return SWM_E_CUDA;
+  float m[8];
+  bool ok = cudaMemcpy(d, corners, 32, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (ok) {
+    undistort_points_kernel<<<1, 32>>>(d, 4, camera_dev(cam), d + 8);
+    ok = cudaMemcpy(m, d + 8, 32, cudaMemcpyDeviceToHost) == cudaSuccess;
+  }
+  cudaFree(d);
+  if (!ok) return SWM_E_CUDA;
+  bounds4[0] = std::min(m[0], m[4]);  // mnMinX = min(mat(0,0), mat(2,0))   Frame.cc:501-504
+  bounds4[1] = std::max(m[2], m[6]);
+  bounds4[2] = std::min(m[1], m[3]);
+  bounds4[3] = std::max(m[5], m[7]);
+  return SWM_OK;
+}
+
+int swm_frame_from_extractor(swm_frame* f, swm_orb* h, int index, const swm_camera* cam, const float* bounds4) {
+  if (!f) return SWM_E_INVALID;
+  if (!h || !bounds4 || !(bounds4[1] > bounds4[0]) || !(bounds4[3] > bounds4[2])) { f->err = "bad argument"; return SWM_E_INVALID; }
+  OrbDeviceView v;
+  int rc = orb_device_view(h, &v);
+  if (rc != SWM_OK) { f->err = "the extractor holds no resident batch"; return rc; }
+  if (index < 0 || index >= v.batch) { f->err = "frame index outside the extractor's last batch"; return SWM_E_INVALID; }
+  if (v.device != f->device) { f->err = "extractor and frame live on different devices"; return SWM_E_INVALID; }
+  FCK(f, cudaSetDevice(f->device));
+  // the keypoint count is the only thing read back: it sizes the frame's arrays and later kernel grids
+  int n = 0;
+  FCK(f, cudaMemcpyAsync(&n, v.n + index, 4, cudaMemcpyDeviceToHost, v.stream));
+  FCK(f, cudaStreamSynchronize(v.stream));
+  if (n > v.cap) n = v.cap;
+  if ((rc = frame_reserve(f, n, bounds4))) return rc;
+  if (n > 0) {
+    frame_from_kps_kernel<<<(n + 255) / 256, 256, 0, v.stream>>>(
+        v.kps + (size_t)index * v.cap, reinterpret_cast<const uint4*>(v.desc + (size_t)index * v.cap * 32), n,
+        camera_dev(cam), f->b[0].as<float>(), f->b[1].as<float>(), f->b[2].as<int32_t>(), f->b[3].as<float>(),
+        f->b[4].as<uint4>());
+    FCK(f, cudaGetLastError());
+  }
+  return frame_grid(f, v.stream);
+}
+
+int swm_frame_upload(swm_frame* f, const swm_frame_view* v) {
+  if (!f) return SWM_E_INVALID;
+  if (!frame_ok(v)) { f->err = "bad argument"; return SWM_E_INVALID; }
+  FCK(f, cudaSetDevice(f->device));
+  FCK(f, cudaEventSynchronize(f->ready));  // a previous build of this frame may still be in flight
+  const float bounds[4] = {v->min_x, v->max_x, v->min_y, v->max_y};
+  int rc;
+  if ((rc = frame_reserve(f, v->n, bounds))) return rc;
+  const size_t n = (size_t)v->n;
+  if (n) {
+    FCK(f, cudaMemcpyAsync(f->b[0].p, v->x, n * 4, cudaMemcpyHostToDevice, f->stream));
+    FCK(f, cudaMemcpyAsync(f->b[1].p, v->y, n * 4, cudaMemcpyHostToDevice, f->stream));
+    FCK(f, cudaMemcpyAsync(f->b[2].p, v->octave, n * 4, cudaMemcpyHostToDevice, f->stream));
+    FCK(f, cudaMemcpyAsync(f->b[3].p, v->angle, n * 4, cudaMemcpyHostToDevice, f->stream));
+    FCK(f, cudaMemcpyAsync(f->b[4].p, v->desc, n * 32, cudaMemcpyHostToDevice, f->stream));
+  }
+  if ((rc = frame_grid(f, f->stream))) return rc;
+  FCK(f, cudaStreamSynchronize(f->stream));  // the host arrays may be pageable / reused by the caller
+  return SWM_OK;
+}
+
+int swm_frame_download(swm_frame* f, float* x, float* y, int32_t* octave, float* angle, uint8_t* desc,
+                       int32_t* grid_starts, int32_t* grid_items) {
+  if (!f) return SWM_E_INVALID;
+  FCK(f, cudaSetDevice(f->device));
+  FCK(f, cudaEventSynchronize(f->ready));
+  const size_t n = (size_t)f->n;
+  if (n) {
+    if (x) FCK(f, cudaMemcpy(x, f->b[0].p, n * 4, cudaMemcpyDeviceToHost));
+    if (y) FCK(f, cudaMemcpy(y, f->b[1].p, n * 4, cudaMemcpyDeviceToHost));
+    if (octave) FCK(f, cudaMemcpy(octave, f->b[2].p, n * 4, cudaMemcpyDeviceToHost));
+    if (angle) FCK(f, cudaMemcpy(angle, f->b[3].p, n * 4, cudaMemcpyDeviceToHost));
+    if (desc) FCK(f, cudaMemcpy(desc, f->b[4].p, n * 32, cudaMemcpyDeviceToHost));
+  }
+  if (grid_starts || grid_items) {
+    if (!f->dev.starts) { f->err = "frame has not been built"; return SWM_E_STATE; }
+    std::vector<int32_t> st((size_t)kCells + 1);
+    FCK(f, cudaMemcpy(st.data(), f->dev.starts, st.size() * 4, cudaMemcpyDeviceToHost));
+    if (grid_starts) memcpy(grid_starts, st.data(), st.size() * 4);
+    if (grid_items && st[kCells] > 0)
+      FCK(f, cudaMemcpy(grid_items, f->dev.items, (size_t)st[kCells] * 4, cudaMemcpyDeviceToHost));
+  }
   return SWM_OK;
 }
 

@@ -47,4 +47,15 @@ inline std::string cuda_err(const char* what, cudaError_t e) {
 // Verifies a usable sm_100 device; fills err on failure.  No CPU fallback exists.
 int check_device(int device, std::string* err);
 
+// Device-resident outputs of the extractor's most recent batch (extract.cu), for consumers inside the library
+// that continue on the GPU (swm_frame_from_extractor in match.cu).
+struct OrbDeviceView {
+  const swm_keypoint* kps;  // [batch][cap]
+  const uint8_t* desc;      // [batch][cap][32]
+  const int32_t* n;         // [batch]
+  int cap, batch, device;
+  cudaStream_t stream;      // the stream the batch was enqueued on
+};
+int orb_device_view(swm_orb* h, OrbDeviceView* out);
+
 }  // namespace swm

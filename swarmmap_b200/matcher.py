@@ -10,7 +10,7 @@ import numpy as np
 from . import _lib
 from ._lib import FeatVec, FrameView, SwmError, WindowQuery, check, ptr
 
-__all__ = ["ORBmatcher", "Frame", "FeatureVector"]
+__all__ = ["ORBmatcher", "Frame", "FeatureVector", "ResidentFrame", "Camera"]
 
 GRID_COLS, GRID_ROWS = 64, 48
 
@@ -39,6 +39,87 @@ class Frame:
         b = self.bounds
         return FrameView(self.N, ptr(self.x).value, ptr(self.y).value, ptr(self.octave).value, ptr(self.angle).value,
                          ptr(self.desc).value, b[0], b[1], b[2], b[3])
+
+
+class Camera:
+    """mK + mDistCoef of a Frame (code/src/Frame.cc:60-61), k3 = 0 for four-coefficient settings files."""
+
+    def __init__(self, fx, fy, cx, cy, k1=0.0, k2=0.0, p1=0.0, p2=0.0, k3=0.0):
+        self.c = _lib.Camera(fx, fy, cx, cy, k1, k2, p1, p2, k3)
+
+    def bounds(self, cols, rows, device=0):
+        """Frame::ComputeImageBounds (Frame.cc:486-514): (mnMinX, mnMaxX, mnMinY, mnMaxY), computed on the device."""
+        out = np.zeros(4, np.float32)
+        rc = _lib.load().swm_camera_bounds(device, C.byref(self.c), int(cols), int(rows), _lib.ptr(out))
+        if rc != 0:
+            raise _lib.SwmError(f"swm_camera_bounds: {_lib.ERRORS.get(rc, rc)}")
+        return out
+
+
+class ResidentFrame:
+    """A Frame whose undistorted keypoints, descriptors and grid live on the device:
+    built straight from the extractor's device output (Frame::UndistortKeyPoints + AssignFeaturesToGrid, Frame.cc:
+    454-484, 277-292) or uploaded once from host arrays, then passed to the ORBmatcher methods in place of a Frame."""
+
+    def __init__(self, device=0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        self.mvScaleFactors = None  # set by from_extractor / upload (the SearchByProjection wrappers read it)
+        rc = self._lib.swm_frame_create(device, C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.swm_frame_last_error(None)
+            raise _lib.SwmError(f"swm_frame_create: {_lib.ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.swm_frame_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.swm_frame_last_error(self._h)
+            raise _lib.SwmError(f"{what}: {_lib.ERRORS.get(rc, rc)}: {msg.decode() if msg else ''}")
+
+    @property
+    def N(self):
+        return int(self._lib.swm_frame_size(self._h))
+
+    def from_extractor(self, extractor, index, camera, bounds):
+        """Frame `index` of the extractor's last batch; camera may be None (no distortion)."""
+        b = np.ascontiguousarray(bounds, np.float32)
+        cam = C.byref(camera.c) if camera is not None else None
+        self._check(self._lib.swm_frame_from_extractor(self._h, extractor._h, int(index), cam, _lib.ptr(b)),
+                    "swm_frame_from_extractor")
+        self.mvScaleFactors = extractor.GetScaleFactors()
+        return self
+
+    def upload(self, frame):
+        v = frame.view()
+        self._check(self._lib.swm_frame_upload(self._h, C.byref(v)), "swm_frame_upload")
+        self.mvScaleFactors = frame.mvScaleFactors
+        return self
+
+    def download(self, grid=False):
+        n = self.N
+        x = np.zeros(n, np.float32); y = np.zeros(n, np.float32)
+        octave = np.zeros(n, np.int32); angle = np.zeros(n, np.float32)
+        desc = np.zeros((n, 32), np.uint8)
+        starts = np.zeros(64 * 48 + 1, np.int32) if grid else None
+        items = np.zeros(max(n, 1), np.int32) if grid else None
+        self._check(self._lib.swm_frame_download(self._h, _lib.ptr(x), _lib.ptr(y), _lib.ptr(octave), _lib.ptr(angle),
+                                                 _lib.ptr(desc), _lib.ptr(starts) if grid else None,
+                                                 _lib.ptr(items) if grid else None), "swm_frame_download")
+        out = dict(x=x, y=y, octave=octave, angle=angle, desc=desc)
+        if grid:
+            out["starts"] = starts
+            out["items"] = items[:starts[-1]]
+        return out
 
 
 class FeatureVector:
@@ -123,9 +204,16 @@ class ORBmatcher:
         assert vbPrevMatched.dtype == np.float32 and vbPrevMatched.shape == (F1.N, 2) and vbPrevMatched.flags.c_contiguous
         matches = np.full(F1.N, -1, np.int32)
         n = C.c_int(0)
-        v1, v2 = F1.view(), F2.view()
-        rc = self._lib.swm_match_init(self._h, C.byref(v1), C.byref(v2), ptr(vbPrevMatched), ptr(matches),
-                                      int(windowSize), self.mfNNratio, int(self.mbCheckOrientation), C.byref(n))
+        if isinstance(F1, ResidentFrame) != isinstance(F2, ResidentFrame):
+            raise TypeError("both frames must be resident or both host-side")
+        if isinstance(F1, ResidentFrame):
+            rc = self._lib.swm_match_init_resident(self._h, F1._h, F2._h, ptr(vbPrevMatched), ptr(matches),
+                                                   int(windowSize), self.mfNNratio, int(self.mbCheckOrientation),
+                                                   C.byref(n))
+        else:
+            v1, v2 = F1.view(), F2.view()
+            rc = self._lib.swm_match_init(self._h, C.byref(v1), C.byref(v2), ptr(vbPrevMatched), ptr(matches),
+                                          int(windowSize), self.mfNNratio, int(self.mbCheckOrientation), C.byref(n))
         self._check(rc, "swm_match_init")
         return n.value, matches
 
@@ -150,10 +238,15 @@ class ORBmatcher:
             assignment = np.full(tgt.N, -1, np.int32)
         tb = np.ascontiguousarray(tgt_blocked, np.uint8) if tgt_blocked is not None else None
         n = C.c_int(0)
-        tv = tgt.view()
-        rc = self._lib.swm_match_window(self._h, C.byref(tv), C.byref(q), ptr(tb) if tb is not None else None,
-                                        int(th_dist), int(ratio_mode), self.mfNNratio, int(check_ori),
-                                        ptr(assignment), C.byref(n))
+        if isinstance(tgt, ResidentFrame):
+            rc = self._lib.swm_match_window_resident(self._h, tgt._h, C.byref(q), ptr(tb) if tb is not None else None,
+                                                     int(th_dist), int(ratio_mode), self.mfNNratio, int(check_ori),
+                                                     ptr(assignment), C.byref(n))
+        else:
+            tv = tgt.view()
+            rc = self._lib.swm_match_window(self._h, C.byref(tv), C.byref(q), ptr(tb) if tb is not None else None,
+                                            int(th_dist), int(ratio_mode), self.mfNNratio, int(check_ori),
+                                            ptr(assignment), C.byref(n))
         self._check(rc, "swm_match_window")
         return n.value, assignment
 
@@ -213,11 +306,18 @@ class ORBmatcher:
         v2 = np.ascontiguousarray(validF, np.uint8) if validF is not None else None
         out = np.full(F.N if mode == 0 else KF.N, -1, np.int32)
         n = C.c_int(0)
-        a, b = KF.view(), F.view()
         fa, fb = fvKF.view(), fvF.view()
-        rc = self._lib.swm_match_bow(self._h, C.byref(a), C.byref(fa), ptr(validKF), C.byref(b), C.byref(fb),
-                                     ptr(v2) if v2 is not None else None, mode, self.mfNNratio,
-                                     int(self.mbCheckOrientation), ptr(out), C.byref(n))
+        if isinstance(KF, ResidentFrame) != isinstance(F, ResidentFrame):
+            raise TypeError("both frames must be resident or both host-side")
+        if isinstance(KF, ResidentFrame):
+            rc = self._lib.swm_match_bow_resident(self._h, KF._h, C.byref(fa), ptr(validKF), F._h, C.byref(fb),
+                                                  ptr(v2) if v2 is not None else None, mode, self.mfNNratio,
+                                                  int(self.mbCheckOrientation), ptr(out), C.byref(n))
+        else:
+            a, b = KF.view(), F.view()
+            rc = self._lib.swm_match_bow(self._h, C.byref(a), C.byref(fa), ptr(validKF), C.byref(b), C.byref(fb),
+                                         ptr(v2) if v2 is not None else None, mode, self.mfNNratio,
+                                         int(self.mbCheckOrientation), ptr(out), C.byref(n))
         self._check(rc, "swm_match_bow")
         return n.value, out
 

@@ -99,6 +99,8 @@ def lib():
         L.orc_search_by_bow.argtypes = [vp, vp, vp, vp, vp, vp, ci, cf, ci, vp]
         L.orc_search_by_bow.restype = ci
         L.orc_bruteforce_top2.argtypes = [vp, ci, vp, C.c_int64, vp]
+        L.orc_undistort_points.argtypes = [vp, ci, vp, vp]
+        L.orc_image_bounds.argtypes = [ci, ci, vp, vp]
         _lib = L
     return _lib
 
@@ -328,4 +330,19 @@ def bruteforce_top2(q, db):
     db = np.ascontiguousarray(db, np.uint8)
     out = np.zeros((len(q), 4), np.int32)
     lib().orc_bruteforce_top2(_p(q), len(q), _p(db), len(db), _p(out))
+    return out
+
+
+def undistort_points(xy, cam9):
+    xy = np.ascontiguousarray(xy, np.float32)
+    cam = np.ascontiguousarray(cam9, np.float32)
+    out = np.zeros_like(xy)
+    lib().orc_undistort_points(_p(xy), len(xy), _p(cam), _p(out))
+    return out
+
+
+def image_bounds(cols, rows, cam9):
+    cam = np.ascontiguousarray(cam9, np.float32)
+    out = np.zeros(4, np.float32)
+    lib().orc_image_bounds(cols, rows, _p(cam), _p(out))
     return out

@@ -102,3 +102,34 @@ def test_tile_select_properties(oracle):
         for dx in (-1, 0, 1):
             if dx or dy:
                 assert not (occ & np.roll(np.roll(occ, dy, 0), dx, 1)).any()
+
+
+# EuRoC cam0, TUM1 (5 coefficients), KITTI-like (no distortion)
+CAMERAS = {
+    "euroc": [458.654, 457.296, 367.215, 248.375, -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0],
+    "tum1": [517.306408, 516.469215, 318.643040, 255.313989, 0.262383, -0.953104, -0.005358, 0.002628, 1.163314],
+    "kitti": [718.856, 718.856, 607.1928, 185.2157, 0.0, 0.0, 0.0, 0.0, 0.0],
+}
+
+
+@pytest.mark.parametrize("name", sorted(CAMERAS))
+def test_undistort_points_bit_exact(oracle, name):
+    """Frame::UndistortKeyPoints (Frame.cc:454-484) = cv::undistortPoints(K, D, P = K): the oracle's restatement
+    of the 5-iteration scheme equals cv2 bit for bit, and so do the image bounds built from it (:486-514)."""
+    cam = np.array(CAMERAS[name], np.float32)
+    w, h = 752, 480
+    rng = np.random.default_rng(5)
+    xy = np.stack([rng.uniform(0, w, 6000), rng.uniform(0, h, 6000)], 1).astype(np.float32)
+    xy[:2000] = np.round(xy[:2000])  # level-0 keypoints are integers
+    K = np.array([[cam[0], 0, cam[2]], [0, cam[1], cam[3]], [0, 0, 1]], np.float32)
+    got = oracle.undistort_points(xy, cam)
+    if cam[4] == 0:
+        np.testing.assert_array_equal(got, xy)  # mvKeysUn = mvKeys (:456-460)
+        np.testing.assert_array_equal(oracle.image_bounds(w, h, cam), [0, w, 0, h])
+        return
+    ref = cv2.undistortPoints(xy.reshape(-1, 1, 2), K, cam[4:9], None, K).reshape(-1, 2)
+    np.testing.assert_array_equal(got, ref)
+    corners = np.array([[0, 0], [w, 0], [0, h], [w, h]], np.float32)
+    m = cv2.undistortPoints(corners.reshape(-1, 1, 2), K, cam[4:9], None, K).reshape(-1, 2)
+    exp = [min(m[0, 0], m[2, 0]), max(m[1, 0], m[3, 0]), min(m[0, 1], m[1, 1]), max(m[2, 1], m[3, 1])]
+    np.testing.assert_array_equal(oracle.image_bounds(w, h, cam), np.array(exp, np.float32))
