@@ -393,6 +393,30 @@ def main():
         for i in range(20):
             m.SearchByProjectionLastFrame(fs[1], fs[0], u, v, valid, 15)
         extras["search_by_projection_ms"] = (time.perf_counter() - t0) / 20 * 1e3
+        # tracking step with the frame kept on the device: operator() on a host image,
+        # undistort + grid on the GPU, SearchByProjection against the resident frame -- versus the same step through
+        # host arrays (keypoints back to the host, Frame built there, uploaded again by the matcher)
+        from swarmmap_b200.matcher import Camera, ResidentFrame
+        cam = Camera(718.856, 718.856, 607.1928, 185.2157, -0.2834, 0.0739, 0.0002, 1.76e-05, 0.0)
+        bounds = cam.bounds(1241, 376, local_rank)
+        rf = ResidentFrame(local_rank)
+        def track_resident(img):
+            ex4k(img)
+            rf.from_extractor(ex4k, 0, cam, bounds)
+            return m.SearchByProjectionLastFrame(rf, fs[0], u, v, valid, 15)
+        def track_host(img):
+            f = Frame.from_keypoints(*ex4k(img), 1241, 376, sf)
+            return m.SearchByProjectionLastFrame(f, fs[0], u, v, valid, 15)
+        for fn, key in ((track_resident, "track_step_resident_ms"), (track_host, "track_step_host_arrays_ms")):
+            for _ in range(3):
+                fn(seq[1])
+            t0 = time.perf_counter()
+            for i in range(20):
+                fn(seq[1 + i % 2])
+            extras[key] = (time.perf_counter() - t0) / 20 * 1e3
+        extras["track_step_cfg"] = ("1241x376, 4000 features: operator() from a host image + frame build + "
+                                    "SearchByProjection(th=15) of 4000 last-frame points; resident = undistort/grid on the "
+                                    "GPU and match in place, host_arrays = no undistortion, Frame rebuilt on the host")
         if not args.no_cpu_baseline:
             import oracle_lib
             t0 = time.perf_counter()

@@ -62,14 +62,17 @@ class ORBmatcher {
   int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<Point2fT>& vbPrevMatched,
                               std::vector<int>& vnMatches12, int windowSize = 10) {
     FlatFrame a, b;
-    gather(F1, a);
-    gather(F2, b);
+    const bool res = resident_of(F1, 0) && resident_of(F2, 0);  // both on the device, or both gathered
+    gather(F1, a, res);
+    gather(F2, b, res);
     std::vector<float> prev(2 * a.n);
     for (int i = 0; i < a.n; i++) { prev[2 * i] = vbPrevMatched[i].x; prev[2 * i + 1] = vbPrevMatched[i].y; }
     vnMatches12.assign(a.n, -1);
     int n = 0;
     swm_frame_view va = a.view(), vb = b.view();
-    check(swm_match_init(m_, &va, &vb, prev.data(), vnMatches12.data(), windowSize, mfNNratio, mbCheckOrientation, &n));
+    check(res ? swm_match_init_resident(m_, resident_of(F1, 0), resident_of(F2, 0), prev.data(), vnMatches12.data(),
+                                        windowSize, mfNNratio, mbCheckOrientation, &n)
+              : swm_match_init(m_, &va, &vb, prev.data(), vnMatches12.data(), windowSize, mfNNratio, mbCheckOrientation, &n));
     for (int i = 0; i < a.n; i++) { vbPrevMatched[i].x = prev[2 * i]; vbPrevMatched[i].y = prev[2 * i + 1]; }
     return n;
   }
@@ -117,7 +120,7 @@ class ORBmatcher {
     int n = 0;
     swm_frame_view vc = cur.view();
     swm_window_query wq = q.view();
-    check(swm_match_window(m_, &vc, &wq, blocked.data(), TH_HIGH, 0, mfNNratio, mbCheckOrientation, asg.data(), &n));
+    check(window_call(resident_of(CurrentFrame, 0), &vc, &wq, blocked.data(), TH_HIGH, 0, mbCheckOrientation, asg.data(), &n));
     for (int j = 0; j < cur.n; j++) {
       if (asg[j] >= 0) CurrentFrame.mvpMapPoints[j] = LastFrame.mvpMapPoints[asg[j]];  // :1317
       else if (asg[j] == -1) CurrentFrame.mvpMapPoints[j] = nullptr;
@@ -152,7 +155,7 @@ class ORBmatcher {
     int n = 0;
     swm_frame_view vf = f.view();
     swm_window_query wq = q.view();
-    check(swm_match_window(m_, &vf, &wq, blocked.data(), TH_HIGH, 1, mfNNratio, 0, asg.data(), &n));
+    check(window_call(resident_of(F, 0), &vf, &wq, blocked.data(), TH_HIGH, 1, 0, asg.data(), &n));
     for (int j = 0; j < f.n; j++)
       if (asg[j] >= 0) F.mvpMapPoints[j] = vpMapPoints[asg[j]];             // :115
     return n;
@@ -204,7 +207,7 @@ class ORBmatcher {
     int n = 0;
     swm_frame_view vc = cur.view();
     swm_window_query wq = q.view();
-    check(swm_match_window(m_, &vc, &wq, blocked.data(), ORBdist, 0, mfNNratio, mbCheckOrientation, asg.data(), &n));
+    check(window_call(resident_of(CurrentFrame, 0), &vc, &wq, blocked.data(), ORBdist, 0, mbCheckOrientation, asg.data(), &n));
     for (int j = 0; j < cur.n; j++) {
       if (asg[j] >= 0) CurrentFrame.mvpMapPoints[j] = vpMPs[asg[j]];
       else if (asg[j] == -1) CurrentFrame.mvpMapPoints[j] = nullptr;
@@ -262,7 +265,7 @@ class ORBmatcher {
     int n = 0;
     swm_frame_view vk = kf.view();
     swm_window_query wq = q.view();
-    check(swm_match_window(m_, &vk, &wq, blocked.data(), TH_LOW, 0, mfNNratio, 0, asg.data(), &n));
+    check(window_call(resident_of(*pKF, 0), &vk, &wq, blocked.data(), TH_LOW, 0, 0, asg.data(), &n));
     for (int j = 0; j < kf.n; j++)
       if (asg[j] >= 0) vpMatched[j] = vpPoints[asg[j]];                   // :366
     return n;
@@ -273,8 +276,9 @@ class ORBmatcher {
   int SearchByBoW(KeyFrameT* pKF, FrameT& F, std::vector<MapPointT*>& vpMapPointMatches) {
     const std::vector<MapPointT*> vpMapPointsKF = pKF->GetMapPointMatches();
     FlatFrame a, b;
-    gather(*pKF, a);
-    gather(F, b);
+    const bool res = resident_of(*pKF, 0) && resident_of(F, 0);
+    gather(*pKF, a, res);
+    gather(F, b, res);
     std::vector<uint8_t> valid(a.n, 0);
     for (int i = 0; i < a.n; i++) valid[i] = vpMapPointsKF[i] && !vpMapPointsKF[i]->isBad();  // :182-188
     FlatFeatVec fa(pKF->mFeatVec), fb(F.mFeatVec);
@@ -282,7 +286,9 @@ class ORBmatcher {
     int n = 0;
     swm_frame_view va = a.view(), vb = b.view();
     swm_featvec ga = fa.view(), gb = fb.view();
-    check(swm_match_bow(m_, &va, &ga, valid.data(), &vb, &gb, nullptr, 0, mfNNratio, mbCheckOrientation, out.data(), &n));
+    check(res ? swm_match_bow_resident(m_, resident_of(*pKF, 0), &ga, valid.data(), resident_of(F, 0), &gb, nullptr, 0,
+                                       mfNNratio, mbCheckOrientation, out.data(), &n)
+              : swm_match_bow(m_, &va, &ga, valid.data(), &vb, &gb, nullptr, 0, mfNNratio, mbCheckOrientation, out.data(), &n));
     vpMapPointMatches.assign(b.n, static_cast<MapPointT*>(nullptr));
     for (int j = 0; j < b.n; j++)
       if (out[j] >= 0) vpMapPointMatches[j] = vpMapPointsKF[out[j]];
@@ -294,8 +300,9 @@ class ORBmatcher {
   int SearchByBoW(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12) {
     const std::vector<MapPointT*> mp1 = pKF1->GetMapPointMatches(), mp2 = pKF2->GetMapPointMatches();
     FlatFrame a, b;
-    gather(*pKF1, a);
-    gather(*pKF2, b);
+    const bool res = resident_of(*pKF1, 0) && resident_of(*pKF2, 0);
+    gather(*pKF1, a, res);
+    gather(*pKF2, b, res);
     std::vector<uint8_t> v1(a.n, 0), v2(b.n, 0);
     for (int i = 0; i < a.n; i++) v1[i] = mp1[i] && !mp1[i]->isBad();
     for (int i = 0; i < b.n; i++) v2[i] = mp2[i] && !mp2[i]->isBad();
@@ -304,7 +311,9 @@ class ORBmatcher {
     int n = 0;
     swm_frame_view va = a.view(), vb = b.view();
     swm_featvec ga = fa.view(), gb = fb.view();
-    check(swm_match_bow(m_, &va, &ga, v1.data(), &vb, &gb, v2.data(), 1, mfNNratio, mbCheckOrientation, out.data(), &n));
+    check(res ? swm_match_bow_resident(m_, resident_of(*pKF1, 0), &ga, v1.data(), resident_of(*pKF2, 0), &gb, v2.data(), 1,
+                                       mfNNratio, mbCheckOrientation, out.data(), &n)
+              : swm_match_bow(m_, &va, &ga, v1.data(), &vb, &gb, v2.data(), 1, mfNNratio, mbCheckOrientation, out.data(), &n));
     vpMatches12.assign(a.n, static_cast<MapPointT*>(nullptr));
     for (int i = 0; i < a.n; i++)
       if (out[i] >= 0) vpMatches12[i] = mp2[out[i]];
@@ -359,17 +368,31 @@ class ORBmatcher {
     }
   };
 
+  // A Frame / KeyFrame that carries `const swm_frame* mpResident` (built by ORB_SLAM2::ResidentFrame from the
+  // extractor's device output, host/ResidentFrame.h) is matched in place on the GPU; otherwise its arrays are
+  // gathered and uploaded per call.
+  template <class FrameT>
+  static auto resident_of(const FrameT& F, int) -> decltype(F.mpResident) { return F.mpResident; }
+  template <class FrameT>
+  static const swm_frame* resident_of(const FrameT&, long) { return nullptr; }
+  int window_call(const swm_frame* res, const swm_frame_view* v, const swm_window_query* q, const uint8_t* blocked,
+                  int th, int ratio_mode, int check_ori, int32_t* asg, int* n) {
+    return res ? swm_match_window_resident(m_, res, q, blocked, th, ratio_mode, mfNNratio, check_ori, asg, n)
+               : swm_match_window(m_, v, q, blocked, th, ratio_mode, mfNNratio, check_ori, asg, n);
+  }
+
   // Frame / KeyFrame members read by every matcher: N, mvKeysUn, mDescriptors, image bounds.
   template <class FrameT>
-  static void gather(const FrameT& F, FlatFrame& o) {
+  static void gather(const FrameT& F, FlatFrame& o, bool use_resident = true) {
     o.n = F.N;
+    o.min_x = F.mnMinX; o.min_y = F.mnMinY; o.max_x = F.mnMaxX; o.max_y = F.mnMaxY;
+    if (use_resident && resident_of(F, 0)) return;  // the arrays already live on the device
     o.x.resize(o.n); o.y.resize(o.n); o.angle.resize(o.n); o.octave.resize(o.n); o.desc.resize((size_t)o.n * 32);
     for (int i = 0; i < o.n; i++) {
       o.x[i] = F.mvKeysUn[i].pt.x; o.y[i] = F.mvKeysUn[i].pt.y;
       o.angle[i] = F.mvKeysUn[i].angle; o.octave[i] = F.mvKeysUn[i].octave;
       std::memcpy(&o.desc[(size_t)i * 32], F.mDescriptors.ptr(i), 32);
     }
-    o.min_x = F.mnMinX; o.min_y = F.mnMinY; o.max_x = F.mnMaxX; o.max_y = F.mnMaxY;
   }
   template <class MapPointT>
   static cv::Mat descriptor_of(MapPointT* p) { return p->GetDescriptor(); }

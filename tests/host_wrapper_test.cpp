@@ -8,6 +8,7 @@
 
 #include "../swarmmap_b200/host/ORBextractor.h"
 #include "../swarmmap_b200/host/ORBmatcher.h"
+#include "../swarmmap_b200/host/ResidentFrame.h"
 
 struct Mat4 {  // stand-in for the CV_32F cv::Mat pose / position
   float v[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
@@ -49,6 +50,7 @@ struct Frame {
   bool IsInImage(float x, float y) const { return x >= mnMinX && x < mnMaxX && y >= mnMinY && y < mnMaxY; }
   std::vector<float> mvScaleFactors;
   std::map<unsigned, std::vector<unsigned>> mFeatVec;
+  const swm_frame* mpResident = nullptr;  // set when the features also live on the device (host/ResidentFrame.h)
   std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
 };
 
@@ -123,6 +125,31 @@ int main(int argc, char** argv) {
   const int n_loop = ml.SearchByProjection(&f5, Scw, local, matched, 10);
   std::printf("reloc %d loop %d\n", n_reloc, n_loop);
   if (n_reloc < f1.N / 2 || n_loop < f1.N / 2) { std::printf("HOST_WRAPPER_FAIL\n"); return 1; }
+  // Resident path: the same frame built on the device from the extractor's output must give the host path's results
+  Frame f6;
+  fill(f6, ex, img);  // the extractor's last batch is now f6's image
+  const swm_camera cam = {Frame::fx, Frame::fy, Frame::cx, Frame::cy, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float bounds[4];
+  ORB_SLAM2::ResidentFrame::ComputeImageBounds(cam, w, h, bounds);
+  ORB_SLAM2::ResidentFrame rf6, rf1;
+  rf6.FromExtractor(ex, 0, &cam, bounds);
+  std::vector<cv::KeyPoint> un;
+  rf6.DownloadUndistorted(f6.mvKeys, un);
+  bool same_un = rf6.size() == f6.N && bounds[0] == 0 && bounds[1] == w && bounds[2] == 0 && bounds[3] == h;
+  for (int i = 0; i < f6.N && same_un; i++) same_un = un[i].pt.x == f6.mvKeys[i].pt.x && un[i].pt.y == f6.mvKeys[i].pt.y;
+  f6.mpResident = rf6.get();
+  ORB_SLAM2::ORBmatcher m6(0.9f, true);
+  const int n_proj_res = m6.SearchByProjection(f6, f1, 15.0f, true);  // f6 (== f2's image) matched in place on the GPU
+  int same_proj = 0;
+  for (int j = 0; j < f6.N; j++) same_proj += f6.mvpMapPoints[j] == f2.mvpMapPoints[j];
+  rf1.FromExtractor(ex, 0, &cam, bounds);  // same image as f1: both operands resident for the BoW matcher
+  f1.mpResident = rf1.get();
+  std::vector<MapPoint*> bow_res;
+  const int n_bow_res = mb.SearchByBoW(&f1, f6, bow_res);
+  f1.mpResident = nullptr;
+  std::printf("resident: undistort-identity %d proj %d (host %d) same slots %d/%d bow %d (host %d)\n", (int)same_un, n_proj_res,
+              n_proj, same_proj, f6.N, n_bow_res, n_bow);
+  if (!same_un || n_proj_res != n_proj || same_proj != f6.N || n_bow_res != n_bow) { std::printf("HOST_WRAPPER_FAIL\n"); return 1; }
   const int d0 = ORB_SLAM2::ORBmatcher::DescriptorDistance(f1.mDescriptors.row(0), f1.mDescriptors.row(0));
   const int d1 = ORB_SLAM2::ORBmatcher::DescriptorDistance(f1.mDescriptors.row(0), f1.mDescriptors.row(1));
   std::printf("init %d proj %d self %d mappoints %d bow %d bowkf %d d0 %d d1 %d\n", n_init, n_proj, self, n_mp, n_bow,
