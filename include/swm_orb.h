@@ -252,6 +252,41 @@ int swm_match_bow_resident(swm_matcher* m, const swm_frame* f1, const swm_featve
                            const swm_frame* f2, const swm_featvec* fv2, const uint8_t* valid2, int mode, float nnratio,
                            int check_ori, int32_t* matches, int* nmatches);
 
+/* ------------------------------------------------------------------ DBoW2 transform
+ * TemplatedVocabulary<FORB>::transform(features, BowVector&, FeatureVector&, levelsup)
+ * (code/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1151-1218, per feature :1242-1283) as called by
+ * Frame::ComputeBoW (code/src/Frame.cc:445-452), KeyFrame::ComputeBoW (code/src/KeyFrame.cc:126-133) and the
+ * server for every received keyframe (code/src/Map.cc:372-385); SwarmMap always passes levelsup = 4. */
+#define SWM_BOW_MAX_FEATURES 8192
+typedef struct swm_vocab swm_vocab; /* opaque: the vocabulary tree on one device */
+/* blob: the file TemplatedVocabulary::loadFromBinaryFile reads (:1478-1522), e.g. ORBvoc.bin:
+ * uint32 nb_nodes, uint32 size_node (41), int32 k, L, scoring, weighting; then per node id 1.. :
+ * int32 parent, 32 descriptor bytes, float weight, uint8 is_leaf. */
+int swm_vocab_create(int device, const uint8_t* blob, size_t bytes, swm_vocab** out);
+void swm_vocab_destroy(swm_vocab* v);
+const char* swm_vocab_last_error(const swm_vocab* v);
+int swm_vocab_info(const swm_vocab* v, int32_t* k, int32_t* L, int32_t* n_nodes, int32_t* n_words);
+
+/* Host output slabs for `batch` frames of capacity `cap` features each.  Frame b:
+ *   BowVector      word_ids[b*cap ..], word_values[b*cap ..] (n_words[b] entries, ascending word id = std::map order)
+ *   FeatureVector  node_ids[b*cap ..] (n_nodes[b] entries, ascending), node_offsets[b*(cap+1) ..] (n_nodes[b] + 1),
+ *                  feats[b*cap ..] (ascending feature indices per node: FeatureVector.cpp:31-45)
+ * i.e. the swm_featvec CSR the SearchByBoW entry points take. */
+typedef struct swm_bow_out {
+  uint32_t* word_ids;
+  double* word_values;
+  int32_t* n_words;
+  uint32_t* node_ids;
+  int32_t* node_offsets;
+  uint32_t* feats;
+  int32_t* n_nodes;
+} swm_bow_out;
+/* desc: host [batch][cap][32], n[b] valid rows per frame (<= cap <= SWM_BOW_MAX_FEATURES). */
+int swm_bow_transform(swm_vocab* v, const uint8_t* desc, const int32_t* n, int batch, int cap, int levelsup,
+                      const swm_bow_out* out);
+/* The same for one resident frame (cap = swm_frame_size(f)); the descriptors never leave the device. */
+int swm_bow_transform_frame(swm_vocab* v, const swm_frame* f, int levelsup, const swm_bow_out* out);
+
 /* ------------------------------------------------------------------ place-recognition shard (config 5) */
 typedef struct swm_db swm_db; /* one GPU's shard of the keyframe-descriptor database */
 /* desc: ndesc x 32 bytes (host), kf_of_desc optional (NULL -> desc i belongs to kf i / desc_per_kf). */

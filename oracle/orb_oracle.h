@@ -20,6 +20,7 @@
 #ifndef ORB_ORACLE_H
 #define ORB_ORACLE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -150,6 +151,22 @@ void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* db, int64_t nd
 void orc_undistort_points(const float* xy, int n, const float* cam9, float* out_xy);
 /* Frame::ComputeImageBounds (Frame.cc:486-514): out4 = mnMinX, mnMaxX, mnMinY, mnMaxY. */
 void orc_image_bounds(int cols, int rows, const float* cam9, float* out4);
+
+/* ---- DBoW2 (vendored in the reference: code/Thirdparty/DBoW2/DBoW2; needs OpenCV, so it cannot be compiled here) ----
+ * Vocabulary from the binary layout read by TemplatedVocabulary::loadFromBinaryFile (TemplatedVocabulary.h:1478-1522):
+ * header nb_nodes, size_node, k, L, scoring, weighting, then per node (ids 1..): int32 parent, 32 descriptor bytes,
+ * float weight, uint8 is_leaf.  Children lists in file order, word ids = leaves in file order. */
+typedef struct orc_vocab orc_vocab;
+orc_vocab* orc_vocab_load(const uint8_t* blob, size_t bytes);
+void orc_vocab_destroy(orc_vocab* v);
+void orc_vocab_info(const orc_vocab* v, int32_t* k, int32_t* L, int32_t* n_nodes, int32_t* n_words);
+/* TemplatedVocabulary::transform(features, BowVector&, FeatureVector&, levelsup) (:1151-1218, per feature :1242-1283;
+ * FORB::distance FORB.cpp:82-102; BowVector::addWeight / addIfNotExist / normalize BowVector.cpp:33-90;
+ * FeatureVector::addFeature FeatureVector.cpp:31-45).  Outputs sized for n entries; offsets n + 1.
+ * Returns the number of words; *n_nodes_out the number of FeatureVector nodes. */
+int orc_bow_transform(const orc_vocab* v, const uint8_t* desc, int n, int levelsup, uint32_t* word_ids,
+                      double* word_values, uint32_t* node_ids, int32_t* offsets, uint32_t* feats, int32_t* n_nodes_out);
+double orc_time_bow_transform(const orc_vocab* v, const uint8_t* desc, int n, int levelsup, int iters);
 
 /* ---- timing helpers for bench.py's cpu_baseline (run entirely on the CPU) ---- */
 double orc_time_extract(orc_extractor* e, const uint8_t* imgs, int n_imgs, int w, int h, int iters);

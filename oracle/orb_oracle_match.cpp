@@ -7,6 +7,8 @@
 #include <cmath>
 #include <cstring>
 #include <vector>
+#include <map>
+#include <chrono>
 
 #include "orb_oracle.h"
 
@@ -377,6 +379,158 @@ void orc_image_bounds(int cols, int rows, const float* cam9, float* out4) {
   out4[1] = std::max(m[2], m[6]);  // mnMaxX = max(mat(1,0), mat(3,0))
   out4[2] = std::min(m[1], m[3]);  // mnMinY = min(mat(0,1), mat(1,1))
   out4[3] = std::max(m[5], m[7]);  // mnMaxY = max(mat(2,1), mat(3,1))
+}
+
+// ---------------------------------------------------------------------------------------------
+// DBoW2 vocabulary + transform (see header for the reference lines)
+// ---------------------------------------------------------------------------------------------
+struct orc_vocab {
+  struct Node {
+    uint32_t parent = 0;
+    std::vector<uint32_t> children;
+    uint8_t desc[32] = {0};
+    double weight = 0;  // WordValue is double; the file stores float (:1507)
+    uint32_t word_id = 0;
+  };
+  int k = 0, L = 0, scoring = 0, weighting = 0;
+  std::vector<Node> nodes;
+  int n_words = 0;
+};
+
+orc_vocab* orc_vocab_load(const uint8_t* blob, size_t bytes) {
+  if (bytes < 24) return nullptr;
+  uint32_t nb_nodes, size_node;
+  int32_t hdr[4];
+  memcpy(&nb_nodes, blob, 4);
+  memcpy(&size_node, blob + 4, 4);
+  memcpy(hdr, blob + 8, 16);
+  if (size_node != 41) return nullptr;
+  orc_vocab* v = new orc_vocab();
+  v->k = hdr[0]; v->L = hdr[1]; v->scoring = hdr[2]; v->weighting = hdr[3];
+  const size_t n_rec = (bytes - 24) / size_node;
+  v->nodes.resize(n_rec + 1);
+  for (size_t r = 0; r < n_rec; r++) {
+    const uint8_t* buf = blob + 24 + r * size_node;
+    const uint32_t nid = (uint32_t)r + 1;
+    int32_t parent;
+    float w;
+    memcpy(&parent, buf, 4);
+    memcpy(&w, buf + 36, 4);
+    if (parent < 0 || (size_t)parent >= v->nodes.size()) { delete v; return nullptr; }
+    orc_vocab::Node& n = v->nodes[nid];
+    n.parent = (uint32_t)parent;
+    v->nodes[parent].children.push_back(nid);  // :1504
+    memcpy(n.desc, buf + 4, 32);
+    n.weight = w;
+    if (buf[40]) n.word_id = (uint32_t)v->n_words++;  // :1509-1512
+  }
+  (void)nb_nodes;
+  return v;
+}
+
+void orc_vocab_destroy(orc_vocab* v) { delete v; }
+
+void orc_vocab_info(const orc_vocab* v, int32_t* k, int32_t* L, int32_t* n_nodes, int32_t* n_words) {
+  *k = v->k; *L = v->L; *n_nodes = (int32_t)v->nodes.size(); *n_words = v->n_words;
+}
+
+static int forb_distance(const uint8_t* a, const uint8_t* b) {  // FORB.cpp:82-102
+  int dist = 0;
+  for (int i = 0; i < 8; i++) {
+    uint32_t x, y;
+    memcpy(&x, a + 4 * i, 4);
+    memcpy(&y, b + 4 * i, 4);
+    uint32_t v = x ^ y;
+    v = v - ((v >> 1) & 0x55555555);
+    v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+    dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+  }
+  return dist;
+}
+
+// transform(feature, word_id, weight, nid, levelsup), :1242-1283.  When the leaf is shallower than nid_level the
+// reference leaves *nid unset (an uninitialised read in the caller); defined here as the leaf itself.
+static void transform_one(const orc_vocab* v, const uint8_t* f, int levelsup, uint32_t* word, double* weight, uint32_t* nid) {
+  const int nid_level = v->L - levelsup;
+  bool nid_set = false;
+  if (nid_level <= 0) { *nid = 0; nid_set = true; }
+  uint32_t final_id = 0;
+  int current_level = 0;
+  do {
+    ++current_level;
+    const std::vector<uint32_t>& nodes = v->nodes[final_id].children;
+    final_id = nodes[0];
+    double best_d = forb_distance(f, v->nodes[final_id].desc);
+    for (size_t c = 1; c < nodes.size(); c++) {
+      const double d = forb_distance(f, v->nodes[nodes[c]].desc);
+      if (d < best_d) { best_d = d; final_id = nodes[c]; }
+    }
+    if (current_level == nid_level) { *nid = final_id; nid_set = true; }
+  } while (!v->nodes[final_id].children.empty());
+  if (!nid_set) *nid = final_id;
+  *word = v->nodes[final_id].word_id;
+  *weight = v->nodes[final_id].weight;
+}
+
+int orc_bow_transform(const orc_vocab* v, const uint8_t* desc, int n, int levelsup, uint32_t* word_ids,
+                      double* word_values, uint32_t* node_ids, int32_t* offsets, uint32_t* feats, int32_t* n_nodes_out) {
+  std::map<uint32_t, double> bow;                    // BowVector
+  std::map<uint32_t, std::vector<uint32_t>> fv;      // FeatureVector
+  *n_nodes_out = 0;
+  offsets[0] = 0;
+  if (v->nodes.size() <= 1) return 0;                // empty()
+  const bool tf = v->weighting == 0 || v->weighting == 1;  // TF_IDF, TF -> addWeight; IDF, BINARY -> addIfNotExist
+  const bool must = v->scoring != 5;                 // DotProductScoring does not normalise
+  const bool l2 = v->scoring == 1;
+  for (int i = 0; i < n; i++) {
+    uint32_t id, nid;
+    double w;
+    transform_one(v, desc + (size_t)i * 32, levelsup, &id, &w, &nid);
+    if (w > 0) {
+      auto it = bow.lower_bound(id);
+      if (it != bow.end() && it->first == id) {
+        if (tf) it->second += w;
+      } else {
+        bow.insert(it, std::make_pair(id, w));
+      }
+      fv[nid].push_back((uint32_t)i);
+    }
+  }
+  if (tf && !bow.empty() && !must) {
+    const double nd = (double)bow.size();
+    for (auto& e : bow) e.second /= nd;
+  }
+  if (must) {
+    double norm = 0.0;
+    if (!l2) {
+      for (auto& e : bow) norm += fabs(e.second);
+    } else {
+      for (auto& e : bow) norm += e.second * e.second;
+      norm = sqrt(norm);
+    }
+    if (norm > 0.0)
+      for (auto& e : bow) e.second /= norm;
+  }
+  int nw = 0;
+  for (auto& e : bow) { word_ids[nw] = e.first; word_values[nw] = e.second; nw++; }
+  int nn = 0, nf = 0;
+  for (auto& e : fv) {
+    node_ids[nn] = e.first;
+    for (uint32_t idx : e.second) feats[nf++] = idx;
+    offsets[++nn] = nf;
+  }
+  *n_nodes_out = nn;
+  return nw;
+}
+
+double orc_time_bow_transform(const orc_vocab* v, const uint8_t* desc, int n, int levelsup, int iters) {
+  std::vector<uint32_t> a(n + 1), c(n + 1), e(n + 1);
+  std::vector<double> b(n + 1);
+  std::vector<int32_t> d(n + 2);
+  int32_t nn;
+  auto t0 = std::chrono::steady_clock::now();
+  for (int it = 0; it < iters; it++) orc_bow_transform(v, desc, n, levelsup, a.data(), b.data(), c.data(), d.data(), e.data(), &nn);
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 }  // extern "C"

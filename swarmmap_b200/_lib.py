@@ -48,6 +48,11 @@ class Camera(C.Structure):
                 ("k1", C.c_float), ("k2", C.c_float), ("p1", C.c_float), ("p2", C.c_float), ("k3", C.c_float)]
 
 
+class BowOut(C.Structure):
+    _fields_ = [("word_ids", C.c_void_p), ("word_values", C.c_void_p), ("n_words", C.c_void_p),
+                ("node_ids", C.c_void_p), ("node_offsets", C.c_void_p), ("feats", C.c_void_p), ("n_nodes", C.c_void_p)]
+
+
 class FeatVec(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("node_ids", C.c_void_p), ("offsets", C.c_void_p), ("feats", C.c_void_p)]
 
@@ -94,6 +99,12 @@ SYMBOLS = [
     ("swm_match_init_resident", _i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp]),
     ("swm_match_window_resident", _i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp]),
     ("swm_match_bow_resident", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp]),
+    ("swm_vocab_create", _i, [_i, _vp, _sz, _vp]),
+    ("swm_vocab_destroy", None, [_vp]),
+    ("swm_vocab_last_error", C.c_char_p, [_vp]),
+    ("swm_vocab_info", _i, [_vp, _vp, _vp, _vp, _vp]),
+    ("swm_bow_transform", _i, [_vp, _vp, _vp, _i, _i, _i, _vp]),
+    ("swm_bow_transform_frame", _i, [_vp, _vp, _i, _vp]),
     ("swm_db_create", _i, [_i, _vp, _i64, C.c_int32, _i64, _vp]),
     ("swm_db_create_device", _i, [_i, _vp, _i64, C.c_int32, _i64, _vp]),
     ("swm_db_destroy", None, [_vp]),

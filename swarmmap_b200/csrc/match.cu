@@ -1859,3 +1859,15 @@ int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t*
 }
 
 }  // extern "C"
+
+namespace swm {
+int frame_device_view(const swm_frame* f, FrameDeviceView* out) {
+  if (!f || !out) return SWM_E_INVALID;
+  out->desc = f->dev.desc;
+  out->n = f->n;
+  out->device = f->device;
+  out->ready = f->ready;
+  return SWM_OK;
+}
+}  // namespace swm
+

@@ -58,4 +58,12 @@ struct OrbDeviceView {
 };
 int orb_device_view(swm_orb* h, OrbDeviceView* out);
 
+// Descriptors of a resident frame (match.cu) for the vocabulary transform (bow.cu).
+struct FrameDeviceView {
+  const uint4* desc;  // n x 2
+  int n, device;
+  cudaEvent_t ready;  // recorded after the frame's last write
+};
+int frame_device_view(const swm_frame* f, FrameDeviceView* out);
+
 }  // namespace swm

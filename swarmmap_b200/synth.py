@@ -87,3 +87,51 @@ def make_batch(n, w=EUROC[0], h=EUROC[1], seed=20220410):
         f = canvas[oy:oy + h, ox:ox + w] + rng.normal(0, 2.0, (h, w)).astype(np.float32)
         out[i] = np.clip(np.rint(f), 0, 255).astype(np.uint8)
     return out
+
+
+def make_vocabulary(k=10, L=3, seed=1, early_leaf=0.03, zero_weight=0.02, weighting=0, scoring=0):
+    """A synthetic DBoW2 ORB vocabulary in the binary layout TemplatedVocabulary::loadFromBinaryFile reads
+    (reference code/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1478-1522; the real ORBvoc.bin is not shipped):
+    header (nb_nodes, size_node = 41, k, L, scoring, weighting) + per node (int32 parent, 32 descriptor bytes,
+    float weight, uint8 is_leaf), ids in creation order (a parent's k children are consecutive, then depth first,
+    like HKmeansStep).  Children are the parent's descriptor with random bit flips, a few inner nodes stop early and
+    a few words carry weight 0 ("stopped" words are dropped by transform)."""
+    rng = np.random.default_rng(seed)
+    parents, descs, weights, leaves = [], [], [], []
+
+    def add_children(parent_id, parent_desc, depth):
+        first = len(parents) + 1
+        mine = []
+        for _ in range(k):
+            bits = np.unpackbits(parent_desc) if parent_desc is not None else rng.integers(0, 2, 256, dtype=np.uint8)
+            if parent_desc is not None:
+                flip = rng.choice(256, max(4, 96 >> depth), replace=False)
+                bits = bits.copy()
+                bits[flip] ^= 1
+            d = np.packbits(bits)
+            parents.append(parent_id)
+            descs.append(d)
+            weights.append(0.0)
+            leaves.append(0)
+            mine.append(d)
+        for c in range(k):
+            nid = first + c
+            if depth == L or (depth < L and depth >= 1 and rng.random() < early_leaf):
+                leaves[nid - 1] = 1
+                weights[nid - 1] = 0.0 if rng.random() < zero_weight else float(np.float32(rng.uniform(0.05, 12.0)))
+            else:
+                add_children(nid, mine[c], depth + 1)
+
+    add_children(0, None, 1)
+    n = len(parents)
+    out = bytearray()
+    out += np.array([n, 41], np.uint32).tobytes()
+    out += np.array([k, L, scoring, weighting], np.int32).tobytes()
+    rec = np.zeros(n, np.dtype([("parent", "<i4"), ("desc", "u1", 32), ("weight", "<f4"), ("leaf", "u1")]))
+    assert rec.dtype.itemsize == 41
+    rec["parent"] = parents
+    rec["desc"] = np.stack(descs)
+    rec["weight"] = np.array(weights, np.float32)
+    rec["leaf"] = leaves
+    out += rec.tobytes()
+    return bytes(out)

@@ -100,6 +100,13 @@ def lib():
         L.orc_search_by_bow.restype = ci
         L.orc_bruteforce_top2.argtypes = [vp, ci, vp, C.c_int64, vp]
         L.orc_undistort_points.argtypes = [vp, ci, vp, vp]
+        L.orc_vocab_load.restype = vp
+        L.orc_vocab_load.argtypes = [vp, C.c_size_t]
+        L.orc_vocab_destroy.argtypes = [vp]
+        L.orc_vocab_info.argtypes = [vp, vp, vp, vp, vp]
+        L.orc_bow_transform.argtypes = [vp, vp, ci, ci, vp, vp, vp, vp, vp, vp]
+        L.orc_time_bow_transform.restype = C.c_double
+        L.orc_time_bow_transform.argtypes = [vp, vp, ci, ci, ci]
         L.orc_image_bounds.argtypes = [ci, ci, vp, vp]
         _lib = L
     return _lib
@@ -346,3 +353,36 @@ def image_bounds(cols, rows, cam9):
     out = np.zeros(4, np.float32)
     lib().orc_image_bounds(cols, rows, _p(cam), _p(out))
     return out
+
+
+class Vocabulary:
+    """Oracle restatement of DBoW2's TemplatedVocabulary<FORB> (load from the ORBvoc.bin layout + transform)."""
+
+    def __init__(self, blob):
+        self._blob = np.frombuffer(blob, np.uint8).copy()
+        self._h = lib().orc_vocab_load(_p(self._blob), len(self._blob))
+        if not self._h:
+            raise ValueError("bad vocabulary blob")
+        a = [C.c_int32() for _ in range(4)]
+        lib().orc_vocab_info(self._h, *[C.byref(x) for x in a])
+        self.k, self.L, self.n_nodes, self.n_words = [x.value for x in a]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_vocab_destroy(self._h)
+            self._h = None
+
+    def transform(self, desc, levelsup=4):
+        """-> (word_ids, word_values, node_ids, offsets, feats): BowVector + FeatureVector (CSR) of one frame."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        n = len(desc)
+        wid = np.zeros(n + 1, np.uint32); wv = np.zeros(n + 1, np.float64)
+        nid = np.zeros(n + 1, np.uint32); off = np.zeros(n + 2, np.int32); feats = np.zeros(n + 1, np.uint32)
+        nn = C.c_int32(0)
+        nw = lib().orc_bow_transform(self._h, _p(desc), n, int(levelsup), _p(wid), _p(wv), _p(nid), _p(off), _p(feats),
+                                     C.byref(nn))
+        return wid[:nw], wv[:nw], nid[:nn.value], off[:nn.value + 1], feats[:off[nn.value]]
+
+    def time_transform(self, desc, levelsup, iters):
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        return lib().orc_time_bow_transform(self._h, _p(desc), len(desc), int(levelsup), int(iters))
