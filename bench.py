@@ -417,6 +417,33 @@ def main():
         extras["track_step_cfg"] = ("1241x376, 4000 features: operator() from a host image + frame build + "
                                     "SearchByProjection(th=15) of 4000 last-frame points; resident = undistort/grid on the "
                                     "GPU and match in place, host_arrays = no undistortion, Frame rebuilt on the host")
+        # DBoW2 transform: Frame::ComputeBoW on the extractor's descriptors, synthetic
+        # k = 10, L = 5 vocabulary in the ORBvoc.bin layout (the real file is not shipped), levelsup = 4
+        from swarmmap_b200.bow import ORBVocabulary
+        vblob = synth.make_vocabulary(10, 5, seed=20220407)
+        voc = ORBVocabulary(vblob, device=local_rank)
+        exb = ORBextractor(NFEAT, 1.2, 8, 20, 7, device=local_rank, max_batch=64)
+        bk, bd, bn = exb.extract_batch(frames[:64])
+        for _ in range(2):
+            voc.transform_batch(bd, bn, 4)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            voc.transform_batch(bd, bn, 4)
+        t_b = (time.perf_counter() - t0) / 5
+        one = bd[0, :bn[0]]
+        for _ in range(3):
+            voc.transform(one, 4)
+        t0 = time.perf_counter()
+        for _ in range(20):
+            voc.transform(one, 4)
+        extras["bow_transform"] = {"frames_per_s_batch64": 64 / t_b, "ms_single_frame": (time.perf_counter() - t0) / 20 * 1e3,
+                                   "features_per_frame": float(bn.mean()),
+                                   "cfg": f"synthetic vocabulary k=10 L=5 ({voc.n_nodes} nodes, {voc.n_words} words), "
+                                          "host descriptors in, BowVector + FeatureVector out, levelsup 4"}
+        if not args.no_cpu_baseline:
+            import oracle_lib
+            ov = oracle_lib.Vocabulary(vblob)
+            extras["bow_transform"]["cpu_oracle_ms_single_frame"] = ov.time_transform(one, 4, 20) / 20 * 1e3
         if not args.no_cpu_baseline:
             import oracle_lib
             t0 = time.perf_counter()

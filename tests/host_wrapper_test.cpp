@@ -9,6 +9,7 @@
 #include "../swarmmap_b200/host/ORBextractor.h"
 #include "../swarmmap_b200/host/ORBmatcher.h"
 #include "../swarmmap_b200/host/ResidentFrame.h"
+#include "../swarmmap_b200/host/ORBVocabulary.h"
 
 struct Mat4 {  // stand-in for the CV_32F cv::Mat pose / position
   float v[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
@@ -150,6 +151,41 @@ int main(int argc, char** argv) {
   std::printf("resident: undistort-identity %d proj %d (host %d) same slots %d/%d bow %d (host %d)\n", (int)same_un, n_proj_res,
               n_proj, same_proj, f6.N, n_bow_res, n_bow);
   if (!same_un || n_proj_res != n_proj || same_proj != f6.N || n_bow_res != n_bow) { std::printf("HOST_WRAPPER_FAIL\n"); return 1; }
+  // Vocabulary: a two-level synthetic tree in the ORBvoc.bin layout; transform() must fill DBoW2's containers
+  {
+    const int k = 4;
+    std::vector<uint8_t> blob(24 + (size_t)(k + k * k) * 41, 0);
+    const uint32_t nb = k + k * k, sz = 41;
+    const int32_t hdr[4] = {k, 2, 0, 0};  // k, L, L1_NORM, TF_IDF
+    std::memcpy(&blob[0], &nb, 4); std::memcpy(&blob[4], &sz, 4); std::memcpy(&blob[8], hdr, 16);
+    unsigned s2 = 7;
+    for (uint32_t r = 0; r < nb; r++) {
+      uint8_t* rec = &blob[24 + (size_t)r * 41];
+      const int32_t parent = r < (uint32_t)k ? 0 : (int32_t)((r - k) / k + 1);
+      std::memcpy(rec, &parent, 4);
+      for (int b = 0; b < 32; b++) { s2 = s2 * 1664525u + 1013904223u; rec[4 + b] = (uint8_t)(s2 >> 24); }
+      const float w = 1.0f + (float)(r % 5);
+      std::memcpy(rec + 36, &w, 4);
+      rec[40] = r >= (uint32_t)k;
+    }
+    ORB_SLAM2::ORBVocabulary voc;
+    if (!voc.loadFromMemory(blob.data(), blob.size()) || voc.size() != (unsigned)(k * k)) { std::printf("HOST_WRAPPER_FAIL vocab\n"); return 1; }
+    std::vector<cv::Mat> feats;
+    for (int i = 0; i < f1.N; i++) feats.push_back(f1.mDescriptors.row(i));
+    DBoW2::BowVector bv;
+    DBoW2::FeatureVector fvv;
+    voc.transform(feats, bv, fvv, 1);
+    double sum = 0;
+    size_t nfeat = 0;
+    for (auto& e : bv) sum += e.second;
+    for (auto& e : fvv) nfeat += e.second.size();
+    std::printf("vocabulary: words %u bow entries %zu (L1 sum %.12f) nodes %zu features %zu\n", voc.size(), bv.size(), sum,
+                fvv.size(), nfeat);
+    if (bv.empty() || bv.size() > (size_t)(k * k) || fvv.size() > (size_t)k || nfeat != (size_t)f1.N || sum < 0.999999 || sum > 1.000001) {
+      std::printf("HOST_WRAPPER_FAIL vocab transform\n");
+      return 1;
+    }
+  }
   const int d0 = ORB_SLAM2::ORBmatcher::DescriptorDistance(f1.mDescriptors.row(0), f1.mDescriptors.row(0));
   const int d1 = ORB_SLAM2::ORBmatcher::DescriptorDistance(f1.mDescriptors.row(0), f1.mDescriptors.row(1));
   std::printf("init %d proj %d self %d mappoints %d bow %d bowkf %d d0 %d d1 %d\n", n_init, n_proj, self, n_mp, n_bow,
