@@ -26,4 +26,16 @@ q = torch.randint(0, 256, (300, 32), dtype=torch.uint8, device="cuda")
 s = place.PlaceShard(db, 8, 0)
 keys, votes = s.query(q, 2, 50)
 torch.cuda.synchronize()
+# resident frames + vocabulary transform
+from swarmmap_b200.matcher import Camera, ResidentFrame
+from swarmmap_b200.bow import ORBVocabulary
+cam = Camera(458.654, 457.296, 367.215, 248.375, -0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.0)
+b4 = cam.bounds(752, 480)
+ex.extract_batch(imgs[:2])
+rf = [ResidentFrame().from_extractor(ex, i, cam, b4) for i in range(2)]
+print("resident proj", m.SearchByProjectionLastFrame(rf[1], fs[0], fs[0].x, fs[0].y, np.ones(fs[0].N, np.uint8), 15)[0])
+voc = ORBVocabulary(synth.make_vocabulary(10, 3, seed=2))
+r0, r1 = voc.transform_frame(rf[0], 2), voc.transform_frame(rf[1], 2)
+print("bow words", len(r0.word_ids), "nodes", len(r0.node_ids), "batch", len(voc.transform_batch(d[:2], n[:2], 2)))
+print("resident bow", m.SearchByBoW(rf[0], r0.feature_vector(), np.ones(rf[0].N, np.uint8), rf[1], r1.feature_vector())[0])
 print("ok", int(n.sum()))
