@@ -212,6 +212,23 @@ int swm_match_bow(swm_matcher* m, const swm_frame_view* f1, const swm_featvec* f
                   const swm_frame_view* f2, const swm_featvec* fv2, const uint8_t* valid2, int mode, float nnratio,
                   int check_ori, int32_t* matches, int* nmatches);
 
+/* ORBmatcher::SearchForTriangulation (ORBmatcher.cc:599-749) with CheckDistEpipolarLine (:131-148), monocular
+ * (mvuRight < 0, bOnlyStereo = false).  The C++ wrapper computes the epipole (:605-611) and passes F12 and pKF2's
+ * level tables; valid1 / valid2 mark keypoints WITHOUT a MapPoint (:640-643, :662-666).  The reference never sets
+ * vbMatched2, so every KF1 keypoint picks independently: smallest distance <= TH_LOW among the candidates of its
+ * vocabulary node that pass the epipole-distance and epipolar-line tests, the last one on ties; then the rotation
+ * histogram prunes.  matches12 (n1): KF2 index or -1 (vMatchedPairs = the non-negative entries in index order). */
+typedef struct swm_triangulation_query {
+  const float* F12;            /* 3 x 3, row-major */
+  float ex, ey;                /* epipole of KF1's camera centre in KF2 */
+  const float* scale_factors2; /* pKF2->mvScaleFactors */
+  const float* level_sigma2;   /* pKF2->mvLevelSigma2 */
+  int32_t nlevels;
+} swm_triangulation_query;
+int swm_match_triangulation(swm_matcher* m, const swm_frame_view* f1, const swm_featvec* fv1, const uint8_t* valid1,
+                            const swm_frame_view* f2, const swm_featvec* fv2, const uint8_t* valid2,
+                            const swm_triangulation_query* q, int check_ori, int32_t* matches12, int* nmatches);
+
 /* ------------------------------------------------------------------ resident frames
  * Frame::UndistortKeyPoints (code/src/Frame.cc:454-484), ComputeImageBounds
  * (:486-514) and AssignFeaturesToGrid (:277-292, PosInGrid :427-442) on the device, so that the
@@ -251,6 +268,9 @@ int swm_match_window_resident(swm_matcher* m, const swm_frame* tgt, const swm_wi
 int swm_match_bow_resident(swm_matcher* m, const swm_frame* f1, const swm_featvec* fv1, const uint8_t* valid1,
                            const swm_frame* f2, const swm_featvec* fv2, const uint8_t* valid2, int mode, float nnratio,
                            int check_ori, int32_t* matches, int* nmatches);
+int swm_match_triangulation_resident(swm_matcher* m, const swm_frame* f1, const swm_featvec* fv1, const uint8_t* valid1,
+                                     const swm_frame* f2, const swm_featvec* fv2, const uint8_t* valid2,
+                                     const swm_triangulation_query* q, int check_ori, int32_t* matches12, int* nmatches);
 
 /* ------------------------------------------------------------------ DBoW2 transform
  * TemplatedVocabulary<FORB>::transform(features, BowVector&, FeatureVector&, levelsup)

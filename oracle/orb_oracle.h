@@ -138,6 +138,16 @@ int orc_search_by_bow(const orc_frame* f1, const orc_featvec* fv1, const uint8_t
                       const orc_featvec* fv2, const uint8_t* valid2, int mode, float nnratio, int check_ori,
                       int32_t* matches /* mode 0: size n2 -> idx1 or -1; mode 1: size n1 -> idx2 or -1 */);
 
+/* ORBmatcher::SearchForTriangulation (:599-749), monocular (mvuRight < 0, bOnlyStereo = false), with
+ * CheckDistEpipolarLine (:131-148).  valid1 / valid2: 1 = the keypoint has no MapPoint yet (:640-643, :662-666).
+ * F12: 3x3 row-major; (ex, ey): epipole of KF1's centre in KF2 (:605-611); scale_factors2 / level_sigma2: pKF2's
+ * tables.  Note the reference never sets vbMatched2, so rows are independent.  Float expressions are evaluated
+ * left to right without contraction.  matches12: n1 entries (idx2 or -1).  Returns nmatches. */
+int orc_search_for_triangulation(const orc_frame* f1, const orc_featvec* fv1, const uint8_t* valid1, const orc_frame* f2,
+                                 const orc_featvec* fv2, const uint8_t* valid2, const float* F12, float ex, float ey,
+                                 const float* scale_factors2, const float* level_sigma2, int check_ori,
+                                 int32_t* matches12);
+
 /* Brute-force top-2 of each query against a descriptor database (config 5). out: per query
  * (dist0, idx0, dist1, idx1); ties broken by lower index. */
 void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int32_t* out4);

@@ -311,6 +311,77 @@ int orc_search_by_bow(const orc_frame* f1, const orc_featvec* fv1, const uint8_t
   return nmatches;
 }
 
+// CheckDistEpipolarLine, :131-148
+static bool check_dist_epipolar_line(float x1, float y1, float x2, float y2, int octave2, const float* F12,
+                                     const float* level_sigma2) {
+  const float a = x1 * F12[0] + y1 * F12[3] + F12[6];
+  const float b = x1 * F12[1] + y1 * F12[4] + F12[7];
+  const float c = x1 * F12[2] + y1 * F12[5] + F12[8];
+  const float num = a * x2 + b * y2 + c;
+  const float den = a * a + b * b;
+  if (den == 0) return false;
+  const float dsqr = num * num / den;
+  return dsqr < 3.84 * level_sigma2[octave2];
+}
+
+// ORBmatcher::SearchForTriangulation, :599-749 (monocular)
+int orc_search_for_triangulation(const orc_frame* f1, const orc_featvec* fv1, const uint8_t* valid1, const orc_frame* f2,
+                                 const orc_featvec* fv2, const uint8_t* valid2, const float* F12, float ex, float ey,
+                                 const float* scale_factors2, const float* level_sigma2, int check_ori,
+                                 int32_t* matches12) {
+  int nmatches = 0;
+  for (int i = 0; i < f1->n; i++) matches12[i] = -1;
+  std::vector<std::vector<int>> rot_hist(HISTO_LENGTH);
+  int a = 0, b = 0;
+  while (a < fv1->n_nodes && b < fv2->n_nodes) {
+    if (fv1->node_ids[a] == fv2->node_ids[b]) {
+      for (int i1 = fv1->offsets[a]; i1 < fv1->offsets[a + 1]; i1++) {
+        const uint32_t idx1 = fv1->feats[i1];
+        if (!valid1[idx1]) continue;  // already a MapPoint
+        const uint8_t* d1 = f1->desc + (size_t)idx1 * 32;
+        int best_dist = TH_LOW, best_idx2 = -1;
+        for (int i2 = fv2->offsets[b]; i2 < fv2->offsets[b + 1]; i2++) {
+          const uint32_t idx2 = fv2->feats[i2];
+          if (!valid2[idx2]) continue;  // vbMatched2 is never set in the reference; pMP2 != NULL
+          const int dist = dist256(d1, f2->desc + (size_t)idx2 * 32);
+          if (dist > TH_LOW || dist > best_dist) continue;
+          const float distex = ex - f2->x[idx2];
+          const float distey = ey - f2->y[idx2];
+          if (distex * distex + distey * distey < 100 * scale_factors2[f2->octave[idx2]]) continue;
+          if (check_dist_epipolar_line(f1->x[idx1], f1->y[idx1], f2->x[idx2], f2->y[idx2], f2->octave[idx2], F12,
+                                       level_sigma2)) {
+            best_idx2 = (int)idx2;
+            best_dist = dist;
+          }
+        }
+        if (best_idx2 >= 0) {
+          matches12[idx1] = best_idx2;
+          nmatches++;
+          if (check_ori) rot_hist[rot_bin(f1->angle[idx1], f2->angle[best_idx2])].push_back((int)idx1);
+        }
+      }
+      a++;
+      b++;
+    } else if (fv1->node_ids[a] < fv2->node_ids[b]) {
+      a = (int)(std::lower_bound(fv1->node_ids, fv1->node_ids + fv1->n_nodes, fv2->node_ids[b]) - fv1->node_ids);
+    } else {
+      b = (int)(std::lower_bound(fv2->node_ids, fv2->node_ids + fv2->n_nodes, fv1->node_ids[a]) - fv2->node_ids);
+    }
+  }
+  if (check_ori) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rot_hist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx : rot_hist[i]) {
+        matches12[idx] = -1;
+        nmatches--;
+      }
+    }
+  }
+  return nmatches;
+}
+
 // Brute-force top-2 (config 5): ties broken by the lower database index.
 void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int32_t* out4) {
   for (int i = 0; i < nq; i++) {

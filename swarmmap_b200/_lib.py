@@ -48,6 +48,11 @@ class Camera(C.Structure):
                 ("k1", C.c_float), ("k2", C.c_float), ("p1", C.c_float), ("p2", C.c_float), ("k3", C.c_float)]
 
 
+class TriangulationQuery(C.Structure):
+    _fields_ = [("F12", C.c_void_p), ("ex", C.c_float), ("ey", C.c_float), ("scale_factors2", C.c_void_p),
+                ("level_sigma2", C.c_void_p), ("nlevels", C.c_int32)]
+
+
 class BowOut(C.Structure):
     _fields_ = [("word_ids", C.c_void_p), ("word_values", C.c_void_p), ("n_words", C.c_void_p),
                 ("node_ids", C.c_void_p), ("node_offsets", C.c_void_p), ("feats", C.c_void_p), ("n_nodes", C.c_void_p)]
@@ -88,6 +93,8 @@ SYMBOLS = [
     ("swm_match_init", _i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp]),
     ("swm_match_window", _i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp]),
     ("swm_match_bow", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp]),
+    ("swm_match_triangulation", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    ("swm_match_triangulation_resident", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     ("swm_camera_bounds", _i, [_i, _vp, _i, _i, _vp]),
     ("swm_frame_create", _i, [_i, _vp]),
     ("swm_frame_destroy", None, [_vp]),

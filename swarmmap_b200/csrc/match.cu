@@ -660,6 +660,120 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
 }
 
 // ---------------------------------------------------------------------------------------------
+// SearchForTriangulation (ORBmatcher.cc:599-749, monocular) with CheckDistEpipolarLine (:131-148).  The reference
+// never sets vbMatched2, so the rows are independent: warp per row, the winner is the candidate of smallest distance
+// among those that pass the epipole and epipolar-line tests, the LAST one on ties ("dist > bestDist -> continue").
+// Float expressions are evaluated left to right with explicit round-to-nearest operations (no FMA contraction).
+// ---------------------------------------------------------------------------------------------
+struct TriDev {
+  float F[9];
+  float ex, ey;
+  const float* sf2;     // pKF2->mvScaleFactors
+  const float* sigma2;  // pKF2->mvLevelSigma2
+};
+
+__global__ void __launch_bounds__(256) tri_rows_kernel(FrameDev f1, FrameDev f2, const uint8_t* __restrict__ valid2, int rows,
+                                                       const int32_t* __restrict__ row_src,
+                                                       const int32_t* __restrict__ row_start,
+                                                       const int32_t* __restrict__ cand_idx, TriDev t, int check_ori,
+                                                       int32_t* __restrict__ out, int32_t* __restrict__ ev_bin) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int s = row_src[r];
+  const uint4 d0 = __ldg(f1.desc + 2 * s), d1 = __ldg(f1.desc + 2 * s + 1);
+  const float x1 = f1.x[s], y1 = f1.y[s];
+  // l = x1' F12 = [a b c]  (:134-136)
+  const float a = __fadd_rn(__fadd_rn(__fmul_rn(x1, t.F[0]), __fmul_rn(y1, t.F[3])), t.F[6]);
+  const float b = __fadd_rn(__fadd_rn(__fmul_rn(x1, t.F[1]), __fmul_rn(y1, t.F[4])), t.F[7]);
+  const float c = __fadd_rn(__fadd_rn(__fmul_rn(x1, t.F[2]), __fmul_rn(y1, t.F[5])), t.F[8]);
+  const float den = __fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b));
+  unsigned long long best = ~0ull;
+  const int c0 = row_start[r];
+  for (int ci = c0 + lane; ci < row_start[r + 1]; ci += 32) {
+    const int j = cand_idx[ci];
+    if (!valid2[j]) continue;  // pMP2 (:662-666)
+    const int dist = ham256(d0, d1, f2.desc + 2 * j);
+    if (dist > kThLow) continue;  // :674
+    const float x2 = f2.x[j], y2 = f2.y[j];
+    const int oct = f2.octave[j];
+    const float dex = __fsub_rn(t.ex, x2), dey = __fsub_rn(t.ey, y2);  // :679-683
+    if (__fadd_rn(__fmul_rn(dex, dex), __fmul_rn(dey, dey)) < __fmul_rn(100.0f, t.sf2[oct])) continue;
+    const float num = __fadd_rn(__fadd_rn(__fmul_rn(a, x2), __fmul_rn(b, y2)), c);
+    if (den == 0.0f) continue;
+    const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+    if (!((double)dsqr < __dmul_rn(3.84, (double)t.sigma2[oct]))) continue;  // :147
+    const unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(0x7FFFFFFF - (ci - c0));
+    best = best < key ? best : key;
+  }
+  best = warp_min_u64(best);
+  if (lane == 0) {
+    int j = -1, bin = -1;
+    if (best != ~0ull) {
+      j = cand_idx[c0 + (0x7FFFFFFF - (int)(unsigned)best)];
+      if (check_ori) bin = rot_bin(f1.angle[s], f2.angle[j]);
+    }
+    out[s] = j;
+    ev_bin[s] = bin;
+  }
+}
+
+// nmatches, rotation histogram, ComputeThreeMaxima, pruning (:724-738).  One CTA.
+__global__ void __launch_bounds__(1024) tri_finalize_kernel(int n1, int32_t* __restrict__ out, const int32_t* __restrict__ ev_bin,
+                                                            int check_ori, int32_t* __restrict__ nmatches) {
+  __shared__ int s_hist[kHistoLen];
+  __shared__ int s_keep[3];
+  __shared__ int s_n;
+  const int tid = threadIdx.x;
+  if (tid < kHistoLen) s_hist[tid] = 0;
+  if (tid == 0) s_n = 0;
+  __syncthreads();
+  int mine = 0;
+  for (int s = tid; s < n1; s += 1024) {
+    if (out[s] >= 0) mine++;
+    if (check_ori && ev_bin[s] >= 0) atomicAdd(&s_hist[ev_bin[s]], 1);
+  }
+  if (mine) atomicAdd(&s_n, mine);
+  __syncthreads();
+  if (check_ori) {
+    if (tid == 0) {  // ComputeThreeMaxima, :1475-1506
+      int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+      for (int i = 0; i < kHistoLen; i++) {
+        const int cnt = s_hist[i];
+        if (cnt > max1) {
+          max3 = max2; max2 = max1; max1 = cnt;
+          ind3 = ind2; ind2 = ind1; ind1 = i;
+        } else if (cnt > max2) {
+          max3 = max2; max2 = cnt;
+          ind3 = ind2; ind2 = i;
+        } else if (cnt > max3) {
+          max3 = cnt;
+          ind3 = i;
+        }
+      }
+      if ((float)max2 < 0.1f * (float)max1) {
+        ind2 = -1;
+        ind3 = -1;
+      } else if ((float)max3 < 0.1f * (float)max1) {
+        ind3 = -1;
+      }
+      s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+    }
+    __syncthreads();
+    int dropped = 0;
+    for (int s = tid; s < n1; s += 1024) {
+      const int bin = ev_bin[s];
+      if (bin < 0 || bin == s_keep[0] || bin == s_keep[1] || bin == s_keep[2]) continue;
+      out[s] = -1;
+      dropped++;
+    }
+    if (dropped) atomicSub(&s_n, dropped);
+    __syncthreads();
+  }
+  if (tid == 0) nmatches[0] = s_n;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Place-recognition shard (BASELINE config 5): brute-force top-2 of each query over the shard.
 // Each thread owns one query (descriptor in registers); the CTA streams database tiles through
 // shared memory (broadcast reads), keeping a running top-2 of packed keys dist<<48 | global index.
@@ -1449,17 +1563,13 @@ int match_window_impl(swm_matcher* m, const FrameSrc& tgt, const swm_window_quer
   return SWM_OK;
 }
 
-int match_bow_impl(swm_matcher* m, const FrameSrc& f1, const swm_featvec* fv1, const uint8_t* valid1, const FrameSrc& f2,
-                   const swm_featvec* fv2, const uint8_t* valid2, int mode, float nnratio, int check_ori, int32_t* matches,
-                   int* nmatches) {
-  *nmatches = 0;
-  const int n1 = f1.n(), n2 = f2.n();
-  const int n_out = mode == 0 ? n2 : n1;
-  for (int i = 0; i < n_out; i++) matches[i] = -1;
-  if (n1 == 0 || n2 == 0) return SWM_OK;
-  // merge-walk the two sorted FeatureVectors (:166-241 / :507-581); rows = valid side-1 features of
-  // shared nodes in visiting order, candidates = side-2 features of the node.
-  std::vector<int32_t> row_src, row_start(1, 0), cand;
+// Merge-walk of two sorted FeatureVectors (ORBmatcher.cc:166-241, :507-581, :629-722): rows = the valid side-1
+// features of shared nodes in visiting order, candidates = the side-2 features of the node.
+int node_rows(swm_matcher* m, const swm_featvec* fv1, const uint8_t* valid1, int n1, const swm_featvec* fv2, int n2,
+              std::vector<int32_t>& row_src, std::vector<int32_t>& row_start, std::vector<int32_t>& cand) {
+  row_src.clear();
+  cand.clear();
+  row_start.assign(1, 0);
   int a = 0, b = 0;
   while (a < fv1->n_nodes && b < fv2->n_nodes) {
     const uint32_t ia = fv1->node_ids[a], ib = fv2->node_ids[b];
@@ -1482,6 +1592,22 @@ int match_bow_impl(swm_matcher* m, const FrameSrc& f1, const swm_featvec* fv1, c
     } else {
       b = (int)(std::lower_bound(fv2->node_ids, fv2->node_ids + fv2->n_nodes, ia) - fv2->node_ids);
     }
+  }
+  return SWM_OK;
+}
+
+int match_bow_impl(swm_matcher* m, const FrameSrc& f1, const swm_featvec* fv1, const uint8_t* valid1, const FrameSrc& f2,
+                   const swm_featvec* fv2, const uint8_t* valid2, int mode, float nnratio, int check_ori, int32_t* matches,
+                   int* nmatches) {
+  *nmatches = 0;
+  const int n1 = f1.n(), n2 = f2.n();
+  const int n_out = mode == 0 ? n2 : n1;
+  for (int i = 0; i < n_out; i++) matches[i] = -1;
+  if (n1 == 0 || n2 == 0) return SWM_OK;
+  std::vector<int32_t> row_src, row_start, cand;
+  {
+    const int wrc = node_rows(m, fv1, valid1, n1, fv2, n2, row_src, row_start, cand);
+    if (wrc != SWM_OK) return wrc;
   }
   const int R = (int)row_src.size();
   if (R == 0) return SWM_OK;
@@ -1533,6 +1659,59 @@ int match_bow_impl(swm_matcher* m, const FrameSrc& f1, const swm_featvec* fv1, c
   MCK(m, cudaMemcpyAsync(nmatches, ra.nmatches, 4, cudaMemcpyDeviceToHost, m->stream));
   MCK(m, cudaStreamSynchronize(m->stream));
   return SWM_OK;
+}
+
+int match_triangulation_impl(swm_matcher* m, const FrameSrc& f1, const swm_featvec* fv1, const uint8_t* valid1,
+                             const FrameSrc& f2, const swm_featvec* fv2, const uint8_t* valid2,
+                             const swm_triangulation_query* q, int check_ori, int32_t* matches12, int* nmatches) {
+  *nmatches = 0;
+  const int n1 = f1.n(), n2 = f2.n();
+  for (int i = 0; i < n1; i++) matches12[i] = -1;
+  if (n1 == 0 || n2 == 0) return SWM_OK;
+  std::vector<int32_t> row_src, row_start, cand;
+  int rc = node_rows(m, fv1, valid1, n1, fv2, n2, row_src, row_start, cand);
+  if (rc != SWM_OK) return rc;
+  const int R = (int)row_src.size();
+  if (R == 0) return SWM_OK;
+  MCK(m, cudaSetDevice(m->device));
+  FrameDev d1, d2;
+  const size_t nl = (size_t)q->nlevels;
+  if ((rc = arena_begin(m, src_bytes(f1) + src_bytes(f2) + (size_t)R * 8 + cand.size() * 4 + (size_t)n2 + nl * 8 + 10 * 256))) return rc;
+  if ((rc = acquire_frame(m, 0, f1, &d1))) return rc;
+  if ((rc = acquire_frame(m, 1, f2, &d2))) return rc;
+  if ((rc = upload(m, m->rows[4], row_src.data(), (size_t)R * 4))) return rc;
+  if ((rc = upload(m, m->rows[1], row_start.data(), (size_t)(R + 1) * 4))) return rc;
+  if ((rc = upload(m, m->rows[2], cand.data(), cand.size() * 4))) return rc;
+  if ((rc = upload(m, m->q[4], valid2, (size_t)n2))) return rc;
+  if ((rc = upload(m, m->q[0], q->scale_factors2, nl * 4))) return rc;
+  if ((rc = upload(m, m->q[1], q->level_sigma2, nl * 4))) return rc;
+  if ((rc = arena_flush(m))) return rc;
+  MCK(m, m->state[3].ensure((size_t)n1 * 4));
+  MCK(m, m->state[4].ensure((size_t)n1 * 4));
+  MCK(m, m->state[6].ensure(16));
+  MCK(m, cudaMemsetAsync(m->state[3].p, 0xFF, (size_t)n1 * 4, m->stream));
+  MCK(m, cudaMemsetAsync(m->state[4].p, 0xFF, (size_t)n1 * 4, m->stream));
+  TriDev t;
+  for (int i = 0; i < 9; i++) t.F[i] = q->F12[i];
+  t.ex = q->ex;
+  t.ey = q->ey;
+  t.sf2 = m->q[0].as<float>();
+  t.sigma2 = m->q[1].as<float>();
+  tri_rows_kernel<<<(R + 7) / 8, 256, 0, m->stream>>>(d1, d2, m->q[4].as<uint8_t>(), R, m->rows[4].as<int32_t>(),
+                                                      m->rows[1].as<int32_t>(), m->rows[2].as<int32_t>(), t, check_ori,
+                                                      m->state[3].as<int32_t>(), m->state[4].as<int32_t>());
+  MCK(m, cudaGetLastError());
+  tri_finalize_kernel<<<1, 1024, 0, m->stream>>>(n1, m->state[3].as<int32_t>(), m->state[4].as<int32_t>(), check_ori,
+                                                 m->state[6].as<int32_t>());
+  MCK(m, cudaGetLastError());
+  MCK(m, cudaMemcpyAsync(matches12, m->state[3].p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
+  MCK(m, cudaMemcpyAsync(nmatches, m->state[6].p, 4, cudaMemcpyDeviceToHost, m->stream));
+  MCK(m, cudaStreamSynchronize(m->stream));
+  return SWM_OK;
+}
+
+bool tri_query_ok(const swm_triangulation_query* q) {
+  return q && q->F12 && q->scale_factors2 && q->level_sigma2 && q->nlevels > 0 && q->nlevels <= SWM_MAX_LEVELS;
 }
 
 }  // namespace
@@ -1603,6 +1782,30 @@ int swm_match_bow_resident(swm_matcher* m, const swm_frame* f1, const swm_featve
   }
   return match_bow_impl(m, FrameSrc{nullptr, f1}, fv1, valid1, FrameSrc{nullptr, f2}, fv2, valid2, mode, nnratio, check_ori,
                         matches, nmatches);
+}
+
+int swm_match_triangulation(swm_matcher* m, const swm_frame_view* f1, const swm_featvec* fv1, const uint8_t* valid1,
+                            const swm_frame_view* f2, const swm_featvec* fv2, const uint8_t* valid2,
+                            const swm_triangulation_query* q, int check_ori, int32_t* matches12, int* nmatches) {
+  if (!m) return SWM_E_INVALID;
+  if (!frame_ok(f1) || !frame_ok(f2) || !fv1 || !fv2 || !valid1 || !valid2 || !tri_query_ok(q) || !matches12 || !nmatches) {
+    m->err = "bad argument";
+    return SWM_E_INVALID;
+  }
+  return match_triangulation_impl(m, FrameSrc{f1, nullptr}, fv1, valid1, FrameSrc{f2, nullptr}, fv2, valid2, q, check_ori,
+                                  matches12, nmatches);
+}
+
+int swm_match_triangulation_resident(swm_matcher* m, const swm_frame* f1, const swm_featvec* fv1, const uint8_t* valid1,
+                                     const swm_frame* f2, const swm_featvec* fv2, const uint8_t* valid2,
+                                     const swm_triangulation_query* q, int check_ori, int32_t* matches12, int* nmatches) {
+  if (!m) return SWM_E_INVALID;
+  if (!f1 || !f2 || !fv1 || !fv2 || !valid1 || !valid2 || !tri_query_ok(q) || !matches12 || !nmatches) {
+    m->err = "bad argument";
+    return SWM_E_INVALID;
+  }
+  return match_triangulation_impl(m, FrameSrc{nullptr, f1}, fv1, valid1, FrameSrc{nullptr, f2}, fv2, valid2, q, check_ori,
+                                  matches12, nmatches);
 }
 
 // ------------------------------------------------------------------------------ resident frames

@@ -320,6 +320,56 @@ class ORBmatcher {
     return n;
   }
 
+  // ---- Matching to triangulate new MapPoints, with the epipolar constraint (ORBmatcher.cc:599-749), monocular.
+  // F12 is the 3x3 CV_32F fundamental matrix LocalMapping::ComputeF12 builds.  The stereo branches need mvuRight >= 0
+  // and are not served (bOnlyStereo must be false; SwarmMap is monocular).
+  template <class KeyFrameT, class MatT>
+  int SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, const MatT& F12,
+                             std::vector<std::pair<size_t, size_t>>& vMatchedPairs, const bool bOnlyStereo) {
+    if (bOnlyStereo) throw std::runtime_error("ORBmatcher::SearchForTriangulation: stereo-only mode not supported (monocular SwarmMap)");
+    // epipole in the second image (:605-611): C2 = R2w * Cw + t2w, products of CV_32F accumulate in double
+    float Cw[3], R2w[9], t2w[3], C2[3];
+    world_pos(pKF1->GetCameraCenter(), Cw);
+    const auto R = pKF2->GetRotation();
+    const auto t = pKF2->GetTranslation();
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) R2w[3 * r + c] = R.template at<float>(r, c);
+      t2w[r] = t.template at<float>(r);
+    }
+    transform(R2w, t2w, Cw, C2);
+    const float invz = 1.0f / C2[2];
+    swm_triangulation_query q;
+    float F[9];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) F[3 * r + c] = F12.template at<float>(r, c);
+    q.F12 = F;
+    q.ex = pKF2->fx * C2[0] * invz + pKF2->cx;
+    q.ey = pKF2->fy * C2[1] * invz + pKF2->cy;
+    q.scale_factors2 = pKF2->mvScaleFactors.data();
+    q.level_sigma2 = pKF2->mvLevelSigma2.data();
+    q.nlevels = (int32_t)pKF2->mvScaleFactors.size();
+    FlatFrame a, b;
+    const bool res = resident_of(*pKF1, 0) && resident_of(*pKF2, 0);
+    gather(*pKF1, a, res);
+    gather(*pKF2, b, res);
+    std::vector<uint8_t> v1(a.n, 0), v2(b.n, 0);
+    for (int i = 0; i < a.n; i++) v1[i] = pKF1->GetMapPoint(i) == nullptr;  // :640-643
+    for (int i = 0; i < b.n; i++) v2[i] = pKF2->GetMapPoint(i) == nullptr;  // :662-666
+    FlatFeatVec fa(pKF1->mFeatVec), fb(pKF2->mFeatVec);
+    std::vector<int32_t> out(a.n, -1);
+    int n = 0;
+    swm_frame_view va = a.view(), vb = b.view();
+    swm_featvec ga = fa.view(), gb = fb.view();
+    check(res ? swm_match_triangulation_resident(m_, resident_of(*pKF1, 0), &ga, v1.data(), resident_of(*pKF2, 0), &gb,
+                                                 v2.data(), &q, mbCheckOrientation, out.data(), &n)
+              : swm_match_triangulation(m_, &va, &ga, v1.data(), &vb, &gb, v2.data(), &q, mbCheckOrientation, out.data(), &n));
+    vMatchedPairs.clear();
+    vMatchedPairs.reserve(n);
+    for (int i = 0; i < a.n; i++)
+      if (out[i] >= 0) vMatchedPairs.push_back(std::make_pair((size_t)i, (size_t)out[i]));  // :743-747
+    return n;
+  }
+
  protected:
   struct FlatFrame {
     int n = 0;

@@ -322,6 +322,36 @@ class ORBmatcher:
         return n.value, out
 
 
+def _search_for_triangulation(self, KF1, fv1, no_mp1, KF2, fv2, no_mp2, F12, ex, ey, scale_factors2, level_sigma2):
+    """SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo=false), ORBmatcher.cc:599-749 (monocular).
+    no_mp1 / no_mp2: 1 where the keypoint has no MapPoint yet; (ex, ey): epipole of KF1's centre in KF2 (:605-611).
+    Returns (nmatches, vMatches12); vMatchedPairs = [(i, m) for i, m in enumerate(vMatches12) if m >= 0]."""
+    from ._lib import TriangulationQuery
+    v1 = np.ascontiguousarray(no_mp1, np.uint8)
+    v2 = np.ascontiguousarray(no_mp2, np.uint8)
+    F = np.ascontiguousarray(F12, np.float32).reshape(9)
+    sf = np.ascontiguousarray(scale_factors2, np.float32)
+    s2 = np.ascontiguousarray(level_sigma2, np.float32)
+    q = TriangulationQuery(ptr(F).value, float(ex), float(ey), ptr(sf).value, ptr(s2).value, len(sf))
+    out = np.full(KF1.N, -1, np.int32)
+    n = C.c_int(0)
+    fa, fb = fv1.view(), fv2.view()
+    if isinstance(KF1, ResidentFrame) != isinstance(KF2, ResidentFrame):
+        raise TypeError("both keyframes must be resident or both host-side")
+    if isinstance(KF1, ResidentFrame):
+        rc = self._lib.swm_match_triangulation_resident(self._h, KF1._h, C.byref(fa), ptr(v1), KF2._h, C.byref(fb), ptr(v2),
+                                                        C.byref(q), int(self.mbCheckOrientation), ptr(out), C.byref(n))
+    else:
+        a, b = KF1.view(), KF2.view()
+        rc = self._lib.swm_match_triangulation(self._h, C.byref(a), C.byref(fa), ptr(v1), C.byref(b), C.byref(fb), ptr(v2),
+                                               C.byref(q), int(self.mbCheckOrientation), ptr(out), C.byref(n))
+    self._check(rc, "swm_match_triangulation")
+    return n.value, out
+
+
+ORBmatcher.SearchForTriangulation = _search_for_triangulation
+
+
 def smoke(kps, desc):
     """Tiny matcher call for __graft_entry__.smoke(): match a frame against itself."""
     f = Frame.from_keypoints(kps, desc, 752, 480)

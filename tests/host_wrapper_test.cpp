@@ -53,6 +53,13 @@ struct Frame {
   std::map<unsigned, std::vector<unsigned>> mFeatVec;
   const swm_frame* mpResident = nullptr;  // set when the features also live on the device (host/ResidentFrame.h)
   std::vector<MapPoint*> GetMapPointMatches() { return mvpMapPoints; }
+  // KeyFrame accessors used by SearchForTriangulation
+  std::vector<float> mvLevelSigma2;
+  Mat4 mOw, mRcw, mtcw;
+  MapPoint* GetMapPoint(int i) { return mvpMapPoints[i]; }
+  Mat4 GetCameraCenter() { return mOw; }
+  Mat4 GetRotation() { return mRcw; }
+  Mat4 GetTranslation() { return mtcw; }
 };
 
 static void fill(Frame& f, ORB_SLAM2::ORBextractor& ex, const cv::Mat& img) {
@@ -185,6 +192,28 @@ int main(int argc, char** argv) {
       std::printf("HOST_WRAPPER_FAIL vocab transform\n");
       return 1;
     }
+  }
+  // SearchForTriangulation: two keyframes of the same image, a fundamental matrix for a sideways translation; every
+  // keypoint lies on its own epipolar line (identical images), the epipole is far outside the image
+  {
+    Frame k1, k2;
+    fill(k1, ex, img);
+    fill(k2, ex, img);
+    k2.mvLevelSigma2 = ex.GetScaleSigmaSquares();
+    k1.mOw.v[0] = 1.0f; k1.mOw.v[1] = 0.0f; k1.mOw.v[2] = 0.0f;  // camera centre of KF1 in the world
+    k2.mtcw.v[0] = 0.0f; k2.mtcw.v[1] = 0.0f; k2.mtcw.v[2] = 0.001f;
+    // pure x-translation: F = K^-T [t]x K^-1 with t = (1, 0, 0): the epipolar line of (u, v) is the row v
+    Mat4 F;
+    for (int i = 0; i < 16; i++) F.v[i] = 0;
+    F.v[1 * 4 + 2] = -1.0f / Frame::fy;           // F(1,2)
+    F.v[2 * 4 + 1] = 1.0f / Frame::fy;            // F(2,1)
+    std::vector<std::pair<size_t, size_t>> pairs;
+    ORB_SLAM2::ORBmatcher mt(0.6f, false);
+    const int n_tri = mt.SearchForTriangulation(&k1, &k2, F, pairs, false);
+    int self_tri = 0;
+    for (auto& p : pairs) self_tri += p.first == p.second;
+    std::printf("triangulation: %d pairs, %d on the same keypoint of the identical image\n", n_tri, self_tri);
+    if (n_tri != (int)pairs.size() || n_tri < k1.N / 2 || self_tri < n_tri * 9 / 10) { std::printf("HOST_WRAPPER_FAIL triangulation\n"); return 1; }
   }
   const int d0 = ORB_SLAM2::ORBmatcher::DescriptorDistance(f1.mDescriptors.row(0), f1.mDescriptors.row(0));
   const int d1 = ORB_SLAM2::ORBmatcher::DescriptorDistance(f1.mDescriptors.row(0), f1.mDescriptors.row(1));

@@ -332,6 +332,24 @@ def search_by_bow(f1, fv1, valid1, f2, fv2, valid2, mode, nnratio, check_ori):
     return n, out
 
 
+def search_for_triangulation(f1, fv1, valid1, f2, fv2, valid2, F12, ex, ey, scale_factors2, level_sigma2, check_ori):
+    a, k1 = _frame(f1)
+    b, k2 = _frame(f2)
+    v1 = np.ascontiguousarray(valid1, np.uint8)
+    v2 = np.ascontiguousarray(valid2, np.uint8)
+    fa = FeatVec(len(fv1.node_ids), _p(fv1.node_ids).value, _p(fv1.offsets).value, _p(fv1.feats).value)
+    fb = FeatVec(len(fv2.node_ids), _p(fv2.node_ids).value, _p(fv2.offsets).value, _p(fv2.feats).value)
+    F = np.ascontiguousarray(F12, np.float32).reshape(9)
+    sf = np.ascontiguousarray(scale_factors2, np.float32)
+    s2 = np.ascontiguousarray(level_sigma2, np.float32)
+    out = np.full(f1.N, -1, np.int32)
+    fn = lib().orc_search_for_triangulation
+    fn.argtypes = [C.c_void_p] * 7 + [C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    n = fn(C.byref(a), C.byref(fa), _p(v1), C.byref(b), C.byref(fb), _p(v2), _p(F), float(ex), float(ey), _p(sf), _p(s2),
+           int(check_ori), _p(out))
+    return n, out
+
+
 def bruteforce_top2(q, db):
     q = np.ascontiguousarray(q, np.uint8)
     db = np.ascontiguousarray(db, np.uint8)

@@ -199,6 +199,45 @@ def test_search_by_bow(oracle, swm, frames, mode, ratio):
     assert n == 0 and (out == -1).all()
 
 
+def _fundamental(dx, dy, fx=458.654, fy=457.296, cx=367.215, cy=248.375):
+    """F12 for a pure translation (tx, ty, tz) between two views of the same camera: x2' F12' ... built the way
+    LocalMapping::ComputeF12 does (K^-T [t]x R K^-1), float32."""
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1]], np.float64)
+    t = np.array([dx, dy, 0.02])
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    Ki = np.linalg.inv(K)
+    return (Ki.T @ tx @ Ki).astype(np.float32)
+
+
+@pytest.mark.parametrize("check_ori", [True, False])
+@pytest.mark.parametrize("name", ["euroc", "kitti"])
+def test_search_for_triangulation(oracle, swm, frames, name, check_ori):
+    """SearchForTriangulation (ORBmatcher.cc:599-749): match indices and count bit-exact against the oracle, host
+    arrays and resident frames, with MapPoint masks on both sides and an epipole inside the image."""
+    from swarmmap_b200.matcher import FeatureVector, ORBmatcher, ResidentFrame
+    f1, f2 = frames[name][0], frames[name][1]
+    rng = np.random.default_rng(7)
+    fv1 = FeatureVector(_buckets(f1.desc, 5, 40))
+    fv2 = FeatureVector(_buckets(f2.desc, 5, 40))
+    v1 = (rng.random(f1.N) < 0.7).astype(np.uint8)
+    v2 = (rng.random(f2.N) < 0.8).astype(np.uint8)
+    F12 = _fundamental(0.3, 0.05)
+    sf, _, s2, _ = oracle.scale_tables(1.2, 8)
+    ex, ey = 400.0, 200.0
+    m = ORBmatcher(0.6, check_ori)
+    n, out = m.SearchForTriangulation(f1, fv1, v1, f2, fv2, v2, F12, ex, ey, sf, s2)
+    rn, rout = oracle.search_for_triangulation(f1, fv1, v1, f2, fv2, v2, F12, ex, ey, sf, s2, check_ori)
+    assert n == rn and n > 5, (n, rn)
+    np.testing.assert_array_equal(out, rout)
+    r1, r2 = ResidentFrame().upload(f1), ResidentFrame().upload(f2)
+    n2, out2 = m.SearchForTriangulation(r1, fv1, v1, r2, fv2, v2, F12, ex, ey, sf, s2)
+    assert n2 == rn
+    np.testing.assert_array_equal(out2, rout)
+    # nothing to match: all KF1 keypoints already have MapPoints
+    n3, out3 = m.SearchForTriangulation(f1, fv1, np.zeros(f1.N, np.uint8), f2, fv2, v2, F12, ex, ey, sf, s2)
+    assert n3 == 0 and (out3 == -1).all()
+
+
 def _db_case(rng, nq, ndb):
     q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
     db = rng.integers(0, 256, (ndb, 32), dtype=np.uint8)
