@@ -136,6 +136,13 @@ int swm_hamming_matrix_device(const uint8_t* d_a, int na, const uint8_t* d_b, in
 int swm_hamming_matrix(const uint8_t* a, int na, const uint8_t* b, int nb, uint16_t* out, int device);
 /* Element-wise pairs: out[i] = dist(a[i], b[i]). */
 int swm_hamming_pairs(const uint8_t* a, const uint8_t* b, int n, int32_t* out, int device);
+/* MapPoint::ComputeDistinctiveDescriptors (code/src/MapPoint.cc:361-391) for a batch of MapPoints: point p owns the
+ * descriptors desc[offsets[p] .. offsets[p+1]) (its observations, in the std::map<KeyFrame*, size_t> iteration order
+ * the caller gathered them in; at most 1024 per point).  best_idx[p]: index inside the point of the descriptor with
+ * the least median distance to the others (median = sorted[int(0.5 * (N - 1))], first minimum wins), -1 for an
+ * empty point; best_median (may be NULL) that median. */
+int swm_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best_idx,
+                                int32_t* best_median, int device);
 
 /* ------------------------------------------------------------------ matchers (flat POD views) */
 /* One frame's features as the matchers see them (host pointers). */

@@ -148,6 +148,11 @@ int orc_search_for_triangulation(const orc_frame* f1, const orc_featvec* fv1, co
                                  const float* scale_factors2, const float* level_sigma2, int check_ori,
                                  int32_t* matches12);
 
+/* MapPoint::ComputeDistinctiveDescriptors (code/src/MapPoint.cc:361-391) for a batch of MapPoints (CSR offsets):
+ * best_idx[p] = descriptor with the least median distance to the rest (-1 for an empty point). */
+void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best_idx,
+                                 int32_t* best_median);
+
 /* Brute-force top-2 of each query against a descriptor database (config 5). out: per query
  * (dist0, idx0, dist1, idx1); ties broken by lower index. */
 void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int32_t* out4);

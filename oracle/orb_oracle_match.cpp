@@ -382,6 +382,39 @@ int orc_search_for_triangulation(const orc_frame* f1, const orc_featvec* fv1, co
   return nmatches;
 }
 
+// MapPoint::ComputeDistinctiveDescriptors, MapPoint.cc:361-391
+void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best_idx,
+                                 int32_t* best_median) {
+  for (int p = 0; p < npoints; p++) {
+    const uint8_t* d = desc + (size_t)offsets[p] * 32;
+    const size_t N = (size_t)(offsets[p + 1] - offsets[p]);
+    best_idx[p] = -1;
+    best_median[p] = -1;
+    if (N == 0) continue;
+    std::vector<float> distances(N * N);
+    for (size_t i = 0; i < N; i++) {
+      distances[i * N + i] = 0;
+      for (size_t j = i + 1; j < N; j++) {
+        const int distij = dist256(d + i * 32, d + j * 32);
+        distances[i * N + j] = (float)distij;
+        distances[j * N + i] = (float)distij;
+      }
+    }
+    int BestMedian = INT_MAX, BestIdx = 0;
+    for (size_t i = 0; i < N; i++) {
+      std::vector<int> vDists(distances.begin() + i * N, distances.begin() + (i + 1) * N);
+      std::sort(vDists.begin(), vDists.end());
+      const int median = vDists[(size_t)(0.5 * (N - 1))];
+      if (median < BestMedian) {
+        BestMedian = median;
+        BestIdx = (int)i;
+      }
+    }
+    best_idx[p] = BestIdx;
+    best_median[p] = BestMedian;
+  }
+}
+
 // Brute-force top-2 (config 5): ties broken by the lower database index.
 void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int32_t* out4) {
   for (int i = 0; i < nq; i++) {

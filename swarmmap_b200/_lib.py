@@ -86,6 +86,7 @@ SYMBOLS = [
     ("swm_hamming_matrix_device", _i, [_vp, _i, _vp, _i, _vp, _vp]),
     ("swm_hamming_matrix", _i, [_vp, _i, _vp, _i, _vp, _i]),
     ("swm_hamming_pairs", _i, [_vp, _vp, _i, _vp, _i]),
+    ("swm_distinctive_descriptors", _i, [_vp, _vp, _i, _vp, _vp, _i]),
     ("swm_matcher_create", _i, [_i, _vp]),
     ("swm_matcher_destroy", None, [_vp]),
     ("swm_matcher_last_error", C.c_char_p, [_vp]),

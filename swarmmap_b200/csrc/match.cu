@@ -774,6 +774,55 @@ __global__ void __launch_bounds__(1024) tri_finalize_kernel(int n1, int32_t* __r
 }
 
 // ---------------------------------------------------------------------------------------------
+// MapPoint::ComputeDistinctiveDescriptors (code/src/MapPoint.cc:361-391) for a batch of MapPoints: N x N Hamming
+// distances between a point's observed descriptors, per row the median sorted[int(0.5 * (N - 1))], the row with the
+// least median wins (first one on ties).  One CTA per point, descriptors in shared memory, thread per row; the
+// order statistic is found by bisection on the distance value (count(d <= v) >= k + 1), so no sort is needed.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDistinctMax = 1024;  // observations per MapPoint served by one CTA (32 KB of shared memory)
+
+__global__ void __launch_bounds__(128) distinctive_kernel(const uint4* __restrict__ desc, const int32_t* __restrict__ offsets,
+                                                          int32_t* __restrict__ best_idx, int32_t* __restrict__ best_median) {
+  extern __shared__ __align__(16) uint4 s_desc[];
+  __shared__ unsigned long long s_best[4];
+  const int p = blockIdx.x, tid = threadIdx.x;
+  const int o = offsets[p], N = offsets[p + 1] - o;
+  if (N <= 0) {
+    if (tid == 0) { best_idx[p] = -1; best_median[p] = -1; }
+    return;
+  }
+  for (int i = tid; i < 2 * N; i += 128) s_desc[i] = __ldg(desc + 2 * (size_t)o + i);
+  __syncthreads();
+  const int k = (int)(0.5 * (N - 1));  // vDists[0.5 * (N - 1)]
+  unsigned long long best = ~0ull;
+  for (int i = tid; i < N; i += 128) {
+    const uint4 a0 = s_desc[2 * i], a1 = s_desc[2 * i + 1];
+    int lo = 0, hi = 256;  // smallest v with #{j : d(i, j) <= v} >= k + 1
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      int cnt = 0;
+      for (int j = 0; j < N; j++) {  // shared-memory operands: plain loads (ham256 uses the read-only global path)
+        const uint4 b0 = s_desc[2 * j], b1 = s_desc[2 * j + 1];
+        const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                      __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+        cnt += d <= mid;
+      }
+      if (cnt >= k + 1) hi = mid; else lo = mid + 1;
+    }
+    const unsigned long long key = ((unsigned long long)lo << 32) | (unsigned)i;  // median < BestMedian: first wins
+    best = best < key ? best : key;
+  }
+  best = warp_min_u64(best);
+  if ((tid & 31) == 0) s_best[tid >> 5] = best;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 4; w++) best = best < s_best[w] ? best : s_best[w];
+    best_idx[p] = (int)(unsigned)best;
+    best_median[p] = (int)(best >> 32);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Place-recognition shard (BASELINE config 5): brute-force top-2 of each query over the shard.
 // Each thread owns one query (descriptor in registers); the CTA streams database tiles through
 // shared memory (broadcast reads), keeping a running top-2 of packed keys dist<<48 | global index.
@@ -1379,6 +1428,45 @@ int swm_hamming_pairs(const uint8_t* a, const uint8_t* b, int n, int32_t* out, i
   if (e == cudaSuccess) e = cudaMemcpy(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost);
   cudaFree(da); cudaFree(db); cudaFree(dout);
   return e == cudaSuccess ? SWM_OK : SWM_E_CUDA;
+}
+
+int swm_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best_idx,
+                                int32_t* best_median, int device) {
+  if (!offsets || npoints < 0 || !best_idx) return SWM_E_INVALID;
+  if (npoints == 0) return SWM_OK;
+  const long long total = offsets[npoints];
+  int max_n = 0;
+  for (int p = 0; p < npoints; p++) {
+    const int n = offsets[p + 1] - offsets[p];
+    if (n < 0) return SWM_E_INVALID;
+    max_n = std::max(max_n, n);
+  }
+  if (total < 0 || offsets[0] != 0 || (total > 0 && !desc)) return SWM_E_INVALID;
+  if (max_n > kDistinctMax) return SWM_E_CAPACITY;
+  std::string err;
+  int rc = check_device(device, &err);
+  if (rc != SWM_OK) return rc;
+  if (cudaSetDevice(device) != cudaSuccess) return SWM_E_CUDA;
+  uint8_t* d_desc = nullptr;
+  int32_t *d_off = nullptr, *d_out = nullptr;
+  std::vector<int32_t> out(2 * (size_t)npoints);
+  bool ok = cudaMalloc(&d_desc, (size_t)std::max<long long>(total, 1) * 32) == cudaSuccess &&
+            cudaMalloc(&d_off, ((size_t)npoints + 1) * 4) == cudaSuccess &&
+            cudaMalloc(&d_out, 2 * (size_t)npoints * 4) == cudaSuccess;
+  if (ok && total) ok = cudaMemcpy(d_desc, desc, (size_t)total * 32, cudaMemcpyHostToDevice) == cudaSuccess;
+  ok = ok && cudaMemcpy(d_off, offsets, ((size_t)npoints + 1) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+  if (ok) {
+    distinctive_kernel<<<npoints, 128, (size_t)std::max(max_n, 1) * 32>>>((const uint4*)d_desc, d_off, d_out, d_out + npoints);
+    ok = cudaGetLastError() == cudaSuccess &&
+         cudaMemcpy(out.data(), d_out, out.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+  }
+  cudaFree(d_desc); cudaFree(d_off); cudaFree(d_out);
+  if (!ok) return SWM_E_CUDA;
+  for (int p = 0; p < npoints; p++) {
+    best_idx[p] = out[p];
+    if (best_median) best_median[p] = out[(size_t)npoints + p];
+  }
+  return SWM_OK;
 }
 
 int swm_grid_build(swm_matcher* m, const swm_frame_view* f, int32_t* starts, int32_t* items) {

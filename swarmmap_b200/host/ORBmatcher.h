@@ -57,6 +57,22 @@ class ORBmatcher {
       throw std::runtime_error("ORBmatcher::DescriptorDistanceMatrix failed");
   }
 
+  // MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:361-391): index of the observed descriptor with the least
+  // median distance to the others.  In MapPoint.cc replace the N x N loop and the median scan by
+  //   const int BestIdx = ORBmatcher::DistinctiveDescriptor(vDescriptors);
+  // (many MapPoints at once: swm_distinctive_descriptors takes a CSR batch).
+  static int DistinctiveDescriptor(const std::vector<cv::Mat>& vDescriptors, int device = 0) {
+    const int n = (int)vDescriptors.size();
+    if (n == 0) return -1;
+    std::vector<uint8_t> d((size_t)n * 32);
+    for (int i = 0; i < n; i++) std::memcpy(&d[(size_t)i * 32], vDescriptors[i].ptr(0), 32);
+    const int32_t off[2] = {0, n};
+    int32_t best = -1;
+    if (swm_distinctive_descriptors(d.data(), off, 1, &best, nullptr, device) != SWM_OK)
+      throw std::runtime_error("ORBmatcher::DistinctiveDescriptor failed (no CUDA device? there is no CPU fallback)");
+    return best;
+  }
+
   // ---- Matching for the Map Initialization (ORBmatcher.cc:375-479)
   template <class FrameT, class Point2fT>
   int SearchForInitialization(FrameT& F1, FrameT& F2, std::vector<Point2fT>& vbPrevMatched,

@@ -190,6 +190,19 @@ class ORBmatcher:
                     "swm_hamming_matrix")
         return out
 
+    # ---- MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:361-391), batched over MapPoints
+    def ComputeDistinctiveDescriptors(self, desc, offsets):
+        """desc: (total, 32) observed descriptors, point p owns rows offsets[p]:offsets[p+1].  Returns (best index
+        inside each point, its median distance)."""
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        npts = len(offsets) - 1
+        best = np.full(npts, -1, np.int32)
+        med = np.full(npts, -1, np.int32)
+        rc = self._lib.swm_distinctive_descriptors(ptr(desc), ptr(offsets), npts, ptr(best), ptr(med), self.device)
+        self._check(rc, "swm_distinctive_descriptors")
+        return best, med
+
     # ---- Frame grid (Frame.cc:277-292)
     def grid(self, frame):
         starts = np.zeros(GRID_COLS * GRID_ROWS + 1, np.int32)

@@ -350,6 +350,19 @@ def search_for_triangulation(f1, fv1, valid1, f2, fv2, valid2, F12, ex, ey, scal
     return n, out
 
 
+def distinctive_descriptors(desc, offsets):
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    n = len(offsets) - 1
+    best = np.zeros(n, np.int32)
+    med = np.zeros(n, np.int32)
+    fn = lib().orc_distinctive_descriptors
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    fn.restype = None
+    fn(_p(desc), _p(offsets), n, _p(best), _p(med))
+    return best, med
+
+
 def bruteforce_top2(q, db):
     q = np.ascontiguousarray(q, np.uint8)
     db = np.ascontiguousarray(db, np.uint8)

@@ -238,6 +238,31 @@ def test_search_for_triangulation(oracle, swm, frames, name, check_ori):
     assert n3 == 0 and (out3 == -1).all()
 
 
+def test_compute_distinctive_descriptors(oracle, swm):
+    """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:361-391), batched: best index and median per MapPoint equal
+    the oracle's sort-based version (even / odd N, single observation, empty point, duplicates -> first wins)."""
+    from swarmmap_b200.matcher import ORBmatcher
+    rng = np.random.default_rng(11)
+    sizes = [1, 2, 3, 4, 7, 0, 16, 33, 100, 257, 5, 1024] + list(rng.integers(1, 60, 200))
+    chunks = []
+    for n in sizes:
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        d = np.repeat(base[None], n, 0)
+        if n:
+            bits = np.unpackbits(d, axis=1)
+            bits ^= (rng.random(bits.shape) < 0.08).astype(np.uint8)  # observations = noisy copies of one descriptor
+            d = np.packbits(bits, axis=1)
+            if n > 3:
+                d[n // 2] = d[1]  # exact duplicate rows: equal medians, the first must win
+        chunks.append(d)
+    desc = np.concatenate(chunks)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    best, med = ORBmatcher().ComputeDistinctiveDescriptors(desc, offsets)
+    rbest, rmed = oracle.distinctive_descriptors(desc, offsets)
+    np.testing.assert_array_equal(best, rbest)
+    np.testing.assert_array_equal(med, rmed)
+
+
 def _db_case(rng, nq, ndb):
     q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
     db = rng.integers(0, 256, (ndb, 32), dtype=np.uint8)
