@@ -219,6 +219,29 @@ int swm_match_bow(swm_matcher* m, const swm_frame_view* f1, const swm_featvec* f
                   const swm_frame_view* f2, const swm_featvec* fv2, const uint8_t* valid2, int mode, float nnratio,
                   int check_ori, int32_t* matches, int* nmatches);
 
+/* Best keypoint inside a window, one independent row per query: the search loop shared by ORBmatcher::Fuse
+ * (ORBmatcher.cc:824-870 and :962-999) and SearchBySim3 (:1098-1134, :1178-1214).  Candidates =
+ * GetFeaturesInArea(u, v, radius, min_level, max_level) in its order (Fuse / SearchBySim3 pass nPredictedLevel - 1,
+ * nPredictedLevel); with chi2 > 0 the monocular reprojection gate e2 * inv_level_sigma2[level] > chi2 -> skip
+ * (:857-864, chi2 = 5.99) is applied; winner = smallest distance, the first candidate on ties ("dist < bestDist").
+ * best_idx[i] = -1 and best_dist[i] = 256 when no candidate survives.  The callers' accept thresholds (TH_LOW /
+ * TH_HIGH) and the MapPoint bookkeeping (Replace / AddObservation, in order) stay in the C++ wrapper. */
+typedef struct swm_best_query {
+  int32_t m;
+  const uint8_t* desc;
+  const float* u;
+  const float* v;
+  const float* radius;
+  const int32_t* min_level;
+  const int32_t* max_level;
+  const uint8_t* valid;
+  const float* inv_level_sigma2; /* pKF->mvInvLevelSigma2 (read when chi2 > 0) */
+  int32_t nlevels;
+  float chi2;                    /* <= 0: no reprojection gate */
+} swm_best_query;
+int swm_window_best(swm_matcher* m, const swm_frame_view* tgt, const swm_best_query* q, int32_t* best_idx,
+                    int32_t* best_dist);
+
 /* ORBmatcher::SearchForTriangulation (ORBmatcher.cc:599-749) with CheckDistEpipolarLine (:131-148), monocular
  * (mvuRight < 0, bOnlyStereo = false).  The C++ wrapper computes the epipole (:605-611) and passes F12 and pKF2's
  * level tables; valid1 / valid2 mark keypoints WITHOUT a MapPoint (:640-643, :662-666).  The reference never sets
@@ -278,6 +301,8 @@ int swm_match_bow_resident(swm_matcher* m, const swm_frame* f1, const swm_featve
 int swm_match_triangulation_resident(swm_matcher* m, const swm_frame* f1, const swm_featvec* fv1, const uint8_t* valid1,
                                      const swm_frame* f2, const swm_featvec* fv2, const uint8_t* valid2,
                                      const swm_triangulation_query* q, int check_ori, int32_t* matches12, int* nmatches);
+int swm_window_best_resident(swm_matcher* m, const swm_frame* tgt, const swm_best_query* q, int32_t* best_idx,
+                             int32_t* best_dist);
 
 /* ------------------------------------------------------------------ DBoW2 transform
  * TemplatedVocabulary<FORB>::transform(features, BowVector&, FeatureVector&, levelsup)

@@ -148,6 +148,14 @@ int orc_search_for_triangulation(const orc_frame* f1, const orc_featvec* fv1, co
                                  const float* scale_factors2, const float* level_sigma2, int check_ori,
                                  int32_t* matches12);
 
+/* The search loop of ORBmatcher::Fuse (:824-870) / SearchBySim3 (:1098-1134), one independent row per query:
+ * candidates = GetFeaturesInArea(u, v, radius) (Frame.cc:377-425) filtered to levels [pred - 1, pred] (:840-842); with
+ * chi2 > 0 the monocular gate e2 * inv_level_sigma2[level] > chi2 -> skip (:857-864); dist < bestDist (first wins).
+ * best_idx -1 / best_dist 256 when nothing survives. */
+void orc_window_best(const orc_frame* tgt, int m, const uint8_t* desc, const float* u, const float* v, const float* radius,
+                     const int32_t* pred_level, const uint8_t* valid, const float* inv_level_sigma2, float chi2,
+                     int32_t* best_idx, int32_t* best_dist);
+
 /* MapPoint::ComputeDistinctiveDescriptors (code/src/MapPoint.cc:361-391) for a batch of MapPoints (CSR offsets):
  * best_idx[p] = descriptor with the least median distance to the rest (-1 for an empty point). */
 void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best_idx,

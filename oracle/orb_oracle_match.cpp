@@ -382,6 +382,40 @@ int orc_search_for_triangulation(const orc_frame* f1, const orc_featvec* fv1, co
   return nmatches;
 }
 
+// Fuse / SearchBySim3 inner loop (see header)
+void orc_window_best(const orc_frame* tgt, int m, const uint8_t* desc, const float* u, const float* v, const float* radius,
+                     const int32_t* pred_level, const uint8_t* valid, const float* inv_level_sigma2, float chi2,
+                     int32_t* best_idx, int32_t* best_dist) {
+  orc_grid* g = orc_grid_build(tgt);
+  std::vector<int32_t> idx((size_t)std::max(tgt->n, 1));
+  for (int i = 0; i < m; i++) {
+    best_idx[i] = -1;
+    best_dist[i] = 256;
+    if (!valid[i]) continue;
+    const int cnt = orc_grid_query(g, tgt, u[i], v[i], radius[i], -1, -1, idx.data(), (int)idx.size());  // no level args
+    int bestDist = 256, bestIdx = -1;
+    for (int c = 0; c < cnt; c++) {
+      const int j = idx[c];
+      const int kpLevel = tgt->octave[j];
+      if (kpLevel < pred_level[i] - 1 || kpLevel > pred_level[i]) continue;
+      if (chi2 > 0.0f) {
+        const float ex = u[i] - tgt->x[j];
+        const float ey = v[i] - tgt->y[j];
+        const float e2 = ex * ex + ey * ey;
+        if (e2 * inv_level_sigma2[kpLevel] > (double)chi2) continue;
+      }
+      const int dist = dist256(desc + (size_t)i * 32, tgt->desc + (size_t)j * 32);
+      if (dist < bestDist) {
+        bestDist = dist;
+        bestIdx = j;
+      }
+    }
+    best_idx[i] = bestIdx;
+    best_dist[i] = bestDist;
+  }
+  orc_grid_destroy(g);
+}
+
 // MapPoint::ComputeDistinctiveDescriptors, MapPoint.cc:361-391
 void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best_idx,
                                  int32_t* best_median) {

@@ -53,6 +53,12 @@ class TriangulationQuery(C.Structure):
                 ("level_sigma2", C.c_void_p), ("nlevels", C.c_int32)]
 
 
+class BestQuery(C.Structure):
+    _fields_ = [("m", C.c_int32), ("desc", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("radius", C.c_void_p),
+                ("min_level", C.c_void_p), ("max_level", C.c_void_p), ("valid", C.c_void_p),
+                ("inv_level_sigma2", C.c_void_p), ("nlevels", C.c_int32), ("chi2", C.c_float)]
+
+
 class BowOut(C.Structure):
     _fields_ = [("word_ids", C.c_void_p), ("word_values", C.c_void_p), ("n_words", C.c_void_p),
                 ("node_ids", C.c_void_p), ("node_offsets", C.c_void_p), ("feats", C.c_void_p), ("n_nodes", C.c_void_p)]
@@ -94,6 +100,8 @@ SYMBOLS = [
     ("swm_match_init", _i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp]),
     ("swm_match_window", _i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp]),
     ("swm_match_bow", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp]),
+    ("swm_window_best", _i, [_vp, _vp, _vp, _vp, _vp]),
+    ("swm_window_best_resident", _i, [_vp, _vp, _vp, _vp, _vp]),
     ("swm_match_triangulation", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     ("swm_match_triangulation_resident", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _vp]),
     ("swm_camera_bounds", _i, [_i, _vp, _i, _i, _vp]),

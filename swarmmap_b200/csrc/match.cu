@@ -774,6 +774,43 @@ __global__ void __launch_bounds__(1024) tri_finalize_kernel(int n1, int32_t* __r
 }
 
 // ---------------------------------------------------------------------------------------------
+// Best keypoint inside a window, independent rows: the inner loop of ORBmatcher::Fuse (ORBmatcher.cc:824-870,
+// :962-999) and SearchBySim3 (:1098-1134, :1178-1214).  Candidates come from window_rows_kernel in
+// GetFeaturesInArea's order with the level filter applied; the optional monocular reprojection gate
+// (e2 * mvInvLevelSigma2[level] > 5.99 -> skip, :857-864) is evaluated here; "dist < bestDist" = smallest distance,
+// first candidate on ties.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) best_rows_kernel(FrameDev tgt, int rows, const float* __restrict__ u,
+                                                        const float* __restrict__ v, const int32_t* __restrict__ row_start,
+                                                        const int32_t* __restrict__ cand_idx,
+                                                        const uint32_t* __restrict__ cand_val,
+                                                        const float* __restrict__ inv_sigma2, float chi2,
+                                                        int32_t* __restrict__ best_idx, int32_t* __restrict__ best_dist) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float pu = u[r], pv = v[r];
+  const int c0 = row_start[r];
+  unsigned long long best = ~0ull;
+  for (int ci = c0 + lane; ci < row_start[r + 1]; ci += 32) {
+    const int j = cand_idx[ci];
+    const uint32_t val = cand_val[ci];
+    if (chi2 > 0.0f) {
+      const float ex = __fsub_rn(pu, tgt.x[j]), ey = __fsub_rn(pv, tgt.y[j]);
+      const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+      if ((double)__fmul_rn(e2, inv_sigma2[val >> 16]) > (double)chi2) continue;
+    }
+    const unsigned long long key = ((unsigned long long)(val & 0xFFFFu) << 32) | (unsigned)(ci - c0);
+    best = best < key ? best : key;
+  }
+  best = warp_min_u64(best);
+  if (lane == 0) {
+    best_idx[r] = best == ~0ull ? -1 : cand_idx[c0 + (int)(unsigned)best];
+    best_dist[r] = best == ~0ull ? 256 : (int)(best >> 32);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // MapPoint::ComputeDistinctiveDescriptors (code/src/MapPoint.cc:361-391) for a batch of MapPoints: N x N Hamming
 // distances between a point's observed descriptors, per row the median sorted[int(0.5 * (N - 1))], the row with the
 // least median wins (first one on ties).  One CTA per point, descriptors in shared memory, thread per row; the
@@ -1798,6 +1835,56 @@ int match_triangulation_impl(swm_matcher* m, const FrameSrc& f1, const swm_featv
   return SWM_OK;
 }
 
+int window_best_impl(swm_matcher* m, const FrameSrc& tgt, const swm_best_query* bq, int32_t* best_idx, int32_t* best_dist) {
+  const int M = bq->m, n2 = tgt.n();
+  for (int i = 0; i < M; i++) { best_idx[i] = -1; best_dist[i] = 256; }
+  if (M == 0 || n2 == 0) return SWM_OK;
+  MCK(m, cudaSetDevice(m->device));
+  FrameDev d2;
+  int rc;
+  const bool gate = bq->chi2 > 0.0f;
+  if ((rc = arena_begin(m, src_bytes(tgt) + (size_t)M * 64 + (size_t)SWM_MAX_LEVELS * 4 + 12 * 256))) return rc;
+  if ((rc = acquire_frame(m, 1, tgt, &d2))) return rc;
+  if ((rc = upload(m, m->q[0], bq->u, (size_t)M * 4))) return rc;
+  if ((rc = upload(m, m->q[1], bq->v, (size_t)M * 4))) return rc;
+  if ((rc = upload(m, m->q[2], bq->radius, (size_t)M * 4))) return rc;
+  if ((rc = upload(m, m->q[3], bq->min_level, (size_t)M * 4))) return rc;
+  if ((rc = upload(m, m->q[6], bq->max_level, (size_t)M * 4))) return rc;
+  if ((rc = upload(m, m->q[4], bq->valid, (size_t)M))) return rc;
+  if ((rc = upload(m, m->q[7], bq->desc, (size_t)M * 32))) return rc;
+  if (gate && (rc = upload(m, m->q[9], bq->inv_level_sigma2, (size_t)bq->nlevels * 4))) return rc;
+  if ((rc = arena_flush(m))) return rc;
+  if ((rc = acquire_grid(m, 1, tgt, &d2))) return rc;
+  WindowDev q;
+  q.m = M;
+  q.desc = m->q[7].as<uint4>();
+  q.u = m->q[0].as<float>();
+  q.v = m->q[1].as<float>();
+  q.radius = m->q[2].as<float>();
+  q.min_level = m->q[3].as<int32_t>();
+  q.max_level = m->q[6].as<int32_t>();
+  q.valid = m->q[4].as<uint8_t>();
+  int total = 0;
+  if ((rc = build_window_rows(m, d2, q, &total))) return rc;
+  MCK(m, m->state[3].ensure((size_t)M * 4));
+  MCK(m, m->state[4].ensure((size_t)M * 4));
+  best_rows_kernel<<<(M + 7) / 8, 256, 0, m->stream>>>(d2, M, q.u, q.v, m->rows[1].as<int32_t>(), m->rows[2].as<int32_t>(),
+                                                       m->rows[3].as<uint32_t>(), gate ? m->q[9].as<float>() : nullptr,
+                                                       gate ? bq->chi2 : 0.0f, m->state[3].as<int32_t>(),
+                                                       m->state[4].as<int32_t>());
+  MCK(m, cudaGetLastError());
+  MCK(m, cudaMemcpyAsync(best_idx, m->state[3].p, (size_t)M * 4, cudaMemcpyDeviceToHost, m->stream));
+  MCK(m, cudaMemcpyAsync(best_dist, m->state[4].p, (size_t)M * 4, cudaMemcpyDeviceToHost, m->stream));
+  MCK(m, cudaStreamSynchronize(m->stream));
+  return SWM_OK;
+}
+
+bool best_query_ok(const swm_best_query* q) {
+  return q && q->m >= 0 &&
+         (q->m == 0 || (q->desc && q->u && q->v && q->radius && q->min_level && q->max_level && q->valid)) &&
+         (q->chi2 <= 0.0f || (q->inv_level_sigma2 && q->nlevels > 0 && q->nlevels <= SWM_MAX_LEVELS));
+}
+
 bool tri_query_ok(const swm_triangulation_query* q) {
   return q && q->F12 && q->scale_factors2 && q->level_sigma2 && q->nlevels > 0 && q->nlevels <= SWM_MAX_LEVELS;
 }
@@ -1870,6 +1957,19 @@ int swm_match_bow_resident(swm_matcher* m, const swm_frame* f1, const swm_featve
   }
   return match_bow_impl(m, FrameSrc{nullptr, f1}, fv1, valid1, FrameSrc{nullptr, f2}, fv2, valid2, mode, nnratio, check_ori,
                         matches, nmatches);
+}
+
+int swm_window_best(swm_matcher* m, const swm_frame_view* tgt, const swm_best_query* q, int32_t* best_idx, int32_t* best_dist) {
+  if (!m) return SWM_E_INVALID;
+  if (!frame_ok(tgt) || !best_query_ok(q) || !best_idx || !best_dist) { m->err = "bad argument"; return SWM_E_INVALID; }
+  return window_best_impl(m, FrameSrc{tgt, nullptr}, q, best_idx, best_dist);
+}
+
+int swm_window_best_resident(swm_matcher* m, const swm_frame* tgt, const swm_best_query* q, int32_t* best_idx,
+                             int32_t* best_dist) {
+  if (!m) return SWM_E_INVALID;
+  if (!tgt || !best_query_ok(q) || !best_idx || !best_dist) { m->err = "bad argument"; return SWM_E_INVALID; }
+  return window_best_impl(m, FrameSrc{nullptr, tgt}, q, best_idx, best_dist);
 }
 
 int swm_match_triangulation(swm_matcher* m, const swm_frame_view* f1, const swm_featvec* fv1, const uint8_t* valid1,

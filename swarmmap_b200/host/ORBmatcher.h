@@ -336,6 +336,83 @@ class ORBmatcher {
     return n;
   }
 
+  // ---- Project MapPoints into a KeyFrame and search for duplicated MapPoints (ORBmatcher.cc:751-880), monocular.
+  // Pass 1 (host): the reference's visibility tests and projection per MapPoint.  GPU: best keypoint in the window
+  // (swm_window_best, levels [pred - 1, pred], reprojection gate 5.99).  Pass 2 (host, in list order): the
+  // Replace / AddObservation bookkeeping, re-checking isBad() / IsInKeyFrame() at commit time because an earlier
+  // Replace can retire a later point of the list (the reference tests them at the top of each iteration).
+  template <class KeyFrameT, class MapPointT>
+  int Fuse(KeyFrameT* pKF, const std::vector<MapPointT*>& vpMapPoints, const float th = 3.0) {
+    float R[9], t[3], Ow[3];
+    {
+      const auto Rcw = pKF->GetRotation();
+      const auto tcw = pKF->GetTranslation();
+      for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) R[3 * r + c] = Rcw.template at<float>(r, c);
+        t[r] = tcw.template at<float>(r);
+      }
+      world_pos(pKF->GetCameraCenter(), Ow);
+    }
+    const int M = (int)vpMapPoints.size();
+    std::vector<uint8_t> desc((size_t)M * 32, 0), valid(M, 0);
+    std::vector<float> u(M, 0.f), v(M, 0.f), radius(M, 0.f);
+    std::vector<int32_t> lo(M, -1), hi(M, -1);
+    for (int i = 0; i < M; i++) {
+      MapPointT* pMP = vpMapPoints[i];
+      if (!pMP) continue;
+      if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;
+      float Pw[3], Pc[3];
+      world_pos(pMP->GetWorldPos(), Pw);
+      transform(R, t, Pw, Pc);
+      if (Pc[2] < 0.0f) continue;                                          // :779-780
+      const float invz = 1 / Pc[2];
+      const float pu = pKF->fx * (Pc[0] * invz) + pKF->cx, pv = pKF->fy * (Pc[1] * invz) + pKF->cy;
+      if (!pKF->IsInImage(pu, pv)) continue;                                // :790-791
+      const float PO[3] = {Pw[0] - Ow[0], Pw[1] - Ow[1], Pw[2] - Ow[2]};
+      const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);  // cv::norm
+      if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+      float Pn[3];
+      world_pos(pMP->GetNormal(), Pn);
+      if ((double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2] < 0.5 * dist3D) continue;  // :808-809
+      const int pred = pMP->PredictScale(dist3D, pKF->mfLogScaleFactor, pKF->mnScaleLevels);
+      valid[i] = 1;
+      u[i] = pu; v[i] = pv;
+      radius[i] = th * pKF->mvScaleFactors[pred];                          // :814
+      lo[i] = pred - 1; hi[i] = pred;                                       // :840-842
+      std::memcpy(&desc[(size_t)i * 32], descriptor_of(pMP).ptr(0), 32);
+    }
+    swm_best_query q;
+    q.m = M; q.desc = desc.data(); q.u = u.data(); q.v = v.data(); q.radius = radius.data();
+    q.min_level = lo.data(); q.max_level = hi.data(); q.valid = valid.data();
+    q.inv_level_sigma2 = pKF->mvInvLevelSigma2.data();
+    q.nlevels = (int32_t)pKF->mvInvLevelSigma2.size();
+    q.chi2 = 5.99f;
+    std::vector<int32_t> best_idx(M, -1), best_dist(M, 256);
+    FlatFrame kf;
+    gather(*pKF, kf);
+    swm_frame_view vk = kf.view();
+    check(resident_of(*pKF, 0) ? swm_window_best_resident(m_, resident_of(*pKF, 0), &q, best_idx.data(), best_dist.data())
+                               : swm_window_best(m_, &vk, &q, best_idx.data(), best_dist.data()));
+    int nFused = 0;
+    for (int i = 0; i < M; i++) {
+      if (!valid[i] || best_idx[i] < 0 || best_dist[i] > TH_LOW) continue;  // :873
+      MapPointT* pMP = vpMapPoints[i];
+      if (pMP->isBad() || pMP->IsInKeyFrame(pKF)) continue;                 // state may have changed since pass 1
+      MapPointT* pMPinKF = pKF->GetMapPoint(best_idx[i]);
+      if (pMPinKF) {
+        if (!pMPinKF->isBad()) {
+          if (pMPinKF->Observations() > pMP->Observations()) pMP->Replace(pMPinKF);
+          else pMPinKF->Replace(pMP);
+        }
+      } else {
+        pMP->AddObservation(pKF, best_idx[i]);
+        pKF->AddMapPoint(pMP, best_idx[i]);
+      }
+      nFused++;
+    }
+    return nFused;
+  }
+
   // ---- Matching to triangulate new MapPoints, with the epipolar constraint (ORBmatcher.cc:599-749), monocular.
   // F12 is the 3x3 CV_32F fundamental matrix LocalMapping::ComputeF12 builds.  The stereo branches need mvuRight >= 0
   // and are not served (bOnlyStereo must be false; SwarmMap is monocular).

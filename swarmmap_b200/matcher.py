@@ -190,6 +190,31 @@ class ORBmatcher:
                     "swm_hamming_matrix")
         return out
 
+    # ---- the search loop of Fuse (ORBmatcher.cc:824-870, :962-999) and SearchBySim3 (:1098-1134, :1178-1214)
+    def window_best(self, tgt, desc, u, v, radius, pred_level, valid, inv_level_sigma2=None, chi2=0.0):
+        """Per query: the keypoint of `tgt` inside the window at levels [pred - 1, pred] with the smallest distance
+        (first in GetFeaturesInArea order on ties); chi2 > 0 adds Fuse's reprojection gate.  Returns (best_idx,
+        best_dist) with -1 / 256 for rows without a surviving candidate; the caller applies TH_LOW / TH_HIGH."""
+        from ._lib import BestQuery
+        desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        pl = np.ascontiguousarray(pred_level, np.int32)
+        a = dict(u=np.ascontiguousarray(u, np.float32), v=np.ascontiguousarray(v, np.float32),
+                 radius=np.ascontiguousarray(radius, np.float32), lo=np.ascontiguousarray(pl - 1, np.int32), hi=pl,
+                 valid=np.ascontiguousarray(valid, np.uint8))
+        s2 = np.ascontiguousarray(inv_level_sigma2, np.float32) if inv_level_sigma2 is not None else None
+        q = BestQuery(len(pl), ptr(desc).value, ptr(a["u"]).value, ptr(a["v"]).value, ptr(a["radius"]).value,
+                      ptr(a["lo"]).value, ptr(a["hi"]).value, ptr(a["valid"]).value,
+                      ptr(s2).value if s2 is not None else None, len(s2) if s2 is not None else 0, float(chi2))
+        bi = np.full(len(pl), -1, np.int32)
+        bd = np.full(len(pl), 256, np.int32)
+        if isinstance(tgt, ResidentFrame):
+            rc = self._lib.swm_window_best_resident(self._h, tgt._h, C.byref(q), ptr(bi), ptr(bd))
+        else:
+            tv = tgt.view()
+            rc = self._lib.swm_window_best(self._h, C.byref(tv), C.byref(q), ptr(bi), ptr(bd))
+        self._check(rc, "swm_window_best")
+        return bi, bd
+
     # ---- MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:361-391), batched over MapPoints
     def ComputeDistinctiveDescriptors(self, desc, offsets):
         """desc: (total, 32) observed descriptors, point p owns rows offsets[p]:offsets[p+1].  Returns (best index

@@ -35,6 +35,12 @@ struct MapPoint {
   cv::Mat GetDescriptor() { return desc; }
   int Observations() { return nobs; }
   bool isBad() { return bad; }
+  // Fuse bookkeeping
+  std::map<void*, int> obs;
+  MapPoint* replaced_by = nullptr;
+  bool IsInKeyFrame(void* kf) { return obs.count(kf) > 0; }
+  void AddObservation(void* kf, int idx) { obs[kf] = idx; nobs = (int)obs.size(); }
+  void Replace(MapPoint* other) { bad = true; replaced_by = other; }
 };
 
 struct Frame {
@@ -57,6 +63,8 @@ struct Frame {
   std::vector<float> mvLevelSigma2;
   Mat4 mOw, mRcw, mtcw;
   MapPoint* GetMapPoint(int i) { return mvpMapPoints[i]; }
+  void AddMapPoint(MapPoint* p, int i) { mvpMapPoints[i] = p; }
+  std::vector<float> mvInvLevelSigma2;
   Mat4 GetCameraCenter() { return mOw; }
   Mat4 GetRotation() { return mRcw; }
   Mat4 GetTranslation() { return mtcw; }
@@ -214,6 +222,30 @@ int main(int argc, char** argv) {
     for (auto& p : pairs) self_tri += p.first == p.second;
     std::printf("triangulation: %d pairs, %d on the same keypoint of the identical image\n", n_tri, self_tri);
     if (n_tri != (int)pairs.size() || n_tri < k1.N / 2 || self_tri < n_tri * 9 / 10) { std::printf("HOST_WRAPPER_FAIL triangulation\n"); return 1; }
+  }
+  // Fuse: project frame 1's MapPoints (which sit exactly on its keypoints) into a keyframe of the same image: half of
+  // the keyframe's slots are empty (-> AddObservation / AddMapPoint), half hold another point (-> Replace)
+  {
+    Frame kf;
+    fill(kf, ex, img);
+    kf.mvInvLevelSigma2 = ex.GetInverseScaleSigmaSquares();
+    for (int i = 0; i < 3; i++) { kf.mtcw.v[i] = 0.0f; kf.mOw.v[i] = 0.0f; }  // identity pose: the points project onto their keypoints
+    std::vector<MapPoint> fresh(pts.begin(), pts.end());  // copies: no observations yet
+    for (auto& p : fresh) { p.obs.clear(); p.nobs = 0; p.bad = false; }
+    std::vector<MapPoint> resident_pts(kf.N);
+    for (int j = 0; j < kf.N; j += 2) { resident_pts[j].nobs = 3; kf.mvpMapPoints[j] = &resident_pts[j]; }
+    std::vector<MapPoint*> cand;
+    for (auto& p : fresh) cand.push_back(&p);
+    ORB_SLAM2::ORBmatcher mf(0.8f, true);
+    const int n_fused = mf.Fuse(&kf, cand, 3.0f);
+    int added = 0, replaced = 0;
+    for (int j = 0; j < kf.N; j++) added += (j % 2 == 1) && kf.mvpMapPoints[j] != nullptr;
+    for (auto& p : fresh) replaced += p.bad && p.replaced_by != nullptr;
+    std::printf("fuse: %d fused, %d added to empty slots, %d replaced by the keyframe's point\n", n_fused, added, replaced);
+    if (n_fused < kf.N * 8 / 10 || added < kf.N / 2 * 7 / 10 || replaced < kf.N / 2 * 7 / 10 || added + replaced != n_fused) {
+      std::printf("HOST_WRAPPER_FAIL fuse\n");
+      return 1;
+    }
   }
   const int d0 = ORB_SLAM2::ORBmatcher::DescriptorDistance(f1.mDescriptors.row(0), f1.mDescriptors.row(0));
   const int d1 = ORB_SLAM2::ORBmatcher::DescriptorDistance(f1.mDescriptors.row(0), f1.mDescriptors.row(1));

@@ -350,6 +350,23 @@ def search_for_triangulation(f1, fv1, valid1, f2, fv2, valid2, F12, ex, ey, scal
     return n, out
 
 
+def window_best(tgt, desc, u, v, radius, pred_level, valid, inv_level_sigma2, chi2):
+    t, keep = _frame(tgt)
+    desc = np.ascontiguousarray(desc, np.uint8)
+    arr = [np.ascontiguousarray(a, np.float32) for a in (u, v, radius)]
+    pl = np.ascontiguousarray(pred_level, np.int32)
+    va = np.ascontiguousarray(valid, np.uint8)
+    s2 = np.ascontiguousarray(inv_level_sigma2, np.float32)
+    m = len(pl)
+    bi = np.zeros(m, np.int32)
+    bd = np.zeros(m, np.int32)
+    fn = lib().orc_window_best
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 7 + [C.c_float, C.c_void_p, C.c_void_p]
+    fn(C.byref(t), m, _p(desc), _p(arr[0]), _p(arr[1]), _p(arr[2]), _p(pl), _p(va), _p(s2), float(chi2), _p(bi), _p(bd))
+    return bi, bd
+
+
 def distinctive_descriptors(desc, offsets):
     desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
     offsets = np.ascontiguousarray(offsets, np.int32)

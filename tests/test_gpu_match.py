@@ -238,6 +238,33 @@ def test_search_for_triangulation(oracle, swm, frames, name, check_ori):
     assert n3 == 0 and (out3 == -1).all()
 
 
+@pytest.mark.parametrize("chi2", [5.99, 0.0])
+@pytest.mark.parametrize("name", ["euroc", "kitti"])
+def test_window_best_fuse_loop(oracle, swm, frames, name, chi2):
+    """The search loop of Fuse / SearchBySim3: best index and distance per projected MapPoint, bit-exact against the
+    oracle's GetFeaturesInArea-based loop (levels [pred - 1, pred], reprojection gate, first-wins ties)."""
+    from swarmmap_b200.matcher import ORBmatcher, ResidentFrame
+    src, tgt = frames[name][0], frames[name][1]
+    rng = np.random.default_rng(13)
+    sf, _, _, inv_s2 = oracle.scale_tables(1.2, 8)
+    u = src.x + rng.normal(0, 1.5, src.N).astype(np.float32)
+    v = src.y + rng.normal(0, 1.5, src.N).astype(np.float32)
+    pred = np.clip(src.octave + rng.integers(-1, 2, src.N), 0, 7).astype(np.int32)
+    radius = (np.float32(12.0) * sf[pred]).astype(np.float32)
+    valid = (rng.random(src.N) < 0.9).astype(np.uint8)
+    m = ORBmatcher()
+    bi, bd = m.window_best(tgt, src.desc, u, v, radius, pred, valid, inv_s2, chi2)
+    ri, rd = oracle.window_best(tgt, src.desc, u, v, radius, pred, valid, inv_s2, chi2)
+    np.testing.assert_array_equal(bi, ri)
+    np.testing.assert_array_equal(bd, rd)
+    assert (bi >= 0).sum() > src.N // 20
+    if chi2 > 0:
+        assert (bi >= 0).sum() < (m.window_best(tgt, src.desc, u, v, radius, pred, valid)[0] >= 0).sum() + 1
+    bi2, bd2 = m.window_best(ResidentFrame().upload(tgt), src.desc, u, v, radius, pred, valid, inv_s2, chi2)
+    np.testing.assert_array_equal(bi2, ri)
+    np.testing.assert_array_equal(bd2, rd)
+
+
 def test_compute_distinctive_descriptors(oracle, swm):
     """MapPoint::ComputeDistinctiveDescriptors (MapPoint.cc:361-391), batched: best index and median per MapPoint equal
     the oracle's sort-based version (even / odd N, single observation, empty point, duplicates -> first wins)."""
