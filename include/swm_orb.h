@@ -353,6 +353,12 @@ void swm_db_destroy(swm_db* db);
  * match when best <= th_votes (TH_LOW). */
 int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t* d_topk, int32_t* d_votes,
                         int th_votes, void* stream);
+/* Multi-GPU step after the all-gather of the per-shard (nq, k) key blocks: d_gathered is (world, nq, k); writes
+ * the k smallest keys per query to d_topk and, into d_votes (optional, this shard's n_kf counters, += 1), the vote
+ * of every query whose GLOBAL best match is <= th_votes and belongs to a keyframe of this shard (summed over the
+ * ranks this equals the single-shard vote histogram). */
+int swm_db_merge_gathered(swm_db* db, const uint64_t* d_gathered, int world, int nq, int k, uint64_t* d_topk,
+                          int32_t* d_votes, int th_votes, void* stream);
 int64_t swm_db_size(const swm_db* db);
 
 /* Build id string ("swm_orb <version> sm_100a <date>"). */

@@ -125,6 +125,7 @@ SYMBOLS = [
     ("swm_db_create_device", _i, [_i, _vp, _i64, C.c_int32, _i64, _vp]),
     ("swm_db_destroy", None, [_vp]),
     ("swm_db_query_device", _i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    ("swm_db_merge_gathered", _i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     ("swm_db_size", _i64, [_vp]),
 ]
 

@@ -1054,15 +1054,17 @@ __global__ void __launch_bounds__(256, 2) db_top2_mma_kernel(const uint4* __rest
   }
 }
 
-__global__ void db_merge_kernel(const unsigned long long* __restrict__ partial, int nparts, int nq, int k,
+// partial: [nparts][nq][kin] keys (kin = 2 for the slices of one shard scan; the all-gathered (world, nq, k) block of
+// the multi-GPU query has the same layout with kin = k).
+__global__ void db_merge_kernel(const unsigned long long* __restrict__ partial, int nparts, int nq, int kin, int k,
                                 unsigned long long* __restrict__ topk, int32_t* __restrict__ votes, int th_votes,
                                 long long first_kf, int desc_per_kf, long long first_index, long long n_kf) {
   const int qi = blockIdx.x * blockDim.x + threadIdx.x;
   if (qi >= nq) return;
   unsigned long long k0 = ~0ull, k1 = ~0ull;
   for (int p = 0; p < nparts; p++) {
-    for (int e = 0; e < 2; e++) {
-      const unsigned long long key = partial[((size_t)p * nq + qi) * 2 + e];
+    for (int e = 0; e < kin; e++) {
+      const unsigned long long key = partial[((size_t)p * nq + qi) * kin + e];
       if (key < k1) {
         if (key < k0) {
           k1 = k0;
@@ -1076,9 +1078,9 @@ __global__ void db_merge_kernel(const unsigned long long* __restrict__ partial, 
   topk[(size_t)qi * k] = k0;
   if (k > 1) topk[(size_t)qi * k + 1] = k1;
   if (votes && k0 != ~0ull && (int)(k0 >> 48) <= th_votes) {
-    const long long idx = (long long)(k0 & 0xFFFFFFFFFFFFull) - first_index;
+    const long long idx = (long long)(k0 & 0xFFFFFFFFFFFFull) - first_index;  // < 0: another shard's keyframe
     const long long kf = idx / desc_per_kf;
-    if (kf >= 0 && kf < n_kf) atomicAdd(votes + kf, 1);
+    if (idx >= 0 && kf < n_kf) atomicAdd(votes + kf, 1);
   }
   (void)first_kf;
 }
@@ -2244,8 +2246,20 @@ int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t*
         (const uint4*)db->d_desc, db->ndesc, first_index, (const uint4*)d_q, nq, tiles_per_cta, db->d_partial);
   }
   const long long n_kf = (db->ndesc + db->desc_per_kf - 1) / db->desc_per_kf;
-  db_merge_kernel<<<(nq + 127) / 128, 128, 0, st>>>(db->d_partial, (int)parts, nq, k, (unsigned long long*)d_topk,
+  db_merge_kernel<<<(nq + 127) / 128, 128, 0, st>>>(db->d_partial, (int)parts, nq, 2, k, (unsigned long long*)d_topk,
                                                     d_votes, th_votes, db->first_kf, db->desc_per_kf, first_index, n_kf);
+  return cudaGetLastError() == cudaSuccess ? SWM_OK : SWM_E_CUDA;
+}
+
+int swm_db_merge_gathered(swm_db* db, const uint64_t* d_gathered, int world, int nq, int k, uint64_t* d_topk,
+                          int32_t* d_votes, int th_votes, void* stream) {
+  if (!db || !d_gathered || world < 1 || nq <= 0 || k < 1 || k > 2 || !d_topk) return SWM_E_INVALID;
+  if (cudaSetDevice(db->device) != cudaSuccess) return SWM_E_CUDA;
+  const long long first_index = db->first_kf * db->desc_per_kf;
+  const long long n_kf = (db->ndesc + db->desc_per_kf - 1) / db->desc_per_kf;
+  db_merge_kernel<<<(nq + 127) / 128, 128, 0, (cudaStream_t)stream>>>((const unsigned long long*)d_gathered, world, nq, k, k,
+                                                                      (unsigned long long*)d_topk, d_votes, th_votes,
+                                                                      db->first_kf, db->desc_per_kf, first_index, n_kf);
   return cudaGetLastError() == cudaSuccess ? SWM_OK : SWM_E_CUDA;
 }
 

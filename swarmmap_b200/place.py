@@ -125,10 +125,24 @@ class PlaceShard:
         world = dist.get_world_size(self.group)
         if world == 1:
             return keys, votes
-        bucket = [torch.empty_like(keys) for _ in range(world)]
-        dist.all_gather(bucket, keys, group=self.group)
-        merged = merge_topk(torch.stack(bucket, 0), k)
-        return merged, self.votes_from_global(merged, th_votes)
+        if self._h is None:  # CPU test hook (gloo): exchange + torch merge
+            bucket = [torch.empty_like(keys) for _ in range(world)]
+            dist.all_gather(bucket, keys, group=self.group)
+            merged = merge_topk(torch.stack(bucket, 0), k)
+            return merged, self.votes_from_global(merged, th_votes)
+        # one all-gather of the (nq, k) key blocks into a (world, nq, k) buffer, then ONE merge kernel that also
+        # casts this shard's votes from the global best matches
+        nq = int(keys.shape[0])
+        gathered = torch.empty((world, nq, k), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(gathered, keys, group=self.group)
+        merged = torch.empty_like(keys)
+        votes = torch.zeros(self.n_kf, dtype=torch.int32, device=self.device)
+        st = torch.cuda.current_stream(self.device)
+        rc = self._lib.swm_db_merge_gathered(self._h, gathered.data_ptr(), world, nq, k, merged.data_ptr(),
+                                             votes.data_ptr(), int(th_votes), C.c_void_p(st.cuda_stream))
+        if rc != 0:
+            raise _lib.SwmError(f"swm_db_merge_gathered: {_lib.ERRORS.get(rc, rc)}")
+        return merged, votes
 
     def votes_from_global(self, merged, th_votes):
         """Per-keyframe votes of THIS shard from the merged result: a query votes for the keyframe owning

@@ -342,3 +342,33 @@ def test_db_top2_shard(oracle, swm, monkeypatch, kernel, nq, ndb):
     np.testing.assert_array_equal(votes.cpu().numpy(), exp_votes)
     assert lib.swm_db_size(h) == ndb
     lib.swm_db_destroy(h)
+
+
+@pytest.mark.parametrize("k", [1, 2])
+def test_db_merge_gathered_equals_single_shard(oracle, swm, k):
+    """The multi-GPU exchange step on one device: two shards scanned separately, their (nq, k) key blocks stacked the
+    way all_gather_into_tensor lays them out, merged by swm_db_merge_gathered on each 'rank' -> the keys of the
+    single-shard scan, and the two ranks' votes sum to the single-shard vote histogram."""
+    import ctypes as C
+    import torch
+    from swarmmap_b200 import _lib, place
+    lib = _lib.load()
+    rng = np.random.default_rng(21)
+    q, db = _db_case(rng, 333, 24000)
+    per_kf = 8
+    full = place.PlaceShard(db, per_kf, 0)
+    fk, fv = full.query_local(torch.from_numpy(q), k, 50)
+    cut = 11000 // per_kf * per_kf
+    shards = [place.PlaceShard(db[:cut], per_kf, 0), place.PlaceShard(db[cut:], per_kf, cut // per_kf)]
+    local = [s.query_local(torch.from_numpy(q), k, 50)[0] for s in shards]
+    gathered = torch.stack(local, 0).contiguous()
+    votes_sum = torch.zeros(len(db) // per_kf, dtype=torch.int32, device="cuda")
+    for r, s in enumerate(shards):
+        merged = torch.empty_like(local[0])
+        votes = torch.zeros(s.n_kf, dtype=torch.int32, device="cuda")
+        rc = lib.swm_db_merge_gathered(s._h, gathered.data_ptr(), 2, len(q), k, merged.data_ptr(), votes.data_ptr(), 50, None)
+        assert rc == 0
+        torch.cuda.synchronize()
+        assert torch.equal(merged, fk)
+        votes_sum[s.first_kf:s.first_kf + s.n_kf] += votes
+    assert torch.equal(votes_sum, fv)
