@@ -289,6 +289,14 @@ int swm_frame_upload(swm_frame* f, const swm_frame_view* v);
  * grid_starts: 64*48+1 entries, grid_items: up to n entries (same CSR as swm_grid_build). */
 int swm_frame_download(swm_frame* f, float* x, float* y, int32_t* octave, float* angle, uint8_t* desc,
                        int32_t* grid_starts, int32_t* grid_items);
+/* Binary keyframe-feature slab: the wire / on-disk form of a keyframe's features in
+ * place of the Boost text archive (code/src/MapUpdater.cc:192-230, code/include/KeyFrame.h:309-404).  Layout, little
+ * endian: uint32 magic "SWKF", uint32 version (1), int32 n, float min_x, max_x, min_y, max_y, uint32 reserved,
+ * float x[n], float y[n], int32 octave[n], float angle[n], uint8 desc[n][32] = 32 + 48 n bytes (about a quarter of
+ * the text archive).  export: five device-to-host copies; import: validates the header, uploads and rebuilds the grid. */
+size_t swm_frame_slab_bytes(int32_t n);
+int swm_frame_export(swm_frame* f, uint8_t* buf, size_t cap, size_t* bytes);
+int swm_frame_import(swm_frame* f, const uint8_t* buf, size_t bytes);
 
 int swm_match_init_resident(swm_matcher* m, const swm_frame* f1, const swm_frame* f2, float* prev_xy, int32_t* matches12,
                             int window, float nnratio, int check_ori, int* nmatches);

@@ -112,6 +112,9 @@ SYMBOLS = [
     ("swm_frame_from_extractor", _i, [_vp, _vp, _i, _vp, _vp]),
     ("swm_frame_upload", _i, [_vp, _vp]),
     ("swm_frame_download", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("swm_frame_slab_bytes", _sz, [C.c_int32]),
+    ("swm_frame_export", _i, [_vp, _vp, _sz, _vp]),
+    ("swm_frame_import", _i, [_vp, _vp, _sz]),
     ("swm_match_init_resident", _i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp]),
     ("swm_match_window_resident", _i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp]),
     ("swm_match_bow_resident", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp]),

@@ -2105,6 +2105,71 @@ int swm_frame_upload(swm_frame* f, const swm_frame_view* v) {
   return SWM_OK;
 }
 
+// Binary keyframe-feature slab: what travels instead of the Boost text archive of
+// mvKeysUn + mDescriptors (code/src/MapUpdater.cc:192-230, code/include/KeyFrame.h:309-404).  Little-endian:
+//   uint32 magic 'SWKF', uint32 version 1, int32 n, float min_x, max_x, min_y, max_y, uint32 reserved,
+//   float x[n], float y[n], int32 octave[n], float angle[n], uint8 desc[n][32]        = 32 + 48 n bytes
+// i.e. the resident frame's own arrays, so export is five device-to-host copies into the caller's buffer and import
+// five host-to-device copies plus the grid kernel.
+namespace {
+struct SlabHeader {
+  uint32_t magic, version;
+  int32_t n;
+  float min_x, max_x, min_y, max_y;
+  uint32_t reserved;
+};
+static_assert(sizeof(SlabHeader) == 32, "slab header layout");
+constexpr uint32_t kSlabMagic = 0x464B5753u;  // "SWKF"
+}  // namespace
+
+size_t swm_frame_slab_bytes(int32_t n) { return n < 0 ? 0 : sizeof(SlabHeader) + (size_t)n * 48; }
+
+int swm_frame_export(swm_frame* f, uint8_t* buf, size_t cap, size_t* bytes) {
+  if (!f) return SWM_E_INVALID;
+  if (!buf || !bytes) { f->err = "bad argument"; return SWM_E_INVALID; }
+  if (!f->dev.starts) { f->err = "frame has not been built"; return SWM_E_STATE; }
+  const size_t n = (size_t)f->n, need = swm_frame_slab_bytes(f->n);
+  *bytes = need;
+  if (cap < need) { f->err = "slab buffer too small"; return SWM_E_CAPACITY; }
+  FCK(f, cudaSetDevice(f->device));
+  FCK(f, cudaEventSynchronize(f->ready));
+  SlabHeader h{kSlabMagic, 1u, f->n, f->dev.min_x, f->dev.max_x, f->dev.min_y, f->dev.max_y, 0u};
+  memcpy(buf, &h, sizeof(h));
+  uint8_t* p = buf + sizeof(h);
+  if (n) {
+    FCK(f, cudaMemcpyAsync(p, f->b[0].p, n * 4, cudaMemcpyDeviceToHost, f->stream));
+    FCK(f, cudaMemcpyAsync(p + n * 4, f->b[1].p, n * 4, cudaMemcpyDeviceToHost, f->stream));
+    FCK(f, cudaMemcpyAsync(p + n * 8, f->b[2].p, n * 4, cudaMemcpyDeviceToHost, f->stream));
+    FCK(f, cudaMemcpyAsync(p + n * 12, f->b[3].p, n * 4, cudaMemcpyDeviceToHost, f->stream));
+    FCK(f, cudaMemcpyAsync(p + n * 16, f->b[4].p, n * 32, cudaMemcpyDeviceToHost, f->stream));
+    FCK(f, cudaStreamSynchronize(f->stream));
+  }
+  return SWM_OK;
+}
+
+int swm_frame_import(swm_frame* f, const uint8_t* buf, size_t bytes) {
+  if (!f) return SWM_E_INVALID;
+  SlabHeader h;
+  if (!buf || bytes < sizeof(h)) { f->err = "slab too short"; return SWM_E_INVALID; }
+  memcpy(&h, buf, sizeof(h));
+  if (h.magic != kSlabMagic || h.version != 1 || h.n < 0 || bytes < swm_frame_slab_bytes(h.n) || !(h.max_x > h.min_x) ||
+      !(h.max_y > h.min_y)) {
+    f->err = "not a version-1 keyframe slab";
+    return SWM_E_INVALID;
+  }
+  const size_t n = (size_t)h.n;
+  const uint8_t* p = buf + sizeof(h);
+  swm_frame_view v;
+  v.n = h.n;
+  v.x = reinterpret_cast<const float*>(p);
+  v.y = reinterpret_cast<const float*>(p + n * 4);
+  v.octave = reinterpret_cast<const int32_t*>(p + n * 8);
+  v.angle = reinterpret_cast<const float*>(p + n * 12);
+  v.desc = p + n * 16;
+  v.min_x = h.min_x; v.max_x = h.max_x; v.min_y = h.min_y; v.max_y = h.max_y;
+  return swm_frame_upload(f, &v);
+}
+
 int swm_frame_download(swm_frame* f, float* x, float* y, int32_t* octave, float* angle, uint8_t* desc,
                        int32_t* grid_starts, int32_t* grid_items) {
   if (!f) return SWM_E_INVALID;

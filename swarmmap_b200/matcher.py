@@ -105,6 +105,19 @@ class ResidentFrame:
         self.mvScaleFactors = frame.mvScaleFactors
         return self
 
+    def export_slab(self):
+        """The frame as a binary keyframe-feature slab (bytes): header + x, y, octave, angle, descriptors."""
+        nbytes = int(self._lib.swm_frame_slab_bytes(self.N))
+        buf = np.zeros(nbytes, np.uint8)
+        got = C.c_size_t(0)
+        self._check(self._lib.swm_frame_export(self._h, _lib.ptr(buf), nbytes, C.byref(got)), "swm_frame_export")
+        return buf[:got.value].tobytes()
+
+    def import_slab(self, blob):
+        buf = np.frombuffer(blob, np.uint8)
+        self._check(self._lib.swm_frame_import(self._h, _lib.ptr(buf), len(buf)), "swm_frame_import")
+        return self
+
     def download(self, grid=False):
         n = self.N
         x = np.zeros(n, np.float32); y = np.zeros(n, np.float32)

@@ -145,3 +145,30 @@ def test_frame_errors(swm, extracted):
         f.from_extractor(ex, 99, None, np.array([0, 752, 0, 480], np.float32))
     with pytest.raises(SwmError):
         f.from_extractor(ex, 0, None, np.array([0, 0, 0, 480], np.float32))
+
+
+def test_keyframe_slab_roundtrip(oracle, swm, extracted):
+    """Binary keyframe-feature slab: export -> bytes -> import on another frame gives the
+    same arrays and grid, 32 + 48 n bytes; corrupted headers are refused."""
+    from swarmmap_b200._lib import SwmError
+    from swarmmap_b200.matcher import Camera, ResidentFrame
+    ex, kps, desc, n = extracted
+    cam = Camera(*[float(c) for c in CAMERAS["euroc"]])
+    bounds = cam.bounds(752, 480)
+    a = ResidentFrame().from_extractor(ex, 2, cam, bounds)
+    blob = a.export_slab()
+    assert len(blob) == 32 + 48 * a.N and blob[:4] == b"SWKF"
+    b = ResidentFrame().import_slab(blob)
+    da, db = a.download(grid=True), b.download(grid=True)
+    for k in da:
+        np.testing.assert_array_equal(da[k], db[k])
+    from swarmmap_b200.matcher import Frame
+    z = np.zeros(0, np.float32)
+    empty = ResidentFrame().upload(Frame(z, z, np.zeros(0, np.int32), z, np.zeros((0, 32), np.uint8), (0, 0, 752, 480)))
+    assert ResidentFrame().import_slab(empty.export_slab()).N == 0
+    with pytest.raises(SwmError):
+        ResidentFrame().export_slab()  # never built
+    with pytest.raises(SwmError):
+        ResidentFrame().import_slab(b"XXXX" + blob[4:])
+    with pytest.raises(SwmError):
+        ResidentFrame().import_slab(blob[:100])
