@@ -413,6 +413,121 @@ class ORBmatcher {
     return nFused;
   }
 
+  // ---- Project MapPoints into a KeyFrame using a given Sim3 and search for duplicated MapPoints (loop closing,
+  // ORBmatcher.cc:891-1009).  Same split as the other Fuse: host projection, one swm_window_best call (no
+  // reprojection gate), then the in-order bookkeeping (vpReplacePoint / AddObservation).
+  template <class KeyFrameT, class MapPointT, class MatT>
+  int Fuse(KeyFrameT* pKF, const MatT& Scw, const std::vector<MapPointT*>& vpPoints, float th,
+           std::vector<MapPointT*>& vpReplacePoint) {
+    // Decompose Scw (:899-904): scw = |row 0 of sRcw|, Rcw = sRcw / scw, tcw = Scw[0:3, 3] / scw, Ow = -Rcw' tcw
+    double dot = 0;
+    for (int c = 0; c < 3; c++) dot += (double)Scw.template at<float>(0, c) * Scw.template at<float>(0, c);
+    const float scw = (float)std::sqrt(dot);
+    const double inv = 1.0 / scw;
+    float R[9], t[3], Ow[3];
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) R[3 * r + c] = (float)((double)Scw.template at<float>(r, c) * inv);
+      t[r] = (float)((double)Scw.template at<float>(r, 3) * inv);
+    }
+    for (int r = 0; r < 3; r++)
+      Ow[r] = (float)(-((double)R[r] * t[0] + (double)R[3 + r] * t[1] + (double)R[6 + r] * t[2]));
+    const auto spAlreadyFound = pKF->GetMapPoints();
+    const int M = (int)vpPoints.size();
+    std::vector<uint8_t> desc((size_t)M * 32, 0), valid(M, 0);
+    std::vector<float> u(M, 0.f), v(M, 0.f), radius(M, 0.f);
+    std::vector<int32_t> lo(M, -1), hi(M, -1);
+    for (int i = 0; i < M; i++) {
+      MapPointT* pMP = vpPoints[i];
+      if (pMP->isBad() || spAlreadyFound.count(pMP)) continue;             // :918-919
+      float Pw[3], Pc[3];
+      world_pos(pMP->GetGlobalPos(), Pw);
+      transform(R, t, Pw, Pc);
+      if (Pc[2] < 0.0f) continue;
+      const float invz = (float)(1.0 / Pc[2]);
+      const float pu = pKF->fx * (Pc[0] * invz) + pKF->cx, pv = pKF->fy * (Pc[1] * invz) + pKF->cy;
+      if (!pKF->IsInImage(pu, pv)) continue;
+      const float PO[3] = {Pw[0] - Ow[0], Pw[1] - Ow[1], Pw[2] - Ow[2]};
+      const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+      if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+      float Pn[3];
+      world_pos(pMP->GetNormal(), Pn);
+      if ((double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2] < 0.5 * dist3D) continue;
+      const int pred = pMP->PredictScale(dist3D, pKF->mfLogScaleFactor, pKF->mnScaleLevels);
+      valid[i] = 1;
+      u[i] = pu; v[i] = pv;
+      radius[i] = th * pKF->mvScaleFactors[pred];
+      lo[i] = pred - 1; hi[i] = pred;
+      std::memcpy(&desc[(size_t)i * 32], descriptor_of(pMP).ptr(0), 32);
+    }
+    swm_best_query q;
+    q.m = M; q.desc = desc.data(); q.u = u.data(); q.v = v.data(); q.radius = radius.data();
+    q.min_level = lo.data(); q.max_level = hi.data(); q.valid = valid.data();
+    q.inv_level_sigma2 = nullptr; q.nlevels = 0; q.chi2 = 0.0f;
+    std::vector<int32_t> best_idx(M, -1), best_dist(M, 256);
+    FlatFrame kf;
+    gather(*pKF, kf);
+    swm_frame_view vk = kf.view();
+    check(resident_of(*pKF, 0) ? swm_window_best_resident(m_, resident_of(*pKF, 0), &q, best_idx.data(), best_dist.data())
+                               : swm_window_best(m_, &vk, &q, best_idx.data(), best_dist.data()));
+    int nFused = 0;
+    for (int i = 0; i < M; i++) {
+      if (!valid[i] || best_idx[i] < 0 || best_dist[i] > TH_LOW) continue;  // :991
+      MapPointT* pMP = vpPoints[i];
+      MapPointT* pMPinKF = pKF->GetMapPoint(best_idx[i]);
+      if (pMPinKF) {
+        if (!pMPinKF->isBad()) vpReplacePoint[i] = pMPinKF;
+      } else {
+        pMP->AddObservation(pKF, best_idx[i]);
+        pKF->AddMapPoint(pMP, best_idx[i]);
+      }
+      nFused++;
+    }
+    return nFused;
+  }
+
+  // ---- Search matches between MapPoints seen in KF1 and KF2 transforming by a Sim3 [s12*R12|t12]
+  // (ORBmatcher.cc:1011-1221).  Host: the two projection loops; GPU: two swm_window_best calls (levels [pred - 1,
+  // pred], no reprojection gate, accept at TH_HIGH); host: the mutual-agreement check.
+  template <class KeyFrameT, class MapPointT, class MatT>
+  int SearchBySim3(KeyFrameT* pKF1, KeyFrameT* pKF2, std::vector<MapPointT*>& vpMatches12, const float& s12, const MatT& R12,
+                   const MatT& t12, const float th) {
+    float R1w[9], t1w[3], R2w[9], t2w[3], sR12[9], sR21[9], T12[3], t21[3];
+    load_pose(pKF1->GetRotation(), pKF1->GetTranslation(), R1w, t1w);
+    load_pose(pKF2->GetRotation(), pKF2->GetTranslation(), R2w, t2w);
+    for (int r = 0; r < 3; r++) {
+      T12[r] = t12.template at<float>(r);
+      for (int c = 0; c < 3; c++) {
+        sR12[3 * r + c] = (float)((double)s12 * (double)R12.template at<float>(r, c));          // s12 * R12
+        sR21[3 * r + c] = (float)((1.0 / s12) * (double)R12.template at<float>(c, r));          // (1.0 / s12) * R12.t()
+      }
+    }
+    for (int r = 0; r < 3; r++)  // t21 = -sR21 * t12
+      t21[r] = (float)(-((double)sR21[3 * r] * T12[0] + (double)sR21[3 * r + 1] * T12[1] + (double)sR21[3 * r + 2] * T12[2]));
+    const std::vector<MapPointT*> mp1 = pKF1->GetMapPointMatches(), mp2 = pKF2->GetMapPointMatches();
+    const int N1 = (int)mp1.size(), N2 = (int)mp2.size();
+    std::vector<uint8_t> already1(N1, 0), already2(N2, 0);
+    for (int i = 0; i < N1; i++) {
+      MapPointT* pMP = vpMatches12[i];
+      if (pMP) {
+        already1[i] = 1;
+        const int idx2 = pMP->GetIndexInKeyFrame(pKF2);
+        if (idx2 >= 0 && idx2 < N2) already2[idx2] = 1;
+      }
+    }
+    std::vector<int32_t> match1, match2;
+    sim3_direction(pKF1, pKF2, mp1, already1, R1w, t1w, sR21, t21, th, match1);  // KF1's points into KF2
+    sim3_direction(pKF2, pKF1, mp2, already2, R2w, t2w, sR12, T12, th, match2);  // KF2's points into KF1
+    int nFound = 0;
+    for (int i1 = 0; i1 < N1; i1++) {  // :1207-1217
+      const int idx2 = match1[i1];
+      if (idx2 >= 0 && match2[idx2] == i1) {
+        vpMatches12[i1] = mp2[idx2];
+        nFound++;
+      }
+    }
+    return nFound;
+  }
+
   // ---- Matching to triangulate new MapPoints, with the epipolar constraint (ORBmatcher.cc:599-749), monocular.
   // F12 is the 3x3 CV_32F fundamental matrix LocalMapping::ComputeF12 builds.  The stereo branches need mvuRight >= 0
   // and are not served (bOnlyStereo must be false; SwarmMap is monocular).
@@ -536,6 +651,59 @@ class ORBmatcher {
       o.angle[i] = F.mvKeysUn[i].angle; o.octave[i] = F.mvKeysUn[i].octave;
       std::memcpy(&o.desc[(size_t)i * 32], F.mDescriptors.ptr(i), 32);
     }
+  }
+  template <class MatR, class MatTr>
+  static void load_pose(const MatR& Rm, const MatTr& tm, float R[9], float t[3]) {
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) R[3 * r + c] = Rm.template at<float>(r, c);
+      t[r] = tm.template at<float>(r);
+    }
+  }
+  // One direction of SearchBySim3 (:1055-1129 / :1132-1204): the source keyframe's MapPoints, moved into the target
+  // camera by (Rsw, tsw) then (sR, tt), searched in the target keyframe.  match[i] = target index or -1.
+  template <class KeyFrameT, class MapPointT>
+  void sim3_direction(KeyFrameT* pSrc, KeyFrameT* pTgt, const std::vector<MapPointT*>& mps, const std::vector<uint8_t>& already,
+                      const float Rsw[9], const float tsw[3], const float sR[9], const float tt[3], float th,
+                      std::vector<int32_t>& match) {
+    (void)pSrc;
+    const int M = (int)mps.size();
+    match.assign(M, -1);
+    std::vector<uint8_t> desc((size_t)M * 32, 0), valid(M, 0);
+    std::vector<float> u(M, 0.f), v(M, 0.f), radius(M, 0.f);
+    std::vector<int32_t> lo(M, -1), hi(M, -1);
+    for (int i = 0; i < M; i++) {
+      MapPointT* pMP = mps[i];
+      if (!pMP || already[i]) continue;
+      if (pMP->isBad()) continue;
+      float Pw[3], Pa[3], Pb[3];
+      world_pos(pMP->GetWorldPos(), Pw);
+      transform(Rsw, tsw, Pw, Pa);
+      transform(sR, tt, Pa, Pb);
+      if (Pb[2] < 0.0) continue;
+      const float invz = (float)(1.0 / Pb[2]);
+      const float pu = pTgt->fx * (Pb[0] * invz) + pTgt->cx, pv = pTgt->fy * (Pb[1] * invz) + pTgt->cy;
+      if (!pTgt->IsInImage(pu, pv)) continue;
+      const float dist3D = (float)std::sqrt((double)Pb[0] * Pb[0] + (double)Pb[1] * Pb[1] + (double)Pb[2] * Pb[2]);
+      if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
+      const int pred = pMP->PredictScale(dist3D, pTgt->mfLogScaleFactor, pTgt->mnScaleLevels);
+      valid[i] = 1;
+      u[i] = pu; v[i] = pv;
+      radius[i] = th * pTgt->mvScaleFactors[pred];
+      lo[i] = pred - 1; hi[i] = pred;
+      std::memcpy(&desc[(size_t)i * 32], descriptor_of(pMP).ptr(0), 32);
+    }
+    swm_best_query q;
+    q.m = M; q.desc = desc.data(); q.u = u.data(); q.v = v.data(); q.radius = radius.data();
+    q.min_level = lo.data(); q.max_level = hi.data(); q.valid = valid.data();
+    q.inv_level_sigma2 = nullptr; q.nlevels = 0; q.chi2 = 0.0f;
+    std::vector<int32_t> best_idx(M, -1), best_dist(M, 256);
+    FlatFrame kf;
+    gather(*pTgt, kf);
+    swm_frame_view vk = kf.view();
+    check(resident_of(*pTgt, 0) ? swm_window_best_resident(m_, resident_of(*pTgt, 0), &q, best_idx.data(), best_dist.data())
+                                : swm_window_best(m_, &vk, &q, best_idx.data(), best_dist.data()));
+    for (int i = 0; i < M; i++)
+      if (valid[i] && best_idx[i] >= 0 && best_dist[i] <= TH_HIGH) match[i] = best_idx[i];  // :1125-1128
   }
   template <class MapPointT>
   static cv::Mat descriptor_of(MapPointT* p) { return p->GetDescriptor(); }

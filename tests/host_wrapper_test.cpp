@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <map>
+#include <set>
 #include <vector>
 
 #include "../swarmmap_b200/host/ORBextractor.h"
@@ -39,6 +40,7 @@ struct MapPoint {
   std::map<void*, int> obs;
   MapPoint* replaced_by = nullptr;
   bool IsInKeyFrame(void* kf) { return obs.count(kf) > 0; }
+  int GetIndexInKeyFrame(void* kf) { auto it = obs.find(kf); return it == obs.end() ? -1 : it->second; }
   void AddObservation(void* kf, int idx) { obs[kf] = idx; nobs = (int)obs.size(); }
   void Replace(MapPoint* other) { bad = true; replaced_by = other; }
 };
@@ -64,6 +66,7 @@ struct Frame {
   Mat4 mOw, mRcw, mtcw;
   MapPoint* GetMapPoint(int i) { return mvpMapPoints[i]; }
   void AddMapPoint(MapPoint* p, int i) { mvpMapPoints[i] = p; }
+  std::set<MapPoint*> GetMapPoints() { std::set<MapPoint*> s; for (auto* p : mvpMapPoints) if (p) s.insert(p); return s; }
   std::vector<float> mvInvLevelSigma2;
   Mat4 GetCameraCenter() { return mOw; }
   Mat4 GetRotation() { return mRcw; }
@@ -246,6 +249,46 @@ int main(int argc, char** argv) {
       std::printf("HOST_WRAPPER_FAIL fuse\n");
       return 1;
     }
+  }
+  // Fuse with a Sim3 pose (loop closing): identity similarity scaled by 2 (Scw = 2 [I|0]) projects the points onto
+  // their keypoints; even slots hold a point (-> vpReplacePoint), odd slots are empty (-> AddMapPoint)
+  {
+    Frame kf;
+    fill(kf, ex, img);
+    std::vector<MapPoint> fresh(pts.begin(), pts.end()), held(kf.N);
+    for (auto& p : fresh) { p.obs.clear(); p.nobs = 0; p.bad = false; }
+    for (int j = 0; j < kf.N; j += 2) kf.mvpMapPoints[j] = &held[j];
+    std::vector<MapPoint*> cand, repl(kf.N, nullptr);
+    for (auto& p : fresh) cand.push_back(&p);
+    Mat4 Scw;
+    for (int i = 0; i < 16; i++) Scw.v[i] = 0;
+    Scw.v[0] = Scw.v[5] = Scw.v[10] = 2.0f; Scw.v[15] = 1.0f;
+    ORB_SLAM2::ORBmatcher mf2(0.8f, true);
+    const int n_fused2 = mf2.Fuse(&kf, Scw, cand, 4.0f, repl);
+    int n_repl = 0, n_added = 0;
+    for (int j = 0; j < kf.N; j++) { n_repl += repl[j] != nullptr; n_added += (j % 2 == 1) && kf.mvpMapPoints[j] != nullptr; }
+    std::printf("fuse(Scw): %d fused, %d to replace, %d added\n", n_fused2, n_repl, n_added);
+    if (n_fused2 < kf.N * 8 / 10 || n_repl + n_added != n_fused2 || n_repl < kf.N / 2 * 7 / 10) { std::printf("HOST_WRAPPER_FAIL fuse sim3\n"); return 1; }
+  }
+  // SearchBySim3 with the identity similarity between two keyframes of the same image: every MapPoint of one keyframe
+  // must find the same keypoint in the other, in both directions
+  {
+    Frame a, b;
+    fill(a, ex, img);
+    fill(b, ex, img);
+    for (int i = 0; i < 3; i++) { a.mtcw.v[i] = 0.0f; b.mtcw.v[i] = 0.0f; }
+    std::vector<MapPoint> pa(pts.begin(), pts.end()), pb(pts.begin(), pts.end());
+    for (int i = 0; i < a.N; i++) { a.mvpMapPoints[i] = &pa[i]; b.mvpMapPoints[i] = &pb[i]; }
+    std::vector<MapPoint*> m12(a.N, nullptr);
+    Mat4 R12, t12;
+    for (int i = 0; i < 3; i++) t12.v[i] = 0.0f;
+    const float s12 = 1.0f;
+    ORB_SLAM2::ORBmatcher ms(0.75f, true);
+    const int n_sim3 = ms.SearchBySim3(&a, &b, m12, s12, R12, t12, 7.5f);
+    int same = 0;
+    for (int i = 0; i < a.N; i++) same += m12[i] == &pb[i];
+    std::printf("sim3: %d mutual matches, %d onto the same keypoint\n", n_sim3, same);
+    if (n_sim3 < a.N * 8 / 10 || same < n_sim3 * 9 / 10) { std::printf("HOST_WRAPPER_FAIL sim3\n"); return 1; }
   }
   const int d0 = ORB_SLAM2::ORBmatcher::DescriptorDistance(f1.mDescriptors.row(0), f1.mDescriptors.row(0));
   const int d1 = ORB_SLAM2::ORBmatcher::DescriptorDistance(f1.mDescriptors.row(0), f1.mDescriptors.row(1));
