@@ -52,6 +52,84 @@ def test_oracle_reproduces_match_golden(oracle):
         np.testing.assert_array_equal(prev, g[f"prev_{k}"])
 
 
+def test_oracle_reproduces_cv2_undistort_golden(oracle):
+    """undistort_cv2.npz holds cv2.undistortPoints outputs (OpenCV is the third-party reference behind
+    Frame::UndistortKeyPoints): the oracle equals them bit for bit, without cv2 in the loop."""
+    g = _load("undistort_cv2.npz")
+    for name in ("euroc", "tum1"):
+        np.testing.assert_array_equal(oracle.undistort_points(g["xy"], g[f"cam_{name}"]), g[f"und_{name}"])
+        m = g[f"und_{name}"][-4:]
+        exp = [min(m[0, 0], m[2, 0]), max(m[1, 0], m[3, 0]), min(m[0, 1], m[1, 1]), max(m[2, 1], m[3, 1])]
+        np.testing.assert_array_equal(oracle.image_bounds(752, 480, g[f"cam_{name}"]), np.array(exp, np.float32))
+
+
+def _next_rows():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    return mg
+
+
+def test_oracle_reproduces_next_rows_golden(oracle):
+    g = _load("next_rows.npz")
+    mg = _next_rows()
+    i = mg.next_rows_inputs()
+    assert sha(i["seq"]) == str(g["seq_sha"]) and sha(np.frombuffer(i["blob"], np.uint8)) == str(g["vocab_sha"])
+    out = mg.next_rows_outputs(i)
+    for k, v in out.items():
+        np.testing.assert_array_equal(np.asarray(v), g[k], err_msg=k)
+
+
+@pytest.mark.gpu
+def test_gpu_reproduces_next_rows_golden(swm):
+    """The CUDA path against the committed outputs, no oracle in the loop."""
+    from swarmmap_b200.bow import ORBVocabulary
+    from swarmmap_b200.matcher import Frame, ORBmatcher
+    from swarmmap_b200.orb import ORBextractor
+    g = _load("next_rows.npz")
+    seq = synth.make_sequence(2, 752, 480, 20220406)
+    assert sha(seq) == str(g["seq_sha"])
+    ex = ORBextractor(1000, 1.2, 8, 20, 7)
+    sf = ex.GetScaleFactors()
+    fs = [Frame.from_keypoints(*ex(img), 752, 480, sf) for img in seq]
+    blob = synth.make_vocabulary(10, 3, seed=42)
+    r = ORBVocabulary(blob).transform(fs[0].desc, 2)
+    np.testing.assert_array_equal(r.word_ids, g["bow_words"])
+    np.testing.assert_array_equal(r.values, g["bow_values"])
+    np.testing.assert_array_equal(r.node_ids, g["bow_nodes"])
+    np.testing.assert_array_equal(r.feats, g["bow_feats"])
+    rng = np.random.default_rng(17)
+    from swarmmap_b200.matcher import FeatureVector
+    node = lambda f: (f.desc[:, 0].astype(np.int64) * 7 + f.desc[:, 5]) % 40
+    fv = [FeatureVector(node(f)) for f in fs]
+    v1 = (rng.random(fs[0].N) < 0.7).astype(np.uint8)
+    v2 = (rng.random(fs[1].N) < 0.8).astype(np.uint8)
+    K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1]])
+    t = np.array([0.3, 0.05, 0.02])
+    tx = np.array([[0, -t[2], t[1]], [t[2], 0, -t[0]], [-t[1], t[0], 0]])
+    F12 = (np.linalg.inv(K).T @ tx @ np.linalg.inv(K)).astype(np.float32)
+    s2 = (sf * sf).astype(np.float32)
+    m = ORBmatcher(0.6, True)
+    tn, tm = m.SearchForTriangulation(fs[0], fv[0], v1, fs[1], fv[1], v2, F12, 400.0, 200.0, sf, s2)
+    assert tn == int(g["tri_n"])
+    np.testing.assert_array_equal(tm, g["tri_matches"])
+    u = (fs[0].x + rng.normal(0, 1.5, fs[0].N)).astype(np.float32)
+    v = (fs[0].y + rng.normal(0, 1.5, fs[0].N)).astype(np.float32)
+    pred = np.clip(fs[0].octave + rng.integers(-1, 2, fs[0].N), 0, 7).astype(np.int32)
+    radius = (np.float32(12.0) * sf[pred]).astype(np.float32)
+    inv_s2 = (np.float32(1.0) / s2).astype(np.float32)
+    bi, bd = m.window_best(fs[1], fs[0].desc, u, v, radius, pred, np.ones(fs[0].N, np.uint8), inv_s2, 5.99)
+    np.testing.assert_array_equal(bi, g["best_idx"])
+    np.testing.assert_array_equal(bd, g["best_dist"])
+    sizes = [1, 2, 3, 8, 0, 31, 64]
+    obs = np.concatenate([fs[0].desc[:20], fs[1].desc[:89]])[:sum(sizes)]
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    db, dm = m.ComputeDistinctiveDescriptors(obs, offsets)
+    np.testing.assert_array_equal(db, g["distinct_idx"])
+    np.testing.assert_array_equal(dm, g["distinct_median"])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["extract_euroc.npz", "extract_kitti.npz"])
 def test_gpu_reproduces_extract_golden(swm, name):
