@@ -344,6 +344,7 @@ struct ResolveArgs {
   const int32_t* row_start;
   const int32_t* cand_idx;
   const uint32_t* cand_val;
+  int32_t* row_list;        // scratch, `rows` entries: the valid, non-empty rows in order (built by the kernel)
   int n1, n2;
   const float* angle1;      // per source
   const float* angle2;      // per target
@@ -405,9 +406,10 @@ constexpr int kResolveWarps = 32;
 __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs a) {
   extern __shared__ __align__(16) uint8_t dsm[];
   __shared__ int s_row[kResolveWarps], s_accept[kResolveWarps], s_best_idx[kResolveWarps], s_best_dist[kResolveWarps];
-  __shared__ int s_second_idx[kResolveWarps], s_after[kResolveWarps];
+  __shared__ int s_second_idx[kResolveWarps];
   __shared__ int s_src[kResolveWarps], s_blk[kResolveWarps], s_bin[kResolveWarps];
-  __shared__ int s_nb, s_cursor, s_nmatches, s_batches;
+  __shared__ int s_cursor, s_nmatches, s_batches, s_nlist;
+  __shared__ int s_wsum[kResolveWarps];
   __shared__ int s_hist[kHistoLen];
   __shared__ int s_keep[3];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -430,48 +432,73 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
     s_cursor = 0;
     s_nmatches = 0;
     s_batches = 0;
+    s_nlist = 0;
   }
   __syncthreads();
 
-  while (true) {
-    // ---- 1. next batch: up to kResolveWarps valid, non-empty rows in order
-    if (wid == 0) {
-      int nb = 0, cur = s_cursor;
-      while (nb < kResolveWarps && cur < a.rows) {
-        const int r = cur + lane;
-        bool ok = false;
-        if (r < a.rows) {
-          const int s = a.row_src ? a.row_src[r] : r;
-          ok = (!a.row_valid || a.row_valid[s]) && a.row_start[r] != a.row_start[r + 1];
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, ok);
-        const int k = nb + __popc(m & ((1u << lane) - 1));
-        if (ok && k < kResolveWarps) {
-          s_row[k] = r;
-          s_after[k] = r + 1;
-        }
-        nb = min(kResolveWarps, nb + __popc(m));
-        cur += 32;
-      }
-      if (lane == 0) s_nb = nb;
+  // ---- 0. the valid, non-empty rows in order, compacted once: a batch is then 32 consecutive list entries and the
+  // commit step can assemble the next batch from registers (no dependent global loads between batches)
+  for (int r0 = 0; r0 < a.rows; r0 += blockDim.x) {
+    const int r = r0 + tid;
+    bool ok = false;
+    if (r < a.rows) {
+      const int s = a.row_src ? a.row_src[r] : r;
+      ok = (!a.row_valid || a.row_valid[s]) && a.row_start[r] != a.row_start[r + 1];
+    }
+    const unsigned bm = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) s_wsum[wid] = __popc(bm);
+    __syncthreads();
+    int off = s_nlist;
+    for (int w = 0; w < wid; w++) off += s_wsum[w];
+    if (ok) a.row_list[off + __popc(bm & ((1u << lane) - 1))] = r;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < kResolveWarps; w++) tot += s_wsum[w];
+      s_nlist += tot;
     }
     __syncthreads();
-    const int nb = s_nb;
-    if (nb == 0) break;
+  }
+  const int n_list = s_nlist;
+  __threadfence_block();
+  if (wid == 0) s_row[lane] = lane < n_list ? a.row_list[lane] : -1;
+  __syncthreads();
 
-    // ---- 2. speculative evaluation, one warp per row
+  while (true) {
+    const int cursor = s_cursor;
+    const int nb = min(kResolveWarps, n_list - cursor);
+    if (nb <= 0) break;
+    // the 32 list entries after this batch, fetched by warp 0 while the batch is evaluated (used by the commit
+    // step to assemble the next batch)
+    int pre = -1;
+    if (wid == 0 && cursor + kResolveWarps + lane < n_list) pre = a.row_list[cursor + kResolveWarps + lane];
+
+    // ---- 1. speculative evaluation, one warp per row
     if (wid < nb) {
       int b, e, best_pos = -1;
       const int r = s_row[wid];
       b = a.row_start[r];
       e = a.row_start[r + 1];
+      const bool small = e - b <= 32;  // the common case: one candidate per lane, loaded once
+      int rj = 0;
+      uint32_t rval = 0;
+      bool rok = false;
       unsigned long long best = kNone;  // key = dist << 32 | position: smallest distance, first in enumeration order
-      for (int c = b + lane; c < e; c += 32) {
-        const int j = a.cand_idx[c];
-        const unsigned dist = a.cand_val[c] & 0xFFFFu;
-        if (!cand_skip(a, matched_dist, blocked, j, dist)) {
-          const unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(c - b);
-          best = key < best ? key : best;
+      if (small) {
+        if (b + lane < e) {
+          rj = a.cand_idx[b + lane];
+          rval = a.cand_val[b + lane];
+          rok = !cand_skip(a, matched_dist, blocked, rj, rval & 0xFFFFu);
+        }
+        if (rok) best = ((unsigned long long)(rval & 0xFFFFu) << 32) | (unsigned)lane;
+      } else {
+        for (int c = b + lane; c < e; c += 32) {
+          const int j = a.cand_idx[c];
+          const unsigned dist = a.cand_val[c] & 0xFFFFu;
+          if (!cand_skip(a, matched_dist, blocked, j, dist)) {
+            const unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(c - b);
+            best = key < best ? key : best;
+          }
         }
       }
       best = warp_min_u64(best);
@@ -480,33 +507,42 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
       if (best != kNone) {
         best_pos = (int)(best & 0xFFFFFFFFu);
         best_dist = (int)(best >> 32);
-        best_idx = a.cand_idx[b + best_pos];
+        best_idx = small ? __shfl_sync(0xffffffffu, rj, best_pos) : a.cand_idx[b + best_pos];
         const bool need_second = !(a.mode == kModeWindow && a.ratio_mode == 0);
         int second_dist = a.mode == kModeInit ? 0x7FFFFFFF : 256, second_level = -1;  // INT_MAX (:404) vs 256 (:57,:190)
         if (need_second) {
           // second best: P = first minimum before the winner, Q = first minimum after it; the running
           // "bestDist2" of the reference ends as P if P <= Q else Q (matcher section).
           unsigned long long p = kNone, q = kNone;
-          for (int c = b + lane; c < e; c += 32) {
-            if (c - b == best_pos) continue;
-            const int j = a.cand_idx[c];
-            const unsigned dist = a.cand_val[c] & 0xFFFFu;
-            if (!cand_skip(a, matched_dist, blocked, j, dist)) {
-              const unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(c - b);
-              if (c - b < best_pos) p = key < p ? key : p;
-              else q = key < q ? key : q;
+          if (small) {
+            if (rok && lane != best_pos) {
+              const unsigned long long key = ((unsigned long long)(rval & 0xFFFFu) << 32) | (unsigned)lane;
+              if (lane < best_pos) p = key;
+              else q = key;
+            }
+          } else {
+            for (int c = b + lane; c < e; c += 32) {
+              if (c - b == best_pos) continue;
+              const int j = a.cand_idx[c];
+              const unsigned dist = a.cand_val[c] & 0xFFFFu;
+              if (!cand_skip(a, matched_dist, blocked, j, dist)) {
+                const unsigned long long key = ((unsigned long long)dist << 32) | (unsigned)(c - b);
+                if (c - b < best_pos) p = key < p ? key : p;
+                else q = key < q ? key : q;
+              }
             }
           }
           p = warp_min_u64(p);
           q = warp_min_u64(q);
           const unsigned long long sec = (p >> 32) <= (q >> 32) ? p : q;
           if (sec != kNone) {
+            const int sp = (int)(sec & 0xFFFFFFFFu);
             second_dist = (int)(sec >> 32);
-            second_level = (int)(a.cand_val[b + (int)(sec & 0xFFFFFFFFu)] >> 16);
-            second_idx = a.cand_idx[b + (int)(sec & 0xFFFFFFFFu)];
+            second_level = (int)((small ? __shfl_sync(0xffffffffu, rval, sp) : a.cand_val[b + sp]) >> 16);
+            second_idx = small ? __shfl_sync(0xffffffffu, rj, sp) : a.cand_idx[b + sp];
           }
         }
-        const int best_level = (int)(a.cand_val[b + best_pos] >> 16);
+        const int best_level = (int)((small ? __shfl_sync(0xffffffffu, rval, best_pos) : a.cand_val[b + best_pos]) >> 16);
         if (a.mode == kModeInit) {
           accept = best_dist <= kThLow && (float)best_dist < __fmul_rn((float)second_dist, a.nnratio);  // :426-427
         } else if (a.mode == kModeWindow) {
@@ -586,10 +622,16 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
       for (int o = 16; o > 0; o >>= 1) delta += __shfl_xor_sync(0xffffffffu, delta, o);
       __syncwarp();
       if (k < nb && acc) mark[bi] = 0x7FFFFFFF;
+      // next batch = the uncommitted tail of this one followed by the prefetched list entries
+      const int keep = first + lane;
+      const int old_row = keep < kResolveWarps ? s_row[keep] : -1;
+      const int from_pre = __shfl_sync(0xffffffffu, pre, (lane - (kResolveWarps - first)) & 31);
+      __syncwarp();
+      s_row[lane] = keep < kResolveWarps ? old_row : from_pre;
       if (lane == 0) {
         s_nmatches += delta;
         s_batches++;
-        s_cursor = first < nb ? s_row[first] : s_after[nb - 1];
+        s_cursor = cursor + first;
       }
     }
     __syncthreads();
@@ -1131,6 +1173,7 @@ struct swm_matcher {
   DevBuf f[2][6];  // x, y, octave, angle, desc, (grid starts+items+cell_of)
   DevBuf q[10];
   DevBuf iq[5];    // SearchForInitialization's source rows, built on the device (owned)
+  DevBuf rowlist;  // resolve_kernel's compacted row list
   DevBuf rows[5];  // row_count, row_start, cand_idx, cand_val, row_src
   DevBuf state[7]; // blocked, matched_dist, matches21, out, ev_bin, ev_tgt, nmatches/prev
   // upload arena: every host array of a call is packed into one pinned buffer and sent with ONE copy
@@ -1145,6 +1188,7 @@ struct swm_matcher {
     for (auto& a : f) for (auto& b : a) b.release();
     for (auto& b : q) b.release();
     for (auto& b : iq) b.release();
+    rowlist.release();
     for (auto& b : rows) b.release();
     for (auto& b : state) b.release();
   }
@@ -1359,7 +1403,10 @@ int launch_resolve(swm_matcher* m, const ResolveArgs& a) {
     MCK(m, cudaFuncSetAttribute(resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set[m->device & 63] = true;
   }
-  resolve_kernel<<<1, kResolveWarps * 32, bytes, m->stream>>>(a);
+  MCK(m, m->rowlist.ensure(((size_t)a.rows + 64) * 4));
+  ResolveArgs ra = a;
+  ra.row_list = m->rowlist.as<int32_t>();
+  resolve_kernel<<<1, kResolveWarps * 32, bytes, m->stream>>>(ra);
   MCK(m, cudaGetLastError());
   return SWM_OK;
 }
