@@ -407,7 +407,8 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
   extern __shared__ __align__(16) uint8_t dsm[];
   __shared__ int s_row[kResolveWarps], s_accept[kResolveWarps], s_best_idx[kResolveWarps], s_best_dist[kResolveWarps];
   __shared__ int s_second_idx[kResolveWarps];
-  __shared__ int s_src[kResolveWarps], s_blk[kResolveWarps], s_bin[kResolveWarps];
+  __shared__ int s_rb[kResolveWarps], s_re[kResolveWarps];  // candidate span of each row of the batch
+  __shared__ int s_src[kResolveWarps], s_blk[kResolveWarps];
   __shared__ int s_cursor, s_nmatches, s_batches, s_nlist;
   __shared__ int s_wsum[kResolveWarps];
   __shared__ int s_hist[kHistoLen];
@@ -461,7 +462,12 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
   }
   const int n_list = s_nlist;
   __threadfence_block();
-  if (wid == 0) s_row[lane] = lane < n_list ? a.row_list[lane] : -1;
+  if (wid == 0) {
+    const int r = lane < n_list ? a.row_list[lane] : -1;
+    s_row[lane] = r;
+    s_rb[lane] = r >= 0 ? a.row_start[r] : 0;
+    s_re[lane] = r >= 0 ? a.row_start[r + 1] : 0;
+  }
   __syncthreads();
 
   while (true) {
@@ -470,15 +476,19 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
     if (nb <= 0) break;
     // the 32 list entries after this batch, fetched by warp 0 while the batch is evaluated (used by the commit
     // step to assemble the next batch)
-    int pre = -1;
-    if (wid == 0 && cursor + kResolveWarps + lane < n_list) pre = a.row_list[cursor + kResolveWarps + lane];
+    int pre = -1, pre_b = 0, pre_e = 0;
+    if (wid == 0 && cursor + kResolveWarps + lane < n_list) {
+      pre = a.row_list[cursor + kResolveWarps + lane];
+      pre_b = a.row_start[pre];
+      pre_e = a.row_start[pre + 1];
+    }
 
     // ---- 1. speculative evaluation, one warp per row
     if (wid < nb) {
       int b, e, best_pos = -1;
       const int r = s_row[wid];
-      b = a.row_start[r];
-      e = a.row_start[r + 1];
+      b = s_rb[wid];
+      e = s_re[wid];
       const bool small = e - b <= 32;  // the common case: one candidate per lane, loaded once
       int rj = 0;
       uint32_t rval = 0;
@@ -565,7 +575,6 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
         const int s = a.row_src ? a.row_src[r] : r;
         s_src[wid] = s;
         s_blk[wid] = (a.mode == kModeWindow && accept) ? a.blocks[s] : 1;
-        s_bin[wid] = (accept && a.check_ori) ? rot_bin(a.angle1[s], a.angle2[best_idx]) : -1;
         if (accept) atomicMin(mark + best_idx, wid);
       }
     }
@@ -614,8 +623,8 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
         }
         delta++;
         if (a.check_ori) {
-          a.ev_bin[s] = s_bin[k];
-          a.ev_tgt[s] = ev_tgt;
+          a.ev_bin[s] = bi;  // the partner; turned into its histogram bin after the loop (keeps two dependent
+          a.ev_tgt[s] = ev_tgt;  // global loads out of every batch)
         }
       }
 #pragma unroll
@@ -624,10 +633,15 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
       if (k < nb && acc) mark[bi] = 0x7FFFFFFF;
       // next batch = the uncommitted tail of this one followed by the prefetched list entries
       const int keep = first + lane;
-      const int old_row = keep < kResolveWarps ? s_row[keep] : -1;
-      const int from_pre = __shfl_sync(0xffffffffu, pre, (lane - (kResolveWarps - first)) & 31);
+      const bool old = keep < kResolveWarps;
+      const int old_row = old ? s_row[keep] : -1, old_b = old ? s_rb[keep] : 0, old_e = old ? s_re[keep] : 0;
+      const int src_lane = (lane - (kResolveWarps - first)) & 31;
+      const int from_pre = __shfl_sync(0xffffffffu, pre, src_lane);
+      const int from_b = __shfl_sync(0xffffffffu, pre_b, src_lane), from_e = __shfl_sync(0xffffffffu, pre_e, src_lane);
       __syncwarp();
-      s_row[lane] = keep < kResolveWarps ? old_row : from_pre;
+      s_row[lane] = old ? old_row : from_pre;
+      s_rb[lane] = old ? old_b : from_b;
+      s_re[lane] = old ? old_e : from_e;
       if (lane == 0) {
         s_nmatches += delta;
         s_batches++;
@@ -641,8 +655,14 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
   if (a.check_ori) {
     if (tid < kHistoLen) s_hist[tid] = 0;
     __syncthreads();
-    for (int s = tid; s < a.n1; s += blockDim.x)
-      if (a.ev_bin[s] >= 0) atomicAdd(&s_hist[a.ev_bin[s]], 1);
+    for (int s = tid; s < a.n1; s += blockDim.x) {
+      const int partner = a.ev_bin[s];
+      if (partner >= 0) {
+        const int bin = rot_bin(a.angle1[s], a.angle2[partner]);
+        a.ev_bin[s] = bin;
+        atomicAdd(&s_hist[bin], 1);
+      }
+    }
     __syncthreads();
     if (tid == 0) {  // ComputeThreeMaxima, :1475-1506
       int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
