@@ -490,6 +490,9 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
       b = s_rb[wid];
       e = s_re[wid];
       const bool small = e - b <= 32;  // the common case: one candidate per lane, loaded once
+      // what the in-order commit needs from global memory, requested before the candidate scan (uniform address)
+      const int src_s = a.row_src ? a.row_src[r] : r;
+      const int src_blk = a.mode == kModeWindow ? a.blocks[src_s] : 1;
       int rj = 0;
       uint32_t rval = 0;
       bool rok = false;
@@ -500,7 +503,9 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
           rval = a.cand_val[b + lane];
           rok = !cand_skip(a, matched_dist, blocked, rj, rval & 0xFFFFu);
         }
-        if (rok) best = ((unsigned long long)(rval & 0xFFFFu) << 32) | (unsigned)lane;
+        // one hardware warp reduction on a 32-bit key (distance << 8 | lane) instead of ten shuffles
+        const unsigned k32 = __reduce_min_sync(0xffffffffu, rok ? (((rval & 0xFFFFu) << 8) | (unsigned)lane) : 0xFFFFFFFFu);
+        if (k32 != 0xFFFFFFFFu) best = ((unsigned long long)(k32 >> 8) << 32) | (k32 & 31u);
       } else {
         for (int c = b + lane; c < e; c += 32) {
           const int j = a.cand_idx[c];
@@ -510,8 +515,8 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
             best = key < best ? key : best;
           }
         }
+        best = warp_min_u64(best);
       }
-      best = warp_min_u64(best);
       bool accept = false;
       int best_idx = -1, best_dist = 0, second_idx = -1;
       if (best != kNone) {
@@ -525,11 +530,11 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
           // "bestDist2" of the reference ends as P if P <= Q else Q (matcher section).
           unsigned long long p = kNone, q = kNone;
           if (small) {
-            if (rok && lane != best_pos) {
-              const unsigned long long key = ((unsigned long long)(rval & 0xFFFFu) << 32) | (unsigned)lane;
-              if (lane < best_pos) p = key;
-              else q = key;
-            }
+            const unsigned kk = (rok && lane != best_pos) ? (((rval & 0xFFFFu) << 8) | (unsigned)lane) : 0xFFFFFFFFu;
+            const unsigned p32 = __reduce_min_sync(0xffffffffu, lane < best_pos ? kk : 0xFFFFFFFFu);
+            const unsigned q32 = __reduce_min_sync(0xffffffffu, lane > best_pos ? kk : 0xFFFFFFFFu);
+            if (p32 != 0xFFFFFFFFu) p = ((unsigned long long)(p32 >> 8) << 32) | (p32 & 31u);
+            if (q32 != 0xFFFFFFFFu) q = ((unsigned long long)(q32 >> 8) << 32) | (q32 & 31u);
           } else {
             for (int c = b + lane; c < e; c += 32) {
               if (c - b == best_pos) continue;
@@ -541,9 +546,9 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
                 else q = key < q ? key : q;
               }
             }
+            p = warp_min_u64(p);
+            q = warp_min_u64(q);
           }
-          p = warp_min_u64(p);
-          q = warp_min_u64(q);
           const unsigned long long sec = (p >> 32) <= (q >> 32) ? p : q;
           if (sec != kNone) {
             const int sp = (int)(sec & 0xFFFFFFFFu);
@@ -572,9 +577,8 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
         s_best_dist[wid] = best_dist;
         s_second_idx[wid] = second_idx;
         // everything the in-order commit needs from global memory is fetched here, in parallel
-        const int s = a.row_src ? a.row_src[r] : r;
-        s_src[wid] = s;
-        s_blk[wid] = (a.mode == kModeWindow && accept) ? a.blocks[s] : 1;
+        s_src[wid] = src_s;
+        s_blk[wid] = (a.mode == kModeWindow && accept) ? src_blk : 1;
         if (accept) atomicMin(mark + best_idx, wid);
       }
     }
