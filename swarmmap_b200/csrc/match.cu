@@ -582,6 +582,13 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
         if (accept) atomicMin(mark + best_idx, wid);
       }
     }
+    if (wid == 0 && pre >= 0) {
+      // warm L1 with the candidate lists of the rows that can enter the next batch (first and last line of each)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a.cand_idx + pre_b));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a.cand_val + pre_b));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a.cand_idx + pre_e - 1));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(a.cand_val + pre_e - 1));
+    }
     __syncthreads();
 
     // ---- 3. commit, by the lanes of warp 0 (lane k = row k of the batch).  A row conflicts if an earlier
