@@ -1211,11 +1211,18 @@ struct swm_matcher {
   uint8_t* h_arena = nullptr;
   uint8_t* d_arena = nullptr;
   size_t arena_cap = 0, arena_used = 0;
+  // results come back through one pinned staging buffer (pageable destinations make every D2H copy a staged,
+  // synchronising transfer); filled by down_copy, handed to the caller's arrays by down_finish
+  uint8_t* h_down = nullptr;
+  size_t down_cap = 0, down_used = 0;
+  struct Down { void* dst; size_t off, bytes; };
+  std::vector<Down> downs;
   void free_all() {
     if (h_arena) cudaFreeHost(h_arena);
     if (d_arena) cudaFree(d_arena);
-    h_arena = d_arena = nullptr;
-    arena_cap = arena_used = 0;
+    if (h_down) cudaFreeHost(h_down);
+    h_arena = d_arena = h_down = nullptr;
+    arena_cap = arena_used = down_cap = down_used = 0;
     for (auto& a : f) for (auto& b : a) b.release();
     for (auto& b : q) b.release();
     for (auto& b : iq) b.release();
@@ -1303,6 +1310,38 @@ int upload(swm_matcher* m, DevBuf& b, const void* src, size_t bytes) {
 int arena_flush(swm_matcher* m) {
   if (m->arena_used)
     MCK(m, cudaMemcpyAsync(m->d_arena, m->h_arena, m->arena_used, cudaMemcpyHostToDevice, m->stream));
+  return SWM_OK;
+}
+
+// Result download through the pinned staging buffer: down_begin(total) once, down_copy per array, down_finish
+// synchronises the stream and copies into the caller's (pageable) arrays.
+int down_begin(swm_matcher* m, size_t bytes) {
+  bytes += 1024;
+  if (bytes > m->down_cap) {
+    MCK(m, cudaStreamSynchronize(m->stream));
+    if (m->h_down) cudaFreeHost(m->h_down);
+    m->h_down = nullptr;
+    m->down_cap = 0;
+    MCK(m, cudaMallocHost(&m->h_down, bytes + bytes / 2));
+    m->down_cap = bytes + bytes / 2;
+  }
+  m->down_used = 0;
+  m->downs.clear();
+  return SWM_OK;
+}
+int down_copy(swm_matcher* m, void* dst, const void* d_src, size_t bytes) {
+  const size_t off = (m->down_used + 63) & ~(size_t)63;
+  if (off + bytes > m->down_cap) { m->err = "internal: download buffer overflow"; return SWM_E_CAPACITY; }
+  if (bytes) MCK(m, cudaMemcpyAsync(m->h_down + off, d_src, bytes, cudaMemcpyDeviceToHost, m->stream));
+  m->downs.push_back({dst, off, bytes});
+  m->down_used = off + bytes;
+  return SWM_OK;
+}
+int down_finish(swm_matcher* m) {
+  MCK(m, cudaStreamSynchronize(m->stream));
+  for (const auto& d : m->downs)
+    if (d.bytes) memcpy(d.dst, m->h_down + d.off, d.bytes);
+  m->downs.clear();
   return SWM_OK;
 }
 
@@ -1675,11 +1714,11 @@ int match_init_impl(swm_matcher* m, const FrameSrc& f1, const FrameSrc& f2, floa
   a.nmatches = m->state[6].as<int32_t>();
   if ((rc = launch_resolve(m, a))) return rc;
   MCK(m, cudaGetLastError());
-  MCK(m, cudaMemcpyAsync(matches12, a.out, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
-  MCK(m, cudaMemcpyAsync(prev_xy, a.prev_xy, (size_t)n1 * 8, cudaMemcpyDeviceToHost, m->stream));
-  MCK(m, cudaMemcpyAsync(nmatches, a.nmatches, 4, cudaMemcpyDeviceToHost, m->stream));
-  MCK(m, cudaStreamSynchronize(m->stream));
-  return SWM_OK;
+  if ((rc = down_begin(m, (size_t)n1 * 12 + 256))) return rc;
+  if ((rc = down_copy(m, matches12, a.out, (size_t)n1 * 4))) return rc;
+  if ((rc = down_copy(m, prev_xy, a.prev_xy, (size_t)n1 * 8))) return rc;
+  if ((rc = down_copy(m, nmatches, a.nmatches, 4))) return rc;
+  return down_finish(m);
 }
 
 bool window_query_ok(const swm_window_query* wq, int check_ori) {
@@ -1761,9 +1800,10 @@ int match_window_impl(swm_matcher* m, const FrameSrc& tgt, const swm_window_quer
     cudaMemcpy(dbg, a.nmatches, 8, cudaMemcpyDeviceToHost);
     fprintf(stderr, "[swm match] rows %d batches %d matches %d\n", M, dbg[1], dbg[0]);
   }
-  MCK(m, cudaMemcpyAsync(assignment, a.out, (size_t)n2 * 4, cudaMemcpyDeviceToHost, m->stream));
-  MCK(m, cudaMemcpyAsync(nmatches, a.nmatches, 4, cudaMemcpyDeviceToHost, m->stream));
-  MCK(m, cudaStreamSynchronize(m->stream));
+  if ((rc = down_begin(m, (size_t)n2 * 4 + 256))) return rc;
+  if ((rc = down_copy(m, assignment, a.out, (size_t)n2 * 4))) return rc;
+  if ((rc = down_copy(m, nmatches, a.nmatches, 4))) return rc;
+  if ((rc = down_finish(m))) return rc;
   pt.mark("download");
   return SWM_OK;
 }
@@ -1860,10 +1900,10 @@ int match_bow_impl(swm_matcher* m, const FrameSrc& f1, const swm_featvec* fv1, c
   ra.nmatches = m->state[6].as<int32_t>();
   if ((rc = launch_resolve(m, ra))) return rc;
   MCK(m, cudaGetLastError());
-  MCK(m, cudaMemcpyAsync(matches, ra.out, (size_t)n_out * 4, cudaMemcpyDeviceToHost, m->stream));
-  MCK(m, cudaMemcpyAsync(nmatches, ra.nmatches, 4, cudaMemcpyDeviceToHost, m->stream));
-  MCK(m, cudaStreamSynchronize(m->stream));
-  return SWM_OK;
+  if ((rc = down_begin(m, (size_t)n_out * 4 + 256))) return rc;
+  if ((rc = down_copy(m, matches, ra.out, (size_t)n_out * 4))) return rc;
+  if ((rc = down_copy(m, nmatches, ra.nmatches, 4))) return rc;
+  return down_finish(m);
 }
 
 int match_triangulation_impl(swm_matcher* m, const FrameSrc& f1, const swm_featvec* fv1, const uint8_t* valid1,
@@ -1909,10 +1949,10 @@ int match_triangulation_impl(swm_matcher* m, const FrameSrc& f1, const swm_featv
   tri_finalize_kernel<<<1, 1024, 0, m->stream>>>(n1, m->state[3].as<int32_t>(), m->state[4].as<int32_t>(), check_ori,
                                                  m->state[6].as<int32_t>());
   MCK(m, cudaGetLastError());
-  MCK(m, cudaMemcpyAsync(matches12, m->state[3].p, (size_t)n1 * 4, cudaMemcpyDeviceToHost, m->stream));
-  MCK(m, cudaMemcpyAsync(nmatches, m->state[6].p, 4, cudaMemcpyDeviceToHost, m->stream));
-  MCK(m, cudaStreamSynchronize(m->stream));
-  return SWM_OK;
+  if ((rc = down_begin(m, (size_t)n1 * 4 + 256))) return rc;
+  if ((rc = down_copy(m, matches12, m->state[3].p, (size_t)n1 * 4))) return rc;
+  if ((rc = down_copy(m, nmatches, m->state[6].p, 4))) return rc;
+  return down_finish(m);
 }
 
 int window_best_impl(swm_matcher* m, const FrameSrc& tgt, const swm_best_query* bq, int32_t* best_idx, int32_t* best_dist) {
@@ -1953,10 +1993,10 @@ int window_best_impl(swm_matcher* m, const FrameSrc& tgt, const swm_best_query* 
                                                        gate ? bq->chi2 : 0.0f, m->state[3].as<int32_t>(),
                                                        m->state[4].as<int32_t>());
   MCK(m, cudaGetLastError());
-  MCK(m, cudaMemcpyAsync(best_idx, m->state[3].p, (size_t)M * 4, cudaMemcpyDeviceToHost, m->stream));
-  MCK(m, cudaMemcpyAsync(best_dist, m->state[4].p, (size_t)M * 4, cudaMemcpyDeviceToHost, m->stream));
-  MCK(m, cudaStreamSynchronize(m->stream));
-  return SWM_OK;
+  if ((rc = down_begin(m, (size_t)M * 8 + 256))) return rc;
+  if ((rc = down_copy(m, best_idx, m->state[3].p, (size_t)M * 4))) return rc;
+  if ((rc = down_copy(m, best_dist, m->state[4].p, (size_t)M * 4))) return rc;
+  return down_finish(m);
 }
 
 bool best_query_ok(const swm_best_query* q) {
