@@ -69,6 +69,49 @@ def test_no_cpu_fallback(swm):
     from swarmmap_b200.orb import ORBextractor
     with pytest.raises(swm.SwmError):
         ORBextractor(1000, 1.2, 8, 20, 7)
+    # the later entry points: resident frames, vocabulary, distinctive descriptors, camera bounds
+    f = C.c_void_p()
+    assert lib.swm_frame_create(0, C.byref(f)) == -3 and not f.value
+    from swarmmap_b200 import synth
+    blob = np.frombuffer(synth.make_vocabulary(4, 2, seed=1), np.uint8)
+    v = C.c_void_p()
+    assert lib.swm_vocab_create(0, swm.ptr(blob), len(blob), C.byref(v)) == -3 and not v.value
+    off = np.array([0, 4], np.int32)
+    best = np.zeros(1, np.int32)
+    assert lib.swm_distinctive_descriptors(swm.ptr(a), swm.ptr(off), 1, swm.ptr(best), None, 0) == -3
+    cam = swm.Camera(458.654, 457.296, 367.215, 248.375, -0.28, 0.07, 0.0, 0.0, 0.0)
+    b4 = np.zeros(4, np.float32)
+    assert lib.swm_camera_bounds(0, C.byref(cam), 752, 480, swm.ptr(b4)) == -3
+    from swarmmap_b200.bow import ORBVocabulary
+    from swarmmap_b200.matcher import ResidentFrame
+    with pytest.raises(swm.SwmError):
+        ResidentFrame()
+    with pytest.raises(swm.SwmError):
+        ORBVocabulary(blob.tobytes())
+
+
+def test_vocabulary_blob_validation(swm):
+    """Malformed vocabulary files are rejected before any device work (host-side parser of the ORBvoc.bin layout)."""
+    from swarmmap_b200 import synth
+    lib = swm.load()
+    v = C.c_void_p()
+    good = bytearray(synth.make_vocabulary(4, 2, seed=1))
+    short = np.frombuffer(bytes(good[:10]), np.uint8)
+    assert lib.swm_vocab_create(0, swm.ptr(short), len(short), C.byref(v)) == -1
+    bad_size = bytearray(good)
+    bad_size[4:8] = np.array([40], np.uint32).tobytes()
+    b = np.frombuffer(bytes(bad_size), np.uint8)
+    assert lib.swm_vocab_create(0, swm.ptr(b), len(b), C.byref(v)) == -1
+    assert b"record size" in lib.swm_vocab_last_error(None)
+    bad_parent = bytearray(good)
+    bad_parent[24:28] = np.array([10 ** 6], np.int32).tobytes()
+    b = np.frombuffer(bytes(bad_parent), np.uint8)
+    assert lib.swm_vocab_create(0, swm.ptr(b), len(b), C.byref(v)) == -1
+    bad_scoring = bytearray(good)
+    bad_scoring[16:20] = np.array([9], np.int32).tobytes()
+    b = np.frombuffer(bytes(bad_scoring), np.uint8)
+    assert lib.swm_vocab_create(0, swm.ptr(b), len(b), C.byref(v)) == -1
+    assert not v.value
 
 
 def test_product_never_imports_oracle():
