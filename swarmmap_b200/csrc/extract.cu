@@ -842,11 +842,21 @@ struct swm_orb {
   int32_t* pending_n = nullptr;
   int pending_batch = 0;
   int pending_cap = 0;
+  // single frame into pageable caller memory: results are staged through a pinned buffer and handed over in
+  // swm_orb_sync (only the n valid entries are copied)
+  uint8_t* h_stage = nullptr;
+  size_t stage_cap = 0;
+  swm_keypoint* stage_kps = nullptr;
+  uint8_t* stage_desc = nullptr;
+  int stage_ccap = 0;
 };
 
 namespace {
 
 void free_frame_buffers(swm_orb* h) {
+  if (h->h_stage) cudaFreeHost(h->h_stage);
+  h->h_stage = nullptr;
+  h->stage_cap = 0;
   if (h->graph) cudaGraphExecDestroy(h->graph);
   h->graph = nullptr;
   h->graph_runs = 0;
@@ -1243,6 +1253,39 @@ static int enqueue_host_chunk(swm_orb* h, const uint8_t* src, int nb, int w, int
     if (rc != SWM_OK) return rc;
   }
   if (nb == 1) h->graph_runs++;
+  // A cudaMemcpyAsync into pageable memory is a staged, blocking transfer per call; the one-frame operator() path
+  // (std::vector / cv::Mat destinations) therefore goes through a pinned staging buffer: three back-to-back async
+  // copies, one synchronisation, then plain memcpy of the n valid entries.
+  bool staged = false;
+  if (nb == 1) {
+    cudaPointerAttributes pa;
+    const bool pageable = cudaPointerGetAttributes(&pa, kps) != cudaSuccess || pa.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    if (pageable) {
+      const size_t off_k = 64, off_d = off_k + (((size_t)ccap * sizeof(swm_keypoint) + 63) & ~(size_t)63);
+      const size_t need = off_d + (size_t)ccap * 32;
+      if (need > h->stage_cap) {
+        if (h->h_stage) cudaFreeHost(h->h_stage);
+        h->h_stage = nullptr;
+        h->stage_cap = 0;
+        SWM_CK(h, cudaMallocHost(&h->h_stage, need + need / 2));
+        h->stage_cap = need + need / 2;
+      }
+      SWM_CK(h, cudaMemcpyAsync(h->h_stage, h->d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+      SWM_CK(h, cudaMemcpyAsync(h->h_stage + off_k, h->d_kps, (size_t)ccap * sizeof(swm_keypoint), cudaMemcpyDeviceToHost, h->stream));
+      SWM_CK(h, cudaMemcpyAsync(h->h_stage + off_d, h->d_desc, (size_t)ccap * 32, cudaMemcpyDeviceToHost, h->stream));
+      h->stage_kps = kps;
+      h->stage_desc = desc;
+      h->stage_ccap = ccap;
+      staged = true;
+    }
+  }
+  if (staged) {
+    h->pending_n = n;
+    h->pending_batch = 1;
+    h->pending_cap = cap;
+    return SWM_OK;
+  }
   SWM_CK(h, cudaMemcpyAsync(n, h->d_n, nb * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   if (cap == kcap) {
     SWM_CK(h, cudaMemcpyAsync(kps, h->d_kps, (size_t)kcap * nb * sizeof(swm_keypoint), cudaMemcpyDeviceToHost, h->stream));
@@ -1263,6 +1306,17 @@ int swm_orb_sync(swm_orb* h) {
   if (!h) return SWM_E_INVALID;
   SWM_CK(h, cudaSetDevice(h->device));
   SWM_CK(h, cudaStreamSynchronize(h->stream));
+  if (h->pending_n && h->stage_kps) {  // staged single-frame result -> caller's arrays
+    int32_t cnt;
+    memcpy(&cnt, h->h_stage, sizeof(cnt));
+    h->pending_n[0] = cnt;
+    const size_t take = (size_t)std::max(0, std::min(cnt, h->stage_ccap));
+    const size_t off_k = 64, off_d = off_k + (((size_t)h->stage_ccap * sizeof(swm_keypoint) + 63) & ~(size_t)63);
+    memcpy(h->stage_kps, h->h_stage + off_k, take * sizeof(swm_keypoint));
+    memcpy(h->stage_desc, h->h_stage + off_d, take * 32);
+    h->stage_kps = nullptr;
+    h->stage_desc = nullptr;
+  }
   if (h->pending_n) {
     for (int f = 0; f < h->pending_batch; f++)
       if (h->pending_n[f] > h->pending_cap) h->pending_n[f] = h->pending_cap;
