@@ -156,3 +156,216 @@ def test_triangulation_vs_python(oracle, two_frames):
             exp[idx1] = best_j
     np.testing.assert_array_equal(out, exp)
     assert n == int((exp >= 0).sum()) and n > 3
+
+
+def three_maxima(hist):
+    """ORBmatcher::ComputeThreeMaxima, ORBmatcher.cc:1475-1506."""
+    max1 = max2 = max3 = 0
+    ind1 = ind2 = ind3 = -1
+    for i, h in enumerate(hist):
+        s = len(h)
+        if s > max1:
+            max3, max2, max1 = max2, max1, s
+            ind3, ind2, ind1 = ind2, ind1, i
+        elif s > max2:
+            max3, max2 = max2, s
+            ind3, ind2 = ind2, i
+        elif s > max3:
+            max3, ind3 = s, i
+    if max2 < np.float32(0.1) * np.float32(max1):
+        ind2 = ind3 = -1
+    elif max3 < np.float32(0.1) * np.float32(max1):
+        ind3 = -1
+    return ind1, ind2, ind3
+
+
+def rot_bin(a1, a2):
+    rot = np.float32(a1) - np.float32(a2)
+    if rot < 0:
+        rot = np.float32(rot + np.float32(360.0))
+    b = int(np.round(np.float32(rot * (np.float32(1.0) / np.float32(30)))))  # C round(): no half cases on these inputs
+    return 0 if b == 30 else b
+
+
+def features_in_area_levels(f, grid, x, y, r, lo, hi):
+    out = get_features_in_area(f, grid, x, y, r)
+    if lo > 0 or hi >= 0:  # bCheckLevels, Frame.cc:398
+        out = [j for j in out if not (f.octave[j] < lo) and not (hi >= 0 and f.octave[j] > hi)]
+    return out
+
+
+@pytest.mark.parametrize("check_ori", [True, False])
+def test_search_for_initialization_vs_python(oracle, two_frames, check_ori):
+    """A literal Python SearchForInitialization (ORBmatcher.cc:375-479) incl. the steal rule, the rotation histogram
+    and the vbPrevMatched update."""
+    f1, f2 = two_frames
+    nnratio, window = np.float32(0.9), 60
+    prev0 = np.stack([f1.x, f1.y], 1).astype(np.float32)
+    n, m12, prev = oracle.search_for_initialization(f1, f2, prev0, window, float(nnratio), check_ori)
+    grid = oracle.grid_csr(f2)
+    INT_MAX = 2 ** 31 - 1
+    match12 = np.full(f1.N, -1, np.int64)
+    match21 = np.full(f2.N, -1, np.int64)
+    mdist = np.full(f2.N, INT_MAX, np.int64)
+    hist = [[] for _ in range(30)]
+    nm = 0
+    for i1 in range(f1.N):
+        if f1.octave[i1] > 0:
+            continue
+        cand = features_in_area_levels(f2, grid, prev0[i1, 0], prev0[i1, 1], window, 0, 0)
+        if not cand:
+            continue
+        best, best2, bi = INT_MAX, INT_MAX, -1
+        for i2 in cand:
+            d = hamming(f1.desc[i1], f2.desc[i2])
+            if mdist[i2] <= d:
+                continue
+            if d < best:
+                best2, best, bi = best, d, i2
+            elif d < best2:
+                best2 = d
+        if best <= TH_LOW and np.float32(best) < np.float32(best2) * nnratio:
+            if match21[bi] >= 0:
+                match12[match21[bi]] = -1
+                nm -= 1
+            match12[i1], match21[bi], mdist[bi] = bi, i1, best
+            nm += 1
+            if check_ori:
+                hist[rot_bin(f1.angle[i1], f2.angle[bi])].append(i1)
+    if check_ori:
+        keep = three_maxima(hist)
+        for i in range(30):
+            if i in keep:
+                continue
+            for idx1 in hist[i]:
+                if match12[idx1] >= 0:
+                    match12[idx1] = -1
+                    nm -= 1
+    exp_prev = prev0.copy()
+    for i1 in range(f1.N):
+        if match12[i1] >= 0:
+            exp_prev[i1] = (f2.x[match12[i1]], f2.y[match12[i1]])
+    assert n == nm and n > 20
+    np.testing.assert_array_equal(m12, match12)
+    np.testing.assert_array_equal(prev, exp_prev)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_search_by_bow_vs_python(oracle, two_frames, mode):
+    """Literal Python SearchByBoW: KeyFrame->Frame (ORBmatcher.cc:150-262) and KeyFrame<->KeyFrame (:481-597)."""
+    from swarmmap_b200.matcher import FeatureVector
+    f1, f2 = two_frames
+    rng = np.random.default_rng(4)
+    node = lambda f: (f.desc[:, 7].astype(np.int64) % 9)
+    fv1, fv2 = FeatureVector(node(f1)), FeatureVector(node(f2))
+    v1 = (rng.random(f1.N) < 0.8).astype(np.uint8)
+    v2 = (rng.random(f2.N) < 0.8).astype(np.uint8)
+    nnratio = np.float32(0.75)
+    n, out = oracle.search_by_bow(f1, fv1, v1, f2, fv2, v2 if mode == 1 else None, mode, float(nnratio), True)
+    exp = np.full(f2.N if mode == 0 else f1.N, -1, np.int64)
+    taken = np.zeros(f2.N, bool)
+    hist = [[] for _ in range(30)]
+    nm = 0
+    n2nodes = {int(k): fv2.feats[fv2.offsets[i]:fv2.offsets[i + 1]] for i, k in enumerate(fv2.node_ids)}
+    for i, k in enumerate(fv1.node_ids):
+        if int(k) not in n2nodes:
+            continue
+        for idx1 in fv1.feats[fv1.offsets[i]:fv1.offsets[i + 1]]:
+            if not v1[idx1]:
+                continue
+            b1, b2, bi = 256, 256, -1
+            for idx2 in n2nodes[int(k)]:
+                if taken[idx2] or (mode == 1 and not v2[idx2]):
+                    continue
+                d = hamming(f1.desc[idx1], f2.desc[idx2])
+                if d < b1:
+                    b2, b1, bi = b1, d, int(idx2)
+                elif d < b2:
+                    b2 = d
+            ok = (b1 <= TH_LOW) if mode == 0 else (b1 < TH_LOW)
+            if ok and np.float32(b1) < nnratio * np.float32(b2):
+                taken[bi] = True
+                if mode == 0:
+                    exp[bi] = idx1
+                    hist[rot_bin(f1.angle[idx1], f2.angle[bi])].append(bi)
+                else:
+                    exp[idx1] = bi
+                    hist[rot_bin(f1.angle[idx1], f2.angle[bi])].append(int(idx1))
+                nm += 1
+    keep = three_maxima(hist)
+    for i in range(30):
+        if i in keep:
+            continue
+        for idx in hist[i]:
+            exp[idx] = -1
+            nm -= 1
+    assert n == nm and n > 10
+    np.testing.assert_array_equal(out, exp)
+
+
+@pytest.mark.parametrize("ratio_mode", [1, 0])
+def test_window_matcher_vs_python(oracle, two_frames, ratio_mode):
+    """The generic windowed matcher behind the four SearchByProjection overloads, against literal Python loops:
+    ratio_mode 1 = SearchByProjection(F, vpMapPoints, th) (ORBmatcher.cc:44-121: same-level ratio test, no rotation
+    check, a point only blocks a slot when Observations() > 0), ratio_mode 0 = SearchByProjection(cur, last, th,
+    mono) (:1223-1354: threshold only, rotation histogram over the assigned slots)."""
+    src, tgt = two_frames
+    rng = np.random.default_rng(8)
+    sf = oracle.scale_tables(1.2, 8)[0]
+    m = src.N
+    u = (src.x + rng.normal(0, 2, m)).astype(np.float32)
+    v = (src.y + rng.normal(0, 2, m)).astype(np.float32)
+    valid = (rng.random(m) < 0.9).astype(np.uint8)
+    blocks = (rng.random(m) < 0.7).astype(np.uint8)  # pMP->Observations() > 0
+    tgt_blocked = (rng.random(tgt.N) < 0.1).astype(np.uint8)
+    nnratio = np.float32(0.8)
+    if ratio_mode == 1:
+        lo, hi = src.octave - 1, src.octave.copy()
+        radius = (np.float32(4.0) * np.float32(3.0) * sf[src.octave]).astype(np.float32)
+        th_dist, check_ori = 100, False
+    else:
+        lo, hi = src.octave - 1, src.octave + 1
+        radius = (np.float32(15.0) * sf[src.octave]).astype(np.float32)
+        th_dist, check_ori = 100, True
+    n, asg = oracle.match_window(tgt, src.desc, u, v, radius, lo, hi, valid, blocks, th_dist, ratio_mode, float(nnratio),
+                                 check_ori, src.angle, tgt_blocked)
+    grid = oracle.grid_csr(tgt)
+    blocked = tgt_blocked.astype(bool).copy()
+    exp = np.full(tgt.N, -1, np.int64)
+    hist = [[] for _ in range(30)]
+    nm = 0
+    for i in range(m):
+        if not valid[i]:
+            continue
+        cand = features_in_area_levels(tgt, grid, u[i], v[i], radius[i], lo[i], hi[i])
+        if not cand:
+            continue
+        b1, b2, l1, l2, bi = 256, 256, -1, -1, -1
+        for j in cand:
+            if blocked[j]:
+                continue
+            d = hamming(src.desc[i], tgt.desc[j])
+            if d < b1:
+                b2, l2 = b1, l1
+                b1, l1, bi = d, tgt.octave[j], j
+            elif d < b2:
+                b2, l2 = d, tgt.octave[j]
+        if b1 <= th_dist:
+            if ratio_mode == 1 and l1 == l2 and np.float32(b1) > nnratio * np.float32(b2):
+                continue
+            exp[bi] = i
+            if blocks[i]:
+                blocked[bi] = True
+            nm += 1
+            if check_ori:
+                hist[rot_bin(src.angle[i], tgt.angle[bi])].append(bi)
+    if check_ori:
+        keep = three_maxima(hist)
+        for b in range(30):
+            if b in keep:
+                continue
+            for j in hist[b]:
+                exp[j] = -1
+                nm -= 1
+    assert n == nm and n > 30
+    np.testing.assert_array_equal(asg, exp)
