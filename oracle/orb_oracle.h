@@ -15,7 +15,12 @@
  * delegates to (resize INTER_LINEAR 8U, copyMakeBorder REFLECT_101,
  * GaussianBlur 7x7 sigma 2 8U) and the FAST-9/16 score, (b) the closed-form
  * tables derivable from the reference source (quotas, umax, level sizes),
- * (c) committed golden fixtures under tests/golden/.
+ * (c) committed golden fixtures under tests/golden/ (incl. cv2.undistortPoints outputs),
+ * (d) second, independent Python / numpy readings of the reference sources for the matchers, the
+ * orientation / descriptor stages and the "next" rows (tests/test_oracle_*independent*.py,
+ * tests/test_oracle_bow.py), and (e) for the DBoW2 rows the REFERENCE'S OWN CODE: its vendored
+ * DBoW2 compiles unmodified against oracle/ref_shim (make ref -> oracle/_ref/libdbow2_ref.so) and
+ * tests/test_ref_dbow2.py requires bit-identical BowVector / FeatureVector outputs.
  */
 #ifndef ORB_ORACLE_H
 #define ORB_ORACLE_H

@@ -125,7 +125,9 @@ def make_vocabulary(k=10, L=3, seed=1, early_leaf=0.03, zero_weight=0.02, weight
     add_children(0, None, 1)
     n = len(parents)
     out = bytearray()
-    out += np.array([n, 41], np.uint32).tobytes()
+    # nb_nodes counts the root too, like the reference's writer (m_nodes.size(), TemplatedVocabulary.h:1530); its reader
+    # sizes m_nodes from it, and the parsers here take the record count from the file size
+    out += np.array([n + 1, 41], np.uint32).tobytes()
     out += np.array([k, L, scoring, weighting], np.int32).tobytes()
     rec = np.zeros(n, np.dtype([("parent", "<i4"), ("desc", "u1", 32), ("weight", "<f4"), ("leaf", "u1")]))
     assert rec.dtype.itemsize == 41
