@@ -18,9 +18,10 @@
  * (c) committed golden fixtures under tests/golden/ (incl. cv2.undistortPoints outputs),
  * (d) second, independent Python / numpy readings of the reference sources for the matchers, the
  * orientation / descriptor stages and the "next" rows (tests/test_oracle_*independent*.py,
- * tests/test_oracle_bow.py), and (e) for the DBoW2 rows the REFERENCE'S OWN CODE: its vendored
- * DBoW2 compiles unmodified against oracle/ref_shim (make ref -> oracle/_ref/libdbow2_ref.so) and
- * tests/test_ref_dbow2.py requires bit-identical BowVector / FeatureVector outputs.
+ * tests/test_oracle_bow.py), and (e) the REFERENCE'S OWN CODE where it compiles on its own
+ * (make ref -> oracle/_ref/): ORBextractor.cc's constructor tables and DistributeOctTree
+ * (tests/test_ref_orbextractor.py: identical selection and order) and the vendored DBoW2
+ * (tests/test_ref_dbow2.py: bit-identical BowVector / FeatureVector outputs).
  */
 #ifndef ORB_ORACLE_H
 #define ORB_ORACLE_H

@@ -7,6 +7,7 @@
 #pragma once
 // the real header brings these in transitively and the DBoW2 sources rely on that
 #include <algorithm>
+#include <cassert>
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
@@ -54,6 +55,11 @@ class Mat {
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
   template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * cols * elemSize()); }
   template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * cols * elemSize()); }
+  Mat rowRange(int, int) const { return *this; }   // compile-only (never executed by the wrapper)
+  Mat colRange(int, int) const { return *this; }
+  Mat row(int) const { return *this; }
+  int channels() const { return 1; }
+  void copyTo(Mat& o) const { o = clone(); }
   template <typename T> T& at(int r, int c) { return ptr<T>(r)[c]; }
   template <typename T> const T& at(int r, int c) const { return ptr<T>(r)[c]; }
 
@@ -89,3 +95,98 @@ template <typename T>
 inline FileStorage& operator<<(FileStorage& fs, const T&) { return fs; }
 
 }  // namespace cv
+
+// ---- additions for the reference's ORBextractor.cc (oracle/Makefile target `ref`): geometry types, cv::KeyPoint,
+// Input/OutputArray proxies and the rounding helpers; the image-processing calls are declared in imgproc.hpp and
+// defined as aborting stubs in oracle/ref_orbextractor_wrap.cpp (the wrapper only runs the constructor and
+// DistributeOctTree, which need none of them).
+namespace cv {
+
+template <typename T>
+struct Point_ {
+  T x, y;
+  Point_() : x(0), y(0) {}
+  Point_(T x_, T y_) : x(x_), y(y_) {}
+  Point_& operator*=(T s) { x *= s; y *= s; return *this; }
+};
+typedef Point_<int> Point2i;
+typedef Point2i Point;
+typedef Point_<float> Point2f;
+
+struct Size {
+  int width, height;
+  Size() : width(0), height(0) {}
+  Size(int w, int h) : width(w), height(h) {}
+};
+struct Rect {
+  int x, y, width, height;
+  Rect() : x(0), y(0), width(0), height(0) {}
+  Rect(int x_, int y_, int w, int h) : x(x_), y(y_), width(w), height(h) {}
+};
+struct Scalar {
+  double val[4];
+  Scalar(double a = 0, double b = 0, double c = 0, double d = 0) { val[0] = a; val[1] = b; val[2] = c; val[3] = d; }
+  static Scalar all(double v) { return Scalar(v, v, v, v); }
+};
+struct Range {
+  int start, end;
+  Range(int s, int e) : start(s), end(e) {}
+};
+
+class KeyPoint {
+ public:
+  Point2f pt;
+  float size, angle, response;
+  int octave, class_id;
+  KeyPoint() : size(0), angle(-1), response(0), octave(0), class_id(-1) {}
+  KeyPoint(float x, float y, float size_, float angle_ = -1, float response_ = 0, int octave_ = 0, int class_id_ = -1)
+      : pt(x, y), size(size_), angle(angle_), response(response_), octave(octave_), class_id(class_id_) {}
+  KeyPoint(Point2f p, float size_, float angle_ = -1, float response_ = 0, int octave_ = 0, int class_id_ = -1)
+      : pt(p), size(size_), angle(angle_), response(response_), octave(octave_), class_id(class_id_) {}
+};
+
+template <typename T>
+using Ptr = std::shared_ptr<T>;
+
+namespace cuda { class GpuMat; }
+
+// proxies: enough for signatures and for `image.getMat()` / `descriptors.create()` to compile
+class _InputArray {
+ public:
+  _InputArray() : m_(nullptr), g_(nullptr) {}
+  _InputArray(const Mat& m) : m_(&m), g_(nullptr) {}
+  _InputArray(const cuda::GpuMat& g) : m_(nullptr), g_(&g) {}
+  Mat getMat() const { return m_ ? *m_ : Mat(); }
+  const cuda::GpuMat& getGpuMatRef() const { return *g_; }
+  bool empty() const { return !m_ || m_->empty(); }
+  int type() const { return m_ ? m_->type() : 0; }
+  const Mat* m_;
+  const cuda::GpuMat* g_;
+};
+class _OutputArray : public _InputArray {
+ public:
+  _OutputArray() : out_(nullptr) {}
+  _OutputArray(Mat& m) : _InputArray(m), out_(&m) {}
+  _OutputArray(cuda::GpuMat& g) : _InputArray(g), out_(nullptr) {}
+  void create(int r, int c, int type) const { if (out_) out_->create(r, c, type); }
+  void release() const { if (out_) out_->release(); }
+  Mat getMat() const { return out_ ? *out_ : Mat(); }
+  Mat* out_;
+};
+typedef const _InputArray& InputArray;
+typedef const _OutputArray& OutputArray;
+inline InputArray noArray() { static _InputArray a; return a; }
+
+inline int cvRound(double v) { return (int)std::lrint(v); }   // round half to even, like OpenCV's SSE2 cvRound
+inline int cvFloor(double v) { int i = (int)v; return i - (i > v); }
+inline int cvCeil(double v) { int i = (int)v; return i + (i < v); }
+float fastAtan2(float y, float x);
+
+enum { BORDER_CONSTANT = 0, BORDER_REPLICATE = 1, BORDER_REFLECT = 2, BORDER_REFLECT_101 = 4, BORDER_ISOLATED = 16 };
+enum { INTER_NEAREST = 0, INTER_LINEAR = 1 };
+
+}  // namespace cv
+using cv::cvRound;
+using cv::cvFloor;
+using cv::cvCeil;
+#define CV_Assert(expr) do { if (!(expr)) std::abort(); } while (0)
