@@ -110,6 +110,41 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _reference_dbow2_ms(vblob, desc, levelsup, iters):
+    """ms per Frame::ComputeBoW with the reference's own DBoW2 compiled unmodified (oracle/_ref/libdbow2_ref.so);
+    None when that library is not there.  cpu_baseline leg only."""
+    lib_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref", "libdbow2_ref.so")
+    if not os.path.exists(lib_path):
+        return None
+    try:
+        import ctypes as C
+        import tempfile
+        L = C.CDLL(lib_path)
+        L.ref_vocab_load.restype = C.c_void_p
+        L.ref_vocab_load.argtypes = [C.c_char_p]
+        L.ref_vocab_destroy.argtypes = [C.c_void_p]
+        L.ref_bow_transform.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 6
+        with tempfile.NamedTemporaryFile(suffix=".bin") as f:
+            f.write(vblob)
+            f.flush()
+            h = L.ref_vocab_load(f.name.encode())
+        if not h:
+            return None
+        d = np.ascontiguousarray(desc, np.uint8)
+        n = len(d)
+        bufs = [np.zeros(n + 2, t) for t in (np.uint32, np.float64, np.uint32, np.int32, np.uint32)]
+        nn = C.c_int32(0)
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            L.ref_bow_transform(h, ptr(d), n, levelsup, *[ptr(b) for b in bufs], C.byref(nn))
+        ms = (time.perf_counter() - t0) / iters * 1e3
+        L.ref_vocab_destroy(h)
+        return ms
+    except Exception:  # a baseline that cannot be measured is omitted, never fatal
+        return None
+
+
 def cpu_oracle_rate(frames, seconds_budget, threads):
     """frames/s of the CPU oracle on `threads` host threads over a bounded sample."""
     import oracle_lib
@@ -444,6 +479,9 @@ def main():
             import oracle_lib
             ov = oracle_lib.Vocabulary(vblob)
             extras["bow_transform"]["cpu_oracle_ms_single_frame"] = ov.time_transform(one, 4, 20) / 20 * 1e3
+            ref_ms = _reference_dbow2_ms(vblob, one, 4, 20)
+            if ref_ms is not None:  # the reference's own DBoW2 (oracle/_ref, built from /root/reference where present)
+                extras["bow_transform"]["cpu_reference_dbow2_ms_single_frame"] = ref_ms
         if not args.no_cpu_baseline:
             import oracle_lib
             t0 = time.perf_counter()
