@@ -1,0 +1,3 @@
+// stand-in: see cvcuda_shim.hpp
+#pragma once
+#include <cvcuda_shim.hpp>

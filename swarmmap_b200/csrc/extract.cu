@@ -895,7 +895,7 @@ void build_taps(int s, int d, std::vector<ResizeTap>& out, bool horizontal) {
 
 int setup_geometry(swm_orb* h, int w, int hh) {
   if (h->allocated && h->lay.w == w && h->lay.h == hh) return SWM_OK;
-  if (h->allocated) free_frame_buffers(h);
+  free_frame_buffers(h);  // unconditional: a set-up that failed part-way leaves buffers behind with allocated == false
   const int nl = h->cfg.nlevels;
   FrameLayout& L = h->lay;
   memset(&L, 0, sizeof(L));
@@ -1182,7 +1182,7 @@ int swm_orb_create(const swm_orb_cfg* cfg, int device, swm_orb** out) {
 void swm_orb_destroy(swm_orb* h) {
   if (!h) return;
   cudaSetDevice(h->device);
-  if (h->allocated) free_frame_buffers(h);
+  free_frame_buffers(h);  // unconditional: a set-up that failed part-way leaves buffers behind with allocated == false
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }

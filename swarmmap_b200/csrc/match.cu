@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -743,6 +744,7 @@ struct TriDev {
   float ex, ey;
   const float* sf2;     // pKF2->mvScaleFactors
   const float* sigma2;  // pKF2->mvLevelSigma2
+  int nlevels;          // entries in the two tables; candidates of a higher octave are skipped
 };
 
 __global__ void __launch_bounds__(256) tri_rows_kernel(FrameDev f1, FrameDev f2, const uint8_t* __restrict__ valid2, int rows,
@@ -770,6 +772,7 @@ __global__ void __launch_bounds__(256) tri_rows_kernel(FrameDev f1, FrameDev f2,
     if (dist > kThLow) continue;  // :674
     const float x2 = f2.x[j], y2 = f2.y[j];
     const int oct = f2.octave[j];
+    if ((unsigned)oct >= (unsigned)t.nlevels) continue;                // outside the caller's tables
     const float dex = __fsub_rn(t.ex, x2), dey = __fsub_rn(t.ey, y2);  // :679-683
     if (__fadd_rn(__fmul_rn(dex, dex), __fmul_rn(dey, dey)) < __fmul_rn(100.0f, t.sf2[oct])) continue;
     const float num = __fadd_rn(__fadd_rn(__fmul_rn(a, x2), __fmul_rn(b, y2)), c);
@@ -857,7 +860,7 @@ __global__ void __launch_bounds__(256) best_rows_kernel(FrameDev tgt, int rows, 
                                                         const float* __restrict__ v, const int32_t* __restrict__ row_start,
                                                         const int32_t* __restrict__ cand_idx,
                                                         const uint32_t* __restrict__ cand_val,
-                                                        const float* __restrict__ inv_sigma2, float chi2,
+                                                        const float* __restrict__ inv_sigma2, int nlevels, float chi2,
                                                         int32_t* __restrict__ best_idx, int32_t* __restrict__ best_dist) {
   const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -869,6 +872,7 @@ __global__ void __launch_bounds__(256) best_rows_kernel(FrameDev tgt, int rows, 
     const int j = cand_idx[ci];
     const uint32_t val = cand_val[ci];
     if (chi2 > 0.0f) {
+      if ((int)(val >> 16) >= nlevels) continue;  // outside the caller's mvInvLevelSigma2
       const float ex = __fsub_rn(pu, tgt.x[j]), ey = __fsub_rn(pv, tgt.y[j]);
       const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
       if ((double)__fmul_rn(e2, inv_sigma2[val >> 16]) > (double)chi2) continue;
@@ -1347,9 +1351,20 @@ int down_finish(swm_matcher* m) {
 
 size_t frame_bytes(const swm_frame_view* f) { return (size_t)f->n * 48 + 5 * 256; }
 
+// The keypoint arrays are caller-supplied (a keyframe slab may come off the wire): octave[] indexes the per-level
+// tables inside the kernels and is packed into 16 bits next to the distance, so it must lie in [0, SWM_MAX_LEVELS);
+// coordinates must be finite (they are turned into grid cells).
+bool payload_ok(const swm_frame_view* f) {
+  for (int i = 0; i < f->n; i++) {
+    if ((uint32_t)f->octave[i] >= (uint32_t)SWM_MAX_LEVELS) return false;
+    if (!std::isfinite(f->x[i]) || !std::isfinite(f->y[i])) return false;
+  }
+  return true;
+}
+
 bool frame_ok(const swm_frame_view* f) {
   return f && f->n >= 0 && (f->n == 0 || (f->x && f->y && f->octave && f->angle && f->desc)) && f->max_x > f->min_x &&
-         f->max_y > f->min_y;
+         f->max_y > f->min_y && payload_ok(f);
 }
 
 // Packs a frame's arrays into the upload arena (device views valid after arena_flush).
@@ -1543,23 +1558,48 @@ int swm_hamming_matrix_device(const uint8_t* d_a, int na, const uint8_t* d_b, in
   return cudaGetLastError() == cudaSuccess ? SWM_OK : SWM_E_CUDA;
 }
 
+// Device scratch of the handle-less entry points below (swm_hamming_matrix / _pairs, swm_distinctive_descriptors,
+// swm_camera_bounds): one grow-only arena per device, allocated on first use and kept, so that no call on the path
+// allocates or frees device memory.  A call holds the arena's mutex from upload to download (these entry points
+// run on the default stream and return host results, so they were serialised per device already).
+namespace {
+struct StaticScratch {
+  std::mutex mu;
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  uint8_t* reserve(size_t bytes) {
+    if (bytes > cap) {
+      if (p) cudaFree(p);
+      p = nullptr; cap = 0;
+      const size_t want = (std::max(bytes, (size_t)1 << 20) + 255) & ~(size_t)255;
+      if (cudaMalloc(&p, want) != cudaSuccess) return nullptr;
+      cap = want;
+    }
+    return p;
+  }
+};
+StaticScratch g_static_scratch[64];
+inline size_t up256(size_t n) { return (n + 255) & ~(size_t)255; }
+}  // namespace
+
 int swm_hamming_matrix(const uint8_t* a, int na, const uint8_t* b, int nb, uint16_t* out, int device) {
   if (!a || !b || !out || na < 0 || nb < 0) return SWM_E_INVALID;
   std::string err;
   int rc = check_device(device, &err);
   if (rc != SWM_OK) return rc;
   if (na == 0 || nb == 0) return SWM_OK;
-  if (cudaSetDevice(device) != cudaSuccess) return SWM_E_CUDA;
-  uint8_t *da = nullptr, *db = nullptr;
-  uint16_t* dout = nullptr;
-  cudaError_t e = cudaMalloc(&da, (size_t)na * 32);
-  if (e == cudaSuccess) e = cudaMalloc(&db, (size_t)nb * 32);
-  if (e == cudaSuccess) e = cudaMalloc(&dout, (size_t)na * nb * 2);
-  if (e == cudaSuccess) e = cudaMemcpy(da, a, (size_t)na * 32, cudaMemcpyHostToDevice);
+  if (device < 0 || device >= 64 || cudaSetDevice(device) != cudaSuccess) return SWM_E_CUDA;
+  StaticScratch& sc = g_static_scratch[device];
+  std::lock_guard<std::mutex> lock(sc.mu);
+  const size_t oa = 0, ob = up256((size_t)na * 32), oo = ob + up256((size_t)nb * 32);
+  uint8_t* base = sc.reserve(oo + (size_t)na * nb * 2);
+  if (!base) return SWM_E_CUDA;
+  uint8_t *da = base + oa, *db = base + ob;
+  uint16_t* dout = (uint16_t*)(base + oo);
+  cudaError_t e = cudaMemcpy(da, a, (size_t)na * 32, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(db, b, (size_t)nb * 32, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) rc = swm_hamming_matrix_device(da, na, db, nb, dout, nullptr);
   if (e == cudaSuccess && rc == SWM_OK) e = cudaMemcpy(out, dout, (size_t)na * nb * 2, cudaMemcpyDeviceToHost);
-  cudaFree(da); cudaFree(db); cudaFree(dout);
   return e == cudaSuccess ? rc : SWM_E_CUDA;
 }
 
@@ -1569,20 +1609,21 @@ int swm_hamming_pairs(const uint8_t* a, const uint8_t* b, int n, int32_t* out, i
   int rc = check_device(device, &err);
   if (rc != SWM_OK) return rc;
   if (n == 0) return SWM_OK;
-  if (cudaSetDevice(device) != cudaSuccess) return SWM_E_CUDA;
-  uint8_t *da = nullptr, *db = nullptr;
-  int32_t* dout = nullptr;
-  cudaError_t e = cudaMalloc(&da, (size_t)n * 32);
-  if (e == cudaSuccess) e = cudaMalloc(&db, (size_t)n * 32);
-  if (e == cudaSuccess) e = cudaMalloc(&dout, (size_t)n * 4);
-  if (e == cudaSuccess) e = cudaMemcpy(da, a, (size_t)n * 32, cudaMemcpyHostToDevice);
+  if (device < 0 || device >= 64 || cudaSetDevice(device) != cudaSuccess) return SWM_E_CUDA;
+  StaticScratch& sc = g_static_scratch[device];
+  std::lock_guard<std::mutex> lock(sc.mu);
+  const size_t ob = up256((size_t)n * 32), oo = 2 * ob;
+  uint8_t* base = sc.reserve(oo + (size_t)n * 4);
+  if (!base) return SWM_E_CUDA;
+  uint8_t *da = base, *db = base + ob;
+  int32_t* dout = (int32_t*)(base + oo);
+  cudaError_t e = cudaMemcpy(da, a, (size_t)n * 32, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(db, b, (size_t)n * 32, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
     hamming_pairs_kernel<<<(n + 255) / 256, 256>>>((const uint4*)da, (const uint4*)db, n, dout);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(out, dout, (size_t)n * 4, cudaMemcpyDeviceToHost);
-  cudaFree(da); cudaFree(db); cudaFree(dout);
   return e == cudaSuccess ? SWM_OK : SWM_E_CUDA;
 }
 
@@ -1602,13 +1643,16 @@ int swm_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int
   std::string err;
   int rc = check_device(device, &err);
   if (rc != SWM_OK) return rc;
-  if (cudaSetDevice(device) != cudaSuccess) return SWM_E_CUDA;
-  uint8_t* d_desc = nullptr;
-  int32_t *d_off = nullptr, *d_out = nullptr;
+  if (device < 0 || device >= 64 || cudaSetDevice(device) != cudaSuccess) return SWM_E_CUDA;
+  StaticScratch& sc = g_static_scratch[device];
+  std::lock_guard<std::mutex> lock(sc.mu);
+  const size_t o_off = up256((size_t)std::max<long long>(total, 1) * 32), o_out = o_off + up256(((size_t)npoints + 1) * 4);
+  uint8_t* base = sc.reserve(o_out + 2 * (size_t)npoints * 4);
+  if (!base) return SWM_E_CUDA;
+  uint8_t* d_desc = base;
+  int32_t *d_off = (int32_t*)(base + o_off), *d_out = (int32_t*)(base + o_out);
   std::vector<int32_t> out(2 * (size_t)npoints);
-  bool ok = cudaMalloc(&d_desc, (size_t)std::max<long long>(total, 1) * 32) == cudaSuccess &&
-            cudaMalloc(&d_off, ((size_t)npoints + 1) * 4) == cudaSuccess &&
-            cudaMalloc(&d_out, 2 * (size_t)npoints * 4) == cudaSuccess;
+  bool ok = true;
   if (ok && total) ok = cudaMemcpy(d_desc, desc, (size_t)total * 32, cudaMemcpyHostToDevice) == cudaSuccess;
   ok = ok && cudaMemcpy(d_off, offsets, ((size_t)npoints + 1) * 4, cudaMemcpyHostToDevice) == cudaSuccess;
   if (ok) {
@@ -1616,7 +1660,6 @@ int swm_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int
     ok = cudaGetLastError() == cudaSuccess &&
          cudaMemcpy(out.data(), d_out, out.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
   }
-  cudaFree(d_desc); cudaFree(d_off); cudaFree(d_out);
   if (!ok) return SWM_E_CUDA;
   for (int p = 0; p < npoints; p++) {
     best_idx[p] = out[p];
@@ -1815,17 +1858,20 @@ int node_rows(swm_matcher* m, const swm_featvec* fv1, const uint8_t* valid1, int
   row_src.clear();
   cand.clear();
   row_start.assign(1, 0);
+  for (const swm_featvec* fv : {fv1, fv2})  // offsets[] is caller-supplied: non-negative and non-decreasing
+    for (int a = 0; a < fv->n_nodes; a++)
+      if (fv->offsets[a] < 0 || fv->offsets[a + 1] < fv->offsets[a]) { m->err = "feature vector offsets not monotonic"; return SWM_E_INVALID; }
   int a = 0, b = 0;
   while (a < fv1->n_nodes && b < fv2->n_nodes) {
     const uint32_t ia = fv1->node_ids[a], ib = fv2->node_ids[b];
     if (ia == ib) {
       for (int i1 = fv1->offsets[a]; i1 < fv1->offsets[a + 1]; i1++) {
         const uint32_t idx1 = fv1->feats[i1];
-        if ((int)idx1 >= n1) { m->err = "feature index out of range"; return SWM_E_INVALID; }
+        if (idx1 >= (uint32_t)n1) { m->err = "feature index out of range"; return SWM_E_INVALID; }
         if (!valid1[idx1]) continue;
         row_src.push_back((int32_t)idx1);
         for (int i2 = fv2->offsets[b]; i2 < fv2->offsets[b + 1]; i2++) {
-          if ((int)fv2->feats[i2] >= n2) { m->err = "feature index out of range"; return SWM_E_INVALID; }
+          if (fv2->feats[i2] >= (uint32_t)n2) { m->err = "feature index out of range"; return SWM_E_INVALID; }
           cand.push_back((int32_t)fv2->feats[i2]);
         }
         row_start.push_back((int32_t)cand.size());
@@ -1942,6 +1988,7 @@ int match_triangulation_impl(swm_matcher* m, const FrameSrc& f1, const swm_featv
   t.ey = q->ey;
   t.sf2 = m->q[0].as<float>();
   t.sigma2 = m->q[1].as<float>();
+  t.nlevels = q->nlevels;
   tri_rows_kernel<<<(R + 7) / 8, 256, 0, m->stream>>>(d1, d2, m->q[4].as<uint8_t>(), R, m->rows[4].as<int32_t>(),
                                                       m->rows[1].as<int32_t>(), m->rows[2].as<int32_t>(), t, check_ori,
                                                       m->state[3].as<int32_t>(), m->state[4].as<int32_t>());
@@ -1990,7 +2037,7 @@ int window_best_impl(swm_matcher* m, const FrameSrc& tgt, const swm_best_query* 
   MCK(m, m->state[4].ensure((size_t)M * 4));
   best_rows_kernel<<<(M + 7) / 8, 256, 0, m->stream>>>(d2, M, q.u, q.v, m->rows[1].as<int32_t>(), m->rows[2].as<int32_t>(),
                                                        m->rows[3].as<uint32_t>(), gate ? m->q[9].as<float>() : nullptr,
-                                                       gate ? bq->chi2 : 0.0f, m->state[3].as<int32_t>(),
+                                                       gate ? bq->nlevels : 0, gate ? bq->chi2 : 0.0f, m->state[3].as<int32_t>(),
                                                        m->state[4].as<int32_t>());
   MCK(m, cudaGetLastError());
   if ((rc = down_begin(m, (size_t)M * 8 + 256))) return rc;
@@ -2158,17 +2205,18 @@ int swm_camera_bounds(int device, const swm_camera* cam, int cols, int rows, flo
   std::string err;
   int rc = check_device(device, &err);
   if (rc != SWM_OK) return rc;
-  if (cudaSetDevice(device) != cudaSuccess) return SWM_E_CUDA;
+  if (device < 0 || device >= 64 || cudaSetDevice(device) != cudaSuccess) return SWM_E_CUDA;
   const float corners[8] = {0.f, 0.f, (float)cols, 0.f, 0.f, (float)rows, (float)cols, (float)rows};  // Frame.cc:490-494
-  float* d = nullptr;
-  if (cudaMalloc(&d, 64) != cudaSuccess) return SWM_E_CUDA;
+  StaticScratch& sc = g_static_scratch[device];
+  std::lock_guard<std::mutex> lock(sc.mu);
+  float* d = (float*)sc.reserve(64);
+  if (!d) return SWM_E_CUDA;
   float m[8];
   bool ok = cudaMemcpy(d, corners, 32, cudaMemcpyHostToDevice) == cudaSuccess;
   if (ok) {
     undistort_points_kernel<<<1, 32>>>(d, 4, camera_dev(cam), d + 8);
     ok = cudaMemcpy(m, d + 8, 32, cudaMemcpyDeviceToHost) == cudaSuccess;
   }
-  cudaFree(d);
   if (!ok) return SWM_E_CUDA;
   bounds4[0] = std::min(m[0], m[4]);  // mnMinX = min(mat(0,0), mat(2,0))   Frame.cc:501-504
   bounds4[1] = std::max(m[2], m[6]);

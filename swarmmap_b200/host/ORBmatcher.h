@@ -12,6 +12,8 @@
 // flat arrays, calls swm_match_*, and scatters the indices back into mvpMapPoints / vpMatches.
 #pragma once
 #include <cmath>
+#include <cstdint>
+#include <cstring>
 #include <set>
 #include <stdexcept>
 #include <string>
@@ -41,14 +43,25 @@ class ORBmatcher {
   ORBmatcher(const ORBmatcher&) = delete;
   ORBmatcher& operator=(const ORBmatcher&) = delete;
 
-  // Hamming distance between two ORB descriptors (ORBmatcher.cc:1511-1525).  One pair per call goes
-  // through swm_hamming_pairs; bulk callers (MapPoint::ComputeDistinctiveDescriptors' N x N loop,
-  // MapPoint.cc:361-391) should call DescriptorDistanceMatrix instead.
-  static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b, int device = 0) {
-    int32_t d = -1;
-    if (swm_hamming_pairs(a.ptr(0), b.ptr(0), 1, &d, device) != SWM_OK)
-      throw std::runtime_error("ORBmatcher::DescriptorDistance: no CUDA device (there is no CPU fallback)");
-    return d;
+  // Hamming distance between two ORB descriptors (ORBmatcher.cc:1511-1525).  ONE 32-byte pair is host glue, not the
+  // hot path: the reference's callers use it inside scalar loops (MapPoint.cc:368, Frame.cc:589), where a device
+  // round trip per pair would cost four orders of magnitude more than the eight popcounts below, which give the same
+  // integer as the reference's SWAR bit trick.  Everything batched -- DescriptorDistanceMatrix, DescriptorDistancePairs,
+  // DistinctiveDescriptor, all Search* -- runs on the GPU and has no host path.
+  static int DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
+    uint32_t pa[8], pb[8];
+    std::memcpy(pa, a.ptr(0), 32);
+    std::memcpy(pb, b.ptr(0), 32);
+    int dist = 0;
+    for (int i = 0; i < 8; i++) dist += __builtin_popcount(pa[i] ^ pb[i]);
+    return dist;
+  }
+  // n pairs in one device call (a, b: n x 32 bytes).
+  static void DescriptorDistancePairs(const unsigned char* a, const unsigned char* b, int n, std::vector<int32_t>& out,
+                                      int device = 0) {
+    out.resize((size_t)n);
+    if (swm_hamming_pairs(a, b, n, out.data(), device) != SWM_OK)
+      throw std::runtime_error("ORBmatcher::DescriptorDistancePairs: no CUDA device (there is no CPU fallback)");
   }
   static void DescriptorDistanceMatrix(const unsigned char* a, int na, const unsigned char* b, int nb,
                                        std::vector<uint16_t>& out, int device = 0) {
@@ -188,10 +201,8 @@ class ORBmatcher {
     Query q(M);
     float R[9], t[3];
     pose(CurrentFrame.mTcw, R, t);
-    // Ow = -Rcw^T * tcw (:1362)
     float Ow[3];
-    for (int c = 0; c < 3; c++)
-      Ow[c] = (float)-((double)R[c] * t[0] + (double)R[3 + c] * t[1] + (double)R[6 + c] * t[2]);
+    centre(R, t, Ow);                                                     // :1362
     for (int i = 0; i < M; i++) {
       MapPointT* pMP = vpMPs[i];
       if (!pMP || pMP->isBad() || sAlreadyFound.count(pMP)) continue;     // :1379
@@ -204,8 +215,8 @@ class ORBmatcher {
       const float v = FrameT::fy * xc[1] * invzc + FrameT::cy;
       if (u < FrameT::mnMinX || u > FrameT::mnMaxX) continue;
       if (v < FrameT::mnMinY || v > FrameT::mnMaxY) continue;
-      const float dx = xw[0] - Ow[0], dy = xw[1] - Ow[1], dz = xw[2] - Ow[2];
-      const float dist3D = std::sqrt(dx * dx + dy * dy + dz * dz);        // cv::norm(PO), :1399
+      const float PO[3] = {xw[0] - Ow[0], xw[1] - Ow[1], xw[2] - Ow[2]};
+      const float dist3D = norm3(PO);                                     // cv::norm(PO), :1399
       if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
       const int lvl = pMP->PredictScale(dist3D, CurrentFrame.mfLogScaleFactor, CurrentFrame.mnScaleLevels);
       q.valid[i] = 1;
@@ -238,14 +249,8 @@ class ORBmatcher {
     FlatFrame kf;
     gather(*pKF, kf);
     // decompose Scw (:273-277)
-    float sR[9], st[3];
-    pose(Scw, sR, st);
-    const float scw = std::sqrt(sR[0] * sR[0] + sR[1] * sR[1] + sR[2] * sR[2]);
     float R[9], t[3], Ow[3];
-    for (int i = 0; i < 9; i++) R[i] = sR[i] / scw;
-    for (int i = 0; i < 3; i++) t[i] = st[i] / scw;
-    for (int c = 0; c < 3; c++)
-      Ow[c] = (float)-((double)R[c] * t[0] + (double)R[3 + c] * t[1] + (double)R[6 + c] * t[2]);
+    sim3_decompose(Scw, R, t, Ow);
     std::set<MapPointT*> found(vpMatched.begin(), vpMatched.end());
     found.erase(static_cast<MapPointT*>(nullptr));
     const int M = (int)vpPoints.size();
@@ -261,12 +266,12 @@ class ORBmatcher {
       const float u = pKF->fx * (xc[0] * invz) + pKF->cx;
       const float v = pKF->fy * (xc[1] * invz) + pKF->cy;
       if (!pKF->IsInImage(u, v)) continue;                                // :314
-      const float dx = xw[0] - Ow[0], dy = xw[1] - Ow[1], dz = xw[2] - Ow[2];
-      const float dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+      const float PO[3] = {xw[0] - Ow[0], xw[1] - Ow[1], xw[2] - Ow[2]};
+      const float dist = norm3(PO);                                       // :319
       if (dist < pMP->GetMinDistanceInvariance() || dist > pMP->GetMaxDistanceInvariance()) continue;
       float pn[3];
       world_pos(pMP->GetNormal(), pn);
-      if (dx * pn[0] + dy * pn[1] + dz * pn[2] < 0.5 * dist) continue;    // :327
+      if (dot3(PO, pn) < 0.5 * dist) continue;                            // :327
       const int lvl = pMP->PredictScale(dist, pKF->mfLogScaleFactor, pKF->mnScaleLevels);
       q.valid[i] = 1;
       q.u[i] = u; q.v[i] = v;
@@ -369,11 +374,11 @@ class ORBmatcher {
       const float pu = pKF->fx * (Pc[0] * invz) + pKF->cx, pv = pKF->fy * (Pc[1] * invz) + pKF->cy;
       if (!pKF->IsInImage(pu, pv)) continue;                                // :790-791
       const float PO[3] = {Pw[0] - Ow[0], Pw[1] - Ow[1], Pw[2] - Ow[2]};
-      const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);  // cv::norm
+      const float dist3D = norm3(PO);                                      // cv::norm
       if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
       float Pn[3];
       world_pos(pMP->GetNormal(), Pn);
-      if ((double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2] < 0.5 * dist3D) continue;  // :808-809
+      if (dot3(PO, Pn) < 0.5 * dist3D) continue;                           // :808-809
       const int pred = pMP->PredictScale(dist3D, pKF->mfLogScaleFactor, pKF->mnScaleLevels);
       valid[i] = 1;
       u[i] = pu; v[i] = pv;
@@ -420,17 +425,8 @@ class ORBmatcher {
   int Fuse(KeyFrameT* pKF, const MatT& Scw, const std::vector<MapPointT*>& vpPoints, float th,
            std::vector<MapPointT*>& vpReplacePoint) {
     // Decompose Scw (:899-904): scw = |row 0 of sRcw|, Rcw = sRcw / scw, tcw = Scw[0:3, 3] / scw, Ow = -Rcw' tcw
-    double dot = 0;
-    for (int c = 0; c < 3; c++) dot += (double)Scw.template at<float>(0, c) * Scw.template at<float>(0, c);
-    const float scw = (float)std::sqrt(dot);
-    const double inv = 1.0 / scw;
     float R[9], t[3], Ow[3];
-    for (int r = 0; r < 3; r++) {
-      for (int c = 0; c < 3; c++) R[3 * r + c] = (float)((double)Scw.template at<float>(r, c) * inv);
-      t[r] = (float)((double)Scw.template at<float>(r, 3) * inv);
-    }
-    for (int r = 0; r < 3; r++)
-      Ow[r] = (float)(-((double)R[r] * t[0] + (double)R[3 + r] * t[1] + (double)R[6 + r] * t[2]));
+    sim3_decompose(Scw, R, t, Ow);
     const auto spAlreadyFound = pKF->GetMapPoints();
     const int M = (int)vpPoints.size();
     std::vector<uint8_t> desc((size_t)M * 32, 0), valid(M, 0);
@@ -447,11 +443,11 @@ class ORBmatcher {
       const float pu = pKF->fx * (Pc[0] * invz) + pKF->cx, pv = pKF->fy * (Pc[1] * invz) + pKF->cy;
       if (!pKF->IsInImage(pu, pv)) continue;
       const float PO[3] = {Pw[0] - Ow[0], Pw[1] - Ow[1], Pw[2] - Ow[2]};
-      const float dist3D = (float)std::sqrt((double)PO[0] * PO[0] + (double)PO[1] * PO[1] + (double)PO[2] * PO[2]);
+      const float dist3D = norm3(PO);
       if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
       float Pn[3];
       world_pos(pMP->GetNormal(), Pn);
-      if ((double)PO[0] * Pn[0] + (double)PO[1] * Pn[1] + (double)PO[2] * Pn[2] < 0.5 * dist3D) continue;
+      if (dot3(PO, Pn) < 0.5 * dist3D) continue;
       const int pred = pMP->PredictScale(dist3D, pKF->mfLogScaleFactor, pKF->mnScaleLevels);
       valid[i] = 1;
       u[i] = pu; v[i] = pv;
@@ -497,12 +493,11 @@ class ORBmatcher {
     for (int r = 0; r < 3; r++) {
       T12[r] = t12.template at<float>(r);
       for (int c = 0; c < 3; c++) {
-        sR12[3 * r + c] = (float)((double)s12 * (double)R12.template at<float>(r, c));          // s12 * R12
-        sR21[3 * r + c] = (float)((1.0 / s12) * (double)R12.template at<float>(c, r));          // (1.0 / s12) * R12.t()
+        sR12[3 * r + c] = fmul(R12.template at<float>(r, c), s12);                              // s12 * R12
+        sR21[3 * r + c] = fmul(R12.template at<float>(c, r), (float)(1.0 / (double)s12));       // (1.0 / s12) * R12.t()
       }
     }
-    for (int r = 0; r < 3; r++)  // t21 = -sR21 * t12
-      t21[r] = (float)(-((double)sR21[3 * r] * T12[0] + (double)sR21[3 * r + 1] * T12[1] + (double)sR21[3 * r + 2] * T12[2]));
+    transform(sR21, nullptr, T12, t21, -1.0);  // t21 = -sR21 * t12
     const std::vector<MapPointT*> mp1 = pKF1->GetMapPointMatches(), mp2 = pKF2->GetMapPointMatches();
     const int N1 = (int)mp1.size(), N2 = (int)mp2.size();
     std::vector<uint8_t> already1(N1, 0), already2(N2, 0);
@@ -535,7 +530,7 @@ class ORBmatcher {
   int SearchForTriangulation(KeyFrameT* pKF1, KeyFrameT* pKF2, const MatT& F12,
                              std::vector<std::pair<size_t, size_t>>& vMatchedPairs, const bool bOnlyStereo) {
     if (bOnlyStereo) throw std::runtime_error("ORBmatcher::SearchForTriangulation: stereo-only mode not supported (monocular SwarmMap)");
-    // epipole in the second image (:605-611): C2 = R2w * Cw + t2w, products of CV_32F accumulate in double
+    // epipole in the second image (:605-611): C2 = R2w * Cw + t2w
     float Cw[3], R2w[9], t2w[3], C2[3];
     world_pos(pKF1->GetCameraCenter(), Cw);
     const auto R = pKF2->GetRotation();
@@ -683,7 +678,7 @@ class ORBmatcher {
       const float invz = (float)(1.0 / Pb[2]);
       const float pu = pTgt->fx * (Pb[0] * invz) + pTgt->cx, pv = pTgt->fy * (Pb[1] * invz) + pTgt->cy;
       if (!pTgt->IsInImage(pu, pv)) continue;
-      const float dist3D = (float)std::sqrt((double)Pb[0] * Pb[0] + (double)Pb[1] * Pb[1] + (double)Pb[2] * Pb[2]);
+      const float dist3D = norm3(Pb);
       if (dist3D < pMP->GetMinDistanceInvariance() || dist3D > pMP->GetMaxDistanceInvariance()) continue;
       const int pred = pMP->PredictScale(dist3D, pTgt->mfLogScaleFactor, pTgt->mnScaleLevels);
       valid[i] = 1;
@@ -707,7 +702,13 @@ class ORBmatcher {
   }
   template <class MapPointT>
   static cv::Mat descriptor_of(MapPointT* p) { return p->GetDescriptor(); }
-  // mTcw is a 4x4 CV_32F; cv::Mat products of CV_32F accumulate in double (OpenCV gemm), mirrored here.
+  // ---- cv::Mat arithmetic of the reference's projections, as OpenCV evaluates it for these shapes (pinned against
+  // cv2 in tests/test_ref_orbmatcher.py::test_cv_shim_numerics_match_cv2, and against the reference's ORBmatcher.cc
+  // compiled on a cv::Mat stand-in with the same rules in tests/ref_vs_product_test.cpp):
+  //   R * x + t      (3x3 * 3x1, no transpose): cv::gemm's small-matrix path -- FLOAT products and sums, left to
+  //                  right, then (float)(acc * alpha + t * beta) in double;
+  //   -R.t() * t     (transposed operand): generic path, accumulation in DOUBLE, (float)(alpha * acc);
+  //   Mat::dot, cv::norm: accumulation in double;  Mat * s, Mat / s: float product with (float)s resp. (float)(1.0 / s).
   template <class MatT>
   static void pose(const MatT& Tcw, float R[9], float t[3]) {
     for (int r = 0; r < 3; r++) {
@@ -717,9 +718,35 @@ class ORBmatcher {
   }
   template <class MatT>
   static void world_pos(const MatT& p, float x[3]) { for (int i = 0; i < 3; i++) x[i] = p.template at<float>(i); }
-  static void transform(const float R[9], const float t[3], const float x[3], float out[3]) {
-    for (int r = 0; r < 3; r++)
-      out[r] = (float)((double)R[3 * r] * x[0] + (double)R[3 * r + 1] * x[1] + (double)R[3 * r + 2] * x[2] + (double)t[r]);
+  static void transform(const float R[9], const float t[3], const float x[3], float out[3], double alpha = 1.0) {
+    for (int r = 0; r < 3; r++) {
+      float acc = fmul(R[3 * r], x[0]);
+      acc = fadd(acc, fmul(R[3 * r + 1], x[1]));
+      acc = fadd(acc, fmul(R[3 * r + 2], x[2]));
+      out[r] = t ? (float)((double)acc * alpha + (double)t[r]) : (float)((double)acc * alpha);
+    }
+  }
+  // volatile stores keep the compiler from contracting a * b + c into an FMA whatever -ffp-contract says
+  static float fmul(float a, float b) { volatile float r = a * b; return r; }
+  static float fadd(float a, float b) { volatile float r = a + b; return r; }
+  static void centre(const float R[9], const float t[3], float Ow[3]) {  // -R.t() * t
+    for (int c = 0; c < 3; c++)
+      Ow[c] = (float)(-1.0 * ((double)R[c] * (double)t[0] + (double)R[3 + c] * (double)t[1] + (double)R[6 + c] * (double)t[2]));
+  }
+  static double dot3(const float a[3], const float b[3]) {
+    return (double)a[0] * (double)b[0] + (double)a[1] * (double)b[1] + (double)a[2] * (double)b[2];
+  }
+  static float norm3(const float a[3]) { return (float)std::sqrt(dot3(a, a)); }
+  // Decompose a Sim3 (:272-276, :899-903): scw = sqrt(row0 . row0), Rcw = sRcw / scw, tcw = Scw[0:3, 3] / scw
+  template <class MatT>
+  static void sim3_decompose(const MatT& Scw, float R[9], float t[3], float Ow[3]) {
+    float sR[9], st[3];
+    pose(Scw, sR, st);
+    const float scw = (float)std::sqrt(dot3(sR, sR));
+    const float inv = (float)(1.0 / (double)scw);
+    for (int i = 0; i < 9; i++) R[i] = fmul(sR[i], inv);
+    for (int i = 0; i < 3; i++) t[i] = fmul(st[i], inv);
+    centre(R, t, Ow);
   }
   void check(int rc) {
     if (rc != SWM_OK) throw std::runtime_error(std::string("ORBmatcher: ") + swm_matcher_last_error(m_));

@@ -317,7 +317,8 @@ class ORBmatcher:
         """SearchByProjection(Frame &F, const vector<MapPoint*>&, th), ORBmatcher.cc:44-121."""
         sf = np.asarray(F.mvScaleFactors, np.float32)
         pred_level = np.asarray(pred_level, np.int32)
-        r = np.where(np.asarray(view_cos, np.float32) > np.float32(0.998), np.float32(2.5), np.float32(4.0))  # :123-128
+        # RadiusByViewingCos (:123-128) compares the float against the DOUBLE literal 0.998
+        r = np.where(np.asarray(view_cos, np.float32).astype(np.float64) > 0.998, np.float32(2.5), np.float32(4.0))
         if th != 1.0:
             r = (r * np.float32(th)).astype(np.float32)
         radius = (r.astype(np.float32) * sf[pred_level]).astype(np.float32)

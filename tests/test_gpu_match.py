@@ -134,7 +134,7 @@ def test_search_by_projection_wrappers(oracle, swm, frames):
     m3 = ORBmatcher(0.8, True)
     cosv = rng.uniform(0.99, 1.0, last.N).astype(np.float32)
     n, asg = m3.SearchByProjectionMapPoints(cur, last.desc, u, v, last.octave, cosv, valid, th=1.0)
-    r = np.where(cosv > np.float32(0.998), np.float32(2.5), np.float32(4.0)).astype(np.float32) * sf[last.octave]
+    r = np.where(cosv.astype(np.float64) > 0.998, np.float32(2.5), np.float32(4.0)).astype(np.float32) * sf[last.octave]
     on, oasg = oracle.match_window(cur, last.desc, u, v, r.astype(np.float32), last.octave - 1, last.octave, valid,
                                    valid, 100, 1, 0.8, False)
     assert n == on and (asg == oasg).all() and n > 100
