@@ -312,6 +312,59 @@ int swm_match_triangulation_resident(swm_matcher* m, const swm_frame* f1, const 
 int swm_window_best_resident(swm_matcher* m, const swm_frame* tgt, const swm_best_query* q, int32_t* best_idx,
                              int32_t* best_dist);
 
+/* ------------------------------------------------------------------ batched matchers (throughput form)
+ * P independent matching problems per call: what a GPU serving many agents -- or a recorded stream being replayed --
+ * has in flight.  All host arrays of all jobs travel in ONE upload, six launches serve the whole batch (one resolve
+ * CTA per job replays that job's greedy order: code/src/ORBmatcher.cc:44-121, :150-262, :375-479, :481-597,
+ * :1223-1354), ONE download brings every result back, and there is no synchronisation in the middle of the call.
+ * Each job has exactly the semantics and the results of the corresponding single call above: swm_match_window,
+ * swm_match_init, swm_match_bow.  A job's frames are host arrays (f1 / f2 / tgt) OR resident frames (r1 / r2 /
+ * tgt_resident), never both.  nmatches is written into the job. */
+typedef struct swm_window_job {
+  const swm_frame_view* tgt;
+  const swm_frame* tgt_resident;
+  const swm_window_query* q;
+  const uint8_t* tgt_blocked; /* n2, may be NULL */
+  int32_t th_dist, ratio_mode;
+  float nnratio;
+  int32_t check_ori;
+  int32_t* assignment;        /* n2, in/out */
+  int32_t nmatches;           /* out */
+} swm_window_job;
+int swm_match_window_batch(swm_matcher* m, swm_window_job* jobs, int njobs);
+
+typedef struct swm_init_job {
+  const swm_frame_view *f1, *f2;
+  const swm_frame *r1, *r2;
+  float* prev_xy;             /* n1 x 2, in/out */
+  int32_t* matches12;         /* n1, out */
+  int32_t window;
+  float nnratio;
+  int32_t check_ori;
+  int32_t nmatches;           /* out */
+} swm_init_job;
+int swm_match_init_batch(swm_matcher* m, swm_init_job* jobs, int njobs);
+
+/* The merge-walk over the two FeatureVectors and the expansion of the shared nodes into candidate rows run on the
+ * device from the two CSRs (node ids strictly ascending). */
+typedef struct swm_bow_job {
+  const swm_frame_view *f1, *f2;
+  const swm_frame *r1, *r2;
+  const swm_featvec *fv1, *fv2;
+  const uint8_t *valid1, *valid2; /* valid2: mode 1 only */
+  int32_t mode;
+  float nnratio;
+  int32_t check_ori;
+  int32_t* matches;           /* mode 0: n2 entries, mode 1: n1 entries */
+  int32_t nmatches;           /* out */
+} swm_bow_job;
+int swm_match_bow_batch(swm_matcher* m, swm_bow_job* jobs, int njobs);
+
+/* Resident frames for `count` frames of the extractor's most recent batch in two launches and one read-back of the
+ * keypoint counts (indices == NULL: frames 0 .. count-1).  Same results as swm_frame_from_extractor per frame. */
+int swm_frames_from_extractor(swm_frame** frames, int count, swm_orb* h, const int32_t* indices, const swm_camera* cam,
+                              const float* bounds4);
+
 /* ------------------------------------------------------------------ DBoW2 transform
  * TemplatedVocabulary<FORB>::transform(features, BowVector&, FeatureVector&, levelsup)
  * (code/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1151-1218, per feature :1242-1283) as called by

@@ -21,6 +21,35 @@ __global__ void score_map_kernel(const cv::cuda::PtrStepSzb img, int threshold, 
   if (i < img.rows - 3 && j < img.cols - 3) isKeyPoint2(img, i, j, threshold, scoreMat);
 }
 
+// tileCalcKeypoints_kernel's four phases (Fast_gpu.cu:296-340) run as separate launches, i.e. in LOCK-STEP over the
+// whole image: every tile finishes a phase before any tile starts the next.  The per-pixel work is the reference's own
+// device code (isKeyPoint2, isMax); only the phase boundaries are kernel boundaries here instead of __syncthreads(),
+// which removes the inter-block race of the original launch and nothing else.  tile = the original kernel's block:
+// pixels j in [3 + 32 bx, 35 + 32 bx), i in [3 + 32 by, 35 + 32 by).
+__global__ void ls_score_kernel(const cv::cuda::PtrStepSzb img, int threshold, cv::cuda::PtrStepi scoreMat,
+                                const uint8_t* has_kp, int tiles_x, uint8_t* is_kp) {
+  const int j = threadIdx.x + blockIdx.x * blockDim.x + 3;
+  const int i = threadIdx.y + blockIdx.y * blockDim.y + 3;
+  if (!(i < img.rows - 3 && j < img.cols - 3)) return;
+  if (has_kp && has_kp[((i - 3) / 32) * tiles_x + (j - 3) / 32]) return;  // `if (hasKp) return;` (:318)
+  is_kp[(size_t)i * img.cols + j] = isKeyPoint2(img, i, j, threshold, scoreMat) ? 1 : 0;
+}
+__global__ void ls_nms_kernel(const cv::cuda::PtrStepSzb img, cv::cuda::PtrStepi scoreMat, const uint8_t* is_kp,
+                              const uint8_t* skip_tiles, uint8_t* has_kp, int tiles_x, int32_t* out, int cap,
+                              unsigned int* counter) {
+  const int j = threadIdx.x + blockIdx.x * blockDim.x + 3;
+  const int i = threadIdx.y + blockIdx.y * blockDim.y + 3;
+  if (!(i < img.rows - 3 && j < img.cols - 3)) return;
+  const int tile = ((i - 3) / 32) * tiles_x + (j - 3) / 32;
+  if (skip_tiles && skip_tiles[tile]) return;
+  if (!is_kp[(size_t)i * img.cols + j]) return;
+  if (isMax(make_short2(j, i), scoreMat)) {
+    if (has_kp) has_kp[tile] = 1;
+    const unsigned int ind = atomicInc(counter, (unsigned int)(-1));
+    if ((int)ind < cap) { out[3 * ind] = j; out[3 * ind + 1] = i; out[3 * ind + 2] = scoreMat(i, j); }
+  }
+}
+
 cv::cuda::GpuMat upload(const uint8_t* img, int w, int h, int stride) {
   cv::cuda::GpuMat g(h, w, CV_8UC1);
   g.upload(img, (size_t)stride);
@@ -48,6 +77,36 @@ int refc_fast_detect(const uint8_t* img, int w, int h, int stride, int hi, int l
     out[3 * i] = (int32_t)kps[i].pt.x; out[3 * i + 1] = (int32_t)kps[i].pt.y; out[3 * i + 2] = (int32_t)kps[i].response;
   }
   return n;
+}
+
+// The lock-step execution described above.  out: n x (x, y, score); has_kp_out (tiles_x * tiles_y, may be NULL)
+// receives each tile's pass-1 outcome.
+int refc_fast_detect_lockstep(const uint8_t* img, int w, int h, int stride, int hi, int lo, int32_t* out, int cap,
+                              uint8_t* has_kp_out) {
+  cv::cuda::GpuMat g = upload(img, w, h, stride);
+  cv::cuda::GpuMat score(h, w, CV_32SC1);
+  cv::cuda::Stream st;
+  score.setTo(cv::Scalar::all(0), st);
+  const int tiles_x = (w - 6 + 31) / 32, tiles_y = (h - 6 + 31) / 32;
+  uint8_t *is_kp, *has_kp, *snap;
+  int32_t* d_out;
+  unsigned int* counter;
+  cudaMalloc(&is_kp, (size_t)w * h); cudaMalloc(&has_kp, tiles_x * tiles_y); cudaMalloc(&snap, tiles_x * tiles_y);
+  cudaMalloc(&d_out, (size_t)cap * 12); cudaMalloc(&counter, 4);
+  cudaMemset(is_kp, 0, (size_t)w * h); cudaMemset(has_kp, 0, tiles_x * tiles_y); cudaMemset(counter, 0, 4);
+  dim3 block(32, 8), grid((w + 31) / 32, (h + 7) / 8);
+  ls_score_kernel<<<grid, block>>>(g, hi, score, nullptr, tiles_x, is_kp);
+  ls_nms_kernel<<<grid, block>>>(g, score, is_kp, nullptr, has_kp, tiles_x, d_out, cap, counter);
+  cudaMemcpy(snap, has_kp, tiles_x * tiles_y, cudaMemcpyDeviceToDevice);  // pass-1 outcome, frozen
+  cudaMemset(is_kp, 0, (size_t)w * h);
+  ls_score_kernel<<<grid, block>>>(g, lo, score, snap, tiles_x, is_kp);
+  ls_nms_kernel<<<grid, block>>>(g, score, is_kp, snap, nullptr, tiles_x, d_out, cap, counter);
+  unsigned int n = 0;
+  cudaMemcpy(&n, counter, 4, cudaMemcpyDeviceToHost);
+  cudaMemcpy(out, d_out, (size_t)(n < (unsigned)cap ? n : cap) * 12, cudaMemcpyDeviceToHost);
+  if (has_kp_out) cudaMemcpy(has_kp_out, snap, tiles_x * tiles_y, cudaMemcpyDeviceToHost);
+  cudaFree(is_kp); cudaFree(has_kp); cudaFree(snap); cudaFree(d_out); cudaFree(counter);
+  return (int)n;
 }
 
 // score map at one threshold: 0 where isKeyPoint2 says "not a corner", cornerScore otherwise

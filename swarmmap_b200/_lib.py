@@ -68,6 +68,25 @@ class FeatVec(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("node_ids", C.c_void_p), ("offsets", C.c_void_p), ("feats", C.c_void_p)]
 
 
+class WindowJob(C.Structure):
+    _fields_ = [("tgt", C.c_void_p), ("tgt_resident", C.c_void_p), ("q", C.c_void_p), ("tgt_blocked", C.c_void_p),
+                ("th_dist", C.c_int32), ("ratio_mode", C.c_int32), ("nnratio", C.c_float), ("check_ori", C.c_int32),
+                ("assignment", C.c_void_p), ("nmatches", C.c_int32)]
+
+
+class InitJob(C.Structure):
+    _fields_ = [("f1", C.c_void_p), ("f2", C.c_void_p), ("r1", C.c_void_p), ("r2", C.c_void_p),
+                ("prev_xy", C.c_void_p), ("matches12", C.c_void_p), ("window", C.c_int32), ("nnratio", C.c_float),
+                ("check_ori", C.c_int32), ("nmatches", C.c_int32)]
+
+
+class BowJob(C.Structure):
+    _fields_ = [("f1", C.c_void_p), ("f2", C.c_void_p), ("r1", C.c_void_p), ("r2", C.c_void_p),
+                ("fv1", C.c_void_p), ("fv2", C.c_void_p), ("valid1", C.c_void_p), ("valid2", C.c_void_p),
+                ("mode", C.c_int32), ("nnratio", C.c_float), ("check_ori", C.c_int32), ("matches", C.c_void_p),
+                ("nmatches", C.c_int32)]
+
+
 # every symbol include/swm_orb.h declares: (name, restype, argtypes)
 _vp, _i, _f, _sz, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_int64
 SYMBOLS = [
@@ -118,6 +137,10 @@ SYMBOLS = [
     ("swm_match_init_resident", _i, [_vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp]),
     ("swm_match_window_resident", _i, [_vp, _vp, _vp, _vp, _i, _i, _f, _i, _vp, _vp]),
     ("swm_match_bow_resident", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _f, _i, _vp, _vp]),
+    ("swm_match_window_batch", _i, [_vp, _vp, _i]),
+    ("swm_match_init_batch", _i, [_vp, _vp, _i]),
+    ("swm_match_bow_batch", _i, [_vp, _vp, _i]),
+    ("swm_frames_from_extractor", _i, [_vp, _i, _vp, _vp, _vp, _vp]),
     ("swm_vocab_create", _i, [_i, _vp, _sz, _vp]),
     ("swm_vocab_destroy", None, [_vp]),
     ("swm_vocab_last_error", C.c_char_p, [_vp]),

@@ -79,8 +79,8 @@ struct FrameDev {
   const int32_t* items;
 };
 
-__global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int32_t* __restrict__ starts,
-                                                          int32_t* __restrict__ items, int32_t* __restrict__ cell_of) {
+__device__ __forceinline__ void grid_build_body(const FrameDev& f, int32_t* __restrict__ starts,
+                                                int32_t* __restrict__ items, int32_t* __restrict__ cell_of) {
   __shared__ int s_cnt[kCells + 1];
   __shared__ int s_part[1024];
   const int tid = threadIdx.x;
@@ -136,6 +136,11 @@ __global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int32_t* _
       items[j + 1] = v;
     }
   }
+}
+
+__global__ void __launch_bounds__(1024) grid_build_kernel(FrameDev f, int32_t* __restrict__ starts,
+                                                          int32_t* __restrict__ items, int32_t* __restrict__ cell_of) {
+  grid_build_body(f, starts, items, cell_of);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -233,10 +238,9 @@ struct WindowDev {
   const uint8_t* valid;
 };
 
-__global__ void __launch_bounds__(256) window_rows_kernel(FrameDev f, WindowDev q, int pass,
-                                                          int32_t* __restrict__ row_count,
-                                                          const int32_t* __restrict__ row_start,
-                                                          int32_t* __restrict__ cand_idx, uint32_t* __restrict__ cand_val) {
+__device__ __forceinline__ void window_rows_body(const FrameDev& f, const WindowDev& q, int pass,
+                                                 int32_t* __restrict__ row_count, const int32_t* __restrict__ row_start,
+                                                 int32_t* __restrict__ cand_idx, uint32_t* __restrict__ cand_val) {
   const int s = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (s >= q.m) return;
@@ -287,6 +291,13 @@ __global__ void __launch_bounds__(256) window_rows_kernel(FrameDev f, WindowDev 
     }
   }
   if (!pass && lane == 0) row_count[s] = total;
+}
+
+__global__ void __launch_bounds__(256) window_rows_kernel(FrameDev f, WindowDev q, int pass,
+                                                          int32_t* __restrict__ row_count,
+                                                          const int32_t* __restrict__ row_start,
+                                                          int32_t* __restrict__ cand_idx, uint32_t* __restrict__ cand_val) {
+  window_rows_body(f, q, pass, row_count, row_start, cand_idx, cand_val);
 }
 
 // BoW rows: candidate indices come from the shared vocabulary nodes (host-built spans); fill distances.
@@ -404,7 +415,7 @@ __device__ __forceinline__ bool cand_skip(const ResolveArgs& a, const int* match
 // next batch.  Every committed row decided exactly as the serial loop would: indices stay bit-exact.
 constexpr int kResolveWarps = 32;
 
-__global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs a) {
+__device__ __forceinline__ void resolve_body(const ResolveArgs& a) {
   extern __shared__ __align__(16) uint8_t dsm[];
   __shared__ int s_row[kResolveWarps], s_accept[kResolveWarps], s_best_idx[kResolveWarps], s_best_dist[kResolveWarps];
   __shared__ int s_second_idx[kResolveWarps];
@@ -732,6 +743,8 @@ __global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs
     a.nmatches[1] = s_batches;  // diagnostics: speculative batches executed
   }
 }
+
+__global__ void __launch_bounds__(kResolveWarps * 32) resolve_kernel(ResolveArgs a) { resolve_body(a); }
 
 // ---------------------------------------------------------------------------------------------
 // SearchForTriangulation (ORBmatcher.cc:599-749, monocular) with CheckDistEpipolarLine (:131-148).  The reference
@@ -1211,6 +1224,11 @@ struct swm_matcher {
   DevBuf rowlist;  // resolve_kernel's compacted row list
   DevBuf rows[5];  // row_count, row_start, cand_idx, cand_val, row_src
   DevBuf state[7]; // blocked, matched_dist, matches21, out, ev_bin, ev_tgt, nmatches/prev
+  // batch calls (match_batch.cuh): per-call scratch and the shared candidate buffers (index, level | distance),
+  // grow-only, sized from earlier calls
+  DevBuf bscratch;
+  DevBuf bcand[2];
+  size_t bcand_cap = 0;
   // upload arena: every host array of a call is packed into one pinned buffer and sent with ONE copy
   uint8_t* h_arena = nullptr;
   uint8_t* d_arena = nullptr;
@@ -1233,6 +1251,9 @@ struct swm_matcher {
     rowlist.release();
     for (auto& b : rows) b.release();
     for (auto& b : state) b.release();
+    bscratch.release();
+    for (auto& b : bcand) b.release();
+    bcand_cap = 0;
   }
 };
 
@@ -1245,6 +1266,10 @@ struct swm_frame {
   FrameDev dev{};
   cudaStream_t stream = nullptr;  // uploads; frames built from the extractor use the extractor's stream
   cudaEvent_t ready = nullptr;    // recorded after the last kernel that writes the frame
+  // swm_frames_from_extractor: the first frame of a batch carries the build table and the pinned count read-back
+  DevBuf bstage;
+  int32_t* h_counts = nullptr;
+  size_t h_counts_cap = 0;
 };
 
 namespace {
@@ -2187,6 +2212,8 @@ void swm_frame_destroy(swm_frame* f) {
   cudaSetDevice(f->device);
   if (f->ready) cudaEventSynchronize(f->ready);
   for (auto& b : f->b) b.release();
+  f->bstage.release();
+  if (f->h_counts) cudaFreeHost(f->h_counts);
   if (f->ready) cudaEventDestroy(f->ready);
   if (f->stream) cudaStreamDestroy(f->stream);
   delete f;
@@ -2507,3 +2534,4 @@ int frame_device_view(const swm_frame* f, FrameDeviceView* out) {
 }
 }  // namespace swm
 
+#include "match_batch.cuh"

@@ -374,6 +374,114 @@ class ORBmatcher:
         return n.value, out
 
 
+# ---- batched (throughput) forms: P independent problems per call, same results as the single calls
+
+def _frame_fields(fr, keep):
+    """(host view pointer, resident handle) of a Frame / ResidentFrame for a batch job."""
+    if isinstance(fr, ResidentFrame):
+        return None, fr._h
+    v = fr.view()
+    keep.append(v)
+    return C.addressof(v), None
+
+
+def _window_job(self, keep, tgt, desc, u, v, radius, min_level, max_level, valid, blocks, th_dist, ratio_mode=0,
+                angle=None, tgt_blocked=None, assignment=None, check_ori=None):
+    from ._lib import WindowJob
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    a = [np.ascontiguousarray(u, np.float32), np.ascontiguousarray(v, np.float32),
+         np.ascontiguousarray(radius, np.float32), np.ascontiguousarray(min_level, np.int32),
+         np.ascontiguousarray(max_level, np.int32), np.ascontiguousarray(valid, np.uint8),
+         np.ascontiguousarray(blocks, np.uint8)]
+    check_ori = self.mbCheckOrientation if check_ori is None else bool(check_ori)
+    ang = np.ascontiguousarray(angle, np.float32) if angle is not None else None
+    if check_ori and ang is None:
+        raise ValueError("angle is required when the orientation check is on")
+    q = WindowQuery(len(a[0]), ptr(desc).value, ptr(a[0]).value, ptr(a[1]).value, ptr(a[2]).value, ptr(a[3]).value,
+                    ptr(a[4]).value, ptr(a[5]).value, ptr(ang).value if ang is not None else None, ptr(a[6]).value)
+    asg = np.full(tgt.N, -1, np.int32) if assignment is None else assignment
+    tb = np.ascontiguousarray(tgt_blocked, np.uint8) if tgt_blocked is not None else None
+    hv, hr = _frame_fields(tgt, keep)
+    keep.extend([desc, a, ang, q, tb, asg])
+    return WindowJob(hv, hr, C.addressof(q), ptr(tb).value if tb is not None else None, int(th_dist), int(ratio_mode),
+                     self.mfNNratio, int(check_ori), ptr(asg).value, 0), asg
+
+
+def _match_window_batch(self, jobs):
+    """jobs: list of dicts with match_window's arguments.  Returns [(nmatches, assignment), ...]."""
+    from ._lib import WindowJob
+    keep, outs = [], []
+    arr = (WindowJob * len(jobs))()
+    for i, kw in enumerate(jobs):
+        arr[i], asg = _window_job(self, keep, **kw)
+        outs.append(asg)
+    self._check(self._lib.swm_match_window_batch(self._h, arr, len(jobs)), "swm_match_window_batch")
+    return [(int(arr[i].nmatches), outs[i]) for i in range(len(jobs))]
+
+
+def _search_for_initialization_batch(self, pairs, windowSize=10):
+    """pairs: list of (F1, F2, vbPrevMatched (N1 x 2 float32, updated in place)).  Returns [(nmatches, vnMatches12)]."""
+    from ._lib import InitJob
+    keep, outs = [], []
+    arr = (InitJob * len(pairs))()
+    for i, (F1, F2, prev) in enumerate(pairs):
+        assert prev.dtype == np.float32 and prev.shape == (F1.N, 2) and prev.flags.c_contiguous
+        if isinstance(F1, ResidentFrame) != isinstance(F2, ResidentFrame):
+            raise TypeError("both frames must be resident or both host-side")
+        m12 = np.full(F1.N, -1, np.int32)
+        v1, r1 = _frame_fields(F1, keep)
+        v2, r2 = _frame_fields(F2, keep)
+        arr[i] = InitJob(v1, v2, r1, r2, ptr(prev).value, ptr(m12).value, int(windowSize), self.mfNNratio,
+                         int(self.mbCheckOrientation), 0)
+        outs.append(m12)
+    self._check(self._lib.swm_match_init_batch(self._h, arr, len(pairs)), "swm_match_init_batch")
+    return [(int(arr[i].nmatches), outs[i]) for i in range(len(pairs))]
+
+
+def _search_by_bow_batch(self, jobs):
+    """jobs: list of (KF, fvKF, validKF, F, fvF, validF-or-None).  Returns [(nmatches, matches)]."""
+    from ._lib import BowJob
+    keep, outs = [], []
+    arr = (BowJob * len(jobs))()
+    for i, (KF, fvKF, validKF, F, fvF, validF) in enumerate(jobs):
+        mode = 0 if validF is None else 1
+        if isinstance(KF, ResidentFrame) != isinstance(F, ResidentFrame):
+            raise TypeError("both frames must be resident or both host-side")
+        v1 = np.ascontiguousarray(validKF, np.uint8)
+        v2 = np.ascontiguousarray(validF, np.uint8) if validF is not None else None
+        out = np.full(F.N if mode == 0 else KF.N, -1, np.int32)
+        fa, fb = fvKF.view(), fvF.view()
+        h1, r1 = _frame_fields(KF, keep)
+        h2, r2 = _frame_fields(F, keep)
+        keep.extend([v1, v2, fa, fb])
+        arr[i] = BowJob(h1, h2, r1, r2, C.addressof(fa), C.addressof(fb), ptr(v1).value,
+                        ptr(v2).value if v2 is not None else None, mode, self.mfNNratio, int(self.mbCheckOrientation),
+                        ptr(out).value, 0)
+        outs.append(out)
+    self._check(self._lib.swm_match_bow_batch(self._h, arr, len(jobs)), "swm_match_bow_batch")
+    return [(int(arr[i].nmatches), outs[i]) for i in range(len(jobs))]
+
+
+ORBmatcher.match_window_batch = _match_window_batch
+ORBmatcher.SearchForInitializationBatch = _search_for_initialization_batch
+ORBmatcher.SearchByBoWBatch = _search_by_bow_batch
+
+
+def resident_frames_from_extractor(extractor, count, camera, bounds, device=0, frames=None):
+    """ResidentFrames for frames 0..count-1 of the extractor's last batch (two launches, one count read-back)."""
+    lib = _lib.load()
+    frames = frames if frames is not None else [ResidentFrame(device) for _ in range(count)]
+    hs = (C.c_void_p * count)(*[f._h for f in frames[:count]])
+    b = np.ascontiguousarray(bounds, np.float32)
+    cam = C.byref(camera.c) if camera is not None else None
+    rc = lib.swm_frames_from_extractor(hs, count, extractor._h, None, cam, _lib.ptr(b))
+    frames[0]._check(rc, "swm_frames_from_extractor")
+    sf = extractor.GetScaleFactors()
+    for f in frames[:count]:
+        f.mvScaleFactors = sf
+    return frames
+
+
 def _search_for_triangulation(self, KF1, fv1, no_mp1, KF2, fv2, no_mp2, F12, ex, ey, scale_factors2, level_sigma2):
     """SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs, bOnlyStereo=false), ORBmatcher.cc:599-749 (monocular).
     no_mp1 / no_mp2: 1 where the keypoint has no MapPoint yet; (ex, ey): epipole of KF1's centre in KF2 (:605-611).

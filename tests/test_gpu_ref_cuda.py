@@ -9,9 +9,12 @@ What is compared, and how the reference kernel's races are kept o
     kernel has no inter-block race and its only nondeterminism is the atomicInc output order, so the sorted keypoint
     set must equal orc_fast_tile_select's exactly (incl. tiles that retry at minThFAST);
   * on whole level ROIs the kernel does race across tile borders (a block may read a neighbour's score before it is
-    written or after the neighbour's retry pass rewrote it); the oracle's lock-step definition is what the kernel
-    produces when no such read is early or late, so the two sets may differ only in tiles touched by that race: the
-    test bounds the differing tiles (<= 2 %) and prints the count;
+    written or after the neighbour's retry pass rewrote it).  The oracle's lock-step definition is what the kernel
+    produces when no such read is early or late; it is checked EXACTLY by running the kernel's four phases as four
+    launches built from the reference's own device functions (isKeyPoint2, isMax; oracle/ref_cuda_wrap.cu
+    refc_fast_detect_lockstep): keypoint set and per-tile retry flags identical on whole ROIs.  The original racy
+    launch is run too and reported (measured on a B200: 43 of ~1970 keypoints in 20 of 322 tiles at level 0), with a
+    loose bound;
   * IC_Angle_kernel + addBorder_kernel (:403-471): pt / octave / size bit-exact, angle within 1e-4 rad;
   * calcOrb_kernel (Orb_gpu.cu:67-100): >= 99.9 % of descriptor bits (its cosf / sinf are the fast-math intrinsics).
 """
@@ -121,8 +124,27 @@ def test_single_tile_keypoint_sets_equal_reference_kernel(oracle, refc, extracte
     assert retried > 20 and with_kp > 150, (retried, with_kp)
 
 
+@pytest.mark.parametrize("level", [0, 1, 2, 4, 7])
+def test_whole_roi_lockstep_of_reference_device_code(oracle, refc, extracted, level):
+    cpu = extracted[0]
+    plane = cpu.level(level, 0)
+    roi = np.ascontiguousarray(plane[19 + 16:-(19 + 16), 19 + 16:-(19 + 16)])  # [16, w-16) x [16, h-16)
+    h, w = roi.shape
+    tiles_x, tiles_y = (w - 6 + 31) // 32, (h - 6 + 31) // 32
+    out = np.zeros((10000, 3), np.int32)
+    has_kp = np.zeros((tiles_y, tiles_x), np.uint8)
+    n = refc.refc_fast_detect_lockstep(_p(roi), w, h, roi.strides[0], 20, 7, _p(out), 10000, _p(has_kp))
+    got = sorted(map(tuple, out[:n].tolist()), key=lambda t: (t[1], t[0]))
+    o = cpu.level_fast(level)
+    exp = sorted(zip(o["x"].tolist(), o["y"].tolist(), o["score"].tolist()), key=lambda t: (t[1], t[0]))
+    assert len(exp) > 50 and got == exp
+    score = oracle.fast_score_map(roi, 7)
+    _, retry = oracle.fast_tile_select(score, 20, want_retry=True)
+    np.testing.assert_array_equal(has_kp == 0, retry[:tiles_y, :tiles_x] != 0)
+
+
 @pytest.mark.parametrize("level", [0, 2, 5])
-def test_whole_roi_differs_from_lockstep_only_by_the_tile_race(oracle, refc, extracted, level):
+def test_whole_roi_racy_launch_is_close_to_lockstep(oracle, refc, extracted, level):
     cpu = extracted[0]
     plane = cpu.level(level, 0)
     roi = np.ascontiguousarray(plane[19 + 16:-(19 + 16), 19 + 16:-(19 + 16)])  # [16, w-16) x [16, h-16)
@@ -135,7 +157,7 @@ def test_whole_roi_differs_from_lockstep_only_by_the_tile_race(oracle, refc, ext
     print(f"level {level}: reference kernel {len(got)} keypoints, lock-step oracle {len(exp)}, "
           f"{len(diff)} differ in {len(tiles)} of {n_tiles} tiles")
     assert len(exp) > 100
-    assert len(tiles) <= max(1, int(0.02 * n_tiles)), (len(tiles), n_tiles)
+    assert len(tiles) <= max(2, int(0.15 * n_tiles)), (len(tiles), n_tiles)
 
 
 def test_ic_angle_equals_reference_kernel(oracle, refc, ref_tables, extracted):
