@@ -360,6 +360,10 @@ typedef struct swm_bow_job {
 } swm_bow_job;
 int swm_match_bow_batch(swm_matcher* m, swm_bow_job* jobs, int njobs);
 
+/* Device time (ms, CUDA events on the matcher's stream) of the six kernels of the most recent batch call, without its
+ * upload and download: what bench.py reports next to the host-clock time of the whole call. */
+float swm_matcher_last_device_ms(const swm_matcher* m);
+
 /* Resident frames for `count` frames of the extractor's most recent batch in two launches and one read-back of the
  * keypoint counts (indices == NULL: frames 0 .. count-1).  Same results as swm_frame_from_extractor per frame. */
 int swm_frames_from_extractor(swm_frame** frames, int count, swm_orb* h, const int32_t* indices, const swm_camera* cam,
@@ -420,7 +424,19 @@ int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t*
  * ranks this equals the single-shard vote histogram). */
 int swm_db_merge_gathered(swm_db* db, const uint64_t* d_gathered, int world, int nq, int k, uint64_t* d_topk,
                           int32_t* d_votes, int th_votes, void* stream);
+/* The whole sharded query on one rank, for a C++ caller (the role of AgentMediator::CheckOverlapCandidates,
+ * code/src/AgentMediator.cc:140-202 + KeyFrameDatabase.cc:74-185): local top-k, ONE ncclAllGather of the (nq, k) key
+ * blocks over NVLink, merge + votes -- three enqueues on `stream`, no host synchronisation.  nccl_comm: an
+ * ncclComm_t (passed as void* so that this header does not need nccl.h) of `world` ranks, one shard each; the
+ * library binds ncclAllGather from the NCCL already loaded in the process (dlopen, no link-time dependency).
+ * d_topk (nq x k) is identical on every rank; d_votes: this shard's keyframes, as in swm_db_merge_gathered. */
+int swm_db_query_sharded(swm_db* db, void* nccl_comm, int world, const uint8_t* d_q, int nq, int k, uint64_t* d_topk,
+                         int32_t* d_votes, int th_votes, void* stream);
 int64_t swm_db_size(const swm_db* db);
+/* Measured int8 rate of the tensor pipe on `device`, in TOP/s: one CTA per SM issues `iters` back-to-back tcgen05
+ * kind::i8 MMAs and nothing else (mode 0: 128 x 64 x 32 with A in TMEM, the shape the shard scan issues; mode 1:
+ * 128 x 256 x 32 from shared memory).  The denominator of the shard scan's roofline in bench.py. */
+int swm_i8_peak(int device, int mode, int iters, double* tops);
 
 /* Build id string ("swm_orb <version> sm_100a <date>"). */
 const char* swm_version(void);

@@ -141,6 +141,7 @@ SYMBOLS = [
     ("swm_match_init_batch", _i, [_vp, _vp, _i]),
     ("swm_match_bow_batch", _i, [_vp, _vp, _i]),
     ("swm_frames_from_extractor", _i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    ("swm_matcher_last_device_ms", C.c_float, [_vp]),
     ("swm_vocab_create", _i, [_i, _vp, _sz, _vp]),
     ("swm_vocab_destroy", None, [_vp]),
     ("swm_vocab_last_error", C.c_char_p, [_vp]),
@@ -152,7 +153,9 @@ SYMBOLS = [
     ("swm_db_destroy", None, [_vp]),
     ("swm_db_query_device", _i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     ("swm_db_merge_gathered", _i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
+    ("swm_db_query_sharded", _i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp]),
     ("swm_db_size", _i64, [_vp]),
+    ("swm_i8_peak", _i, [_i, _i, _i, _vp]),
 ]
 
 _lib = None

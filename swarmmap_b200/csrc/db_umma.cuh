@@ -435,3 +435,67 @@ db_top2_umma_kernel(const uint4* __restrict__ db, long long ndb, long long first
 }
 
 }  // namespace umma
+
+// ------------------------------------------------------------------------------------------------
+// Measured int8 peak of the tensor pipe (tcgen05 kind::i8): a pure MMA issue loop, no producers and no epilogue.
+// One CTA per SM; one elected thread issues `iters` MMAs of the scan's own shapes back to back and commits once.
+//   mode 0: 128 x 64 x 32, A from TMEM (.ts)   -- the shape db_top2_umma_kernel issues for K steps 0-7
+//   mode 1: 128 x 256 x 32, A and B from shared memory (.ss) -- the largest single-CTA int8 MMA
+// Operands are whatever the freshly allocated shared memory / TMEM holds (the values do not matter for the rate).
+// The roofline of the shard scan is reported against this number instead of the nominal 4.5 POP/s.
+// ------------------------------------------------------------------------------------------------
+namespace umma {
+constexpr int kPeakSmem = 32 * 1024;  // B at +0 (<= 18.4 KB), A at +24 KB (4 KB)
+__global__ void __launch_bounds__(128, 1) i8_peak_kernel(int mode, int iters, unsigned long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < kPeakSmem / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x01010101u, 0, 0x02020202u, 0);
+  if (tid == 0) {
+    mbar_init(smem_u32(&s_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem;
+  if (warp == 0) {
+    const uint32_t b_lo = smem_desc_lo(smem_u32(smem));
+    const uint32_t a_lo = smem_desc_lo(smem_u32(smem + 24 * 1024));
+    // N = 256 instruction descriptor for mode 1 (same fields as kIdesc)
+    const uint32_t idesc256 = (2u << 4) | (1u << 7) | (0u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+    const long long t0 = clock64();
+    if (elect_one()) {
+      if (mode == 0) {
+        // six accumulator tiles in rotation (the scan keeps 3 stages x 2 tiles in flight): back-to-back MMAs into ONE
+        // accumulator would measure the accumulate latency, not the issue rate
+        for (int i = 0; i < iters; i++) mma_i8_ts(tmem_base + (uint32_t)(i % 6) * kTileN, tmem_base + kTmemA, b_lo, i > 5);
+      } else {
+        for (int i = 0; i < iters; i++)
+          asm volatile(
+              "{\n.reg .b64 da, db;\n.reg .pred p;\nsetp.eq.u32 p, 1, 1;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %4};\n"
+              "tcgen05.mma.cta_group::1.kind::i8 [%0], da, db, %5, p;\n}" ::"r"(tmem_base + (uint32_t)(i & 1) * 256u),
+              "r"(a_lo), "r"(b_lo), "r"(kDescHiA), "r"(kDescHiA), "r"(idesc256)  // 256-byte 8-row groups: A 4 KB, B 8 KB
+              : "memory");
+      }
+      mma_commit(smem_u32(&s_bar));
+    }
+    __syncwarp();
+    mbar_wait(smem_u32(&s_bar), 0);
+    if (tid == 0 && cycles) cycles[blockIdx.x] = (unsigned long long)(clock64() - t0);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+}  // namespace umma

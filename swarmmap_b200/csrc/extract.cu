@@ -849,6 +849,7 @@ struct swm_orb {
   swm_keypoint* stage_kps = nullptr;
   uint8_t* stage_desc = nullptr;
   int stage_ccap = 0;
+  int graph_stride = 0;  // row stride the single-frame graph was captured with
 };
 
 namespace {
@@ -1212,7 +1213,12 @@ static int enqueue_host_chunk(swm_orb* h, const uint8_t* src, int nb, int w, int
                               size_t frame_stride, swm_keypoint* kps, uint8_t* desc, int cap, int32_t* n) {
   const int kcap = h->max_kp;
   const int ccap = cap < kcap ? cap : kcap;
-  if (frame_stride == (size_t)stride * h_px && stride == h->img_pitch) {
+  // Device-side row stride of the uploaded frames.  Tightly packed host frames (stride == w, e.g. the 1241-pixel
+  // KITTI rows) go up as ONE linear copy and keep their stride: a 2-D copy of odd-length rows runs at a fraction of the
+  // link rate, while the level-0 kernel reads rows of any alignment (byte path) at the device-resident rate.
+  int dstride = h->img_pitch;
+  if (frame_stride == (size_t)stride * h_px && (stride == h->img_pitch || stride == w)) {
+    dstride = stride;
     SWM_CK(h, cudaMemcpyAsync(h->d_img, src, (size_t)stride * h_px * nb, cudaMemcpyHostToDevice, h->stream));
   } else if (frame_stride == (size_t)stride * h_px) {
     SWM_CK(h, cudaMemcpy2DAsync(h->d_img, h->img_pitch, src, stride, w, (size_t)h_px * nb, cudaMemcpyHostToDevice,
@@ -1229,16 +1235,18 @@ static int enqueue_host_chunk(swm_orb* h, const uint8_t* src, int nb, int w, int
   // arguments and is never captured.
   static const bool no_graph = getenv("SWM_NO_GRAPH") != nullptr;
   const bool graphable = nb == 1 && !no_graph && !h->debug_score;
-  if (graphable && h->graph) {
-    h->last_img = h->d_img; h->last_stride = h->img_pitch; h->last_frame_stride = (long long)h->img_pitch * h_px;
+  if (graphable && h->graph && h->graph_stride == dstride) {
+    h->last_img = h->d_img; h->last_stride = dstride; h->last_frame_stride = (long long)dstride * h_px;
     h->last_kps = h->d_kps; h->last_desc = h->d_desc; h->last_n = h->d_n; h->last_cap = kcap;
     h->last_batch = 1;
     h->last_stream = h->stream;
     SWM_CK(h, cudaGraphLaunch(h->graph, h->stream));
   } else if (graphable && h->graph_runs >= 1) {
     cudaGraph_t g = nullptr;
+    if (h->graph) { cudaGraphExecDestroy(h->graph); h->graph = nullptr; }  // captured for another row stride
+    h->graph_stride = dstride;
     SWM_CK(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-    rc = swm_orb_extract_batch_device(h, h->d_img, 1, w, h_px, h->img_pitch, (size_t)h->img_pitch * h_px, h->d_kps,
+    rc = swm_orb_extract_batch_device(h, h->d_img, 1, w, h_px, dstride, (size_t)dstride * h_px, h->d_kps,
                                       h->d_desc, kcap, h->d_n, h->stream);
     const cudaError_t ce = cudaStreamEndCapture(h->stream, &g);
     if (rc != SWM_OK) { if (g) cudaGraphDestroy(g); return rc; }
@@ -1248,7 +1256,7 @@ static int enqueue_host_chunk(swm_orb* h, const uint8_t* src, int nb, int w, int
     SWM_CK(h, ie);
     SWM_CK(h, cudaGraphLaunch(h->graph, h->stream));
   } else {
-    rc = swm_orb_extract_batch_device(h, h->d_img, nb, w, h_px, h->img_pitch, (size_t)h->img_pitch * h_px, h->d_kps,
+    rc = swm_orb_extract_batch_device(h, h->d_img, nb, w, h_px, dstride, (size_t)dstride * h_px, h->d_kps,
                                       h->d_desc, kcap, h->d_n, h->stream);
     if (rc != SWM_OK) return rc;
   }

@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -1229,6 +1230,8 @@ struct swm_matcher {
   DevBuf bscratch;
   DevBuf bcand[2];
   size_t bcand_cap = 0;
+  cudaEvent_t bev[2] = {nullptr, nullptr};  // around the kernels of the last batch call (swm_matcher_last_device_ms)
+  float last_device_ms = 0.f;
   // upload arena: every host array of a call is packed into one pinned buffer and sent with ONE copy
   uint8_t* h_arena = nullptr;
   uint8_t* d_arena = nullptr;
@@ -1254,6 +1257,10 @@ struct swm_matcher {
     bscratch.release();
     for (auto& b : bcand) b.release();
     bcand_cap = 0;
+    for (auto& e : bev) {
+      if (e) cudaEventDestroy(e);
+      e = nullptr;
+    }
   }
 };
 
@@ -2402,6 +2409,9 @@ struct swm_db {
   unsigned long long* d_partial = nullptr;
   size_t partial_cap = 0;
   int n_sm = 148;
+  // swm_db_query_sharded: this shard's (nq, k) key block and the all-gathered (world, nq, k) blocks, grow-only
+  unsigned long long* d_exchange = nullptr;
+  size_t exchange_cap = 0;
 };
 
 extern "C" {
@@ -2451,10 +2461,38 @@ void swm_db_destroy(swm_db* db) {
   cudaSetDevice(db->device);
   if (db->owns) cudaFree(db->d_desc);
   cudaFree(db->d_partial);
+  cudaFree(db->d_exchange);
   delete db;
 }
 
 int64_t swm_db_size(const swm_db* db) { return db ? db->ndesc : 0; }
+
+// Measured int8 rate of the tensor pipe: `iters` back-to-back tcgen05 kind::i8 MMAs per SM (see umma::i8_peak_kernel).
+int swm_i8_peak(int device, int mode, int iters, double* tops) {
+  if (!tops || iters < 16 || (mode != 0 && mode != 1)) return SWM_E_INVALID;
+  std::string err;
+  int rc = check_device(device, &err);
+  if (rc != SWM_OK) return rc;
+  if (cudaSetDevice(device) != cudaSuccess) return SWM_E_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SWM_E_CUDA;
+  const int ctas = prop.multiProcessorCount;
+  cudaEvent_t e0, e1;
+  if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return SWM_E_CUDA;
+  umma::i8_peak_kernel<<<ctas, 128, umma::kPeakSmem>>>(mode, 64, nullptr);  // warm-up
+  cudaEventRecord(e0);
+  umma::i8_peak_kernel<<<ctas, 128, umma::kPeakSmem>>>(mode, iters, nullptr);
+  cudaEventRecord(e1);
+  const bool ok = cudaEventSynchronize(e1) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+  float ms = 0.f;
+  if (ok) cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (!ok || ms <= 0.f) return SWM_E_CUDA;
+  const double n = mode == 0 ? 64.0 : 256.0;
+  *tops = (double)ctas * iters * 2.0 * 128.0 * n * 32.0 / (ms * 1e-3) / 1e12;
+  return SWM_OK;
+}
 
 int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t* d_topk, int32_t* d_votes,
                         int th_votes, void* stream) {
@@ -2519,6 +2557,56 @@ int swm_db_merge_gathered(swm_db* db, const uint64_t* d_gathered, int world, int
                                                                       (unsigned long long*)d_topk, d_votes, th_votes,
                                                                       db->first_kf, db->desc_per_kf, first_index, n_kf);
   return cudaGetLastError() == cudaSuccess ? SWM_OK : SWM_E_CUDA;
+}
+
+}  // extern "C"
+
+// ---- NCCL, bound at first use: libswm_orb.so does not link libnccl (a host process -- SwarmMap's server, or a
+// PyTorch rank -- has its own copy loaded; binding to that one avoids two NCCL runtimes in one process).
+namespace {
+using nccl_allgather_fn = int (*)(const void*, void*, size_t, int, void*, cudaStream_t);
+constexpr int kNcclUint64 = 5;  // ncclDataType_t::ncclUint64 (nccl.h)
+nccl_allgather_fn bind_nccl_allgather() {
+  static nccl_allgather_fn fn = [] {
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // already in the process?
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    void* sym = h ? dlsym(h, "ncclAllGather") : dlsym(RTLD_DEFAULT, "ncclAllGather");
+    return reinterpret_cast<nccl_allgather_fn>(sym);
+  }();
+  return fn;
+}
+}  // namespace
+
+extern "C" {
+
+// Config 5 end to end on one rank, callable from a C++ server (the role of AgentMediator::CheckOverlapCandidates,
+// code/src/AgentMediator.cc:140-202): brute-force top-k of the queries against this shard, ONE ncclAllGather of the
+// fixed-size (nq, k) key blocks over NVLink, and the merge kernel that also casts this shard's votes from the GLOBAL
+// best matches -- three enqueues on `stream`, no host synchronisation.  nccl_comm is an ncclComm_t whose rank owns
+// this shard; world = its size.  d_topk: (nq, k) merged keys, identical on every rank.
+int swm_db_query_sharded(swm_db* db, void* nccl_comm, int world, const uint8_t* d_q, int nq, int k, uint64_t* d_topk,
+                         int32_t* d_votes, int th_votes, void* stream) {
+  if (!db || !d_q || nq <= 0 || k < 1 || k > 2 || !d_topk || world < 1 || (world > 1 && !nccl_comm)) return SWM_E_INVALID;
+  if (world == 1) return swm_db_query_device(db, d_q, nq, k, d_topk, d_votes, th_votes, stream);
+  if (cudaSetDevice(db->device) != cudaSuccess) return SWM_E_CUDA;
+  const size_t block = (size_t)nq * k;
+  const size_t need = block * ((size_t)world + 1) * sizeof(unsigned long long);
+  if (need > db->exchange_cap) {
+    cudaFree(db->d_exchange);
+    db->d_exchange = nullptr;
+    db->exchange_cap = 0;
+    if (cudaMalloc(&db->d_exchange, need) != cudaSuccess) return SWM_E_CUDA;
+    db->exchange_cap = need;
+  }
+  nccl_allgather_fn allgather = bind_nccl_allgather();
+  if (!allgather) return SWM_E_STATE;  // no NCCL in this process and none on the library path
+  unsigned long long* local = db->d_exchange;
+  unsigned long long* gathered = db->d_exchange + block;
+  int rc = swm_db_query_device(db, d_q, nq, k, (uint64_t*)local, nullptr, th_votes, stream);
+  if (rc != SWM_OK) return rc;
+  if (allgather(local, gathered, block, kNcclUint64, nccl_comm, (cudaStream_t)stream) != 0) return SWM_E_CUDA;
+  return swm_db_merge_gathered(db, (const uint64_t*)gathered, world, nq, k, d_topk, d_votes, th_votes, stream);
 }
 
 }  // extern "C"

@@ -560,12 +560,17 @@ int run_batch(swm_matcher* m, std::vector<HostJob>& jobs) {
   }
   if ((rc = down_begin(m, inout_bytes + 256))) return rc;
   if (zero_bytes) MCK(m, cudaMemsetAsync(zeros, 0, zero_bytes, m->stream));
+  if (!m->bev[0]) {
+    MCK(m, cudaEventCreate(&m->bev[0]));
+    MCK(m, cudaEventCreate(&m->bev[1]));
+  }
 
   for (int attempt = 0; attempt < 2; attempt++) {
     BatchCtl h_ctl{(int32_t)std::min<size_t>(m->bcand_cap, 0x7FFFFFFF), 0, 0, 0};
     MCK(m, cudaMemcpyAsync(ctl, &h_ctl, sizeof(h_ctl), cudaMemcpyHostToDevice, m->stream));
     MCK(m, cudaMemsetAsync(job_total, 0, ((size_t)P + 1) * 4, m->stream));
     const dim3 rows_grid((unsigned)((max_rows + 7) / 8), (unsigned)P);
+    MCK(m, cudaEventRecord(m->bev[0], m->stream));
     bq_prepare_kernel<<<P, 1024, 0, m->stream>>>(d_jobs, job_total, job_rows, ctl);
     bq_count_kernel<<<rows_grid, 256, 0, m->stream>>>(d_jobs);
     bq_scan_kernel<<<P, 1024, 0, m->stream>>>(d_jobs, job_total);
@@ -575,10 +580,12 @@ int run_batch(swm_matcher* m, std::vector<HostJob>& jobs) {
     bq_resolve_kernel<<<P, kResolveWarps * 32, max_smem, m->stream>>>(d_jobs, job_base, job_rows, ctl,
                                                                       m->bcand[0].as<int32_t>(), m->bcand[1].as<uint32_t>());
     MCK(m, cudaGetLastError());
+    MCK(m, cudaEventRecord(m->bev[1], m->stream));
     MCK(m, cudaMemcpyAsync(m->h_down, m->d_arena, inout_bytes, cudaMemcpyDeviceToHost, m->stream));
     MCK(m, cudaMemcpyAsync(m->h_down + up256b(inout_bytes), ctl, sizeof(BatchCtl), cudaMemcpyDeviceToHost, m->stream));
     MCK(m, cudaStreamSynchronize(m->stream));
     memcpy(&h_ctl, m->h_down + up256b(inout_bytes), sizeof(h_ctl));
+    MCK(m, cudaEventElapsedTime(&m->last_device_ms, m->bev[0], m->bev[1]));
     if (h_ctl.bad_index) { m->err = "feature index out of range"; return SWM_E_INVALID; }
     if (!h_ctl.overflow) break;
     if (attempt == 1) { m->err = "internal: candidate buffer overflow after regrowth"; return SWM_E_CAPACITY; }
@@ -597,6 +604,8 @@ int run_batch(swm_matcher* m, std::vector<HostJob>& jobs) {
 }  // namespace
 
 extern "C" {
+
+float swm_matcher_last_device_ms(const swm_matcher* m) { return m ? m->last_device_ms : 0.f; }
 
 int swm_match_window_batch(swm_matcher* m, swm_window_job* jobs, int njobs) {
   if (!m) return SWM_E_INVALID;

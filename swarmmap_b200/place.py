@@ -144,6 +144,22 @@ class PlaceShard:
             raise _lib.SwmError(f"swm_db_merge_gathered: {_lib.ERRORS.get(rc, rc)}")
         return merged, votes
 
+    def query_sharded(self, q, comm, world, k=2, th_votes=50):
+        """The same query through the C ABI alone (swm_db_query_sharded): local scan, ONE ncclAllGather issued by the
+        library on the current stream, merge + votes -- what a C++ server calls.  comm: raw ncclComm_t (c_void_p),
+        e.g. from nccl_comm_from_torch()."""
+        dq = q.to(self.device).contiguous() if isinstance(q, torch.Tensor) else \
+            torch.from_numpy(np.ascontiguousarray(q, np.uint8)).to(self.device)
+        nq = int(dq.shape[0])
+        merged = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        votes = torch.zeros(self.n_kf, dtype=torch.int32, device=self.device)
+        st = torch.cuda.current_stream(self.device)
+        rc = self._lib.swm_db_query_sharded(self._h, comm, int(world), dq.data_ptr(), nq, k, merged.data_ptr(),
+                                            votes.data_ptr(), int(th_votes), C.c_void_p(st.cuda_stream))
+        if rc != 0:
+            raise _lib.SwmError(f"swm_db_query_sharded: {_lib.ERRORS.get(rc, rc)}")
+        return merged, votes
+
     def votes_from_global(self, merged, th_votes):
         """Per-keyframe votes of THIS shard from the merged result: a query votes for the keyframe owning
         its global best match when that distance is <= th_votes (TH_LOW); summed over ranks this equals
@@ -153,3 +169,32 @@ class PlaceShard:
         mask = (d >= 0) & (d <= th_votes) & (i >= first) & (i < first + self.n_desc)
         kf = torch.div(i[mask] - first, self.desc_per_kf, rounding_mode="floor")
         return torch.bincount(kf, minlength=self.n_kf).to(torch.int32)
+
+
+class _NcclUniqueId(C.Structure):
+    _fields_ = [("internal", C.c_char * 128)]
+
+
+def nccl_comm_from_torch(device, group=None):
+    """A raw ncclComm_t over the ranks of the (initialised) torch.distributed group, created with the NCCL library
+    the process already has loaded: rank 0 makes the unique id, torch broadcasts its 128 bytes, every rank calls
+    ncclCommInitRank.  Returns (comm as c_void_p, nccl ctypes library); destroy with lib.ncclCommDestroy(comm)."""
+    nccl = C.CDLL("libnccl.so.2")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    uid = _NcclUniqueId()
+    if rank == 0:
+        nccl.ncclGetUniqueId.argtypes = [C.POINTER(_NcclUniqueId)]
+        if nccl.ncclGetUniqueId(C.byref(uid)) != 0:
+            raise RuntimeError("ncclGetUniqueId failed")
+    raw = C.string_at(C.byref(uid), 128) if rank == 0 else bytes(128)
+    t = torch.tensor(list(raw), dtype=torch.uint8, device=torch.device("cuda", device))
+    dist.broadcast(t, src=0, group=group)
+    C.memmove(C.byref(uid), bytes(t.cpu().tolist()), 128)
+    comm = C.c_void_p()
+    nccl.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, _NcclUniqueId, C.c_int]
+    torch.cuda.set_device(device)
+    rc = nccl.ncclCommInitRank(C.byref(comm), world, uid, rank)
+    if rc != 0:
+        raise RuntimeError(f"ncclCommInitRank failed ({rc})")
+    nccl.ncclCommDestroy.argtypes = [C.c_void_p]
+    return comm, nccl

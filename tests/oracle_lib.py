@@ -43,10 +43,13 @@ _lib = None
 
 
 def build(force=False):
-    so = os.path.join(ORACLE_DIR, "liborb_oracle.so")
+    """SWM_ORACLE_VARIANT=O1 selects the -O1 build (the reference's release level, CMakeLists.txt:24-25) for the CPU
+    baseline runs of tools/cpu_baseline.py; the default -O2 library is the one every test uses."""
+    name = "liborb_oracle_O1.so" if os.environ.get("SWM_ORACLE_VARIANT") == "O1" else "liborb_oracle.so"
+    so = os.path.join(ORACLE_DIR, name)
     srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".cpp", ".h", ".inc"))]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.run(["make", "-C", ORACLE_DIR, "liborb_oracle.so"], check=True, capture_output=True)
+        subprocess.run(["make", "-C", ORACLE_DIR, name], check=True, capture_output=True)
     return so
 
 

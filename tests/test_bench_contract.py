@@ -1,12 +1,13 @@
-"""The bench.py JSON contract, checked on the committed end-of-round lines (profiles/r1r_bench.json from
-`python bench.py`, profiles/r1n_bench_reference.json from `python bench.py --impl reference`), and the parts of
-bench.py that run without a GPU (argument parsing, the reference arm on a tiny sample)."""
+"""The bench.py JSON contract, checked on the committed lines (profiles/r2_bench.json from `python bench.py` on one
+B200, profiles/r1n_bench_reference.json from `python bench.py --impl reference`), and the parts of bench.py that run
+without a GPU (argument parsing, the reference arm on a tiny sample)."""
 import json
 import os
 import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEV_LINE = "r2e_bench.json"
 
 
 def _line(name):
@@ -15,7 +16,7 @@ def _line(name):
 
 
 def test_device_arm_line_has_every_contract_key():
-    d = _line("r1r_bench.json")
+    d = _line(DEV_LINE)
     base = json.load(open(os.path.join(ROOT, "BASELINE.json")))
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
@@ -43,12 +44,30 @@ def test_device_arm_line_has_every_contract_key():
     assert k["sm_mhz"] > 0 and k["sm_max_mhz"] >= k["sm_mhz"] and not set(k["reasons"]) & {
         "hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     h = d["hamming"]
-    assert h["roofline"]["bound"] == "tensor" and 0 < h["roofline"]["frac"] < 1
+    assert h["roofline"]["bound"] == "tensor" and 0 < h["roofline"]["frac"] < 1.2
+    assert d["config"]["timed_region_s"] > 0.5 and e["timed_region_s"] > 0.5
+    assert 0 < e["h2d_ceiling"]["e2e_frac_of_ceiling"] <= 1.05
+    # one record per remaining BASELINE.json config, each with its own workload, device value, e2e and a parity check
+    w = d["workloads"]
+    k2 = w["config2_kitti"]
+    assert k2["config"]["frame"] == [1241, 376] and k2["extract"]["value"] > 0 and k2["extract"]["e2e"]["value"] > 0
+    assert k2["init_matching"]["value"] > 0 and k2["init_matching"]["parity"]["identical"] is True
+    t = w["config34_tracking"]
+    assert t["parity"]["identical"] is True
+    for variant in ("projection_only", "with_bow"):
+        v = t["variants"][variant]
+        assert v["value"] >= 5000 and v["e2e"]["value"] >= 5000  # north_star's floor per GPU, with bit-exact matches
+    p5 = w["config5_place"]
+    assert "100 000 keyframes x 256" in p5["config"]["workload"] and p5["parity"]["votes_on_planted_keyframes"] is True
+    assert p5["parity"]["oracle_sample"]["identical"] is True and p5["value"] > 1e12
+    proto = d["cpu_baseline_protocol"]
+    for variant in ("O2", "O1"):
+        assert [x["agents"] for x in proto[variant]["extract"]][:2] == [1, 2] and proto[variant]["matchers"]
 
 
 def test_reference_arm_line():
     d = _line("r1n_bench_reference.json")
-    dev = _line("r1r_bench.json")
+    dev = _line(DEV_LINE)
     assert d["impl"] == "reference" and d["metric"] == dev["metric"] and d["unit"] == dev["unit"]
     assert d["config"]["workload"] == dev["config"]["workload"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
