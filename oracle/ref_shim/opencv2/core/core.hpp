@@ -30,11 +30,13 @@ namespace cv {
 class Mat {
  public:
   int rows = 0, cols = 0;
+  size_t step = 0;  // bytes per row (always dense here)
   unsigned char* data = nullptr;
   Mat() {}
   Mat(int r, int c, int type) { create(r, c, type); }
   void create(int r, int c, int type) {
     rows = r; cols = c; type_ = type;
+    step = (size_t)c * (type == CV_32F ? 4 : 1);
     const size_t bytes = (size_t)r * c * elemSize();
     buf_ = std::shared_ptr<unsigned char>(new unsigned char[bytes ? bytes : 1], std::default_delete<unsigned char[]>());
     data = buf_.get();
@@ -53,6 +55,8 @@ class Mat {
   size_t elemSize() const { return type_ == CV_32F ? 4 : 1; }
   int type() const { return type_; }
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+  unsigned char* ptr(int r = 0) { return data + (size_t)r * cols * elemSize(); }
+  const unsigned char* ptr(int r = 0) const { return data + (size_t)r * cols * elemSize(); }
   template <typename T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * cols * elemSize()); }
   template <typename T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * cols * elemSize()); }
   Mat rowRange(int, int) const { return *this; }   // compile-only (never executed by the wrapper)

@@ -3,7 +3,7 @@
 // Same contract as db_top2_mma_kernel (match.cu): for every query descriptor the two nearest
 // database descriptors of a slice, as 64-bit keys (dist << 48 | global index), ties -> lower index.
 // The reference computes these distances one pair at a time with ORBmatcher::DescriptorDistance
-// (/root/reference/code/src/ORBmatcher.cc:1845-1862); the brute-force scan is the all-pairs form of it.
+// (/root/reference/code/src/ORBmatcher.cc:1511-1525); the brute-force scan is the all-pairs form of it.
 //
 // Formulation.  For 256-bit descriptors q, x:  hamming(q, x) = popc(q) + popc(x) - 2 q.x.  With
 //   A[m][k] = +64 if bit k of query m is 0, -64 if it is 1          (s8, k < 256)

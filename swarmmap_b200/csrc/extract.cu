@@ -32,6 +32,33 @@ namespace swm {
 __device__ float4 g_pattern[8 * 32];
 __constant__ int c_umax[16];
 
+// ---- mbarrier / TMA bulk-copy helpers (PTX ISA: mbarrier, cp.async.bulk)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t done;
+  int spins = 0;
+  do {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    if (!done && ++spins > (1 << 22)) __trap();  // a lost transaction must abort, not hang the GPU
+  } while (!done);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Pyramid kernel: one CTA produces a 64x32 tile of level l -- the un-blurred plane (plus the
 // mirrored border pixels that reflect into the tile) and the Gaussian-blurred plane.  Everything
@@ -46,6 +73,13 @@ constexpr int PS_WORDS = 18;            // staged words per row: x0-4 .. x0+67
 constexpr int PS_COLS = PS_WORDS * 4;   // 72
 constexpr int PS_ROWS = TH + 6;         // y0-3 .. y0+34
 constexpr int SRC_ROWS = 62, SRC_WORDS = 30;  // level l-1 window of one tile, scale factor <= 1.5 (checked on the host)
+// The window is staged by TMA: one cp.async.bulk per source row, from a 16-byte aligned source x (the ROI origin of a
+// plane is 32-byte aligned and the pitch a multiple of 128), so a row holds up to 12 bytes of lead-in + 120 + tail.
+constexpr int SRC_PITCH = 144;
+#ifndef SWM_PYR_TMA
+#define SWM_PYR_TMA 1  // 0: stage the window with 16-byte __ldg loads instead (A/B switch, 2 % faster, profiles/README.md r2g)
+#endif
+
 
 struct PyrArgs {
   LevelGeom dst, src;
@@ -71,7 +105,9 @@ __device__ __forceinline__ void store4(uint8_t* row, int gx, int w, uint32_t wor
 template <bool kFirst>
 __global__ void __launch_bounds__(256) pyr_kernel(const PyrArgs a) {
   __shared__ __align__(16) uint32_t s_px[PS_ROWS * PS_WORDS];
-  __shared__ __align__(16) uint32_t s_src[kFirst ? 1 : SRC_ROWS * SRC_WORDS];
+  __shared__ __align__(128) uint8_t s_src[kFirst ? 16 : SRC_ROWS * SRC_PITCH];
+  __shared__ __align__(8) uint64_t s_bar;
+  (void)s_bar;
   __shared__ __align__(16) uint16_t s_h[kFirst ? 4 : SRC_ROWS * PS_COLS];
   __shared__ __align__(16) uint2 s_v[TH * PS_WORDS];
   __shared__ ResizeTap s_xt[kFirst ? 1 : PS_COLS];
@@ -109,52 +145,72 @@ __global__ void __launch_bounds__(256) pyr_kernel(const PyrArgs a) {
     // taps of the staged columns/rows (reflected destination coordinates), window of level l-1
     const int dlo = max(0, x0 - 4), dhi = min(w - 1, x0 + PS_COLS - 5);
     const int rlo = max(0, y0 - 3), rhi = min(h - 1, y0 + PS_ROWS - 4);
-    const int sx_base = xt[dlo].ofs & ~3;
+    const int sx_base = xt[dlo].ofs & ~15;  // 16-byte aligned: the row copies below are TMA bulk copies
     const int sy_base = yt[rlo].ofs;
-    const int nwords = ((xt[dhi].ofs + 1 - sx_base) >> 2) + 1;
+    const int nbytes = (xt[dhi].ofs + 2 - sx_base + 15) & ~15;
     const int nrows = min(yt[rhi].ofs + 1, sh - 1) - sy_base + 1;
-    if (tid < PS_COLS) {
-      ResizeTap t = xt[reflect101(min(x0 - 4 + tid, w + 2), w)];
+#if SWM_PYR_TMA
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    if (tid < 32) {
+      // warp 0: one cp.async.bulk per source row, all completing on one mbarrier (SASS: UBLKCP + SYNCS)
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&s_bar, (uint32_t)(nrows * nbytes));
+      }
+      __syncwarp();
+      for (int r = tid; r < nrows; r += 32)
+        bulk_g2s(s_src + r * SRC_PITCH, src + (long long)(sy_base + r) * spitch + sx_base, (uint32_t)nbytes, &s_bar);
+    } else if (tid >= 64 && tid < 64 + PS_COLS) {
+#else
+    {  // 16-byte loads of the aligned window: 9 lanes per row, 28 rows per sweep
+      const int q = tid % 9, r0 = tid / 9;
+      if (r0 < 28 && 16 * q < nbytes)
+        for (int r = r0; r < nrows; r += 28)
+          *reinterpret_cast<uint4*>(s_src + r * SRC_PITCH + 16 * q) =
+              __ldg(reinterpret_cast<const uint4*>(src + (long long)(sy_base + r) * spitch + sx_base + 16 * q));
+    }
+    if (tid >= 64 && tid < 64 + PS_COLS) {
+#endif
+      ResizeTap t = xt[reflect101(min(x0 - 4 + (tid - 64), w + 2), w)];
       t.ofs = (int16_t)(t.ofs - sx_base);
-      s_xt[tid] = t;
-    } else if (tid >= 128 && tid < 128 + PS_ROWS) {
-      ResizeTap t = yt[reflect101(min(y0 - 3 + (tid - 128), h + 2), h)];
+      s_xt[tid - 64] = t;
+    } else if (tid >= 160 && tid < 160 + PS_ROWS) {
+      ResizeTap t = yt[reflect101(min(y0 - 3 + (tid - 160), h + 2), h)];
       const int o0 = t.ofs - sy_base;
       t.ofs = (int16_t)o0;
       t.pad = (int16_t)min(o0 + 1, sh - 1 - sy_base);  // second source row, clamped like cv::resize
-      s_yt[tid - 128] = t;
+      s_yt[tid - 160] = t;
     }
-    {
-      const int lane = tid & 31;
-      if (lane < nwords) {
-        const uint8_t* col = src + sx_base + 4 * lane;
-        for (int r = tid >> 5; r < nrows; r += 8)
-          s_src[r * SRC_WORDS + lane] = __ldg(reinterpret_cast<const uint32_t*>(col + (long long)(sy_base + r) * spitch));
-      }
-    }
+#if SWM_PYR_TMA
+    if (tid < 32) mbar_wait(&s_bar, 0);  // one warp polls the mbarrier, the rest park on the CTA barrier
+#endif
     __syncthreads();
-    // row pass: one value per (source row, destination column), kept as (sum >> 4) in 16 bits
+    // row pass: one value per (source row, destination column), kept as (sum >> 4) in 16 bits.  (A four-columns-per-
+    // thread form -- three aligned word loads, a funnel shift per column, IDP.2A on 16-bit taps -- executes as many
+    // instructions once the per-column selects are counted and measured 12 % slower; profiles/README.md r2g.)
     if (tid < 3 * PS_COLS) {
       const int c = tid % PS_COLS, g = tid / PS_COLS;
       const ResizeTap t = s_xt[c];
-      const uint8_t* sb = reinterpret_cast<const uint8_t*>(s_src) + t.ofs;
+      const uint8_t* sb = s_src + t.ofs;
       for (int r = g; r < nrows; r += 3) {
-        const uint8_t* p = sb + r * (SRC_WORDS * 4);
+        const uint8_t* p = sb + r * SRC_PITCH;
         s_h[r * PS_COLS + c] = (uint16_t)((p[0] * t.a0 + p[1] * t.a1) >> 4);
       }
     }
     __syncthreads();
-    // column pass, 4 pixels per item
+    // column pass, 4 pixels per item: ((b0 * h0) >> 16) + ((b1 * h1) >> 16) + 2) >> 2 with the two products taken as
+    // the high words of (b << 16) * h (IMAD.HI with the +2 and the first product riding in the accumulator)
     for (int i = tid; i < PS_ROWS * PS_WORDS; i += 256) {
       const int r = i / PS_WORDS, j = i - r * PS_WORDS;
       const ResizeTap t = s_yt[r];
       const uint2 h0 = *reinterpret_cast<const uint2*>(s_h + t.ofs * PS_COLS + 4 * j);
       const uint2 h1 = *reinterpret_cast<const uint2*>(s_h + t.pad * PS_COLS + 4 * j);
-      const int b0 = t.a0, b1 = t.a1;
-      const uint32_t p0 = (((b0 * (int)(h0.x & 0xFFFF)) >> 16) + ((b1 * (int)(h1.x & 0xFFFF)) >> 16) + 2) >> 2;
-      const uint32_t p1 = (((b0 * (int)(h0.x >> 16)) >> 16) + ((b1 * (int)(h1.x >> 16)) >> 16) + 2) >> 2;
-      const uint32_t p2 = (((b0 * (int)(h0.y & 0xFFFF)) >> 16) + ((b1 * (int)(h1.y & 0xFFFF)) >> 16) + 2) >> 2;
-      const uint32_t p3 = (((b0 * (int)(h0.y >> 16)) >> 16) + ((b1 * (int)(h1.y >> 16)) >> 16) + 2) >> 2;
+      const uint32_t B0 = (uint32_t)t.a0 << 16, B1 = (uint32_t)t.a1 << 16;
+      const uint32_t p0 = (__umulhi(B1, h1.x & 0xFFFFu) + (__umulhi(B0, h0.x & 0xFFFFu) + 2u)) >> 2;
+      const uint32_t p1 = (__umulhi(B1, h1.x >> 16) + (__umulhi(B0, h0.x >> 16) + 2u)) >> 2;
+      const uint32_t p2 = (__umulhi(B1, h1.y & 0xFFFFu) + (__umulhi(B0, h0.y & 0xFFFFu) + 2u)) >> 2;
+      const uint32_t p3 = (__umulhi(B1, h1.y >> 16) + (__umulhi(B0, h0.y >> 16) + 2u)) >> 2;
       s_px[i] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
     }
   }
@@ -285,33 +341,6 @@ constexpr int FS_ITEMS = 34 * FS_SW;                // quick-reject word items p
 constexpr int FS_IT = (FS_ITEMS + 255) / 256;
 constexpr int FS_MAXCAND = (FB_W + 2) * 34;
 static_assert(kFx + FB_W + 4 <= FS_COLS && 4 + FS_SW <= FS_WORDS - 1, "staged tile too narrow");
-
-// ---- mbarrier / TMA bulk-copy helpers (PTX ISA: mbarrier, cp.async.bulk)
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
-  uint32_t done;
-  int spins = 0;
-  do {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(phase)
-        : "memory");
-    if (!done && ++spins > (1 << 22)) __trap();  // a lost transaction must abort, not hang the GPU
-  } while (!done);
-}
 
 __device__ __forceinline__ uint32_t oob_mask(uint32_t a, uint32_t v, uint32_t c7) {
   // bit 7 of each byte set iff |a - v| > th, with c7 = (127 - th) * 0x01010101

@@ -8,12 +8,14 @@
 // (checkCudaErrors -> exit, Fast_gpu.cu:346-352) -- here a std::runtime_error carrying
 // swm_last_error(); an empty image returns silently (ORBextractor.cc:750-751).
 #pragma once
+#include <cstring>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #ifdef SWM_HAVE_OPENCV
 #include <opencv2/core.hpp>
+#include <opencv2/core/cuda.hpp>
 #else
 #include "cv_shim.h"
 #endif
@@ -21,13 +23,21 @@
 
 namespace ORB_SLAM2 {
 
-// What the public mvImagePyramid / mvImagePyramidBorder vectors expose (device memory, as in the
-// reference where they are cv::cuda::GpuMat over cudaMallocManaged buffers).
+// What the public mvImagePyramid / mvImagePyramidBorder vectors hold (device memory).  With OpenCV they are
+// cv::cuda::GpuMat HEADERS over the extractor's planes (no allocation, no copy), the reference's own member type
+// (include/ORBextractor.h:90-92), so Frame::ComputeStereoMatches' uses compile (Frame.cc:521,611-630; note that it
+// dereferences them on the host, which the reference can only do because its allocator hands out managed memory).
+// Without OpenCV (tests) a plain view with the same field names stands in.
 struct PyramidLevelView {
   const unsigned char* data = nullptr;  // device pointer to ROI pixel (0,0)
   int cols = 0, rows = 0;
   size_t step = 0;
 };
+#ifdef SWM_HAVE_OPENCV
+typedef cv::cuda::GpuMat PyramidLevel;
+#else
+typedef PyramidLevelView PyramidLevel;
+#endif
 
 class ORBextractor {
  public:
@@ -100,8 +110,8 @@ class ORBextractor {
   // ROI after the call (blurred, like the reference's in-place filter); mvImagePyramidBorder[l] the
   // un-blurred plane whose 19-px reflect-101 border lies at negative offsets of `data`.
   bool mvImagePyramidAllocatedFlag;
-  std::vector<PyramidLevelView> mvImagePyramid;
-  std::vector<PyramidLevelView> mvImagePyramidBorder;
+  std::vector<PyramidLevel> mvImagePyramid;
+  std::vector<PyramidLevel> mvImagePyramidBorder;
 
   swm_orb* handle() { return h_; }
 
@@ -114,8 +124,16 @@ class ORBextractor {
         const unsigned char* dev = nullptr;
         int w = 0, h = 0, pitch = 0;
         if (swm_orb_level_ptr(h_, 0, l, which, &dev, &w, &h, &pitch) != SWM_OK) return;
+#ifdef SWM_HAVE_OPENCV
+        // Border: the whole (h + 38) x (w + 38) un-blurred buffer, as ComputePyramid allocates it (ORBextractor.cc:827);
+        // Pyramid: the level ROI of the blurred plane (the reference blurs its ROI view in place, :719)
+        unsigned char* p = const_cast<unsigned char*>(dev);
+        if (which) mvImagePyramid[l] = cv::cuda::GpuMat(h, w, CV_8UC1, p, (size_t)pitch);
+        else mvImagePyramidBorder[l] = cv::cuda::GpuMat(h + 38, w + 38, CV_8UC1, p - 19 * (size_t)pitch - 19, (size_t)pitch);
+#else
         PyramidLevelView& v = which ? mvImagePyramid[l] : mvImagePyramidBorder[l];
         v.data = dev; v.cols = w; v.rows = h; v.step = (size_t)pitch;
+#endif
       }
     }
     mvImagePyramidAllocatedFlag = true;

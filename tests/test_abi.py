@@ -122,3 +122,27 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".inc")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle_lib" not in txt and "orb_oracle" not in txt and "liborb_oracle" not in txt, f
+
+
+def test_opencv_branch_compiles():
+    """The SWM_HAVE_OPENCV branch of the drop-in extractor header (cv::InputArray / OutputArray, mvImagePyramid and
+    mvImagePyramidBorder as cv::cuda::GpuMat headers over the device planes) compiles against headers that declare the
+    OpenCV signatures it uses (the images have no OpenCV C++ headers; oracle/ref_shim stands in)."""
+    import subprocess
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-DSWM_HAVE_OPENCV", "-I", os.path.join(ROOT, "oracle", "ref_shim"),
+                        os.path.join(ROOT, "tests", "opencv_build_check.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_batch_and_sharded_entry_points_reject_bad_arguments(swm):
+    """Argument validation of the round-2 entry points happens before any device work."""
+    lib = swm.load()
+    assert lib.swm_match_window_batch(None, None, 0) == -1
+    assert lib.swm_match_init_batch(None, None, 0) == -1
+    assert lib.swm_match_bow_batch(None, None, 0) == -1
+    assert lib.swm_frames_from_extractor(None, 0, None, None, None, None) == -1
+    assert lib.swm_db_query_sharded(None, None, 2, None, 0, 2, None, None, 50, None) == -1
+    t = C.c_double(0)
+    assert lib.swm_i8_peak(0, 7, 1000, C.byref(t)) == -1          # unknown mode
+    assert lib.swm_i8_peak(0, 0, 1000, C.byref(t)) in (-3, 0)     # no device here / measured on a GPU box
+    assert lib.swm_matcher_last_device_ms(None) == 0.0
