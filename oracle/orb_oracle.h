@@ -8,20 +8,21 @@
  * cpu_baseline / --impl reference legs can CHECK the CUDA product against it.
  * Nothing under swarmmap_b200/ may include, link or call it.
  *
- * PARITY STATUS: the reference ships no tests / golden vectors for this path
- * and cannot be compiled here (needs OpenCV-CUDA, Boost, ...),
- * so parity is "unpinned by the reference's own tests".  The oracle is pinned
- * instead against (a) cv2 4.13 for the three OpenCV primitives the reference
- * delegates to (resize INTER_LINEAR 8U, copyMakeBorder REFLECT_101,
- * GaussianBlur 7x7 sigma 2 8U) and the FAST-9/16 score, (b) the closed-form
- * tables derivable from the reference source (quotas, umax, level sizes),
- * (c) committed golden fixtures under tests/golden/ (incl. cv2.undistortPoints outputs),
- * (d) second, independent Python / numpy readings of the reference sources for the matchers, the
- * orientation / descriptor stages and the "next" rows (tests/test_oracle_*independent*.py,
- * tests/test_oracle_bow.py), and (e) the REFERENCE'S OWN CODE where it compiles on its own
- * (make ref -> oracle/_ref/): ORBextractor.cc's constructor tables and DistributeOctTree
- * (tests/test_ref_orbextractor.py: identical selection and order) and the vendored DBoW2
- * (tests/test_ref_dbow2.py: bit-identical BowVector / FeatureVector outputs).
+ * PARITY STATUS: the reference ships no tests / golden vectors for this path and cannot be built as a whole here
+ * (OpenCV-CUDA, Boost, ...) -- but every source file ON the path compiles on its own against
+ * stand-in headers, and every function below is checked against output of the REFERENCE'S OWN CODE compiled
+ * unmodified (`make ref` -> oracle/_ref/):
+ *   ORBextractor.cc (constructor tables, DistributeOctTree)      tests/test_ref_orbextractor.py
+ *   Thirdparty/DBoW2 (transform, FORB::distance)                 tests/test_ref_dbow2.py
+ *   ORBmatcher.cc with its own ORBmatcher.h, the grid / scale bodies of Frame.cc, KeyFrame.cc, MapPoint.cc:
+ *     every Search*, Fuse, SearchBySim3, SearchForTriangulation  tests/test_ref_orbmatcher.py
+ *   cuda/Fast_gpu.cu, cuda/Orb_gpu.cu (nvcc, sm_100a, -use_fast_math): corner test + score, tile retry + NMS
+ *     (single-tile launches of the real kernel and a lock-step run of its device functions), IC_Angle, rBRIEF
+ *                                                                tests/test_gpu_ref_cuda.py (needs a GPU)
+ * What the reference delegates to an un-vendored OpenCV is pinned to cv2 4.13 instead: resize INTER_LINEAR 8U,
+ * copyMakeBorder REFLECT_101, GaussianBlur 7x7 sigma 2 8U, the FAST-9/16 score, undistortPoints and the cv::gemm /
+ * cv::norm accumulation rules of the projections (tests/test_oracle_cv2.py, test_cv_shim_numerics_match_cv2).
+ * Kept from round 1: closed-form tables, golden fixtures under tests/golden/, second independent numpy readings.
  */
 #ifndef ORB_ORACLE_H
 #define ORB_ORACLE_H

@@ -16,7 +16,6 @@
 // with a larger buffer (no host synchronisation in the middle of a call in the steady state).
 // Results are identical to the single-job entry points (same device bodies) and to the oracle.
 #pragma once
-#include <thread>
 
 namespace swm {
 
@@ -306,11 +305,10 @@ struct HostJob {
 };
 
 struct Packer {  // bump allocator over the matcher's upload arena: host copy in, device address out
+  // (Spreading the copies over helper threads was measured: spawning them costs more than the ~1 ms of memcpy a
+  // 128-job batch needs -- 2.3 ms vs 1.4 ms per call -- so packing stays on the calling thread.)
   swm_matcher* m;
   bool overflow = false;
-  struct Op { uint8_t* dst; const void* src; size_t bytes; };
-  std::vector<Op> ops;  // large copies are deferred and spread over a few host threads (flush)
-  size_t deferred = 0;
   size_t reserve(size_t bytes) {
     const size_t off = (m->arena_used + 255) & ~(size_t)255;
     if (off + bytes > m->arena_cap) { overflow = true; return 0; }
@@ -321,32 +319,8 @@ struct Packer {  // bump allocator over the matcher's upload arena: host copy in
   T* put(const void* src, size_t bytes) {
     const size_t off = reserve(bytes);
     if (overflow) return nullptr;
-    if (bytes && src) {
-      if (bytes >= 2048) { ops.push_back({m->h_arena + off, src, bytes}); deferred += bytes; }
-      else memcpy(m->h_arena + off, src, bytes);
-    }
+    if (bytes && src) memcpy(m->h_arena + off, src, bytes);
     return reinterpret_cast<T*>(m->d_arena + off);
-  }
-  // Packing a few hundred jobs is several MB of memcpy into the pinned arena: one host thread moves ~10 GB/s, the
-  // upload that follows 50 GB/s, so the copies are split over up to 8 threads when there is enough to split.
-  void flush() {
-    const int nt = deferred < ((size_t)1 << 20) ? 1 : (int)std::min<size_t>(8, std::max<unsigned>(1, std::thread::hardware_concurrency() / 2));
-    if (nt <= 1) {
-      for (const Op& o : ops) memcpy(o.dst, o.src, o.bytes);
-    } else {
-      std::vector<std::thread> th;
-      const size_t per = (deferred + nt - 1) / nt;
-      size_t i = 0;
-      for (int t = 0; t < nt && i < ops.size(); t++) {
-        size_t acc = 0, j = i;
-        while (j < ops.size() && acc < per) acc += ops[j++].bytes;
-        th.emplace_back([this, i, j] { for (size_t k = i; k < j; k++) memcpy(ops[k].dst, ops[k].src, ops[k].bytes); });
-        i = j;
-      }
-      for (auto& t : th) t.join();
-    }
-    ops.clear();
-    deferred = 0;
   }
 };
 
@@ -458,7 +432,7 @@ int run_batch(swm_matcher* m, std::vector<HostJob>& jobs) {
   // in/out region first: one contiguous span comes back with a single copy
   for (auto& j : jobs) {
     j.off_out = pk.reserve((size_t)j.n_out * 4);
-    if (j.kind == kJobWindow) { pk.ops.push_back({m->h_arena + j.off_out, j.out, (size_t)j.n_out * 4}); pk.deferred += (size_t)j.n_out * 4; }
+    if (j.kind == kJobWindow) memcpy(m->h_arena + j.off_out, j.out, (size_t)j.n_out * 4);
     else memset(m->h_arena + j.off_out, 0xFF, (size_t)j.n_out * 4);
     j.off_n = pk.reserve(16);
     memset(m->h_arena + j.off_n, 0, 16);
@@ -579,7 +553,6 @@ int run_batch(swm_matcher* m, std::vector<HostJob>& jobs) {
   }
   BatchJob* d_jobs = pk.put<BatchJob>(bj.data(), (size_t)P * sizeof(BatchJob));
   if (pk.overflow || cv.used > m->bscratch.cap) { m->err = "internal: batch arena overflow"; return SWM_E_CAPACITY; }
-  pk.flush();
   for (const swm_frame* f : waits) MCK(m, cudaStreamWaitEvent(m->stream, f->ready, 0));
   if ((rc = arena_flush(m))) return rc;
   static bool attr_set[64] = {};
