@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libswm_orb.so")
+# SWM_LIB_PATH: developer switch for A/B runs of kernel variants built under build/variants/ (tools/ab_variants.sh)
+LIB_PATH = os.environ.get("SWM_LIB_PATH") or os.path.join(HERE, "libswm_orb.so")
 
 SWM_OK = 0
 ERRORS = {-1: "SWM_E_INVALID", -2: "SWM_E_CUDA", -3: "SWM_E_NODEVICE", -4: "SWM_E_CAPACITY", -5: "SWM_E_STATE"}

@@ -13,6 +13,8 @@
 //   IC_Angle_kernel / addBorder_kernel  src/cuda/Fast_gpu.cu:403-471
 //   Gaussian 7x7 sigma 2                src/ORBextractor.cc:835,719,742 (cv::GaussianBlur 8U semantics)
 //   calcOrb_kernel                      src/cuda/Orb_gpu.cu:67-100
+#include <cuda.h>  // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint, no libcuda link)
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -59,6 +61,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
   } while (!done);
 }
 
+}  // namespace swm
+#include "pyr_walk.cuh"
+namespace swm {
+
+#ifndef SWM_PYR_TILED
+#define SWM_PYR_TILED 0  // 1: the round-1 shared-memory tile kernel (A/B baseline of pyr_walk.cuh)
+#endif
 // ------------------------------------------------------------------------------------------------
 // Pyramid kernel: one CTA produces a 64x32 tile of level l -- the un-blurred plane (plus the
 // mirrored border pixels that reflect into the tile) and the Gaussian-blurred plane.  Everything
@@ -81,27 +90,7 @@ constexpr int SRC_PITCH = 144;
 #endif
 
 
-struct PyrArgs {
-  LevelGeom dst, src;
-  const uint8_t* img;
-  int img_stride;
-  long long img_frame_stride;
-  uint8_t* plain;
-  uint8_t* blur;
-  long long slab_bytes;
-  const ResizeTap* xtab;
-  const ResizeTap* ytab;
-};
-
-__device__ __forceinline__ void store4(uint8_t* row, int gx, int w, uint32_t word) {
-  if (gx + 3 < w) {
-    *reinterpret_cast<uint32_t*>(row + gx) = word;
-  } else {
-    for (int k = 0; k < 4; k++)
-      if (gx + k < w) row[gx + k] = (uint8_t)(word >> (8 * k));
-  }
-}
-
+#if SWM_PYR_TILED
 template <bool kFirst>
 __global__ void __launch_bounds__(256) pyr_kernel(const PyrArgs a) {
   __shared__ __align__(16) uint32_t s_px[PS_ROWS * PS_WORDS];
@@ -313,6 +302,8 @@ __global__ void __launch_bounds__(256) pyr_kernel(const PyrArgs a) {
     }
   }
 }
+
+#endif  // SWM_PYR_TILED
 
 // ------------------------------------------------------------------------------------------------
 // FAST kernel (Fast_gpu.cu:284-341, deterministic lock-step form).  One CTA = two horizontally
@@ -836,6 +827,7 @@ struct swm_orb {
   bool allocated = false;
   FrameLayout* d_lay = nullptr;
   ResizeTap *d_xtab = nullptr, *d_ytab = nullptr;
+  CUtensorMap* d_maps = nullptr;  // per level: the un-blurred plane over all frames, for pyr_walk_kernel's TMA tiles
   uint8_t *d_plain = nullptr, *d_blur = nullptr, *d_score = nullptr;
   uint8_t* d_retry = nullptr;
   int4* d_fblk = nullptr;       // per FAST block: (level, bx, by, 0)
@@ -890,15 +882,22 @@ void free_frame_buffers(swm_orb* h) {
   if (h->graph) cudaGraphExecDestroy(h->graph);
   h->graph = nullptr;
   h->graph_runs = 0;
-  cudaFree(h->d_lay); cudaFree(h->d_xtab); cudaFree(h->d_ytab);
+  cudaFree(h->d_lay); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_maps);
   cudaFree(h->d_plain); cudaFree(h->d_blur); cudaFree(h->d_score);
   cudaFree(h->d_retry); cudaFree(h->d_retry_list); cudaFree(h->d_fblk); cudaFree(h->d_pts); cudaFree(h->d_pnode); cudaFree(h->d_pchild); cudaFree(h->d_cand); cudaFree(h->d_sel); cudaFree(h->d_counts);
   cudaFree(h->d_img); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_n);
-  h->d_lay = nullptr; h->d_xtab = h->d_ytab = nullptr;
+  h->d_lay = nullptr; h->d_xtab = h->d_ytab = nullptr; h->d_maps = nullptr;
   h->d_plain = h->d_blur = h->d_score = nullptr;
   h->d_retry = nullptr; h->d_retry_list = nullptr; h->d_fblk = nullptr; h->d_pts = nullptr; h->d_pnode = nullptr; h->d_pchild = nullptr; h->d_cand = h->d_sel = nullptr; h->d_counts = nullptr;
   h->d_img = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->d_n = nullptr;
   h->allocated = false;
+}
+
+// pyr_walk_kernel's strips: the bordered row [-20, w + 20) in lanes of 4 columns, at most kWalkLanes useful lanes per warp
+void walk_strips(int w, int* nstrips, int* strip_lanes) {
+  const int nl = (w + 2 * (-kWalkX0) + 3) / 4;
+  *nstrips = (nl + kWalkLanes - 1) / kWalkLanes;
+  *strip_lanes = (nl + *nstrips - 1) / *nstrips;
 }
 
 // cv::resize INTER_LINEAR coefficient tables (OpenCV imgproc resize.cpp, restated): for each
@@ -958,6 +957,41 @@ int setup_geometry(swm_orb* h, int w, int hh) {
       build_taps(L.lv[l - 1].w, g.w, xt, true);
       build_taps(L.lv[l - 1].h, g.h, yt, false);
     }
+    if (l > 0) {  // pyr_walk_kernel: limits of its per-lane window and of its staged source rows
+      const ResizeTap* xt0 = xt.data() + g.xtab_off;
+      const ResizeTap* yt0 = yt.data() + g.ytab_off;
+      const int sh = L.lv[l - 1].h;
+      int nstrips, sl;
+      walk_strips(g.w, &nstrips, &sl);
+      bool ok = true;
+      for (int st = 0; st < nstrips && ok; st++) {
+        int xb = 1 << 30, xend = -1;
+        for (int lane = 0; lane < 32; lane++) {
+          const int X = kWalkX0 + 4 * (st * sl + lane - 1);
+          int lo = 1 << 30, hi = -1;
+          for (int k = 0; k < 4; k++) {
+            const int o = xt0[reflect101(X + k, g.w)].ofs;
+            lo = std::min(lo, o);
+            hi = std::max(hi, o);
+          }
+          if (hi - lo > 6) ok = false;  // four adjacent columns' taps within 7 source bytes
+          xb = std::min(xb, lo & ~3);
+          xend = std::max(xend, (lo & ~3) + 12);
+        }
+        if (((xend - (xb & ~15) + 15) & ~15) > kWalkRowBytes) ok = false;
+      }
+      for (int v0 = -5; v0 <= g.h + 2 && ok; v0++) {
+        int lo = 1 << 30, hi = -1;
+        for (int i = 0; i < 4; i++) {
+          const int v = v0 + i, ay = v < 0 ? -v : (v >= g.h ? 2 * g.h - 2 - v : v);
+          lo = std::min(lo, (int)yt0[ay].ofs);
+          hi = std::max(hi, std::min(yt0[ay].ofs + 1, sh - 1));
+        }
+        if (hi - lo + 1 > kWalkStageRows) ok = false;
+      }
+      if (!ok) { h->err = "scale factor too large for the pyramid kernel"; return SWM_E_INVALID; }
+    }
+#if SWM_PYR_TILED
     if (l > 0) {  // the source window of every 64x32 tile must fit the kernel's shared-memory staging
       const ResizeTap* xt0 = xt.data() + g.xtab_off;
       const ResizeTap* yt0 = yt.data() + g.ytab_off;
@@ -970,6 +1004,7 @@ int setup_geometry(swm_orb* h, int w, int hh) {
         if (yt0[rhi].ofs + 2 - yt0[rlo].ofs > SRC_ROWS) { h->err = "scale factor too large for the pyramid tile"; return SWM_E_INVALID; }
       }
     }
+#endif
     g.tiles_x = (g.w - 2 * kEdge + 31) / 32;
     g.tiles_y = (g.h - 2 * kEdge + 31) / 32;
     g.tile_off = tile_off;
@@ -1030,6 +1065,31 @@ int setup_geometry(swm_orb* h, int w, int hh) {
   SWM_CK(h, cudaMemcpy(h->d_lay, &L, sizeof(L), cudaMemcpyHostToDevice));
   SWM_CK(h, cudaMemcpy(h->d_xtab, xt.data(), xt.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
   SWM_CK(h, cudaMemcpy(h->d_ytab, yt.data(), yt.size() * sizeof(ResizeTap), cudaMemcpyHostToDevice));
+  {
+    // tensor maps of the un-blurred planes: u8 tensor (row byte, row, frame), box kWalkRowBytes x kWalkStageRows x 1
+    typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    SWM_CK(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) { h->err = "cuTensorMapEncodeTiled is not available in this driver"; return SWM_E_CUDA; }
+    std::vector<CUtensorMap> maps(nl);
+    memset(maps.data(), 0, sizeof(CUtensorMap) * nl);
+    for (int l = 0; l + 1 < nl; l++) {
+      const LevelGeom& g = L.lv[l];
+      const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.rows, (cuuint64_t)B};
+      const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)L.slab_bytes};
+      const cuuint32_t box[3] = {(cuuint32_t)kWalkRowBytes, (cuuint32_t)kWalkStageRows, 1u};
+      const cuuint32_t estr[3] = {1u, 1u, 1u};
+      const CUresult r = ((EncodeTiled)fn)(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->d_plain + g.plane_off, dims, strides, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed for a pyramid plane (code " + std::to_string((int)r) + ")"; return SWM_E_CUDA; }
+    }
+    SWM_CK(h, cudaMalloc(&h->d_maps, sizeof(CUtensorMap) * nl));
+    SWM_CK(h, cudaMemcpy(h->d_maps, maps.data(), sizeof(CUtensorMap) * nl, cudaMemcpyHostToDevice));
+  }
   // planes start zeroed so padding bytes are deterministic
   SWM_CK(h, cudaMemset(h->d_plain, 0, (size_t)L.slab_bytes * B));
   SWM_CK(h, cudaMemset(h->d_blur, 0, (size_t)L.slab_bytes * B));
@@ -1070,9 +1130,28 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
       a.slab_bytes = L.slab_bytes;
       a.xtab = h->d_xtab;
       a.ytab = h->d_ytab;
+      a.src_map = h->d_maps + (l ? l - 1 : 0);
+#if SWM_PYR_TILED
+      a.strip_lanes = a.nstrips = a.rows_per_job = a.nrb = 0;
       dim3 grid((a.dst.w + TW - 1) / TW, (a.dst.h + TH - 1) / TH, batch);
       if (l == 0) pyr_kernel<true><<<grid, 256, 0, st>>>(a);
       else pyr_kernel<false><<<grid, 256, 0, st>>>(a);
+#else
+      // one warp per (strip of <= 120 columns of the bordered row, block of rows).  Row blocks are as long as the
+      // batch allows while the level still fills the GPU about twice over (the 8-row blur warm-up is amortised over
+      // 64 rows for large batches; a single frame gets 16-row blocks and several hundred warps per level).
+      walk_strips(a.dst.w, &a.nstrips, &a.strip_lanes);
+      const int want_jobs = 2 * h->n_sm * 24;
+      const int nrb_want = std::max(1, (want_jobs + batch * a.nstrips - 1) / (batch * a.nstrips));
+      int rows = (int)align_up((a.dst.h + nrb_want - 1) / nrb_want, 4);
+      rows = std::min(64, std::max(16, rows));
+      a.nrb = (a.dst.h + rows - 1) / rows;
+      a.rows_per_job = (int)align_up((a.dst.h + a.nrb - 1) / a.nrb, 4);
+      a.nrb = (a.dst.h + a.rows_per_job - 1) / a.rows_per_job;
+      dim3 grid(a.nstrips, a.nrb, batch);
+      if (l == 0) pyr_walk_kernel<true><<<grid, 32, 0, st>>>(a);
+      else pyr_walk_kernel<false><<<grid, 32, 0, st>>>(a);
+#endif
       launches++;
     }
   }
