@@ -63,6 +63,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 
 }  // namespace swm
 #include "pyr_walk.cuh"
+#include "fast_tile.cuh"
 namespace swm {
 
 #ifndef SWM_PYR_TILED
@@ -305,6 +306,10 @@ __global__ void __launch_bounds__(256) pyr_kernel(const PyrArgs a) {
 
 #endif  // SWM_PYR_TILED
 
+#ifndef SWM_FAST_BLOCK
+#define SWM_FAST_BLOCK 0  // 1: the round-1 256-thread block kernel (A/B baseline of fast_tile.cuh)
+#endif
+#if SWM_FAST_BLOCK
 // ------------------------------------------------------------------------------------------------
 // FAST kernel (Fast_gpu.cu:284-341, deterministic lock-step form).  One CTA = two horizontally
 // adjacent 32x32 FAST tiles of one level, anchored on the reference's tile grid (level pixel
@@ -324,16 +329,15 @@ __global__ void __launch_bounds__(256) pyr_kernel(const PyrArgs a) {
 // first column is level x = FB_W*bx, i.e. 16-byte aligned in the plane, so every row is one TMA bulk copy
 // (cp.async.bulk, 160 B) completing on an mbarrier.  Local column of the first interior pixel
 // (level x = 19 + FB_W bx) is kFx = 19; local row of the first interior row is 4.
-constexpr int kFT = 4, FB_W = 32 * kFT;
+constexpr int FB_W = 32 * kFT;
 constexpr int FS_WORDS = 40, FS_COLS = FS_WORDS * 4, FS_ROWS = TH + 8;
-constexpr int kFx = 19;
 constexpr int FS_SW = FB_W / 4 + 1;                  // words per row that hold scored pixels (local x 18 .. 19+FB_W)
 constexpr int FS_ITEMS = 34 * FS_SW;                // quick-reject word items per CTA
 constexpr int FS_IT = (FS_ITEMS + 255) / 256;
 constexpr int FS_MAXCAND = (FB_W + 2) * 34;
 static_assert(kFx + FB_W + 4 <= FS_COLS && 4 + FS_SW <= FS_WORDS - 1, "staged tile too narrow");
 
-__device__ __forceinline__ uint32_t oob_mask(uint32_t a, uint32_t v, uint32_t c7) {
+__device__ __forceinline__ uint32_t oob_mask_blk(uint32_t a, uint32_t v, uint32_t c7) {
   // bit 7 of each byte set iff |a - v| > th, with c7 = (127 - th) * 0x01010101
   const uint32_t ad = __vabsdiffu4(a, v);
   return (((ad & 0x7F7F7F7Fu) + c7) | ad) & 0x80808080u;
@@ -343,7 +347,7 @@ __device__ __forceinline__ uint32_t oob_mask(uint32_t a, uint32_t v, uint32_t c7
 // max(v - r, 0); sliding 9-minimum by doubling with VIMNMX(3).U16x2, maximum over the 16 arcs.
 // Same value as swm::fast_score (swm_core.cuh) without its early-outs; checked bit-exact on the device
 // by the parity tests (the ptxas negated-max hazard does not apply: nothing is negated after a min/max).
-__device__ __forceinline__ int fast_score_x2(const uint8_t* c, int pitch, int th) {
+__device__ __forceinline__ int fast_score_blk(const uint8_t* c, int pitch, int th) {
   const int v = c[0];
   const uint32_t nv = ((uint32_t)(-v) & 0xFFFFu) | ((uint32_t)v << 16);  // (-v, +v)
   uint32_t d[16];
@@ -467,13 +471,13 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
         if (gy >= kEdge && gy < h - kEdge) {
           const uint32_t* row = s_px + ly * FS_WORDS + jw;
           const uint32_t v = row[0];
-          m = (oob_mask(row[-3 * FS_WORDS], v, c7) | oob_mask(row[3 * FS_WORDS], v, c7)) & s_colmask[jw];
-          if (m) m &= oob_mask(__funnelshift_r(row[0], row[1], 24), v, c7) | oob_mask(__funnelshift_r(row[-1], row[0], 8), v, c7);
+          m = (oob_mask_blk(row[-3 * FS_WORDS], v, c7) | oob_mask_blk(row[3 * FS_WORDS], v, c7)) & s_colmask[jw];
+          if (m) m &= oob_mask_blk(__funnelshift_r(row[0], row[1], 24), v, c7) | oob_mask_blk(__funnelshift_r(row[-1], row[0], 8), v, c7);
           if (m) {
             const uint32_t* rp = row + 2 * FS_WORDS;
             const uint32_t* rm = row - 2 * FS_WORDS;
-            m &= oob_mask(__funnelshift_r(rp[0], rp[1], 16), v, c7) | oob_mask(__funnelshift_r(rm[-1], rm[0], 16), v, c7);
-            if (m) m &= oob_mask(__funnelshift_r(rm[0], rm[1], 16), v, c7) | oob_mask(__funnelshift_r(rp[-1], rp[0], 16), v, c7);
+            m &= oob_mask_blk(__funnelshift_r(rp[0], rp[1], 16), v, c7) | oob_mask_blk(__funnelshift_r(rm[-1], rm[0], 16), v, c7);
+            if (m) m &= oob_mask_blk(__funnelshift_r(rm[0], rm[1], 16), v, c7) | oob_mask_blk(__funnelshift_r(rp[-1], rp[0], 16), v, c7);
           }
         }
       }
@@ -518,7 +522,7 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
     for (int i = tid; i < n_cand; i += 256) {
       const int e = s_list[i];
       const int ly = e >> 8, lx = e & 255;
-      const int sc = fast_score_x2(s_pxb + ly * FS_COLS + lx, FS_COLS, th_run);
+      const int sc = fast_score_blk(s_pxb + ly * FS_COLS + lx, FS_COLS, th_run);
       s_scb[ly * FS_COLS + lx] = (uint8_t)sc;
       if (sc >= (pass == 1 ? ini_th : 1) && lx >= kFx && lx < kFx + FB_W && ly >= 4 && ly <= 35 &&
           (pass == 1 || s_flag[(kFT + 2) + 1 + ((lx - kFx) >> 5)] != 0))
@@ -591,6 +595,8 @@ __global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restr
     }
   }
 }
+
+#endif  // SWM_FAST_BLOCK
 
 // ------------------------------------------------------------------------------------------------
 // Quadtree: one CTA per (level, frame).
@@ -828,6 +834,7 @@ struct swm_orb {
   FrameLayout* d_lay = nullptr;
   ResizeTap *d_xtab = nullptr, *d_ytab = nullptr;
   CUtensorMap* d_maps = nullptr;  // per level: the un-blurred plane over all frames, for pyr_walk_kernel's TMA tiles
+  CUtensorMap* d_fmaps = nullptr; // the same planes with fast_tile_kernel's box
   uint8_t *d_plain = nullptr, *d_blur = nullptr, *d_score = nullptr;
   uint8_t* d_retry = nullptr;
   int4* d_fblk = nullptr;       // per FAST block: (level, bx, by, 0)
@@ -882,11 +889,11 @@ void free_frame_buffers(swm_orb* h) {
   if (h->graph) cudaGraphExecDestroy(h->graph);
   h->graph = nullptr;
   h->graph_runs = 0;
-  cudaFree(h->d_lay); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_maps);
+  cudaFree(h->d_lay); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_maps); cudaFree(h->d_fmaps);
   cudaFree(h->d_plain); cudaFree(h->d_blur); cudaFree(h->d_score);
   cudaFree(h->d_retry); cudaFree(h->d_retry_list); cudaFree(h->d_fblk); cudaFree(h->d_pts); cudaFree(h->d_pnode); cudaFree(h->d_pchild); cudaFree(h->d_cand); cudaFree(h->d_sel); cudaFree(h->d_counts);
   cudaFree(h->d_img); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_n);
-  h->d_lay = nullptr; h->d_xtab = h->d_ytab = nullptr; h->d_maps = nullptr;
+  h->d_lay = nullptr; h->d_xtab = h->d_ytab = nullptr; h->d_maps = nullptr; h->d_fmaps = nullptr;
   h->d_plain = h->d_blur = h->d_score = nullptr;
   h->d_retry = nullptr; h->d_retry_list = nullptr; h->d_fblk = nullptr; h->d_pts = nullptr; h->d_pnode = nullptr; h->d_pchild = nullptr; h->d_cand = h->d_sel = nullptr; h->d_counts = nullptr;
   h->d_img = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->d_n = nullptr;
@@ -1074,21 +1081,25 @@ int setup_geometry(swm_orb* h, int w, int hh) {
     cudaDriverEntryPointQueryResult qres;
     SWM_CK(h, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
     if (!fn || qres != cudaDriverEntryPointSuccess) { h->err = "cuTensorMapEncodeTiled is not available in this driver"; return SWM_E_CUDA; }
-    std::vector<CUtensorMap> maps(nl);
-    memset(maps.data(), 0, sizeof(CUtensorMap) * nl);
-    for (int l = 0; l + 1 < nl; l++) {
+    std::vector<CUtensorMap> maps(2 * nl);
+    memset(maps.data(), 0, sizeof(CUtensorMap) * 2 * nl);
+    for (int l = 0; l < nl; l++) {
       const LevelGeom& g = L.lv[l];
       const cuuint64_t dims[3] = {(cuuint64_t)g.pitch, (cuuint64_t)g.rows, (cuuint64_t)B};
       const cuuint64_t strides[2] = {(cuuint64_t)g.pitch, (cuuint64_t)L.slab_bytes};
-      const cuuint32_t box[3] = {(cuuint32_t)kWalkRowBytes, (cuuint32_t)kWalkStageRows, 1u};
       const cuuint32_t estr[3] = {1u, 1u, 1u};
-      const CUresult r = ((EncodeTiled)fn)(&maps[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->d_plain + g.plane_off, dims, strides, box, estr,
-                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-      if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed for a pyramid plane (code " + std::to_string((int)r) + ")"; return SWM_E_CUDA; }
+      for (int which = 0; which < 2; which++) {  // 0: pyramid walk (source rows of level l + 1), 1: FAST tile window
+        const cuuint32_t box[3] = {(cuuint32_t)(which ? FT_PITCH : kWalkRowBytes), (cuuint32_t)(which ? FT_ROWS : kWalkStageRows), 1u};
+        const CUresult r = ((EncodeTiled)fn)(&maps[which * nl + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, h->d_plain + g.plane_off, dims, strides,
+                                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { h->err = "cuTensorMapEncodeTiled failed for a pyramid plane (code " + std::to_string((int)r) + ")"; return SWM_E_CUDA; }
+      }
     }
     SWM_CK(h, cudaMalloc(&h->d_maps, sizeof(CUtensorMap) * nl));
+    SWM_CK(h, cudaMalloc(&h->d_fmaps, sizeof(CUtensorMap) * nl));
     SWM_CK(h, cudaMemcpy(h->d_maps, maps.data(), sizeof(CUtensorMap) * nl, cudaMemcpyHostToDevice));
+    SWM_CK(h, cudaMemcpy(h->d_fmaps, maps.data() + nl, sizeof(CUtensorMap) * nl, cudaMemcpyHostToDevice));
   }
   // planes start zeroed so padding bytes are deterministic
   SWM_CK(h, cudaMemset(h->d_plain, 0, (size_t)L.slab_bytes * B));
@@ -1160,10 +1171,27 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
     SWM_CK(h, cudaMemsetAsync(h->d_retry_list, 0, sizeof(int), st));
     dim3 grid(L.fblk_total, batch);
     uint8_t* dbg = h->debug_score ? h->d_score : nullptr;
+#if !SWM_FAST_BLOCK
+    FastArgs fa;
+    fa.L = h->d_lay;
+    fa.maps = h->d_fmaps;
+    fa.fblk_desc = h->d_fblk;
+    fa.ini_th = h->cfg.ini_th_fast;
+    fa.min_th = h->cfg.min_th_fast;
+    fa.retry = h->d_retry;
+    fa.retry_list = h->d_retry_list;
+    fa.cand = h->d_cand;
+    fa.cand_count = d_cand_count;
+    fa.dbg_score = dbg;
+    fast_tile_kernel<1><<<grid, 32, 0, st>>>(fa);
+    fa.dbg_score = nullptr;
+    fast_tile_kernel<2><<<h->n_sm * 24, 32, 0, st>>>(fa);
+#else
     fast_kernel<<<grid, 256, 0, st>>>(h->d_lay, h->d_plain, h->d_fblk, h->cfg.ini_th_fast, h->cfg.min_th_fast, 1,
                                       h->d_retry, h->d_retry_list, h->d_cand, d_cand_count, dbg);
     fast_kernel<<<h->n_sm * 3, 256, 0, st>>>(h->d_lay, h->d_plain, h->d_fblk, h->cfg.ini_th_fast, h->cfg.min_th_fast, 2,
                                              h->d_retry, h->d_retry_list, h->d_cand, d_cand_count, nullptr);
+#endif
     launches += 2;
   }
   if (mask & SWM_STAGE_OCTREE) {

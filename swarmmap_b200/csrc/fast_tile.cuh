@@ -1,0 +1,305 @@
+// fast_tile.cuh -- FAST-9/16 detection, score, tile retry and non-max suppression with one WARP per run of 32x32 tiles
+// (round 2; replaces the 256-thread block kernel of round 1).
+//
+// Reference behaviour restated (paths relative to /root/reference/code/):
+//   tileCalcKeypoints_kernel   src/cuda/Fast_gpu.cu:284-341  (deterministic lock-step form; tiles anchored at (19,19))
+//   isKeyPoint2 / cornerScore  src/cuda/Fast_gpu.cu:70-266   (largest threshold at which the pixel is still a corner)
+//   ComputeKeyPointsOctTree    src/ORBextractor.cc:691-744   (iniThFAST first, minThFAST where a tile found nothing)
+//
+// A CTA is ONE warp that walks a horizontal run of up to kFT tiles of one level.  Per tile:
+//   * the 64 x 40 byte window (tile + 4 px halo, 16-byte aligned start) arrives by ONE tensor-map TMA copy (cp.async.bulk.tensor.3d,
+//     UTMALDG in SASS) into a double buffer: the next tile's copy is in flight while this one is processed;
+//   * packed quick reject, 4 pixels per word item: the four opposite ring pairs with VABSDIFF4 + carry-trick band test
+//     (exact: every 9-arc holds one pixel of each pair); survivors are compacted with warp ballots (no block scan);
+//   * survivors are scored on two 16-bit lanes (bright ring, dark ring): three-wide minima, then minima of three of
+//     those = all 9-arcs, then the maximum (VIMNMX3.U16x2);
+//   * strict 3x3 non-max suppression in the shared score tile; warp-aggregated append to the (frame, level) list.
+//   pass 1: keypoint iff S_hi(p) > S_hi(q) for the 8 neighbours (S_hi: scores below iniThFAST count as 0), so it detects
+//           at iniThFAST; a tile without a keypoint is flagged for retry and its run goes on the retry list;
+//   pass 2 (persistent grid over the retry list): only flagged tiles are redone, at minThFAST, against
+//           S_eff = S in retried tiles, S_hi elsewhere.
+// No block barrier, no atomics in shared memory.  Append order is unordered; everything downstream orders by explicit keys.
+#pragma once
+
+namespace swm {
+
+constexpr int kFT = 4;                       // tiles per run (one warp)
+// Staged window: 64 x 40 bytes from level (X0 - 19, Y0 - 4), X0 - 19 = 32 * tile: the TMA needs a 16-byte aligned start
+// (an unaligned first coordinate faults), so the first interior pixel sits at local (kFx, 4) = (19, 4).
+constexpr int FT_PITCH = 64, FT_ROWS = 40, kFx = 19;
+constexpr int FT_WORDS = FT_PITCH / 4;
+constexpr int FT_QW0 = 4, FT_QW = 9;         // words per row that hold scored pixels (local x 18 .. 51): words 4 .. 12
+constexpr int FT_SCP = 48, FT_SCX = 16;      // score tile: pitch and the local x of its column 0
+constexpr int FT_ITEMS = 34 * FT_QW;         // quick-reject word items per tile (rows 3 .. 36)
+constexpr int FT_IT = (FT_ITEMS + 31) / 32;
+constexpr int FT_LIST = 34 * 34 + 4;
+
+__device__ __forceinline__ uint32_t oob_mask(uint32_t a, uint32_t v, uint32_t c7) {
+  // bit 7 of each byte set iff |a - v| > th, with c7 = (127 - th) * 0x01010101
+  const uint32_t ad = __vabsdiffu4(a, v);
+  return (((ad & 0x7F7F7F7Fu) + c7) | ad) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// FAST score of the pixel at shared address c (row pitch FT_PITCH) on two 16-bit lanes per register: lane 0 = bright
+// ring max(r - v, 0), lane 1 = dark ring max(v - r, 0).  min over every 9-arc = min3 of three 3-wide minima; maximum
+// over the 16 arcs; both polarities at once.  Same value as swm::fast_score (swm_core.cuh) without its early-outs;
+// checked bit-exact on the device by the parity tests.  (Nothing is negated after a min/max: the ptxas hazard noted in
+// swm_core.cuh does not apply.)  `zero` is an opaque 0 so that the clamp operand stays one register.
+__device__ __forceinline__ int fast_score_x2(uint32_t c, int th, uint32_t zero) {
+  constexpr int P = FT_PITCH;
+  const uint32_t v = lds8(c);
+  const uint32_t nv = ((0u - v) & 0xFFFFu) | (v << 16);  // (-v, +v)
+  uint32_t d[16];
+#define SWM_RING(k, off) d[k] = __viaddmax_s16x2(lds8(c + (off)) * 0xFFFF0001u, nv, zero)  // (r,-r)+(-v,v), clamp 0
+  SWM_RING(0, 3 * P);      SWM_RING(1, 3 * P + 1);   SWM_RING(2, 2 * P + 2);   SWM_RING(3, P + 3);
+  SWM_RING(4, 3);          SWM_RING(5, -P + 3);      SWM_RING(6, -2 * P + 2);  SWM_RING(7, -3 * P + 1);
+  SWM_RING(8, -3 * P);     SWM_RING(9, -3 * P - 1);  SWM_RING(10, -2 * P - 2); SWM_RING(11, -P - 3);
+  SWM_RING(12, -3);        SWM_RING(13, P - 3);      SWM_RING(14, 2 * P - 2);  SWM_RING(15, 3 * P - 1);
+#undef SWM_RING
+  uint32_t p3[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) p3[k] = __vimin3_u16x2(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+  uint32_t best = 0;
+#pragma unroll
+  for (int k = 0; k < 16; k += 2) {
+    const uint32_t m0 = __vimin3_u16x2(p3[k], p3[(k + 3) & 15], p3[(k + 6) & 15]);
+    const uint32_t m1 = __vimin3_u16x2(p3[k + 1], p3[(k + 4) & 15], p3[(k + 7) & 15]);
+    best = __vimax3_u16x2(best, m0, m1);
+  }
+  const int b = max((int)(best & 0xFFFFu), (int)(best >> 16));
+  return b > th ? b - 1 : 0;
+}
+
+struct FastArgs {
+  const FrameLayout* L;
+  const CUtensorMap* maps;   // per level: un-blurred plane (row byte, row, frame), box FT_PITCH x FT_ROWS x 1
+  const int4* fblk_desc;     // per run: (level, bx, by, -)
+  int ini_th, min_th;
+  uint8_t* retry;            // per (frame, tile): 1 = no pass-1 keypoint
+  int* retry_list;           // [0] = count, then frame * runs + run
+  uint32_t* cand;
+  int* cand_count;
+  uint8_t* dbg_score;        // parity introspection: score map S at minThFAST (pass 1 only), or null
+};
+
+template <int kPass>
+__global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
+  __shared__ __align__(128) uint8_t s_px[2][FT_ROWS * FT_PITCH];
+  __shared__ __align__(16) uint8_t s_sc[FT_ROWS * FT_SCP];
+  __shared__ uint16_t s_list[FT_LIST];
+  __shared__ uint32_t s_colmask[FT_QW];
+  __shared__ uint8_t s_flag[3 * (kFT + 2)];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  const FrameLayout* __restrict__ L = a.L;
+  const int lane = threadIdx.x;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int nrun = L->fblk_total;
+  const uint32_t zero = (uint32_t)(a.ini_th >> 31);  // 0 (thresholds are positive); opaque to the compiler
+  const uint32_t px_u32 = smem_u32(s_px), sc_u32 = smem_u32(s_sc), bar_u32 = smem_u32(s_bar);
+  if (lane == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t phbits = 0;
+  const int th_run = (kPass == 1 && a.dbg_score == nullptr) ? a.ini_th : a.min_th;
+  const uint32_t c7 = (uint32_t)(127 - th_run) * 0x01010101u;
+
+  for (int work = blockIdx.x;; work += gridDim.x) {
+    int fb;
+    if (kPass == 1) {
+      if (work != (int)blockIdx.x) break;
+      fb = blockIdx.y * nrun + blockIdx.x;
+    } else {
+      if (work >= a.retry_list[0]) break;
+      fb = a.retry_list[1 + work];
+    }
+    const int f = kPass == 1 ? (int)blockIdx.y : fb / nrun;
+    const int4 bd = __ldg(&a.fblk_desc[fb - f * nrun]);
+    const int lvl = bd.x, bx = bd.y, by = bd.z;
+    const LevelGeom& g = L->lv[lvl];
+    const int w = g.w, h = g.h;
+    uint8_t* fretry = a.retry + (long long)f * L->tiles_total + g.tile_off;
+    const int t0 = by * g.tiles_x + kFT * bx;
+    const int ntile = min(kFT, g.tiles_x - kFT * bx);
+    const int Y0 = kEdge + 32 * by;
+    if (kPass == 2) {
+      __syncwarp();
+      if (lane < 3 * (kFT + 2)) {
+        const int ny = by + lane / (kFT + 2) - 1, nx = kFT * bx + lane % (kFT + 2) - 1;
+        s_flag[lane] = (ny >= 0 && ny < g.tiles_y && nx >= 0 && nx < g.tiles_x) ? fretry[ny * g.tiles_x + nx] : 0;
+      }
+      __syncwarp();
+    }
+    const CUtensorMap* map = a.maps + lvl;
+    auto active = [&](int j) -> int {  // first tile >= j of the run that has to be processed
+      if (kPass == 2)
+        while (j < ntile && s_flag[(kFT + 2) + 1 + j] == 0) j++;
+      return j;
+    };
+    auto issue = [&](int j, int buf) {
+      if (lane == 0) {
+        const uint32_t bar = bar_u32 + 8u * buf;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(FT_ROWS * FT_PITCH) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                px_u32 + buf * (FT_ROWS * FT_PITCH)),
+            "l"(map), "r"(kPadX + 32 * (kFT * bx + j)), "r"(kEdge + Y0 - 4), "r"(f), "r"(bar)
+            : "memory");
+      }
+    };
+    int anymask = 0;
+    int buf = 0;
+    int j = active(0);
+    if (j < ntile) issue(j, buf);
+    while (j < ntile) {
+      const int jn = active(j + 1);
+      __syncwarp();  // every lane is done with the other buffer (tile before this one)
+      if (jn < ntile) issue(jn, buf ^ 1);
+      const int X0 = kEdge + 32 * (kFT * bx + j);   // first interior pixel (level coords); staged origin (X0-19, Y0-4)
+      // score tile cleared; scored columns of each word: interior +- 1 px and level x in [19, w - 19)
+      for (int i = lane; i < FT_ROWS * FT_SCP / 16; i += 32) reinterpret_cast<uint4*>(s_sc)[i] = make_uint4(0, 0, 0, 0);
+      if (lane < FT_QW) {
+        uint32_t m = 0;
+        for (int k = 0; k < 4; k++) {
+          const int lx = 4 * (FT_QW0 + lane) + k, gx = X0 - kFx + lx;
+          if (lx >= kFx - 1 && lx <= kFx + 32 && gx >= kEdge && gx < w - kEdge) m |= 0x80u << (8 * k);
+        }
+        s_colmask[lane] = m;
+      }
+      mbar_wait(&s_bar[buf], (phbits >> buf) & 1u);
+      phbits ^= 1u << buf;
+      __syncwarp();
+      const uint32_t* px = reinterpret_cast<const uint32_t*>(s_px[buf]);
+      const uint32_t pxb = px_u32 + buf * (FT_ROWS * FT_PITCH);
+
+      // ---- packed quick reject on the scored region (interior + 1 px): rows ly 3..36, words 4..12; ballot compaction
+      int n_cand = 0;
+#pragma unroll 1
+      for (int it = 0; it < FT_IT; it++) {
+        const int i = lane + 32 * it;
+        uint32_t m = 0;
+        int ly = 0, jw = 0;
+        if (i < FT_ITEMS) {
+          const int r = i / FT_QW;
+          jw = i - r * FT_QW;
+          ly = r + 3;
+          const int gy = Y0 - 4 + ly;
+          if (gy >= kEdge && gy < h - kEdge) {
+            const uint32_t* row = px + ly * FT_WORDS + FT_QW0 + jw;
+            const uint32_t v = row[0];
+            m = (oob_mask(row[-3 * FT_WORDS], v, c7) | oob_mask(row[3 * FT_WORDS], v, c7)) & s_colmask[jw];
+            if (m) m &= oob_mask(__funnelshift_r(row[0], row[1], 24), v, c7) | oob_mask(__funnelshift_r(row[-1], row[0], 8), v, c7);
+            if (m) {
+              const uint32_t* rp = row + 2 * FT_WORDS;
+              const uint32_t* rm = row - 2 * FT_WORDS;
+              m &= oob_mask(__funnelshift_r(rp[0], rp[1], 16), v, c7) | oob_mask(__funnelshift_r(rm[-1], rm[0], 16), v, c7);
+              if (m) m &= oob_mask(__funnelshift_r(rm[0], rm[1], 16), v, c7) | oob_mask(__funnelshift_r(rp[-1], rp[0], 16), v, c7);
+            }
+          }
+        }
+        const uint32_t e0 = (uint32_t)((ly << 8) | (4 * (FT_QW0 + jw)));
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const bool on = (m & (0x80u << (8 * k))) != 0;
+          const uint32_t bal = __ballot_sync(0xffffffffu, on);
+          if (on) s_list[n_cand + __popc(bal & lt)] = (uint16_t)(e0 + k);
+          n_cand += __popc(bal);
+        }
+      }
+      __syncwarp();
+
+      // ---- score the survivors; those that can be keypoints are compacted to the front of the same list
+      int n2 = 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < n_cand; c0 += 32) {
+        const int c = c0 + lane;
+        bool q = false;
+        uint32_t e = 0;
+        if (c < n_cand) {
+          e = s_list[c];
+          const int ly = e >> 8, lx = e & 255;
+          const int sc = fast_score_x2(pxb + (uint32_t)(ly * FT_PITCH + lx), th_run, zero);
+          s_sc[ly * FT_SCP + lx - FT_SCX] = (uint8_t)sc;
+          q = sc >= (kPass == 1 ? a.ini_th : 1) && lx >= kFx && lx < kFx + 32 && ly >= 4 && ly < 36;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, q);
+        __syncwarp();
+        if (q) s_list[n2 + __popc(bal & lt)] = (uint16_t)e;
+        n2 += __popc(bal);
+      }
+      __syncwarp();
+
+      // ---- non-max suppression (strict, 8 neighbours) of the short list
+      bool tile_any = false;
+#pragma unroll 1
+      for (int c0 = 0; c0 < n2; c0 += 32) {
+        const int c = c0 + lane;
+        bool kp = false;
+        int lx = 0, ly = 0, sc = 0;
+        if (c < n2) {
+          const int e = s_list[c];
+          ly = e >> 8;
+          lx = e & 255;
+          const uint32_t sp = sc_u32 + (uint32_t)(ly * FT_SCP + lx - FT_SCX);
+          sc = (int)lds8(sp);
+          kp = true;
+#pragma unroll
+          for (int dy = -1; dy <= 1; dy++)
+#pragma unroll
+            for (int dx = -1; dx <= 1; dx++) {
+              if (dx == 0 && dy == 0) continue;
+              int qv = (int)lds8(sp + dy * FT_SCP + dx);
+              bool raw = false;
+              if (kPass == 2) {
+                const int qx = lx + dx, qy = ly + dy;
+                const int fy = qy < 4 ? 0 : (qy > 35 ? 2 : 1);
+                const int fx = qx < kFx ? 0 : (qx > kFx + 31 ? 2 : 1);
+                raw = s_flag[fy * (kFT + 2) + j + fx] != 0;
+              }
+              if (!raw && qv < a.ini_th) qv = 0;
+              kp = kp && sc > qv;
+            }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, kp);
+        if (bal) {
+          tile_any = true;
+          int base = 0;
+          if (lane == 0) base = atomicAdd(a.cand_count + f * L->nlevels + lvl, __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (kp) {
+            const int idx = base + __popc(bal & lt);
+            if (idx < g.cand_cap)
+              a.cand[(long long)f * L->cand_total + g.cand_off + idx] = pack_pt(X0 - kFx + lx - kBand, Y0 - 4 + ly - kBand, sc);
+          }
+        }
+      }
+      if (tile_any) anymask |= 1 << j;
+      if (kPass == 1 && a.dbg_score) {  // parity introspection only: the score map S at minThFAST for the tile interior
+        uint8_t* scp = a.dbg_score + (long long)f * L->slab_bytes + g.plane_off + (long long)kEdge * g.pitch + kPadX;
+        for (int i = lane; i < 32 * 32; i += 32) {
+          const int ly = (i >> 5) + 4, lx = (i & 31) + kFx;
+          const int gx = X0 - kFx + lx, gy = Y0 - 4 + ly;
+          if (gx < w - kEdge && gy < h - kEdge) scp[(long long)gy * g.pitch + gx] = s_sc[ly * FT_SCP + lx - FT_SCX];
+        }
+      }
+      j = jn;
+      buf ^= 1;
+    }
+    if (kPass == 1) {
+      // a tile with no pass-1 keypoint is retried at minThFAST (ORBextractor.cc:718-727); pass 2 re-runs only these runs
+      const bool r = lane < ntile && !((anymask >> lane) & 1);
+      if (lane < ntile) fretry[t0 + lane] = r ? 1 : 0;
+      const uint32_t any_retry = __ballot_sync(0xffffffffu, r);
+      if (any_retry && lane == 0) a.retry_list[1 + atomicAdd(a.retry_list, 1)] = fb;
+    }
+  }
+}
+
+}  // namespace swm

@@ -181,12 +181,31 @@ __global__ void __launch_bounds__(32, 24) pyr_walk_kernel(const PyrArgs a) {
   uint32_t H0[4] = {0, 0, 0, 0}, H1[4] = {0, 0, 0, 0};
   int r0 = -1, r1 = -1;
 
+  // level 0: my word of frame row v (reflect-101 rows; -5 <= v <= h + 9 and h >= 39).  The words of the NEXT step are
+  // loaded one step ahead, so the walk does not wait on the frame either.
+  auto frame_word = [&](int v) -> uint32_t {
+    const int ay = v < 0 ? -v : (v >= h ? 2 * h - 2 - v : v);
+    const uint8_t* row = src + (long long)ay * spitch;
+    if (fastlane) return __ldg(reinterpret_cast<const uint32_t*>(row + X));
+    return (uint32_t)__ldg(row + cx0) | ((uint32_t)__ldg(row + cx1) << 8) | ((uint32_t)__ldg(row + cx2) << 16) |
+           ((uint32_t)__ldg(row + cx3) << 24);
+  };
+  uint32_t cw[4] = {0, 0, 0, 0}, nw[4] = {0, 0, 0, 0};
+  if (kFirst) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) cw[i] = frame_word(y0 - 5 + i);
+  }
+
   uint32_t e[10], o[10];
 #pragma unroll
   for (int k = 0; k < 10; k++) e[k] = o[k] = 0;
 #pragma unroll 1
   for (int it = 0; it < nit; it++) {
     const int vb = y0 - 5 + 4 * it;  // two warm-up steps fill the blur window (rows y0-5 .. y0+2)
+    if (kFirst) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) nw[i] = frame_word(vb + 4 + i);
+    }
     if (!kFirst) {
       if (it + 2 < nit) lo_n2 = prefetch(it + 2, tap_n2);
       const int sg = it % kWalkStages;
@@ -198,14 +217,7 @@ __global__ void __launch_bounds__(32, 24) pyr_walk_kernel(const PyrArgs a) {
       const int v = vb + i;
       uint32_t word, ev, ov;
       if (kFirst) {
-        const int ay = v < 0 ? -v : (v >= h ? 2 * h - 2 - v : v);  // reflect-101; -5 <= v <= h + 5 and h >= 39
-        const uint8_t* row = src + (long long)ay * spitch;
-        if (fastlane) {
-          word = __ldg(reinterpret_cast<const uint32_t*>(row + X));
-        } else {
-          word = (uint32_t)__ldg(row + cx0) | ((uint32_t)__ldg(row + cx1) << 8) | ((uint32_t)__ldg(row + cx2) << 16) |
-                 ((uint32_t)__ldg(row + cx3) << 24);
-        }
+        word = cw[i];
         ev = word & 0x00FF00FFu;
         ov = (word >> 8) & 0x00FF00FFu;
       } else {
@@ -297,6 +309,8 @@ __global__ void __launch_bounds__(32, 24) pyr_walk_kernel(const PyrArgs a) {
       e[k] = e[k + 4];
       o[k] = o[k + 4];
     }
+#pragma unroll
+    for (int i = 0; i < 4; i++) cw[i] = nw[i];
     lo_cur = lo_n1;
     lo_n1 = lo_n2;
     tap_cur = tap_n1;
