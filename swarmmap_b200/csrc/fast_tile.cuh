@@ -26,7 +26,10 @@ namespace swm {
 constexpr int kFT = 4;                       // tiles per run (one warp)
 // Staged window: 64 x 40 bytes from level (X0 - 19, Y0 - 4), X0 - 19 = 32 * tile: the TMA needs a 16-byte aligned start
 // (an unaligned first coordinate faults), so the first interior pixel sits at local (kFx, 4) = (19, 4).
-constexpr int FT_PITCH = 64, FT_ROWS = 40, kFx = 19;
+#ifndef SWM_FT_PITCH
+#define SWM_FT_PITCH 64
+#endif
+constexpr int FT_PITCH = SWM_FT_PITCH, FT_ROWS = 40, kFx = 19;
 constexpr int FT_WORDS = FT_PITCH / 4;
 constexpr int FT_QW0 = 4, FT_QW = 9;         // words per row that hold scored pixels (local x 18 .. 51): words 4 .. 12
 constexpr int FT_SCP = 48, FT_SCX = 16;      // score tile: pitch and the local x of its column 0
@@ -38,6 +41,17 @@ __device__ __forceinline__ uint32_t oob_mask(uint32_t a, uint32_t v, uint32_t c7
   // bit 7 of each byte set iff |a - v| > th, with c7 = (127 - th) * 0x01010101
   const uint32_t ad = __vabsdiffu4(a, v);
   return (((ad & 0x7F7F7F7Fu) + c7) | ad) & 0x80808080u;
+}
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t lds8(uint32_t addr) {
   uint32_t v;
@@ -100,7 +114,7 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
   const uint32_t lt = (1u << lane) - 1u;
   const int nrun = L->fblk_total;
   const uint32_t zero = (uint32_t)(a.ini_th >> 31);  // 0 (thresholds are positive); opaque to the compiler
-  const uint32_t px_u32 = smem_u32(s_px), sc_u32 = smem_u32(s_sc), bar_u32 = smem_u32(s_bar);
+  const uint32_t px_u32 = smem_u32(s_px), sc_u32 = smem_u32(s_sc), bar_u32 = smem_u32(s_bar), list_u32 = smem_u32(s_list);
   if (lane == 0) {
     mbar_init(&s_bar[0], 1);
     mbar_init(&s_bar[1], 1);
@@ -204,14 +218,20 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
             }
           }
         }
+        // survivors -> list: exclusive prefix of the per-lane counts (0..4) from three bit-plane ballots
+        const uint32_t cnt = (uint32_t)__popc(m);
+        const uint32_t b0 = __ballot_sync(0xffffffffu, cnt & 1u), b1 = __ballot_sync(0xffffffffu, cnt & 2u),
+                       b2 = __ballot_sync(0xffffffffu, cnt & 4u);
+        uint32_t addr = list_u32 + 2u * (uint32_t)(n_cand + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt));
         const uint32_t e0 = (uint32_t)((ly << 8) | (4 * (FT_QW0 + jw)));
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          const bool on = (m & (0x80u << (8 * k))) != 0;
-          const uint32_t bal = __ballot_sync(0xffffffffu, on);
-          if (on) s_list[n_cand + __popc(bal & lt)] = (uint16_t)(e0 + k);
-          n_cand += __popc(bal);
+          if (m & (0x80u << (8 * k))) {
+            sts16(addr, e0 + k);
+            addr += 2;
+          }
         }
+        n_cand += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
       }
       __syncwarp();
 
@@ -223,15 +243,15 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
         bool q = false;
         uint32_t e = 0;
         if (c < n_cand) {
-          e = s_list[c];
+          e = lds16(list_u32 + 2u * c);
           const int ly = e >> 8, lx = e & 255;
           const int sc = fast_score_x2(pxb + (uint32_t)(ly * FT_PITCH + lx), th_run, zero);
-          s_sc[ly * FT_SCP + lx - FT_SCX] = (uint8_t)sc;
+          sts8(sc_u32 + (uint32_t)(ly * FT_SCP + lx - FT_SCX), (uint32_t)sc);
           q = sc >= (kPass == 1 ? a.ini_th : 1) && lx >= kFx && lx < kFx + 32 && ly >= 4 && ly < 36;
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, q);
         __syncwarp();
-        if (q) s_list[n2 + __popc(bal & lt)] = (uint16_t)e;
+        if (q) sts16(list_u32 + 2u * (uint32_t)(n2 + __popc(bal & lt)), e);
         n2 += __popc(bal);
       }
       __syncwarp();
@@ -244,7 +264,7 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
         bool kp = false;
         int lx = 0, ly = 0, sc = 0;
         if (c < n2) {
-          const int e = s_list[c];
+          const int e = (int)lds16(list_u32 + 2u * c);
           ly = e >> 8;
           lx = e & 255;
           const uint32_t sp = sc_u32 + (uint32_t)(ly * FT_SCP + lx - FT_SCX);
