@@ -9,7 +9,7 @@
 // A CTA is ONE warp that walks a horizontal run of up to kFT tiles of one level.  Per tile:
 //   * the 64 x 40 byte window (tile + 4 px halo, 16-byte aligned start) arrives by ONE tensor-map TMA copy (cp.async.bulk.tensor.3d,
 //     UTMALDG in SASS) into a double buffer: the next tile's copy is in flight while this one is processed;
-//   * packed quick reject, 4 pixels per word item: the four opposite ring pairs with VABSDIFF4 + carry-trick band test
+//   * packed quick reject, 8 pixels (an aligned word pair) per item: the four opposite ring pairs with VABSDIFF4 + carry-trick band test
 //     (exact: every 9-arc holds one pixel of each pair); survivors are compacted with warp ballots (no block scan);
 //   * survivors are scored on two 16-bit lanes (bright ring, dark ring): three-wide minima, then minima of three of
 //     those = all 9-arcs, then the maximum (VIMNMX3.U16x2);
@@ -33,14 +33,18 @@ constexpr int FT_PITCH = SWM_FT_PITCH, FT_ROWS = 40, kFx = 19;
 constexpr int FT_WORDS = FT_PITCH / 4;
 constexpr int FT_QW0 = 4, FT_QW = 9;         // words per row that hold scored pixels (local x 18 .. 51): words 4 .. 12
 constexpr int FT_SCP = 48, FT_SCX = 16;      // score tile: pitch and the local x of its column 0
-constexpr int FT_ITEMS = 34 * FT_QW;         // quick-reject word items per tile (rows 3 .. 36)
-constexpr int FT_IT = (FT_ITEMS + 31) / 32;
+constexpr int FT_QP = 5;                     // quick-reject items per row: the aligned word pairs (4,5) .. (12,13)
+constexpr int FT_PITEMS = 34 * FT_QP;        // items per tile (rows 3 .. 36)
+constexpr int FT_PIT = (FT_PITEMS + 31) / 32;
 constexpr int FT_LIST = 34 * 34 + 4;
 
-__device__ __forceinline__ uint32_t oob_mask(uint32_t a, uint32_t v, uint32_t c7) {
-  // bit 7 of each byte set iff |a - v| > th, with c7 = (127 - th) * 0x01010101
+// Quick-reject band test of four pixels: bit 7 of a byte of the result is set if |a - v| > th (c7 = (127 - th) *
+// 0x01010101).  The carry of a byte sum into its neighbour is NOT masked off: it can only set the flag of a pixel with
+// |a - v| == th, i.e. let one more pixel through to the exact score, never drop one -- and the integer ALU pipe, which
+// bounds this kernel (ncu: 78 % busy), is spared one LOP3 per test.  Bits other than 7, 15, 23, 31 are garbage.
+__device__ __forceinline__ uint32_t oob_bits(uint32_t a, uint32_t v, uint32_t c7) {
   const uint32_t ad = __vabsdiffu4(a, v);
-  return (((ad & 0x7F7F7F7Fu) + c7) | ad) & 0x80808080u;
+  return (ad + c7) | ad;
 }
 __device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((uint16_t)v) : "memory");
@@ -53,6 +57,16 @@ __device__ __forceinline__ uint32_t lds16(uint32_t addr) {
 __device__ __forceinline__ void sts8(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32s(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint32_t lds8(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -60,16 +74,17 @@ __device__ __forceinline__ uint32_t lds8(uint32_t addr) {
 }
 
 // FAST score of the pixel at shared address c (row pitch FT_PITCH) on two 16-bit lanes per register: lane 0 = bright
-// ring max(r - v, 0), lane 1 = dark ring max(v - r, 0).  min over every 9-arc = min3 of three 3-wide minima; maximum
-// over the 16 arcs; both polarities at once.  Same value as swm::fast_score (swm_core.cuh) without its early-outs;
-// checked bit-exact on the device by the parity tests.  (Nothing is negated after a min/max: the ptxas hazard noted in
-// swm_core.cuh does not apply.)  `zero` is an opaque 0 so that the clamp operand stays one register.
-__device__ __forceinline__ int fast_score_x2(uint32_t c, int th, uint32_t zero) {
+// ring r - v, lane 1 = dark ring v - r, both biased by 0x4000 so that they stay positive and ONE IMAD (FMA pipe) makes
+// both from a ring byte: r * 0xFFFF0001 = (r, -r), plus (0x4000 - v, 0x4000 + v); no carry crosses the lanes.  min over
+// every 9-arc = min3 of three 3-wide minima; maximum over the 16 arcs; both polarities at once (VIMNMX3.U16x2).  A ring
+// difference below zero needs no clamp: an arc that holds one cannot reach a positive minimum.  Same value as
+// swm::fast_score (swm_core.cuh) without its early-outs; checked bit-exact on the device by the parity tests.
+__device__ __forceinline__ int fast_score_x2(uint32_t c, int th) {
   constexpr int P = FT_PITCH;
   const uint32_t v = lds8(c);
-  const uint32_t nv = ((0u - v) & 0xFFFFu) | (v << 16);  // (-v, +v)
+  const uint32_t kv = (0x4000u - v) | ((0x4000u + v) << 16);
   uint32_t d[16];
-#define SWM_RING(k, off) d[k] = __viaddmax_s16x2(lds8(c + (off)) * 0xFFFF0001u, nv, zero)  // (r,-r)+(-v,v), clamp 0
+#define SWM_RING(k, off) d[k] = lds8(c + (off)) * 0xFFFF0001u + kv
   SWM_RING(0, 3 * P);      SWM_RING(1, 3 * P + 1);   SWM_RING(2, 2 * P + 2);   SWM_RING(3, P + 3);
   SWM_RING(4, 3);          SWM_RING(5, -P + 3);      SWM_RING(6, -2 * P + 2);  SWM_RING(7, -3 * P + 1);
   SWM_RING(8, -3 * P);     SWM_RING(9, -3 * P - 1);  SWM_RING(10, -2 * P - 2); SWM_RING(11, -P - 3);
@@ -85,7 +100,7 @@ __device__ __forceinline__ int fast_score_x2(uint32_t c, int th, uint32_t zero) 
     const uint32_t m1 = __vimin3_u16x2(p3[k + 1], p3[(k + 4) & 15], p3[(k + 7) & 15]);
     best = __vimax3_u16x2(best, m0, m1);
   }
-  const int b = max((int)(best & 0xFFFFu), (int)(best >> 16));
+  const int b = max((int)(best & 0xFFFFu), (int)(best >> 16)) - 0x4000;
   return b > th ? b - 1 : 0;
 }
 
@@ -106,14 +121,13 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
   __shared__ __align__(128) uint8_t s_px[2][FT_ROWS * FT_PITCH];
   __shared__ __align__(16) uint8_t s_sc[FT_ROWS * FT_SCP];
   __shared__ uint16_t s_list[FT_LIST];
-  __shared__ uint32_t s_colmask[FT_QW];
+  __shared__ uint32_t s_colmask[2 * FT_QP];
   __shared__ uint8_t s_flag[3 * (kFT + 2)];
   __shared__ __align__(8) uint64_t s_bar[2];
   const FrameLayout* __restrict__ L = a.L;
   const int lane = threadIdx.x;
   const uint32_t lt = (1u << lane) - 1u;
   const int nrun = L->fblk_total;
-  const uint32_t zero = (uint32_t)(a.ini_th >> 31);  // 0 (thresholds are positive); opaque to the compiler
   const uint32_t px_u32 = smem_u32(s_px), sc_u32 = smem_u32(s_sc), bar_u32 = smem_u32(s_bar), list_u32 = smem_u32(s_list);
   if (lane == 0) {
     mbar_init(&s_bar[0], 1);
@@ -179,7 +193,7 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
       const int X0 = kEdge + 32 * (kFT * bx + j);   // first interior pixel (level coords); staged origin (X0-19, Y0-4)
       // score tile cleared; scored columns of each word: interior +- 1 px and level x in [19, w - 19)
       for (int i = lane; i < FT_ROWS * FT_SCP / 16; i += 32) reinterpret_cast<uint4*>(s_sc)[i] = make_uint4(0, 0, 0, 0);
-      if (lane < FT_QW) {
+      if (lane < 2 * FT_QP) {
         uint32_t m = 0;
         for (int k = 0; k < 4; k++) {
           const int lx = 4 * (FT_QW0 + lane) + k, gx = X0 - kFx + lx;
@@ -190,48 +204,55 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
       mbar_wait(&s_bar[buf], (phbits >> buf) & 1u);
       phbits ^= 1u << buf;
       __syncwarp();
-      const uint32_t* px = reinterpret_cast<const uint32_t*>(s_px[buf]);
       const uint32_t pxb = px_u32 + buf * (FT_ROWS * FT_PITCH);
 
-      // ---- packed quick reject on the scored region (interior + 1 px): rows ly 3..36, words 4..12; ballot compaction
+      // ---- packed quick reject on the scored region (interior + 1 px): rows ly 3..36, words 4..12.  An item is an
+      // aligned PAIR of words (8 pixels): 11 loads (LDS.64 for the pair, LDS.32 for its left / right neighbour) serve
+      // both words, all four opposite ring pairs are tested unconditionally (a warp hardly ever leaves early).
       int n_cand = 0;
 #pragma unroll 1
-      for (int it = 0; it < FT_IT; it++) {
+      for (int it = 0; it < FT_PIT; it++) {
         const int i = lane + 32 * it;
-        uint32_t m = 0;
-        int ly = 0, jw = 0;
-        if (i < FT_ITEMS) {
-          const int r = i / FT_QW;
-          jw = i - r * FT_QW;
+        uint32_t m0 = 0, m1 = 0;
+        int ly = 0, p = 0;
+        if (i < FT_PITEMS) {
+          const int r = i / FT_QP;
+          p = i - r * FT_QP;
           ly = r + 3;
           const int gy = Y0 - 4 + ly;
           if (gy >= kEdge && gy < h - kEdge) {
-            const uint32_t* row = px + ly * FT_WORDS + FT_QW0 + jw;
-            const uint32_t v = row[0];
-            m = (oob_mask(row[-3 * FT_WORDS], v, c7) | oob_mask(row[3 * FT_WORDS], v, c7)) & s_colmask[jw];
-            if (m) m &= oob_mask(__funnelshift_r(row[0], row[1], 24), v, c7) | oob_mask(__funnelshift_r(row[-1], row[0], 8), v, c7);
-            if (m) {
-              const uint32_t* rp = row + 2 * FT_WORDS;
-              const uint32_t* rm = row - 2 * FT_WORDS;
-              m &= oob_mask(__funnelshift_r(rp[0], rp[1], 16), v, c7) | oob_mask(__funnelshift_r(rm[-1], rm[0], 16), v, c7);
-              if (m) m &= oob_mask(__funnelshift_r(rm[0], rm[1], 16), v, c7) | oob_mask(__funnelshift_r(rp[-1], rp[0], 16), v, c7);
-            }
+            const uint32_t base = pxb + (uint32_t)(ly * FT_PITCH + 4 * FT_QW0 + 8 * p);  // first word of the pair
+            const uint2 c = lds64(base), cm3 = lds64(base - 3 * FT_PITCH), cp3 = lds64(base + 3 * FT_PITCH);
+            const uint2 cp = lds64(base + 2 * FT_PITCH), cm = lds64(base - 2 * FT_PITCH);
+            const uint32_t l0 = lds32s(base - 4), r0 = lds32s(base + 8);
+            const uint32_t lp = lds32s(base + 2 * FT_PITCH - 4), rp = lds32s(base + 2 * FT_PITCH + 8);
+            const uint32_t lm = lds32s(base - 2 * FT_PITCH - 4), rm = lds32s(base - 2 * FT_PITCH + 8);
+            const uint32_t v0 = c.x, v1 = c.y;
+            const uint32_t fpp = __funnelshift_r(cp.x, cp.y, 16), fmm = __funnelshift_r(cm.x, cm.y, 16);  // rows +2 / -2, between the words
+            m0 = (oob_bits(cm3.x, v0, c7) | oob_bits(cp3.x, v0, c7)) & s_colmask[2 * p];
+            m0 &= oob_bits(__funnelshift_r(v0, v1, 24), v0, c7) | oob_bits(__funnelshift_r(l0, v0, 8), v0, c7);
+            m0 &= oob_bits(fpp, v0, c7) | oob_bits(__funnelshift_r(lm, cm.x, 16), v0, c7);
+            m0 &= oob_bits(fmm, v0, c7) | oob_bits(__funnelshift_r(lp, cp.x, 16), v0, c7);
+            m1 = (oob_bits(cm3.y, v1, c7) | oob_bits(cp3.y, v1, c7)) & s_colmask[2 * p + 1];
+            m1 &= oob_bits(__funnelshift_r(v1, r0, 24), v1, c7) | oob_bits(__funnelshift_r(v0, v1, 8), v1, c7);
+            m1 &= oob_bits(__funnelshift_r(cp.y, rp, 16), v1, c7) | oob_bits(fmm, v1, c7);
+            m1 &= oob_bits(__funnelshift_r(cm.y, rm, 16), v1, c7) | oob_bits(fpp, v1, c7);
           }
         }
-        // survivors -> list: exclusive prefix of the per-lane counts (0..4) from three bit-plane ballots
-        const uint32_t cnt = (uint32_t)__popc(m);
+        // survivors -> list: exclusive prefix of the per-lane counts (0..8) from four bit-plane ballots
+        const uint32_t cnt = (uint32_t)(__popc(m0) + __popc(m1));
         const uint32_t b0 = __ballot_sync(0xffffffffu, cnt & 1u), b1 = __ballot_sync(0xffffffffu, cnt & 2u),
-                       b2 = __ballot_sync(0xffffffffu, cnt & 4u);
-        uint32_t addr = list_u32 + 2u * (uint32_t)(n_cand + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt));
-        const uint32_t e0 = (uint32_t)((ly << 8) | (4 * (FT_QW0 + jw)));
+                       b2 = __ballot_sync(0xffffffffu, cnt & 4u), b3 = __ballot_sync(0xffffffffu, cnt & 8u);
+        uint32_t addr = list_u32 + 2u * (uint32_t)(n_cand + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt));
+        const uint32_t e0 = (uint32_t)((ly << 8) | (4 * FT_QW0 + 8 * p));
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          if (m & (0x80u << (8 * k))) {
+        for (int k = 0; k < 8; k++) {
+          if ((k < 4 ? m0 : m1) & (0x80u << (8 * (k & 3)))) {
             sts16(addr, e0 + k);
             addr += 2;
           }
         }
-        n_cand += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+        n_cand += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
       }
       __syncwarp();
 
@@ -245,7 +266,7 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
         if (c < n_cand) {
           e = lds16(list_u32 + 2u * c);
           const int ly = e >> 8, lx = e & 255;
-          const int sc = fast_score_x2(pxb + (uint32_t)(ly * FT_PITCH + lx), th_run, zero);
+          const int sc = fast_score_x2(pxb + (uint32_t)(ly * FT_PITCH + lx), th_run);
           sts8(sc_u32 + (uint32_t)(ly * FT_SCP + lx - FT_SCX), (uint32_t)sc);
           q = sc >= (kPass == 1 ? a.ini_th : 1) && lx >= kFx && lx < kFx + 32 && ly >= 4 && ly < 36;
         }
