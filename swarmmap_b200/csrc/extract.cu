@@ -1,14 +1,14 @@
-// extract.cu -- B200 (sm_100a) ORB extractor: word-packed pyramid + border + Gaussian blur kernel,
-// FAST kernel (TMA-staged tiles, packed quick reject, 16x2-SIMD score, tile retry + non-max
-// suppression), block-parallel quadtree, orientation + rBRIEF, and the C ABI of the extractor
-// (include/swm_orb.h).  Batched over frames: every launch covers all frames of a batch, nothing
+// extract.cu -- B200 (sm_100a) ORB extractor: pyramid + border + Gaussian blur as a register-resident column walk
+// (pyr_walk.cuh), FAST with one warp per run of tiles (fast_tile.cuh: tensor-map TMA windows, packed quick reject,
+// 16x2-SIMD score, tile retry + non-max suppression), block-parallel quadtree, orientation + rBRIEF, and the C ABI of
+// the extractor (include/swm_orb.h).  Batched over frames: every launch covers all frames of a batch, nothing
 // returns to the host between stages.
 //
 // Reference behaviour restated (paths relative to /root/reference/code/):
 //   ORBextractor::operator()            src/ORBextractor.cc:746-819
 //   ORBextractor::ComputePyramid        src/ORBextractor.cc:821-855   (cv::resize INTER_LINEAR 8U semantics)
 //   ComputeKeyPointsOctTree             src/ORBextractor.cc:691-744
-//   tileCalcKeypoints_kernel            src/cuda/Fast_gpu.cu:284-341  (lock-step deterministic form, fast_kernel)
+//   tileCalcKeypoints_kernel            src/cuda/Fast_gpu.cu:284-341  (lock-step deterministic form, fast_tile.cuh)
 //   DistributeOctTree                   src/ORBextractor.cc:465-689   (octree_core.cuh)
 //   IC_Angle_kernel / addBorder_kernel  src/cuda/Fast_gpu.cu:403-471
 //   Gaussian 7x7 sigma 2                src/ORBextractor.cc:835,719,742 (cv::GaussianBlur 8U semantics)
@@ -34,19 +34,11 @@ namespace swm {
 __device__ float4 g_pattern[8 * 32];
 __constant__ int c_umax[16];
 
-// ---- mbarrier / TMA bulk-copy helpers (PTX ISA: mbarrier, cp.async.bulk)
+// ---- mbarrier helpers (PTX ISA: mbarrier); the TMA tile copies are issued in pyr_walk.cuh / fast_tile.cuh
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
   uint32_t done;
@@ -65,538 +57,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 #include "pyr_walk.cuh"
 #include "fast_tile.cuh"
 namespace swm {
-
-#ifndef SWM_PYR_TILED
-#define SWM_PYR_TILED 0  // 1: the round-1 shared-memory tile kernel (A/B baseline of pyr_walk.cuh)
-#endif
-// ------------------------------------------------------------------------------------------------
-// Pyramid kernel: one CTA produces a 64x32 tile of level l -- the un-blurred plane (plus the
-// mirrored border pixels that reflect into the tile) and the Gaussian-blurred plane.  Everything
-// is done on packed 32-bit words (4 pixels): level 0 copies the input frame; levels >= 1 stage the
-// needed window of level l-1 in shared memory and run cv::resize's separable fixed-point bilinear
-// (row pass once per SOURCE row, then the column pass).  The blur is column pass first on two
-// 16-bit lanes per register, then the row pass with IDP.2A dot products (exact: no intermediate
-// rounding in cv::GaussianBlur's 8-bit path, so pass order does not matter).
-// ------------------------------------------------------------------------------------------------
-constexpr int TW = 64, TH = 32;
-constexpr int PS_WORDS = 18;            // staged words per row: x0-4 .. x0+67
-constexpr int PS_COLS = PS_WORDS * 4;   // 72
-constexpr int PS_ROWS = TH + 6;         // y0-3 .. y0+34
-constexpr int SRC_ROWS = 62, SRC_WORDS = 30;  // level l-1 window of one tile, scale factor <= 1.5 (checked on the host)
-// The window is staged by TMA: one cp.async.bulk per source row, from a 16-byte aligned source x (the ROI origin of a
-// plane is 32-byte aligned and the pitch a multiple of 128), so a row holds up to 12 bytes of lead-in + 120 + tail.
-constexpr int SRC_PITCH = 144;
-#ifndef SWM_PYR_TMA
-#define SWM_PYR_TMA 1  // 0: stage the window with 16-byte __ldg loads instead (A/B switch, 2 % faster, profiles/README.md r2g)
-#endif
-
-
-#if SWM_PYR_TILED
-template <bool kFirst>
-__global__ void __launch_bounds__(256) pyr_kernel(const PyrArgs a) {
-  __shared__ __align__(16) uint32_t s_px[PS_ROWS * PS_WORDS];
-  __shared__ __align__(128) uint8_t s_src[kFirst ? 16 : SRC_ROWS * SRC_PITCH];
-  __shared__ __align__(8) uint64_t s_bar;
-  (void)s_bar;
-  __shared__ __align__(16) uint16_t s_h[kFirst ? 4 : SRC_ROWS * PS_COLS];
-  __shared__ __align__(16) uint2 s_v[TH * PS_WORDS];
-  __shared__ ResizeTap s_xt[kFirst ? 1 : PS_COLS];
-  __shared__ ResizeTap s_yt[kFirst ? 1 : PS_ROWS];
-  const int tid = threadIdx.x;
-  const int f = blockIdx.z;
-  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
-  const int w = a.dst.w, h = a.dst.h;
-  const long long fo = (long long)f * a.slab_bytes;
-  if (kFirst) {
-    // ---- level 0: copy the frame tile (+halo, reflect-101 at the image edge)
-    const uint8_t* src = a.img + (long long)f * a.img_frame_stride;
-    const bool aligned = ((reinterpret_cast<unsigned long long>(src) | (unsigned long long)a.img_stride) & 3ull) == 0;
-    for (int i = tid; i < PS_ROWS * PS_WORDS; i += 256) {
-      const int r = i / PS_WORDS, j = i - r * PS_WORDS;
-      const int gy = reflect101(min(y0 - 3 + r, h + 2), h);
-      const int gx = x0 - 4 + 4 * j;
-      const uint8_t* row = src + (long long)gy * a.img_stride;
-      uint32_t v;
-      if (aligned && gx >= 0 && gx + 3 < w) {
-        v = __ldg(reinterpret_cast<const uint32_t*>(row + gx));
-      } else {
-        v = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) v |= (uint32_t)__ldg(row + reflect101(min(gx + k, w + 2), w)) << (8 * k);
-      }
-      s_px[i] = v;
-    }
-  } else {
-    // ---- levels >= 1: bilinear resize of the un-blurred level l-1 (cv::resize INTER_LINEAR 8U)
-    const uint8_t* src = a.plain + fo + a.src.plane_off + (long long)kEdge * a.src.pitch + kPadX;
-    const int spitch = a.src.pitch, sh = a.src.h;
-    const ResizeTap* __restrict__ xt = a.xtab + a.dst.xtab_off;
-    const ResizeTap* __restrict__ yt = a.ytab + a.dst.ytab_off;
-    // taps of the staged columns/rows (reflected destination coordinates), window of level l-1
-    const int dlo = max(0, x0 - 4), dhi = min(w - 1, x0 + PS_COLS - 5);
-    const int rlo = max(0, y0 - 3), rhi = min(h - 1, y0 + PS_ROWS - 4);
-    const int sx_base = xt[dlo].ofs & ~15;  // 16-byte aligned: the row copies below are TMA bulk copies
-    const int sy_base = yt[rlo].ofs;
-    const int nbytes = (xt[dhi].ofs + 2 - sx_base + 15) & ~15;
-    const int nrows = min(yt[rhi].ofs + 1, sh - 1) - sy_base + 1;
-#if SWM_PYR_TMA
-    if (tid == 0) mbar_init(&s_bar, 1);
-    __syncthreads();
-    if (tid < 32) {
-      // warp 0: one cp.async.bulk per source row, all completing on one mbarrier (SASS: UBLKCP + SYNCS)
-      if (tid == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&s_bar, (uint32_t)(nrows * nbytes));
-      }
-      __syncwarp();
-      for (int r = tid; r < nrows; r += 32)
-        bulk_g2s(s_src + r * SRC_PITCH, src + (long long)(sy_base + r) * spitch + sx_base, (uint32_t)nbytes, &s_bar);
-    } else if (tid >= 64 && tid < 64 + PS_COLS) {
-#else
-    {  // 16-byte loads of the aligned window: 9 lanes per row, 28 rows per sweep
-      const int q = tid % 9, r0 = tid / 9;
-      if (r0 < 28 && 16 * q < nbytes)
-        for (int r = r0; r < nrows; r += 28)
-          *reinterpret_cast<uint4*>(s_src + r * SRC_PITCH + 16 * q) =
-              __ldg(reinterpret_cast<const uint4*>(src + (long long)(sy_base + r) * spitch + sx_base + 16 * q));
-    }
-    if (tid >= 64 && tid < 64 + PS_COLS) {
-#endif
-      ResizeTap t = xt[reflect101(min(x0 - 4 + (tid - 64), w + 2), w)];
-      t.ofs = (int16_t)(t.ofs - sx_base);
-      s_xt[tid - 64] = t;
-    } else if (tid >= 160 && tid < 160 + PS_ROWS) {
-      ResizeTap t = yt[reflect101(min(y0 - 3 + (tid - 160), h + 2), h)];
-      const int o0 = t.ofs - sy_base;
-      t.ofs = (int16_t)o0;
-      t.pad = (int16_t)min(o0 + 1, sh - 1 - sy_base);  // second source row, clamped like cv::resize
-      s_yt[tid - 160] = t;
-    }
-#if SWM_PYR_TMA
-    if (tid < 32) mbar_wait(&s_bar, 0);  // one warp polls the mbarrier, the rest park on the CTA barrier
-#endif
-    __syncthreads();
-    // row pass: one value per (source row, destination column), kept as (sum >> 4) in 16 bits.  (A four-columns-per-
-    // thread form -- three aligned word loads, a funnel shift per column, IDP.2A on 16-bit taps -- executes as many
-    // instructions once the per-column selects are counted and measured 12 % slower; profiles/README.md r2g.)
-    if (tid < 3 * PS_COLS) {
-      const int c = tid % PS_COLS, g = tid / PS_COLS;
-      const ResizeTap t = s_xt[c];
-      const uint8_t* sb = s_src + t.ofs;
-      for (int r = g; r < nrows; r += 3) {
-        const uint8_t* p = sb + r * SRC_PITCH;
-        s_h[r * PS_COLS + c] = (uint16_t)((p[0] * t.a0 + p[1] * t.a1) >> 4);
-      }
-    }
-    __syncthreads();
-    // column pass, 4 pixels per item: ((b0 * h0) >> 16) + ((b1 * h1) >> 16) + 2) >> 2 with the two products taken as
-    // the high words of (b << 16) * h (IMAD.HI with the +2 and the first product riding in the accumulator)
-    for (int i = tid; i < PS_ROWS * PS_WORDS; i += 256) {
-      const int r = i / PS_WORDS, j = i - r * PS_WORDS;
-      const ResizeTap t = s_yt[r];
-      const uint2 h0 = *reinterpret_cast<const uint2*>(s_h + t.ofs * PS_COLS + 4 * j);
-      const uint2 h1 = *reinterpret_cast<const uint2*>(s_h + t.pad * PS_COLS + 4 * j);
-      const uint32_t B0 = (uint32_t)t.a0 << 16, B1 = (uint32_t)t.a1 << 16;
-      const uint32_t p0 = (__umulhi(B1, h1.x & 0xFFFFu) + (__umulhi(B0, h0.x & 0xFFFFu) + 2u)) >> 2;
-      const uint32_t p1 = (__umulhi(B1, h1.x >> 16) + (__umulhi(B0, h0.x >> 16) + 2u)) >> 2;
-      const uint32_t p2 = (__umulhi(B1, h1.y & 0xFFFFu) + (__umulhi(B0, h0.y & 0xFFFFu) + 2u)) >> 2;
-      const uint32_t p3 = (__umulhi(B1, h1.y >> 16) + (__umulhi(B0, h0.y >> 16) + 2u)) >> 2;
-      s_px[i] = p0 | (p1 << 8) | (p2 << 16) | (p3 << 24);
-    }
-  }
-  __syncthreads();
-
-  const long long roi0 = fo + a.dst.plane_off + (long long)kEdge * a.dst.pitch + kPadX;
-  uint8_t* dplain = a.plain + roi0;
-  uint8_t* dblur = a.blur + roi0;
-  const int pitch = a.dst.pitch;
-
-  // ---- un-blurred tile and the border rows that mirror into it
-#pragma unroll
-  for (int pass = 0; pass < 2; pass++) {
-    const int r = (tid >> 4) + 16 * pass, j = tid & 15;
-    const int gy = y0 + r, gx = x0 + 4 * j;
-    if (gy < h && gx < w) {
-      const uint32_t word = s_px[(r + 3) * PS_WORDS + j + 1];
-      store4(dplain + (long long)gy * pitch, gx, w, word);
-      // copyMakeBorder(BORDER_REFLECT_101, 19), rows: an in-image row within 19 px of the top / bottom edge
-      // is also the border row that reflects onto it (ORBextractor.cc:846-851) -> same word, mirrored row.
-      if (gy >= 1 && gy <= kEdge) store4(dplain + (long long)(-gy) * pitch, gx, w, word);
-      if (gy >= h - 1 - kEdge && gy <= h - 2) store4(dplain + (long long)(2 * (h - 1) - gy) * pitch, gx, w, word);
-    }
-  }
-  // copyMakeBorder, columns: only tiles that hold x in [1,19] or [w-20,w-2] take part; each such pixel is
-  // written to its mirrored column, in its own row and in that row's mirrored rows (the corners).
-  {
-    const int lo0 = max(x0, 1), hi0 = min(x0 + TW - 1, kEdge);                  // left strip sources
-    const int lo1 = max(x0, w - 1 - kEdge), hi1 = min(x0 + TW - 1, w - 2);      // right strip sources
-    const int n0 = max(hi0 - lo0 + 1, 0), n1 = max(hi1 - lo1 + 1, 0);
-    const int ncols = n0 + n1;
-    if (ncols > 0) {
-      const uint8_t* s_pxb = reinterpret_cast<const uint8_t*>(s_px);
-      for (int i = tid; i < TH * ncols; i += 256) {
-        const int r = i / ncols, ci = i - r * ncols;
-        const int gy = y0 + r;
-        if (gy >= h) break;
-        const int x = ci < n0 ? lo0 + ci : lo1 + (ci - n0);
-        const int dx = ci < n0 ? -x : 2 * (w - 1) - x;
-        const uint8_t v = s_pxb[(r + 3) * PS_COLS + (x - x0) + 4];
-        dplain[(long long)gy * pitch + dx] = v;
-        if (gy >= 1 && gy <= kEdge) dplain[(long long)(-gy) * pitch + dx] = v;
-        if (gy >= h - 1 - kEdge && gy <= h - 2) dplain[(long long)(2 * (h - 1) - gy) * pitch + dx] = v;
-      }
-    }
-  }
-
-  // ---- blur, column pass: thread = (word column, group of 4 output rows); two pixels per register
-  if (tid < PS_WORDS * 8) {
-    const int j = tid % PS_WORDS, g = tid / PS_WORDS;
-    uint32_t e[10], o[10];
-#pragma unroll
-    for (int k = 0; k < 10; k++) {
-      const uint32_t wv = s_px[(4 * g + k) * PS_WORDS + j];
-      e[k] = wv & 0x00FF00FFu;
-      o[k] = (wv >> 8) & 0x00FF00FFu;
-    }
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-      const uint32_t ve = 18u * (e[i] + e[i + 6]) + 34u * (e[i + 1] + e[i + 5]) + 48u * (e[i + 2] + e[i + 4]) + 56u * e[i + 3];
-      const uint32_t vo = 18u * (o[i] + o[i + 6]) + 34u * (o[i + 1] + o[i + 5]) + 48u * (o[i + 2] + o[i + 4]) + 56u * o[i + 3];
-      // lanes: ve = (V0, V2), vo = (V1, V3) -> adjacent pairs (V0,V1), (V2,V3)
-      s_v[(4 * g + i) * PS_WORDS + j] = make_uint2(__byte_perm(ve, vo, 0x5410), __byte_perm(ve, vo, 0x7632));
-    }
-  }
-  __syncthreads();
-
-  // ---- blur, row pass: 4 outputs per item from the pairs of words j-1, j, j+1
-#pragma unroll
-  for (int pass = 0; pass < 2; pass++) {
-    const int r = (tid >> 4) + 16 * pass, j = (tid & 15) + 1;
-    const int gy = y0 + r, gx = x0 + 4 * (j - 1);
-    if (gy < h && gx < w) {
-      const uint2 A = s_v[r * PS_WORDS + j - 1], Bm = s_v[r * PS_WORDS + j], Cn = s_v[r * PS_WORDS + j + 1];
-      // V index relative to the first pixel of word j: A = (-4,-3),(-2,-1); Bm = (0,1),(2,3); Cn = (4,5),(6,7)
-      const uint32_t m3m2 = __byte_perm(A.x, A.y, 0x5432);    // (-3,-2)
-      const uint32_t m1p0 = __byte_perm(A.y, Bm.x, 0x5432);   // (-1, 0)
-      const uint32_t p1p2 = __byte_perm(Bm.x, Bm.y, 0x5432);  // ( 1, 2)
-      const uint32_t p3p4 = __byte_perm(Bm.y, Cn.x, 0x5432);  // ( 3, 4)
-      const uint32_t p5p6 = __byte_perm(Cn.x, Cn.y, 0x5432);  // ( 5, 6)
-      const uint32_t k01 = 18u | (34u << 8), k23 = 48u | (56u << 8), k45 = 48u | (34u << 8), k6 = 18u;
-      uint32_t o0 = __dp2a_lo(m3m2, k01, 0x8000u);
-      o0 = __dp2a_lo(m1p0, k23, o0);
-      o0 = __dp2a_lo(p1p2, k45, o0);
-      o0 = __dp2a_lo(p3p4, k6, o0);
-      uint32_t o1 = __dp2a_lo(A.y, k01, 0x8000u);
-      o1 = __dp2a_lo(Bm.x, k23, o1);
-      o1 = __dp2a_lo(Bm.y, k45, o1);
-      o1 = __dp2a_lo(Cn.x, k6, o1);
-      uint32_t o2 = __dp2a_lo(m1p0, k01, 0x8000u);
-      o2 = __dp2a_lo(p1p2, k23, o2);
-      o2 = __dp2a_lo(p3p4, k45, o2);
-      o2 = __dp2a_lo(p5p6, k6, o2);
-      uint32_t o3 = __dp2a_lo(Bm.x, k01, 0x8000u);
-      o3 = __dp2a_lo(Bm.y, k23, o3);
-      o3 = __dp2a_lo(Cn.x, k45, o3);
-      o3 = __dp2a_lo(Cn.y, k6, o3);
-      const uint32_t word = (o0 >> 16) | ((o1 >> 16) << 8) | ((o2 >> 16) << 16) | ((o3 >> 16) << 24);
-      store4(dblur + (long long)gy * pitch, gx, w, word);
-    }
-  }
-}
-
-#endif  // SWM_PYR_TILED
-
-#ifndef SWM_FAST_BLOCK
-#define SWM_FAST_BLOCK 0  // 1: the round-1 256-thread block kernel (A/B baseline of fast_tile.cuh)
-#endif
-#if SWM_FAST_BLOCK
-// ------------------------------------------------------------------------------------------------
-// FAST kernel (Fast_gpu.cu:284-341, deterministic lock-step form).  One CTA = two horizontally
-// adjacent 32x32 FAST tiles of one level, anchored on the reference's tile grid (level pixel
-// (19,19)).  The tile (+4 px halo) is staged as words; a packed-byte test of the four opposite
-// ring pairs rejects most pixels 4 at a time (exact: every 9-arc contains one pixel of each pair);
-// survivors are compacted into a shared list, scored (largest threshold at which the pixel is
-// still a corner) and non-max suppressed against the shared score tile.
-//   pass 1: keypoint iff S_hi(p) > S_hi(q) for the 8 neighbours; a tile with no pass-1 keypoint
-//           is flagged for retry;
-//   pass 2 (blocks with a retry tile): keypoint iff S(p) > S_eff(q), S_eff = S in retried tiles,
-//           S_hi elsewhere.  Scores are recomputed, no score map is kept in HBM (debug builds of
-//           the tests can ask for one).
-// Survivors are appended (unordered) to the per-(frame, level) candidate list; everything
-// downstream orders by explicit keys, so the append order does not matter.
-// ------------------------------------------------------------------------------------------------
-// One CTA = kFT horizontally adjacent 32x32 FAST tiles (FB_W = 128 pixels).  Staged tile: 160 x 40 bytes whose
-// first column is level x = FB_W*bx, i.e. 16-byte aligned in the plane, so every row is one TMA bulk copy
-// (cp.async.bulk, 160 B) completing on an mbarrier.  Local column of the first interior pixel
-// (level x = 19 + FB_W bx) is kFx = 19; local row of the first interior row is 4.
-constexpr int FB_W = 32 * kFT;
-constexpr int FS_WORDS = 40, FS_COLS = FS_WORDS * 4, FS_ROWS = TH + 8;
-constexpr int FS_SW = FB_W / 4 + 1;                  // words per row that hold scored pixels (local x 18 .. 19+FB_W)
-constexpr int FS_ITEMS = 34 * FS_SW;                // quick-reject word items per CTA
-constexpr int FS_IT = (FS_ITEMS + 255) / 256;
-constexpr int FS_MAXCAND = (FB_W + 2) * 34;
-static_assert(kFx + FB_W + 4 <= FS_COLS && 4 + FS_SW <= FS_WORDS - 1, "staged tile too narrow");
-
-__device__ __forceinline__ uint32_t oob_mask_blk(uint32_t a, uint32_t v, uint32_t c7) {
-  // bit 7 of each byte set iff |a - v| > th, with c7 = (127 - th) * 0x01010101
-  const uint32_t ad = __vabsdiffu4(a, v);
-  return (((ad & 0x7F7F7F7Fu) + c7) | ad) & 0x80808080u;
-}
-
-// FAST score on two 16-bit lanes per register: lane 0 = bright ring max(r - v, 0), lane 1 = dark ring
-// max(v - r, 0); sliding 9-minimum by doubling with VIMNMX(3).U16x2, maximum over the 16 arcs.
-// Same value as swm::fast_score (swm_core.cuh) without its early-outs; checked bit-exact on the device
-// by the parity tests (the ptxas negated-max hazard does not apply: nothing is negated after a min/max).
-__device__ __forceinline__ int fast_score_blk(const uint8_t* c, int pitch, int th) {
-  const int v = c[0];
-  const uint32_t nv = ((uint32_t)(-v) & 0xFFFFu) | ((uint32_t)v << 16);  // (-v, +v)
-  uint32_t d[16];
-#define SWM_RING(k, off) d[k] = __viaddmax_s16x2((uint32_t)c[off] * 0xFFFF0001u, nv, 0u)  // (r,-r)+(-v,v), clamp 0
-  SWM_RING(0, 3 * pitch);      SWM_RING(1, 3 * pitch + 1);   SWM_RING(2, 2 * pitch + 2);   SWM_RING(3, pitch + 3);
-  SWM_RING(4, 3);              SWM_RING(5, -pitch + 3);      SWM_RING(6, -2 * pitch + 2);  SWM_RING(7, -3 * pitch + 1);
-  SWM_RING(8, -3 * pitch);     SWM_RING(9, -3 * pitch - 1);  SWM_RING(10, -2 * pitch - 2); SWM_RING(11, -pitch - 3);
-  SWM_RING(12, -3);            SWM_RING(13, pitch - 3);      SWM_RING(14, 2 * pitch - 2);  SWM_RING(15, 3 * pitch - 1);
-#undef SWM_RING
-  uint32_t p2[16], p4[16];
-#pragma unroll
-  for (int k = 0; k < 16; k++) p2[k] = __vminu2(d[k], d[(k + 1) & 15]);
-#pragma unroll
-  for (int k = 0; k < 16; k++) p4[k] = __vminu2(p2[k], p2[(k + 2) & 15]);
-  uint32_t best = 0;
-#pragma unroll
-  for (int k = 0; k < 16; k += 2) {
-    const uint32_t m0 = __vimin3_u16x2(p4[k], p4[(k + 4) & 15], d[(k + 8) & 15]);
-    const uint32_t m1 = __vimin3_u16x2(p4[k + 1], p4[(k + 5) & 15], d[(k + 9) & 15]);
-    best = __vimax3_u16x2(best, m0, m1);
-  }
-  const int b = max((int)(best & 0xFFFFu), (int)(best >> 16));
-  return b > th ? b - 1 : 0;
-}
-
-__global__ void __launch_bounds__(256, 3) fast_kernel(const FrameLayout* __restrict__ L, const uint8_t* __restrict__ plain,
-                                                      const int4* __restrict__ fblk_desc, int ini_th, int min_th, int pass,
-                                                      uint8_t* __restrict__ retry, int* __restrict__ retry_list,
-                                                      uint32_t* __restrict__ cand,
-                                                      int* __restrict__ cand_count, uint8_t* __restrict__ dbg_score) {
-  __shared__ __align__(16) uint32_t s_px[FS_ROWS * FS_WORDS];
-  __shared__ __align__(16) uint32_t s_sc[FS_ROWS * FS_WORDS];
-  __shared__ uint16_t s_list[FS_MAXCAND + 2];
-  __shared__ uint16_t s_list2[FB_W * TH + 2];
-  __shared__ uint32_t s_colmask[FS_WORDS];
-  __shared__ int s_warp[8];
-  __shared__ int s_total, s_n2, s_blk;
-  __shared__ int s_any[kFT];
-  __shared__ uint8_t s_flag[3 * (kFT + 2)];
-  __shared__ __align__(8) uint64_t s_bar;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int nblk = L->fblk_total;
-  uint32_t bar_phase = 0;
-  if (tid == 0) mbar_init(&s_bar, 1);
-  __syncthreads();
-  // pass 1: one block per (frame, tile pair).  pass 2: a persistent grid walks the list of blocks that
-  // hold a retry tile (appended by pass 1), so the common "nothing to retry" case costs almost nothing.
-  for (int work = blockIdx.x;; work += gridDim.x) {
-    int fb;
-    if (pass == 1) {
-      if (work != (int)blockIdx.x) break;
-      fb = blockIdx.y * nblk + blockIdx.x;
-    } else {
-      __syncthreads();
-      if (tid == 0) s_blk = work < retry_list[0] ? retry_list[1 + work] : -1;
-      __syncthreads();
-      fb = s_blk;
-      if (fb < 0) break;
-    }
-    const int f = pass == 1 ? (int)blockIdx.y : fb / nblk;
-    const int blk = fb - f * nblk;
-    const int4 bd = __ldg(&fblk_desc[blk]);  // (level, bx, by, -) of this block, built on the host
-    const int lvl = bd.x, bx = bd.y, by = bd.z;
-    const LevelGeom& g = L->lv[lvl];
-    uint8_t* fretry = retry + (long long)f * L->tiles_total + g.tile_off;
-    const int t0 = by * g.tiles_x + kFT * bx;  // first of this block's tiles
-    const int ntile = min(kFT, g.tiles_x - kFT * bx);
-    const int w = g.w, h = g.h;
-    const int X0 = kEdge + FB_W * bx, Y0 = kEdge + 32 * by;  // first interior pixel (level coords)
-    const int sx0 = X0 - kFx, sy0 = Y0 - 4;                // staged origin; sx0 = FB_W bx is 16-byte aligned
-    if (pass == 2 && tid < 3 * (kFT + 2)) {
-      const int ny = by + tid / (kFT + 2) - 1, nx = kFT * bx + tid % (kFT + 2) - 1;
-      s_flag[tid] = (ny >= 0 && ny < g.tiles_y && nx >= 0 && nx < g.tiles_x) ? fretry[ny * g.tiles_x + nx] : 0;
-    }
-    if (tid < kFT) s_any[tid] = 0;
-    if (tid == kFT) s_n2 = 0;
-    if (tid >= 32 && tid < 32 + FS_WORDS) {
-      // per-word byte mask of the columns that are scored: interior +- 1 px and level x in [19, w-19)
-      const int jw = tid - 32;
-      const int lo = max(kFx - 1, kEdge - sx0), hi = min(kFx + FB_W, w - kEdge - 1 - sx0);
-      uint32_t m = 0;
-      for (int k = 0; k < 4; k++)
-        if (4 * jw + k >= lo && 4 * jw + k <= hi) m |= 0x80u << (8 * k);
-      s_colmask[jw] = m;
-    }
-    const uint8_t* roi = plain + (long long)f * L->slab_bytes + g.plane_off + (long long)kEdge * g.pitch + kPadX;
-    uint8_t* s_scb = reinterpret_cast<uint8_t*>(s_sc);
-    const uint8_t* s_pxb = reinterpret_cast<const uint8_t*>(s_px);
-
-    // ---- stage 96 x 40 bytes: warp 0 issues one TMA bulk copy per row (rows past the plane are skipped: only
-    // pixels outside the FAST band could read them, and those are masked), the others clear the score tile.
-    if (wid == 0) {
-      const int nrows = min(FS_ROWS, h + kEdge - sy0);
-      if (lane == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&s_bar, (uint32_t)nrows * FS_COLS);
-      }
-      __syncwarp();
-      for (int r = lane; r < nrows; r += 32)
-        bulk_g2s(s_px + r * FS_WORDS, roi + (long long)(sy0 + r) * g.pitch + sx0, FS_COLS, &s_bar);
-    }
-    for (int i = tid; i < FS_ROWS * FS_WORDS; i += 256) s_sc[i] = 0;
-    if (wid == 0) mbar_wait(&s_bar, bar_phase);  // one warp polls the mbarrier, the rest park on the CTA barrier
-    bar_phase ^= 1;
-    __syncthreads();
-
-    // Pass 1 only ever uses S_hi (scores below iniThFAST count as 0), so it detects at iniThFAST: same
-    // keypoints, a fraction of the candidates.  Pass 2 (and the debug score map) need S at minThFAST.
-    const int th_run = (pass == 1 && dbg_score == nullptr) ? ini_th : min_th;
-    // ---- packed quick reject on the scored region (interior + 1 px): rows ly 3..36, words 4..4+FS_SW-1
-    const uint32_t c7 = (uint32_t)(127 - th_run) * 0x01010101u;
-    uint32_t masks[FS_IT];
-    int n_mine = 0;
-#pragma unroll
-    for (int it = 0; it < FS_IT; it++) {
-      const int i = tid + 256 * it;
-      uint32_t m = 0;
-      if (i < FS_ITEMS) {
-        const int r = i / FS_SW, ly = r + 3, jw = i - r * FS_SW + 4;
-        const int gy = sy0 + ly;
-        if (gy >= kEdge && gy < h - kEdge) {
-          const uint32_t* row = s_px + ly * FS_WORDS + jw;
-          const uint32_t v = row[0];
-          m = (oob_mask_blk(row[-3 * FS_WORDS], v, c7) | oob_mask_blk(row[3 * FS_WORDS], v, c7)) & s_colmask[jw];
-          if (m) m &= oob_mask_blk(__funnelshift_r(row[0], row[1], 24), v, c7) | oob_mask_blk(__funnelshift_r(row[-1], row[0], 8), v, c7);
-          if (m) {
-            const uint32_t* rp = row + 2 * FS_WORDS;
-            const uint32_t* rm = row - 2 * FS_WORDS;
-            m &= oob_mask_blk(__funnelshift_r(rp[0], rp[1], 16), v, c7) | oob_mask_blk(__funnelshift_r(rm[-1], rm[0], 16), v, c7);
-            if (m) m &= oob_mask_blk(__funnelshift_r(rm[0], rm[1], 16), v, c7) | oob_mask_blk(__funnelshift_r(rp[-1], rp[0], 16), v, c7);
-          }
-        }
-      }
-      masks[it] = m;
-      n_mine += __popc(m);
-    }
-    // block-wide exclusive scan of the per-thread candidate counts
-    int incl = n_mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_warp[wid] = incl;
-    __syncthreads();
-    if (tid == 0) {
-      int run = 0;
-      for (int k = 0; k < 8; k++) {
-        const int v = s_warp[k];
-        s_warp[k] = run;
-        run += v;
-      }
-      s_total = run;
-    }
-    __syncthreads();
-    int pos = s_warp[wid] + incl - n_mine;
-#pragma unroll
-    for (int it = 0; it < FS_IT; it++) {
-      const uint32_t m = masks[it];
-      if (m) {
-        const int i = tid + 256 * it;
-        const int r = i / FS_SW, ly = r + 3, jw = i - r * FS_SW + 4;
-#pragma unroll
-        for (int k = 0; k < 4; k++)
-          if (m & (0x80u << (8 * k))) s_list[pos++] = (uint16_t)((ly << 8) | (4 * jw + k));
-      }
-    }
-    __syncthreads();
-    const int n_cand = s_total;
-
-    // ---- score the survivors; those that can be keypoints go on a second, much shorter list
-    for (int i = tid; i < n_cand; i += 256) {
-      const int e = s_list[i];
-      const int ly = e >> 8, lx = e & 255;
-      const int sc = fast_score_blk(s_pxb + ly * FS_COLS + lx, FS_COLS, th_run);
-      s_scb[ly * FS_COLS + lx] = (uint8_t)sc;
-      if (sc >= (pass == 1 ? ini_th : 1) && lx >= kFx && lx < kFx + FB_W && ly >= 4 && ly <= 35 &&
-          (pass == 1 || s_flag[(kFT + 2) + 1 + ((lx - kFx) >> 5)] != 0))
-        s_list2[atomicAdd(&s_n2, 1)] = (uint16_t)e;
-    }
-    __syncthreads();
-    const int n2 = s_n2;
-
-    // ---- non-max suppression (strict, 8 neighbours) of the short list
-    for (int i0 = 0; i0 < n2; i0 += 256) {
-      const int i = i0 + tid;
-      bool kp = false;
-      int lx = 0, ly = 0, c = 0;
-      if (i < n2) {
-        const int e = s_list2[i];
-        ly = e >> 8;
-        lx = e & 255;
-        const uint8_t* sp = s_scb + ly * FS_COLS + lx;
-        c = sp[0];
-        kp = true;
-#pragma unroll
-        for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
-          for (int dx = -1; dx <= 1; dx++) {
-            if (dx == 0 && dy == 0) continue;
-            int q = sp[dy * FS_COLS + dx];
-            bool raw = false;
-            if (pass == 2) {
-              const int qx = lx + dx, qy = ly + dy;
-              const int fy = qy < 4 ? 0 : (qy > 35 ? 2 : 1);
-              const int fx = qx < kFx ? 0 : 1 + ((qx - kFx) >> 5);
-              raw = s_flag[fy * (kFT + 2) + fx] != 0;
-            }
-            if (!raw && q < ini_th) q = 0;
-            kp = kp && c > q;
-          }
-        if (kp && pass == 1) s_any[(lx - kFx) >> 5] = 1;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, kp);
-      if (m) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(cand_count + f * L->nlevels + lvl, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (kp) {
-          const int idx = base + __popc(m & ((1u << lane) - 1));
-          if (idx < g.cand_cap)
-            cand[(long long)f * L->cand_total + g.cand_off + idx] = pack_pt(sx0 + lx - kBand, sy0 + ly - kBand, c);
-        }
-      }
-    }
-    if (pass == 1) {
-      __syncthreads();
-      if (tid == 0) {
-        int any_retry = 0;
-        for (int j = 0; j < ntile; j++) {
-          const int rj = s_any[j] ? 0 : 1;
-          fretry[t0 + j] = (uint8_t)rj;
-          any_retry |= rj;
-        }
-        if (any_retry) retry_list[1 + atomicAdd(retry_list, 1)] = fb;  // pass 2 re-runs only these blocks
-      }
-      if (dbg_score) {  // parity introspection only: the score map S at minThFAST for the block interior
-        uint8_t* sc = dbg_score + (long long)f * L->slab_bytes + g.plane_off + (long long)kEdge * g.pitch + kPadX;
-        for (int i = tid; i < FB_W * 32; i += 256) {
-          const int ly = (i / FB_W) + 4, lx = (i % FB_W) + kFx;
-          const int gx = sx0 + lx, gy = sy0 + ly;
-          if (gx < w - kEdge && gy < h - kEdge) sc[(long long)gy * g.pitch + gx] = s_scb[ly * FS_COLS + lx];
-        }
-      }
-    }
-  }
-}
-
-#endif  // SWM_FAST_BLOCK
 
 // ------------------------------------------------------------------------------------------------
 // Quadtree: one CTA per (level, frame).
@@ -998,20 +458,6 @@ int setup_geometry(swm_orb* h, int w, int hh) {
       }
       if (!ok) { h->err = "scale factor too large for the pyramid kernel"; return SWM_E_INVALID; }
     }
-#if SWM_PYR_TILED
-    if (l > 0) {  // the source window of every 64x32 tile must fit the kernel's shared-memory staging
-      const ResizeTap* xt0 = xt.data() + g.xtab_off;
-      const ResizeTap* yt0 = yt.data() + g.ytab_off;
-      for (int x0 = 0; x0 < g.w; x0 += TW) {
-        const int dlo = std::max(0, x0 - 4), dhi = std::min(g.w - 1, x0 + PS_COLS - 5);
-        if (((xt0[dhi].ofs + 1 - (xt0[dlo].ofs & ~3)) >> 2) + 1 > SRC_WORDS) { h->err = "scale factor too large for the pyramid tile"; return SWM_E_INVALID; }
-      }
-      for (int y0 = 0; y0 < g.h; y0 += TH) {
-        const int rlo = std::max(0, y0 - 3), rhi = std::min(g.h - 1, y0 + PS_ROWS - 4);
-        if (yt0[rhi].ofs + 2 - yt0[rlo].ofs > SRC_ROWS) { h->err = "scale factor too large for the pyramid tile"; return SWM_E_INVALID; }
-      }
-    }
-#endif
     g.tiles_x = (g.w - 2 * kEdge + 31) / 32;
     g.tiles_y = (g.h - 2 * kEdge + 31) / 32;
     g.tile_off = tile_off;
@@ -1142,12 +588,6 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
       a.xtab = h->d_xtab;
       a.ytab = h->d_ytab;
       a.src_map = h->d_maps + (l ? l - 1 : 0);
-#if SWM_PYR_TILED
-      a.strip_lanes = a.nstrips = a.rows_per_job = a.nrb = 0;
-      dim3 grid((a.dst.w + TW - 1) / TW, (a.dst.h + TH - 1) / TH, batch);
-      if (l == 0) pyr_kernel<true><<<grid, 256, 0, st>>>(a);
-      else pyr_kernel<false><<<grid, 256, 0, st>>>(a);
-#else
       // one warp per (strip of <= 120 columns of the bordered row, block of rows).  Row blocks are as long as the
       // batch allows while the level still fills the GPU about twice over (the 8-row blur warm-up is amortised over
       // 64 rows for large batches; a single frame gets 16-row blocks and several hundred warps per level).
@@ -1162,7 +602,6 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
       dim3 grid(a.nstrips, a.nrb, batch);
       if (l == 0) pyr_walk_kernel<true><<<grid, 32, 0, st>>>(a);
       else pyr_walk_kernel<false><<<grid, 32, 0, st>>>(a);
-#endif
       launches++;
     }
   }
@@ -1171,7 +610,6 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
     SWM_CK(h, cudaMemsetAsync(h->d_retry_list, 0, sizeof(int), st));
     dim3 grid(L.fblk_total, batch);
     uint8_t* dbg = h->debug_score ? h->d_score : nullptr;
-#if !SWM_FAST_BLOCK
     FastArgs fa;
     fa.L = h->d_lay;
     fa.maps = h->d_fmaps;
@@ -1186,12 +624,6 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
     fast_tile_kernel<1><<<grid, 32, 0, st>>>(fa);
     fa.dbg_score = nullptr;
     fast_tile_kernel<2><<<h->n_sm * 24, 32, 0, st>>>(fa);
-#else
-    fast_kernel<<<grid, 256, 0, st>>>(h->d_lay, h->d_plain, h->d_fblk, h->cfg.ini_th_fast, h->cfg.min_th_fast, 1,
-                                      h->d_retry, h->d_retry_list, h->d_cand, d_cand_count, dbg);
-    fast_kernel<<<h->n_sm * 3, 256, 0, st>>>(h->d_lay, h->d_plain, h->d_fblk, h->cfg.ini_th_fast, h->cfg.min_th_fast, 2,
-                                             h->d_retry, h->d_retry_list, h->d_cand, d_cand_count, nullptr);
-#endif
     launches += 2;
   }
   if (mask & SWM_STAGE_OCTREE) {

@@ -7,8 +7,9 @@
 //   ComputeKeyPointsOctTree    src/ORBextractor.cc:691-744   (iniThFAST first, minThFAST where a tile found nothing)
 //
 // A CTA is ONE warp that walks a horizontal run of up to kFT tiles of one level.  Per tile:
-//   * the 64 x 40 byte window (tile + 4 px halo, 16-byte aligned start) arrives by ONE tensor-map TMA copy (cp.async.bulk.tensor.3d,
-//     UTMALDG in SASS) into a double buffer: the next tile's copy is in flight while this one is processed;
+//   * the 80 x 40 byte window (tile + 4 px halo, 16-byte aligned start) arrives by ONE tensor-map TMA copy
+//     (cp.async.bulk.tensor.3d, UTMALDG in SASS); the next tile's copy is issued as soon as the scores of this one are
+//     done and lands while it is non-max suppressed (a second window buffer measured slower: fewer warps per SM);
 //   * packed quick reject, 8 pixels (an aligned word pair) per item: the four opposite ring pairs with VABSDIFF4 + carry-trick band test
 //     (exact: every 9-arc holds one pixel of each pair); survivors are compacted with warp ballots (no block scan);
 //   * survivors are scored on two 16-bit lanes (bright ring, dark ring): three-wide minima, then minima of three of
@@ -24,15 +25,19 @@
 namespace swm {
 
 constexpr int kFT = 4;                       // tiles per run (one warp)
-// Staged window: 64 x 40 bytes from level (X0 - 19, Y0 - 4), X0 - 19 = 32 * tile: the TMA needs a 16-byte aligned start
+// Staged window: FT_PITCH x 40 bytes from level (X0 - 19, Y0 - 4), X0 - 19 = 32 * tile: the TMA needs a 16-byte aligned start
 // (an unaligned first coordinate faults), so the first interior pixel sits at local (kFx, 4) = (19, 4).
 #ifndef SWM_FT_PITCH
-#define SWM_FT_PITCH 64
+#define SWM_FT_PITCH 80  // 80: rows land 20 banks apart, fewer shared-memory conflicts than 64 (0.727 vs 0.741 ms); the window needs 56
 #endif
 constexpr int FT_PITCH = SWM_FT_PITCH, FT_ROWS = 40, kFx = 19;
 constexpr int FT_WORDS = FT_PITCH / 4;
 constexpr int FT_QW0 = 4, FT_QW = 9;         // words per row that hold scored pixels (local x 18 .. 51): words 4 .. 12
 constexpr int FT_SCP = 48, FT_SCX = 16;      // score tile: pitch and the local x of its column 0
+#ifndef SWM_FT_BUFS
+#define SWM_FT_BUFS 1  // 1: single window buffer, the next tile's copy starts when the scores are done: more warps per SM (0.741 vs 0.765 ms); 2: double buffer
+#endif
+constexpr int FT_BUFS = SWM_FT_BUFS;
 constexpr int FT_QP = 5;                     // quick-reject items per row: the aligned word pairs (4,5) .. (12,13)
 constexpr int FT_PITEMS = 34 * FT_QP;        // items per tile (rows 3 .. 36)
 constexpr int FT_PIT = (FT_PITEMS + 31) / 32;
@@ -84,7 +89,7 @@ __device__ __forceinline__ int fast_score_x2(uint32_t c, int th) {
   const uint32_t v = lds8(c);
   const uint32_t kv = (0x4000u - v) | ((0x4000u + v) << 16);
   uint32_t d[16];
-#define SWM_RING(k, off) d[k] = lds8(c + (off)) * 0xFFFF0001u + kv
+#define SWM_RING(k, off) d[k] = lds8(c + (uint32_t)(off)) * 0xFFFF0001u + kv
   SWM_RING(0, 3 * P);      SWM_RING(1, 3 * P + 1);   SWM_RING(2, 2 * P + 2);   SWM_RING(3, P + 3);
   SWM_RING(4, 3);          SWM_RING(5, -P + 3);      SWM_RING(6, -2 * P + 2);  SWM_RING(7, -3 * P + 1);
   SWM_RING(8, -3 * P);     SWM_RING(9, -3 * P - 1);  SWM_RING(10, -2 * P - 2); SWM_RING(11, -P - 3);
@@ -118,7 +123,7 @@ struct FastArgs {
 
 template <int kPass>
 __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
-  __shared__ __align__(128) uint8_t s_px[2][FT_ROWS * FT_PITCH];
+  __shared__ __align__(128) uint8_t s_px[FT_BUFS][FT_ROWS * FT_PITCH];
   __shared__ __align__(16) uint8_t s_sc[FT_ROWS * FT_SCP];
   __shared__ uint16_t s_list[FT_LIST];
   __shared__ uint32_t s_colmask[2 * FT_QP];
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
     while (j < ntile) {
       const int jn = active(j + 1);
       __syncwarp();  // every lane is done with the other buffer (tile before this one)
-      if (jn < ntile) issue(jn, buf ^ 1);
+      if (FT_BUFS == 2 && jn < ntile) issue(jn, buf ^ 1);
       const int X0 = kEdge + 32 * (kFT * bx + j);   // first interior pixel (level coords); staged origin (X0-19, Y0-4)
       // score tile cleared; scored columns of each word: interior +- 1 px and level x in [19, w - 19)
       for (int i = lane; i < FT_ROWS * FT_SCP / 16; i += 32) reinterpret_cast<uint4*>(s_sc)[i] = make_uint4(0, 0, 0, 0);
@@ -277,6 +282,7 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
       }
       __syncwarp();
 
+      if (FT_BUFS == 1 && jn < ntile) issue(jn, 0);  // the window is no longer read (the score loop ended with a __syncwarp)
       // ---- non-max suppression (strict, 8 neighbours) of the short list
       bool tile_any = false;
 #pragma unroll 1
@@ -331,7 +337,7 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
         }
       }
       j = jn;
-      buf ^= 1;
+      if (FT_BUFS == 2) buf ^= 1;
     }
     if (kPass == 1) {
       // a tile with no pass-1 keypoint is retried at minThFAST (ORBextractor.cc:718-727); pass 2 re-runs only these runs
