@@ -244,20 +244,25 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
             m1 &= oob_bits(__funnelshift_r(cm.y, rm, 16), v1, c7) | oob_bits(fpp, v1, c7);
           }
         }
-        // survivors -> list: exclusive prefix of the per-lane counts (0..8) from four bit-plane ballots
-        const uint32_t cnt = (uint32_t)(__popc(m0) + __popc(m1));
-        const uint32_t b0 = __ballot_sync(0xffffffffu, cnt & 1u), b1 = __ballot_sync(0xffffffffu, cnt & 2u),
-                       b2 = __ballot_sync(0xffffffffu, cnt & 4u), b3 = __ballot_sync(0xffffffffu, cnt & 8u);
-        uint32_t addr = list_u32 + 2u * (uint32_t)(n_cand + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt));
-        const uint32_t e0 = (uint32_t)((ly << 8) | (4 * FT_QW0 + 8 * p));
+        // survivors -> list: exclusive prefix of the per-lane counts (0..8) by a shuffle scan
+        const int cnt = __popc(m0) + __popc(m1);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        uint32_t addr = list_u32 + 2u * (uint32_t)(n_cand + incl - cnt);
+        uint32_t e = (uint32_t)((ly << 8) | (4 * FT_QW0 + 8 * p));
 #pragma unroll
         for (int k = 0; k < 8; k++) {
           if ((k < 4 ? m0 : m1) & (0x80u << (8 * (k & 3)))) {
-            sts16(addr, e0 + k);
+            sts16(addr, e);
             addr += 2;
           }
+          e++;
         }
-        n_cand += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
+        n_cand += __shfl_sync(0xffffffffu, incl, 31);
       }
       __syncwarp();
 
@@ -273,7 +278,7 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
           const int ly = e >> 8, lx = e & 255;
           const int sc = fast_score_x2(pxb + (uint32_t)(ly * FT_PITCH + lx), th_run);
           sts8(sc_u32 + (uint32_t)(ly * FT_SCP + lx - FT_SCX), (uint32_t)sc);
-          q = sc >= (kPass == 1 ? a.ini_th : 1) && lx >= kFx && lx < kFx + 32 && ly >= 4 && ly < 36;
+          q = sc >= (kPass == 1 ? a.ini_th : 1) && (unsigned)(lx - kFx) < 32u && (unsigned)(ly - 4) < 32u;  // tile interior
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, q);
         __syncwarp();

@@ -344,6 +344,50 @@ def test_db_top2_shard(oracle, swm, monkeypatch, kernel, nq, ndb):
     lib.swm_db_destroy(h)
 
 
+def test_db_top2_config5_scale(oracle, swm):
+    """BASELINE config 5 shape at a size the oracle still finishes in seconds: 2000 queries x 4096 keyframes x 256
+    descriptors (1 048 576), 1 % of the keyframes hold noisy copies of query descriptors.  The whole query batch runs on
+    the tcgen05 shard scan; 32 sampled queries (every planted one among them) are checked against the oracle's brute
+    force -- distance and index of best and second best -- and the vote histogram lands on the planted keyframes only."""
+    import ctypes as C
+    import torch
+    from swarmmap_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(555)
+    nq, n_kf, per_kf, first_kf = 2000, 4096, 256, 70000
+    ndb = n_kf * per_kf
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    db = rng.integers(0, 256, (ndb, 32), dtype=np.uint8)
+    planted_kf = rng.choice(n_kf, n_kf // 100, replace=False)
+    planted_q = rng.choice(nq, len(planted_kf), replace=False)
+    for kf, qi in zip(planted_kf, planted_q):
+        bits = np.unpackbits(q[qi])
+        bits[rng.choice(256, 12, replace=False)] ^= 1
+        db[kf * per_kf + int(rng.integers(0, per_kf))] = np.packbits(bits)
+    h = C.c_void_p()
+    assert lib.swm_db_create(0, _lib.ptr(db), ndb, per_kf, first_kf, C.byref(h)) == 0
+    dq = torch.from_numpy(q).cuda()
+    topk = torch.zeros((nq, 2), dtype=torch.int64, device="cuda")
+    votes = torch.zeros(n_kf, dtype=torch.int32, device="cuda")
+    assert lib.swm_db_query_device(h, dq.data_ptr(), nq, 2, topk.data_ptr(), votes.data_ptr(), 50, None) == 0
+    torch.cuda.synchronize()
+    t = topk.cpu().numpy().astype(np.uint64)
+    dist = (t >> np.uint64(48)).astype(np.int64)
+    idx = (t & np.uint64((1 << 48) - 1)).astype(np.int64) - first_kf * per_kf
+    sample = np.unique(np.concatenate([planted_q[:16], rng.choice(nq, 16, replace=False)]))
+    ref = oracle.bruteforce_top2(q[sample], db)
+    np.testing.assert_array_equal(dist[sample, 0], ref[:, 0])
+    np.testing.assert_array_equal(idx[sample, 0], ref[:, 1])
+    np.testing.assert_array_equal(dist[sample, 1], ref[:, 2])
+    np.testing.assert_array_equal(idx[sample, 1], ref[:, 3])
+    assert (dist[planted_q, 0] == 12).all() and (dist[np.setdiff1d(np.arange(nq), planted_q), 0] > 50).all()
+    v = votes.cpu().numpy()
+    exp = np.zeros(n_kf, np.int64)
+    exp[planted_kf] = 1
+    np.testing.assert_array_equal(v, exp)
+    lib.swm_db_destroy(h)
+
+
 @pytest.mark.parametrize("k", [1, 2])
 def test_db_merge_gathered_equals_single_shard(oracle, swm, k):
     """The multi-GPU exchange step on one device: two shards scanned separately, their (nq, k) key blocks stacked the
