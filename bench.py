@@ -987,7 +987,8 @@ def main():
                          "traffic": (traffic_pf * SB if traffic_pf else None),
                          "traffic_source": f"ncu dram__bytes_read+write of the same launch set (profiles/{traffic_src})" if traffic_src else None,
                          "peak_source": peak_src,
-                         "kernel": "pyr_kernel x8 (pyramid+border, blur fused) + fast_kernel x2 (FAST score+tile retry+NMS), 256-frame launches",
+                         "kernel": "pyr_walk_kernel x8 (pyramid + border + fused blur, column walk, tensor-map TMA source rows) + fast_tile_kernel x2 "
+                                   "(FAST quick reject + score + tile retry + NMS, tensor-map TMA windows), 256-frame launches",
                          "bytes_per_frame": PYR_FAST_BYTES, "ms_per_launch_set": ms_pf,
                          "frac_counting_fused_blur_bytes": (PYR_FAST_BYTES + BLUR_BYTES) * SB / (ms_pf * 1e-3) / 1e9 / peak},
             "cpu_baseline": cpu_rec,

@@ -592,7 +592,10 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
       // batch allows while the level still fills the GPU about twice over (the 8-row blur warm-up is amortised over
       // 64 rows for large batches; a single frame gets 16-row blocks and several hundred warps per level).
       walk_strips(a.dst.w, &a.nstrips, &a.strip_lanes);
-      const int want_jobs = 2 * h->n_sm * 24;
+#ifndef SWM_WALK_WAVES
+#define SWM_WALK_WAVES 2
+#endif
+      const int want_jobs = SWM_WALK_WAVES * h->n_sm * 24;
       const int nrb_want = std::max(1, (want_jobs + batch * a.nstrips - 1) / (batch * a.nstrips));
       int rows = (int)align_up((a.dst.h + nrb_want - 1) / nrb_want, 4);
       rows = std::min(64, std::max(16, rows));
