@@ -300,6 +300,7 @@ struct swm_orb {
   int4* d_fblk = nullptr;       // per FAST block: (level, bx, by, 0)
   int* d_retry_list = nullptr;  // [0] = count, then (frame * blocks + block) ids holding a retry tile
   int n_sm = 148;
+  int fast_run = kFT;           // FAST tiles per warp: kFT for batch handles, 1 for a single-frame handle (shorter critical path)
   uint32_t *d_cand = nullptr, *d_sel = nullptr;
   uint32_t* d_pts = nullptr;     // quadtree scratch per (frame, level): capped point list, node labels, child ids
   uint16_t* d_pnode = nullptr;
@@ -462,7 +463,7 @@ int setup_geometry(swm_orb* h, int w, int hh) {
     g.tiles_y = (g.h - 2 * kEdge + 31) / 32;
     g.tile_off = tile_off;
     tile_off += g.tiles_x * g.tiles_y;
-    g.fblk_x = (g.tiles_x + kFT - 1) / kFT;
+    g.fblk_x = (g.tiles_x + h->fast_run - 1) / h->fast_run;
     g.fblk_off = fblk_off;
     fblk_off += g.fblk_x * g.tiles_y;
     // strict 8-neighbour maxima cannot be adjacent: at most one per 2x2 block
@@ -598,7 +599,7 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
       const int want_jobs = SWM_WALK_WAVES * h->n_sm * 24;
       const int nrb_want = std::max(1, (want_jobs + batch * a.nstrips - 1) / (batch * a.nstrips));
       int rows = (int)align_up((a.dst.h + nrb_want - 1) / nrb_want, 4);
-      rows = std::min(64, std::max(16, rows));
+      rows = std::min(64, std::max(batch >= 4 ? 16 : 8, rows));
       a.nrb = (a.dst.h + rows - 1) / rows;
       a.rows_per_job = (int)align_up((a.dst.h + a.nrb - 1) / a.nrb, 4);
       a.nrb = (a.dst.h + a.rows_per_job - 1) / a.rows_per_job;
@@ -624,6 +625,7 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
     fa.cand = h->d_cand;
     fa.cand_count = d_cand_count;
     fa.dbg_score = dbg;
+    fa.run_len = h->fast_run;
     fast_tile_kernel<1><<<grid, 32, 0, st>>>(fa);
     fa.dbg_score = nullptr;
     fast_tile_kernel<2><<<h->n_sm * 24, 32, 0, st>>>(fa);
@@ -676,6 +678,7 @@ int swm_orb_create(const swm_orb_cfg* cfg, int device, swm_orb** out) {
   h->cfg = *cfg;
   h->device = device;
   h->max_pts = cfg->max_fast_per_level > 0 ? cfg->max_fast_per_level : 10000;
+  h->fast_run = cfg->max_batch >= 8 ? kFT : 1;
   if (h->max_pts > 20000) h->max_pts = 20000;
   // scale tables: float chain with a double scale factor (ORBextractor.cc:346-362, ORBextractor.h:108)
   const double s = cfg->scale_factor;

@@ -24,7 +24,7 @@
 
 namespace swm {
 
-constexpr int kFT = 4;                       // tiles per run (one warp)
+constexpr int kFT = 4;                       // most tiles per run (one warp); FastArgs::run_len <= kFT is what a handle uses
 // Staged window: FT_PITCH x 40 bytes from level (X0 - 19, Y0 - 4), X0 - 19 = 32 * tile: the TMA needs a 16-byte aligned start
 // (an unaligned first coordinate faults), so the first interior pixel sits at local (kFx, 4) = (19, 4).
 #ifndef SWM_FT_PITCH
@@ -119,6 +119,7 @@ struct FastArgs {
   uint32_t* cand;
   int* cand_count;
   uint8_t* dbg_score;        // parity introspection: score map S at minThFAST (pass 1 only), or null
+  int run_len;               // tiles per run: kFT for batches (set-up amortised), 1 for a single-frame handle (latency)
 };
 
 template <int kPass>
@@ -159,13 +160,14 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
     const LevelGeom& g = L->lv[lvl];
     const int w = g.w, h = g.h;
     uint8_t* fretry = a.retry + (long long)f * L->tiles_total + g.tile_off;
-    const int t0 = by * g.tiles_x + kFT * bx;
-    const int ntile = min(kFT, g.tiles_x - kFT * bx);
+    const int tx0 = a.run_len * bx;  // first tile of the run
+    const int t0 = by * g.tiles_x + tx0;
+    const int ntile = min(a.run_len, g.tiles_x - tx0);
     const int Y0 = kEdge + 32 * by;
     if (kPass == 2) {
       __syncwarp();
       if (lane < 3 * (kFT + 2)) {
-        const int ny = by + lane / (kFT + 2) - 1, nx = kFT * bx + lane % (kFT + 2) - 1;
+        const int ny = by + lane / (kFT + 2) - 1, nx = tx0 + lane % (kFT + 2) - 1;
         s_flag[lane] = (ny >= 0 && ny < g.tiles_y && nx >= 0 && nx < g.tiles_x) ? fretry[ny * g.tiles_x + nx] : 0;
       }
       __syncwarp();
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
         asm volatile(
             "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
                 px_u32 + buf * (FT_ROWS * FT_PITCH)),
-            "l"(map), "r"(kPadX + 32 * (kFT * bx + j)), "r"(kEdge + Y0 - 4), "r"(f), "r"(bar)
+            "l"(map), "r"(kPadX + 32 * (tx0 + j)), "r"(kEdge + Y0 - 4), "r"(f), "r"(bar)
             : "memory");
       }
     };
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
       const int jn = active(j + 1);
       __syncwarp();  // every lane is done with the other buffer (tile before this one)
       if (FT_BUFS == 2 && jn < ntile) issue(jn, buf ^ 1);
-      const int X0 = kEdge + 32 * (kFT * bx + j);   // first interior pixel (level coords); staged origin (X0-19, Y0-4)
+      const int X0 = kEdge + 32 * (tx0 + j);   // first interior pixel (level coords); staged origin (X0-19, Y0-4)
       // score tile cleared; scored columns of each word: interior +- 1 px and level x in [19, w - 19)
       for (int i = lane; i < FT_ROWS * FT_SCP / 16; i += 32) reinterpret_cast<uint4*>(s_sc)[i] = make_uint4(0, 0, 0, 0);
       if (lane < 2 * FT_QP) {
