@@ -628,7 +628,9 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
     fa.run_len = h->fast_run;
     fast_tile_kernel<1><<<grid, 32, 0, st>>>(fa);
     fa.dbg_score = nullptr;
-    fast_tile_kernel<2><<<h->n_sm * 24, 32, 0, st>>>(fa);
+    // pass 2 walks the retry list with a persistent grid; a single frame has few runs, so it gets few warps to start
+    const int grid2 = std::min(h->n_sm * 24, std::max(h->n_sm, L.fblk_total * batch / 4));
+    fast_tile_kernel<2><<<grid2, 32, 0, st>>>(fa);
     launches += 2;
   }
   if (mask & SWM_STAGE_OCTREE) {
