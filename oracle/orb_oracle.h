@@ -168,6 +168,22 @@ void orc_window_best(const orc_frame* tgt, int m, const uint8_t* desc, const flo
 void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, int npoints, int32_t* best_idx,
                                  int32_t* best_median);
 
+/* ---- Frame::ComputeStereoMatches (Frame.cc:516-690): for every left keypoint the right keypoint of the same image row
+ * band with the smallest descriptor distance (octave within +-1, disparity in [-3, mbf/mb]), refined by an 11x11 SAD
+ * search over +-5 px in the un-blurred pyramid level of the left keypoint and a parabola fit, then the 1.5 * 1.4 * median
+ * SAD filter.  plane[l] points at ROI pixel (0,0) of level l (reads reach into the 19-px border, like the reference's
+ * colRange on a ROI GpuMat).  Outputs mvuRight / mvDepth (-1 = no match).  Returns the number of matches kept. */
+typedef struct orc_pyramid {
+  int nlevels;
+  const uint8_t* const* plane;
+  const int32_t* stride;
+  const int32_t* w;
+  const int32_t* h;
+} orc_pyramid;
+int orc_stereo_matches(const orc_keypoint* kl, const uint8_t* dl, int nl, const orc_keypoint* kr, const uint8_t* dr, int nr,
+                       const orc_pyramid* pl, const orc_pyramid* pr, const float* scale_factors,
+                       const float* inv_scale_factors, float mbf, float mb, float* u_right, float* depth);
+
 /* Brute-force top-2 of each query against a descriptor database (config 5). out: per query
  * (dist0, idx0, dist1, idx1); ties broken by lower index. */
 void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int32_t* out4);

@@ -449,6 +449,107 @@ void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, in
   }
 }
 
+// Frame::ComputeStereoMatches, Frame.cc:516-690.  Float expressions are evaluated left to right in float exactly as
+// written there (the oracle is compiled with -ffp-contract=off); `round` is C's (half away from zero); the SAD values
+// are integers, so cv::norm's double accumulation and the float it is stored in are exact.
+int orc_stereo_matches(const orc_keypoint* kl, const uint8_t* dl, int nl, const orc_keypoint* kr, const uint8_t* dr, int nr,
+                       const orc_pyramid* pl, const orc_pyramid* pr, const float* sf, const float* inv_sf, float mbf, float mb,
+                       float* u_right, float* depth) {
+  const int TH_HIGH = 100;  // ORBmatcher.cc:38
+  for (int i = 0; i < nl; i++) u_right[i] = depth[i] = -1.0f;
+  const int nRows = pl->h[0];
+  std::vector<std::vector<int>> vRowIndices(nRows);  // :524-541
+  for (int iR = 0; iR < nr; iR++) {
+    const float kpY = kr[iR].y;
+    const float r = 2.0f * sf[kr[iR].octave];
+    const int maxr = (int)std::ceil(kpY + r);
+    const int minr = (int)std::floor(kpY - r);
+    for (int yi = minr; yi <= maxr; yi++)
+      if (yi >= 0 && yi < nRows) vRowIndices[yi].push_back(iR);  // (the reference indexes unchecked; keypoints keep >= 14 px from the edge)
+  }
+  const float minZ = mb, minD = -3, maxD = mbf / minZ;  // :544-546
+  std::vector<std::pair<int, int>> vDistIdx;
+  for (int iL = 0; iL < nl; iL++) {
+    const int levelL = kl[iL].octave;
+    const float vL = kl[iL].y, uL = kl[iL].x;
+    const int row = (int)vL;  // vRowIndices[vL]: float -> size_t truncation
+    if (row < 0 || row >= nRows) continue;
+    const std::vector<int>& cand = vRowIndices[row];
+    if (cand.empty()) continue;
+    const float minU = uL - maxD, maxU = uL - minD;
+    if (maxU < 0) continue;
+    int bestDist = TH_HIGH, bestIdxR = 0;
+    for (int iR : cand) {  // :572-594
+      if (kr[iR].octave < levelL - 1 || kr[iR].octave > levelL + 1) continue;
+      const float uR = kr[iR].x;
+      if (uR >= minU && uR <= maxU) {
+        const int dist = dist256(dl + (size_t)iL * 32, dr + (size_t)iR * 32);
+        if (dist < bestDist) {
+          bestDist = dist;
+          bestIdxR = iR;
+        }
+      }
+    }
+    if (!(bestDist < TH_HIGH)) continue;
+    // sub-pixel match by correlation, :597-672
+    const float uR0 = kr[bestIdxR].x;
+    const float scaleFactor = inv_sf[levelL];
+    const float scaleduL = std::round(uL * scaleFactor), scaledvL = std::round(vL * scaleFactor);
+    const float scaleduR0 = std::round(uR0 * scaleFactor);
+    const int w = 5, L = 5;
+    const uint8_t* imL = pl->plane[levelL];
+    const uint8_t* imR = pr->plane[levelL];
+    const int sL = pl->stride[levelL], sR = pr->stride[levelL];
+    const int y0 = (int)(scaledvL - w), xL0 = (int)(scaleduL - w);
+    const float iniu = scaleduR0 + L - w, endu = scaleduR0 + L + w + 1;
+    if (iniu < 0 || endu >= pr->w[levelL]) continue;
+    const int cL = imL[(y0 + w) * sL + xL0 + w];
+    int bestSad = INT_MAX, bestincR = 0;
+    float vDists[2 * 5 + 1];
+    for (int incR = -L; incR <= +L; incR++) {
+      const int xR0 = (int)(scaleduR0 + incR - w);
+      const int cR = imR[(y0 + w) * sR + xR0 + w];
+      int sad = 0;
+      for (int yy = 0; yy < 2 * w + 1; yy++)
+        for (int xx = 0; xx < 2 * w + 1; xx++)
+          sad += std::abs((imL[(y0 + yy) * sL + xL0 + xx] - cL) - (imR[(y0 + yy) * sR + xR0 + xx] - cR));
+      const float dist = (float)sad;
+      if (dist < bestSad) {
+        bestSad = (int)dist;
+        bestincR = incR;
+      }
+      vDists[L + incR] = dist;
+    }
+    if (bestincR == -L || bestincR == L) continue;
+    const float dist1 = vDists[L + bestincR - 1], dist2 = vDists[L + bestincR], dist3 = vDists[L + bestincR + 1];
+    const float deltaR = (dist1 - dist3) / (2.0f * (dist1 + dist3 - 2.0f * dist2));
+    if (deltaR < -1 || deltaR > 1) continue;
+    float bestuR = sf[levelL] * ((float)scaleduR0 + (float)bestincR + deltaR);
+    float disparity = (uL - bestuR);
+    if (disparity >= 0 && disparity < maxD) {
+      if (disparity <= 0) {
+        disparity = 0.01;
+        bestuR = uL - 0.01;
+      }
+      depth[iL] = mbf / disparity;
+      u_right[iL] = bestuR;
+      vDistIdx.push_back(std::pair<int, int>(bestSad, iL));
+    }
+  }
+  if (vDistIdx.empty()) return 0;  // (the reference would index an empty vector here)
+  std::sort(vDistIdx.begin(), vDistIdx.end());  // :675-689
+  const float median = vDistIdx[vDistIdx.size() / 2].first;
+  const float thDist = 1.5f * 1.4f * median;
+  int kept = (int)vDistIdx.size();
+  for (int i = (int)vDistIdx.size() - 1; i >= 0; i--) {
+    if (vDistIdx[i].first < thDist) break;
+    u_right[vDistIdx[i].second] = -1;
+    depth[vDistIdx[i].second] = -1;
+    kept--;
+  }
+  return kept;
+}
+
 // Brute-force top-2 (config 5): ties broken by the lower database index.
 void orc_bruteforce_top2(const uint8_t* q, int nq, const uint8_t* db, int64_t ndb, int32_t* out4) {
   for (int i = 0; i < nq; i++) {

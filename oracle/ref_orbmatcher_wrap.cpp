@@ -8,6 +8,7 @@
 // The harness builds the doubles from flat arrays, calls the reference's member function, and flattens the result.
 // Test infrastructure only (tests/test_ref_orbmatcher.py, tests/ref_vs_product_test.cpp); nothing in the product
 // links or loads this.
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdint>
@@ -27,6 +28,7 @@ float Frame::mnMinX, Frame::mnMaxX, Frame::mnMinY, Frame::mnMaxY;
 float Frame::mfGridElementWidthInv, Frame::mfGridElementHeightInv;
 // the reference's own function bodies (see the header comment)
 #include "_ref/gen/frame_grid.inc"
+#include "_ref/gen/frame_stereo.inc"
 #include "_ref/gen/keyframe_grid.inc"
 #include "_ref/gen/mappoint_scale.inc"
 
@@ -436,6 +438,49 @@ int refm_search_by_sim3(const refm_frame* k1d, const refm_frame* k2d, const refm
   const int n = m.SearchBySim3(k1.get(), k2.get(), v, s12, R, vec3(t12), th);
   flatten(v, matches12);
   return n;
+}
+
+// Frame::ComputeStereoMatches (code/src/Frame.cc:516-690, the reference's own body).  Keypoints as (x, y, octave)
+// triples; plane[l] = ROI pixel (0,0) of the un-blurred pyramid level l (a view on a bordered plane, like the
+// reference's mvImagePyramid: its window reads may reach into the border).
+int refm_stereo_matches(const float* lx, const float* ly, const int32_t* loct, const uint8_t* ldesc, int nl,
+                        const float* rx, const float* ry, const int32_t* roct, const uint8_t* rdesc, int nr,
+                        const uint8_t* const* lplane, const uint8_t* const* rplane, const int32_t* stride, const int32_t* w,
+                        const int32_t* h, int nlevels, const float* scale_factors, const float* inv_scale_factors, float mbf,
+                        float mb, float* u_right, float* depth) {
+  Frame F;
+  ORBextractor exl, exr;
+  for (int l = 0; l < nlevels; l++) {
+    exl.mvImagePyramid.push_back(cv::cuda::GpuMat(h[l], w[l], const_cast<unsigned char*>(lplane[l]), (size_t)stride[l]));
+    exr.mvImagePyramid.push_back(cv::cuda::GpuMat(h[l], w[l], const_cast<unsigned char*>(rplane[l]), (size_t)stride[l]));
+  }
+  F.mpORBextractorLeft = &exl;
+  F.mpORBextractorRight = &exr;
+  F.N = nl;
+  F.mvKeys.resize(nl);
+  for (int i = 0; i < nl; i++) {
+    F.mvKeys[i].pt.x = lx[i]; F.mvKeys[i].pt.y = ly[i]; F.mvKeys[i].octave = loct[i];
+  }
+  F.mvKeysRight.resize(nr);
+  for (int i = 0; i < nr; i++) {
+    F.mvKeysRight[i].pt.x = rx[i]; F.mvKeysRight[i].pt.y = ry[i]; F.mvKeysRight[i].octave = roct[i];
+  }
+  F.mDescriptors = cv::Mat(nl, 32, CV_8U);
+  if (nl) memcpy(F.mDescriptors.data, ldesc, (size_t)nl * 32);
+  F.mDescriptorsRight = cv::Mat(nr, 32, CV_8U);
+  if (nr) memcpy(F.mDescriptorsRight.data, rdesc, (size_t)nr * 32);
+  F.mvScaleFactors.assign(scale_factors, scale_factors + nlevels);
+  F.mvInvScaleFactors.assign(inv_scale_factors, inv_scale_factors + nlevels);
+  F.mbf = mbf;
+  F.mb = mb;
+  F.ComputeStereoMatches();
+  int kept = 0;
+  for (int i = 0; i < nl; i++) {
+    u_right[i] = F.mvuRight[i];
+    depth[i] = F.mvDepth[i];
+    kept += F.mvuRight[i] >= 0;
+  }
+  return kept;
 }
 
 #pragma GCC visibility pop

@@ -62,6 +62,9 @@ class Mat {
 
   Mat() {}
   Mat(int r, int c, int type) { create(r, c, type); }
+  Mat(int r, int c, int type, void* ext, size_t ext_step) {  // header over caller-owned rows (Frame.cc:609,630)
+    rows = r; cols = c; type_ = type; step = ext_step; data = static_cast<unsigned char*>(ext);
+  }
   Mat(const MatExpr& e);
   Mat& operator=(const MatExpr& e);
 
@@ -71,6 +74,20 @@ class Mat {
     const size_t bytes = (size_t)r * step;
     buf_ = std::shared_ptr<unsigned char>(new unsigned char[bytes ? bytes : 1], std::default_delete<unsigned char[]>());
     data = buf_.get();
+  }
+  static Mat ones(int r, int c, int type) {
+    Mat m(r, c, type);
+    for (int i = 0; i < r; i++)
+      for (int j = 0; j < c; j++) m.at<float>(i, j) = 1.f;
+    return m;
+  }
+  // 8U -> 32F (may be in place, as Frame.cc:610,631 call it): exact
+  void convertTo(Mat& dst, int rtype) const {
+    assert(rtype == CV_32F);
+    Mat m(rows, cols, CV_32F);
+    for (int i = 0; i < rows; i++)
+      for (int j = 0; j < cols; j++) m.at<float>(i, j) = type_ == CV_32F ? at<float>(i, j) : (float)at<unsigned char>(i, j);
+    dst = m;
   }
   static Mat zeros(int r, int c, int type) {
     Mat m(r, c, type);
@@ -203,6 +220,32 @@ inline Mat operator-(const Mat& l, const Mat& c) {
     for (int j = 0; j < l.cols; j++) r.at<float>(i, j) = l.at<float>(i, j) - c.at<float>(i, j);
   return r;
 }
+
+inline Mat operator-(const Mat& l, const MatExpr& x) { return l - x.eval(); }  // A - s * B: addWeighted in float
+
+enum { NORM_INF = 1, NORM_L1 = 2, NORM_L2 = 4 };
+inline double norm(const Mat& a, const Mat& b, int type) {  // NORM_L1 of a difference, accumulation in double
+  assert(type == NORM_L1 && a.rows == b.rows && a.cols == b.cols);
+  double s = 0;
+  for (int i = 0; i < a.rows; i++)
+    for (int j = 0; j < a.cols; j++) s += std::abs((double)a.at<float>(i, j) - (double)b.at<float>(i, j));
+  return s;
+}
+
+namespace cuda {
+// a view on caller-owned image rows: what Frame::ComputeStereoMatches uses of cv::cuda::GpuMat (Frame.cc:608,629)
+class GpuMat {
+ public:
+  int rows = 0, cols = 0;
+  size_t step = 0;
+  unsigned char* data = nullptr;
+  GpuMat() {}
+  GpuMat(int r, int c, unsigned char* d, size_t s) : rows(r), cols(c), step(s), data(d) {}
+  int type() const { return CV_8U; }
+  GpuMat rowRange(int a, int b) const { return GpuMat(b - a, cols, data + (ptrdiff_t)a * (ptrdiff_t)step, step); }
+  GpuMat colRange(int a, int b) const { return GpuMat(rows, b - a, data + a, step); }
+};
+}  // namespace cuda
 
 inline double norm(const Mat& m) {  // NORM_L2, accumulation in double
   double s = 0;

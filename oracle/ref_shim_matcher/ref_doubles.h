@@ -77,10 +77,22 @@ class MapPoint {
   int index = -1;  // position in the harness' point table
 };
 
+// what Frame::ComputeStereoMatches reads of the extractors (include/ORBextractor.h:90): the un-bordered pyramid views
+class ORBextractor {
+ public:
+  std::vector<cv::cuda::GpuMat> mvImagePyramid;
+};
+
 class Frame {
  public:
   int N = 0;
   std::vector<cv::KeyPoint> mvKeys, mvKeysUn;
+  // stereo members (code/include/Frame.h), read and written by ComputeStereoMatches, body from code/src/Frame.cc:516-690
+  std::vector<cv::KeyPoint> mvKeysRight;
+  cv::Mat mDescriptorsRight;
+  std::vector<float> mvDepth, mvInvScaleFactors;
+  ORBextractor *mpORBextractorLeft = nullptr, *mpORBextractorRight = nullptr;
+  void ComputeStereoMatches();
   std::vector<float> mvuRight;
   cv::Mat mDescriptors;
   std::vector<MapPoint*> mvpMapPoints;

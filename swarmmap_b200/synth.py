@@ -89,6 +89,27 @@ def make_batch(n, w=EUROC[0], h=EUROC[1], seed=20220410):
     return out
 
 
+def make_stereo_pair(w=EUROC[0], h=EUROC[1], seed=20220420, d_near=40.0, d_far=4.0, right_shift=0):
+    """A rectified stereo pair: the right view is the left view with a row-dependent horizontal disparity (far at the
+    top, near at the bottom, like a ground plane; sub-pixel through linear interpolation) + fresh sensor noise.
+    right_shift moves the right view the other way (negative disparities, for the matcher's rejection paths)."""
+    rng = np.random.default_rng(seed + 32452843)
+    canvas = make_canvas(w + 256, h, seed)
+    left = canvas[:, 64:64 + w]
+    right = np.empty_like(left)
+    xs = np.arange(w, dtype=np.float32)
+    for y in range(h):
+        d = d_far + (d_near - d_far) * y / (h - 1) - right_shift
+        src = xs + 64 + d  # right(x) = left(x + d): a point at left column u appears at right column u - d
+        x0 = np.floor(src).astype(np.int32)
+        f = src - x0
+        right[y] = canvas[y, x0] * (1 - f) + canvas[y, x0 + 1] * f
+    out = []
+    for img in (left, right):
+        out.append(np.clip(np.rint(img + rng.normal(0, 2.0, img.shape).astype(np.float32)), 0, 255).astype(np.uint8))
+    return out[0], out[1]
+
+
 def make_vocabulary(k=10, L=3, seed=1, early_leaf=0.03, zero_weight=0.02, weighting=0, scoring=0):
     """A synthetic DBoW2 ORB vocabulary in the binary layout TemplatedVocabulary::loadFromBinaryFile reads
     (reference code/Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1478-1522; the real ORBvoc.bin is not shipped):

@@ -383,6 +383,43 @@ def distinctive_descriptors(desc, offsets):
     return best, med
 
 
+class Pyramid(C.Structure):
+    _fields_ = [("nlevels", C.c_int), ("plane", C.c_void_p), ("stride", C.c_void_p), ("w", C.c_void_p), ("h", C.c_void_p)]
+
+
+def stereo_matches(kl, dl, kr, dr, planes_l, planes_r, sf, inv_sf, mbf, mb):
+    """Oracle of Frame::ComputeStereoMatches (Frame.cc:516-690).  kl / kr: KP_DTYPE arrays; planes_*: per level the
+    BORDERED un-blurred plane (19 px) as a 2-D uint8 array.  -> (uRight, depth, kept)."""
+    nlev = len(planes_l)
+    keep = []
+
+    def pyr(planes):
+        ptrs = (C.c_void_p * nlev)()
+        for l, pl in enumerate(planes):
+            pl = np.ascontiguousarray(pl, np.uint8)
+            keep.append(pl)
+            ptrs[l] = pl.ctypes.data + 19 * pl.shape[1] + 19
+        stride = np.array([p.shape[1] for p in planes], np.int32)
+        w = np.array([p.shape[1] - 38 for p in planes], np.int32)
+        h = np.array([p.shape[0] - 38 for p in planes], np.int32)
+        keep.extend([ptrs, stride, w, h])
+        return Pyramid(nlev, C.cast(ptrs, C.c_void_p), _p(stride), _p(w), _p(h))
+
+    kl = np.ascontiguousarray(kl, KP_DTYPE)
+    kr = np.ascontiguousarray(kr, KP_DTYPE)
+    dl, dr = np.ascontiguousarray(dl, np.uint8), np.ascontiguousarray(dr, np.uint8)
+    sf, inv_sf = np.ascontiguousarray(sf, np.float32), np.ascontiguousarray(inv_sf, np.float32)
+    pl, pr = pyr(planes_l), pyr(planes_r)
+    ur, dep = np.zeros(len(kl), np.float32), np.zeros(len(kl), np.float32)
+    fn = lib().orc_stereo_matches
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                   C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p]
+    n = fn(_p(kl), _p(dl), len(kl), _p(kr), _p(dr), len(kr), C.byref(pl), C.byref(pr), _p(sf), _p(inv_sf), mbf, mb,
+           _p(ur), _p(dep))
+    return ur, dep, n
+
+
 def bruteforce_top2(q, db):
     q = np.ascontiguousarray(q, np.uint8)
     db = np.ascontiguousarray(db, np.uint8)

@@ -299,3 +299,40 @@ def project(K, pc, inv_double=True):
     u = f32(f32(f32(fx * pc[0]) * invz) + cx)
     v = f32(f32(f32(fy * pc[1]) * invz) + cy)
     return u, v, invz
+
+
+def stereo_matches(kl, dl, kr, dr, planes_l, planes_r, sf, inv_sf, mbf, mb):
+    """Frame::ComputeStereoMatches, the reference's own body (Frame.cc:516-690).  kl / kr: keypoint record arrays
+    (x, y, octave); planes_*: per level the BORDERED un-blurred plane (19 px) as a 2-D uint8 array.  -> (uRight, depth)."""
+    nl, nr, nlev = len(kl), len(kr), len(planes_l)
+    keep = []
+
+    def col(a, name, dt):
+        v = np.ascontiguousarray(a[name], dt)
+        keep.append(v)
+        return _p(v)
+
+    def rois(planes):
+        ptrs = (C.c_void_p * nlev)()
+        for l, pl in enumerate(planes):
+            pl = np.ascontiguousarray(pl, np.uint8)
+            keep.append(pl)
+            ptrs[l] = pl.ctypes.data + 19 * pl.shape[1] + 19
+        return ptrs
+
+    pl_, pr_ = rois(planes_l), rois(planes_r)
+    stride = np.array([p.shape[1] for p in planes_l], np.int32)
+    w = np.array([p.shape[1] - 38 for p in planes_l], np.int32)
+    h = np.array([p.shape[0] - 38 for p in planes_l], np.int32)
+    dl, dr = _arr(dl, np.uint8), _arr(dr, np.uint8)
+    sf, inv_sf = _arr(sf, np.float32), _arr(inv_sf, np.float32)
+    ur, dep = np.zeros(nl, np.float32), np.zeros(nl, np.float32)
+    fn = lib().refm_stereo_matches
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 4 + [C.c_int] + [C.c_void_p] * 5 + [C.c_int] + \
+                  [C.c_void_p] * 2 + [C.c_float] * 2 + [C.c_void_p] * 2
+    n = fn(col(kl, "x", np.float32), col(kl, "y", np.float32), col(kl, "octave", np.int32), _p(dl), nl,
+           col(kr, "x", np.float32), col(kr, "y", np.float32), col(kr, "octave", np.int32), _p(dr), nr,
+           C.cast(pl_, C.c_void_p), C.cast(pr_, C.c_void_p), _p(stride), _p(w), _p(h), nlev, _p(sf), _p(inv_sf),
+           mbf, mb, _p(ur), _p(dep))
+    return ur, dep, n
