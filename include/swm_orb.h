@@ -111,6 +111,15 @@ int swm_orb_level_quotas(const swm_orb* h, int32_t* quotas);
 int swm_orb_max_keypoints(const swm_orb* h);
 /* Number of kernel launches issued by the last extract call (bench.py's gpu_launches). */
 int swm_orb_last_launches(const swm_orb* h);
+/* Frame::ComputeStereoMatches (reference code/src/Frame.cc:516-690) on the device, from the resident results of two
+ * extractors: `left` and `right` hold the last extracted batch of the left and right views of the same frames (same
+ * device, batch, frame size and pyramid).  For frame f of the batch, left keypoint i gets
+ * u_right[f * cap + i] = mvuRight[i] and depth[f * cap + i] = mvDepth[i] (-1 = no stereo match), bit-identical to the
+ * reference's loop: best descriptor distance in the keypoint's row band (octave +-1, disparity in [-3, bf / b]), 11x11
+ * SAD refinement over +-5 px in the un-blurred pyramid level, parabola fit, 1.5 * 1.4 * median SAD filter.  bf = mbf
+ * (baseline x fx), b = mb (baseline in metres).  cap >= swm_orb_max_keypoints(left), or the cap the batch was extracted
+ * with; host outputs, returns after the results are in place. */
+int swm_orb_stereo_match(swm_orb* left, swm_orb* right, float bf, float b, float* u_right, float* depth, int cap);
 /* Re-runs the selected stages on the data of the last *_device/_batch call (the caller brackets it with
  * CUDA events on `stream`): per-stage timing for bench.py's roofline and stage breakdown. */
 int swm_orb_run_stage(swm_orb* h, int stage_mask, int batch, void* stream);

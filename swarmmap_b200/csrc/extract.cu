@@ -16,6 +16,7 @@
 #include <cuda.h>  // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched with cudaGetDriverEntryPoint, no libcuda link)
 
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -56,6 +57,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
 }  // namespace swm
 #include "pyr_walk.cuh"
 #include "fast_tile.cuh"
+#include "stereo.cuh"
 namespace swm {
 
 // ------------------------------------------------------------------------------------------------
@@ -295,6 +297,11 @@ struct swm_orb {
   ResizeTap *d_xtab = nullptr, *d_ytab = nullptr;
   CUtensorMap* d_maps = nullptr;  // per level: the un-blurred plane over all frames, for pyr_walk_kernel's TMA tiles
   CUtensorMap* d_fmaps = nullptr; // the same planes with fast_tile_kernel's box
+  // stereo matching (left-view handle owns the scratch): per (frame, left keypoint) uRight, depth, SAD
+  float *d_uright = nullptr, *d_depth = nullptr;
+  int32_t* d_sad = nullptr;
+  size_t stereo_cap = 0;
+  cudaEvent_t stereo_ev = nullptr;
   uint8_t *d_plain = nullptr, *d_blur = nullptr, *d_score = nullptr;
   uint8_t* d_retry = nullptr;
   int4* d_fblk = nullptr;       // per FAST block: (level, bx, by, 0)
@@ -350,11 +357,11 @@ void free_frame_buffers(swm_orb* h) {
   if (h->graph) cudaGraphExecDestroy(h->graph);
   h->graph = nullptr;
   h->graph_runs = 0;
-  cudaFree(h->d_lay); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_maps); cudaFree(h->d_fmaps);
+  cudaFree(h->d_lay); cudaFree(h->d_xtab); cudaFree(h->d_ytab); cudaFree(h->d_maps); cudaFree(h->d_fmaps); cudaFree(h->d_uright); cudaFree(h->d_depth); cudaFree(h->d_sad);
   cudaFree(h->d_plain); cudaFree(h->d_blur); cudaFree(h->d_score);
   cudaFree(h->d_retry); cudaFree(h->d_retry_list); cudaFree(h->d_fblk); cudaFree(h->d_pts); cudaFree(h->d_pnode); cudaFree(h->d_pchild); cudaFree(h->d_cand); cudaFree(h->d_sel); cudaFree(h->d_counts);
   cudaFree(h->d_img); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFree(h->d_n);
-  h->d_lay = nullptr; h->d_xtab = h->d_ytab = nullptr; h->d_maps = nullptr; h->d_fmaps = nullptr;
+  h->d_lay = nullptr; h->d_xtab = h->d_ytab = nullptr; h->d_maps = nullptr; h->d_fmaps = nullptr; h->d_uright = h->d_depth = nullptr; h->d_sad = nullptr; h->stereo_cap = 0;
   h->d_plain = h->d_blur = h->d_score = nullptr;
   h->d_retry = nullptr; h->d_retry_list = nullptr; h->d_fblk = nullptr; h->d_pts = nullptr; h->d_pnode = nullptr; h->d_pchild = nullptr; h->d_cand = h->d_sel = nullptr; h->d_counts = nullptr;
   h->d_img = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->d_n = nullptr;
@@ -958,6 +965,57 @@ int swm_orb_extract(swm_orb* h, const uint8_t* img, int w, int h_px, int stride,
   int rc = swm_orb_extract_batch(h, img, 1, w, h_px, stride, (size_t)stride * h_px, kps, desc, cap, &nn);
   *n = nn;
   return rc;
+}
+
+int swm_orb_stereo_match(swm_orb* left, swm_orb* right, float bf, float b, float* u_right, float* depth, int cap) {
+  if (!left || !right) return SWM_E_INVALID;
+  swm_orb* h = left;
+  if (!u_right || !depth || !(bf > 0) || !(b > 0)) { h->err = "bad argument"; return SWM_E_INVALID; }
+  if (!left->last_kps || !right->last_kps || left->last_batch < 1) { h->err = "both extractors must hold an extracted batch"; return SWM_E_STATE; }
+  if (left->device != right->device || left->last_batch != right->last_batch || left->lay.w != right->lay.w ||
+      left->lay.h != right->lay.h || left->cfg.nlevels != right->cfg.nlevels || left->cfg.scale_factor != right->cfg.scale_factor) {
+    h->err = "left and right extractor differ in device, batch, frame size or pyramid";
+    return SWM_E_INVALID;
+  }
+  if (left->last_cap >= 65536 || right->last_cap >= 65536) { h->err = "more than 65535 keypoints per frame"; return SWM_E_CAPACITY; }
+  const int B = left->last_batch, capl = left->last_cap;
+  if (cap < capl) { h->err = "output capacity below the extractor's keypoint capacity"; return SWM_E_CAPACITY; }
+  SWM_CK(h, cudaSetDevice(h->device));
+  const size_t need = (size_t)B * capl;
+  if (need > h->stereo_cap) {
+    cudaFree(h->d_uright); cudaFree(h->d_depth); cudaFree(h->d_sad);
+    h->d_uright = h->d_depth = nullptr; h->d_sad = nullptr; h->stereo_cap = 0;
+    const size_t want = std::max(need, (size_t)h->cfg.max_batch * capl);
+    SWM_CK(h, cudaMalloc(&h->d_uright, want * 4));
+    SWM_CK(h, cudaMalloc(&h->d_depth, want * 4));
+    SWM_CK(h, cudaMalloc(&h->d_sad, want * 4));
+    h->stereo_cap = want;
+  }
+  if (!h->stereo_ev) SWM_CK(h, cudaEventCreateWithFlags(&h->stereo_ev, cudaEventDisableTiming));
+  cudaStream_t st = left->last_stream;
+  if (right->last_stream != st) {  // the right view's batch may still be in flight on its own stream
+    SWM_CK(h, cudaEventRecord(h->stereo_ev, right->last_stream));
+    SWM_CK(h, cudaStreamWaitEvent(st, h->stereo_ev, 0));
+  }
+  StereoArgs a;
+  a.L = left->d_lay;
+  a.kl = left->last_kps; a.dl = left->last_desc; a.nl = left->last_n;
+  a.kr = right->last_kps; a.dr = right->last_desc; a.nr = right->last_n;
+  a.cap_l = capl; a.cap_r = right->last_cap;
+  a.plain_l = left->d_plain; a.plain_r = right->d_plain;
+  for (int i = 0; i < SWM_MAX_LEVELS; i++) {
+    a.sf[i] = i < left->cfg.nlevels ? left->sf[i] : 1.0f;
+    a.inv_sf[i] = i < left->cfg.nlevels ? left->inv_sf[i] : 1.0f;
+  }
+  a.mbf = bf; a.mb = b;
+  a.u_right = h->d_uright; a.depth = h->d_depth; a.sad = h->d_sad;
+  stereo_match_kernel<<<dim3((capl + 7) / 8, B), 256, 0, st>>>(a);
+  stereo_filter_kernel<<<B, 1024, 0, st>>>(left->last_n, capl, h->d_uright, h->d_depth, h->d_sad);
+  SWM_CK(h, cudaGetLastError());
+  SWM_CK(h, cudaMemcpy2DAsync(u_right, (size_t)cap * 4, h->d_uright, (size_t)capl * 4, (size_t)capl * 4, B, cudaMemcpyDeviceToHost, st));
+  SWM_CK(h, cudaMemcpy2DAsync(depth, (size_t)cap * 4, h->d_depth, (size_t)capl * 4, (size_t)capl * 4, B, cudaMemcpyDeviceToHost, st));
+  SWM_CK(h, cudaStreamSynchronize(st));
+  return SWM_OK;
 }
 
 int swm_orb_run_stage(swm_orb* h, int stage_mask, int batch, void* stream) {

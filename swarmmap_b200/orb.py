@@ -130,6 +130,16 @@ class ORBextractor:
                                                     d_kps_ptr, d_desc_ptr, cap, d_n_ptr, stream)
         check(rc, self._h, "swm_orb_extract_batch_device")
 
+    def stereo_match(self, right, bf, b, batch):
+        """Frame::ComputeStereoMatches (reference Frame.cc:516-690) for the batch this extractor (left view) and `right`
+        (right view) extracted last: returns (mvuRight, mvDepth) as (batch, cap) float32 arrays, -1 = no match."""
+        cap = self.max_keypoints()
+        u = np.empty((batch, cap), np.float32)
+        z = np.empty((batch, cap), np.float32)
+        check(self._lib.swm_orb_stereo_match(self._h, right._h, bf, b, ptr(u), ptr(z), cap), self._h,
+              "swm_orb_stereo_match")
+        return u, z
+
     def run_stage(self, mask, batch, stream=None):
         check(self._lib.swm_orb_run_stage(self._h, mask, batch, stream), self._h, "swm_orb_run_stage")
 
