@@ -116,7 +116,7 @@ int swm_orb_last_launches(const swm_orb* h);
  * device, batch, frame size and pyramid).  For frame f of the batch, left keypoint i gets
  * u_right[f * cap + i] = mvuRight[i] and depth[f * cap + i] = mvDepth[i] (-1 = no stereo match), bit-identical to the
  * reference's loop: best descriptor distance in the keypoint's row band (octave +-1, disparity in [-3, bf / b]), 11x11
- * SAD refinement over +-5 px in the un-blurred pyramid level, parabola fit, 1.5 * 1.4 * median SAD filter.  bf = mbf
+ * SAD refinement over +-5 px in mvImagePyramid[level] as operator() leaves it (blurred in place), parabola fit, 1.5 * 1.4 * median SAD filter.  bf = mbf
  * (baseline x fx), b = mb (baseline in metres).  cap >= swm_orb_max_keypoints(left), or the cap the batch was extracted
  * with; host outputs, returns after the results are in place. */
 int swm_orb_stereo_match(swm_orb* left, swm_orb* right, float bf, float b, float* u_right, float* depth, int cap);

@@ -170,8 +170,9 @@ void orc_distinctive_descriptors(const uint8_t* desc, const int32_t* offsets, in
 
 /* ---- Frame::ComputeStereoMatches (Frame.cc:516-690): for every left keypoint the right keypoint of the same image row
  * band with the smallest descriptor distance (octave within +-1, disparity in [-3, mbf/mb]), refined by an 11x11 SAD
- * search over +-5 px in the un-blurred pyramid level of the left keypoint and a parabola fit, then the 1.5 * 1.4 * median
- * SAD filter.  plane[l] points at ROI pixel (0,0) of level l (reads reach into the 19-px border, like the reference's
+ * search over +-5 px in mvImagePyramid[level of the left keypoint] and a parabola fit, then the 1.5 * 1.4 * median
+ * SAD filter.  plane[l] points at ROI pixel (0,0) of level l as operator() leaves it -- blurred in place inside its un-blurred
+ * 19-px border (reads may reach into the border, like the reference's
  * colRange on a ROI GpuMat).  Outputs mvuRight / mvDepth (-1 = no match).  Returns the number of matches kept. */
 typedef struct orc_pyramid {
   int nlevels;

@@ -1003,6 +1003,7 @@ int swm_orb_stereo_match(swm_orb* left, swm_orb* right, float bf, float b, float
   a.kr = right->last_kps; a.dr = right->last_desc; a.nr = right->last_n;
   a.cap_l = capl; a.cap_r = right->last_cap;
   a.plain_l = left->d_plain; a.plain_r = right->d_plain;
+  a.blur_l = left->d_blur; a.blur_r = right->d_blur;
   for (int i = 0; i < SWM_MAX_LEVELS; i++) {
     a.sf[i] = i < left->cfg.nlevels ? left->sf[i] : 1.0f;
     a.inv_sf[i] = i < left->cfg.nlevels ? left->inv_sf[i] : 1.0f;

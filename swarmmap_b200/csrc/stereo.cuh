@@ -6,7 +6,10 @@
 //     row band of a right keypoint [floor(y - r), ceil(y + r)], r = 2 * scale(octave)            :531-541
 //     best descriptor distance among the right keypoints of the left keypoint's row, octave +-1,
 //     uR in [uL - bf/b, uL + 3], strict <, candidates in ascending index                         :549-594
-//     11 x 11 SAD over +-5 px in the un-blurred level of the left keypoint, centre-subtracted     :597-647
+//     11 x 11 SAD over +-5 px in mvImagePyramid[level of the left keypoint], centre-subtracted    :597-647
+//       (operator() blurs mvImagePyramid[l] in place, ORBextractor.cc:765,788, so inside the level these are the
+//       BLURRED pixels; a window column or row outside the level would read the un-blurred border of the bordered
+//       buffer the level is a view of -- px() below makes the same choice)
 //     parabola fit, disparity / depth                                                            :649-672
 //     1.5 * 1.4 * median SAD filter                                                              :675-689
 //
@@ -24,11 +27,20 @@ struct StereoArgs {
   const swm_keypoint* kl; const uint8_t* dl; const int32_t* nl;  // left view: [B][cap_l]
   const swm_keypoint* kr; const uint8_t* dr; const int32_t* nr;  // right view: [B][cap_r]
   int cap_l, cap_r;
-  const uint8_t* plain_l; const uint8_t* plain_r;                // un-blurred plane sets
+  const uint8_t* plain_l; const uint8_t* plain_r;                // un-blurred plane sets (border pixels)
+  const uint8_t* blur_l; const uint8_t* blur_r;                  // blurred plane sets (what mvImagePyramid holds after operator())
   float sf[SWM_MAX_LEVELS], inv_sf[SWM_MAX_LEVELS];
   float mbf, mb;
   float* u_right; float* depth; int32_t* sad;                    // [B][cap_l]
 };
+
+// pixel (x, y) of mvImagePyramid[level] as Frame::ComputeStereoMatches sees it: blurred inside the level, the reflect-101
+// border of the un-blurred buffer outside (both planes share one layout; `roi` = offset of level pixel (0,0))
+__device__ __forceinline__ int stereo_px(const uint8_t* __restrict__ plain, const uint8_t* __restrict__ blur, long long roi, int pitch,
+                                         int w, int h, int x, int y) {
+  const uint8_t* p = ((unsigned)x < (unsigned)w && (unsigned)y < (unsigned)h) ? blur : plain;
+  return p[roi + (long long)y * pitch + x];
+}
 
 __global__ void __launch_bounds__(256) stereo_match_kernel(const StereoArgs a) {
   const int f = blockIdx.y, lane = threadIdx.x & 31;
@@ -77,21 +89,19 @@ __global__ void __launch_bounds__(256) stereo_match_kernel(const StereoArgs a) {
     if (!(scaleduR0 < 0 || __fadd_rn(scaleduR0, 11.0f) >= (float)g.w)) {
       const long long roi = (long long)f * L->slab_bytes + g.plane_off + (long long)kEdge * g.pitch + kPadX;
       const int y0 = (int)scaledvL - 5, xL0 = (int)scaleduL - 5, xRm = (int)scaleduR0 - 10;  // xRm: window of incR = -5
-      const uint8_t* imL = a.plain_l + roi + (long long)y0 * g.pitch + xL0;
-      const uint8_t* imR = a.plain_r + roi + (long long)y0 * g.pitch + xRm;
-      const int cL = imL[5 * g.pitch + 5];
+      const int cL = stereo_px(a.plain_l, a.blur_l, roi, g.pitch, g.w, g.h, xL0 + 5, y0 + 5);
       int cR[11], sad[11];
 #pragma unroll
       for (int k = 0; k < 11; k++) {
-        cR[k] = imR[5 * g.pitch + 5 + k];
+        cR[k] = stereo_px(a.plain_r, a.blur_r, roi, g.pitch, g.w, g.h, xRm + 5 + k, y0 + 5);
         sad[k] = 0;
       }
       for (int pos = lane; pos < 121; pos += 32) {
         const int yy = pos / 11, xx = pos - yy * 11;
-        const int l = (int)imL[yy * g.pitch + xx] - cL;
-        const uint8_t* rrow = imR + yy * g.pitch + xx;
+        const int l = stereo_px(a.plain_l, a.blur_l, roi, g.pitch, g.w, g.h, xL0 + xx, y0 + yy) - cL;
 #pragma unroll
-        for (int k = 0; k < 11; k++) sad[k] += abs(l - ((int)rrow[k] - cR[k]));
+        for (int k = 0; k < 11; k++)
+          sad[k] += abs(l - (stereo_px(a.plain_r, a.blur_r, roi, g.pitch, g.w, g.h, xRm + xx + k, y0 + yy) - cR[k]));
       }
 #pragma unroll
       for (int k = 0; k < 11; k++) sad[k] = __reduce_add_sync(0xffffffffu, sad[k]);

@@ -115,6 +115,22 @@ class ORBextractor {
 
   swm_orb* handle() { return h_; }
 
+  // Frame::ComputeStereoMatches (reference Frame.cc:516-690) on the device, from the frames THIS extractor (the left
+  // view, Frame::mpORBextractorLeft) and `right` (mpORBextractorRight) extracted last: fills mvuRight / mvDepth for the
+  // N keypoints of the left view, bit-identical to the reference's loop (INTEGRATION.md shows the three-line body that
+  // replaces the member in Frame.cc).
+  void ComputeStereoMatches(ORBextractor& right, float mbf, float mb, int N, std::vector<float>& mvuRight,
+                            std::vector<float>& mvDepth) {
+    const int cap = swm_orb_max_keypoints(h_);
+    stereo_u_.resize(cap);
+    stereo_z_.resize(cap);
+    if (swm_orb_stereo_match(h_, right.h_, mbf, mb, stereo_u_.data(), stereo_z_.data(), cap) != SWM_OK)
+      throw std::runtime_error(std::string("ORBextractor::ComputeStereoMatches: ") + swm_last_error(h_));
+    if (N > cap) N = cap;
+    mvuRight.assign(stereo_u_.begin(), stereo_u_.begin() + N);
+    mvDepth.assign(stereo_z_.begin(), stereo_z_.begin() + N);
+  }
+
  protected:
   void refresh_pyramid_views() {
     mvImagePyramid.resize(nlevels_);
@@ -145,6 +161,7 @@ class ORBextractor {
   std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
   std::vector<cv::KeyPoint> kp_buf_;
   std::vector<unsigned char> desc_buf_;
+  std::vector<float> stereo_u_, stereo_z_;
 };
 
 }  // namespace ORB_SLAM2

@@ -169,6 +169,28 @@ int main(int argc, char** argv) {
   std::printf("resident: undistort-identity %d proj %d (host %d) same slots %d/%d bow %d (host %d)\n", (int)same_un, n_proj_res,
               n_proj, same_proj, f6.N, n_bow_res, n_bow);
   if (!same_un || n_proj_res != n_proj || same_proj != f6.N || n_bow_res != n_bow) { std::printf("HOST_WRAPPER_FAIL\n"); return 1; }
+  // Stereo: the right view is the left view moved 12 px to the left; ComputeStereoMatches must recover that disparity
+  {
+    cv::Mat imgR(h, w, CV_8U);
+    for (int y = 0; y < h; y++)
+      for (int x = 0; x < w; x++) imgR.ptr(y)[x] = img.ptr(y)[x + 12 < w ? x + 12 : w - 1];
+    ORB_SLAM2::ORBextractor exL(1000, 1.2f, 8, 20, 7), exR(1000, 1.2f, 8, 20, 7);
+    Frame fl, fr;
+    fill(fl, exL, img);
+    fill(fr, exR, imgR);
+    std::vector<float> uRight, depth;
+    const float mbf = 47.9f, mb = 47.9f / 458.654f;
+    exL.ComputeStereoMatches(exR, mbf, mb, fl.N, uRight, depth);
+    int n_st = 0, n_ok = 0;
+    for (int i = 0; i < fl.N; i++)
+      if (uRight[i] >= 0) {
+        n_st++;
+        const float d = fl.mvKeys[i].pt.x - uRight[i];
+        n_ok += d > 10.5f && d < 13.5f && depth[i] == mbf / d;
+      }
+    std::printf("stereo: %d of %d left keypoints matched, %d with the planted disparity\n", n_st, fl.N, n_ok);
+    if (n_st < fl.N / 4 || n_ok < n_st * 9 / 10) { std::printf("HOST_WRAPPER_FAIL stereo\n"); return 1; }
+  }
   // Vocabulary: a two-level synthetic tree in the ORBvoc.bin layout; transform() must fill DBoW2's containers
   {
     const int k = 4;

@@ -1,6 +1,6 @@
 """Frame::ComputeStereoMatches on the GPU (swm_orb_stereo_match, csrc/stereo.cuh) against the oracle
 (orc_stereo_matches, itself pinned to the reference's own body in tests/test_ref_stereo.py).  The oracle is fed the
-GPU extractor's own keypoints, descriptors and un-blurred planes, so the comparison isolates the stereo stage:
+GPU extractor's own keypoints, descriptors and pyramid (blurred in place inside its un-blurred border), so the comparison isolates the stereo stage:
 mvuRight and mvDepth must be bit-identical floats."""
 import numpy as np
 import pytest
@@ -8,6 +8,13 @@ import pytest
 from swarmmap_b200 import synth
 
 pytestmark = pytest.mark.gpu
+
+
+def _composite(ex, f, l):
+    """mvImagePyramid[l] after operator(): the bordered un-blurred buffer with the level blurred in place."""
+    buf = ex.debug_plane(f, l, 0).copy()
+    buf[19:-19, 19:-19] = ex.debug_plane(f, l, 1)
+    return buf
 
 
 def _pairs(w, h, seeds, **kw):
@@ -38,8 +45,8 @@ def test_stereo_matches_equal_oracle(oracle, swm, w, h, nfeat, kw, mbf, fx):
     sf, inv_sf, _, _ = oracle.scale_tables(1.2, 8)
     total = 0
     for f in range(B):
-        pl = [exl.debug_plane(f, l, 0) for l in range(8)]
-        pr = [exr.debug_plane(f, l, 0) for l in range(8)]
+        pl = [_composite(exl, f, l) for l in range(8)]
+        pr = [_composite(exr, f, l) for l in range(8)]
         u0, z0, n0 = oracle.stereo_matches(kl[f, :nl[f]], dl[f, :nl[f]], kr[f, :nr[f]], dr[f, :nr[f]], pl, pr, sf, inv_sf, mbf, mb)
         np.testing.assert_array_equal(u[f, :nl[f]].view(np.uint32), u0.view(np.uint32), err_msg=f"mvuRight frame {f}")
         np.testing.assert_array_equal(z[f, :nl[f]].view(np.uint32), z0.view(np.uint32), err_msg=f"mvDepth frame {f}")

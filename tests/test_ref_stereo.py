@@ -18,7 +18,12 @@ def _views(w, h, nfeat, seed, **kw):
     for img in (left, right):
         ex = oracle_lib.Extractor(nfeat, 1.2, 8, 20, 7)
         k, d = ex(img)
-        out.append((k, d, [ex.level(l, 0) for l in range(8)]))
+        planes = []
+        for l in range(8):  # mvImagePyramid[l] after operator(): blurred in place inside the un-blurred bordered buffer
+            buf = ex.level(l, 0).copy()
+            buf[19:-19, 19:-19] = ex.level(l, 1)
+            planes.append(buf)
+        out.append((k, d, planes))
     return out
 
 
