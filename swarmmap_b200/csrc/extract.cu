@@ -148,15 +148,21 @@ __global__ void __launch_bounds__(256) describe_kernel(const FrameLayout* __rest
   const int pitch = g.pitch;
 
   // IC_Angle (Fast_gpu.cu:403-460): integer moments over the radius-15 disc, one lane per column
-  const uint8_t* c = plain + off;
+  // (row pointers advance by the pitch and the disc half-widths are compile-time offsets: the loop is 2 loads + 6
+  // integer instructions per row pair, where index arithmetic per load used to be a third of this kernel)
+  const uint8_t* rp = plain + off + lane;  // row y + v, my column of the 31-wide window shifted by umax below
+  const uint8_t* rm = rp;                  // row y - v
   int m10 = 0, m01 = 0;
-  if (lane <= 2 * kHalfPatch) m10 = (lane - kHalfPatch) * (int)c[lane - kHalfPatch];
+  if (lane <= 2 * kHalfPatch) m10 = (lane - kHalfPatch) * (int)rp[-kHalfPatch];
 #pragma unroll
   for (int v = 1; v <= kHalfPatch; ++v) {
-    const int d = c_umax[v];
+    constexpr int kUmax[kHalfPatch + 1] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};  // ORBextractor.cc:380-404
+    const int d = kUmax[v];
+    rp += pitch;
+    rm -= pitch;
     if (lane <= 2 * d) {
       const int u = lane - d;
-      const int vp = c[u + v * pitch], vm = c[u - v * pitch];
+      const int vp = rp[-d], vm = rm[-d];
       m01 += v * (vp - vm);
       m10 += u * (vp + vm);
     }
@@ -736,7 +742,9 @@ int swm_orb_create(const swm_orb_cfg* cfg, int device, swm_orb** out) {
         umax[v] = v0;
         ++v0;
       }
-      cudaError_t e2 = cudaMemcpyToSymbol(c_umax, umax, sizeof(umax));
+      static const int kUmaxExpected[16] = {15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3};
+      cudaError_t e2 = memcmp(umax, kUmaxExpected, sizeof(umax)) == 0 ? cudaSuccess : cudaErrorInvalidValue;  // describe_kernel's compile-time table
+      if (e2 == cudaSuccess) e2 = cudaMemcpyToSymbol(c_umax, umax, sizeof(umax));
       if (e2 == cudaSuccess) {
         std::vector<float> pat(8 * 32 * 4);
         for (int t = 0; t < 32; t++)
