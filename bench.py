@@ -936,6 +936,38 @@ def main():
         for i in range(50):
             ex1(frames[i % distinct])
         latency["single_frame_operator_ms"] = (time.perf_counter() - t0) / 50 * 1e3
+        del ex1
+        # stereo front-end (Frame::ComputeStereoMatches, Frame.cc:516-690): 32 rectified pairs per call, both views
+        # resident from their extractors; informational, checked against the oracle on pair 0
+        sl, sr = synth.make_stereo_pair(W, H, 20220421)
+        SBT = 32
+        exl = ORBextractor(NFEAT, 1.2, 8, 20, 7, device=ctx.local_rank, max_batch=SBT)
+        exr = ORBextractor(NFEAT, 1.2, 8, 20, 7, device=ctx.local_rank, max_batch=SBT)
+        kl, dl, nl = exl.extract_batch(np.repeat(sl[None], SBT, 0))
+        kr, dr, nr = exr.extract_batch(np.repeat(sr[None], SBT, 0))
+        bf, bl = 47.90639384423901, 47.90639384423901 / 458.654
+        u, z = exl.stereo_match(exr, bf, bl, SBT)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            u, z = exl.stereo_match(exr, bf, bl, SBT)
+        latency["stereo_match_ms_per_pair"] = (time.perf_counter() - t0) / 10 / SBT * 1e3
+        latency["stereo_matches_per_pair"] = int((u[0, :nl[0]] >= 0).sum())
+        if cpu:
+            import oracle_lib
+
+            def comp(ex):
+                out = []
+                for l in range(8):
+                    buf = ex.debug_plane(0, l, 0).copy()
+                    buf[19:-19, 19:-19] = ex.debug_plane(0, l, 1)
+                    out.append(buf)
+                return out
+            sf_, isf_, _, _ = oracle_lib.scale_tables(1.2, 8)
+            u0, z0, _ = oracle_lib.stereo_matches(kl[0, :nl[0]], dl[0, :nl[0]], kr[0, :nr[0]], dr[0, :nr[0]], comp(exl), comp(exr),
+                                           sf_, isf_, bf, bl)
+            latency["stereo_identical_to_oracle"] = bool(np.array_equal(u[0, :nl[0]].view(np.uint32), u0.view(np.uint32)) and
+                                                         np.array_equal(z[0, :nl[0]].view(np.uint32), z0.view(np.uint32)))
+        del exl, exr
 
     # ---- reduce over ranks (max time), rank 0 prints
     (ms_total, ms_e2e, ms_pf, c_h2d, c_both), (cnt,) = ctx.reduce(

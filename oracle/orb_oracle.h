@@ -16,6 +16,7 @@
  *   Thirdparty/DBoW2 (transform, FORB::distance)                 tests/test_ref_dbow2.py
  *   ORBmatcher.cc with its own ORBmatcher.h, the grid / scale bodies of Frame.cc, KeyFrame.cc, MapPoint.cc:
  *     every Search*, Fuse, SearchBySim3, SearchForTriangulation  tests/test_ref_orbmatcher.py
+ *   Frame.cc:516-690 (ComputeStereoMatches, body cut at build time)  tests/test_ref_stereo.py
  *   cuda/Fast_gpu.cu, cuda/Orb_gpu.cu (nvcc, sm_100a, -use_fast_math): corner test + score, tile retry + NMS
  *     (single-tile launches of the real kernel and a lock-step run of its device functions), IC_Angle, rBRIEF
  *                                                                tests/test_gpu_ref_cuda.py (needs a GPU)

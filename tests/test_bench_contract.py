@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DEV_LINE = "r2u_bench.json"
+DEV_LINE = "r2y_bench.json"
 
 
 def _line(name):
