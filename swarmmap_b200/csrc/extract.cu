@@ -612,7 +612,10 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
       const int want_jobs = SWM_WALK_WAVES * h->n_sm * 24;
       const int nrb_want = std::max(1, (want_jobs + batch * a.nstrips - 1) / (batch * a.nstrips));
       int rows = (int)align_up((a.dst.h + nrb_want - 1) / nrb_want, 4);
-      rows = std::min(64, std::max(batch >= 4 ? 16 : 8, rows));
+#ifndef SWM_WALK_MAXROWS
+#define SWM_WALK_MAXROWS 64
+#endif
+      rows = std::min(SWM_WALK_MAXROWS, std::max(batch >= 4 ? 16 : 8, rows));
       a.nrb = (a.dst.h + rows - 1) / rows;
       a.rows_per_job = (int)align_up((a.dst.h + a.nrb - 1) / a.nrb, 4);
       a.nrb = (a.dst.h + a.rows_per_job - 1) / a.rows_per_job;
