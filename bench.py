@@ -861,7 +861,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=4096, help="frames per step per GPU")
+    ap.add_argument("--batch", type=int, default=8192, help="frames per step per GPU (8192 x 20 steps = a timed region above 1 s)")
     ap.add_argument("--impl", default="swm", choices=["swm", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only", default="", help="comma list of workloads to run besides the headline (kitti,tracking,place); default all")

@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DEV_LINE = "r2y_bench.json"
+DEV_LINE = "r2z_bench.json"
 
 
 def _line(name):
@@ -45,7 +45,7 @@ def test_device_arm_line_has_every_contract_key():
         "hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     h = d["hamming"]
     assert h["roofline"]["bound"] == "tensor" and 0 < h["roofline"]["frac"] < 1.2
-    assert d["config"]["timed_region_s"] > 0.5 and e["timed_region_s"] > 0.5
+    assert d["config"]["timed_region_s"] >= 1.0 and e["timed_region_s"] >= 1.0
     assert 0 < e["h2d_ceiling"]["e2e_frac_of_ceiling"] <= 1.05
     # one record per remaining BASELINE.json config, each with its own workload, device value, e2e and a parity check
     w = d["workloads"]
