@@ -123,8 +123,8 @@ int swm_orb_stereo_match(swm_orb* left, swm_orb* right, float bf, float b, float
 /* Re-runs the selected stages on the data of the last *_device/_batch call (the caller brackets it with
  * CUDA events on `stream`): per-stage timing for bench.py's roofline and stage breakdown. */
 int swm_orb_run_stage(swm_orb* h, int stage_mask, int batch, void* stream);
-#define SWM_STAGE_PYRAMID 1 /* pyramid + border + Gaussian blur (pyr_kernel x nlevels) */
-#define SWM_STAGE_NMS 2     /* FAST score + tile retry + non-max suppression (fast_kernel x 2) */
+#define SWM_STAGE_PYRAMID 1 /* pyramid + border + Gaussian blur (pyr_walk_kernel x nlevels) */
+#define SWM_STAGE_NMS 2     /* FAST score + tile retry + non-max suppression (fast_tile_kernel x 2) */
 #define SWM_STAGE_OCTREE 4
 #define SWM_STAGE_DESCRIBE 8 /* orientation + rBRIEF + output assembly */
 
