@@ -774,22 +774,46 @@ def workload_place(ctx, cpu):
     if ctx.world > 1:
         comm, nccl = place.nccl_comm_from_torch(ctx.local_rank)
 
+    # N > 1: the exchange runs over peer memory inside the merge kernel (swm_db_query_peers); the NCCL form
+    # (swm_db_query_sharded: scan, ncclAllGather, merge) is timed beside it and must give the same keys and votes
+    peers = False
+    if ctx.world > 1:
+        try:
+            shard.enable_peers(nq_max=NQ)
+            peers = True
+        except Exception as e:  # no peer access between these GPUs: the NCCL form is the product path
+            if ctx.rank == 0:
+                print(f"place: peer-memory exchange unavailable ({e}); NCCL exchange", file=sys.stderr)
+        (_,), (npeers,) = ctx.reduce([0.0], [1.0 if peers else 0.0])
+        peers = int(npeers) == ctx.world  # a collective: all ranks or none
+
+    def query_nccl():
+        return shard.query_sharded(q, comm, ctx.world, 2, 50)
+
     def query():
         if ctx.world > 1:
-            return shard.query_sharded(q, comm, ctx.world, 2, 50)
+            return shard.query_peers(q, 2, 50) if peers else query_nccl()
         return shard.query(q, 2, 50)
 
-    for _ in range(2):
-        keys, votes = query()
-    ctx.barrier()
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        ctx.barrier()
+        reps_ = 10
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps_):
+            out = fn()
+        b.record()
+        ctx.barrier()
+        return a.elapsed_time(b) / reps_, out
+
     reps = 10
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        keys, votes = query()
-    e1.record()
-    ctx.barrier()
-    ms = e0.elapsed_time(e1) / reps
+    ms, (keys, votes) = timed(query)
+    ms_nccl, same_as_nccl = None, None
+    if ctx.world > 1 and peers:
+        ms_nccl, (keys_n, votes_n) = timed(query_nccl)
+        same_as_nccl = bool(torch.equal(keys, keys_n) and torch.equal(votes, votes_n))
     # e2e: host query descriptors in, host keys + votes out
     hq = q.cpu().pin_memory()
     ctx.barrier()
@@ -797,7 +821,7 @@ def workload_place(ctx, cpu):
     for _ in range(reps):
         dq = hq.to(ctx.dev, non_blocking=True)
         if ctx.world > 1:
-            k2, v2 = shard.query_sharded(dq, comm, ctx.world, 2, 50)
+            k2, v2 = shard.query_peers(dq, 2, 50) if peers else shard.query_sharded(dq, comm, ctx.world, 2, 50)
         else:
             k2, v2 = shard.query(dq, 2, 50)
         k_h, v_h = k2.cpu(), v2.cpu()
@@ -832,17 +856,23 @@ def workload_place(ctx, cpu):
     lib.swm_i8_peak(ctx.local_rank, 1, 4096, C.byref(peak256))
     if comm is not None:
         nccl.ncclCommDestroy(comm)
-    (ms_r, wall_r), _ = ctx.reduce([ms, wall])
+    (ms_r, wall_r, ms_nccl_r), (same_all,) = ctx.reduce([ms, wall, ms_nccl or 0.0], [1.0 if same_as_nccl in (None, True) else 0.0])
+    if ctx.world > 1 and peers:
+        parity["peer_exchange_identical_to_nccl_exchange"] = int(same_all) == ctx.world
     pairs = float(NQ) * NKF * DPK
     ops = pairs * 512 / (ms_r * 1e-3) / 1e12
     return {"config": {"workload": "BASELINE config 5: 2000 query descriptors x 100 000 keyframes x 256 descriptors (25.6 M, 819 MB), 1 % "
                                    "planted noisy copies, top-2 + per-keyframe votes, database sharded by keyframe id over the ranks",
-                       "scaling": "strong", "n_gpus": ctx.world, "exchange": "ncclAllGather of (2000, 2) 64-bit keys inside swm_db_query_sharded"
-                       if ctx.world > 1 else "none (one shard)"},
+                       "scaling": "strong", "n_gpus": ctx.world,
+                       "exchange": ("none (one shard)" if ctx.world == 1 else
+                                    "peer-memory stores of the (2000, 2) 64-bit key blocks + flags over NVLink inside the merge kernel "
+                                    "(swm_db_query_peers: scan + ONE fused kernel)" if peers else
+                                    "ncclAllGather of (2000, 2) 64-bit keys inside swm_db_query_sharded"),
+                       "ms_per_query_batch_nccl_exchange": (ms_nccl_r if ctx.world > 1 and peers else None)},
             "metric": "hamming_matches_per_sec", "unit": "256-bit pairs/s", "value": pairs / (ms_r * 1e-3),
             "ms_per_query_batch": ms_r, "e2e": {"value": pairs / (wall_r * 1e-3), "unit": "256-bit pairs/s", "ms_per_query_batch": wall_r,
                                                 "h2d_bytes_per_step": NQ * 32, "d2h_bytes_per_step": NQ * 16 + n_kf * 4},
-            "kernel": "db_top2_umma_kernel (tcgen05 kind::i8, A in TMEM, accumulators in TMEM) + db_merge_kernel",
+            "kernel": "db_top2_umma_kernel (tcgen05 kind::i8, A in TMEM, accumulators in TMEM) + db_merge_kernel / db_merge_peers_kernel",
             "roofline": {"bound": "tensor", "unit": "TOP/s (int8)", "achieved": ops / ctx.world, "peak": max(peak.value, peak256.value),
                          "frac": ops / ctx.world / max(peak.value, peak256.value, 1e-9),
                          "issued": ops / ctx.world * 288.0 / 256.0,

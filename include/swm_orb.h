@@ -441,6 +441,22 @@ int swm_db_merge_gathered(swm_db* db, const uint64_t* d_gathered, int world, int
  * d_topk (nq x k) is identical on every rank; d_votes: this shard's keyframes, as in swm_db_merge_gathered. */
 int swm_db_query_sharded(swm_db* db, void* nccl_comm, int world, const uint8_t* d_q, int nq, int k, uint64_t* d_topk,
                          int32_t* d_votes, int th_votes, void* stream);
+/* The same sharded query with the exchange over PEER MEMORY (NVLink / NVSwitch) inside the merge kernel instead of an
+ * NCCL collective: every rank owns a window that its peers store their (nq, k) key block into, publish a flag, and wait
+ * for the others' flags -- one kernel per rank after the shard scan (db_merge_peers_kernel, csrc/match.cu).  All ranks
+ * live on one node with peer access between their GPUs.
+ *   swm_db_peer_window: allocate this rank's window for `world` ranks and up to nq_max (<= 8192) queries; returns its
+ *     cudaIpcMemHandle_t as 64 opaque bytes (ipc_handle64, may be NULL) and / or its device address (window, may be
+ *     NULL) for ranks that share the process;
+ *   swm_db_peer_open: give the windows of all ranks in rank order -- either world x 64 bytes of IPC handles gathered
+ *     from the other processes by whatever transport the server has (MPI, torch.distributed, a socket), or an array of
+ *     device addresses when the ranks share a process; the entry of `rank` itself is ignored;
+ *   swm_db_query_peers: a collective -- every rank enqueues it with the same nq and k, the same number of times;
+ *     results as swm_db_query_sharded.  Three enqueues become two (scan, fused merge + exchange + merge). */
+int swm_db_peer_window(swm_db* db, int world, int nq_max, void* ipc_handle64, void** window);
+int swm_db_peer_open(swm_db* db, int rank, const void* ipc_handles, void* const* windows);
+int swm_db_query_peers(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t* d_topk, int32_t* d_votes, int th_votes,
+                       void* stream);
 int64_t swm_db_size(const swm_db* db);
 /* Measured int8 rate of the tensor pipe on `device`, in TOP/s: one CTA per SM issues `iters` back-to-back tcgen05
  * kind::i8 MMAs and nothing else (mode 0: 128 x 64 x 32 with A in TMEM, the shape the shard scan issues; mode 1:

@@ -156,6 +156,9 @@ SYMBOLS = [
     ("swm_db_query_device", _i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     ("swm_db_merge_gathered", _i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp]),
     ("swm_db_query_sharded", _i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp]),
+    ("swm_db_peer_window", _i, [_vp, _i, _i, _vp, _vp]),
+    ("swm_db_peer_open", _i, [_vp, _i, _vp, _vp]),
+    ("swm_db_query_peers", _i, [_vp, _vp, _i, _i, _vp, _vp, _i, _vp]),
     ("swm_db_size", _i64, [_vp]),
     ("swm_i8_peak", _i, [_i, _i, _i, _vp]),
 ]

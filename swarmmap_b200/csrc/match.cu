@@ -1176,6 +1176,95 @@ __global__ void db_merge_kernel(const unsigned long long* __restrict__ partial, 
   (void)first_kf;
 }
 
+
+// ---- Sharded place query, exchange over PEER MEMORY (NVLink / NVSwitch) inside the merge kernel.
+// Every rank owns a window that its peers write into: keys[2][world][nq_max][2] (u64) followed by flags[2][world][kPeerBlocks]
+// (u32), the leading 2 = parity of the query sequence number (a rank can be at most one query ahead of a peer: it
+// cannot finish query s + 1 before that peer has pushed s + 1, which it does after it finished reading s).
+// One launch per rank does what swm_db_query_sharded needs three enqueues for (slice merge, all-gather, final merge):
+//   1. merge this shard's slice results for my queries (as db_merge_kernel);
+//   2. store the (nq, k) keys into slot `rank` of EVERY rank's window -- remote stores over NVLink --, fence, then
+//      publish flag[rank][block] = seq in each window (release, system scope);
+//   3. wait until my own window holds flag[r][block] == seq for every r (acquire), merge the world key blocks with
+//      L1-bypassing loads, write the global top-k and cast this shard's votes.
+// CTAs only wait for the SAME block index of the other ranks and the whole grid (ceil(nq / 128) CTAs) is resident at
+// once, so the launch behaves like a collective: every rank must enqueue it with the same nq, k and seq.
+constexpr int kPeerBlocks = 64;  // CTAs of 128 queries: nq <= 8192 per call
+constexpr int kPeerMaxWorld = 16;
+struct PeerWindows {
+  unsigned long long* keys[kPeerMaxWorld];  // window base of rank r as mapped in THIS process
+};
+__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(128) db_merge_peers_kernel(const unsigned long long* __restrict__ partial, int nparts, int nq, int k,
+                                                             PeerWindows win, int rank, int world, int nq_max, unsigned int seq,
+                                                             unsigned long long* __restrict__ topk, int32_t* __restrict__ votes,
+                                                             int th_votes, int desc_per_kf, long long first_index, long long n_kf) {
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  const int par = (int)(seq & 1u);
+  const size_t keys_per_par = (size_t)world * nq_max * 2;
+  const size_t flag_base = 2 * keys_per_par;  // in u64 units; flags follow the keys
+  // 1. this shard's top-2 of my query
+  unsigned long long k0 = ~0ull, k1 = ~0ull;
+  if (qi < nq) {
+    for (int p = 0; p < nparts; p++)
+      for (int e = 0; e < 2; e++) {
+        const unsigned long long key = partial[((size_t)p * nq + qi) * 2 + e];
+        if (key < k1) {
+          if (key < k0) { k1 = k0; k0 = key; }
+          else k1 = key;
+        }
+      }
+    // 2a. push into slot `rank` of every window
+    const size_t slot = (size_t)par * keys_per_par + ((size_t)rank * nq_max + qi) * 2;
+    for (int r = 0; r < world; r++) {
+      unsigned long long* w = win.keys[r] + slot;
+      w[0] = k0;
+      w[1] = k1;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  // 2b. publish: one flag per (writer rank, block) in every window
+  if (threadIdx.x < world) {
+    unsigned int* flags = reinterpret_cast<unsigned int*>(win.keys[threadIdx.x] + flag_base);
+    st_release_sys(flags + ((size_t)par * world + rank) * kPeerBlocks + blockIdx.x, seq);
+  }
+  // 3. wait for every rank's block in MY window
+  if (threadIdx.x < world) {
+    const unsigned int* flags = reinterpret_cast<const unsigned int*>(win.keys[rank] + flag_base);
+    const unsigned int* f = flags + ((size_t)par * world + threadIdx.x) * kPeerBlocks + blockIdx.x;
+    long long spins = 0;
+    while (ld_acquire_sys(f) != seq)
+      if (++spins > (1ll << 31)) __trap();  // a rank that never arrives must abort, not hang the GPU
+  }
+  __syncthreads();
+  if (qi >= nq) return;
+  k0 = k1 = ~0ull;
+  const unsigned long long* mine = win.keys[rank] + (size_t)par * keys_per_par;
+  for (int r = 0; r < world; r++)
+    for (int e = 0; e < k; e++) {
+      const unsigned long long key = __ldcg(mine + ((size_t)r * nq_max + qi) * 2 + e);  // written by a peer: not through L1
+      if (key < k1) {
+        if (key < k0) { k1 = k0; k0 = key; }
+        else k1 = key;
+      }
+    }
+  topk[(size_t)qi * k] = k0;
+  if (k > 1) topk[(size_t)qi * k + 1] = k1;
+  if (votes && k0 != ~0ull && (int)(k0 >> 48) <= th_votes) {
+    const long long idx = (long long)(k0 & 0xFFFFFFFFFFFFull) - first_index;  // < 0: another shard's keyframe
+    const long long kf = idx / desc_per_kf;
+    if (idx >= 0 && kf < n_kf) atomicAdd(votes + kf, 1);
+  }
+}
+
 }  // namespace swm
 
 // =================================================================================================
@@ -2412,6 +2501,13 @@ struct swm_db {
   // swm_db_query_sharded: this shard's (nq, k) key block and the all-gathered (world, nq, k) blocks, grow-only
   unsigned long long* d_exchange = nullptr;
   size_t exchange_cap = 0;
+  // swm_db_query_peers: my exchange window (peers write into it) and the peers' windows as mapped here
+  unsigned long long* d_window = nullptr;
+  size_t window_bytes = 0;
+  int peer_world = 0, peer_rank = -1, peer_nq_max = 0;
+  unsigned int peer_seq = 0;
+  unsigned long long* peer_win[16] = {};
+  bool peer_ipc[16] = {};  // opened with cudaIpcOpenMemHandle (to be closed), as opposed to a same-process pointer
 };
 
 extern "C" {
@@ -2462,6 +2558,9 @@ void swm_db_destroy(swm_db* db) {
   if (db->owns) cudaFree(db->d_desc);
   cudaFree(db->d_partial);
   cudaFree(db->d_exchange);
+  for (int r = 0; r < 16; r++)
+    if (db->peer_ipc[r] && db->peer_win[r]) cudaIpcCloseMemHandle(db->peer_win[r]);
+  cudaFree(db->d_window);
   delete db;
 }
 
@@ -2494,11 +2593,10 @@ int swm_i8_peak(int device, int mode, int iters, double* tops) {
   return SWM_OK;
 }
 
-int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t* d_topk, int32_t* d_votes,
-                        int th_votes, void* stream) {
-  if (!db || !d_q || nq <= 0 || k < 1 || k > 2 || !d_topk) return SWM_E_INVALID;
-  if (cudaSetDevice(db->device) != cudaSuccess) return SWM_E_CUDA;
-  cudaStream_t st = (cudaStream_t)stream;
+}  // extern "C"
+
+// The shard scan: slices x query blocks of one of the three top-2 kernels into db->d_partial ([parts][nq][2] keys).
+static int db_scan(swm_db* db, const uint8_t* d_q, int nq, cudaStream_t st, long long* parts_out) {
   // Three kernels produce identical keys.  Default: tcgen05 int8 (db_umma.cuh).  SWM_DB_KERNEL=imma selects the
   // legacy mma.sync kernel, SWM_DB_KERNEL=popc the CUDA-core LOP3+POPC kernel; both are kept as A/B baselines for
   // profiles/ and as independent implementations the parity tests cross-check.
@@ -2541,9 +2639,100 @@ int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t*
     umma::db_top2_umma_kernel<<<grid, umma::kThreads, umma::kSmemBytes, st>>>(
         (const uint4*)db->d_desc, db->ndesc, first_index, (const uint4*)d_q, nq, tiles_per_cta, db->d_partial);
   }
+  *parts_out = parts;
+  return cudaGetLastError() == cudaSuccess ? SWM_OK : SWM_E_CUDA;
+}
+
+extern "C" {
+
+int swm_db_query_device(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t* d_topk, int32_t* d_votes,
+                        int th_votes, void* stream) {
+  if (!db || !d_q || nq <= 0 || k < 1 || k > 2 || !d_topk) return SWM_E_INVALID;
+  if (cudaSetDevice(db->device) != cudaSuccess) return SWM_E_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long parts = 0;
+  const int rc = db_scan(db, d_q, nq, st, &parts);
+  if (rc != SWM_OK) return rc;
+  const long long first_index = db->first_kf * db->desc_per_kf;
   const long long n_kf = (db->ndesc + db->desc_per_kf - 1) / db->desc_per_kf;
   db_merge_kernel<<<(nq + 127) / 128, 128, 0, st>>>(db->d_partial, (int)parts, nq, 2, k, (unsigned long long*)d_topk,
                                                     d_votes, th_votes, db->first_kf, db->desc_per_kf, first_index, n_kf);
+  return cudaGetLastError() == cudaSuccess ? SWM_OK : SWM_E_CUDA;
+}
+
+// ---- peer-memory exchange (see db_merge_peers_kernel)
+static size_t peer_window_bytes(int world, int nq_max) {
+  return (size_t)2 * world * nq_max * 2 * sizeof(unsigned long long) + (size_t)2 * world * kPeerBlocks * sizeof(unsigned int);
+}
+
+int swm_db_peer_window(swm_db* db, int world, int nq_max, void* ipc_handle64, void** window) {
+  if (!db || world < 1 || world > kPeerMaxWorld || nq_max < 1 || nq_max > 128 * kPeerBlocks) return SWM_E_INVALID;
+  if (cudaSetDevice(db->device) != cudaSuccess) return SWM_E_CUDA;
+  for (int r = 0; r < 16; r++) {
+    if (db->peer_ipc[r] && db->peer_win[r]) cudaIpcCloseMemHandle(db->peer_win[r]);
+    db->peer_win[r] = nullptr;
+    db->peer_ipc[r] = false;
+  }
+  cudaFree(db->d_window);
+  db->d_window = nullptr;
+  db->peer_world = 0;
+  db->peer_rank = -1;
+  const size_t bytes = peer_window_bytes(world, nq_max);
+  if (cudaMalloc(&db->d_window, bytes) != cudaSuccess) return SWM_E_CUDA;
+  if (cudaMemset(db->d_window, 0, bytes) != cudaSuccess) return SWM_E_CUDA;  // flags start at 0; sequence numbers start at 1
+  db->window_bytes = bytes;
+  db->peer_nq_max = nq_max;
+  db->peer_world = world;
+  db->peer_seq = 0;
+  if (ipc_handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the handle is exchanged as 64 opaque bytes");
+    cudaIpcMemHandle_t hdl;
+    if (cudaIpcGetMemHandle(&hdl, db->d_window) != cudaSuccess) return SWM_E_CUDA;
+    memcpy(ipc_handle64, &hdl, 64);
+  }
+  if (window) *window = db->d_window;
+  return SWM_OK;
+}
+
+int swm_db_peer_open(swm_db* db, int rank, const void* ipc_handles, void* const* windows) {
+  if (!db || !db->d_window || rank < 0 || rank >= db->peer_world || (!ipc_handles && !windows)) return SWM_E_INVALID;
+  if (cudaSetDevice(db->device) != cudaSuccess) return SWM_E_CUDA;
+  for (int r = 0; r < db->peer_world; r++) {
+    if (r == rank) {
+      db->peer_win[r] = db->d_window;
+    } else if (windows) {  // same process (tests, a server that drives several GPUs from one process)
+      db->peer_win[r] = static_cast<unsigned long long*>(windows[r]);
+    } else {
+      cudaIpcMemHandle_t hdl;
+      memcpy(&hdl, static_cast<const char*>(ipc_handles) + 64 * (size_t)r, 64);
+      void* p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, hdl, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return SWM_E_CUDA;
+      db->peer_win[r] = static_cast<unsigned long long*>(p);
+      db->peer_ipc[r] = true;
+    }
+    if (!db->peer_win[r]) return SWM_E_INVALID;
+  }
+  db->peer_rank = rank;
+  return SWM_OK;
+}
+
+int swm_db_query_peers(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t* d_topk, int32_t* d_votes, int th_votes,
+                       void* stream) {
+  if (!db || !d_q || nq <= 0 || k < 1 || k > 2 || !d_topk) return SWM_E_INVALID;
+  if (db->peer_rank < 0 || nq > db->peer_nq_max) return SWM_E_STATE;
+  if (cudaSetDevice(db->device) != cudaSuccess) return SWM_E_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long parts = 0;
+  const int rc = db_scan(db, d_q, nq, st, &parts);
+  if (rc != SWM_OK) return rc;
+  PeerWindows win;
+  for (int r = 0; r < kPeerMaxWorld; r++) win.keys[r] = r < db->peer_world ? db->peer_win[r] : nullptr;
+  const long long first_index = db->first_kf * db->desc_per_kf;
+  const long long n_kf = (db->ndesc + db->desc_per_kf - 1) / db->desc_per_kf;
+  db->peer_seq++;
+  db_merge_peers_kernel<<<(nq + 127) / 128, 128, 0, st>>>(db->d_partial, (int)parts, nq, k, win, db->peer_rank, db->peer_world,
+                                                          db->peer_nq_max, db->peer_seq, (unsigned long long*)d_topk, d_votes,
+                                                          th_votes, db->desc_per_kf, first_index, n_kf);
   return cudaGetLastError() == cudaSuccess ? SWM_OK : SWM_E_CUDA;
 }
 

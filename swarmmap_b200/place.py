@@ -160,6 +160,56 @@ class PlaceShard:
             raise _lib.SwmError(f"swm_db_query_sharded: {_lib.ERRORS.get(rc, rc)}")
         return merged, votes
 
+    def enable_peers(self, nq_max=2048, group=None, same_process=None):
+        """Set up the peer-memory exchange (swm_db_peer_window / swm_db_peer_open).  Across processes (one rank per GPU,
+        torch.distributed initialised): the 64-byte IPC handles of the windows are all-gathered through the group.
+        same_process: a list of PlaceShard objects in rank order that share this process (tests on one GPU, a server
+        driving several GPUs): call it on every shard after all of them exist."""
+        if same_process is not None:
+            world, rank = len(same_process), same_process.index(self)
+            wins = (C.c_void_p * world)()
+            for r, sh in enumerate(same_process):
+                if getattr(sh, "_window", None) is None or sh._peer_world != world or sh._peer_nq_max < nq_max:
+                    w = C.c_void_p()
+                    rc = sh._lib.swm_db_peer_window(sh._h, world, int(nq_max), None, C.byref(w))
+                    if rc != 0:
+                        raise _lib.SwmError(f"swm_db_peer_window: {_lib.ERRORS.get(rc, rc)}")
+                    sh._window, sh._peer_world, sh._peer_nq_max = w.value, world, int(nq_max)
+                wins[r] = sh._window
+            rc = self._lib.swm_db_peer_open(self._h, rank, None, wins)
+            if rc != 0:
+                raise _lib.SwmError(f"swm_db_peer_open: {_lib.ERRORS.get(rc, rc)}")
+            return
+        group = group if group is not None else self.group
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        hdl = (C.c_uint8 * 64)()
+        rc = self._lib.swm_db_peer_window(self._h, world, int(nq_max), hdl, None)
+        if rc != 0:
+            raise _lib.SwmError(f"swm_db_peer_window: {_lib.ERRORS.get(rc, rc)}")
+        mine = torch.tensor(list(bytes(hdl)), dtype=torch.uint8, device=self.device)
+        allh = torch.empty((world, 64), dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(allh, mine, group=group)
+        raw = bytes(allh.cpu().numpy().tobytes())
+        rc = self._lib.swm_db_peer_open(self._h, rank, raw, None)
+        if rc != 0:
+            raise _lib.SwmError(f"swm_db_peer_open: {_lib.ERRORS.get(rc, rc)}")
+        dist.barrier(group=group)  # every window is mapped everywhere before the first push
+
+    def query_peers(self, q, k=2, th_votes=50):
+        """Global top-k with the exchange over peer memory inside the merge kernel (swm_db_query_peers): a collective,
+        every rank calls it with the same number of queries.  Returns (keys (nq,k), this shard's votes)."""
+        dq = q.to(self.device).contiguous() if isinstance(q, torch.Tensor) else \
+            torch.from_numpy(np.ascontiguousarray(q, np.uint8)).to(self.device)
+        nq = int(dq.shape[0])
+        merged = torch.empty((nq, k), dtype=torch.int64, device=self.device)
+        votes = torch.zeros(self.n_kf, dtype=torch.int32, device=self.device)
+        st = torch.cuda.current_stream(self.device)
+        rc = self._lib.swm_db_query_peers(self._h, dq.data_ptr(), nq, k, merged.data_ptr(), votes.data_ptr(),
+                                          int(th_votes), C.c_void_p(st.cuda_stream))
+        if rc != 0:
+            raise _lib.SwmError(f"swm_db_query_peers: {_lib.ERRORS.get(rc, rc)}")
+        return merged, votes
+
     def votes_from_global(self, merged, th_votes):
         """Per-keyframe votes of THIS shard from the merged result: a query votes for the keyframe owning
         its global best match when that distance is <= th_votes (TH_LOW); summed over ranks this equals

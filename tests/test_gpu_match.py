@@ -416,3 +416,36 @@ def test_db_merge_gathered_equals_single_shard(oracle, swm, k):
         assert torch.equal(merged, fk)
         votes_sum[s.first_kf:s.first_kf + s.n_kf] += votes
     assert torch.equal(votes_sum, fv)
+
+
+@pytest.mark.parametrize("world,k", [(1, 2), (2, 2), (3, 1), (4, 2)])
+def test_db_query_peers_equals_single_shard(oracle, swm, world, k):
+    """The peer-memory exchange (db_merge_peers_kernel: push into every rank's window, flags, wait, merge) with `world`
+    shards driven from ONE process on one GPU, each on its own stream so that the kernels really wait for each other:
+    every rank gets the keys of the single-shard scan, the votes sum to the single-shard histogram, and a second and
+    third query reuse the windows (sequence parity)."""
+    import torch
+    from swarmmap_b200 import place
+    rng = np.random.default_rng(31 + world)
+    per_kf = 8
+    q, db = _db_case(rng, 500, 32000)
+    full = place.PlaceShard(db, per_kf, 0)
+    n_kf = len(db) // per_kf
+    cuts = [0] + sorted(int(c) // per_kf * per_kf for c in rng.choice(np.arange(4000, 28000), world - 1, replace=False)) + [len(db)]
+    shards = [place.PlaceShard(db[cuts[r]:cuts[r + 1]], per_kf, cuts[r] // per_kf) for r in range(world)]
+    for sh in shards:
+        sh.enable_peers(nq_max=512, same_process=shards)
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    for rep, nq in enumerate((500, 77, 500)):
+        qq = torch.from_numpy(q[:nq])
+        fk, fv = full.query_local(qq, k, 50)
+        outs = []
+        for r in (list(range(world)) if rep != 1 else list(reversed(range(world)))):  # any enqueue order
+            with torch.cuda.stream(streams[r]):
+                outs.append((r, shards[r].query_peers(qq, k, 50)))
+        torch.cuda.synchronize()
+        votes_sum = torch.zeros(n_kf, dtype=torch.int32, device="cuda")
+        for r, (keys, votes) in outs:
+            assert torch.equal(keys, fk), f"rank {r} rep {rep}"
+            votes_sum[shards[r].first_kf:shards[r].first_kf + shards[r].n_kf] += votes
+        assert torch.equal(votes_sum, fv)
