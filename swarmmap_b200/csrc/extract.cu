@@ -642,11 +642,12 @@ int enqueue(swm_orb* h, int mask, const uint8_t* d_imgs, int batch, int stride, 
     fa.cand_count = d_cand_count;
     fa.dbg_score = dbg;
     fa.run_len = h->fast_run;
-    fast_tile_kernel<1><<<grid, 32, 0, st>>>(fa);
+    if (dbg) fast_tile_kernel<1, true><<<grid, 32, 0, st>>>(fa);
+    else fast_tile_kernel<1, false><<<grid, 32, 0, st>>>(fa);
     fa.dbg_score = nullptr;
     // pass 2 walks the retry list with a persistent grid; a single frame has few runs, so it gets few warps to start
     const int grid2 = std::min(h->n_sm * 24, std::max(h->n_sm, L.fblk_total * batch / 4));
-    fast_tile_kernel<2><<<grid2, 32, 0, st>>>(fa);
+    fast_tile_kernel<2, false><<<grid2, 32, 0, st>>>(fa);
     launches += 2;
   }
   if (mask & SWM_STAGE_OCTREE) {

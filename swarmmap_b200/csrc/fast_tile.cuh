@@ -122,7 +122,9 @@ struct FastArgs {
   int run_len;               // tiles per run: kFT for batches (set-up amortised), 1 for a single-frame handle (latency)
 };
 
-template <int kPass>
+// kDbg (pass 1 only): keep the score map S at minThFAST for the parity tests; the product instantiation detects at
+// iniThFAST, where every non-zero score already is >= iniThFAST and the S_hi clamp of the neighbours is a no-op.
+template <int kPass, bool kDbg>
 __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
   __shared__ __align__(128) uint8_t s_px[FT_BUFS][FT_ROWS * FT_PITCH];
   __shared__ __align__(16) uint8_t s_sc[FT_ROWS * FT_SCP];
@@ -142,7 +144,8 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
   }
   __syncwarp();
   uint32_t phbits = 0;
-  const int th_run = (kPass == 1 && a.dbg_score == nullptr) ? a.ini_th : a.min_th;
+  bool cm_valid = false;  // s_colmask holds the masks of an unclipped tile
+  const int th_run = (kPass == 1 && !kDbg) ? a.ini_th : a.min_th;
   const uint32_t c7 = (uint32_t)(127 - th_run) * 0x01010101u;
 
   for (int work = blockIdx.x;; work += gridDim.x) {
@@ -200,13 +203,18 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
       const int X0 = kEdge + 32 * (tx0 + j);   // first interior pixel (level coords); staged origin (X0-19, Y0-4)
       // score tile cleared; scored columns of each word: interior +- 1 px and level x in [19, w - 19)
       for (int i = lane; i < FT_ROWS * FT_SCP / 16; i += 32) reinterpret_cast<uint4*>(s_sc)[i] = make_uint4(0, 0, 0, 0);
-      if (lane < 2 * FT_QP) {
-        uint32_t m = 0;
-        for (int k = 0; k < 4; k++) {
-          const int lx = 4 * (FT_QW0 + lane) + k, gx = X0 - kFx + lx;
-          if (lx >= kFx - 1 && lx <= kFx + 32 && gx >= kEdge && gx < w - kEdge) m |= 0x80u << (8 * k);
+      // (only the first tile of a level row and one that reaches the right end of the FAST band have clipped masks)
+      const bool clipped = X0 + 32 >= w - kEdge || X0 - 1 < kEdge;
+      if (!cm_valid || clipped) {
+        if (lane < 2 * FT_QP) {
+          uint32_t m = 0;
+          for (int k = 0; k < 4; k++) {
+            const int lx = 4 * (FT_QW0 + lane) + k, gx = X0 - kFx + lx;
+            if (lx >= kFx - 1 && lx <= kFx + 32 && gx >= kEdge && gx < w - kEdge) m |= 0x80u << (8 * k);
+          }
+          s_colmask[lane] = m;
         }
-        s_colmask[lane] = m;
+        cm_valid = !clipped;
       }
       mbar_wait(&s_bar[buf], (phbits >> buf) & 1u);
       phbits ^= 1u << buf;
@@ -303,23 +311,31 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
           lx = e & 255;
           const uint32_t sp = sc_u32 + (uint32_t)(ly * FT_SCP + lx - FT_SCX);
           sc = (int)lds8(sp);
-          kp = true;
+          if (kPass == 1 && !kDbg) {
+            // every stored score is 0 or >= iniThFAST: strict maximum of the raw 3x3 neighbourhood
+            const int m0 = max(max((int)lds8(sp - FT_SCP - 1), (int)lds8(sp - FT_SCP)), (int)lds8(sp - FT_SCP + 1));
+            const int m1 = max(max((int)lds8(sp - 1), (int)lds8(sp + 1)), (int)lds8(sp + FT_SCP - 1));
+            const int m2 = max((int)lds8(sp + FT_SCP), (int)lds8(sp + FT_SCP + 1));
+            kp = sc > max(max(m0, m1), m2);
+          } else {
+            kp = true;
 #pragma unroll
-          for (int dy = -1; dy <= 1; dy++)
+            for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
-            for (int dx = -1; dx <= 1; dx++) {
-              if (dx == 0 && dy == 0) continue;
-              int qv = (int)lds8(sp + dy * FT_SCP + dx);
-              bool raw = false;
-              if (kPass == 2) {
-                const int qx = lx + dx, qy = ly + dy;
-                const int fy = qy < 4 ? 0 : (qy > 35 ? 2 : 1);
-                const int fx = qx < kFx ? 0 : (qx > kFx + 31 ? 2 : 1);
-                raw = s_flag[fy * (kFT + 2) + j + fx] != 0;
+              for (int dx = -1; dx <= 1; dx++) {
+                if (dx == 0 && dy == 0) continue;
+                int qv = (int)lds8(sp + dy * FT_SCP + dx);
+                bool raw = false;
+                if (kPass == 2) {
+                  const int qx = lx + dx, qy = ly + dy;
+                  const int fy = qy < 4 ? 0 : (qy > 35 ? 2 : 1);
+                  const int fx = qx < kFx ? 0 : (qx > kFx + 31 ? 2 : 1);
+                  raw = s_flag[fy * (kFT + 2) + j + fx] != 0;
+                }
+                if (!raw && qv < a.ini_th) qv = 0;
+                kp = kp && sc > qv;
               }
-              if (!raw && qv < a.ini_th) qv = 0;
-              kp = kp && sc > qv;
-            }
+          }
         }
         const uint32_t bal = __ballot_sync(0xffffffffu, kp);
         if (bal) {
@@ -335,7 +351,7 @@ __global__ void __launch_bounds__(32, 24) fast_tile_kernel(const FastArgs a) {
         }
       }
       if (tile_any) anymask |= 1 << j;
-      if (kPass == 1 && a.dbg_score) {  // parity introspection only: the score map S at minThFAST for the tile interior
+      if (kPass == 1 && kDbg) {  // parity introspection only: the score map S at minThFAST for the tile interior
         uint8_t* scp = a.dbg_score + (long long)f * L->slab_bytes + g.plane_off + (long long)kEdge * g.pitch + kPadX;
         for (int i = lane; i < 32 * 32; i += 32) {
           const int ly = (i >> 5) + 4, lx = (i & 31) + kFx;
