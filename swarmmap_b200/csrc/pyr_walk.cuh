@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(32, 24) pyr_walk_kernel(const PyrArgs a) {
   const bool pstore = mine && X + 3 >= -kEdge && X < w + kEdge;
   // blurred plane: columns [0, w) only; a last partial word is written byte by byte
   const int bcount = (mine && X >= 0) ? min(max(w - X, 0), 4) : 0;
+  const bool has_partial = __any_sync(0xffffffffu, bcount > 0 && bcount < 4);  // warp-uniform: only the last strip, if at all
   const long long roi0 = (long long)f * a.slab_bytes + a.dst.plane_off + (long long)kEdge * pitch + kPadX;
   // running pointers: my word in un-blurred row v and in blurred row v - 8 (the row the blur emits while v is made)
   uint8_t* pr = a.plain + roi0 + (long long)(y0 - 5) * pitch + X;
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(32, 24) pyr_walk_kernel(const PyrArgs a) {
 
   // Step j makes rows v .. v+3 and needs source rows lo .. lo+7 of level l-1: lanes 0-3 read the four row taps (they
   // are handed to the row loop by shuffle later), one lane issues the TMA tile.  Returns lo; tap = my row's tap.
+  uint32_t psg = 0, csg = 0, cphase = 0;  // producer stage, consumer stage and its mbarrier phase
   auto prefetch = [&](int j, int2& tap) -> int {
     int s0 = 1 << 30;
     tap = make_int2(0, 0);
@@ -151,11 +153,11 @@ __global__ void __launch_bounds__(32, 24) pyr_walk_kernel(const PyrArgs a) {
     }
     const int lo = __reduce_min_sync(0xffffffffu, s0);
     if (lane == 0) {
-      const int sg = j % kWalkStages;
-      const uint32_t bar = bar_u32 + 8u * sg;
+      const uint32_t bar = bar_u32 + 8u * psg;
       asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kWalkStageRows * kWalkRowBytes) : "memory");
-      tma_tile_3d(stage_u32 + sg * (kWalkStageRows * kWalkRowBytes), a.src_map, kPadX + xb, kEdge + lo, f, bar);
+      tma_tile_3d(stage_u32 + psg * (kWalkStageRows * kWalkRowBytes), a.src_map, kPadX + xb, kEdge + lo, f, bar);
     }
+    psg = psg == kWalkStages - 1 ? 0 : psg + 1;  // steps are prefetched in order: stage = step mod kWalkStages
     return lo;
   };
   int lo_cur = 0, lo_n1 = 0, lo_n2 = 0;
@@ -208,9 +210,19 @@ __global__ void __launch_bounds__(32, 24) pyr_walk_kernel(const PyrArgs a) {
     }
     if (!kFirst) {
       if (it + 2 < nit) lo_n2 = prefetch(it + 2, tap_n2);
-      const int sg = it % kWalkStages;
-      mbar_wait(&s_bar[sg], (uint32_t)(it / kWalkStages) & 1u);
-      row0_addr = lane_addr + (uint32_t)(sg * kWalkStageRows - lo_cur) * kWalkRowBytes;
+      {  // wait for this step's tile (a lost transaction must abort, not hang the GPU)
+        const uint32_t bar = bar_u32 + 8u * csg;
+        uint32_t done;
+        int spins = 0;
+        do {
+          asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                       : "=r"(done) : "r"(bar), "r"(cphase) : "memory");
+          if (!done && ++spins > (1 << 22)) __trap();
+        } while (!done);
+      }
+      row0_addr = lane_addr + (csg * kWalkStageRows - (uint32_t)lo_cur) * kWalkRowBytes;
+      if (csg == kWalkStages - 1) { csg = 0; cphase ^= 1u; }
+      else csg++;
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -293,9 +305,8 @@ __global__ void __launch_bounds__(32, 24) pyr_walk_kernel(const PyrArgs a) {
         o3 = __dp2a_lo(C23, k6, o3);
         const uint32_t bw = __byte_perm(__byte_perm(o0, o1, 0x0062), __byte_perm(o2, o3, 0x0062), 0x5410);
         if (gy < y1) {
-          if (bcount == 4) {
-            *reinterpret_cast<uint32_t*>(br) = bw;
-          } else if (bcount > 0) {
+          if (bcount == 4) *reinterpret_cast<uint32_t*>(br) = bw;
+          if (has_partial && bcount > 0 && bcount < 4) {  // the word that holds column w - 1 when w is not a multiple of 4
             br[0] = (uint8_t)bw;
             if (bcount > 1) br[1] = (uint8_t)(bw >> 8);
             if (bcount > 2) br[2] = (uint8_t)(bw >> 16);
