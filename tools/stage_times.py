@@ -19,7 +19,8 @@ sp = C.c_void_p(st.cuda_stream)
 ex.extract_batch_device(d_img.data_ptr(), B, 752, 480, 752, 752 * 480, d_kps.data_ptr(), d_desc.data_ptr(), cap, d_n.data_ptr(), sp)
 torch.cuda.synchronize()
 out = []
-for name, mask in (("pyr", _lib.STAGE_PYRAMID), ("fast", _lib.STAGE_NMS), ("octree", _lib.STAGE_OCTREE), ("describe", _lib.STAGE_DESCRIBE)):
+for name, mask in (("pyr", _lib.STAGE_PYRAMID), ("fast", _lib.STAGE_NMS), ("pyr+fast", _lib.STAGE_PYRAMID | _lib.STAGE_NMS),
+                   ("octree", _lib.STAGE_OCTREE), ("describe", _lib.STAGE_DESCRIBE), ("all", 15)):
     for _ in range(3):
         ex.run_stage(mask, B, sp)
     torch.cuda.synchronize()
