@@ -38,4 +38,23 @@ voc = ORBVocabulary(synth.make_vocabulary(10, 3, seed=2))
 r0, r1 = voc.transform_frame(rf[0], 2), voc.transform_frame(rf[1], 2)
 print("bow words", len(r0.word_ids), "nodes", len(r0.node_ids), "batch", len(voc.transform_batch(d[:2], n[:2], 2)))
 print("resident bow", m.SearchByBoW(rf[0], r0.feature_vector(), np.ones(rf[0].N, np.uint8), rf[1], r1.feature_vector())[0])
+# stereo front-end (two extractors)
+sl, sr = synth.make_stereo_pair(752, 480, 5)
+exl, exr = ORBextractor(800, 1.2, 8, 20, 7, max_batch=2), ORBextractor(800, 1.2, 8, 20, 7, max_batch=2)
+exl.extract_batch(np.stack([sl, sl]))
+exr.extract_batch(np.stack([sr, sr]))
+u, z = exl.stereo_match(exr, 47.9, 47.9 / 458.654, 2)
+print("stereo", int((u >= 0).sum()))
+# (the peer-memory place exchange is NOT run here: compute-sanitizer serialises kernel launches, and the merge kernels of
+# two ranks wait for each other -- tests/test_gpu_match.py::test_db_query_peers_equals_single_shard covers it; a world
+# of one rank still runs the kernel's push / flag / wait / merge path)
+one = [place.PlaceShard(db.cpu().numpy(), 8, 0)]
+one[0].enable_peers(nq_max=512, same_process=one)
+k1, v1 = one[0].query_peers(q, 2, 50)
+torch.cuda.synchronize()
+assert torch.equal(k1, keys)
+print("peers (world 1) ok")
+# batched matchers (one resolve CTA per job)
+res = m.SearchForInitializationBatch([(fs[0], fs[1], prev.copy()), (fs[1], fs[0], np.ascontiguousarray(np.stack([fs[1].x, fs[1].y], 1).astype(np.float32)))], 100)
+print("init batch", [int(r[0]) for r in res])
 print("ok", int(n.sum()))
