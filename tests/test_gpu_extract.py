@@ -107,6 +107,43 @@ def test_batch_matches_single(oracle, swm):
     _check_frame(gpu, cpu, imgs[5], 1)
 
 
+def test_bench_batch_size_invariances(oracle, swm):
+    """Size-independent properties at the bench's handle batch (64 frames per call, the long-row-block / four-tile-run
+    configuration of the kernels, which the small-batch tests above do not reach): a frame's result does not depend on
+    its slot in the batch, on its neighbours, or on the run; a single-frame handle (8-row blocks, one tile per warp)
+    gives the same bytes; and three sampled frames equal the oracle."""
+    from swarmmap_b200.orb import ORBextractor
+    base = synth.make_batch(16, 752, 480, 20220411)
+    rng = np.random.default_rng(5)
+    order = rng.integers(0, 16, 64)
+    imgs = base[order]
+    big = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=64)
+    k1, d1, n1 = big.extract_batch(imgs)
+    k2, d2, n2 = big.extract_batch(imgs[::-1].copy())  # same frames, reversed slots, second run
+    one = ORBextractor(1000, 1.2, 8, 20, 7, max_batch=1)
+    first_slot = {}
+    for s in range(64):
+        f = int(order[s])
+        r = 63 - s
+        assert n1[s] == n2[r]
+        assert k1[s, :n1[s]].tobytes() == k2[r, :n2[r]].tobytes() and d1[s, :n1[s]].tobytes() == d2[r, :n2[r]].tobytes()
+        if f in first_slot:  # the same frame in another slot of the same batch
+            t = first_slot[f]
+            assert n1[s] == n1[t] and k1[s, :n1[s]].tobytes() == k1[t, :n1[t]].tobytes() and d1[s, :n1[s]].tobytes() == d1[t, :n1[t]].tobytes()
+        else:
+            first_slot[f] = s
+    for f in (0, 7, 15):
+        s = first_slot.get(f)
+        if s is None:
+            continue
+        ks, ds = one(base[f])
+        assert len(ks) == n1[s] and ks.tobytes() == k1[s, :n1[s]].tobytes() and ds.tobytes() == d1[s, :n1[s]].tobytes()
+        okps, odesc = oracle.Extractor(1000, 1.2, 8, 20, 7)(base[f])
+        assert len(okps) == n1[s]
+        for fld in ("x", "y", "size", "response", "octave"):
+            np.testing.assert_array_equal(k1[s, :n1[s]][fld], okps[fld])
+
+
 @pytest.mark.parametrize("w,h", [(640, 480), (333, 257), (200, 150), (1001, 301)])
 def test_odd_sizes(oracle, swm, w, h):
     gpu, cpu = _extractors(oracle, 500)
