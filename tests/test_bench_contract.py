@@ -1,5 +1,5 @@
-"""The bench.py JSON contract, checked on the committed lines (profiles/r2u_bench.json from `python bench.py` on one
-B200, profiles/r2u_bench_reference.json from `python bench.py --impl reference`), and the parts of bench.py that run
+"""The bench.py JSON contract, checked on the committed lines (profiles/r2ae_bench.json from `python bench.py` on one
+B200, profiles/r2ae_bench_reference.json from `python bench.py --impl reference`), and the parts of bench.py that run
 without a GPU (argument parsing, the reference arm on a tiny sample)."""
 import json
 import os
@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DEV_LINE = "r2z_bench.json"
+DEV_LINE = "r2ae_bench.json"
 
 
 def _line(name):
@@ -66,7 +66,7 @@ def test_device_arm_line_has_every_contract_key():
 
 
 def test_reference_arm_line():
-    d = _line("r2u_bench_reference.json")
+    d = _line("r2ae_bench_reference.json")
     dev = _line(DEV_LINE)
     assert d["impl"] == "reference" and d["metric"] == dev["metric"] and d["unit"] == dev["unit"]
     assert d["config"]["workload"] == dev["config"]["workload"]
