@@ -121,7 +121,8 @@ __global__ void __launch_bounds__(256) octree_kernel(const FrameLayout* __restri
 // ------------------------------------------------------------------------------------------------
 // Orientation (un-blurred plane) + rBRIEF (blurred plane) + keypoint record, one warp per keypoint.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) describe_kernel(const FrameLayout* __restrict__ L, const uint8_t* __restrict__ plain,
+// 8 CTAs per SM (32 registers): the kernel waits on loads, more resident warps hide them (0.359 vs 0.366 ms at 40 registers)
+__global__ void __launch_bounds__(256, 8) describe_kernel(const FrameLayout* __restrict__ L, const uint8_t* __restrict__ plain,
                                                        const uint8_t* __restrict__ blur, const uint32_t* __restrict__ sel,
                                                        const int* __restrict__ sel_count, swm_keypoint* __restrict__ kps,
                                                        uint8_t* __restrict__ desc, int cap, int32_t* __restrict__ n_out) {
