@@ -919,7 +919,7 @@ def main():
     sampler.start()
     ms_total, n_kp = eb.time_device(args.steps, args.warmup)
     launches = eb.launches_per_step() * args.steps
-    eb.setup_e2e(8, 32)
+    eb.setup_e2e(8, 64)
     ms_e2e, kp_e2e = eb.time_e2e(args.steps, args.warmup)
     assert kp_e2e == n_kp * args.steps, (kp_e2e, n_kp, args.steps)  # the streamed path produced the same keypoints
     clocks = sampler.stop()

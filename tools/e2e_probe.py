@@ -5,8 +5,8 @@ import numpy as np, torch
 from swarmmap_b200 import synth
 from swarmmap_b200.orb import ORBextractor, KP_DTYPE
 W, H = 752, 480
-B = 512
-frames = synth.make_batch(B, W, H, 20220410)
+B = 2048
+frames = np.tile(synth.make_batch(256, W, H, 20220410), (B // 256, 1, 1))
 h_img = torch.from_numpy(frames).pin_memory()
 d = torch.empty_like(h_img, device="cuda")
 for _ in range(3): d.copy_(h_img, non_blocking=True)
@@ -15,7 +15,7 @@ for _ in range(10): d.copy_(h_img, non_blocking=True)
 torch.cuda.synchronize(); dt = time.perf_counter() - t
 print("raw pinned H2D GB/s", 10 * h_img.numel() / dt / 1e9)
 h_np = h_img.numpy()
-for nslot, eb in ((4, 32), (4, 64), (3, 64), (2, 128), (8, 32), (6, 16), (4, 128)):
+for nslot, eb in ((8, 32), (8, 64), (6, 64), (12, 32), (16, 32), (4, 128), (12, 64)):
     exs = [ORBextractor(1000, 1.2, 8, 20, 7, max_batch=eb) for _ in range(nslot)]
     cap = exs[0].max_keypoints()
     outs = []
