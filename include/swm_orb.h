@@ -452,7 +452,9 @@ int swm_db_query_sharded(swm_db* db, void* nccl_comm, int world, const uint8_t* 
  *     from the other processes by whatever transport the server has (MPI, torch.distributed, a socket), or an array of
  *     device addresses when the ranks share a process; the entry of `rank` itself is ignored;
  *   swm_db_query_peers: a collective -- every rank enqueues it with the same nq and k, the same number of times;
- *     results as swm_db_query_sharded.  Three enqueues become two (scan, fused merge + exchange + merge). */
+ *     results as swm_db_query_sharded.  Three enqueues become two (scan, fused merge + exchange + merge).  A rank that
+ *     never joins makes the others abort (device trap) after minutes of waiting; a rank that re-creates its window
+ *     (swm_db_peer_window again) must hand the new handle to every peer before the next query. */
 int swm_db_peer_window(swm_db* db, int world, int nq_max, void* ipc_handle64, void** window);
 int swm_db_peer_open(swm_db* db, int rank, const void* ipc_handles, void* const* windows);
 int swm_db_query_peers(swm_db* db, const uint8_t* d_q, int nq, int k, uint64_t* d_topk, int32_t* d_votes, int th_votes,

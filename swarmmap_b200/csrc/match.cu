@@ -1242,7 +1242,7 @@ __global__ void __launch_bounds__(128) db_merge_peers_kernel(const unsigned long
     const unsigned int* f = flags + ((size_t)par * world + threadIdx.x) * kPeerBlocks + blockIdx.x;
     long long spins = 0;
     while (ld_acquire_sys(f) != seq)
-      if (++spins > (1ll << 31)) __trap();  // a rank that never arrives must abort, not hang the GPU
+      if (++spins > (1ll << 28)) __trap();  // minutes: a rank that never arrives must abort, not hang the GPU for ever
   }
   __syncthreads();
   if (qi >= nq) return;

@@ -424,8 +424,11 @@ def test_db_query_peers_equals_single_shard(oracle, swm, world, k):
     shards driven from ONE process on one GPU, each on its own stream so that the kernels really wait for each other:
     every rank gets the keys of the single-shard scan, the votes sum to the single-shard histogram, and a second and
     third query reuse the windows (sequence parity)."""
+    import os
     import torch
     from swarmmap_b200 import place
+    if os.environ.get("CUDA_LAUNCH_BLOCKING") == "1":
+        pytest.skip("the ranks' kernels wait for each other: they cannot run with serialised launches")
     rng = np.random.default_rng(31 + world)
     per_kf = 8
     q, db = _db_case(rng, 500, 32000)
