@@ -20,9 +20,18 @@
  *   swm_match_window            ORBmatcher::SearchByProjection x4    src/ORBmatcher.cc:44-121,264-373,1223-1354,1356-1473
  *   swm_match_bow               ORBmatcher::SearchByBoW x2           src/ORBmatcher.cc:150-262,481-597
  *   swm_grid_build              Frame::AssignFeaturesToGrid/GetFeaturesInArea  src/Frame.cc:277-292,377-442
+ *   swm_orb_stereo_match        Frame::ComputeStereoMatches          src/Frame.cc:516-690
+ *   swm_frame_*                 Frame::UndistortKeyPoints / ComputeImageBounds / AssignFeaturesToGrid on the device
+ *                               src/Frame.cc:454-514,277-292
+ *   swm_match_triangulation, swm_window_best, swm_distinctive_descriptors
+ *                               SearchForTriangulation, the search loop of Fuse x2 / SearchBySim3,
+ *                               MapPoint::ComputeDistinctiveDescriptors    src/ORBmatcher.cc:599-1221, src/MapPoint.cc:361-391
+ *   swm_match_*_batch           the same Search* calls for many agents in one call (src/Tracking.cc:470-472,619-626,715-737)
+ *   swm_vocab_*, swm_bow_*      DBoW2 transform (Frame::ComputeBoW)  Thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1151-1283
  *   swm_db_*                    role of KeyFrameDatabase::DetectLoopCandidates + SearchByBoW(KF,KF) in
  *                               AgentMediator::CheckOverlapCandidates (src/AgentMediator.cc:140-202), recast as
- *                               brute-force Hamming top-k over a sharded descriptor database (BASELINE config 5)
+ *                               brute-force Hamming top-k over a sharded descriptor database (BASELINE config 5);
+ *                               across GPUs: swm_db_query_peers (peer-memory exchange) / swm_db_query_sharded (NCCL)
  */
 #ifndef SWM_ORB_H
 #define SWM_ORB_H
