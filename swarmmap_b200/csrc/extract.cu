@@ -148,6 +148,23 @@ __global__ void __launch_bounds__(256, 8) describe_kernel(const FrameLayout* __r
   const long long off = (long long)f * L->slab_bytes + g.plane_off + (long long)(y + kEdge) * g.pitch + kPadX + x;
   const int pitch = g.pitch;
 
+  // The 37x37 neighbourhood of the BLURRED plane (rBRIEF's samples) is requested first, as 4-byte cp.async copies
+  // straight into shared memory (LDGSTS: no registers held): it does not depend on the angle, so its latency overlaps
+  // the orientation's own loads instead of following them.
+  constexpr int kPR = 18, kPW = 11;  // patch radius (max rotated pattern offset is 18), words per patch row
+  uint32_t* patch = s_patch + (threadIdx.x >> 5) * ((2 * kPR + 1) * kPW);
+  const int ox = (x - kPR) & ~3;
+  {
+    const uint8_t* b0 = blur + (long long)f * L->slab_bytes + g.plane_off + (long long)(y - kPR + kEdge) * g.pitch + kPadX + ox;
+    const uint32_t p0 = smem_u32(patch);
+#pragma unroll
+    for (int it = 0; it < 13; it++) {
+      const int idx = lane + 32 * it;
+      const int r = idx / kPW, wd = idx - r * kPW;
+      if (idx < (2 * kPR + 1) * kPW)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(p0 + 4u * idx), "l"(b0 + (long long)r * g.pitch + 4 * wd) : "memory");
+    }
+  }
   // IC_Angle (Fast_gpu.cu:403-460): integer moments over the radius-15 disc, one lane per column
   // (row pointers advance by the pitch and the disc half-widths are compile-time offsets: the loop is 2 loads + 6
   // integer instructions per row pair, where index arithmetic per load used to be a third of this kernel)
@@ -184,24 +201,8 @@ __global__ void __launch_bounds__(256, 8) describe_kernel(const FrameLayout* __r
   const float factor_pi = (float)(3.1415926535897932384626433832795 / 180.f);
   const float rad = __fmul_rn(ang, factor_pi);
   const float ca = cosf(rad), sb = sinf(rad);
-  constexpr int kPR = 18, kPW = 11;  // patch radius (max rotated pattern offset is 18), words per patch row
-  uint32_t* patch = s_patch + (threadIdx.x >> 5) * ((2 * kPR + 1) * kPW);
-  const int ox = (x - kPR) & ~3;
-  {
-    const uint8_t* b0 = blur + (long long)f * L->slab_bytes + g.plane_off + (long long)(y - kPR + kEdge) * g.pitch + kPadX + ox;
-    uint32_t v[13];
-#pragma unroll
-    for (int it = 0; it < 13; it++) {
-      const int idx = lane + 32 * it;
-      const int r = idx / kPW, wd = idx - r * kPW;
-      v[it] = idx < (2 * kPR + 1) * kPW ? __ldg(reinterpret_cast<const uint32_t*>(b0 + (long long)r * pitch) + wd) : 0u;
-    }
-#pragma unroll
-    for (int it = 0; it < 13; it++) {
-      const int idx = lane + 32 * it;
-      if (idx < (2 * kPR + 1) * kPW) patch[idx] = v[it];
-    }
-  }
+  // the patch requested before the orientation loop has landed
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncwarp();
   const uint8_t* b = reinterpret_cast<const uint8_t*>(patch) + kPR * (kPW * 4) + (x - ox);
   int val = 0;
