@@ -1,4 +1,4 @@
-"""The bench.py JSON contract, checked on the committed lines (profiles/r2ai_bench.json from `python bench.py` on one
+"""The bench.py JSON contract, checked on the committed lines (profiles/r2am_bench.json from `python bench.py` on one
 B200, profiles/r2ae_bench_reference.json from `python bench.py --impl reference`), and the parts of bench.py that run
 without a GPU (argument parsing, the reference arm on a tiny sample)."""
 import json
@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DEV_LINE = "r2ai_bench.json"
+DEV_LINE = "r2am_bench.json"
 
 
 def _line(name):
